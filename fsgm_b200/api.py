@@ -1,0 +1,175 @@
+"""ctypes binding of libfsgm.so (include/fsgm.h) — the harness tests/ and bench.py drive the product through.
+
+The functions keep the reference's gateway names and argument order (calc_cost_sgm.cpp:539 etc.), with numpy
+host arrays in the reference's layout: row-major, x fastest, images uint8 [H][W], two-plane doubles [2][H][W].
+The *_dev methods take torch CUDA tensors (device memory plumbing only) and pass raw device pointers through.
+
+There is no fallback: importing this module without a built libfsgm.so raises, and every call raises
+FsgmError on a non-zero status.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libfsgm.so")
+
+FSGM_OK, FSGM_ERR_ARG, FSGM_ERR_DOMAIN, FSGM_ERR_CUDA, FSGM_ERR_NOMEM, FSGM_ERR_NCCL = 0, -1, -2, -3, -4, -5
+
+
+class FsgmError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"fsgm error {code}: {msg}")
+        self.code = code
+
+
+class EpiOpts(C.Structure):
+    _fields_ = [("paths", C.c_int), ("total_pass", C.c_int), ("subpixel", C.c_int),
+                ("adaptive_p2", C.c_int), ("vz_to_disp", C.c_int)]
+
+
+def load_library() -> C.CDLL:
+    if not os.path.exists(_LIB_PATH):
+        raise ImportError(f"{_LIB_PATH} is missing: build it with `python fsgm_b200/build.py` "
+                          "(there is no CPU fallback for the fSGM hot path)")
+    lib = C.CDLL(_LIB_PATH)
+    lib.fsgm_last_error.restype = C.c_char_p
+    lib.fsgm_launch_count.restype = C.c_uint64
+    lib.fsgm_scratch_bytes.restype = C.c_size_t
+    return lib
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        _lib = load_library()
+    return _lib
+
+
+def _hp(a: np.ndarray, dtype, shape=None):
+    """host pointer of a C-contiguous numpy array of the right dtype"""
+    if a is None:
+        return None
+    if a.dtype != dtype or not a.flags["C_CONTIGUOUS"]:
+        raise TypeError(f"expected C-contiguous {np.dtype(dtype)} array, got {a.dtype}")
+    if shape is not None and tuple(a.shape) != tuple(shape):
+        raise ValueError(f"expected shape {shape}, got {a.shape}")
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _dp(t):
+    """device pointer of a contiguous torch CUDA tensor"""
+    if t is None:
+        return None
+    if not t.is_cuda or not t.is_contiguous():
+        raise TypeError("expected a contiguous CUDA tensor")
+    return C.c_void_p(t.data_ptr())
+
+
+def epi_opts(paths=4, total_pass=2, subpixel=1, adaptive_p2=0, vz_to_disp=1) -> EpiOpts:
+    return EpiOpts(paths, total_pass, subpixel, adaptive_p2, vz_to_disp)
+
+
+class Context:
+    """One per GPU (fsgm_create / fsgm_destroy)."""
+
+    def __init__(self, device: int = 0):
+        self._l = lib()
+        self._h = C.c_void_p()
+        rc = self._l.fsgm_create(int(device), C.byref(self._h))
+        if rc != FSGM_OK:
+            raise FsgmError(rc, f"fsgm_create(device={device}) failed — an sm_100 GPU is required, there is no CPU path")
+        self.device = device
+
+    def close(self):
+        if self._h:
+            self._l.fsgm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc: int):
+        if rc != FSGM_OK:
+            raise FsgmError(rc, self._l.fsgm_last_error(self._h).decode())
+
+    def set_stream(self, cuda_stream_ptr: int | None):
+        self._ck(self._l.fsgm_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))
+
+    def use_torch_stream(self):
+        import torch
+        ptr = torch.cuda.current_stream(self.device).cuda_stream
+        # torch's default stream is the NULL handle, which fsgm_set_stream reads as "back to the context's own
+        # stream"; cudaStreamLegacy (0x1) names the same default stream explicitly.
+        self.set_stream(ptr if ptr else 1)
+
+    def synchronize(self):
+        self._ck(self._l.fsgm_synchronize(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._l.fsgm_launch_count(self._h))
+
+    @property
+    def scratch_bytes(self) -> int:
+        return int(self._l.fsgm_scratch_bytes(self._h))
+
+    # ------------------------------------------------------------------ gateway 1 (host arrays)
+    def calc_cost_sgm(self, I1, I2, dMax, vMax, pixelPosD0, normlizeDirection, offsetFromPosD0, P1, P2, opts=None):
+        """[bestD, minC, conf, bestD2] = calc_cost_sgm(...)  (calc_cost_sgm.cpp:17, :539-598)"""
+        H, W = I1.shape
+        bestD, minC = np.empty((H, W), np.uint32), np.empty((H, W), np.uint32)
+        conf, bestD2 = np.empty((H, W), np.uint8), np.empty((H, W), np.uint32)
+        self._ck(self._l.fsgm_calc_cost_sgm(
+            self._h, _hp(I1, np.uint8), _hp(I2, np.uint8, (H, W)), W, H, int(dMax), C.c_double(vMax),
+            _hp(pixelPosD0, np.float64, (2, H, W)), _hp(normlizeDirection, np.float64, (2, H, W)),
+            _hp(offsetFromPosD0, np.float64, (H, W)), int(P1), int(P2), C.byref(opts) if opts is not None else None,
+            _hp(bestD, np.uint32), _hp(minC, np.uint32), _hp(conf, np.uint8), _hp(bestD2, np.uint32)))
+        return bestD, minC, conf, bestD2
+
+    def calc_cost_sgm_batch(self, I1, I2, dMax, vMax, pixelPosD0, normlizeDirection, offsetFromPosD0, P1, P2, opts=None,
+                            out=None):
+        n, H, W = I1.shape
+        bestD, minC = out if out is not None else (np.empty((n, H, W), np.uint32), np.empty((n, H, W), np.uint32))
+        self._ck(self._l.fsgm_calc_cost_sgm_batch(
+            self._h, n, _hp(I1, np.uint8), _hp(I2, np.uint8, (n, H, W)), W, H, int(dMax), C.c_double(vMax),
+            _hp(pixelPosD0, np.float64, (n, 2, H, W)), _hp(normlizeDirection, np.float64, (n, 2, H, W)),
+            _hp(offsetFromPosD0, np.float64, (n, H, W)), int(P1), int(P2), C.byref(opts) if opts is not None else None,
+            _hp(bestD, np.uint32), _hp(minC, np.uint32)))
+        return bestD, minC
+
+    # ------------------------------------------------------------------ device-resident forms (torch tensors)
+    def calc_cost_sgm_dev(self, I1, I2, dMax, vMax, Pd0, dirn, O, P1, P2, bestD, minC, opts=None):
+        n, H, W = I1.shape
+        self._ck(self._l.fsgm_calc_cost_sgm_dev(
+            self._h, n, _dp(I1), _dp(I2), W, H, int(dMax), C.c_double(vMax), _dp(Pd0), _dp(dirn), _dp(O), int(P1), int(P2),
+            C.byref(opts) if opts is not None else None, _dp(bestD), _dp(minC)))
+
+    def census_dev(self, img, cen):
+        n, H, W = img.shape
+        self._ck(self._l.fsgm_census_dev(self._h, n, _dp(img), W, H, _dp(cen)))
+
+    def epi_cost_dev(self, cen1, cen2, dMax, vMax, Pd0, dirn, O, raw, Cvol):
+        n, H, W = cen1.shape
+        self._ck(self._l.fsgm_epi_cost_dev(self._h, n, _dp(cen1), _dp(cen2), W, H, int(dMax), C.c_double(vMax),
+                                           _dp(Pd0), _dp(dirn), _dp(O), _dp(raw), _dp(Cvol)))
+
+    def sweep_dev(self, Cvol, I1, P1, P2, direction, L, adaptive_thr=0):
+        n, H, W, D = Cvol.shape
+        self._ck(self._l.fsgm_sweep_dev(self._h, n, _dp(Cvol), _dp(I1), W, H, D, int(P1), int(P2), int(adaptive_thr),
+                                        int(direction), _dp(L)))
+
+    def epi_aggregate_dev(self, Cvol, I1, P1, P2, O, vMax, bestD, minC, Sp=None, opts=None):
+        n, H, W, D = Cvol.shape
+        self._ck(self._l.fsgm_epi_aggregate_dev(self._h, n, _dp(Cvol), _dp(I1), W, H, D, int(P1), int(P2),
+                                                C.byref(opts) if opts is not None else None, _dp(Sp), _dp(O),
+                                                C.c_double(vMax), _dp(bestD), _dp(minC)))

@@ -1,0 +1,294 @@
+// Path aggregation — replaces the sweeps of sgm() (reference calc_cost_sgm.cpp:114-257, step :33-66).
+//
+//   L_r(p,d) = C(p,d) + min( L_r(p-r,d), L_r(p-r,d-1)+P1, L_r(p-r,d+1)+P1, min_k L_r(p-r,k)+P2 ) - min_k L_r(p-r,k)
+//
+// with the reference's path-start rule: where p-r is outside the image, L = C and the stored minimum
+// is 0, not min(C) (:152-180).  The reference advances four ring-buffered paths per pixel in raster
+// order; the paths never read each other, so here every direction is an independent set of scanlines.
+//
+// Mapping: one warp per scanline, labels spread across lanes (2*NREG consecutive labels per lane, kept
+// as u16x2 in NREG registers).  Neighbour labels come from two warp shuffles, min_k from a packed min
+// tree + one REDUX.MIN.  The next pixels' cost rows are prefetched PF steps ahead into a register ring
+// so the serial chain never waits on HBM.  Horizontal directions walk a row (contiguous 256-B steps);
+// the six others walk "wrapped" columns: x advances by dx every row and the path restarts when it wraps,
+// which gives every warp exactly H steps and keeps neighbouring warps on neighbouring 256-B rows.
+//
+// HBM layout: C and every L_r are u8 [pair][y][x][d] (label-contiguous): 1 B read + 1 B written per voxel
+// and direction.  u16 exists only in registers.
+//
+// Arithmetic: the reference computes in unsigned char with mod-256 truncation (common.h:4-8).  When
+// P1,P2 >= 0, cmax+P1+P2 <= 255 and 2*cmax+P2 <= 255 no truncation can fire and the u16 lanes are exact
+// (WRAP=false); otherwise the WRAP=true instantiation reproduces every truncation explicitly.
+#include "fsgm_internal.h"
+
+namespace fsgm {
+
+constexpr int SWEEP_WARPS = 8;       // warps per CTA
+constexpr int PF = 4;                // prefetch depth (steps)
+constexpr uint32_t BIG2 = 0x3F003F00u;
+
+enum LoadMode { LM_FULL = 0, LM_VECPAD = 1, LM_BYTES = 2 };
+
+struct SweepParams {
+    const uint8_t* C;
+    const uint8_t* I1;
+    uint8_t* L[8];
+    int dir[8];
+    int line_start[9];    // prefix sum of scanline counts over the enabled directions
+    int n_dirs;
+    int W, H, D;
+    int P1, P2, adaptive_thr;
+};
+
+template <int NREG> struct Row;
+template <> struct Row<1> { using T = uint16_t; };
+template <> struct Row<2> { using T = uint32_t; };
+template <> struct Row<4> { using T = uint2; };
+template <> struct Row<8> { using T = uint4; };
+
+template <int NREG> struct Words { uint32_t w[(NREG + 1) / 2]; };
+
+template <int NREG, int MODE>
+__device__ __forceinline__ Words<NREG> load_row(const uint8_t* __restrict__ pix, int lane, int D)
+{
+    Words<NREG> r;
+    constexpr int NB = 2 * NREG;
+    if (MODE == LM_BYTES) {
+#pragma unroll
+        for (int k = 0; k < (NREG + 1) / 2; ++k) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int j = 0; j < 4 && k * 4 + j < NB; ++j) {
+                int d = lane * NB + k * 4 + j;
+                if (d < D) v |= (uint32_t)__ldg(pix + d) << (8 * j);
+            }
+            r.w[k] = v;
+        }
+    } else {
+        const bool alive = (MODE == LM_FULL) || (lane * NB < D);
+        if (NREG == 1) { r.w[0] = alive ? __ldg(reinterpret_cast<const uint16_t*>(pix) + lane) : 0; }
+        else if (NREG == 2) { r.w[0] = alive ? __ldg(reinterpret_cast<const uint32_t*>(pix) + lane) : 0; }
+        else if (NREG == 4) {
+            uint2 v = alive ? __ldg(reinterpret_cast<const uint2*>(pix) + lane) : make_uint2(0, 0);
+            r.w[0] = v.x; r.w[1] = v.y;
+        } else {
+            uint4 v = alive ? __ldg(reinterpret_cast<const uint4*>(pix) + lane) : make_uint4(0, 0, 0, 0);
+            r.w[0] = v.x; r.w[1] = v.y; r.w[2] = v.z; r.w[3] = v.w;
+        }
+    }
+    return r;
+}
+
+template <int NREG, int MODE>
+__device__ __forceinline__ void store_row(uint8_t* __restrict__ pix, int lane, int D, const uint32_t (&L)[NREG])
+{
+    constexpr int NB = 2 * NREG;
+    uint32_t w[(NREG + 1) / 2];
+#pragma unroll
+    for (int k = 0; k < (NREG + 1) / 2; ++k)
+        w[k] = (2 * k + 1 < NREG) ? __byte_perm(L[2 * k], L[2 * k + 1], 0x6420) : __byte_perm(L[2 * k], 0, 0x6420);
+    if (MODE == LM_BYTES) {
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+            int d = lane * NB + j;
+            if (d < D) pix[d] = (uint8_t)(w[j >> 2] >> (8 * (j & 3)));
+        }
+    } else {
+        const bool alive = (MODE == LM_FULL) || (lane * NB < D);
+        if (!alive) return;
+        if (NREG == 1) reinterpret_cast<uint16_t*>(pix)[lane] = (uint16_t)w[0];
+        else if (NREG == 2) reinterpret_cast<uint32_t*>(pix)[lane] = w[0];
+        else if (NREG == 4) reinterpret_cast<uint2*>(pix)[lane] = make_uint2(w[0], w[1]);
+        else reinterpret_cast<uint4*>(pix)[lane] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+template <int NREG, int MODE, bool WRAP, bool ADAPT>
+__global__ void __launch_bounds__(SWEEP_WARPS * 32)
+sweep_kernel(const SweepParams prm)
+{
+    const int lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * SWEEP_WARPS + (threadIdx.x >> 5);
+    if (gw >= prm.line_start[prm.n_dirs]) return;
+    int k = 0;
+    while (gw >= prm.line_start[k + 1]) ++k;
+    const int line = gw - prm.line_start[k];
+    const int r = prm.dir[k];
+    const int dx = dir_dx(r), dy = dir_dy(r);
+    const int W = prm.W, H = prm.H, D = prm.D;
+    const size_t N = (size_t)W * H;
+    const uint8_t* __restrict__ Cb = prm.C + blockIdx.y * N * D;
+    uint8_t* __restrict__ Lb = prm.L[k] + blockIdx.y * N * D;
+    const uint8_t* __restrict__ Ib = ADAPT ? prm.I1 + blockIdx.y * N : nullptr;
+    constexpr int NB = 2 * NREG;
+
+    // scanline geometry
+    int x, y, len;
+    if (dy == 0) { y = line; x = dx > 0 ? 0 : W - 1; len = W; }
+    else         { x = line; y = dy > 0 ? 0 : H - 1; len = H; }
+    int xf = x, yf = y;                       // prefetch cursor
+
+    // per-lane masks for labels >= D and for the warp's outer neighbours
+    uint32_t cdead[NREG];
+#pragma unroll
+    for (int i = 0; i < NREG; ++i) {
+        int d0 = lane * NB + 2 * i;
+        cdead[i] = (MODE == LM_FULL) ? 0u : ((d0 >= D ? 0xFFFFu : 0u) | (d0 + 1 >= D ? 0xFFFF0000u : 0u));
+    }
+    const uint32_t qdead_first = (lane == 0) ? 0x0000FFFFu : 0u;                 // label -1
+    const uint32_t qdead_last = (lane == 31) ? 0xFFFF0000u : 0u;                 // label 64*NREG
+
+    const uint32_t P1P1 = WRAP ? ((prm.P1 & 0xFF) * 0x10001u) : (uint32_t)prm.P1 * 0x10001u;
+
+    Words<NREG> ring[PF];
+#pragma unroll
+    for (int j = 0; j < PF; ++j) {
+        if (j < len) ring[j] = load_row<NREG, MODE>(Cb + ((size_t)yf * W + xf) * D, lane, D);
+        if (dy == 0) xf += dx;
+        else { yf += dy; xf += dx; xf = xf < 0 ? W - 1 : (xf >= W ? 0 : xf); }
+    }
+
+    uint32_t Lr[NREG];
+    uint32_t M = 0;
+    int prev_pix = 0;
+
+    for (int t0 = 0; t0 < len; t0 += PF) {
+#pragma unroll
+        for (int j = 0; j < PF; ++j) {
+            const int t = t0 + j;
+            if (t >= len) break;
+            const Words<NREG> cw = ring[j];
+            if (t + PF < len) ring[j] = load_row<NREG, MODE>(Cb + ((size_t)yf * W + xf) * D, lane, D);
+            if (dy == 0) xf += dx;
+            else { yf += dy; xf += dx; xf = xf < 0 ? W - 1 : (xf >= W ? 0 : xf); }
+
+            // unpack the cost row to u16x2
+            uint32_t c[NREG];
+#pragma unroll
+            for (int i = 0; i < NREG; ++i) {
+                c[i] = __byte_perm(cw.w[i >> 1], 0, (i & 1) ? 0x4342 : 0x4140);
+                if (MODE != LM_FULL && !WRAP) c[i] |= cdead[i] & BIG2;
+            }
+            const int pix = y * W + x;
+            // a path (re)starts at the first step and, for the wrapped columns, whenever x just wrapped
+            const bool start = (t == 0) || (dy != 0 && dx != 0 && x == (dx > 0 ? 0 : W - 1));
+            if (start) {
+#pragma unroll
+                for (int i = 0; i < NREG; ++i) Lr[i] = c[i];
+                M = 0;
+            } else {
+                int P2 = prm.P2;
+                if (ADAPT) {
+                    int a = Ib[pix], b = Ib[prev_pix];
+                    if (abs(a - b) > prm.adaptive_thr) P2 = P2 / 8;
+                }
+                uint32_t q[NREG + 1];
+                uint32_t up = __shfl_up_sync(0xffffffffu, Lr[NREG - 1], 1);
+                uint32_t dn = __shfl_down_sync(0xffffffffu, Lr[0], 1);
+                q[0] = __byte_perm(up, Lr[0], 0x5432);
+#pragma unroll
+                for (int i = 1; i < NREG; ++i) q[i] = __byte_perm(Lr[i - 1], Lr[i], 0x5432);
+                q[NREG] = __byte_perm(Lr[NREG - 1], dn, 0x5432);
+                uint32_t newL[NREG];
+                if (!WRAP) {
+                    q[0] |= qdead_first & BIG2;
+                    q[NREG] |= qdead_last & BIG2;
+                    const uint32_t MM = M * 0x10001u;
+                    const uint32_t far2 = MM + (uint32_t)P2 * 0x10001u;
+#pragma unroll
+                    for (int i = 0; i < NREG; ++i) {
+                        uint32_t nb = __vminu2(q[i], q[i + 1]);
+                        uint32_t b = __viaddmin_u16x2(nb, P1P1, Lr[i]);        // min(nb + P1, L(p-r,d))
+                        b = __vminu2(b, far2);
+                        newL[i] = c[i] + b - MM;
+                    }
+                } else {
+                    // explicit mod-256 emulation of every unsigned-char store / std::min<PathCost> in :40-61
+                    const uint32_t K = 0x00FF00FFu;
+                    const uint32_t MM = M * 0x10001u;
+                    const uint32_t far2 = (MM + ((uint32_t)(P2 & 0xFF)) * 0x10001u) & K;
+                    uint32_t qm[NREG + 1];
+#pragma unroll
+                    for (int i = 0; i <= NREG; ++i) {
+                        // dead neighbour (label < 0 or >= D): 0xFF is neutral for an unsigned-char min
+                        uint32_t dead = 0;
+                        int dl = lane * NB + 2 * i - 1;       // label held in the low half of q[i]
+                        if (dl < 0 || dl >= D) dead |= 0x000000FFu;
+                        if (dl + 1 >= D) dead |= 0x00FF0000u;
+                        qm[i] = ((q[i] + P1P1) & K) | dead;
+                    }
+#pragma unroll
+                    for (int i = 0; i < NREG; ++i) {
+                        uint32_t b = __vminu2(__vminu2(qm[i], qm[i + 1]), __vminu2(Lr[i], far2));
+                        newL[i] = (c[i] + b + (0x01000100u - MM)) & K;
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < NREG; ++i) Lr[i] = newL[i];
+                // new minimum over the live labels
+                uint32_t m = WRAP ? (Lr[0] | (cdead[0] & 0x00FF00FFu)) : Lr[0];
+#pragma unroll
+                for (int i = 1; i < NREG; ++i) m = __vminu2(m, WRAP ? (Lr[i] | (cdead[i] & 0x00FF00FFu)) : Lr[i]);
+                m = min(m & 0xFFFFu, m >> 16);
+                M = __reduce_min_sync(0xffffffffu, m);
+            }
+            store_row<NREG, MODE>(Lb + (size_t)pix * D, lane, D, Lr);
+            prev_pix = pix;
+            if (dy == 0) x += dx;
+            else { y += dy; x += dx; x = x < 0 ? W - 1 : (x >= W ? 0 : x); }
+        }
+    }
+}
+
+template <int NREG, int MODE>
+static void sweep_dispatch2(const SweepParams& p, bool wrap, bool adapt, dim3 grid, cudaStream_t s)
+{
+    if (!wrap && !adapt) sweep_kernel<NREG, MODE, false, false><<<grid, SWEEP_WARPS * 32, 0, s>>>(p);
+    else if (!wrap && adapt) sweep_kernel<NREG, MODE, false, true><<<grid, SWEEP_WARPS * 32, 0, s>>>(p);
+    else if (wrap && !adapt) sweep_kernel<NREG, MODE, true, false><<<grid, SWEEP_WARPS * 32, 0, s>>>(p);
+    else sweep_kernel<NREG, MODE, true, true><<<grid, SWEEP_WARPS * 32, 0, s>>>(p);
+}
+
+template <int NREG>
+static void sweep_dispatch(const SweepParams& p, int mode, bool wrap, bool adapt, dim3 grid, cudaStream_t s)
+{
+    if (mode == LM_FULL) sweep_dispatch2<NREG, LM_FULL>(p, wrap, adapt, grid, s);
+    else if (mode == LM_VECPAD) sweep_dispatch2<NREG, LM_VECPAD>(p, wrap, adapt, grid, s);
+    else sweep_dispatch2<NREG, LM_BYTES>(p, wrap, adapt, grid, s);
+}
+
+bool sweep_needs_wrap(int P1, int P2, int cmax)
+{
+    return !(P1 >= 0 && P2 >= 0 && cmax + P1 + P2 <= 255 && 2 * cmax + P2 <= 255);
+}
+
+int launch_sweeps(fsgm_ctx* c, int n, const uint8_t* C, const uint8_t* I1, int W, int H, int D,
+                  int P1, int P2, int adaptive_thr, int cmax, const int* dirs, int n_dirs, uint8_t* const* Lvols)
+{
+    if (D < 1 || D > 512) return fail(c, FSGM_ERR_DOMAIN, "label count must be in 1..512");
+    if (n_dirs < 1 || n_dirs > 8) return fail(c, FSGM_ERR_ARG, "n_dirs");
+    SweepParams p{};
+    p.C = C; p.I1 = I1; p.n_dirs = n_dirs; p.W = W; p.H = H; p.D = D; p.P1 = P1; p.P2 = P2; p.adaptive_thr = adaptive_thr;
+    p.line_start[0] = 0;
+    for (int k = 0; k < n_dirs; ++k) {
+        p.dir[k] = dirs[k];
+        p.L[k] = Lvols[k];
+        p.line_start[k + 1] = p.line_start[k] + (dir_dy(dirs[k]) == 0 ? H : W);
+    }
+    const int nreg = D <= 64 ? 1 : D <= 128 ? 2 : D <= 256 ? 4 : 8;
+    const int nb = 2 * nreg;
+    const int mode = (D == 32 * nb) ? LM_FULL : (D % nb == 0 ? LM_VECPAD : LM_BYTES);
+    const bool wrap = sweep_needs_wrap(P1, P2, cmax);
+    const bool adapt = adaptive_thr > 0;
+    dim3 grid((p.line_start[n_dirs] + SWEEP_WARPS - 1) / SWEEP_WARPS, n);
+    switch (nreg) {
+        case 1: sweep_dispatch<1>(p, mode, wrap, adapt, grid, c->stream); break;
+        case 2: sweep_dispatch<2>(p, mode, wrap, adapt, grid, c->stream); break;
+        case 4: sweep_dispatch<4>(p, mode, wrap, adapt, grid, c->stream); break;
+        default: sweep_dispatch<8>(p, mode, wrap, adapt, grid, c->stream); break;
+    }
+    FSGM_LAUNCHED(c);
+    return FSGM_OK;
+}
+
+}  // namespace fsgm

@@ -1,0 +1,300 @@
+// C-ABI layer (include/fsgm.h): context, scratch arena, the gateway-shaped entry points and the
+// stage entry points.  Host code is C++; everything that touches pixels is a kernel in the sibling
+// .cu files.  There is no CPU fallback anywhere in this library.
+#include "fsgm_internal.h"
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+namespace fsgm {
+
+int fail(fsgm_ctx* c, int code, const char* what, const char* detail)
+{
+    if (c) {
+        c->err = what ? what : "";
+        if (detail) { c->err += ": "; c->err += detail; }
+    }
+    return code;
+}
+
+int arena_reserve(fsgm_ctx* c, size_t total)
+{
+    total = align256(total) + 4096;
+    if (c->arena_top != 0) return fail(c, FSGM_ERR_ARG, "arena_reserve inside an active scope");
+    if (total <= c->arena_bytes) return FSGM_OK;
+    FSGM_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->arena) { cudaFree(c->arena); c->arena = nullptr; c->arena_bytes = 0; }
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&c->arena), total);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(c, FSGM_ERR_NOMEM, "cudaMalloc(scratch arena)", cudaGetErrorString(e)); }
+    c->arena_bytes = total;
+    return FSGM_OK;
+}
+
+int arena_alloc(fsgm_ctx* c, size_t bytes, void** out)
+{
+    size_t need = align256(bytes);
+    if (c->arena_top + need > c->arena_bytes) return fail(c, FSGM_ERR_NOMEM, "scratch arena exhausted (reserve too small)");
+    *out = c->arena + c->arena_top;
+    c->arena_top += need;
+    return FSGM_OK;
+}
+
+static int check_dims(fsgm_ctx* c, int n, int W, int H, int D)
+{
+    if (!c) return FSGM_ERR_ARG;
+    if (n < 1 || W < 1 || H < 1) return fail(c, FSGM_ERR_ARG, "n_pairs, width and height must be positive");
+    if (D < 1 || D > 512) return fail(c, FSGM_ERR_DOMAIN, "dMax must be in 1..512");
+    if ((size_t)W * H > (size_t)1 << 30) return fail(c, FSGM_ERR_DOMAIN, "image too large");
+    return FSGM_OK;
+}
+
+static int enabled_dirs(const fsgm_epi_opts& o, int* dirs)
+{
+    int k = 0;
+    for (int r = 0; r < 8; ++r)
+        if (dir_enabled(r, o.total_pass, o.paths == 8)) dirs[k++] = r;
+    return k;
+}
+
+static int check_opts(fsgm_ctx* c, const fsgm_epi_opts* in, fsgm_epi_opts* o)
+{
+    if (in) *o = *in; else fsgm_epi_opts_default(o);
+    if (o->paths != 4 && o->paths != 8) return fail(c, FSGM_ERR_ARG, "opts.paths must be 4 or 8");
+    if (o->total_pass < 1 || o->total_pass > 2) return fail(c, FSGM_ERR_DOMAIN, "opts.total_pass must be 1 or 2");
+    return FSGM_OK;
+}
+
+// scratch needed by the epipolar pipeline for `n` pairs
+static size_t epi_scratch_bytes(int n, int W, int H, int D, int n_dirs, bool want_raw)
+{
+    const size_t N = (size_t)W * H, V = N * D;
+    size_t b = 0;
+    b += 2 * align256(n * N * 4);             // census x2
+    b += align256(D * 8);                     // vz table
+    if (want_raw) b += align256(n * V);       // raw cost
+    b += align256(n * V);                     // C
+    b += (size_t)n_dirs * align256(n * V);    // L_r
+    return b + 4096;
+}
+
+// The whole hot path on device-resident inputs (asynchronous on c->stream).
+static int epi_pipeline_dev(fsgm_ctx* c, int n, const uint8_t* I1, const uint8_t* I2, int W, int H, int D, double vMax,
+                            const double* Pd0, const double* dirn, const double* O, int P1, int P2,
+                            const fsgm_epi_opts& o, uint32_t* bestD, uint32_t* minC)
+{
+    const size_t N = (size_t)W * H, V = N * D;
+    int dirs[8];
+    const int nd = enabled_dirs(o, dirs);
+    uint32_t *cen1, *cen2; uint8_t *raw, *C, *L[8];
+    FSGM_TRY(arena_get(c, n * N, &cen1));
+    FSGM_TRY(arena_get(c, n * N, &cen2));
+    FSGM_TRY(arena_get(c, n * V, &raw));
+    FSGM_TRY(arena_get(c, n * V, &C));
+    for (int k = 0; k < nd; ++k) FSGM_TRY(arena_get(c, n * V, &L[k]));
+    FSGM_TRY(launch_census(c, n, I1, W, H, cen1));
+    FSGM_TRY(launch_census(c, n, I2, W, H, cen2));
+    FSGM_TRY(launch_epi_cost(c, n, cen1, cen2, W, H, D, vMax, Pd0, dirn, O, raw, C));
+    FSGM_TRY(launch_sweeps(c, n, C, I1, W, H, D, P1, P2, o.adaptive_p2 ? 25 : 0, /*cmax=*/24, dirs, nd, L));
+    FSGM_TRY(launch_epi_wta(c, n, L, nd, W, H, D, o.subpixel, o.vz_to_disp, O, vMax, nullptr, bestD, minC));
+    return FSGM_OK;
+}
+
+}  // namespace fsgm
+
+using namespace fsgm;
+
+extern "C" {
+
+int fsgm_abi_version(void) { return 1; }
+
+void fsgm_epi_opts_default(fsgm_epi_opts* o)
+{
+    if (!o) return;
+    o->paths = 4; o->total_pass = 2; o->subpixel = 1; o->adaptive_p2 = 0; o->vz_to_disp = 1;
+}
+
+int fsgm_create(int device, fsgm_ctx** out)
+{
+    if (!out) return FSGM_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) { cudaGetLastError(); return FSGM_ERR_CUDA; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return FSGM_ERR_CUDA;
+    if (prop.major != 10) return FSGM_ERR_CUDA;          // kernels are built for sm_100a only; no fallback
+    if (cudaSetDevice(device) != cudaSuccess) return FSGM_ERR_CUDA;
+    fsgm_ctx* c = new (std::nothrow) fsgm_ctx();
+    if (!c) return FSGM_ERR_NOMEM;
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return FSGM_ERR_CUDA; }
+    c->stream = c->own_stream;
+    *out = c;
+    return FSGM_OK;
+}
+
+void fsgm_destroy(fsgm_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->arena) cudaFree(c->arena);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+int fsgm_set_stream(fsgm_ctx* c, void* s)
+{
+    if (!c) return FSGM_ERR_ARG;
+    FSGM_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->stream = s ? static_cast<cudaStream_t>(s) : c->own_stream;
+    return FSGM_OK;
+}
+
+int fsgm_synchronize(fsgm_ctx* c)
+{
+    if (!c) return FSGM_ERR_ARG;
+    FSGM_CUDA(c, cudaStreamSynchronize(c->stream));
+    return FSGM_OK;
+}
+
+const char* fsgm_last_error(const fsgm_ctx* c) { return c ? c->err.c_str() : "null context"; }
+uint64_t fsgm_launch_count(const fsgm_ctx* c) { return c ? c->launches : 0; }
+size_t fsgm_scratch_bytes(const fsgm_ctx* c) { return c ? c->arena_bytes : 0; }
+
+// ---------------------------------------------------------------------------------------------
+// stage entry points
+// ---------------------------------------------------------------------------------------------
+int fsgm_census_dev(fsgm_ctx* c, int n_images, const uint8_t* d_img, int W, int H, uint32_t* d_census)
+{
+    FSGM_TRY(check_dims(c, n_images, W, H, 1));
+    if (!d_img || !d_census) return fail(c, FSGM_ERR_ARG, "null pointer");
+    FSGM_CUDA(c, cudaSetDevice(c->device));
+    return launch_census(c, n_images, d_img, W, H, d_census);
+}
+
+int fsgm_epi_cost_dev(fsgm_ctx* c, int n, const uint32_t* d_cen1, const uint32_t* d_cen2, int W, int H, int D, double vMax,
+                      const double* d_Pd0, const double* d_dir, const double* d_O, uint8_t* d_raw, uint8_t* d_C)
+{
+    FSGM_TRY(check_dims(c, n, W, H, D));
+    if (!d_cen1 || !d_cen2 || !d_Pd0 || !d_dir || !d_O || !d_C) return fail(c, FSGM_ERR_ARG, "null pointer");
+    FSGM_CUDA(c, cudaSetDevice(c->device));
+    const size_t V = (size_t)W * H * D;
+    FSGM_TRY(arena_reserve(c, align256(D * 8) + (d_raw ? 0 : align256(n * V))));
+    ArenaScope scope(c);
+    uint8_t* raw = d_raw;
+    if (!raw) FSGM_TRY(arena_get(c, n * V, &raw));
+    return launch_epi_cost(c, n, d_cen1, d_cen2, W, H, D, vMax, d_Pd0, d_dir, d_O, raw, d_C);
+}
+
+int fsgm_sweep_dev(fsgm_ctx* c, int n, const uint8_t* d_C, const uint8_t* d_I1, int W, int H, int D,
+                   int P1, int P2, int adaptive_thr, int direction, uint8_t* d_L)
+{
+    FSGM_TRY(check_dims(c, n, W, H, D));
+    if (!d_C || !d_L || (adaptive_thr > 0 && !d_I1)) return fail(c, FSGM_ERR_ARG, "null pointer");
+    if (direction < 0 || direction > 7) return fail(c, FSGM_ERR_ARG, "direction must be 0..7");
+    FSGM_CUDA(c, cudaSetDevice(c->device));
+    uint8_t* L[1] = { d_L };
+    // stage-level callers may pass any u8 volume: assume nothing about its range (cmax = 255)
+    return launch_sweeps(c, n, d_C, d_I1, W, H, D, P1, P2, adaptive_thr, 255, &direction, 1, L);
+}
+
+int fsgm_epi_aggregate_dev(fsgm_ctx* c, int n, const uint8_t* d_C, const uint8_t* d_I1, int W, int H, int D,
+                           int P1, int P2, const fsgm_epi_opts* opts, uint16_t* d_Sp,
+                           const double* d_O, double vMax, uint32_t* d_bestD, uint32_t* d_minC)
+{
+    FSGM_TRY(check_dims(c, n, W, H, D));
+    fsgm_epi_opts o;
+    FSGM_TRY(check_opts(c, opts, &o));
+    if (!d_C || !d_bestD || !d_minC || (o.vz_to_disp && !d_O) || (o.adaptive_p2 && !d_I1)) return fail(c, FSGM_ERR_ARG, "null pointer");
+    FSGM_CUDA(c, cudaSetDevice(c->device));
+    int dirs[8];
+    const int nd = enabled_dirs(o, dirs);
+    const size_t V = (size_t)W * H * D;
+    FSGM_TRY(arena_reserve(c, (size_t)nd * align256(n * V)));
+    ArenaScope scope(c);
+    uint8_t* L[8];
+    for (int k = 0; k < nd; ++k) FSGM_TRY(arena_get(c, n * V, &L[k]));
+    FSGM_TRY(launch_sweeps(c, n, d_C, d_I1, W, H, D, P1, P2, o.adaptive_p2 ? 25 : 0, 255, dirs, nd, L));
+    return launch_epi_wta(c, n, L, nd, W, H, D, o.subpixel, o.vz_to_disp, d_O, vMax, d_Sp, d_bestD, d_minC);
+}
+
+// ---------------------------------------------------------------------------------------------
+// gateway 1: calc_cost_sgm
+// ---------------------------------------------------------------------------------------------
+int fsgm_calc_cost_sgm_dev(fsgm_ctx* c, int n, const uint8_t* d_I1, const uint8_t* d_I2, int W, int H, int D, double vMax,
+                           const double* d_Pd0, const double* d_dir, const double* d_O, int P1, int P2,
+                           const fsgm_epi_opts* opts, uint32_t* d_bestD, uint32_t* d_minC)
+{
+    FSGM_TRY(check_dims(c, n, W, H, D));
+    fsgm_epi_opts o;
+    FSGM_TRY(check_opts(c, opts, &o));
+    if (!d_I1 || !d_I2 || !d_Pd0 || !d_dir || !d_O || !d_bestD || !d_minC) return fail(c, FSGM_ERR_ARG, "null pointer");
+    FSGM_CUDA(c, cudaSetDevice(c->device));
+    int dirs[8];
+    const int nd = enabled_dirs(o, dirs);
+    // process the batch in chunks that keep the scratch arena under ~1/3 of the device memory
+    size_t free_b = 0, total_b = 0;
+    FSGM_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
+    const size_t budget = std::max(c->arena_bytes, (free_b + c->arena_bytes) / 3);
+    const size_t per_pair = epi_scratch_bytes(1, W, H, D, nd, true);
+    int chunk = (int)std::min<size_t>(n, std::max<size_t>(1, budget / per_pair));
+    FSGM_TRY(arena_reserve(c, epi_scratch_bytes(chunk, W, H, D, nd, true)));
+    const size_t N = (size_t)W * H;
+    for (int i0 = 0; i0 < n; i0 += chunk) {
+        const int m = std::min(chunk, n - i0);
+        ArenaScope scope(c);
+        FSGM_TRY(epi_pipeline_dev(c, m, d_I1 + i0 * N, d_I2 + i0 * N, W, H, D, vMax, d_Pd0 + i0 * 2 * N, d_dir + i0 * 2 * N,
+                                  d_O + i0 * N, P1, P2, o, d_bestD + i0 * N, d_minC + i0 * N));
+    }
+    return FSGM_OK;
+}
+
+int fsgm_calc_cost_sgm_batch(fsgm_ctx* c, int n, const uint8_t* I1, const uint8_t* I2, int W, int H, int D, double vMax,
+                             const double* Pd0, const double* dirn, const double* O, int P1, int P2,
+                             const fsgm_epi_opts* opts, uint32_t* bestD, uint32_t* minC)
+{
+    FSGM_TRY(check_dims(c, n, W, H, D));
+    if (!I1 || !I2 || !Pd0 || !dirn || !O || !bestD || !minC) return fail(c, FSGM_ERR_ARG, "null pointer");
+    FSGM_CUDA(c, cudaSetDevice(c->device));
+    const size_t N = (size_t)W * H;
+    // device staging for inputs and outputs (separate from the arena so the pipeline can size its own scratch)
+    uint8_t *dI = nullptr; double* dG = nullptr; uint32_t* dOut = nullptr;
+    auto cleanup = [&]() { cudaFree(dI); cudaFree(dG); cudaFree(dOut); };
+    if (cudaMalloc(&dI, 2 * n * N) != cudaSuccess || cudaMalloc(&dG, 5 * n * N * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&dOut, 2 * n * N * sizeof(uint32_t)) != cudaSuccess) {
+        cudaGetLastError(); cleanup();
+        return fail(c, FSGM_ERR_NOMEM, "cudaMalloc(host-gateway staging)");
+    }
+    uint8_t *dI1 = dI, *dI2 = dI + n * N;
+    double *dPd0 = dG, *dDir = dG + 2 * n * N, *dO = dG + 4 * n * N;
+    uint32_t *dBest = dOut, *dMin = dOut + n * N;
+    int rc = FSGM_OK;
+    cudaStream_t s = c->stream;
+    auto H2D = [&](void* d, const void* h, size_t b) { return cudaMemcpyAsync(d, h, b, cudaMemcpyHostToDevice, s); };
+    if (H2D(dI1, I1, n * N) || H2D(dI2, I2, n * N) || H2D(dPd0, Pd0, 2 * n * N * 8) || H2D(dDir, dirn, 2 * n * N * 8) ||
+        H2D(dO, O, n * N * 8))
+        rc = fail(c, FSGM_ERR_CUDA, "H2D copy", cudaGetErrorString(cudaGetLastError()));
+    if (rc == FSGM_OK) rc = fsgm_calc_cost_sgm_dev(c, n, dI1, dI2, W, H, D, vMax, dPd0, dDir, dO, P1, P2, opts, dBest, dMin);
+    if (rc == FSGM_OK) {
+        if (cudaMemcpyAsync(bestD, dBest, n * N * 4, cudaMemcpyDeviceToHost, s) ||
+            cudaMemcpyAsync(minC, dMin, n * N * 4, cudaMemcpyDeviceToHost, s) || cudaStreamSynchronize(s))
+            rc = fail(c, FSGM_ERR_CUDA, "D2H copy", cudaGetErrorString(cudaGetLastError()));
+    } else cudaStreamSynchronize(s);
+    cleanup();
+    return rc;
+}
+
+int fsgm_calc_cost_sgm(fsgm_ctx* c, const uint8_t* I1, const uint8_t* I2, int W, int H, int D, double vMax,
+                       const double* Pd0, const double* dirn, const double* O, int P1, int P2,
+                       const fsgm_epi_opts* opts, uint32_t* bestD, uint32_t* minC, uint8_t* conf, uint32_t* bestD2)
+{
+    int rc = fsgm_calc_cost_sgm_batch(c, 1, I1, I2, W, H, D, vMax, Pd0, dirn, O, P1, P2, opts, bestD, minC);
+    if (rc != FSGM_OK) return rc;
+    // outputs 3 and 4 of the gateway are allocated but never written by the reference (:571-572, :589-590)
+    if (conf) std::memset(conf, 0, (size_t)W * H);
+    if (bestD2) std::memset(bestD2, 0, (size_t)W * H * sizeof(uint32_t));
+    return FSGM_OK;
+}
+
+}  // extern "C"

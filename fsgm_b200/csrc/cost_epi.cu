@@ -1,0 +1,167 @@
+// Epipolar matching-cost volume — replaces calc_cost() (reference calc_cost_sgm.cpp:319-412).
+//
+//   raw[p][d] = popc(cen1[p] ^ cen2[q(p,d)])            q = clamp(round(Pd0(p) - 1 + (O(p)*vz(d))*u(p)))
+//   C[p][d]   = (u8)(1.0*sum_{5x5}(raw[.][d])/25 + 0.5)  replicate border over the COST volume (:387-404)
+//
+// Geometry is evaluated in fp64 with explicit round-to-nearest mul/add (no FMA contraction — the
+// reference is compiled without it and a fused multiply-add changes round() outcomes), C `round`
+// (half away from zero), then the x86 double->int conversion the reference gets from gcc
+// (cvttsd2si: out-of-range / NaN -> INT_MIN, which the following clamp turns into 0).
+// vz(d) is tabulated on the host with the reference's exact expression (:360-361).
+//
+// Layout: label-contiguous u8 [pair][y][x][d]; a warp writes 128 B (uchar4 per lane) per store.
+#include "fsgm_internal.h"
+
+namespace fsgm {
+
+__device__ __forceinline__ int ref_round_to_index(double v, int hi)
+{
+    // C round(): half away from zero.  v - trunc(v) is exact, so the tie test is exact too.
+    double t = trunc(v);
+    double f = __dsub_rn(v, t);
+    if (fabs(f) >= 0.5) t = __dadd_rn(t, copysign(1.0, v));
+    // x86 cvttsd2si semantics followed by clamp(.,0,hi) (calc_cost_sgm.cpp:371-375)
+    if (!(t < 2147483648.0)) return 0;                  // too large or NaN -> INT_MIN -> 0
+    int i = __double2int_rz(t);                         // saturates to INT_MIN below -2^31 -> 0 after clamp
+    return min(max(i, 0), hi);
+}
+
+// One warp per pixel, each lane 4 consecutive labels per 128-label chunk.
+__global__ void __launch_bounds__(256)
+epi_raw_cost_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restrict__ cen2,
+                    const double* __restrict__ Pd0, const double* __restrict__ dirn, const double* __restrict__ O,
+                    const double* __restrict__ vz, int W, int H, int D, uint8_t* __restrict__ raw)
+{
+    const size_t N = (size_t)W * H;
+    const int lane = threadIdx.x & 31;
+    const size_t warp = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int pair = blockIdx.y;
+    if (warp >= N) return;
+    const size_t p = warp, gp = pair * N + p;
+    const double bx = __dsub_rn(Pd0[pair * 2 * N + p], 1.0), by = __dsub_rn(Pd0[pair * 2 * N + N + p], 1.0);
+    const double ux = dirn[pair * 2 * N + p], uy = dirn[pair * 2 * N + N + p], off = O[gp];
+    const uint32_t c1 = cen1[gp];
+    const uint32_t* c2 = cen2 + pair * N;
+    uint8_t* out = raw + gp * D;
+    const bool vec = (D & 3) == 0;
+    for (int d0 = lane * 4; d0 < D; d0 += 128) {
+        uint32_t packed = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int d = d0 + j;
+            uint32_t h = 0;
+            if (d < D) {
+                double t = __dmul_rn(off, vz[d]);
+                int x2 = ref_round_to_index(__dadd_rn(bx, __dmul_rn(t, ux)), W - 1);
+                int y2 = ref_round_to_index(__dadd_rn(by, __dmul_rn(t, uy)), H - 1);
+                h = __popc(c1 ^ __ldg(c2 + (size_t)y2 * W + x2));
+            }
+            packed |= h << (8 * j);
+        }
+        if (vec) *reinterpret_cast<uint32_t*>(out + d0) = packed;
+        else
+            for (int j = 0; j < 4 && d0 + j < D; ++j) out[d0 + j] = (uint8_t)(packed >> (8 * j));
+    }
+}
+
+// 5x5 box over (x,y) per label, replicate border.  Thread = (x, 4 labels), marching down a row segment
+// with a register ring of the five horizontal 5-sums (each <= 5*24 so four of them fit one 32-bit word).
+// (u8)(1.0*s/25 + 0.5) == (2*s + 25) / 50 in integers: 2*s+25 is odd, never a multiple of 50, and the
+// fp64 quotient is within 1e-13 of a value whose distance to the next integer is >= 1/50.
+__device__ __forceinline__ uint32_t box_norm4(uint32_t lo, uint32_t hi)   // lo: bytes 0,2 as u16x2; hi: bytes 1,3
+{
+    uint32_t a = ((2 * (lo & 0xFFFF) + 25) * 1311u) >> 16;      // /50 for values < 2^12: 1311/65536 = 1/49.99
+    uint32_t b = ((2 * (lo >> 16) + 25) * 1311u) >> 16;
+    uint32_t c = ((2 * (hi & 0xFFFF) + 25) * 1311u) >> 16;
+    uint32_t d = ((2 * (hi >> 16) + 25) * 1311u) >> 16;
+    return a | (c << 8) | (b << 16) | (d << 24);
+}
+
+constexpr int BOX_ROWS = 16;     // rows produced per thread (plus 4 warm-up rows)
+
+__global__ void __launch_bounds__(256)
+epi_box5_kernel(const uint8_t* __restrict__ raw, uint8_t* __restrict__ C, int W, int H, int D)
+{
+    // thread -> (x, label quad).  D4 = D/4 quads; blockDim.x threads cover `xs` columns x D4 quads.
+    const int D4 = D >> 2;
+    const int xs = blockDim.x / D4;
+    const int q = threadIdx.x % D4, xl = threadIdx.x / D4;
+    if (xl >= xs) return;
+    const int x = blockIdx.x * xs + xl;
+    if (x >= W) return;
+    const size_t N = (size_t)W * H;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(raw + blockIdx.z * N * D);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(C + blockIdx.z * N * D);
+    const int y0 = blockIdx.y * BOX_ROWS;
+    int xc[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) xc[k] = min(max(x + k - 2, 0), W - 1);
+    auto hsum = [&](int y) -> uint32_t {            // horizontal 5-sum of four labels, bytes stay < 256
+        int yy = min(max(y, 0), H - 1);
+        const uint32_t* row = src + (size_t)yy * W * D4 + q;
+        uint32_t s = 0;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) s += __ldg(row + (size_t)xc[k] * D4);
+        return s;
+    };
+    uint32_t h0 = hsum(y0 - 2), h1 = hsum(y0 - 1), h2 = hsum(y0), h3 = hsum(y0 + 1);
+    for (int y = y0; y < min(y0 + BOX_ROWS, H); ++y) {
+        uint32_t h4 = hsum(y + 2);
+        uint32_t lo = (h0 & 0x00FF00FFu) + (h1 & 0x00FF00FFu) + (h2 & 0x00FF00FFu) + (h3 & 0x00FF00FFu) + (h4 & 0x00FF00FFu);
+        uint32_t hi = ((h0 >> 8) & 0x00FF00FFu) + ((h1 >> 8) & 0x00FF00FFu) + ((h2 >> 8) & 0x00FF00FFu) +
+                      ((h3 >> 8) & 0x00FF00FFu) + ((h4 >> 8) & 0x00FF00FFu);
+        dst[((size_t)y * W + x) * D4 + q] = box_norm4(lo, hi);
+        h0 = h1; h1 = h2; h2 = h3; h3 = h4;
+    }
+}
+
+// generic fallback for D not a multiple of 4: one thread per voxel
+__global__ void epi_box5_scalar_kernel(const uint8_t* __restrict__ raw, uint8_t* __restrict__ C, int W, int H, int D)
+{
+    const size_t N = (size_t)W * H, V = N * D;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V) return;
+    const uint8_t* src = raw + blockIdx.z * V;
+    int d = (int)(i % D);
+    size_t p = i / D;
+    int x = (int)(p % W), y = (int)(p / W);
+    uint32_t s = 0;
+    for (int dy = -2; dy <= 2; ++dy)
+        for (int dx = -2; dx <= 2; ++dx) {
+            int yy = min(max(y + dy, 0), H - 1), xx = min(max(x + dx, 0), W - 1);
+            s += src[((size_t)yy * W + xx) * D + d];
+        }
+    C[blockIdx.z * V + i] = (uint8_t)((2 * s + 25) / 50);
+}
+
+int launch_epi_cost(fsgm_ctx* c, int n, const uint32_t* cen1, const uint32_t* cen2, int W, int H, int D, double vMax,
+                    const double* Pd0, const double* dirn, const double* O, uint8_t* raw, uint8_t* C)
+{
+    // vz table with the reference's exact expression and evaluation order (calc_cost_sgm.cpp:339,360-361)
+    std::vector<double> vz(D);
+    const double nn = D + 1;
+    for (int d = 0; d < D; ++d) { volatile double r = 1.0 * d / nn * vMax; vz[d] = r / (1 - r); }
+    double* d_vz = nullptr;
+    FSGM_TRY(arena_get(c, (size_t)D, &d_vz));
+    FSGM_CUDA(c, cudaMemcpyAsync(d_vz, vz.data(), D * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    FSGM_CUDA(c, cudaStreamSynchronize(c->stream));      // vz is a stack/host temporary
+    const size_t N = (size_t)W * H;
+    {
+        dim3 grid((unsigned)((N + 7) / 8), n);
+        epi_raw_cost_kernel<<<grid, 256, 0, c->stream>>>(cen1, cen2, Pd0, dirn, O, d_vz, W, H, D, raw);
+        FSGM_LAUNCHED(c);
+    }
+    if ((D & 3) == 0 && D / 4 <= 256) {
+        int D4 = D / 4, xs = 256 / D4;
+        dim3 grid((W + xs - 1) / xs, (H + BOX_ROWS - 1) / BOX_ROWS, n);
+        epi_box5_kernel<<<grid, 256, 0, c->stream>>>(raw, C, W, H, D);
+    } else {
+        size_t V = N * D;
+        dim3 grid((unsigned)((V + 255) / 256), 1, n);
+        epi_box5_scalar_kernel<<<grid, 256, 0, c->stream>>>(raw, C, W, H, D);
+    }
+    FSGM_LAUNCHED(c);
+    return FSGM_OK;
+}
+
+}  // namespace fsgm

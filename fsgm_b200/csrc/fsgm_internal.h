@@ -1,0 +1,71 @@
+// Internal declarations shared by the kernels and the C-ABI layer.  Not installed.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <string>
+#include <vector>
+#include "../../include/fsgm.h"
+
+struct fsgm_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;        // the stream kernels are launched on
+    char* arena = nullptr;                // scratch, grown on demand, reused across calls
+    size_t arena_bytes = 0;
+    size_t arena_top = 0;
+    uint64_t launches = 0;
+    int sm_count = 0;
+    std::string err;
+};
+
+namespace fsgm {
+
+// ---- error plumbing ---------------------------------------------------------------------------
+int  fail(fsgm_ctx* c, int code, const char* what, const char* detail = nullptr);
+#define FSGM_CUDA(ctx, expr)                                                         \
+    do { cudaError_t e__ = (expr);                                                   \
+         if (e__ != cudaSuccess) return fsgm::fail((ctx), FSGM_ERR_CUDA, #expr, cudaGetErrorString(e__)); } while (0)
+#define FSGM_TRY(expr) do { int rc__ = (expr); if (rc__ != FSGM_OK) return rc__; } while (0)
+#define FSGM_LAUNCHED(ctx)                                                           \
+    do { (ctx)->launches++; cudaError_t e__ = cudaGetLastError();                    \
+         if (e__ != cudaSuccess) return fsgm::fail((ctx), FSGM_ERR_CUDA, "kernel launch", cudaGetErrorString(e__)); } while (0)
+
+// ---- scratch arena: bump allocator, reset per top-level call ----------------------------------
+struct ArenaScope {                       // restores the arena top on scope exit
+    fsgm_ctx* c; size_t saved;
+    explicit ArenaScope(fsgm_ctx* ctx) : c(ctx), saved(ctx->arena_top) {}
+    ~ArenaScope() { c->arena_top = saved; }
+};
+int arena_reserve(fsgm_ctx* c, size_t total_bytes);            // make sure the arena holds this much
+int arena_alloc(fsgm_ctx* c, size_t bytes, void** out);        // 256-B aligned slice; fails if not reserved
+template <class T> inline int arena_get(fsgm_ctx* c, size_t count, T** out) {
+    return arena_alloc(c, count * sizeof(T), reinterpret_cast<void**>(out));
+}
+inline size_t align256(size_t b) { return (b + 255) & ~size_t(255); }
+
+// ---- direction table (same order as include/fsgm.h documents) ---------------------------------
+//   r: 0 L1(+1,0)  1 L3(0,+1)  2 L2(+1,+1)  3 L4(-1,+1)   4..7 = negated (pass 1)
+__host__ __device__ inline int dir_dx(int r) { const int t[8] = {1, 0, 1, -1, -1, 0, -1, 1}; return t[r]; }
+__host__ __device__ inline int dir_dy(int r) { const int t[8] = {0, 1, 1, 1, 0, -1, -1, -1}; return t[r]; }
+inline bool dir_enabled(int r, int total_pass, bool diag) {
+    if (r >= 4 && total_pass < 2) return false;
+    if ((r & 3) >= 2 && !diag) return false;
+    return total_pass >= 1;
+}
+
+// ---- kernel launchers (definitions in the .cu files) -------------------------------------------
+int launch_census(fsgm_ctx* c, int n_images, const uint8_t* img, int W, int H, uint32_t* cen);
+int launch_epi_cost(fsgm_ctx* c, int n, const uint32_t* cen1, const uint32_t* cen2, int W, int H, int D, double vMax,
+                    const double* Pd0, const double* dirn, const double* O, uint8_t* raw, uint8_t* C);
+// all enabled directions in one launch; Lvols[k] is the output volume of the k-th enabled direction
+// cmax = upper bound on the values in C (24 for anything built from 5x5 census; 255 = unknown) — selects the
+// exact-u16 or the explicit mod-256 instantiation (see aggregate.cu)
+int launch_sweeps(fsgm_ctx* c, int n, const uint8_t* C, const uint8_t* I1, int W, int H, int D,
+                  int P1, int P2, int adaptive_thr, int cmax, const int* dirs, int n_dirs, uint8_t* const* Lvols);
+bool sweep_needs_wrap(int P1, int P2, int cmax);
+// sum of n_dirs L volumes -> WTA -> subpixel -> (optionally) vz->disparity; Sp16 (u16 [n][N][D]) may be null
+int launch_epi_wta(fsgm_ctx* c, int n, uint8_t* const* Lvols, int n_dirs, int W, int H, int D, int subpixel,
+                   int vz_to_disp, const double* O, double vMax, uint16_t* Sp16, uint32_t* bestD, uint32_t* minC);
+
+}  // namespace fsgm

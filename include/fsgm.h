@@ -1,0 +1,105 @@
+/* fsgm.h — C ABI of the B200-native fSGM hot path (census / Hamming cost volume, multi-direction
+ * semi-global aggregation, winner-take-all + subpixel).
+ *
+ * Every gateway below is a drop-in for one MATLAB MEX gateway of the reference
+ * (`void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[])`): same operands in
+ * the same order, as flat pointers plus explicit sizes, caller-allocated outputs, int status.
+ * Array layout is the reference's: row-major, x fastest (the MATLAB drivers permute before the call,
+ * epipolar_sgm_of.m:33-43); two-plane double arrays are plane-major (plane 0 = X, plane 1 = Y).
+ * INTEGRATION.md shows the MEX / ctypes stubs that bind these symbols.
+ *
+ * Pointers named d_* are DEVICE pointers; all others are HOST pointers.  There is no CPU fallback:
+ * every entry point returns FSGM_ERR_CUDA if no sm_100 device is usable.
+ */
+#ifndef FSGM_H
+#define FSGM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define FSGM_API __attribute__((visibility("default")))
+#else
+#define FSGM_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FSGM_OK             0
+#define FSGM_ERR_ARG       -1   /* null pointer, non-positive size, bad option value           */
+#define FSGM_ERR_DOMAIN    -2   /* parameter combination outside what the kernels implement    */
+#define FSGM_ERR_CUDA      -3   /* CUDA runtime / launch failure (see fsgm_last_error)          */
+#define FSGM_ERR_NOMEM     -4   /* scratch arena could not be grown                            */
+#define FSGM_ERR_NCCL      -5
+
+typedef struct fsgm_ctx fsgm_ctx;
+
+/* ---- context: one per GPU; owns a stream and a scratch arena reused across calls ------------- */
+FSGM_API int         fsgm_create(int device, fsgm_ctx** out);
+FSGM_API void        fsgm_destroy(fsgm_ctx* ctx);
+/* Launch on a caller-owned cudaStream_t instead of the context's own (NULL restores it). */
+FSGM_API int         fsgm_set_stream(fsgm_ctx* ctx, void* cuda_stream);
+FSGM_API int         fsgm_synchronize(fsgm_ctx* ctx);
+FSGM_API const char* fsgm_last_error(const fsgm_ctx* ctx);
+FSGM_API int         fsgm_abi_version(void);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+FSGM_API uint64_t    fsgm_launch_count(const fsgm_ctx* ctx);
+FSGM_API size_t      fsgm_scratch_bytes(const fsgm_ctx* ctx);
+
+/* ---- options that are compile-time constants inside the reference ------------------------- */
+typedef struct fsgm_epi_opts {
+    int paths;        /* 4 = as shipped (calc_cost_sgm.cpp:104 enableDiagnalPath=false), 8 = diagonals on */
+    int total_pass;   /* calc_cost_sgm.cpp:103, reference value 2; 1 keeps only the forward sweeps           */
+    int subpixel;     /* calc_cost_sgm.cpp:560, reference value 1 (always on)                               */
+    int adaptive_p2;  /* calc_cost_sgm.cpp:102, reference value 0; threshold 25 (:68-72)                    */
+    int vz_to_disp;   /* calc_cost_sgm.cpp:592-594 (USE_VZIND), reference value 1                           */
+} fsgm_epi_opts;
+FSGM_API void fsgm_epi_opts_default(fsgm_epi_opts* o);   /* {4, 2, 1, 0, 1} — the reference as shipped */
+
+/* ---- gateway 1: calc_cost_sgm (calc_cost_sgm.cpp:539-598) ----------------------------------
+ * [bestD, minC, conf, bestD2] = calc_cost_sgm(I1, I2, dMax, vMax, pixelPosD0, normlizeDirection,
+ *                                             offsetFromPosD0, P1, P2)
+ * I1,I2 u8[H][W]; pixelPosD0 f64[2][H][W] (1-based); normlizeDirection f64[2][H][W];
+ * offsetFromPosD0 f64[H][W].  bestD u32[H][W] = pixel disparity x256, minC u32[H][W];
+ * conf u8[H][W] and bestD2 u32[H][W] may be NULL, otherwise they are zero-filled exactly as the
+ * reference leaves them (its forward/backward check is commented out, :589-590).
+ * opts == NULL means the reference as shipped. */
+FSGM_API int fsgm_calc_cost_sgm(fsgm_ctx* ctx, const uint8_t* I1, const uint8_t* I2, int width, int height,
+                       int dMax, double vMax, const double* pixelPosD0, const double* normlizeDirection,
+                       const double* offsetFromPosD0, int P1, int P2, const fsgm_epi_opts* opts,
+                       uint32_t* bestD, uint32_t* minC, uint8_t* conf, uint32_t* bestD2);
+
+/* Same call over n_pairs independent pairs; every array is pair-major (pair stride = its per-pair size). */
+FSGM_API int fsgm_calc_cost_sgm_batch(fsgm_ctx* ctx, int n_pairs, const uint8_t* I1, const uint8_t* I2, int width, int height,
+                             int dMax, double vMax, const double* pixelPosD0, const double* normlizeDirection,
+                             const double* offsetFromPosD0, int P1, int P2, const fsgm_epi_opts* opts,
+                             uint32_t* bestD, uint32_t* minC);
+
+/* Device-resident form: inputs and outputs already in HBM, asynchronous on the context's stream. */
+FSGM_API int fsgm_calc_cost_sgm_dev(fsgm_ctx* ctx, int n_pairs, const uint8_t* d_I1, const uint8_t* d_I2, int width, int height,
+                           int dMax, double vMax, const double* d_pixelPosD0, const double* d_normlizeDirection,
+                           const double* d_offsetFromPosD0, int P1, int P2, const fsgm_epi_opts* opts,
+                           uint32_t* d_bestD, uint32_t* d_minC);
+
+/* ---- stage entry points (device pointers; the reference's internal seams) --------------------
+ * census()            common.cpp:3-27
+ * calc_cost()         calc_cost_sgm.cpp:319-412  (d_raw may be NULL; otherwise also receives the pre-box cost)
+ * sgm() sweeps        calc_cost_sgm.cpp:114-257  one direction r = 0..7 in the order
+ *                     L1(+x) L3(+y) L2(+x+y) L4(-x+y), then the same four reversed
+ * sgm() WTA/subpixel  calc_cost_sgm.cpp:259-308 followed by convert_vzInd_to_disp (:414-426) */
+FSGM_API int fsgm_census_dev(fsgm_ctx* ctx, int n_images, const uint8_t* d_img, int width, int height, uint32_t* d_census);
+FSGM_API int fsgm_epi_cost_dev(fsgm_ctx* ctx, int n_pairs, const uint32_t* d_cen1, const uint32_t* d_cen2, int width, int height,
+                      int dMax, double vMax, const double* d_pixelPosD0, const double* d_normlizeDirection,
+                      const double* d_offsetFromPosD0, uint8_t* d_raw, uint8_t* d_C);
+FSGM_API int fsgm_sweep_dev(fsgm_ctx* ctx, int n_pairs, const uint8_t* d_C, const uint8_t* d_I1, int width, int height, int dMax,
+                   int P1, int P2, int adaptive_thr, int direction, uint8_t* d_L);
+FSGM_API int fsgm_epi_aggregate_dev(fsgm_ctx* ctx, int n_pairs, const uint8_t* d_C, const uint8_t* d_I1, int width, int height,
+                           int dMax, int P1, int P2, const fsgm_epi_opts* opts, uint16_t* d_Sp /* may be NULL */,
+                           const double* d_offsetFromPosD0, double vMax, uint32_t* d_bestD, uint32_t* d_minC);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FSGM_H */
