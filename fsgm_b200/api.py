@@ -39,6 +39,7 @@ def load_library() -> C.CDLL:
     lib.fsgm_last_error.restype = C.c_char_p
     lib.fsgm_launch_count.restype = C.c_uint64
     lib.fsgm_scratch_bytes.restype = C.c_size_t
+    lib.fsgm_stage_name.restype = C.c_char_p
     return lib
 
 
@@ -122,6 +123,23 @@ class Context:
     @property
     def scratch_bytes(self) -> int:
         return int(self._l.fsgm_scratch_bytes(self._h))
+
+    # ------------------------------------------------------------------ per-stage device timing
+    def profile(self, on: bool):
+        self._ck(self._l.fsgm_profile_enable(self._h, int(on)))
+
+    def profile_reset(self):
+        self._ck(self._l.fsgm_profile_reset(self._h))
+
+    def profile_read(self) -> dict:
+        """{stage name: (milliseconds, kernel launches)} accumulated since the last reset"""
+        out = {}
+        for st in range(self._l.fsgm_stage_count()):
+            ms, n = C.c_double(), C.c_uint64()
+            self._ck(self._l.fsgm_profile_read(self._h, st, C.byref(ms), C.byref(n)))
+            if n.value:
+                out[self._l.fsgm_stage_name(st).decode()] = (ms.value, n.value)
+        return out
 
     # ------------------------------------------------------------------ gateway 1 (host arrays)
     def calc_cost_sgm(self, I1, I2, dMax, vMax, pixelPosD0, normlizeDirection, offsetFromPosD0, P1, P2, opts=None):

@@ -267,6 +267,7 @@ int launch_sweeps(fsgm_ctx* c, int n, const uint8_t* C, const uint8_t* I1, int W
 {
     if (D < 1 || D > 512) return fail(c, FSGM_ERR_DOMAIN, "label count must be in 1..512");
     if (n_dirs < 1 || n_dirs > 8) return fail(c, FSGM_ERR_ARG, "n_dirs");
+    StageScope ss(c, ST_SWEEP);
     SweepParams p{};
     p.C = C; p.I1 = I1; p.n_dirs = n_dirs; p.W = W; p.H = H; p.D = D; p.P1 = P1; p.P2 = P2; p.adaptive_thr = adaptive_thr;
     p.line_start[0] = 0;

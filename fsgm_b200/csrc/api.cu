@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <algorithm>
 
 namespace fsgm {
 
@@ -36,6 +37,61 @@ int arena_alloc(fsgm_ctx* c, size_t bytes, void** out)
     if (c->arena_top + need > c->arena_bytes) return fail(c, FSGM_ERR_NOMEM, "scratch arena exhausted (reserve too small)");
     *out = c->arena + c->arena_top;
     c->arena_top += need;
+    return FSGM_OK;
+}
+
+StageScope::StageScope(fsgm_ctx* ctx, int st) : c(ctx), stage(st), launches0(ctx->launches)
+{
+    if (!c->profiling) return;
+    if (c->event_pool.empty()) { cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) return; c->event_pool.push_back(e); }
+    a = c->event_pool.back(); c->event_pool.pop_back();
+    cudaEventRecord(a, c->stream);
+}
+StageScope::~StageScope()
+{
+    c->stage_launches[stage] += c->launches - launches0;
+    if (!a) return;
+    cudaEvent_t b;
+    if (c->event_pool.empty()) { if (cudaEventCreate(&b) != cudaSuccess) { c->event_pool.push_back(a); return; } }
+    else { b = c->event_pool.back(); c->event_pool.pop_back(); }
+    cudaEventRecord(b, c->stream);
+    c->timers.push_back({a, b, stage});
+}
+
+static void profile_collect(fsgm_ctx* c)
+{
+    for (auto& t : c->timers) {
+        cudaEventSynchronize(t.b);
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) c->stage_ms[t.stage] += ms;
+        c->event_pool.push_back(t.a); c->event_pool.push_back(t.b);
+    }
+    c->timers.clear();
+}
+
+int pipe_reserve(fsgm_ctx* c, size_t bytes_per_slot)
+{
+    HostPipe& p = c->pipe;
+    if (!p.h2d) {
+        FSGM_CUDA(c, cudaStreamCreateWithFlags(&p.h2d, cudaStreamNonBlocking));
+        FSGM_CUDA(c, cudaStreamCreateWithFlags(&p.d2h, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            FSGM_CUDA(c, cudaEventCreateWithFlags(&p.in_ready[i], cudaEventDisableTiming));
+            FSGM_CUDA(c, cudaEventCreateWithFlags(&p.done[i], cudaEventDisableTiming));
+            FSGM_CUDA(c, cudaEventCreateWithFlags(&p.out_ready[i], cudaEventDisableTiming));
+        }
+    }
+    bytes_per_slot = align256(bytes_per_slot);
+    if (bytes_per_slot <= p.bytes) return FSGM_OK;
+    FSGM_CUDA(c, cudaDeviceSynchronize());
+    for (int i = 0; i < 2; ++i) { if (p.buf[i]) cudaFree(p.buf[i]); p.buf[i] = nullptr; }
+    p.bytes = 0;
+    for (int i = 0; i < 2; ++i)
+        if (cudaMalloc(reinterpret_cast<void**>(&p.buf[i]), bytes_per_slot) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(c, FSGM_ERR_NOMEM, "cudaMalloc(host-gateway staging)");
+        }
+    p.bytes = bytes_per_slot;
     return FSGM_OK;
 }
 
@@ -85,7 +141,8 @@ static int epi_pipeline_dev(fsgm_ctx* c, int n, const uint8_t* I1, const uint8_t
     const size_t N = (size_t)W * H, V = N * D;
     int dirs[8];
     const int nd = enabled_dirs(o, dirs);
-    uint32_t *cen1, *cen2; uint8_t *raw, *C, *L[8];
+    uint32_t *cen1, *cen2; uint8_t *raw, *C, *L[8]; double* vz;
+    FSGM_TRY(arena_get(c, (size_t)D, &vz));
     FSGM_TRY(arena_get(c, n * N, &cen1));
     FSGM_TRY(arena_get(c, n * N, &cen2));
     FSGM_TRY(arena_get(c, n * V, &raw));
@@ -93,7 +150,8 @@ static int epi_pipeline_dev(fsgm_ctx* c, int n, const uint8_t* I1, const uint8_t
     for (int k = 0; k < nd; ++k) FSGM_TRY(arena_get(c, n * V, &L[k]));
     FSGM_TRY(launch_census(c, n, I1, W, H, cen1));
     FSGM_TRY(launch_census(c, n, I2, W, H, cen2));
-    FSGM_TRY(launch_epi_cost(c, n, cen1, cen2, W, H, D, vMax, Pd0, dirn, O, raw, C));
+    FSGM_TRY(launch_vz_table(c, D, vMax, vz));
+    FSGM_TRY(launch_epi_cost(c, n, vz, cen1, cen2, W, H, D, vMax, Pd0, dirn, O, raw, C));
     FSGM_TRY(launch_sweeps(c, n, C, I1, W, H, D, P1, P2, o.adaptive_p2 ? 25 : 0, /*cmax=*/24, dirs, nd, L));
     FSGM_TRY(launch_epi_wta(c, n, L, nd, W, H, D, o.subpixel, o.vz_to_disp, O, vMax, nullptr, bestD, minC));
     return FSGM_OK;
@@ -138,7 +196,15 @@ void fsgm_destroy(fsgm_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    cudaDeviceSynchronize();
     if (c->arena) cudaFree(c->arena);
+    for (auto& t : c->timers) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+    for (auto e : c->event_pool) cudaEventDestroy(e);
+    for (int i = 0; i < 2; ++i) {
+        if (c->pipe.buf[i]) cudaFree(c->pipe.buf[i]);
+        if (c->pipe.in_ready[i]) { cudaEventDestroy(c->pipe.in_ready[i]); cudaEventDestroy(c->pipe.done[i]); cudaEventDestroy(c->pipe.out_ready[i]); }
+    }
+    if (c->pipe.h2d) { cudaStreamDestroy(c->pipe.h2d); cudaStreamDestroy(c->pipe.d2h); }
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -162,6 +228,36 @@ const char* fsgm_last_error(const fsgm_ctx* c) { return c ? c->err.c_str() : "nu
 uint64_t fsgm_launch_count(const fsgm_ctx* c) { return c ? c->launches : 0; }
 size_t fsgm_scratch_bytes(const fsgm_ctx* c) { return c ? c->arena_bytes : 0; }
 
+int fsgm_profile_enable(fsgm_ctx* c, int on)
+{
+    if (!c) return FSGM_ERR_ARG;
+    profile_collect(c);
+    c->profiling = on != 0;
+    return FSGM_OK;
+}
+int fsgm_profile_reset(fsgm_ctx* c)
+{
+    if (!c) return FSGM_ERR_ARG;
+    profile_collect(c);
+    for (int i = 0; i < ST_COUNT; ++i) { c->stage_ms[i] = 0; c->stage_launches[i] = 0; }
+    return FSGM_OK;
+}
+int fsgm_profile_read(fsgm_ctx* c, int stage, double* ms, uint64_t* launches)
+{
+    if (!c || stage < 0 || stage >= ST_COUNT) return FSGM_ERR_ARG;
+    profile_collect(c);
+    if (ms) *ms = c->stage_ms[stage];
+    if (launches) *launches = c->stage_launches[stage];
+    return FSGM_OK;
+}
+const char* fsgm_stage_name(int stage)
+{
+    static const char* names[ST_COUNT] = { "census", "epi_cost", "sweep", "wta", "pyd_cost", "pyd_sweep", "pyd_wta",
+                                           "ng", "pydng_cost", "pydng_sweep", "pydng_wta", "misc" };
+    return (stage >= 0 && stage < ST_COUNT) ? names[stage] : nullptr;
+}
+int fsgm_stage_count(void) { return ST_COUNT; }
+
 // ---------------------------------------------------------------------------------------------
 // stage entry points
 // ---------------------------------------------------------------------------------------------
@@ -183,8 +279,11 @@ int fsgm_epi_cost_dev(fsgm_ctx* c, int n, const uint32_t* d_cen1, const uint32_t
     FSGM_TRY(arena_reserve(c, align256(D * 8) + (d_raw ? 0 : align256(n * V))));
     ArenaScope scope(c);
     uint8_t* raw = d_raw;
+    double* vz;
+    FSGM_TRY(arena_get(c, (size_t)D, &vz));
     if (!raw) FSGM_TRY(arena_get(c, n * V, &raw));
-    return launch_epi_cost(c, n, d_cen1, d_cen2, W, H, D, vMax, d_Pd0, d_dir, d_O, raw, d_C);
+    FSGM_TRY(launch_vz_table(c, D, vMax, vz));
+    return launch_epi_cost(c, n, vz, d_cen1, d_cen2, W, H, D, vMax, d_Pd0, d_dir, d_O, raw, d_C);
 }
 
 int fsgm_sweep_dev(fsgm_ctx* c, int n, const uint8_t* d_C, const uint8_t* d_I1, int W, int H, int D,
@@ -255,33 +354,49 @@ int fsgm_calc_cost_sgm_batch(fsgm_ctx* c, int n, const uint8_t* I1, const uint8_
                              const fsgm_epi_opts* opts, uint32_t* bestD, uint32_t* minC)
 {
     FSGM_TRY(check_dims(c, n, W, H, D));
+    fsgm_epi_opts o;
+    FSGM_TRY(check_opts(c, opts, &o));
     if (!I1 || !I2 || !Pd0 || !dirn || !O || !bestD || !minC) return fail(c, FSGM_ERR_ARG, "null pointer");
     FSGM_CUDA(c, cudaSetDevice(c->device));
     const size_t N = (size_t)W * H;
-    // device staging for inputs and outputs (separate from the arena so the pipeline can size its own scratch)
-    uint8_t *dI = nullptr; double* dG = nullptr; uint32_t* dOut = nullptr;
-    auto cleanup = [&]() { cudaFree(dI); cudaFree(dG); cudaFree(dOut); };
-    if (cudaMalloc(&dI, 2 * n * N) != cudaSuccess || cudaMalloc(&dG, 5 * n * N * sizeof(double)) != cudaSuccess ||
-        cudaMalloc(&dOut, 2 * n * N * sizeof(uint32_t)) != cudaSuccess) {
-        cudaGetLastError(); cleanup();
-        return fail(c, FSGM_ERR_NOMEM, "cudaMalloc(host-gateway staging)");
-    }
-    uint8_t *dI1 = dI, *dI2 = dI + n * N;
-    double *dPd0 = dG, *dDir = dG + 2 * n * N, *dO = dG + 4 * n * N;
-    uint32_t *dBest = dOut, *dMin = dOut + n * N;
+    // Chunks of pairs flow through a 2-slot device staging buffer: H2D of chunk i+1 and D2H of chunk i-1 overlap
+    // the kernels of chunk i (truly asynchronous only when the caller's buffers are pinned).
+    const size_t in_pair = align256(N) * 2 + align256(2 * N * 8) * 2 + align256(N * 8);
+    const size_t out_pair = 2 * align256(N * 4);
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n, (size_t(96) << 20) / (in_pair + out_pair) + 1));
+    FSGM_TRY(pipe_reserve(c, (size_t)chunk * (in_pair + out_pair)));
+    HostPipe& p = c->pipe;
     int rc = FSGM_OK;
-    cudaStream_t s = c->stream;
-    auto H2D = [&](void* d, const void* h, size_t b) { return cudaMemcpyAsync(d, h, b, cudaMemcpyHostToDevice, s); };
-    if (H2D(dI1, I1, n * N) || H2D(dI2, I2, n * N) || H2D(dPd0, Pd0, 2 * n * N * 8) || H2D(dDir, dirn, 2 * n * N * 8) ||
-        H2D(dO, O, n * N * 8))
-        rc = fail(c, FSGM_ERR_CUDA, "H2D copy", cudaGetErrorString(cudaGetLastError()));
-    if (rc == FSGM_OK) rc = fsgm_calc_cost_sgm_dev(c, n, dI1, dI2, W, H, D, vMax, dPd0, dDir, dO, P1, P2, opts, dBest, dMin);
-    if (rc == FSGM_OK) {
-        if (cudaMemcpyAsync(bestD, dBest, n * N * 4, cudaMemcpyDeviceToHost, s) ||
-            cudaMemcpyAsync(minC, dMin, n * N * 4, cudaMemcpyDeviceToHost, s) || cudaStreamSynchronize(s))
+    int used[2] = {0, 0};
+    for (int i0 = 0, it = 0; i0 < n && rc == FSGM_OK; i0 += chunk, ++it) {
+        const int m = std::min(chunk, n - i0), slot = it & 1;
+        char* base = p.buf[slot];
+        uint8_t* dI1 = reinterpret_cast<uint8_t*>(base);                 base += align256(m * N);
+        uint8_t* dI2 = reinterpret_cast<uint8_t*>(base);                 base += align256(m * N);
+        double* dPd0 = reinterpret_cast<double*>(base);                  base += align256(m * 2 * N * 8);
+        double* dDir = reinterpret_cast<double*>(base);                  base += align256(m * 2 * N * 8);
+        double* dO = reinterpret_cast<double*>(base);                    base += align256(m * N * 8);
+        uint32_t* dBest = reinterpret_cast<uint32_t*>(base);             base += align256(m * N * 4);
+        uint32_t* dMin = reinterpret_cast<uint32_t*>(base);
+        if (used[slot]) cudaStreamWaitEvent(p.h2d, p.out_ready[slot], 0);          // slot free once its outputs left
+        auto H2D = [&](void* d, const void* h, size_t b) { return cudaMemcpyAsync(d, h, b, cudaMemcpyHostToDevice, p.h2d); };
+        if (H2D(dI1, I1 + i0 * N, m * N) || H2D(dI2, I2 + i0 * N, m * N) || H2D(dPd0, Pd0 + i0 * 2 * N, m * 2 * N * 8) ||
+            H2D(dDir, dirn + i0 * 2 * N, m * 2 * N * 8) || H2D(dO, O + i0 * N, m * N * 8) ||
+            cudaEventRecord(p.in_ready[slot], p.h2d) || cudaStreamWaitEvent(c->stream, p.in_ready[slot], 0)) {
+            rc = fail(c, FSGM_ERR_CUDA, "H2D copy", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        rc = fsgm_calc_cost_sgm_dev(c, m, dI1, dI2, W, H, D, vMax, dPd0, dDir, dO, P1, P2, &o, dBest, dMin);
+        if (rc != FSGM_OK) break;
+        if (cudaEventRecord(p.done[slot], c->stream) || cudaStreamWaitEvent(p.d2h, p.done[slot], 0) ||
+            cudaMemcpyAsync(bestD + i0 * N, dBest, m * N * 4, cudaMemcpyDeviceToHost, p.d2h) ||
+            cudaMemcpyAsync(minC + i0 * N, dMin, m * N * 4, cudaMemcpyDeviceToHost, p.d2h) ||
+            cudaEventRecord(p.out_ready[slot], p.d2h))
             rc = fail(c, FSGM_ERR_CUDA, "D2H copy", cudaGetErrorString(cudaGetLastError()));
-    } else cudaStreamSynchronize(s);
-    cleanup();
+        used[slot] = 1;
+    }
+    cudaError_t e1 = cudaStreamSynchronize(p.d2h), e2 = cudaStreamSynchronize(c->stream), e3 = cudaStreamSynchronize(p.h2d);
+    if (rc == FSGM_OK && (e1 || e2 || e3)) rc = fail(c, FSGM_ERR_CUDA, "pipeline sync", cudaGetErrorString(e1 ? e1 : (e2 ? e2 : e3)));
     return rc;
 }
 

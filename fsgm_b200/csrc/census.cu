@@ -43,6 +43,7 @@ census5x5_kernel(const uint8_t* __restrict__ img, uint32_t* __restrict__ cen, in
 
 int launch_census(fsgm_ctx* c, int n_images, const uint8_t* img, int W, int H, uint32_t* cen)
 {
+    StageScope ss(c, ST_CENSUS);
     dim3 block(CEN_TX, CEN_TY), grid((W + CEN_TX - 1) / CEN_TX, (H + CEN_TY - 1) / CEN_TY, n_images);
     census5x5_kernel<<<grid, block, 0, c->stream>>>(img, cen, W, H);
     FSGM_LAUNCHED(c);

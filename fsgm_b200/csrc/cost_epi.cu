@@ -134,17 +134,28 @@ __global__ void epi_box5_scalar_kernel(const uint8_t* __restrict__ raw, uint8_t*
     C[blockIdx.z * V + i] = (uint8_t)((2 * s + 25) / 50);
 }
 
-int launch_epi_cost(fsgm_ctx* c, int n, const uint32_t* cen1, const uint32_t* cen2, int W, int H, int D, double vMax,
+// vz(d) = r/(1-r), r = 1.0*d/(D+1)*vMax — the reference's expression and evaluation order
+// (calc_cost_sgm.cpp:339,360-361); IEEE double div/mul on the device are bit-identical to SSE2.
+__global__ void vz_table_kernel(int D, double vMax, double* __restrict__ vz)
+{
+    int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= D) return;
+    double r = __dmul_rn(__ddiv_rn((double)d, (double)(D + 1)), vMax);
+    vz[d] = __ddiv_rn(r, __dsub_rn(1.0, r));
+}
+
+int launch_vz_table(fsgm_ctx* c, int D, double vMax, double* d_vz)
+{
+    vz_table_kernel<<<(D + 127) / 128, 128, 0, c->stream>>>(D, vMax, d_vz);
+    FSGM_LAUNCHED(c);
+    return FSGM_OK;
+}
+
+int launch_epi_cost(fsgm_ctx* c, int n, const double* d_vz, const uint32_t* cen1, const uint32_t* cen2, int W, int H, int D, double vMax,
                     const double* Pd0, const double* dirn, const double* O, uint8_t* raw, uint8_t* C)
 {
-    // vz table with the reference's exact expression and evaluation order (calc_cost_sgm.cpp:339,360-361)
-    std::vector<double> vz(D);
-    const double nn = D + 1;
-    for (int d = 0; d < D; ++d) { volatile double r = 1.0 * d / nn * vMax; vz[d] = r / (1 - r); }
-    double* d_vz = nullptr;
-    FSGM_TRY(arena_get(c, (size_t)D, &d_vz));
-    FSGM_CUDA(c, cudaMemcpyAsync(d_vz, vz.data(), D * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    FSGM_CUDA(c, cudaStreamSynchronize(c->stream));      // vz is a stack/host temporary
+    StageScope ss(c, ST_EPI_COST);
+    (void)vMax;
     const size_t N = (size_t)W * H;
     {
         dim3 grid((unsigned)((N + 7) / 8), n);

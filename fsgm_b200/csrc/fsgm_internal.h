@@ -7,6 +7,20 @@
 #include <vector>
 #include "../../include/fsgm.h"
 
+namespace fsgm {
+// pipeline stages, for the optional per-stage CUDA-event timing (fsgm_profile_*)
+enum Stage { ST_CENSUS = 0, ST_EPI_COST, ST_SWEEP, ST_WTA, ST_PYD_COST, ST_PYD_SWEEP, ST_PYD_WTA,
+             ST_NG, ST_PYDNG_COST, ST_PYDNG_SWEEP, ST_PYDNG_WTA, ST_MISC, ST_COUNT };
+struct StageTimer { cudaEvent_t a, b; int stage; };
+// double-buffered device staging + copy streams for the host-pointer gateways
+struct HostPipe {
+    cudaStream_t h2d = nullptr, d2h = nullptr;
+    cudaEvent_t in_ready[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr}, out_ready[2] = {nullptr, nullptr};
+    char* buf[2] = {nullptr, nullptr};
+    size_t bytes = 0;
+};
+}  // namespace fsgm
+
 struct fsgm_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr;
@@ -17,6 +31,13 @@ struct fsgm_ctx {
     uint64_t launches = 0;
     int sm_count = 0;
     std::string err;
+    // profiling
+    bool profiling = false;
+    std::vector<fsgm::StageTimer> timers;      // recorded, not yet read back
+    std::vector<cudaEvent_t> event_pool;
+    double stage_ms[fsgm::ST_COUNT] = {};
+    uint64_t stage_launches[fsgm::ST_COUNT] = {};
+    fsgm::HostPipe pipe;
 };
 
 namespace fsgm {
@@ -30,6 +51,14 @@ int  fail(fsgm_ctx* c, int code, const char* what, const char* detail = nullptr)
 #define FSGM_LAUNCHED(ctx)                                                           \
     do { (ctx)->launches++; cudaError_t e__ = cudaGetLastError();                    \
          if (e__ != cudaSuccess) return fsgm::fail((ctx), FSGM_ERR_CUDA, "kernel launch", cudaGetErrorString(e__)); } while (0)
+
+// ---- per-stage timing: brackets the enclosed launches with events when profiling is on -----------------
+struct StageScope {
+    fsgm_ctx* c; int stage; cudaEvent_t a = nullptr; uint64_t launches0;
+    StageScope(fsgm_ctx* ctx, int st);
+    ~StageScope();
+};
+int  pipe_reserve(fsgm_ctx* c, size_t bytes_per_slot);
 
 // ---- scratch arena: bump allocator, reset per top-level call ----------------------------------
 struct ArenaScope {                       // restores the arena top on scope exit
@@ -56,7 +85,8 @@ inline bool dir_enabled(int r, int total_pass, bool diag) {
 
 // ---- kernel launchers (definitions in the .cu files) -------------------------------------------
 int launch_census(fsgm_ctx* c, int n_images, const uint8_t* img, int W, int H, uint32_t* cen);
-int launch_epi_cost(fsgm_ctx* c, int n, const uint32_t* cen1, const uint32_t* cen2, int W, int H, int D, double vMax,
+int launch_vz_table(fsgm_ctx* c, int D, double vMax, double* d_vz);
+int launch_epi_cost(fsgm_ctx* c, int n, const double* d_vz, const uint32_t* cen1, const uint32_t* cen2, int W, int H, int D, double vMax,
                     const double* Pd0, const double* dirn, const double* O, uint8_t* raw, uint8_t* C);
 // all enabled directions in one launch; Lvols[k] is the output volume of the k-th enabled direction
 // cmax = upper bound on the values in C (24 for anything built from 5x5 census; 255 = unknown) — selects the

@@ -129,6 +129,7 @@ int launch_epi_wta(fsgm_ctx* c, int n, uint8_t* const* Lvols, int n_dirs, int W,
                    int vz_to_disp, const double* O, double vMax, uint16_t* Sp16, uint32_t* bestD, uint32_t* minC)
 {
     if (D > WTA_MAXD) return fail(c, FSGM_ERR_DOMAIN, "label count must be <= 512");
+    StageScope ss(c, ST_WTA);
     WtaParams p{};
     for (int k = 0; k < n_dirs; ++k) p.L[k] = Lvols[k];
     p.n_dirs = n_dirs; p.W = W; p.H = H; p.D = D; p.subpixel = subpixel; p.vz_to_disp = vz_to_disp;

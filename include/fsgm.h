@@ -48,6 +48,14 @@ FSGM_API int         fsgm_abi_version(void);
 FSGM_API uint64_t    fsgm_launch_count(const fsgm_ctx* ctx);
 FSGM_API size_t      fsgm_scratch_bytes(const fsgm_ctx* ctx);
 
+/* Optional per-stage device timing (CUDA events on the launch stream around every stage's kernels).
+ * fsgm_profile_read synchronises the recorded events and returns accumulated milliseconds / kernel launches. */
+FSGM_API int         fsgm_profile_enable(fsgm_ctx* ctx, int on);
+FSGM_API int         fsgm_profile_reset(fsgm_ctx* ctx);
+FSGM_API int         fsgm_profile_read(fsgm_ctx* ctx, int stage, double* ms, uint64_t* launches);
+FSGM_API const char* fsgm_stage_name(int stage);
+FSGM_API int         fsgm_stage_count(void);
+
 /* ---- options that are compile-time constants inside the reference ------------------------- */
 typedef struct fsgm_epi_opts {
     int paths;        /* 4 = as shipped (calc_cost_sgm.cpp:104 enableDiagnalPath=false), 8 = diagonals on */
