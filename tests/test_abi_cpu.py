@@ -1,0 +1,52 @@
+"""The product library loads without a GPU and exports every symbol include/*.h declares (no compute calls here)."""
+import ctypes
+import glob
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    names = []
+    for h in glob.glob(os.path.join(ROOT, "include", "*.h")):
+        names += re.findall(r"FSGM_API\s+[\w\s\*]+?\b(fsgm_\w+)\s*\(", open(h).read())
+    return sorted(set(names))
+
+
+def test_build_and_exports():
+    from fsgm_b200 import build
+    path = build.build()
+    lib = ctypes.CDLL(path)
+    declared = _declared()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/ but not exported"
+    assert lib.fsgm_abi_version() >= 1
+
+
+def test_no_gpu_means_loud_failure():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from fsgm_b200 import api
+    with pytest.raises(api.FsgmError):
+        api.Context(0)
+
+
+def test_product_never_touches_oracle():
+    """Nothing under fsgm_b200/ may import, link or load anything from oracle/."""
+    for path in glob.glob(os.path.join(ROOT, "fsgm_b200", "**", "*"), recursive=True):
+        if os.path.isfile(path) and path.endswith((".py", ".cu", ".cpp", ".h", ".cuh")):
+            txt = open(path, errors="ignore").read()
+            assert "pyoracle" not in txt and "fsgm_oracle" not in txt and "libref_" not in txt, path
+    out = subprocess.run(["ldd", os.path.join(ROOT, "fsgm_b200", "libfsgm.so")], capture_output=True, text=True).stdout
+    assert "oracle" not in out
+
+
+def test_sass_is_sm100a():
+    out = subprocess.run(["cuobjdump", "-lelf", os.path.join(ROOT, "fsgm_b200", "libfsgm.so")], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
