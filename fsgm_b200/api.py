@@ -191,3 +191,44 @@ class Context:
         self._ck(self._l.fsgm_epi_aggregate_dev(self._h, n, _dp(Cvol), _dp(I1), W, H, D, int(P1), int(P2),
                                                 C.byref(opts) if opts is not None else None, _dp(Sp), _dp(O),
                                                 C.c_double(vMax), _dp(bestD), _dp(minC)))
+
+    # ------------------------------------------------------------------ gateway 2: calc_pyd_cost_sgm
+    def calc_pyd_cost_sgm(self, I1, I2, preMv, halfSearchWinSizeX, halfSearchWinSizeY, aggHalfWinSize, subPixelRefine,
+                          P1, P2, enableDiagnalPath=1, totalPass=2, adpativeP2=0):
+        """[bestD, minC, mvSub] = calc_pyd_cost_sgm(...)  (calc_pyd_cost_sgm.cpp:16, :439-510)"""
+        H, W = I1.shape
+        _, mvH, mvW = preMv.shape
+        bestD, minC = np.empty((H, W), np.uint32), np.empty((H, W), np.uint32)
+        mvSub = np.empty((2, H, W), np.float64)
+        self._ck(self._l.fsgm_calc_pyd_cost_sgm(
+            self._h, _hp(I1, np.uint8), _hp(I2, np.uint8, (H, W)), W, H, _hp(preMv, np.float64), mvW, mvH,
+            int(halfSearchWinSizeX), int(halfSearchWinSizeY), int(aggHalfWinSize), int(subPixelRefine), int(P1), int(P2),
+            int(enableDiagnalPath), int(totalPass), int(adpativeP2), _hp(bestD, np.uint32), _hp(minC, np.uint32),
+            _hp(mvSub, np.float64)))
+        return bestD, minC, mvSub
+
+    def calc_pyd_cost_sgm_dev(self, I1, I2, preMv, rx, ry, agg, sub, P1, P2, diag, passes, adaptive, bestD, minC, mvSub):
+        n, H, W = I1.shape
+        _, _, mvH, mvW = preMv.shape
+        self._ck(self._l.fsgm_calc_pyd_cost_sgm_dev(self._h, n, _dp(I1), _dp(I2), W, H, _dp(preMv), mvW, mvH, int(rx), int(ry),
+                                                    int(agg), int(sub), int(P1), int(P2), int(diag), int(passes), int(adaptive),
+                                                    _dp(bestD), _dp(minC), _dp(mvSub)))
+
+    def pyd_cost_dev(self, cen1, cen2, preMv, agg, rx, ry, Cvol):
+        n, H, W = cen1.shape
+        _, _, mvH, mvW = preMv.shape
+        self._ck(self._l.fsgm_pyd_cost_dev(self._h, n, _dp(cen1), _dp(cen2), W, H, _dp(preMv), mvW, mvH, int(agg), int(rx), int(ry),
+                                           _dp(Cvol)))
+
+    def pyd_sweep_dev(self, Cvol, I1, preMv, rx, ry, P1, P2, adaptive, direction, L):
+        n, H, W, D = Cvol.shape
+        _, _, mvH, mvW = preMv.shape
+        self._ck(self._l.fsgm_pyd_sweep_dev(self._h, n, _dp(Cvol), _dp(I1), _dp(preMv), mvW, mvH, W, H, int(rx), int(ry),
+                                            int(P1), int(P2), int(adaptive), int(direction), _dp(L)))
+
+    def pyd_aggregate_dev(self, Cvol, I1, preMv, rx, ry, sub, P1, P2, diag, passes, adaptive, bestD, minC, mvSub, Sp=None):
+        n, H, W, D = Cvol.shape
+        _, _, mvH, mvW = preMv.shape
+        self._ck(self._l.fsgm_pyd_aggregate_dev(self._h, n, _dp(Cvol), _dp(I1), _dp(preMv), mvW, mvH, W, H, int(rx), int(ry),
+                                                int(sub), int(P1), int(P2), int(diag), int(passes), int(adaptive), _dp(Sp),
+                                                _dp(bestD), _dp(minC), _dp(mvSub)))

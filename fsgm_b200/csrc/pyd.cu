@@ -1,0 +1,305 @@
+// Pyramidal 2-D-window variant — replaces calc_cost(), sgm_step() and sgm2d() of the reference's
+// calc_pyd_cost_sgm.cpp (:374-437, :34-89, :114-372).
+//
+// Labels are a (2rx+1) x (2ry+1) window of integer offsets around a per-pixel prior flow, ordered
+// offx-outer / offy-inner: d = (offx+rx)*Sy + (offy+ry) (:392-393, :81).
+//
+//  cost   C[p][d] = (u8)(1.0*sum_{agg window} h / winPixels + 0.5), h = popc(cen1[p+a] ^ cen2[q]) or the constant 5
+//         when p+a or q is outside the image; q = ((int)(1.0*(offx+x1)+mvx+0.5), (int)(1.0*(offy+y1)+mvy+0.5)) with the
+//         prior taken at the CENTRE pixel and C truncation toward zero (:388-389, :415-416).
+//  sweep  the 1-D recurrence with a 2-D label neighbourhood: the predecessor label of (sx,sy) is
+//         ((int)(sx+ddx+0.5), (int)(sy+ddy+0.5)), (ddx,ddy) = prior(cur) - prior(prev on the path) read with the
+//         mv map's own stride (:213-254); same-label term only if inside the window; P1 term = min over the 5x5
+//         label neighbourhood, centre excluded, inside-window only (:56-76).  All in unsigned char (mod 256).
+//  WTA    first minimum; per-axis parabola if the argmin is not on the window edge (:298-360).
+//
+// Mapping: one warp per scanline exactly as in aggregate.cu (wrapped columns for the six non-horizontal
+// directions); the previous L lives in a per-warp shared-memory row so the 5x5 label neighbourhood is 24 LDS.
+// This path is integer-issue-bound (D*24 min ops per step), not HBM-bound.
+#include "fsgm_internal.h"
+
+namespace fsgm {
+
+constexpr int PYD_WARPS = 8;
+constexpr int PYD_MAXD = 1024;        // (2rx+1)(2ry+1) <= 1024
+constexpr int PYD_MAXS = 64;          // window side <= 64
+
+__device__ __forceinline__ int x86_d2i(double v)
+{
+    if (!(v > -2147483649.0 && v < 2147483648.0)) return INT_MIN;
+    return __double2int_rz(v);
+}
+
+// ------------------------------------------------------------------------------------------------
+// cost volume: one warp per pixel, lanes strided over labels
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pyd_cost_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restrict__ cen2, int W, int H,
+                const double* __restrict__ preMv, int mvW, int mvH, int agg, int rx, int ry, uint8_t* __restrict__ C)
+{
+    __shared__ int fx_s[8][PYD_MAXS + 32], fy_s[8][PYD_MAXS + 32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const size_t N = (size_t)W * H;
+    const size_t p = (size_t)blockIdx.x * 8 + wib;
+    if (p >= N) return;
+    const int pair = blockIdx.y;
+    const int x = (int)(p % W), y = (int)(p / W);
+    const int Sy = 2 * ry + 1, D = (2 * rx + 1) * Sy;
+    const double* mvp = preMv + (size_t)pair * 2 * mvW * mvH;
+    const double mvx = mvp[(size_t)mvW * y + x], mvy = mvp[(size_t)mvW * mvH + (size_t)mvW * y + x];
+    // x2 depends only on s = offx + ax (+x): tabulate it for s in [-(rx+agg), rx+agg]; same for y
+    int* fx = fx_s[wib]; int* fy = fy_s[wib];
+    for (int s = lane; s < 2 * (rx + agg) + 1; s += 32) {
+        int v = x86_d2i(__dadd_rn(__dadd_rn((double)(s - rx - agg + x), mvx), 0.5));
+        fx[s] = (v < 0 || v > W - 1) ? -1 : v;
+    }
+    for (int s = lane; s < 2 * (ry + agg) + 1; s += 32) {
+        int v = x86_d2i(__dadd_rn(__dadd_rn((double)(s - ry - agg + y), mvy), 0.5));
+        fy[s] = (v < 0 || v > H - 1) ? -1 : v;
+    }
+    __syncwarp();
+    const uint32_t* c1 = cen1 + pair * N;
+    const uint32_t* c2 = cen2 + pair * N;
+    const int wp = (2 * agg + 1) * (2 * agg + 1);
+    uint8_t* out = C + (pair * N + p) * D;
+    for (int d = lane; d < D; d += 32) {
+        const int ox = d / Sy, oy = d - ox * Sy;           // offx + rx, offy + ry
+        uint32_t s = 0;
+        for (int ay = -agg; ay <= agg; ++ay) {
+            const int y1 = y + ay;
+            for (int ax = -agg; ax <= agg; ++ax) {
+                const int x1 = x + ax;
+                int h = 5;
+                if (y1 >= 0 && y1 < H && x1 >= 0 && x1 < W) {
+                    const int x2 = fx[ox + ax + agg], y2 = fy[oy + ay + agg];
+                    if (x2 >= 0 && y2 >= 0) h = __popc(__ldg(c1 + (size_t)W * y1 + x1) ^ __ldg(c2 + (size_t)W * y2 + x2));
+                }
+                s += h;
+            }
+        }
+        // (u8)(1.0*s/wp + 0.5): the exact quotient (2s+wp)/(2wp) is at least 1/(2wp) away from the next integer
+        // (wp is odd), far more than the fp64 rounding error, so integer floor division is identical
+        out[d] = (uint8_t)((2 * s + wp) / (2 * wp));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// sweep
+// ------------------------------------------------------------------------------------------------
+struct PydSweepParams {
+    const uint8_t* C; const uint8_t* I1; const double* preMv;
+    uint8_t* L[8]; int dir[8]; int line_start[9]; int n_dirs;
+    int W, H, Sx, Sy, mvW, mvH, P1, P2, adaptive;
+};
+
+template <int NJ>
+__global__ void __launch_bounds__(PYD_WARPS * 32)
+pyd_sweep_kernel(const PydSweepParams prm)
+{
+    __shared__ uint8_t Ls[PYD_WARPS][2][NJ * 32];
+    __shared__ int xt[PYD_WARPS][PYD_MAXS], yt[PYD_WARPS][PYD_MAXS];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int gw = blockIdx.x * PYD_WARPS + wib;
+    if (gw >= prm.line_start[prm.n_dirs]) return;
+    int k = 0;
+    while (gw >= prm.line_start[k + 1]) ++k;
+    const int line = gw - prm.line_start[k], r = prm.dir[k];
+    const int dx = dir_dx(r), dy = dir_dy(r);
+    const int W = prm.W, H = prm.H, Sx = prm.Sx, Sy = prm.Sy, D = Sx * Sy, mvW = prm.mvW;
+    const size_t N = (size_t)W * H, mvN = (size_t)mvW * prm.mvH;
+    const uint8_t* __restrict__ Cb = prm.C + blockIdx.y * N * D;
+    uint8_t* __restrict__ Lb = prm.L[k] + blockIdx.y * N * D;
+    const uint8_t* __restrict__ Ib = prm.I1 + blockIdx.y * N;
+    const double* __restrict__ mvx = prm.preMv + blockIdx.y * 2 * mvN;
+    const double* __restrict__ mvy = mvx + mvN;
+
+    int x, y, len;
+    if (dy == 0) { y = line; x = dx > 0 ? 0 : W - 1; len = W; }
+    else         { x = line; y = dy > 0 ? 0 : H - 1; len = H; }
+
+    // per-lane label geometry (d = lane + 32 j)
+    int lsx[NJ], lsy[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) { int d = lane + 32 * j; lsx[j] = d / Sy; lsy[j] = d - lsx[j] * Sy; }
+
+    uint32_t M = 0;
+    int cur = 0, px = 0, py = 0;
+    uint8_t cnext[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) { int d = lane + 32 * j; cnext[j] = d < D ? __ldg(Cb + ((size_t)y * W + x) * D + d) : 0; }
+
+    for (int t = 0; t < len; ++t) {
+        uint8_t c[NJ];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) c[j] = cnext[j];
+        // next position + prefetch of its cost row
+        int nx = x, ny = y;
+        if (dy == 0) nx += dx; else { ny += dy; nx += dx; nx = nx < 0 ? W - 1 : (nx >= W ? 0 : nx); }
+        if (t + 1 < len) {
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) { int d = lane + 32 * j; cnext[j] = d < D ? __ldg(Cb + ((size_t)ny * W + nx) * D + d) : 0; }
+        }
+        const size_t pix = (size_t)y * W + x;
+        const bool start = (t == 0) || (dy != 0 && dx != 0 && x == (dx > 0 ? 0 : W - 1));
+        uint8_t* Lnew = Ls[wib][cur];
+        const uint8_t* Lpre = Ls[wib][cur ^ 1];
+        uint32_t m = 255;
+        if (start) {
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) Lnew[lane + 32 * j] = c[j];
+            M = 0;
+            __syncwarp();
+        } else {
+            int P2 = prm.P2;
+            if (prm.adaptive && abs((int)Ib[pix] - (int)Ib[(size_t)py * W + px]) > 50) P2 = P2 / 8;
+            const double ddx = __dsub_rn(mvx[(size_t)y * mvW + x], mvx[(size_t)py * mvW + px]);
+            const double ddy = __dsub_rn(mvy[(size_t)y * mvW + x], mvy[(size_t)py * mvW + px]);
+            for (int s = lane; s < Sx; s += 32) {
+                int v = x86_d2i(__dadd_rn(__dadd_rn((double)s, ddx), 0.5));
+                xt[wib][s] = min(max(v, -8), Sx + 8);          // anything further out behaves the same: no neighbour inside
+            }
+            for (int s = lane; s < Sy; s += 32) {
+                int v = x86_d2i(__dadd_rn(__dadd_rn((double)s, ddy), 0.5));
+                yt[wib][s] = min(max(v, -8), Sy + 8);
+            }
+            __syncwarp();
+            const uint32_t far_ = (M + (uint32_t)P2) & 0xFFu;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const int d = lane + 32 * j;
+                if (d < D) {
+                    const int xp = xt[wib][lsx[j]], yp = yt[wib][lsy[j]];
+                    uint32_t best = far_;
+                    for (int mm = -2; mm <= 2; ++mm) {
+                        const int tx = xp + mm;
+                        if (tx < 0 || tx >= Sx) continue;
+                        for (int kk = -2; kk <= 2; ++kk) {
+                            const int ty = yp + kk;
+                            if (ty < 0 || ty >= Sy) continue;
+                            const uint32_t v = Lpre[tx * Sy + ty];
+                            const uint32_t cand = (mm == 0 && kk == 0) ? v : ((v + (uint32_t)prm.P1) & 0xFFu);
+                            best = min(best, cand);
+                        }
+                    }
+                    const uint32_t l = (c[j] + best - M) & 0xFFu;
+                    Lnew[d] = (uint8_t)l;
+                    m = min(m, l);
+                }
+            }
+            M = __reduce_min_sync(0xffffffffu, m);
+            __syncwarp();
+        }
+        // store this pixel's L row (coalesced bytes)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) { int d = lane + 32 * j; if (d < D) Lb[pix * D + d] = Lnew[d]; }
+        cur ^= 1;
+        px = x; py = y; x = nx; y = ny;
+    }
+}
+
+int launch_pyd_cost(fsgm_ctx* c, int n, const uint32_t* cen1, const uint32_t* cen2, int W, int H,
+                    const double* preMv, int mvW, int mvH, int agg, int rx, int ry, uint8_t* C)
+{
+    StageScope ss(c, ST_PYD_COST);
+    if (2 * (rx + agg) + 1 > PYD_MAXS + 32 || 2 * (ry + agg) + 1 > PYD_MAXS + 32)
+        return fail(c, FSGM_ERR_DOMAIN, "search + aggregation window too large");
+    const size_t N = (size_t)W * H;
+    dim3 grid((unsigned)((N + 7) / 8), n);
+    pyd_cost_kernel<<<grid, 256, 0, c->stream>>>(cen1, cen2, W, H, preMv, mvW, mvH, agg, rx, ry, C);
+    FSGM_LAUNCHED(c);
+    return FSGM_OK;
+}
+
+int launch_pyd_sweeps(fsgm_ctx* c, int n, const uint8_t* C, const uint8_t* I1, const double* preMv, int mvW, int mvH,
+                      int W, int H, int Sx, int Sy, int P1, int P2, int adaptive, const int* dirs, int n_dirs, uint8_t* const* Lvols)
+{
+    StageScope ss(c, ST_PYD_SWEEP);
+    const int D = Sx * Sy;
+    if (D > PYD_MAXD || Sx > PYD_MAXS || Sy > PYD_MAXS) return fail(c, FSGM_ERR_DOMAIN, "search window too large (<= 1024 labels)");
+    PydSweepParams p{};
+    p.C = C; p.I1 = I1; p.preMv = preMv; p.n_dirs = n_dirs; p.W = W; p.H = H; p.Sx = Sx; p.Sy = Sy; p.mvW = mvW; p.mvH = mvH;
+    p.P1 = P1; p.P2 = P2; p.adaptive = adaptive;
+    p.line_start[0] = 0;
+    for (int k = 0; k < n_dirs; ++k) {
+        p.dir[k] = dirs[k]; p.L[k] = Lvols[k];
+        p.line_start[k + 1] = p.line_start[k] + (dir_dy(dirs[k]) == 0 ? H : W);
+    }
+    dim3 grid((p.line_start[n_dirs] + PYD_WARPS - 1) / PYD_WARPS, n);
+    if (D <= 128) pyd_sweep_kernel<4><<<grid, PYD_WARPS * 32, 0, c->stream>>>(p);
+    else if (D <= 256) pyd_sweep_kernel<8><<<grid, PYD_WARPS * 32, 0, c->stream>>>(p);
+    else if (D <= 512) pyd_sweep_kernel<16><<<grid, PYD_WARPS * 32, 0, c->stream>>>(p);
+    else pyd_sweep_kernel<32><<<grid, PYD_WARPS * 32, 0, c->stream>>>(p);
+    FSGM_LAUNCHED(c);
+    return FSGM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// WTA + per-axis subpixel: one warp per pixel group, weighted sum of the direction volumes
+// ------------------------------------------------------------------------------------------------
+struct PydWtaParams {
+    const uint8_t* L[8]; int weight[8]; int n_dirs;
+    int W, H, Sx, Sy, subpixel;
+    uint16_t* Sp16; uint32_t* bestD; uint32_t* minC; double* mvSub;
+};
+
+__global__ void __launch_bounds__(PYD_WARPS * 32)
+pyd_wta_kernel(const PydWtaParams prm)
+{
+    __shared__ uint16_t sums[PYD_WARPS][PYD_MAXD];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int Sy = prm.Sy, Sx = prm.Sx, D = Sx * Sy, R = prm.n_dirs;
+    const size_t N = (size_t)prm.W * prm.H, vol = blockIdx.y * N * D;
+    const size_t p = (size_t)blockIdx.x * PYD_WARPS + wib;
+    if (p >= N) return;
+    uint16_t* s = sums[wib];
+    uint32_t key = 0xFFFFFFFFu;
+    for (int d = lane; d < D; d += 32) {
+        uint32_t a = 0;
+        for (int r = 0; r < R; ++r) a += prm.weight[r] * (uint32_t)__ldg(prm.L[r] + vol + p * D + d);
+        s[d] = (uint16_t)a;
+        if (prm.Sp16) prm.Sp16[vol + p * D + d] = (uint16_t)a;
+        key = min(key, (a << 16) | (uint32_t)d);
+    }
+    if (R == 0) key = 0;                               // totalPass == 0: Sp stays zero, argmin = 0
+    key = __reduce_min_sync(0xffffffffu, key);
+    __syncwarp();
+    if (lane != 0) return;
+    const uint32_t idx = key & 0xFFFFu, best = key >> 16;
+    const size_t gp = blockIdx.y * N + p;
+    prm.bestD[gp] = idx;
+    prm.minC[gp] = best;
+    double sx = 0.0, sy = 0.0;
+    if (prm.subpixel && R > 0) {
+        const int lx = idx / Sy, ly = idx - lx * Sy;
+        const double c0 = (double)best;
+        if (ly > 0 && ly < Sy - 1) {
+            const double a = s[idx - 1], b = s[idx + 1];
+            sy = (b < a) ? __ddiv_rn(__ddiv_rn(__dsub_rn(b, a), __dsub_rn(c0, a)), 2.0)
+                         : __ddiv_rn(__ddiv_rn(__dsub_rn(b, a), __dsub_rn(c0, b)), 2.0);
+        }
+        if (lx > 0 && lx < Sx - 1) {
+            const double a = s[idx - Sy], b = s[idx + Sy];
+            sx = (b < a) ? __ddiv_rn(__ddiv_rn(__dsub_rn(b, a), __dsub_rn(c0, a)), 2.0)
+                         : __ddiv_rn(__ddiv_rn(__dsub_rn(b, a), __dsub_rn(c0, b)), 2.0);
+        }
+    }
+    prm.mvSub[blockIdx.y * 2 * N + p] = sx;
+    prm.mvSub[blockIdx.y * 2 * N + N + p] = sy;
+}
+
+int launch_pyd_wta(fsgm_ctx* c, int n, uint8_t* const* Lvols, const int* weights, int n_dirs, int W, int H, int Sx, int Sy,
+                   int subpixel, uint16_t* Sp16, uint32_t* bestD, uint32_t* minC, double* mvSub)
+{
+    StageScope ss(c, ST_PYD_WTA);
+    PydWtaParams p{};
+    for (int k = 0; k < n_dirs; ++k) { p.L[k] = Lvols[k]; p.weight[k] = weights[k]; }
+    p.n_dirs = n_dirs; p.W = W; p.H = H; p.Sx = Sx; p.Sy = Sy; p.subpixel = subpixel;
+    p.Sp16 = Sp16; p.bestD = bestD; p.minC = minC; p.mvSub = mvSub;
+    const size_t N = (size_t)W * H;
+    dim3 grid((unsigned)((N + PYD_WARPS - 1) / PYD_WARPS), n);
+    pyd_wta_kernel<<<grid, PYD_WARPS * 32, 0, c->stream>>>(p);
+    FSGM_LAUNCHED(c);
+    return FSGM_OK;
+}
+
+}  // namespace fsgm

@@ -107,6 +107,34 @@ FSGM_API int fsgm_epi_aggregate_dev(fsgm_ctx* ctx, int n_pairs, const uint8_t* d
                            int dMax, int P1, int P2, const fsgm_epi_opts* opts, uint16_t* d_Sp /* may be NULL */,
                            const double* d_offsetFromPosD0, double vMax, uint32_t* d_bestD, uint32_t* d_minC);
 
+/* ---- gateway 2: calc_pyd_cost_sgm (calc_pyd_cost_sgm.cpp:439-510) ------------------------------
+ * [bestD, minC, mvSub] = calc_pyd_cost_sgm(I1, I2, preMv, halfSearchWinSizeX, halfSearchWinSizeY, aggHalfWinSize,
+ *                                          subPixelRefine, P1, P2, enableDiagnalPath, totalPass, adpativeP2)
+ * preMv f64[2][mvHeight][mvWidth] with its own stride mvWidth >= width (:388, :493-494).
+ * bestD u32[H][W] = raw label sx*(2ry+1)+sy; minC u32[H][W]; mvSub f64[2][H][W] (zeros unless subPixelRefine).
+ * Labels are ordered offx-outer (:392-393).  totalPass is the reference's loop bound (0..16 accepted). */
+FSGM_API int fsgm_calc_pyd_cost_sgm(fsgm_ctx* ctx, const uint8_t* I1, const uint8_t* I2, int width, int height,
+                           const double* preMv, int mvWidth, int mvHeight,
+                           int halfSearchWinSizeX, int halfSearchWinSizeY, int aggHalfWinSize, int subPixelRefine,
+                           int P1, int P2, int enableDiagnalPath, int totalPass, int adpativeP2,
+                           uint32_t* bestD, uint32_t* minC, double* mvSub);
+FSGM_API int fsgm_calc_pyd_cost_sgm_dev(fsgm_ctx* ctx, int n_pairs, const uint8_t* d_I1, const uint8_t* d_I2, int width, int height,
+                           const double* d_preMv, int mvWidth, int mvHeight,
+                           int halfSearchWinSizeX, int halfSearchWinSizeY, int aggHalfWinSize, int subPixelRefine,
+                           int P1, int P2, int enableDiagnalPath, int totalPass, int adpativeP2,
+                           uint32_t* d_bestD, uint32_t* d_minC, double* d_mvSub);
+/* stage seams: calc_cost (:374-437), one sweep of sgm2d (:142-296, step :34-89), sweeps + WTA + subpixel (:114-372) */
+FSGM_API int fsgm_pyd_cost_dev(fsgm_ctx* ctx, int n_pairs, const uint32_t* d_cen1, const uint32_t* d_cen2, int width, int height,
+                           const double* d_preMv, int mvWidth, int mvHeight, int aggHalfWinSize,
+                           int halfSearchWinSizeX, int halfSearchWinSizeY, uint8_t* d_C);
+FSGM_API int fsgm_pyd_sweep_dev(fsgm_ctx* ctx, int n_pairs, const uint8_t* d_C, const uint8_t* d_I1, const double* d_preMv,
+                           int mvWidth, int mvHeight, int width, int height, int halfSearchWinSizeX, int halfSearchWinSizeY,
+                           int P1, int P2, int adpativeP2, int direction, uint8_t* d_L);
+FSGM_API int fsgm_pyd_aggregate_dev(fsgm_ctx* ctx, int n_pairs, const uint8_t* d_C, const uint8_t* d_I1, const double* d_preMv,
+                           int mvWidth, int mvHeight, int width, int height, int halfSearchWinSizeX, int halfSearchWinSizeY,
+                           int subPixelRefine, int P1, int P2, int enableDiagnalPath, int totalPass, int adpativeP2,
+                           uint16_t* d_Sp /* may be NULL */, uint32_t* d_bestD, uint32_t* d_minC, double* d_mvSub);
+
 #ifdef __cplusplus
 }
 #endif

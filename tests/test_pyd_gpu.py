@@ -1,0 +1,113 @@
+"""GPU parity: pyramidal 2-D-window path (calc_pyd_cost_sgm) through the C ABI vs golden vectors and the CPU oracle."""
+import os
+
+import numpy as np
+import pytest
+
+from fsgm_b200 import synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _t(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _oracle_pyd(oracle, *a, **k):
+    return (oracle.ref_pyd if oracle.have_ref("pyd") else oracle.port_pyd)(*a, **k)
+
+
+@pytest.mark.parametrize("name", ["pyd_a", "pyd_b", "pyd_c"])
+def test_pyd_vs_golden(ctx, name):
+    import torch
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    g = {k: z[k] for k in z.files}
+    rx, ry, agg, sub = int(g["rx"]), int(g["ry"]), int(g["agg"]), int(g["sub"])
+    P1, P2, diag, passes, adp = int(g["P1"]), int(g["P2"]), int(g["diag"]), int(g["passes"]), int(g["adaptive"])
+    H, W = g["I1"].shape
+    D = (2 * rx + 1) * (2 * ry + 1)
+    # whole gateway, host arrays
+    bestD, minC, mvSub = ctx.calc_pyd_cost_sgm(g["I1"], g["I2"], g["preMv"], rx, ry, agg, sub, P1, P2, diag, passes, adp)
+    assert np.array_equal(minC, g["minC"])
+    assert np.array_equal(bestD, g["bestD"])
+    assert np.array_equal(mvSub, g["mvSub"])          # fp64 division is IEEE on both sides: expect bit equality
+    # stages: cost volume from our census, Sp from the golden C
+    I1, I2, mv = _t(g["I1"][None]), _t(g["I2"][None]), _t(g["preMv"][None])
+    cen1 = torch.empty((1, H, W), dtype=torch.int32, device="cuda")
+    cen2 = torch.empty_like(cen1)
+    ctx.census_dev(I1, cen1)
+    ctx.census_dev(I2, cen2)
+    Cv = torch.empty((1, H, W, D), dtype=torch.uint8, device="cuda")
+    ctx.pyd_cost_dev(cen1, cen2, mv, agg, rx, ry, Cv)
+    assert np.array_equal(Cv.cpu().numpy()[0], g["C"])
+    Sp = torch.empty((1, H, W, D), dtype=torch.int16, device="cuda")
+    b = torch.empty((1, H, W), dtype=torch.int32, device="cuda")
+    m = torch.empty_like(b)
+    s = torch.empty((1, 2, H, W), dtype=torch.float64, device="cuda")
+    ctx.pyd_aggregate_dev(_t(g["C"][None]), I1, mv, rx, ry, sub, P1, P2, diag, passes, adp, b, m, s, Sp=Sp)
+    assert np.array_equal(Sp.cpu().numpy().view(np.uint16)[0], g["Sp"])
+
+
+CASES = [  # W, H, rx, ry, agg, sub, P1, P2, diag, passes, adaptive, prior
+    (60, 40, 5, 5, 2, 1, 6, 32, 1, 2, 0, "zero"),        # reference defaults (pyramidal_sgm.m:14-22), D = 121
+    (60, 40, 4, 4, 2, 1, 6, 32, 1, 2, 0, "int"),         # BASELINE's +-4 window, D = 81
+    (45, 33, 3, 2, 2, 1, 6, 32, 1, 2, 1, "frac"),        # fractional prior, adaptive P2, D = 35
+    (45, 33, 2, 6, 1, 0, 6, 32, 0, 2, 0, "int"),         # no diagonals, 3x3 aggregation
+    (40, 30, 7, 8, 2, 1, 6, 32, 1, 1, 0, "int"),         # single pass, D = 255 (NJ = 8)
+    (32, 24, 1, 1, 0, 1, 200, 250, 1, 2, 0, "frac"),     # mod-256 domain, no aggregation
+    (30, 20, 2, 2, 2, 1, 6, 32, 1, 3, 0, "int"),         # totalPass = 3 repeats the reversed sweeps
+    (30, 20, 2, 2, 2, 1, 6, 32, 1, 0, 0, "int"),         # totalPass = 0: Sp stays zero
+    (24, 18, 0, 0, 2, 1, 6, 32, 1, 2, 0, "wild"),        # single label; NaN / huge prior values
+]
+
+
+@pytest.mark.parametrize("W,H,rx,ry,agg,sub,P1,P2,diag,passes,adp,prior", CASES)
+def test_pyd_vs_oracle(ctx, oracle, W, H, rx, ry, agg, sub, P1, P2, diag, passes, adp, prior):
+    fp = synth.flow_pair(W, H, seed=W + rx, umax=max(1, rx - 1), vmax=max(1, ry - 1))
+    rng = np.random.default_rng(W * 7 + H)
+    mv = np.zeros((2, H + 3, W + 5))
+    if prior == "int":
+        mv[:] = rng.integers(-3, 4, mv.shape)
+    elif prior == "frac":
+        mv[:] = rng.normal(0, 2.0, mv.shape)
+    elif prior == "wild":
+        mv[:] = rng.normal(0, 2.0, mv.shape)
+        mv[0, 2, 3], mv[1, 4, 5], mv[0, 6, 7], mv[1, 1, 1] = np.nan, 1e300, -1e300, 3e9
+    want = _oracle_pyd(oracle, fp["I1"], fp["I2"], mv, rx, ry, agg, sub, P1, P2, diag, passes, adp)
+    bestD, minC, mvSub = ctx.calc_pyd_cost_sgm(fp["I1"], fp["I2"], mv, rx, ry, agg, sub, P1, P2, diag, passes, adp)
+    assert np.array_equal(minC, want["minC"])
+    assert np.array_equal(bestD, want["bestD"])
+    assert np.array_equal(mvSub, want["mvSub"], equal_nan=True)
+    assert np.nanmax(np.abs(mvSub - want["mvSub"])) <= 1e-4 if mvSub.size else True     # the contract's tolerance
+
+
+def test_pyd_sweep_each_direction(ctx, oracle):
+    import ctypes as C
+    import torch
+    rng = np.random.default_rng(8)
+    H, W, rx, ry = 21, 29, 3, 2
+    Sx, Sy = 2 * rx + 1, 2 * ry + 1
+    D = Sx * Sy
+    Cv = rng.integers(0, 26, (H, W, D), dtype=np.uint8)
+    I1 = rng.integers(0, 256, (H, W), dtype=np.uint8)
+    mv = rng.normal(0, 1.5, (2, H, W + 2))
+    lib = oracle._port()
+    for r in range(8):
+        want = np.empty((H, W, D), np.uint8)
+        lib.orc_sweep2d(Cv.ctypes.data_as(C.c_void_p), I1.ctypes.data_as(C.c_void_p), W, H, mv.ctypes.data_as(C.c_void_p),
+                        W + 2, H, Sx, Sy, 6, 32, 1, r, want.ctypes.data_as(C.c_void_p))
+        L = torch.empty((1, H, W, D), dtype=torch.uint8, device="cuda")
+        ctx.pyd_sweep_dev(_t(Cv[None]), _t(I1[None]), _t(mv[None]), rx, ry, 6, 32, 1, r, L)
+        assert np.array_equal(L.cpu().numpy()[0], want), r
+
+
+def test_pyd_bad_arguments(ctx):
+    from fsgm_b200 import api
+    fp = synth.flow_pair(16, 12, seed=1)
+    with pytest.raises(api.FsgmError):          # prior smaller than the image
+        ctx.calc_pyd_cost_sgm(fp["I1"], fp["I2"], np.zeros((2, 12, 15)), 1, 1, 2, 1, 6, 32)
+    with pytest.raises(api.FsgmError) as e:     # 33*33 labels
+        ctx.calc_pyd_cost_sgm(fp["I1"], fp["I2"], np.zeros((2, 12, 16)), 16, 16, 2, 1, 6, 32)
+    assert e.value.code == api.FSGM_ERR_DOMAIN
