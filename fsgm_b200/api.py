@@ -73,6 +73,19 @@ def _dp(t):
     return C.c_void_p(t.data_ptr())
 
 
+class NgOpts(C.Structure):
+    _fields_ = [("seed", C.c_uint), ("rand_stream", C.c_void_p)]
+
+
+def glibc_rand(seed: int, count: int) -> np.ndarray:
+    """srand(seed); [rand() for _ in range(count)] — the library's own implementation of glibc's generator"""
+    out = np.empty(count, np.int32)
+    rc = lib().fsgm_glibc_rand_fill(C.c_uint(seed), C.c_size_t(count), out.ctypes.data_as(C.c_void_p))
+    if rc != FSGM_OK:
+        raise FsgmError(rc, "fsgm_glibc_rand_fill")
+    return out
+
+
 def epi_opts(paths=4, total_pass=2, subpixel=1, adaptive_p2=0, vz_to_disp=1) -> EpiOpts:
     return EpiOpts(paths, total_pass, subpixel, adaptive_p2, vz_to_disp)
 
@@ -232,3 +245,41 @@ class Context:
         self._ck(self._l.fsgm_pyd_aggregate_dev(self._h, n, _dp(Cvol), _dp(I1), _dp(preMv), mvW, mvH, W, H, int(rx), int(ry),
                                                 int(sub), int(P1), int(P2), int(diag), int(passes), int(adaptive), _dp(Sp),
                                                 _dp(bestD), _dp(minC), _dp(mvSub)))
+
+    # ------------------------------------------------------------------ gateway 3: calc_cost_sgm_ng
+    def calc_cost_sgm_ng(self, I1, I2, preMv=None, halfSearchWinSize=1, aggSize=2, subPixelRefine=0, P1=6, P2=32,
+                         seed=1, rand_stream=None):
+        """[minC, flow] = calc_cost_sgm_ng(...)  (calc_cost_sgm_ng.cpp:25, :484-527); the libc rand() state is an input"""
+        H, W = I1.shape
+        minC, flow = np.empty((H, W), np.uint32), np.empty((2, H, W), np.float64)
+        o = NgOpts(int(seed), None)
+        if rand_stream is not None:
+            o.rand_stream = _hp(rand_stream, np.int32, (H * W * 8,)).value
+        self._ck(self._l.fsgm_calc_cost_sgm_ng(
+            self._h, _hp(I1, np.uint8), _hp(I2, np.uint8, (H, W)), W, H, _hp(preMv, np.float64) if preMv is not None else None,
+            C.c_double(halfSearchWinSize), C.c_double(aggSize), int(subPixelRefine), int(P1), int(P2), C.byref(o),
+            _hp(minC, np.uint32), _hp(flow, np.float64)))
+        return minC, flow
+
+    def calc_cost_sgm_ng_dev(self, I1, I2, P1, P2, minC, flow, seeds=None, Sp=None, Centries=None):
+        n, H, W = I1.shape
+        sd = (C.c_uint * n)(*[int(s) for s in seeds]) if seeds is not None else None
+        self._ck(self._l.fsgm_calc_cost_sgm_ng_dev(self._h, n, _dp(I1), _dp(I2), W, H, int(P1), int(P2), sd, None,
+                                                   _dp(minC), _dp(flow), _dp(Sp), _dp(Centries)))
+
+    # ------------------------------------------------------------------ gateway 4: calc_pyd_cost_sgm_ng
+    def calc_pyd_cost_sgm_ng(self, I1, I2, preMv, halfSearchWinSize, aggSize, subPixelRefine, P1, P2):
+        """[minC, flow] = calc_pyd_cost_sgm_ng(...)  (calc_pyd_cost_sgm_ng.cpp:25, :448-523)"""
+        H, W = I1.shape
+        _, mvH, mvW = preMv.shape
+        minC, flow = np.empty((H, W), np.uint32), np.empty((2, H, W), np.float64)
+        self._ck(self._l.fsgm_calc_pyd_cost_sgm_ng(
+            self._h, _hp(I1, np.uint8), _hp(I2, np.uint8, (H, W)), W, H, _hp(preMv, np.float64), mvW, mvH,
+            int(halfSearchWinSize), int(aggSize), int(subPixelRefine), int(P1), int(P2), _hp(minC, np.uint32), _hp(flow, np.float64)))
+        return minC, flow
+
+    def calc_pyd_cost_sgm_ng_dev(self, I1, I2, preMv, r, aggSize, sub, P1, P2, minC, flow, Sp=None, cost=None, XY=None):
+        n, H, W = I1.shape
+        _, _, mvH, mvW = preMv.shape
+        self._ck(self._l.fsgm_calc_pyd_cost_sgm_ng_dev(self._h, n, _dp(I1), _dp(I2), W, H, _dp(preMv), mvW, mvH, int(r), int(aggSize),
+                                                       int(sub), int(P1), int(P2), _dp(minC), _dp(flow), _dp(Sp), _dp(cost), _dp(XY)))

@@ -1,0 +1,293 @@
+// Neighbour-guided variant — replaces calc_cost_based_on_hint(), sgm_step() and sgm2d() of the reference's
+// calc_cost_sgm_ng.cpp (:122-186, :46-98, :188-419).
+//
+// Per pixel, 108 candidate flow vectors = 4 directions x (top-2 of that direction's ring slot + 1 random) x 3x3
+// offsets; cost on the fly (5x5 census Hamming, clamped coordinates); one forward pass of 4-direction SGM over the
+// explicit (mv, cost) entries with an O(108^2) compatibility search per direction; adaptive P2 (threshold 50);
+// WTA -> flow.
+//
+// The data dependence is a single serial chain over all pixels in raster order: the hints of pixel p come from ring
+// slots last written at p-2 (L1's two-slot ring is swapped every pixel and never reset per row, :247-248,:365-367 —
+// so the first two pixels of a row are seeded by the last two of the previous row) and at (x, y-2) (row rings,
+// :371-385), and the random hints consume libc rand() in raster order (:148-149).  There is no cross-pixel
+// parallelism inside a pair, so one CTA walks one pair and pairs are spread over the SMs (batch parallel); inside
+// a pixel the 2700 census taps and the 4 x 108 x 108 compatibility tests are spread over the CTA's threads.
+// Integer-issue / latency bound; HBM traffic is negligible (the ring rows stay in L2).
+#include "fsgm_internal.h"
+
+namespace fsgm {
+
+constexpr int NGD = 108;              // DIRECTION_NUM * (N + M) * MV_PER_HINT (:194)
+constexpr int NG_THREADS = 256;
+
+struct Top2 { int mvx[2], mvy[2], cost[2]; };       // the two extra slots L[D], L[D+1] of the reference (:196)
+
+struct NgWork {                       // per-pair global scratch, zero-initialised (:204-208)
+    int*     mvrow;                   // [2][W][108][2]  candidate mvs of rows y (parity) and y-1
+    int16_t* Lrow;                    // [3][2][W][108]  path costs of L2, L3, L4 for the two live rows
+    Top2*    toprow;                  // [3][2][W]       top-2 slots of L2, L3, L4 (the reference's row rings)
+};
+
+struct NgParams {
+    const uint8_t* I1; const uint32_t* cen1; const uint32_t* cen2;
+    int* mvrow; int16_t* Lrow; Top2* toprow;            // bases; pair stride computed from W
+    const int* rand_stream;                             // optional caller-supplied rand() stream, 8 per pixel
+    const uint32_t* rng_state;                          // else: 31-word glibc TYPE_3 state per pair (after srand)
+    int W, H, P1, P2;
+    uint32_t* Sp32; int* Cent; uint32_t* minC; double* flow;
+};
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
+
+__global__ void __launch_bounds__(NG_THREADS)
+ng_kernel(const NgParams prm)
+{
+    const int W = prm.W, H = prm.H;
+    const size_t N = (size_t)W * H;
+    const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint8_t* I1 = prm.I1 + pair * N;
+    const uint32_t* cen1 = prm.cen1 + pair * N;
+    const uint32_t* cen2 = prm.cen2 + pair * N;
+    int* mvrow = prm.mvrow + (size_t)pair * 2 * W * NGD * 2;
+    int16_t* Lrow = prm.Lrow + (size_t)pair * 3 * 2 * W * NGD;
+    Top2* toprow = prm.toprow + (size_t)pair * 3 * 2 * W;
+
+    __shared__ int cmx[2][NGD], cmy[2][NGD];            // candidate mvs: [pixel parity] (cur / previous pixel)
+    __shared__ int ccost[NGD];
+    __shared__ int Lc[4][NGD];                          // this pixel's path costs, directions L1,L2,L3,L4
+    __shared__ int L1prev[NGD];                         // L1 costs of the previous pixel
+    __shared__ int pmx[3][NGD], pmy[3][NGD], pco[3][NGD];   // predecessors of L2 (x-1,y-1), L3 (x,y-1), L4 (x+1,y-1)
+    __shared__ Top2 top1[2];                            // L1's two ring slots
+    __shared__ Top2 tcur[4];                            // top-2 being built for this pixel
+    __shared__ int preMin[4];
+    __shared__ uint32_t c1win[25];
+    __shared__ int rnd[8];
+    __shared__ uint32_t rstate[31];
+    __shared__ int rf, rr;
+
+    if (tid < 2) { for (int i = 0; i < 2; ++i) { top1[tid].mvx[i] = 0; top1[tid].mvy[i] = 0; top1[tid].cost[i] = 0; } }
+    if (tid < NGD) { L1prev[tid] = 0; cmx[0][tid] = cmx[1][tid] = cmy[0][tid] = cmy[1][tid] = 0; }
+    if (tid < 31 && !prm.rand_stream) rstate[tid] = prm.rng_state[pair * 31 + tid];
+    if (tid == 0) { rf = 3; rr = 0; }                   // glibc TYPE_3: front = state + SEP_3, rear = state
+    __syncthreads();
+
+    for (int y = 0; y < H; ++y) {
+        const int curRow = (y + 1) & 1, preRow = y & 1;            // the reference's row rings start Pre=0, Cur=1
+        for (int x = 0; x < W; ++x) {
+            const size_t p = (size_t)y * W + x;
+            const int cp = (int)(p & 1);                            // parity buffer of this pixel's candidates
+            const int cur1 = (int)((p + 1) & 1);                    // L1 ring: Cur slot of this pixel
+            const bool startX = (x == 0), startY = (y == 0), startR = (x == W - 1);
+
+            // ---- phase 0: random hints, census window, predecessor rows ------------------------------
+            if (tid == 0) {
+                if (prm.rand_stream) { for (int i = 0; i < 8; ++i) rnd[i] = prm.rand_stream[(pair * N + p) * 8 + i]; }
+                else {
+                    int f = rf, r = rr;
+                    for (int i = 0; i < 8; ++i) {
+                        uint32_t v = rstate[f] + rstate[r];
+                        rstate[f] = v;
+                        rnd[i] = (int)((v >> 1) & 0x7FFFFFFFu);
+                        f = (f + 1 == 31) ? 0 : f + 1; r = (r + 1 == 31) ? 0 : r + 1;
+                    }
+                    rf = f; rr = r;
+                }
+            }
+            if (tid >= 32 && tid < 57) {
+                const int k = tid - 32;
+                c1win[k] = cen1[(size_t)clampi(y + k / 5 - 2, 0, H - 1) * W + clampi(x + k % 5 - 2, 0, W - 1)];
+            }
+            if (!startY) {
+                // predecessor slots: q=0 -> (x-1,y-1) for L2, q=1 -> (x,y-1) for L3, q=2 -> (x+1,y-1) for L4
+                for (int i = tid; i < 3 * NGD; i += NG_THREADS) {
+                    const int q = i / NGD, d = i - q * NGD, xs = x + q - 1;
+                    if (xs >= 0 && xs < W) {
+                        const size_t cell = (size_t)preRow * W + xs;
+                        pmx[q][d] = mvrow[(cell * NGD + d) * 2];
+                        pmy[q][d] = mvrow[(cell * NGD + d) * 2 + 1];
+                        pco[q][d] = Lrow[((size_t)q * 2 * W + cell) * NGD + d];
+                    }
+                }
+            }
+            __syncthreads();
+
+            // ---- phase A: 108 candidates and their costs (2 threads per candidate) --------------------
+            {
+                // every thread runs the shuffle (warp 6 is only partly populated with candidates)
+                const bool act = tid < 2 * NGD;
+                const int c = act ? (tid >> 1) : 0, half = tid & 1;
+                const int l = c / 27, i = (c % 27) / 9, off = c % 9, oy = off / 3 - 1, ox = off % 3 - 1;
+                int hx, hy;
+                if (i < 2) {
+                    // hints are read from the CURRENT ring slot before it is overwritten (:276-277): stale data
+                    const Top2& t = (l == 0) ? top1[cur1] : toprow[((size_t)(l - 1) * 2 + curRow) * W + x];
+                    hx = t.mvx[i]; hy = t.mvy[i];
+                } else {
+                    hx = rnd[2 * l] % 256 - 128; hy = rnd[2 * l + 1] % 128 - 64;
+                }
+                uint32_t s = 0;
+                const int k0 = half ? 13 : 0, k1 = act ? (half ? 25 : 13) : 0;
+                for (int k = k0; k < k1; ++k) {
+                    const int y1 = clampi(y + k / 5 - 2, 0, H - 1), x1 = clampi(x + k % 5 - 2, 0, W - 1);
+                    const int y2 = clampi((int)((uint32_t)(oy + y1) + (uint32_t)hy), 0, H - 1);
+                    const int x2 = clampi((int)((uint32_t)(ox + x1) + (uint32_t)hx), 0, W - 1);
+                    s += __popc(c1win[k] ^ __ldg(cen2 + (size_t)W * y2 + x2));
+                }
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                if (act && !half) {
+                    ccost[c] = (int)((2 * s + 25) / 50);             // (int)(1.0*s/25 + 0.5) (:177)
+                    cmx[cp][c] = (int)((uint32_t)hx + (uint32_t)ox);
+                    cmy[cp][c] = (int)((uint32_t)hy + (uint32_t)oy);
+                }
+            }
+            // previous minima (the top-1 slot of each predecessor, as unsigned char, :53)
+            if (tid == 224) preMin[0] = top1[cur1 ^ 1].cost[0] & 0xFF;
+            if (tid >= 225 && tid < 228 && !startY) {
+                const int q = tid - 225, xs = x + q - 1;
+                if (xs >= 0 && xs < W) preMin[1 + q] = toprow[((size_t)q * 2 + preRow) * W + xs].cost[0] & 0xFF;
+            }
+            __syncthreads();
+
+            // ---- phase B: the four path steps; work item = (direction, candidate) ----------------------
+            const int pixCur = I1[p];
+            for (int item = tid; item < 4 * NGD; item += NG_THREADS) {
+                const int dir = item / NGD, d = item - dir * NGD;    // 0 L1, 1 L2, 2 L3, 3 L4
+                const bool start = dir == 0 ? startX : dir == 1 ? (startX || startY) : dir == 2 ? startY : (startY || startR);
+                int out;
+                if (start) out = ccost[d];
+                else {
+                    const int* qx; const int* qy; const int* qc; int pixPre;
+                    if (dir == 0) { qx = cmx[cp ^ 1]; qy = cmy[cp ^ 1]; qc = L1prev; pixPre = I1[p - 1]; }
+                    else { qx = pmx[dir - 1]; qy = pmy[dir - 1]; qc = pco[dir - 1]; pixPre = I1[p - W + (dir - 2)]; }
+                    const int P2 = abs(pixCur - pixPre) > 50 ? prm.P2 / 8 : prm.P2;          // :101-105
+                    const uint32_t pm = (uint32_t)preMin[dir];
+                    const uint32_t far_ = (pm + (uint32_t)P2) & 0xFFu;
+                    uint32_t same = far_, near_ = far_;
+                    const int mx = cmx[cp][d], my = cmy[cp][d];
+                    for (int d2 = 0; d2 < NGD; ++d2) {
+                        const int ax = qx[d2], ay = qy[d2];
+                        const uint32_t c2 = (uint32_t)qc[d2];
+                        if (ax == mx && ay == my) same = c2 & 0xFFu;                          // last match wins (:71-72)
+                        else if ((uint32_t)(ax - mx + 2) <= 4u && (uint32_t)(ay - my + 2) <= 4u)
+                            near_ = min(near_, (c2 + (uint32_t)prm.P1) & 0xFFu);
+                    }
+                    out = ccost[d] + (int)min(min(far_, same), near_) - (int)pm;                // int, not truncated (:80)
+                }
+                Lc[dir][d] = out;
+            }
+            __syncthreads();
+
+            // ---- phase C: top-2 per direction (warp `dir`), Sp + WTA (warp 4) ---------------------------
+            if (warp < 4) {
+                const int dir = warp;
+                const bool start = dir == 0 ? startX : dir == 1 ? (startX || startY) : dir == 2 ? startY : (startY || startR);
+                // the slot being overwritten keeps whatever it held (stale mvs are part of the reference's behaviour)
+                Top2 old = (dir == 0) ? top1[cur1] : toprow[((size_t)(dir - 1) * 2 + curRow) * W + x];
+                Top2 nw = old;
+                if (start) nw.cost[0] = 0;                                                     // :281,:285,:291,...
+                else {
+                    // sequential strict-< insertion into two slots preset to 255 == the two smallest (cost, index) among
+                    // the entries below 255; missing ones are padded with (255, stale mv of slot 0) / untouched slot 1
+                    uint32_t k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
+                    for (int d = lane; d < NGD; d += 32) {
+                        const int cst = Lc[dir][d];
+                        if (cst < 255) {
+                            const uint32_t key = ((uint32_t)(cst + 1024) << 8) | (uint32_t)d;
+                            if (key < k1) { k2 = k1; k1 = key; } else if (key < k2) k2 = key;
+                        }
+                    }
+                    const uint32_t g1 = __reduce_min_sync(0xffffffffu, k1);
+                    const uint32_t g2 = __reduce_min_sync(0xffffffffu, k1 == g1 ? k2 : k1);
+                    nw.cost[0] = 255; nw.cost[1] = 255;
+                    if (g1 != 0xFFFFFFFFu) {
+                        const int d1 = g1 & 0xFF;
+                        nw.mvx[1] = old.mvx[0]; nw.mvy[1] = old.mvy[0];                        // shifted-down preset slot
+                        nw.mvx[0] = cmx[cp][d1]; nw.mvy[0] = cmy[cp][d1]; nw.cost[0] = Lc[dir][d1];
+                        if (g2 != 0xFFFFFFFFu) {
+                            const int d2 = g2 & 0xFF;
+                            nw.mvx[1] = cmx[cp][d2]; nw.mvy[1] = cmy[cp][d2]; nw.cost[1] = Lc[dir][d2];
+                        }
+                    }
+                }
+                if (lane == 0) tcur[dir] = nw;
+            } else if (warp == 4) {
+                unsigned long long key = ~0ull;
+                for (int d = lane; d < NGD; d += 32) {
+                    const uint32_t a = (uint32_t)(Lc[0][d] + Lc[2][d]) + (uint32_t)(Lc[1][d] + Lc[3][d]);   // :357-362
+                    if (prm.Sp32) prm.Sp32[(pair * N + p) * NGD + d] = a;
+                    const unsigned long long kk = ((unsigned long long)a << 32) | (uint32_t)d;
+                    key = kk < key ? kk : key;
+                }
+                for (int o = 16; o; o >>= 1) {
+                    unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+                    key = other < key ? other : key;
+                }
+                if (lane == 0) {
+                    const int d = (int)(key & 0xFFFFFFFFu);
+                    prm.minC[pair * N + p] = (uint32_t)(key >> 32);
+                    prm.flow[(size_t)pair * 2 * N + p] = (double)cmx[cp][d];
+                    prm.flow[(size_t)pair * 2 * N + N + p] = (double)cmy[cp][d];
+                }
+            } else if (prm.Cent) {
+                for (int d = tid - 160; d < NGD; d += NG_THREADS - 160) {
+                    int* e = prm.Cent + ((pair * N + p) * NGD + d) * 3;
+                    e[0] = cmx[cp][d]; e[1] = cmy[cp][d]; e[2] = ccost[d];
+                }
+            }
+            __syncthreads();
+
+            // ---- phase D: commit this pixel's state to the rings -----------------------------------------
+            {
+                const size_t cell = (size_t)curRow * W + x;
+                for (int i = tid; i < NGD; i += NG_THREADS) {
+                    mvrow[(cell * NGD + i) * 2] = cmx[cp][i];
+                    mvrow[(cell * NGD + i) * 2 + 1] = cmy[cp][i];
+                    L1prev[i] = Lc[0][i];
+                }
+                for (int i = tid; i < 3 * NGD; i += NG_THREADS) {
+                    const int q = i / NGD, d = i - q * NGD;
+                    Lrow[((size_t)q * 2 * W + cell) * NGD + d] = (int16_t)Lc[q + 1][d];
+                }
+                if (tid == 0) top1[cur1] = tcur[0];
+                if (tid >= 1 && tid < 4) toprow[((size_t)(tid - 1) * 2 + curRow) * W + x] = tcur[tid];
+            }
+            __syncthreads();
+        }
+    }
+}
+
+size_t ng_scratch_bytes(int n, int W)
+{
+    return align256((size_t)n * 2 * W * NGD * 2 * sizeof(int)) + align256((size_t)n * 3 * 2 * W * NGD * sizeof(int16_t)) +
+           align256((size_t)n * 3 * 2 * W * sizeof(Top2)) + align256((size_t)n * 31 * 4) + 1024;
+}
+
+int launch_ng(fsgm_ctx* c, int n, const uint8_t* I1, const uint32_t* cen1, const uint32_t* cen2, int W, int H, int P1, int P2,
+              const uint32_t* host_rng_states /* n x 31, host */, const int* d_rand_stream,
+              uint32_t* Sp32, int* Cent, uint32_t* minC, double* flow)
+{
+    StageScope ss(c, ST_NG);
+    NgParams p{};
+    p.I1 = I1; p.cen1 = cen1; p.cen2 = cen2; p.W = W; p.H = H; p.P1 = P1; p.P2 = P2;
+    p.Sp32 = Sp32; p.Cent = Cent; p.minC = minC; p.flow = flow; p.rand_stream = d_rand_stream;
+    uint32_t* d_state = nullptr;
+    const size_t b_mv = (size_t)n * 2 * W * NGD * 2 * sizeof(int), b_L = (size_t)n * 3 * 2 * W * NGD * sizeof(int16_t),
+                 b_top = (size_t)n * 3 * 2 * W * sizeof(Top2);
+    FSGM_TRY(arena_alloc(c, b_mv, (void**)&p.mvrow));
+    FSGM_TRY(arena_alloc(c, b_L, (void**)&p.Lrow));
+    FSGM_TRY(arena_alloc(c, b_top, (void**)&p.toprow));
+    FSGM_TRY(arena_alloc(c, (size_t)n * 31 * 4, (void**)&d_state));
+    FSGM_CUDA(c, cudaMemsetAsync(p.mvrow, 0, b_mv, c->stream));
+    FSGM_CUDA(c, cudaMemsetAsync(p.Lrow, 0, b_L, c->stream));
+    FSGM_CUDA(c, cudaMemsetAsync(p.toprow, 0, b_top, c->stream));
+    if (!d_rand_stream) {
+        FSGM_CUDA(c, cudaMemcpyAsync(d_state, host_rng_states, (size_t)n * 31 * 4, cudaMemcpyHostToDevice, c->stream));
+        FSGM_CUDA(c, cudaStreamSynchronize(c->stream));       // host_rng_states is a caller temporary
+    }
+    p.rng_state = d_state;
+    ng_kernel<<<n, NG_THREADS, 0, c->stream>>>(p);
+    FSGM_LAUNCHED(c);
+    return FSGM_OK;
+}
+
+}  // namespace fsgm

@@ -135,6 +135,43 @@ FSGM_API int fsgm_pyd_aggregate_dev(fsgm_ctx* ctx, int n_pairs, const uint8_t* d
                            int subPixelRefine, int P1, int P2, int enableDiagnalPath, int totalPass, int adpativeP2,
                            uint16_t* d_Sp /* may be NULL */, uint32_t* d_bestD, uint32_t* d_minC, double* d_mvSub);
 
+/* ---- gateway 3: calc_cost_sgm_ng (calc_cost_sgm_ng.cpp:484-527) ----------------------------------
+ * [minC, flow] = calc_cost_sgm_ng(I1, I2, preMv, halfSearchWinSize, aggSize, subPixelRefine, P1, P2)
+ * The reference reads and ignores preMv, halfSearchWinSize, aggSize and subPixelRefine (:497-503); they are accepted
+ * here (preMv may be NULL) and ignored too.  minC u32[H][W]; flow f64[2][H][W] (integer-valued).
+ * The reference draws its random hints from libc rand() (:148-149), 8 values per pixel in raster order, from whatever
+ * state the process is in.  Here that hidden state is an input: either a seed (the stream glibc's srand(seed); rand()
+ * produces — the pinned oracle uses srand(1)) or an explicit stream of 8*W*H rand() values (e.g. MSVC's). */
+typedef struct fsgm_ng_opts {
+    unsigned       seed;          /* used when rand_stream == NULL */
+    const int32_t* rand_stream;   /* HOST pointer, 8*width*height values, or NULL */
+} fsgm_ng_opts;
+FSGM_API void fsgm_ng_opts_default(fsgm_ng_opts* o);            /* {1, NULL} */
+FSGM_API int  fsgm_glibc_rand_fill(unsigned seed, size_t count, int32_t* out);   /* srand(seed); out[i] = rand() */
+FSGM_API int fsgm_calc_cost_sgm_ng(fsgm_ctx* ctx, const uint8_t* I1, const uint8_t* I2, int width, int height,
+                          const double* preMv, double halfSearchWinSize, double aggSize, int subPixelRefine,
+                          int P1, int P2, const fsgm_ng_opts* opts, uint32_t* minC, double* flow);
+/* device form over n_pairs independent pairs (one CTA per pair: the path is serial inside a pair); seeds[n_pairs] is a
+ * HOST array (NULL = all 1); d_rand_stream (device, 8*W*H per pair) overrides the seeds; d_Sp (u32 [n][N][108]) and
+ * d_Centries (int32 [n][N][108][3] = mvx,mvy,cost) are optional stage outputs */
+FSGM_API int fsgm_calc_cost_sgm_ng_dev(fsgm_ctx* ctx, int n_pairs, const uint8_t* d_I1, const uint8_t* d_I2, int width, int height,
+                          int P1, int P2, const unsigned* seeds, const int32_t* d_rand_stream,
+                          uint32_t* d_minC, double* d_flow, uint32_t* d_Sp, int32_t* d_Centries);
+
+/* ---- gateway 4: calc_pyd_cost_sgm_ng (calc_pyd_cost_sgm_ng.cpp:448-523) -------------------------
+ * [minC, flow] = calc_pyd_cost_sgm_ng(I1, I2, preMv, halfSearchWinSize, aggSize, subPixelRefine, P1, P2)
+ * preMv f64[2][mvHeight][mvWidth] (hints are clamped to its size, :392-393); candidates = 9*(2r+1)^2 with
+ * r = halfSearchWinSize (0..3 supported); aggregation radius = aggSize/2 (:490). */
+FSGM_API int fsgm_calc_pyd_cost_sgm_ng(fsgm_ctx* ctx, const uint8_t* I1, const uint8_t* I2, int width, int height,
+                          const double* preMv, int mvWidth, int mvHeight, int halfSearchWinSize, int aggSize,
+                          int subPixelRefine, int P1, int P2, uint32_t* minC, double* flow);
+/* optional stage outputs: d_Sp u32 [n][N][D]; d_cost u8 [n][N][D]; d_XY int32 [n][N][2][9][2r+1] (entry mv factored as
+ * X[h][ox], Y[h][oy]) */
+FSGM_API int fsgm_calc_pyd_cost_sgm_ng_dev(fsgm_ctx* ctx, int n_pairs, const uint8_t* d_I1, const uint8_t* d_I2, int width, int height,
+                          const double* d_preMv, int mvWidth, int mvHeight, int halfSearchWinSize, int aggSize,
+                          int subPixelRefine, int P1, int P2, uint32_t* d_minC, double* d_flow,
+                          uint32_t* d_Sp, uint8_t* d_cost, int32_t* d_XY);
+
 #ifdef __cplusplus
 }
 #endif

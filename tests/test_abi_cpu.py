@@ -50,3 +50,14 @@ def test_product_never_touches_oracle():
 def test_sass_is_sm100a():
     out = subprocess.run(["cuobjdump", "-lelf", os.path.join(ROOT, "fsgm_b200", "libfsgm.so")], capture_output=True, text=True).stdout
     assert "sm_100a" in out
+
+
+def test_glibc_rand_matches_libc():
+    """The library's own implementation of glibc's TYPE_3 generator against the process's libc (srand/rand)."""
+    import numpy as np
+    from fsgm_b200 import api
+    libc = ctypes.CDLL(None)
+    for seed in (1, 0, 42, 2 ** 31 + 5):
+        libc.srand(ctypes.c_uint(seed))
+        want = np.array([libc.rand() for _ in range(2000)], np.int32)
+        assert np.array_equal(api.glibc_rand(seed, 2000), want), seed
