@@ -151,7 +151,9 @@ static int epi_pipeline_dev(fsgm_ctx* c, int n, const uint8_t* I1, const uint8_t
     FSGM_TRY(launch_census(c, n, I1, W, H, cen1));
     FSGM_TRY(launch_census(c, n, I2, W, H, cen2));
     FSGM_TRY(launch_vz_table(c, D, vMax, vz));
-    FSGM_TRY(launch_epi_cost(c, n, vz, cen1, cen2, W, H, D, vMax, Pd0, dirn, O, raw, C));
+    bool fused = false;
+    FSGM_TRY(launch_epi_cost_fused(c, n, vz, cen1, cen2, W, H, D, Pd0, dirn, O, C, &fused));
+    if (!fused) FSGM_TRY(launch_epi_cost(c, n, vz, cen1, cen2, W, H, D, vMax, Pd0, dirn, O, raw, C));
     FSGM_TRY(launch_sweeps(c, n, C, I1, W, H, D, P1, P2, o.adaptive_p2 ? 25 : 0, /*cmax=*/24, dirs, nd, L));
     FSGM_TRY(launch_epi_wta(c, n, L, nd, W, H, D, o.subpixel, o.vz_to_disp, O, vMax, nullptr, bestD, minC));
     return FSGM_OK;
@@ -283,6 +285,11 @@ int fsgm_epi_cost_dev(fsgm_ctx* c, int n, const uint32_t* d_cen1, const uint32_t
     FSGM_TRY(arena_get(c, (size_t)D, &vz));
     if (!raw) FSGM_TRY(arena_get(c, n * V, &raw));
     FSGM_TRY(launch_vz_table(c, D, vMax, vz));
+    if (!d_raw) {                                   // nobody wants the pre-box volume: fused kernel when it applies
+        bool fused = false;
+        FSGM_TRY(launch_epi_cost_fused(c, n, vz, d_cen1, d_cen2, W, H, D, d_Pd0, d_dir, d_O, d_C, &fused));
+        if (fused) return FSGM_OK;
+    }
     return launch_epi_cost(c, n, vz, d_cen1, d_cen2, W, H, D, vMax, d_Pd0, d_dir, d_O, raw, d_C);
 }
 
@@ -332,10 +339,14 @@ int fsgm_calc_cost_sgm_dev(fsgm_ctx* c, int n, const uint8_t* d_I1, const uint8_
     FSGM_CUDA(c, cudaSetDevice(c->device));
     int dirs[8];
     const int nd = enabled_dirs(o, dirs);
-    // process the batch in chunks that keep the scratch arena under ~1/3 of the device memory
-    size_t free_b = 0, total_b = 0;
-    FSGM_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
-    const size_t budget = std::max(c->arena_bytes, (free_b + c->arena_bytes) / 3);
+    // process the batch in chunks that keep the scratch arena under ~1/3 of the device memory (queried once per
+    // context: cudaMemGetInfo is a slow, synchronising call)
+    if (!c->mem_total) {
+        size_t free_b = 0;
+        FSGM_CUDA(c, cudaMemGetInfo(&free_b, &c->mem_total));
+        c->mem_budget = free_b / 3;
+    }
+    const size_t budget = std::max(c->arena_bytes, c->mem_budget);
     const size_t per_pair = epi_scratch_bytes(1, W, H, D, nd, true);
     int chunk = (int)std::min<size_t>(n, std::max<size_t>(1, budget / per_pair));
     FSGM_TRY(arena_reserve(c, epi_scratch_bytes(chunk, W, H, D, nd, true)));

@@ -175,4 +175,144 @@ int launch_epi_cost(fsgm_ctx* c, int n, const double* d_vz, const uint32_t* cen1
     return FSGM_OK;
 }
 
+
+
+// =====================================================================================================
+// Fused cost kernel: raw Hamming cost and the 5x5 box filter in one pass, the raw volume never touches HBM.
+//
+// A CTA owns a strip of FC_TX output columns and marches down FC_TY rows.  Per image row it (1) evaluates the raw
+// cost of the FC_TX+4 columns (2-px halo, replicate border = clamped coordinates) for all D labels into shared
+// memory, (2) forms the horizontal 5-sums, keeps them in a 5-row shared-memory ring and, once five rows are in,
+// emits the vertical sum normalised to (2*s+25)/50 as u8, label-contiguous.  Redundant work: (TX+4)/TX * (TY+4)/TY.
+//
+// Rounding: the reference needs clamp((int)round(v), 0, hi) with C round() (half away from zero) and the x86
+// out-of-range conversion (cvttsd2si -> INT_MIN -> clamped to 0).  Working on w = 2v (exact: the per-pixel constants
+// are doubled once, and scaling by two commutes with every IEEE rounding in bx + (off*vz)*ux):
+//   v >= 0:  round(v) = floor(v + 0.5) = (floor(w) + 1) >> 1     (integer identity, no double rounding)
+//   v <  0:  round(v) <= 0, clamps to 0                            (cvt.rmi.u32 saturates negatives to 0 -> 0)
+//   NaN   :  INT_MIN on x86, clamps to 0                           (cvt of NaN gives 0 -> 0)
+//   round(v) >= 2^31, i.e. w >= 2^32 - 1: INT_MIN on x86, clamps to 0   (cvt.rmi.u32 saturates to 0xFFFFFFFF, +1 wraps to 0)
+// so one unsigned conversion, an add, a shift and an unsigned min reproduce all of it — except NaN, for which the
+// hardware conversion does not return 0.  NaN can only appear when an input is non-finite or |offset| is so large
+// that offset*vz overflows (inf*0); such pixels are flagged while staging and take a checked path.
+constexpr int FC_TX = 32, FC_TY = 64, FC_THREADS = 256;
+
+__device__ __forceinline__ uint32_t ref_round_clamp_w(double w, uint32_t hi)
+{
+    const uint32_t f = __double2uint_rd(w);
+    return min((f + 1u) >> 1, hi);
+}
+
+template <int D4>      // D = 4*D4 labels, D4 in {16, 32, 64}
+__global__ void __launch_bounds__(FC_THREADS)
+epi_cost_fused_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restrict__ cen2,
+                      const double* __restrict__ Pd0, const double* __restrict__ dirn, const double* __restrict__ O,
+                      const double* __restrict__ vz, int W, int H, uint8_t* __restrict__ C)
+{
+    constexpr int D = 4 * D4, NPIX = FC_TX + 4, IPT = FC_THREADS / D4;     // IPT pixels are processed per pass
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t* raw_row = reinterpret_cast<uint32_t*>(smem_raw);                              // [NPIX][D4]
+    uint32_t* hring = raw_row + NPIX * D4;                                                  // [5][FC_TX][D4]
+    double* geo = reinterpret_cast<double*>(hring + 5 * FC_TX * D4);                        // [NPIX][5]
+    uint32_t* gcen = reinterpret_cast<uint32_t*>(geo + NPIX * 5);                           // [NPIX]
+    uint32_t* gslow = gcen + NPIX;                                                          // [NPIX] NaN-capable pixel
+
+    const size_t N = (size_t)W * H;
+    const int pair = blockIdx.z, x0 = blockIdx.x * FC_TX, y0 = blockIdx.y * FC_TY;
+    const int tid = threadIdx.x, q = tid % D4, i0 = tid / D4;
+    const uint32_t* c2 = cen2 + pair * N;
+    const double* PdX = Pd0 + (size_t)pair * 2 * N; const double* PdY = PdX + N;
+    const double* DrX = dirn + (size_t)pair * 2 * N; const double* DrY = DrX + N;
+    const double* Op = O + pair * N;
+    uint32_t* Cout = reinterpret_cast<uint32_t*>(C + pair * N * D);
+    const double vz0 = vz[4 * q], vz1 = vz[4 * q + 1], vz2 = vz[4 * q + 2], vz3 = vz[4 * q + 3];
+    const int yend = min(y0 + FC_TY, H);
+
+    for (int r = y0 - 2; r < yend + 2; ++r) {
+        const int yc = min(max(r, 0), H - 1);
+        // stage the strip's geometry for this row
+        if (tid < NPIX) {
+            const int xc = min(max(x0 - 2 + tid, 0), W - 1);
+            const size_t p = (size_t)yc * W + xc;
+            // doubled constants: w = 2*(b + (off*vz)*u) = 2b + ((2 off)*vz)*u exactly
+            geo[tid * 5 + 0] = __dmul_rn(__dsub_rn(PdX[p], 1.0), 2.0); geo[tid * 5 + 1] = __dmul_rn(__dsub_rn(PdY[p], 1.0), 2.0);
+            geo[tid * 5 + 2] = DrX[p]; geo[tid * 5 + 3] = DrY[p]; geo[tid * 5 + 4] = __dmul_rn(Op[p], 2.0);
+            gcen[tid] = cen1[pair * N + p];
+            const double a0 = PdX[p], a1 = PdY[p], a2 = DrX[p], a3 = DrY[p], a4 = Op[p];
+            const bool fin = isfinite(a0) && isfinite(a1) && isfinite(a2) && isfinite(a3) && fabs(a4) <= 1e300;
+            gslow[tid] = fin ? 0u : 1u;
+        }
+        __syncthreads();
+        // (1) raw cost of NPIX pixels x D labels
+        for (int i = i0; i < NPIX; i += IPT) {
+            const double bx = geo[i * 5], by = geo[i * 5 + 1], ux = geo[i * 5 + 2], uy = geo[i * 5 + 3], off = geo[i * 5 + 4];
+            const uint32_t c1 = gcen[i];
+            const bool slow = gslow[i] != 0;           // uniform across the threads that share pixel i
+            uint32_t packed = 0;
+            const double vzs[4] = {vz0, vz1, vz2, vz3};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const double t = __dmul_rn(off, vzs[j]);
+                const double wx = __dadd_rn(bx, __dmul_rn(t, ux)), wy = __dadd_rn(by, __dmul_rn(t, uy));
+                uint32_t x2 = ref_round_clamp_w(wx, (uint32_t)(W - 1));
+                uint32_t y2 = ref_round_clamp_w(wy, (uint32_t)(H - 1));
+                if (slow) { if (wx != wx) x2 = 0; if (wy != wy) y2 = 0; }
+                packed |= (uint32_t)__popc(c1 ^ __ldg(c2 + (y2 * (uint32_t)W + x2))) << (8 * j);
+            }
+            raw_row[i * D4 + q] = packed;
+        }
+        __syncthreads();
+        // (2) horizontal 5-sum -> ring; vertical 5-sum -> output row r-2
+        const int slot = (r + 10) % 5;
+        for (int xl = i0; xl < FC_TX; xl += IPT) {
+            const uint32_t* rr = raw_row + xl * D4 + q;
+            const uint32_t h = rr[0] + rr[D4] + rr[2 * D4] + rr[3 * D4] + rr[4 * D4];      // bytes <= 120: no carries
+            hring[(slot * FC_TX + xl) * D4 + q] = h;
+            const int yo = r - 2, xo = x0 + xl;
+            if (yo >= y0 && xo < W) {
+                uint32_t lo = h & 0x00FF00FFu, hi = (h >> 8) & 0x00FF00FFu;
+#pragma unroll
+                for (int k = 1; k < 5; ++k) {
+                    const uint32_t v = hring[(((slot + k) % 5) * FC_TX + xl) * D4 + q];
+                    lo += v & 0x00FF00FFu; hi += (v >> 8) & 0x00FF00FFu;
+                }
+                Cout[((size_t)yo * W + xo) * D4 + q] = box_norm4(lo, hi);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+static size_t fused_cost_smem(int D4)
+{
+    return (size_t)(FC_TX + 4) * D4 * 4 + (size_t)5 * FC_TX * D4 * 4 + (size_t)(FC_TX + 4) * 5 * 8 + (size_t)(FC_TX + 4) * 8 + 64;
+}
+
+// returns FSGM_OK and sets *done = true if the fused kernel handles this label count
+int launch_epi_cost_fused(fsgm_ctx* c, int n, const double* d_vz, const uint32_t* cen1, const uint32_t* cen2, int W, int H, int D,
+                          const double* Pd0, const double* dirn, const double* O, uint8_t* C, bool* done)
+{
+    *done = false;
+    if (D != 64 && D != 128 && D != 256) return FSGM_OK;
+    if ((size_t)W * H >= (size_t)1 << 31) return FSGM_OK;
+    StageScope ss(c, ST_EPI_COST);
+    const int D4 = D / 4;
+    const size_t smem = fused_cost_smem(D4);
+    dim3 grid((W + FC_TX - 1) / FC_TX, (H + FC_TY - 1) / FC_TY, n);
+#define FSGM_FC(D4V)                                                                                              \
+    do {                                                                                                          \
+        static bool attr_set = false;                                                                             \
+        if (!attr_set) {                                                                                          \
+            FSGM_CUDA(c, cudaFuncSetAttribute(epi_cost_fused_kernel<D4V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            attr_set = true;                                                                                      \
+        }                                                                                                         \
+        epi_cost_fused_kernel<D4V><<<grid, FC_THREADS, smem, c->stream>>>(cen1, cen2, Pd0, dirn, O, d_vz, W, H, C);    \
+    } while (0)
+    if (D4 == 16) FSGM_FC(16); else if (D4 == 32) FSGM_FC(32); else FSGM_FC(64);
+#undef FSGM_FC
+    FSGM_LAUNCHED(c);
+    *done = true;
+    return FSGM_OK;
+}
+
 }  // namespace fsgm

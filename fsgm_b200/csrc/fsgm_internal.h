@@ -30,6 +30,7 @@ struct fsgm_ctx {
     size_t arena_top = 0;
     uint64_t launches = 0;
     int sm_count = 0;
+    size_t mem_total = 0, mem_budget = 0;   // cudaMemGetInfo, queried once
     std::string err;
     // profiling
     bool profiling = false;
@@ -85,6 +86,8 @@ inline bool dir_enabled(int r, int total_pass, bool diag) {
 
 // ---- kernel launchers (definitions in the .cu files) -------------------------------------------
 int launch_census(fsgm_ctx* c, int n_images, const uint8_t* img, int W, int H, uint32_t* cen);
+int launch_epi_cost_fused(fsgm_ctx* c, int n, const double* d_vz, const uint32_t* cen1, const uint32_t* cen2, int W, int H, int D,
+                          const double* Pd0, const double* dirn, const double* O, uint8_t* C, bool* done);
 int launch_vz_table(fsgm_ctx* c, int D, double vMax, double* d_vz);
 int launch_epi_cost(fsgm_ctx* c, int n, const double* d_vz, const uint32_t* cen1, const uint32_t* cen2, int W, int H, int D, double vMax,
                     const double* Pd0, const double* dirn, const double* O, uint8_t* raw, uint8_t* C);

@@ -131,3 +131,34 @@ def test_bad_arguments(ctx):
     assert e.value.code == api.FSGM_ERR_DOMAIN
     with pytest.raises(api.FsgmError):
         ctx.calc_cost_sgm(p["I1"], p["I2"], 8, 0.3, p["Pd0"], p["dirn"], p["O"], 6, 64, opts=api.epi_opts(paths=5))
+
+
+@pytest.mark.parametrize("W,H,D", [(75, 70, 64), (45, 67, 128), (40, 66, 256)])
+def test_fused_cost_kernel_wild_geometry(ctx, oracle, W, H, D):
+    """Fused raw+box kernel (no raw output requested) incl. NaN / huge / negative / exact-tie geometry."""
+    import torch
+    p = synth.epipolar_pair(W, H, D, seed=D)
+    rng = np.random.default_rng(D)
+    O = p["O"].copy()
+    O[0, :4] = [np.nan, 1e300, -1e300, 3e9]
+    O[1, :5] = [-5.0, 2.0 ** 31, -(2.0 ** 31) - 7, np.inf, -np.inf]
+    O[H // 2, W // 2] = 2.0 ** 31 / 0.1
+    Pd0 = p["Pd0"] + rng.normal(0, 0.3, p["Pd0"].shape)
+    Pd0[0, 2, :6] = [0.5, 1.5, -2.5, 2.5, 3.5, W + 0.5]                # exact .5 ties after the -1
+    Pd0[1, 3, :4] = [2147483648.5, 2147483649.0, -1e9, 0.49999999999999994 + 1]
+    cen1, cen2 = oracle.port_census(p["I1"]), oracle.port_census(p["I2"])
+    import ctypes as C
+    lib = oracle._port()
+    raw = np.empty((H, W, D), np.uint8); want = np.empty((H, W, D), np.uint8)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    lib.orc_epi_cost_raw(vp(cen1), vp(cen2), W, H, D, C.c_double(0.3), vp(Pd0), vp(p["dirn"]), vp(O), vp(raw))
+    lib.orc_box5(vp(raw), W, H, D, vp(want))
+    Cv = torch.empty((1, H, W, D), dtype=torch.uint8, device="cuda")
+    ctx.epi_cost_dev(_t(cen1.view(np.int32)[None]), _t(cen2.view(np.int32)[None]), D, 0.3, _t(Pd0[None]), _t(p["dirn"][None]),
+                     _t(O[None]), None, Cv)
+    assert np.array_equal(Cv.cpu().numpy()[0], want)
+    # and the unfused pair of kernels on the same inputs
+    raw_g = torch.empty_like(Cv); Cv2 = torch.empty_like(Cv)
+    ctx.epi_cost_dev(_t(cen1.view(np.int32)[None]), _t(cen2.view(np.int32)[None]), D, 0.3, _t(Pd0[None]), _t(p["dirn"][None]),
+                     _t(O[None]), raw_g, Cv2)
+    assert np.array_equal(raw_g.cpu().numpy()[0], raw) and np.array_equal(Cv2.cpu().numpy()[0], want)
