@@ -52,6 +52,13 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_stop(self):
+        self.t1 = time.time()
 
     def __enter__(self):
         try:
@@ -66,7 +73,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def __exit__(self, *a):
         if self.proc:
@@ -78,7 +85,10 @@ class ClockSampler:
 
     def summary(self):
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        rows = [r for (t, r) in self.rows if self.t0 is None or (self.t0 <= t <= (self.t1 or t) + 0.15)]
+        if not rows:                      # timed region shorter than the sampling period: fall back to every sample
+            rows = [r for (_, r) in self.rows]
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
             except Exception:
@@ -205,19 +215,21 @@ def run_ours(args):
                                 opts=opts, out=out_views)
 
     # ---- device-resident throughput -------------------------------------------------------------
-    for _ in range(max(3, args.warmup)):
-        step_dev()
-    barrier()
-    ctx.profile(True)
-    ctx.profile_reset()
-    l0 = ctx.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
+    with ClockSampler(local) as clocks:           # nvidia-smi needs ~1 s to start: launch it before the warm-up
+        for _ in range(max(3, args.warmup)):
+            step_dev()
+        barrier()
+        ctx.profile(True)
+        ctx.profile_reset()
+        l0 = ctx.launch_count
+        clocks.mark_start()
         e0.record()
         for _ in range(args.steps):
             step_dev()
         e1.record()
         torch.cuda.synchronize()
+        clocks.mark_stop()
     ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -289,7 +301,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--pairs", type=int, default=16, help="pairs per step per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])

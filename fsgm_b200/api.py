@@ -205,6 +205,18 @@ class Context:
                                                 C.byref(opts) if opts is not None else None, _dp(Sp), _dp(O),
                                                 C.c_double(vMax), _dp(bestD), _dp(minC)))
 
+    def epi_partial_dev(self, Cvol, I1, P1, P2, directions, Sp_partial, adaptive_p2=0):
+        """sweeps for `directions` summed into a u16 partial volume (Cvol: [H][W][D] u8, single pair)"""
+        H, W, D = Cvol.shape
+        dirs = (C.c_int * max(1, len(directions)))(*[int(d) for d in directions])
+        self._ck(self._l.fsgm_epi_partial_dev(self._h, _dp(Cvol), _dp(I1), W, H, D, int(P1), int(P2), int(adaptive_p2),
+                                              dirs, len(directions), _dp(Sp_partial)))
+
+    def epi_wta_sp_dev(self, Sp, next0, D, O, vMax, bestD, minC, subpixel=1, vz_to_disp=1):
+        n_pixels = Sp.numel() // D
+        self._ck(self._l.fsgm_epi_wta_sp_dev(self._h, _dp(Sp), _dp(next0), C.c_size_t(n_pixels), int(D), int(subpixel),
+                                             int(vz_to_disp), _dp(O), C.c_double(vMax), _dp(bestD), _dp(minC)))
+
     # ------------------------------------------------------------------ gateway 2: calc_pyd_cost_sgm
     def calc_pyd_cost_sgm(self, I1, I2, preMv, halfSearchWinSizeX, halfSearchWinSizeY, aggHalfWinSize, subPixelRefine,
                           P1, P2, enableDiagnalPath=1, totalPass=2, adpativeP2=0):

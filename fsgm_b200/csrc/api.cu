@@ -325,6 +325,40 @@ int fsgm_epi_aggregate_dev(fsgm_ctx* c, int n, const uint8_t* d_C, const uint8_t
     return launch_epi_wta(c, n, L, nd, W, H, D, o.subpixel, o.vz_to_disp, d_O, vMax, d_Sp, d_bestD, d_minC);
 }
 
+// Direction-split building blocks (one large pair, the R directions spread over GPUs):
+//  fsgm_epi_partial_dev : sweeps for the listed directions, summed into a u16 partial volume [N][D]
+//  fsgm_epi_wta_sp_dev  : WTA/subpixel/vz over a slab of an already reduced u16 volume
+int fsgm_epi_partial_dev(fsgm_ctx* c, const uint8_t* d_C, const uint8_t* d_I1, int W, int H, int D, int P1, int P2,
+                         int adaptive_p2, const int* directions, int n_dirs, uint16_t* d_Sp_partial)
+{
+    FSGM_TRY(check_dims(c, 1, W, H, D));
+    if (!d_C || !d_Sp_partial || !directions || (adaptive_p2 && !d_I1)) return fail(c, FSGM_ERR_ARG, "null pointer");
+    if (n_dirs < 0 || n_dirs > 8) return fail(c, FSGM_ERR_ARG, "n_dirs must be 0..8");
+    for (int k = 0; k < n_dirs; ++k)
+        if (directions[k] < 0 || directions[k] > 7) return fail(c, FSGM_ERR_ARG, "direction must be 0..7");
+    FSGM_CUDA(c, cudaSetDevice(c->device));
+    const size_t N = (size_t)W * H, V = N * D;
+    if (n_dirs == 0) { FSGM_CUDA(c, cudaMemsetAsync(d_Sp_partial, 0, V * 2, c->stream)); return FSGM_OK; }
+    FSGM_TRY(arena_reserve(c, (size_t)n_dirs * align256(V) + 2 * align256(N * 4)));
+    ArenaScope scope(c);
+    uint8_t* L[8]; uint32_t *b, *m;
+    for (int k = 0; k < n_dirs; ++k) FSGM_TRY(arena_get(c, V, &L[k]));
+    FSGM_TRY(arena_get(c, N, &b));
+    FSGM_TRY(arena_get(c, N, &m));
+    FSGM_TRY(launch_sweeps(c, 1, d_C, d_I1, W, H, D, P1, P2, adaptive_p2 ? 25 : 0, 24, directions, n_dirs, L));
+    return launch_epi_wta(c, 1, L, n_dirs, W, H, D, 0, 0, nullptr, 0.0, d_Sp_partial, b, m);
+}
+
+int fsgm_epi_wta_sp_dev(fsgm_ctx* c, const uint16_t* d_Sp, const uint16_t* d_next_label0, size_t n_pixels, int D,
+                        int subpixel, int vz_to_disp, const double* d_O, double vMax, uint32_t* d_bestD, uint32_t* d_minC)
+{
+    if (!c) return FSGM_ERR_ARG;
+    if (!d_Sp || !d_bestD || !d_minC || (vz_to_disp && !d_O) || n_pixels < 1) return fail(c, FSGM_ERR_ARG, "bad argument");
+    if (D < 1 || D > 512) return fail(c, FSGM_ERR_DOMAIN, "dMax must be in 1..512");
+    FSGM_CUDA(c, cudaSetDevice(c->device));
+    return launch_sp_wta(c, d_Sp, d_next_label0, n_pixels, D, subpixel, vz_to_disp, d_O, vMax, d_bestD, d_minC);
+}
+
 // ---------------------------------------------------------------------------------------------
 // gateway 1: calc_cost_sgm
 // ---------------------------------------------------------------------------------------------

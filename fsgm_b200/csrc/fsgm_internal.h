@@ -101,6 +101,9 @@ bool sweep_needs_wrap(int P1, int P2, int cmax);
 int launch_epi_wta(fsgm_ctx* c, int n, uint8_t* const* Lvols, int n_dirs, int W, int H, int D, int subpixel,
                    int vz_to_disp, const double* O, double vMax, uint16_t* Sp16, uint32_t* bestD, uint32_t* minC);
 
+int launch_sp_wta(fsgm_ctx* c, const uint16_t* Sp, const uint16_t* next0, size_t npix, int D, int subpixel,
+                  int vz_to_disp, const double* O, double vMax, uint32_t* bestD, uint32_t* minC);
+
 // ---- pyramidal 2-D-window variant (pyd.cu) ----------------------------------------------------------
 int launch_pyd_cost(fsgm_ctx* c, int n, const uint32_t* cen1, const uint32_t* cen2, int W, int H,
                     const double* preMv, int mvW, int mvH, int agg, int rx, int ry, uint8_t* C);

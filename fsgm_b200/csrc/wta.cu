@@ -32,6 +32,8 @@ struct WtaParams {
     const double* O;
     double vMax;
     uint16_t* Sp16;
+    const uint16_t* Sp_in;       // if set: sums come from this u16 volume instead of the L_r volumes (direction-split path)
+    const uint16_t* next0;       // if set: Sp[.][0] of the pixel after this slab (the reference's read past label D-1)
     uint32_t* bestD;
     uint32_t* minC;
 };
@@ -57,7 +59,13 @@ epi_wta_kernel(const WtaParams prm)
         const size_t p = group + i;
         if (p >= N) break;
         uint32_t key = 0xFFFFFFFFu;
-        if (VEC8) {
+        if (prm.Sp_in) {
+            for (int d = lane; d < D; d += 32) {
+                const uint32_t a = __ldg(prm.Sp_in + vol + p * D + d);
+                s[d] = (uint16_t)a;
+                key = min(key, (a << 16) | (uint32_t)d);
+            }
+        } else if (VEC8) {
             for (int d0 = lane * 8; d0 < D; d0 += 256) {
                 uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;                   // u16x2 accumulators for 8 labels
                 for (int r = 0; r < R; ++r) {
@@ -95,7 +103,9 @@ epi_wta_kernel(const WtaParams prm)
         if (refine) {                                    // warp-uniform
             c_1 = s[idx - 1];
             if (idx + 1 < (uint32_t)D) c1 = s[idx + 1];
-            else {
+            else if (prm.Sp_in) {
+                c1 = (p + 1 < N) ? __ldg(prm.Sp_in + vol + (p + 1) * D) : (prm.next0 ? __ldg(prm.next0) : 0u);
+            } else {
                 uint32_t v = (lane < R && p + 1 < N) ? __ldg(prm.L[lane] + vol + (p + 1) * D) : 0u;
                 c1 = __reduce_add_sync(0xffffffffu, v);
             }
@@ -138,6 +148,21 @@ int launch_epi_wta(fsgm_ctx* c, int n, uint8_t* const* Lvols, int n_dirs, int W,
     dim3 grid((unsigned)((N + WTA_WARPS * 32 - 1) / (WTA_WARPS * 32)), n);
     if (D % 8 == 0) epi_wta_kernel<true><<<grid, WTA_WARPS * 32, 0, c->stream>>>(p);
     else epi_wta_kernel<false><<<grid, WTA_WARPS * 32, 0, c->stream>>>(p);
+    FSGM_LAUNCHED(c);
+    return FSGM_OK;
+}
+
+// WTA from an already-summed u16 volume covering `npix` consecutive pixels (one slab of the direction-split path)
+int launch_sp_wta(fsgm_ctx* c, const uint16_t* Sp, const uint16_t* next0, size_t npix, int D, int subpixel,
+                  int vz_to_disp, const double* O, double vMax, uint32_t* bestD, uint32_t* minC)
+{
+    if (D > WTA_MAXD) return fail(c, FSGM_ERR_DOMAIN, "label count must be <= 512");
+    StageScope ss(c, ST_WTA);
+    WtaParams p{};
+    p.n_dirs = 0; p.W = (int)npix; p.H = 1; p.D = D; p.subpixel = subpixel; p.vz_to_disp = vz_to_disp;
+    p.O = O; p.vMax = vMax; p.Sp16 = nullptr; p.Sp_in = Sp; p.next0 = next0; p.bestD = bestD; p.minC = minC;
+    dim3 grid((unsigned)((npix + WTA_WARPS * 32 - 1) / (WTA_WARPS * 32)), 1);
+    epi_wta_kernel<false><<<grid, WTA_WARPS * 32, 0, c->stream>>>(p);
     FSGM_LAUNCHED(c);
     return FSGM_OK;
 }

@@ -1,0 +1,111 @@
+"""Multi-GPU host logic for the fSGM hot path.  One process per GPU, torch.distributed for the plumbing.
+
+Two partitionings, nothing else:
+
+* batch of independent pairs  -> `shard_range`: rank r owns a contiguous block of pairs; no data-path collective.
+* one large pair, scan directions split across ranks -> `epi_direction_split`: every rank builds the cost volume
+  (cheap, redundant), aggregates only its own directions into a u16 partial volume, the partial volumes are summed
+  with ONE reduce-scatter over pixel slabs (the u16 pairs viewed as 32-bit words: per-voxel totals are at most
+  8*255 < 65536, so no carry ever crosses a half-word and the integer sum is exact), each rank runs WTA/subpixel on
+  its slab and the 8 B/pixel outputs are all-gathered.  The reference's read of the *next pixel's* label 0 for
+  argmin == dMax-1 (calc_cost_sgm.cpp:293-296) crosses slab boundaries: the first voxel of every slab is all-gathered
+  (one u16 per rank) and handed to the previous rank's WTA.
+
+The compute steps go through a small backend object so the same logic runs on GPUs (GpuBackend: the C ABI via
+fsgm_b200.api) and, in the CPU test-suite, over gloo with a checker backend supplied by the test.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ALL_DIRS_8 = (0, 1, 2, 3, 4, 5, 6, 7)       # L1(+x) L3(+y) L2(+x+y) L4(-x+y), then reversed (include/fsgm.h)
+ALL_DIRS_4 = (0, 1, 4, 5)
+
+
+def shard_range(n: int, rank: int, world: int) -> range:
+    """contiguous block partition of n independent units (pairs) over `world` ranks"""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return range(lo, lo + base + (1 if rank < rem else 0))
+
+
+def split_directions(paths: int, rank: int, world: int):
+    dirs = ALL_DIRS_8 if paths == 8 else ALL_DIRS_4
+    return tuple(dirs[rank::world])
+
+
+def slab_pixels(N: int, world: int) -> int:
+    """pixels per rank after the reduce-scatter: equal slabs, even so that slab*D u16 values pack into whole u32 words"""
+    s = -(-N // world)
+    return s + (s & 1)
+
+
+class GpuBackend:
+    """Compute steps of the direction-split path on one GPU, through the C ABI."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.device = torch.device("cuda", ctx.device)
+
+    def cost_volume(self, pair, D, vMax):
+        I1, I2 = (torch.from_numpy(pair[k][None]).to(self.device) for k in ("I1", "I2"))
+        Pd0, dirn, O = (torch.from_numpy(pair[k][None]).to(self.device) for k in ("Pd0", "dirn", "O"))
+        _, H, W = I1.shape
+        cen1 = torch.empty((1, H, W), dtype=torch.int32, device=self.device)
+        cen2 = torch.empty_like(cen1)
+        self.ctx.census_dev(I1, cen1)
+        self.ctx.census_dev(I2, cen2)
+        Cv = torch.empty((1, H, W, D), dtype=torch.uint8, device=self.device)
+        self.ctx.epi_cost_dev(cen1, cen2, D, vMax, Pd0, dirn, O, None, Cv)
+        return Cv[0], I1[0]
+
+    def partial(self, Cvol, I1, P1, P2, dirs, n_pad):
+        H, W, D = Cvol.shape
+        out = torch.zeros(n_pad * D, dtype=torch.int16, device=self.device)
+        self.ctx.epi_partial_dev(Cvol, I1, P1, P2, dirs, out)
+        return out
+
+    def wta(self, Sp_slab, next0, D, O_slab, vMax):
+        n = Sp_slab.numel() // D
+        bestD = torch.empty(n, dtype=torch.int32, device=self.device)
+        minC = torch.empty_like(bestD)
+        self.ctx.epi_wta_sp_dev(Sp_slab, next0, D, O_slab, vMax, bestD, minC)
+        return bestD, minC
+
+    def to_device(self, a):
+        return torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+
+
+def epi_direction_split(backend, pair, D, vMax, P1, P2, paths=8, group=None):
+    """calc_cost_sgm for ONE pair with the scan directions split over the ranks of `group`.
+    Returns (bestD, minC) as uint32 numpy arrays [H][W], identical on every rank and identical to the single-GPU call."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    H, W = pair["I1"].shape
+    N = H * W
+    slab = slab_pixels(N, world)
+    n_pad = slab * world
+    Cvol, I1 = backend.cost_volume(pair, D, vMax)
+    part = backend.partial(Cvol, I1, P1, P2, split_directions(paths, rank, world), n_pad)    # int16 bits = u16
+    words = part.view(torch.int32)                                                               # two u16 per word
+    per = slab * D // 2
+    if dist.get_backend(group) == "nccl":
+        mine = torch.empty(per, dtype=torch.int32, device=words.device)
+        dist.reduce_scatter_tensor(mine, words, op=dist.ReduceOp.SUM, group=group)
+    else:                                                   # gloo has no reduce-scatter: all-reduce, keep our slab
+        dist.all_reduce(words, op=dist.ReduceOp.SUM, group=group)
+        mine = words[rank * per:(rank + 1) * per].clone()
+    Sp_slab = mine.view(torch.int16)
+    # one u16 per rank, exchanged as int32 (gloo has no 16-bit all_gather); totals are < 2^15 so the round trip is exact
+    firsts = [torch.empty(1, dtype=torch.int32, device=Sp_slab.device) for _ in range(world)]
+    dist.all_gather(firsts, Sp_slab[:1].to(torch.int32) & 0xFFFF, group=group)
+    next0 = firsts[rank + 1].to(torch.int16) if rank + 1 < world else None
+    O_pad = np.zeros(n_pad, np.float64)
+    O_pad[:N] = pair["O"].reshape(-1)
+    bestD, minC = backend.wta(Sp_slab, next0, D, backend.to_device(O_pad[rank * slab:(rank + 1) * slab]), vMax)
+    out = torch.stack([bestD, minC])                                                            # [2][slab]
+    gathered = [torch.empty_like(out) for _ in range(world)]
+    dist.all_gather(gathered, out, group=group)
+    full = torch.cat(gathered, dim=1)[:, :N].cpu().numpy().view(np.uint32)
+    return full[0].reshape(H, W), full[1].reshape(H, W)

@@ -107,6 +107,18 @@ FSGM_API int fsgm_epi_aggregate_dev(fsgm_ctx* ctx, int n_pairs, const uint8_t* d
                            int dMax, int P1, int P2, const fsgm_epi_opts* opts, uint16_t* d_Sp /* may be NULL */,
                            const double* d_offsetFromPosD0, double vMax, uint32_t* d_bestD, uint32_t* d_minC);
 
+/* direction-split building blocks for ONE large pair (the R scan directions spread over GPUs, volumes reduced over
+ * NVLink by the caller — fsgm_b200/dist.py does it with an NCCL reduce-scatter on the u16 pairs viewed as u32):
+ *   partial : sweeps (calc_cost_sgm.cpp:114-257) for the listed directions, summed into u16 [H*W][dMax]
+ *   wta_sp  : calc_cost_sgm.cpp:259-308 + :414-426 over n_pixels consecutive pixels of a reduced volume;
+ *             d_next_label0 = Sp[.][0] of the pixel after the slab (the value the reference reads for label dMax-1),
+ *             NULL = 0 (end of image) */
+FSGM_API int fsgm_epi_partial_dev(fsgm_ctx* ctx, const uint8_t* d_C, const uint8_t* d_I1, int width, int height, int dMax,
+                         int P1, int P2, int adaptive_p2, const int* directions, int n_dirs, uint16_t* d_Sp_partial);
+FSGM_API int fsgm_epi_wta_sp_dev(fsgm_ctx* ctx, const uint16_t* d_Sp, const uint16_t* d_next_label0, size_t n_pixels, int dMax,
+                         int subpixel, int vz_to_disp, const double* d_offsetFromPosD0, double vMax,
+                         uint32_t* d_bestD, uint32_t* d_minC);
+
 /* ---- gateway 2: calc_pyd_cost_sgm (calc_pyd_cost_sgm.cpp:439-510) ------------------------------
  * [bestD, minC, mvSub] = calc_pyd_cost_sgm(I1, I2, preMv, halfSearchWinSizeX, halfSearchWinSizeY, aggHalfWinSize,
  *                                          subPixelRefine, P1, P2, enableDiagnalPath, totalPass, adpativeP2)
