@@ -126,6 +126,9 @@ class Context:
         # stream"; cudaStreamLegacy (0x1) names the same default stream explicitly.
         self.set_stream(ptr if ptr else 1)
 
+    def tune(self, key: int, value: int):
+        self._ck(self._l.fsgm_tune(self._h, int(key), int(value)))
+
     def synchronize(self):
         self._ck(self._l.fsgm_synchronize(self._h))
 

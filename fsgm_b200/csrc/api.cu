@@ -120,17 +120,72 @@ static int check_opts(fsgm_ctx* c, const fsgm_epi_opts* in, fsgm_epi_opts* o)
     return FSGM_OK;
 }
 
-// scratch needed by the epipolar pipeline for `n` pairs
-static size_t epi_scratch_bytes(int n, int W, int H, int D, int n_dirs, bool want_raw)
+constexpr int VS_MAX_SMEM = 227 * 1024;
+
+// cluster size of the row-synchronous fast path for this problem, or 0 if it does not apply
+static int fast_path_cluster(const fsgm_ctx* c, int W, int D, int P1, int P2, int cmax, const fsgm_epi_opts& o)
+{
+    if (c->force_cluster < 0) return 0;
+    if (o.adaptive_p2 || sweep_needs_wrap(P1, P2, cmax)) return 0;
+    if (o.total_pass < 1 || o.total_pass > 2) return 0;
+    const int ndir = o.paths == 8 ? 3 : 1;
+    const int cs = vsweep_cluster_size(W, D, ndir, VS_MAX_SMEM);
+    if (cs && c->force_cluster > 0) {          // forced size must still fit and leave every CTA >= 2 columns
+        const int f = c->force_cluster, Wk = (W + f - 1) / f;
+        if (f >= cs && f <= 8 && (f & (f - 1)) == 0 && (f - 1) * Wk < W && W - (f - 1) * Wk >= 2) return f;
+    }
+    return cs;
+}
+
+static size_t aggregate_scratch_bytes(const fsgm_ctx* c, int n, int W, int H, int D, int P1, int P2, int cmax, const fsgm_epi_opts& o)
 {
     const size_t N = (size_t)W * H, V = N * D;
-    size_t b = 0;
-    b += 2 * align256(n * N * 4);             // census x2
-    b += align256(D * 8);                     // vz table
-    if (want_raw) b += align256(n * V);       // raw cost
-    b += align256(n * V);                     // C
-    b += (size_t)n_dirs * align256(n * V);    // L_r
-    return b + 4096;
+    if (fast_path_cluster(c, W, D, P1, P2, cmax, o))
+        return 2 * align256(n * V) + align256(n * V * 2) + align256(n * N * 8) + 1024;
+    int dirs[8];
+    return (size_t)enabled_dirs(o, dirs) * align256(n * V) + 1024;
+}
+
+// sweeps + WTA + subpixel (+ vz): the row-synchronous cluster kernels when they apply, else generic sweeps + WTA kernel.
+// Sp16 (optional) receives the summed volume for stage parity.
+static int aggregate_and_wta(fsgm_ctx* c, int n, const uint8_t* C, const uint8_t* I1, int W, int H, int D, int P1, int P2, int cmax,
+                             const fsgm_epi_opts& o, const double* O, double vMax, uint16_t* Sp16, uint32_t* bestD, uint32_t* minC)
+{
+    const size_t N = (size_t)W * H, V = N * D;
+    const int cs = fast_path_cluster(c, W, D, P1, P2, cmax, o);
+    if (cs) {
+        const int ndir = o.paths == 8 ? 3 : 1;
+        uint8_t *Lh0, *Lh1 = nullptr; uint16_t *S1, *rec;
+        FSGM_TRY(arena_get(c, n * V, &Lh0));
+        FSGM_TRY(arena_get(c, n * V, &Lh1));
+        FSGM_TRY(arena_get(c, n * V, &S1));
+        FSGM_TRY(arena_get(c, n * N * 4, &rec));
+        const int hd[2] = {0, 4};
+        uint8_t* Lh[2] = {Lh0, Lh1};
+        FSGM_TRY(launch_sweeps(c, n, C, I1, W, H, D, P1, P2, 0, cmax, hd, o.total_pass == 2 ? 2 : 1, Lh));
+        if (o.total_pass == 2) {
+            FSGM_TRY(launch_vsweep(c, n, cs, ndir, false, C, Lh0, Lh1, nullptr, S1, nullptr, nullptr, W, H, D, P1, P2, 0));
+            FSGM_TRY(launch_vsweep(c, n, cs, ndir, true, C, nullptr, nullptr, S1, Sp16, minC, rec, W, H, D, P1, P2, 1));
+        } else {
+            FSGM_TRY(launch_vsweep(c, n, cs, ndir, true, C, Lh0, nullptr, nullptr, Sp16, minC, rec, W, H, D, P1, P2, 0));
+        }
+        return launch_vs_finalize(c, n, rec, minC, O, W, H, D, o.subpixel, o.vz_to_disp, vMax, bestD);
+    }
+    int dirs[8];
+    const int nd = enabled_dirs(o, dirs);
+    uint8_t* L[8];
+    for (int k = 0; k < nd; ++k) FSGM_TRY(arena_get(c, n * V, &L[k]));
+    FSGM_TRY(launch_sweeps(c, n, C, I1, W, H, D, P1, P2, o.adaptive_p2 ? 25 : 0, cmax, dirs, nd, L));
+    return launch_epi_wta(c, n, L, nd, W, H, D, o.subpixel, o.vz_to_disp, O, vMax, Sp16, bestD, minC);
+}
+
+// scratch needed by the epipolar pipeline for `n` pairs
+static size_t epi_scratch_bytes(const fsgm_ctx* c, int n, int W, int H, int D, int P1, int P2, const fsgm_epi_opts& o)
+{
+    const size_t N = (size_t)W * H, V = N * D;
+    const bool fused = (D == 64 || D == 128 || D == 256);
+    return 2 * align256(n * N * 4) + align256(D * 8) + (fused ? 1 : 2) * align256(n * V) +
+           aggregate_scratch_bytes(c, n, W, H, D, P1, P2, 24, o) + 4096;
 }
 
 // The whole hot path on device-resident inputs (asynchronous on c->stream).
@@ -139,23 +194,21 @@ static int epi_pipeline_dev(fsgm_ctx* c, int n, const uint8_t* I1, const uint8_t
                             const fsgm_epi_opts& o, uint32_t* bestD, uint32_t* minC)
 {
     const size_t N = (size_t)W * H, V = N * D;
-    int dirs[8];
-    const int nd = enabled_dirs(o, dirs);
-    uint32_t *cen1, *cen2; uint8_t *raw, *C, *L[8]; double* vz;
+    uint32_t *cen1, *cen2; uint8_t *raw = nullptr, *C; double* vz;
     FSGM_TRY(arena_get(c, (size_t)D, &vz));
     FSGM_TRY(arena_get(c, n * N, &cen1));
     FSGM_TRY(arena_get(c, n * N, &cen2));
-    FSGM_TRY(arena_get(c, n * V, &raw));
     FSGM_TRY(arena_get(c, n * V, &C));
-    for (int k = 0; k < nd; ++k) FSGM_TRY(arena_get(c, n * V, &L[k]));
     FSGM_TRY(launch_census(c, n, I1, W, H, cen1));
     FSGM_TRY(launch_census(c, n, I2, W, H, cen2));
     FSGM_TRY(launch_vz_table(c, D, vMax, vz));
     bool fused = false;
     FSGM_TRY(launch_epi_cost_fused(c, n, vz, cen1, cen2, W, H, D, Pd0, dirn, O, C, &fused));
-    if (!fused) FSGM_TRY(launch_epi_cost(c, n, vz, cen1, cen2, W, H, D, vMax, Pd0, dirn, O, raw, C));
-    FSGM_TRY(launch_sweeps(c, n, C, I1, W, H, D, P1, P2, o.adaptive_p2 ? 25 : 0, /*cmax=*/24, dirs, nd, L));
-    FSGM_TRY(launch_epi_wta(c, n, L, nd, W, H, D, o.subpixel, o.vz_to_disp, O, vMax, nullptr, bestD, minC));
+    if (!fused) {
+        FSGM_TRY(arena_get(c, n * V, &raw));
+        FSGM_TRY(launch_epi_cost(c, n, vz, cen1, cen2, W, H, D, vMax, Pd0, dirn, O, raw, C));
+    }
+    FSGM_TRY(aggregate_and_wta(c, n, C, I1, W, H, D, P1, P2, /*cmax=*/24, o, O, vMax, nullptr, bestD, minC));
     return FSGM_OK;
 }
 
@@ -224,6 +277,13 @@ int fsgm_synchronize(fsgm_ctx* c)
     if (!c) return FSGM_ERR_ARG;
     FSGM_CUDA(c, cudaStreamSynchronize(c->stream));
     return FSGM_OK;
+}
+
+int fsgm_tune(fsgm_ctx* c, int key, int value)
+{
+    if (!c) return FSGM_ERR_ARG;
+    if (key == 1) { c->force_cluster = value; return FSGM_OK; }
+    return fail(c, FSGM_ERR_ARG, "unknown tuning key");
 }
 
 const char* fsgm_last_error(const fsgm_ctx* c) { return c ? c->err.c_str() : "null context"; }
@@ -314,15 +374,11 @@ int fsgm_epi_aggregate_dev(fsgm_ctx* c, int n, const uint8_t* d_C, const uint8_t
     FSGM_TRY(check_opts(c, opts, &o));
     if (!d_C || !d_bestD || !d_minC || (o.vz_to_disp && !d_O) || (o.adaptive_p2 && !d_I1)) return fail(c, FSGM_ERR_ARG, "null pointer");
     FSGM_CUDA(c, cudaSetDevice(c->device));
-    int dirs[8];
-    const int nd = enabled_dirs(o, dirs);
-    const size_t V = (size_t)W * H * D;
-    FSGM_TRY(arena_reserve(c, (size_t)nd * align256(n * V)));
+    // cost volumes handed to this stage entry are expected to come from fsgm_epi_cost_dev (values <= 24).  A caller
+    // with arbitrary u8 volumes uses fsgm_sweep_dev, which assumes nothing about the range.
+    FSGM_TRY(arena_reserve(c, aggregate_scratch_bytes(c, n, W, H, D, P1, P2, 24, o)));
     ArenaScope scope(c);
-    uint8_t* L[8];
-    for (int k = 0; k < nd; ++k) FSGM_TRY(arena_get(c, n * V, &L[k]));
-    FSGM_TRY(launch_sweeps(c, n, d_C, d_I1, W, H, D, P1, P2, o.adaptive_p2 ? 25 : 0, 255, dirs, nd, L));
-    return launch_epi_wta(c, n, L, nd, W, H, D, o.subpixel, o.vz_to_disp, d_O, vMax, d_Sp, d_bestD, d_minC);
+    return aggregate_and_wta(c, n, d_C, d_I1, W, H, D, P1, P2, 24, o, d_O, vMax, d_Sp, d_bestD, d_minC);
 }
 
 // Direction-split building blocks (one large pair, the R directions spread over GPUs):
@@ -381,9 +437,9 @@ int fsgm_calc_cost_sgm_dev(fsgm_ctx* c, int n, const uint8_t* d_I1, const uint8_
         c->mem_budget = free_b / 3;
     }
     const size_t budget = std::max(c->arena_bytes, c->mem_budget);
-    const size_t per_pair = epi_scratch_bytes(1, W, H, D, nd, true);
+    const size_t per_pair = epi_scratch_bytes(c, 1, W, H, D, P1, P2, o);
     int chunk = (int)std::min<size_t>(n, std::max<size_t>(1, budget / per_pair));
-    FSGM_TRY(arena_reserve(c, epi_scratch_bytes(chunk, W, H, D, nd, true)));
+    FSGM_TRY(arena_reserve(c, epi_scratch_bytes(c, chunk, W, H, D, P1, P2, o)));
     const size_t N = (size_t)W * H;
     for (int i0 = 0; i0 < n; i0 += chunk) {
         const int m = std::min(chunk, n - i0);

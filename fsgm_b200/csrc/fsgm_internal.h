@@ -31,6 +31,7 @@ struct fsgm_ctx {
     uint64_t launches = 0;
     int sm_count = 0;
     size_t mem_total = 0, mem_budget = 0;   // cudaMemGetInfo, queried once
+    int force_cluster = 0;                  // tuning/test knob: 0 auto, -1 generic path only, 1/2/4/8 forced cluster size
     std::string err;
     // profiling
     bool profiling = false;
@@ -103,6 +104,13 @@ int launch_epi_wta(fsgm_ctx* c, int n, uint8_t* const* Lvols, int n_dirs, int W,
 
 int launch_sp_wta(fsgm_ctx* c, const uint16_t* Sp, const uint16_t* next0, size_t npix, int D, int subpixel,
                   int vz_to_disp, const double* O, double vMax, uint32_t* bestD, uint32_t* minC);
+
+// ---- row-synchronous cluster path for the non-horizontal directions (vsweep.cu) --------------------------
+int vsweep_cluster_size(int W, int D, int ndir, int max_smem);
+int launch_vsweep(fsgm_ctx* c, int n, int cs, int ndir, bool final_, const uint8_t* C, const uint8_t* addA, const uint8_t* addB,
+                  const uint16_t* Sin, uint16_t* Sout, uint32_t* minC, uint16_t* rec, int W, int H, int D, int P1, int P2, int up);
+int launch_vs_finalize(fsgm_ctx* c, int n, const uint16_t* rec, const uint32_t* minC, const double* O, int W, int H, int D,
+                       int subpixel, int vz_to_disp, double vMax, uint32_t* bestD);
 
 // ---- pyramidal 2-D-window variant (pyd.cu) ----------------------------------------------------------
 int launch_pyd_cost(fsgm_ctx* c, int n, const uint32_t* cen1, const uint32_t* cen2, int W, int H,

@@ -1,0 +1,364 @@
+// Row-synchronous aggregation of the non-horizontal directions — the fast path for the sweeps of sgm()
+// (reference calc_cost_sgm.cpp:114-257) when the image is narrow enough for its path state to live on chip.
+//
+// The generic kernel (aggregate.cu) runs every direction as independent scanlines: each direction reads the cost
+// volume C once and writes its own u8 volume L_r, and a WTA kernel reads all of them back: 3 B per voxel and
+// direction.  The three directions that advance one image row per step (down: (0,+1) (+1,+1) (-1,+1); up: their
+// negatives) all need the SAME cost row at the same time, so here ONE thread-block cluster walks an image row by row:
+//
+//   * the image width is split over the CTAs of the cluster; each CTA keeps the L rows of its columns for the three
+//     directions in shared memory (3 * Wk * D bytes), updated in place: a diagonal path's state stays in one slot
+//     ((x - dx*row) mod Wk) while the pixel it belongs to slides across the strip;
+//   * a path that leaves the strip is handed to the neighbour CTA through distributed shared memory (256 B + its
+//     minimum per row and diagonal), one cluster barrier per row orders the exchange;
+//   * the strip's cost row is fetched once per row by a 1-D bulk TMA copy (cp.async.bulk + mbarrier), two rows ahead;
+//   * per pixel the three new L rows are summed in registers; the DOWN pass adds the two horizontal volumes and
+//     writes one u16 sum; the UP pass adds that sum and does winner-take-all directly, so neither the six L volumes
+//     nor Sp ever exist in HBM.
+//
+// HBM traffic per voxel: down pass 1 (C) + 2 (two horizontal u8 volumes) + 2 (u16 sum out); up pass 1 (C) + 2 (sum in);
+// against 6 * 3 = 18 for the same six directions through the generic kernel + WTA.  Bound: integer issue
+// (~55 instructions per pixel and direction), with the down pass close to the HBM roofline as well.
+//
+// Used only when: D in {64,128,256}, parameters inside the no-wrap domain, no adaptive P2, and the state fits in
+// shared memory with a cluster of <= 8 CTAs (W*D <= ~320 k, e.g. 1242 x 256).  Everything else takes the generic path.
+#include "fsgm_internal.h"
+#include "sgm_step.cuh"
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
+
+namespace fsgm {
+
+constexpr int VS_WARPS = 32;
+
+struct VsParams {
+    const uint8_t* C;            // [n][H][W][D]
+    const uint8_t* addA;         // optional u8 volumes added to the sum (the horizontal directions)
+    const uint8_t* addB;
+    const uint16_t* Sin;         // optional u16 volume added to the sum (the other pass)
+    uint16_t* Sout;              // !FINAL: u16 sum volume; FINAL: optional dump of the total Sp (stage parity), may be null
+    uint32_t* minC;              // FINAL: winner-take-all outputs
+    uint16_t* rec;               //        [n][N][4] = argmin, Sp[argmin-1], Sp[argmin+1] (0 if argmin == D-1), Sp[0]
+    int W, H, Wk, P1, P2;
+    int up;                      // 0: rows 0..H-1 with directions (0,+1)(+1,+1)(-1,+1); 1: rows H-1..0, negated
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int NREG> struct RowT;
+template <> struct RowT<1> { using T = uint16_t; };
+template <> struct RowT<2> { using T = uint32_t; };
+template <> struct RowT<4> { using T = uint2; };
+
+template <int NREG> __device__ __forceinline__ void ld_row(const uint8_t* base, int lane, uint32_t (&w)[(NREG + 1) / 2])
+{
+    if (NREG == 1) w[0] = reinterpret_cast<const uint16_t*>(base)[lane];
+    else if (NREG == 2) w[0] = reinterpret_cast<const uint32_t*>(base)[lane];
+    else { uint2 v = reinterpret_cast<const uint2*>(base)[lane]; w[0] = v.x; w[1] = v.y; }
+}
+template <int NREG> __device__ __forceinline__ void st_row(uint8_t* base, int lane, const uint32_t (&w)[(NREG + 1) / 2])
+{
+    if (NREG == 1) reinterpret_cast<uint16_t*>(base)[lane] = (uint16_t)w[0];
+    else if (NREG == 2) reinterpret_cast<uint32_t*>(base)[lane] = w[0];
+    else reinterpret_cast<uint2*>(base)[lane] = make_uint2(w[0], w[1]);
+}
+
+// NDIR: 1 (vertical only, the reference's 4-path setting) or 3.  FINAL: add Sin and do WTA instead of writing Sout.
+template <int NREG, int NDIR, bool FINAL>
+__global__ void __launch_bounds__(VS_WARPS * 32, 1)
+vsweep_kernel(const VsParams prm)
+{
+    constexpr int D = 64 * NREG, NW = (NREG + 1) / 2;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int CS = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    const int pair = blockIdx.x / CS;
+    const int W = prm.W, H = prm.H, Wk_max = prm.Wk;
+    const int xb = rank * Wk_max, Wk = min(Wk_max, W - xb);
+    const size_t N = (size_t)W * H;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    extern __shared__ __align__(128) unsigned char vs_smem[];
+    uint8_t* cbuf = vs_smem;                                               // [2][Wk_max*D]
+    uint8_t* state = cbuf + 2 * (size_t)Wk_max * D;                        // [NDIR][Wk_max][D]
+    uint32_t* stmin = reinterpret_cast<uint32_t*>(state + (size_t)NDIR * Wk_max * D);   // [NDIR][Wk_max]
+    uint8_t* inbox = reinterpret_cast<uint8_t*>(stmin) + (((size_t)NDIR * Wk_max * 4 + 15) & ~(size_t)15);   // [2][2][D + 16]  (row parity; 0: from left, 1: from right)
+    uint16_t* wsc = reinterpret_cast<uint16_t*>(inbox + 4 * (D + 16));     // FINAL: [VS_WARPS][D] per-warp scratch
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(wsc) + (FINAL ? VS_WARPS * D * 2 : 0));
+
+    const uint8_t* Cb = prm.C + pair * N * D;
+    const uint32_t row_bytes = (uint32_t)Wk * D;
+    auto row_y = [&](int yy) { return prm.up ? H - 1 - yy : yy; };
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    cluster.sync();
+    if (threadIdx.x == 0) {
+        for (int yy = 0; yy < min(2, H); ++yy) {
+            mbar_expect_tx(&bars[yy], row_bytes);
+            tma_load_1d(cbuf + (size_t)yy * Wk_max * D, Cb + ((size_t)row_y(yy) * W + xb) * D, row_bytes, &bars[yy]);
+        }
+    }
+
+    // neighbours' inboxes (distributed shared memory)
+    uint8_t* inbox_right = (rank + 1 < CS) ? cluster.map_shared_rank(inbox, rank + 1) : nullptr;   // we write slot "from left" there
+    uint8_t* inbox_left = (rank > 0) ? cluster.map_shared_rank(inbox, rank - 1) : nullptr;        // we write slot "from right" there
+
+    const uint32_t P1P1 = (uint32_t)prm.P1 * 0x10001u, P2P2 = (uint32_t)prm.P2 * 0x10001u;
+    const uint32_t lo_mask = lane == 0 ? (STEP_BIG2 & 0x0000FFFFu) : 0u, hi_mask = lane == 31 ? (STEP_BIG2 & 0xFFFF0000u) : 0u;
+    const int sdx = prm.up ? -1 : 1;               // x direction of "direction 1" in this pass: (+1,+1) going down, (-1,-1) going up
+
+    for (int yy = 0; yy < H; ++yy) {
+        const int y = row_y(yy), par = yy & 1;
+        mbar_wait(&bars[par], (uint32_t)((yy >> 1) & 1));
+        const uint8_t* crow = cbuf + (size_t)par * Wk_max * D;
+        const int off = yy % Wk;
+        for (int xl = warp; xl < Wk; xl += VS_WARPS) {
+            const int x = xb + xl;
+            const size_t pix = (size_t)y * W + x, vox = (pair * N + pix) * D;
+            // issue the global loads this pixel needs early
+            uint32_t ga[NW], gb[NW];
+            uint32_t gs[NREG];
+            if (prm.addA) ld_row<NREG>(prm.addA + vox, lane, ga);
+            if (prm.addB) ld_row<NREG>(prm.addB + vox, lane, gb);
+            if (FINAL && prm.Sin) {
+                const uint32_t* sp = reinterpret_cast<const uint32_t*>(prm.Sin + vox) + lane * NREG;
+                if (NREG == 4) { uint4 v = *reinterpret_cast<const uint4*>(sp); gs[0] = v.x; gs[1] = v.y; gs[2] = v.z; gs[3] = v.w; }
+                else if (NREG == 2) { uint2 v = *reinterpret_cast<const uint2*>(sp); gs[0] = v.x; gs[1] = v.y; }
+                else gs[0] = *sp;
+            }
+            uint32_t cw[NW], c[NREG], acc[NREG];
+            ld_row<NREG>(crow + (size_t)xl * D, lane, cw);
+            unpack_cost<NREG>(cw, c);
+#pragma unroll
+            for (int i = 0; i < NREG; ++i) acc[i] = 0;
+#pragma unroll
+            for (int k = 0; k < NDIR; ++k) {
+                const int dx = k == 0 ? 0 : (k == 1 ? sdx : -sdx);
+                int slot = xl;
+                if (dx > 0) { slot = xl - off; if (slot < 0) slot += Wk; }
+                if (dx < 0) { slot = xl + off; if (slot >= Wk) slot -= Wk; }
+                const bool restart = (yy == 0) || (dx > 0 && x == 0) || (dx < 0 && x == W - 1);
+                uint8_t* st = state + ((size_t)k * Wk_max + slot) * D;
+                uint32_t L[NREG], Mnew = 0;
+                if (restart) {
+#pragma unroll
+                    for (int i = 0; i < NREG; ++i) L[i] = c[i];
+                } else {
+                    const bool from_left = dx > 0 && xl == 0, from_right = dx < 0 && xl == Wk - 1;
+                    const uint8_t* src = st;
+                    uint32_t M;
+                    if (from_left || from_right) {
+                        src = inbox + ((size_t)((yy - 1) & 1) * 2 + (from_right ? 1 : 0)) * (D + 16);
+                        M = *reinterpret_cast<const uint32_t*>(src + D);
+                    } else M = stmin[k * Wk_max + slot];
+                    uint32_t lw[NW], Lpre[NREG];
+                    ld_row<NREG>(src, lane, lw);
+                    unpack_cost<NREG>(lw, Lpre);
+                    Mnew = sgm_step_u16<NREG>(c, Lpre, M, P1P1, P2P2, lo_mask, hi_mask, L);
+                }
+                uint32_t pw[NW];
+                pack_cost<NREG>(L, pw);
+                st_row<NREG>(st, lane, pw);
+                if (lane == 0) stmin[k * Wk_max + slot] = Mnew;
+                // hand the path over when it leaves the strip (it continues in the neighbour's column next row)
+                if (dx > 0 && xl == Wk - 1 && inbox_right) {
+                    uint8_t* dst = inbox_right + ((size_t)par * 2 + 0) * (D + 16);
+                    st_row<NREG>(dst, lane, pw);
+                    if (lane == 0) *reinterpret_cast<uint32_t*>(dst + D) = Mnew;
+                }
+                if (dx < 0 && xl == 0 && inbox_left) {
+                    uint8_t* dst = inbox_left + ((size_t)par * 2 + 1) * (D + 16);
+                    st_row<NREG>(dst, lane, pw);
+                    if (lane == 0) *reinterpret_cast<uint32_t*>(dst + D) = Mnew;
+                }
+#pragma unroll
+                for (int i = 0; i < NREG; ++i) acc[i] += L[i];
+            }
+            if (prm.addA) { uint32_t t[NREG]; unpack_cost<NREG>(ga, t);
+#pragma unroll
+                for (int i = 0; i < NREG; ++i) acc[i] += t[i]; }
+            if (prm.addB) { uint32_t t[NREG]; unpack_cost<NREG>(gb, t);
+#pragma unroll
+                for (int i = 0; i < NREG; ++i) acc[i] += t[i]; }
+            if (!FINAL) {
+                uint32_t* sp = reinterpret_cast<uint32_t*>(prm.Sout + vox) + lane * NREG;
+                if (NREG == 4) *reinterpret_cast<uint4*>(sp) = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+                else if (NREG == 2) *reinterpret_cast<uint2*>(sp) = make_uint2(acc[0], acc[1]);
+                else *sp = acc[0];
+            } else {
+                if (prm.Sin) {
+#pragma unroll
+                    for (int i = 0; i < NREG; ++i) acc[i] += gs[i];
+                }
+                if (prm.Sout) {
+                    uint32_t* sp = reinterpret_cast<uint32_t*>(prm.Sout + vox) + lane * NREG;
+#pragma unroll
+                    for (int i = 0; i < NREG; ++i) sp[i] = acc[i];
+                }
+                // winner-take-all: first minimum (strict <, calc_cost_sgm.cpp:267) via (sum << 16 | label)
+                uint32_t key = 0xFFFFFFFFu;
+                uint16_t* ws = wsc + warp * D;
+#pragma unroll
+                for (int i = 0; i < NREG; ++i) {
+                    const uint32_t d0 = (uint32_t)(lane * 2 * NREG + 2 * i);
+                    key = min(key, ((acc[i] & 0xFFFFu) << 16) | d0);
+                    key = min(key, (acc[i] & 0xFFFF0000u) | (d0 + 1));
+                    reinterpret_cast<uint32_t*>(ws)[lane * NREG + i] = acc[i];
+                }
+                key = __reduce_min_sync(0xffffffffu, key);
+                __syncwarp();
+                if (lane == 0) {
+                    const uint32_t idx = key & 0xFFFFu;
+                    prm.minC[pair * N + pix] = key >> 16;
+                    uint16_t* r = prm.rec + (pair * N + pix) * 4;
+                    const uint16_t c_1 = idx > 0 ? ws[idx - 1] : 0, c1 = idx + 1 < (uint32_t)D ? ws[idx + 1] : 0;
+                    *reinterpret_cast<uint2*>(r) = make_uint2(idx | ((uint32_t)c_1 << 16), (uint32_t)c1 | ((uint32_t)ws[0] << 16));
+                }
+                __syncwarp();
+            }
+        }
+        // everyone is done with this row: cost buffer `par` is free, outgoing paths are visible after the barrier
+        cluster.sync();
+        if (threadIdx.x == 0 && yy + 2 < H) {
+            mbar_expect_tx(&bars[par], row_bytes);
+            tma_load_1d(cbuf + (size_t)par * Wk_max * D, Cb + ((size_t)row_y(yy + 2) * W + xb) * D, row_bytes, &bars[par]);
+        }
+    }
+}
+
+// subpixel + vz -> disparity from the WTA records (calc_cost_sgm.cpp:278-308, :414-426); the value the reference reads
+// for argmin == D-1 is the NEXT pixel's Sp[0] (0 past the last pixel)
+__device__ __forceinline__ uint32_t vs_x86_d2u(double v)
+{
+    if (!(v > -9223372036854775809.0 && v < 9223372036854775808.0)) return 0u;
+    return (uint32_t)(unsigned long long)__double2ll_rz(v);
+}
+
+__global__ void vs_finalize_kernel(const uint16_t* __restrict__ rec, const uint32_t* __restrict__ minC, const double* __restrict__ O,
+                                   size_t N, int D, int subpixel, int vz_to_disp, double vMax, uint32_t* __restrict__ bestD)
+{
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= N) return;
+    const size_t gp = blockIdx.y * N + p;
+    const uint2 r = *reinterpret_cast<const uint2*>(rec + gp * 4);
+    const uint32_t idx = r.x & 0xFFFFu;
+    uint32_t q = idx;
+    if (subpixel) {
+        if (idx > 1) {
+            const double c_1 = (double)(r.x >> 16), c = (double)minC[gp];
+            double c1 = (double)(r.y & 0xFFFFu);
+            if (idx + 1 >= (uint32_t)D) c1 = (p + 1 < N) ? (double)(rec[(gp + 1) * 4 + 3]) : 0.0;
+            const double num = __dsub_rn(c1, c_1);
+            const double den = (c1 < c_1) ? __dsub_rn(c, c_1) : __dsub_rn(c, c1);
+            q = vs_x86_d2u(__dmul_rn(__dadd_rn((double)idx, __ddiv_rn(__ddiv_rn(num, den), 2.0)), 256.0));
+        } else q = idx * 256u;
+    }
+    if (vz_to_disp) {
+        const double d = __ddiv_rn((double)q, 256.0);
+        const double rr = __dmul_rn(__ddiv_rn(d, (double)(D + 1)), vMax);
+        const double vz = __ddiv_rn(rr, __dsub_rn(1.0, rr));
+        q = vs_x86_d2u(__dmul_rn(__dmul_rn(O[gp], vz), 256.0));
+    }
+    bestD[gp] = q;
+}
+
+// ---- host side ------------------------------------------------------------------------------------------
+static size_t vs_smem_bytes(int D, int Wk, int ndir, bool final_)
+{
+    return 2 * (size_t)Wk * D + (size_t)ndir * Wk * D + (((size_t)ndir * Wk * 4 + 15) & ~(size_t)15) + 4 * (size_t)(D + 16) +
+           (final_ ? (size_t)VS_WARPS * D * 2 : 0) + 64;
+}
+
+// cluster size (1,2,4,8) for which the state fits, or 0
+int vsweep_cluster_size(int W, int D, int ndir, int max_smem)
+{
+    if (D != 64 && D != 128 && D != 256) return 0;
+    for (int cs = 1; cs <= 8; cs *= 2) {
+        const int Wk = (W + cs - 1) / cs;
+        if (Wk < 2 || (cs - 1) * Wk >= W) continue;                        // every CTA needs at least one column
+        if (W - (cs - 1) * Wk < 2 && cs > 1) continue;
+        if (vs_smem_bytes(D, Wk, ndir, true) <= (size_t)max_smem) return cs;
+    }
+    return 0;
+}
+
+template <int NREG, int NDIR, bool FINAL>
+static int vs_launch_t(fsgm_ctx* c, int n, int cs, size_t smem, const VsParams& p)
+{
+    auto kern = vsweep_kernel<NREG, NDIR, FINAL>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        FSGM_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cs * n); cfg.blockDim = dim3(VS_WARPS * 32); cfg.dynamicSmemBytes = smem; cfg.stream = c->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    FSGM_CUDA(c, cudaLaunchKernelEx(&cfg, kern, p));
+    c->launches++;
+    return FSGM_OK;
+}
+
+// one pass (down or up) over n pairs; see VsParams
+int launch_vsweep(fsgm_ctx* c, int n, int cs, int ndir, bool final_, const uint8_t* C, const uint8_t* addA, const uint8_t* addB,
+                  const uint16_t* Sin, uint16_t* Sout, uint32_t* minC, uint16_t* rec, int W, int H, int D, int P1, int P2, int up)
+{
+    StageScope ss(c, ST_SWEEP);
+    VsParams p{};
+    p.C = C; p.addA = addA; p.addB = addB; p.Sin = Sin; p.Sout = Sout; p.minC = minC; p.rec = rec;
+    p.W = W; p.H = H; p.Wk = (W + cs - 1) / cs; p.P1 = P1; p.P2 = P2; p.up = up;
+    const size_t smem = vs_smem_bytes(D, p.Wk, ndir, final_);
+    const int nreg = D / 64;
+#define VS_GO(NR, ND, FN) return vs_launch_t<NR, ND, FN>(c, n, cs, smem, p)
+    if (ndir == 3) {
+        if (final_) { if (nreg == 4) VS_GO(4, 3, true); if (nreg == 2) VS_GO(2, 3, true); VS_GO(1, 3, true); }
+        else        { if (nreg == 4) VS_GO(4, 3, false); if (nreg == 2) VS_GO(2, 3, false); VS_GO(1, 3, false); }
+    } else {
+        if (final_) { if (nreg == 4) VS_GO(4, 1, true); if (nreg == 2) VS_GO(2, 1, true); VS_GO(1, 1, true); }
+        else        { if (nreg == 4) VS_GO(4, 1, false); if (nreg == 2) VS_GO(2, 1, false); VS_GO(1, 1, false); }
+    }
+#undef VS_GO
+}
+
+int launch_vs_finalize(fsgm_ctx* c, int n, const uint16_t* rec, const uint32_t* minC, const double* O, int W, int H, int D,
+                       int subpixel, int vz_to_disp, double vMax, uint32_t* bestD)
+{
+    StageScope ss(c, ST_WTA);
+    const size_t N = (size_t)W * H;
+    dim3 grid((unsigned)((N + 255) / 256), n);
+    vs_finalize_kernel<<<grid, 256, 0, c->stream>>>(rec, minC, O, N, D, subpixel, vz_to_disp, vMax, bestD);
+    FSGM_LAUNCHED(c);
+    return FSGM_OK;
+}
+
+}  // namespace fsgm

@@ -43,6 +43,9 @@ FSGM_API void        fsgm_destroy(fsgm_ctx* ctx);
 FSGM_API int         fsgm_set_stream(fsgm_ctx* ctx, void* cuda_stream);
 FSGM_API int         fsgm_synchronize(fsgm_ctx* ctx);
 FSGM_API const char* fsgm_last_error(const fsgm_ctx* ctx);
+/* Tuning / A-B knobs (results never change).  key 1 = aggregation path of the epipolar variant: 0 auto (default),
+ * -1 generic one-warp-per-scanline kernels only, 1/2/4/8 = thread-block-cluster size of the row-synchronous kernel. */
+FSGM_API int         fsgm_tune(fsgm_ctx* ctx, int key, int value);
 FSGM_API int         fsgm_abi_version(void);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 FSGM_API uint64_t    fsgm_launch_count(const fsgm_ctx* ctx);

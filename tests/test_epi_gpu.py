@@ -162,3 +162,34 @@ def test_fused_cost_kernel_wild_geometry(ctx, oracle, W, H, D):
     ctx.epi_cost_dev(_t(cen1.view(np.int32)[None]), _t(cen2.view(np.int32)[None]), D, 0.3, _t(Pd0[None]), _t(p["dirn"][None]),
                      _t(O[None]), raw_g, Cv2)
     assert np.array_equal(raw_g.cpu().numpy()[0], raw) and np.array_equal(Cv2.cpu().numpy()[0], want)
+
+
+@pytest.mark.parametrize("W,H,D,paths,passes,cluster", [
+    (150, 40, 64, 8, 2, 1), (150, 40, 64, 8, 2, 2), (150, 40, 64, 8, 2, 4), (151, 37, 64, 8, 2, 8),
+    (97, 33, 128, 8, 2, 4), (64, 50, 256, 8, 2, 8), (90, 30, 256, 4, 2, 4), (90, 30, 128, 8, 1, 2), (33, 70, 64, 4, 1, 8),
+    (40, 3, 64, 8, 2, 4), (16, 1, 64, 8, 2, 8), (300, 20, 256, 8, 2, 8),
+])
+def test_cluster_path_equals_oracle_and_generic(ctx, oracle, W, H, D, paths, passes, cluster):
+    """Row-synchronous cluster kernels (vsweep.cu) at every cluster size: Sp, minC, bestD vs the oracle and vs the
+    generic one-warp-per-scanline path."""
+    import torch
+    from fsgm_b200 import api
+    p = synth.epipolar_pair(W, H, D, seed=W + cluster)
+    ref = _oracle_epi(oracle, p, D, 6, 64, paths) if passes == 2 else None
+    o = api.epi_opts(paths=paths, total_pass=passes)
+    Cin = _t((ref["C"] if ref else oracle.port_epi(p["I1"], p["I2"], D, 0.3, p["Pd0"], p["dirn"], p["O"], 6, 64, paths=paths)["C"])[None])
+    I1, O = _t(p["I1"][None]), _t(p["O"][None])
+    outs = {}
+    for mode in (cluster, -1):
+        ctx.tune(1, mode)
+        Sp = torch.zeros((1, H, W, D), dtype=torch.int16, device="cuda")
+        b = torch.empty((1, H, W), dtype=torch.int32, device="cuda"); m = torch.empty_like(b)
+        ctx.epi_aggregate_dev(Cin, I1, 6, 64, O, 0.3, b, m, Sp=Sp, opts=o)
+        outs[mode] = (Sp.cpu().numpy().view(np.uint16)[0], m.cpu().numpy().view(np.uint32)[0], b.cpu().numpy().view(np.uint32)[0])
+    ctx.tune(1, 0)
+    for k in range(3):
+        assert np.array_equal(outs[cluster][k], outs[-1][k]), k
+    if ref is not None:
+        assert np.array_equal(outs[cluster][0].astype(np.uint32), ref["Sp"])
+        assert np.array_equal(outs[cluster][1], ref["minC"])
+        _cmp_bestD(outs[cluster][2], ref, D)
