@@ -185,6 +185,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     ctx = api.Context(local)
     ctx.use_torch_stream()
+    ctx.tune(1, args.tune_cluster)
     opts = api.epi_opts(paths=PATHS)
     P = args.pairs
     N = W * H
@@ -306,6 +307,8 @@ def main():
     ap.add_argument("--pairs", type=int, default=16, help="pairs per step per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--tune-cluster", type=int, default=0,
+                    help="A/B knob (fsgm_tune key 1): 0 auto, -1 generic sweeps only, 1/2/4/8 cluster size")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -20,6 +20,7 @@
 // P1,P2 >= 0, cmax+P1+P2 <= 255 and 2*cmax+P2 <= 255 no truncation can fire and the u16 lanes are exact
 // (WRAP=false); otherwise the WRAP=true instantiation reproduces every truncation explicitly.
 #include "fsgm_internal.h"
+#include "sgm_step.cuh"
 
 namespace fsgm {
 
@@ -100,6 +101,119 @@ __device__ __forceinline__ void store_row(uint8_t* __restrict__ pix, int lane, i
         else if (NREG == 2) reinterpret_cast<uint32_t*>(pix)[lane] = w[0];
         else if (NREG == 4) reinterpret_cast<uint2*>(pix)[lane] = make_uint2(w[0], w[1]);
         else reinterpret_cast<uint4*>(pix)[lane] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
+// No-wrap fast kernel.  Same mapping as sweep_kernel below, restructured so the per-step overhead is small:
+//   * the scanline is tracked as a 32-bit pixel index; addresses are one IMAD.WIDE each (pixel * D + base);
+//   * the pixel indices of the prefetched rows ride along in the register ring, so the store needs no second cursor;
+//   * a path restart is branch-free: the previous state is replaced by zeros with M = 0, for which the step formula
+//     yields L = C, and the new minimum is forced to 0 afterwards (the reference's path-start rule, :152-180).
+// ------------------------------------------------------------------------------------------------------------
+template <int NREG, int MODE, bool ADAPT>
+__global__ void __launch_bounds__(SWEEP_WARPS * 32)
+sweep_fast_kernel(const SweepParams prm)
+{
+    const int lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * SWEEP_WARPS + (threadIdx.x >> 5);
+    if (gw >= prm.line_start[prm.n_dirs]) return;
+    int k = 0;
+    while (gw >= prm.line_start[k + 1]) ++k;
+    const int line = gw - prm.line_start[k];
+    const int r = prm.dir[k];
+    const int dx = dir_dx(r), dy = dir_dy(r);
+    const int W = prm.W, H = prm.H, D = prm.D;
+    const size_t N = (size_t)W * H;
+    constexpr int NB = 2 * NREG;
+    const uint8_t* __restrict__ Cb = prm.C + blockIdx.y * N * D;
+    uint8_t* __restrict__ Lb = prm.L[k] + blockIdx.y * N * D;
+    const uint8_t* __restrict__ Ib = ADAPT ? prm.I1 + blockIdx.y * N : nullptr;
+
+    // scanline as pixel indices: p(t+1) = p(t) + dp, plus `fix` whenever x wraps (every W steps after the first `wrap_in`)
+    int p, len, wrap_in;
+    const int dp = dy * W + dx, fix = -dx * W;
+    if (dy == 0) { p = line * W + (dx > 0 ? 0 : W - 1); len = W; wrap_in = 0x7FFFFFFF; }
+    else {
+        p = (dy > 0 ? 0 : H - 1) * W + line; len = H;
+        wrap_in = dx == 0 ? 0x7FFFFFFF : (dx > 0 ? W - line : line + 1);
+    }
+    int pf = p, pf_wrap = wrap_in;                                   // prefetch cursor
+    int restart_in = wrap_in;                                        // steps until the compute cursor sits on a restart pixel
+
+    uint32_t cdead[NREG];
+#pragma unroll
+    for (int i = 0; i < NREG; ++i) {
+        int d0 = lane * NB + 2 * i;
+        cdead[i] = (MODE == LM_FULL) ? 0u : (((d0 >= D ? 0xFFFFu : 0u) | (d0 + 1 >= D ? 0xFFFF0000u : 0u)) & STEP_BIG2);
+    }
+    const uint32_t lo_mask = (lane == 0) ? (STEP_BIG2 & 0x0000FFFFu) : 0u;
+    const uint32_t hi_mask = (lane == 31) ? (STEP_BIG2 & 0xFFFF0000u) : 0u;
+    const uint32_t P1P1 = (uint32_t)prm.P1 * 0x10001u;
+    uint32_t P2P2 = (uint32_t)prm.P2 * 0x10001u;
+
+    auto advance = [&](int& pix, int& cnt) {
+        pix += dp;
+        if (--cnt == 0) { pix += fix; cnt = W; }
+    };
+
+    Words<NREG> ring[PF];
+    int pring[PF];
+#pragma unroll
+    for (int j = 0; j < PF; ++j) {
+        pring[j] = pf;
+        if (j < len) ring[j] = load_row<NREG, MODE>(Cb + (size_t)(uint32_t)pf * (uint32_t)D, lane, D);
+        advance(pf, pf_wrap);
+    }
+
+    uint32_t Lr[NREG];
+#pragma unroll
+    for (int i = 0; i < NREG; ++i) Lr[i] = 0;
+    uint32_t M = 0;
+    int prev_pix = 0;
+    bool restart = true;
+
+    for (int t0 = 0; t0 < len; t0 += PF) {
+#pragma unroll
+        for (int j = 0; j < PF; ++j) {
+            const int t = t0 + j;
+            if (t >= len) break;
+            const Words<NREG> cw = ring[j];
+            const int pix = pring[j];
+            if (t + PF < len) {
+                pring[j] = pf;
+                ring[j] = load_row<NREG, MODE>(Cb + (size_t)(uint32_t)pf * (uint32_t)D, lane, D);
+            }
+            advance(pf, pf_wrap);
+
+            uint32_t c[NREG], cP2[NREG];
+            unpack_cost<NREG>(cw.w, c);
+            if (ADAPT) {
+                int P2 = prm.P2;
+                if (!restart && abs((int)Ib[pix] - (int)Ib[prev_pix]) > prm.adaptive_thr) P2 = P2 / 8;
+                P2P2 = (uint32_t)P2 * 0x10001u;
+            }
+#pragma unroll
+            for (int i = 0; i < NREG; ++i) {
+                if (MODE != LM_FULL) c[i] |= cdead[i];
+                cP2[i] = c[i] + P2P2;
+            }
+            if (restart) {
+#pragma unroll
+                for (int i = 0; i < NREG; ++i) Lr[i] = 0;
+                M = 0;
+            }
+            uint32_t Ln[NREG];
+            const uint32_t m = sgm_step_u16<NREG>(c, cP2, Lr, M, P1P1, lo_mask, hi_mask, Ln);
+            M = restart ? 0u : m;
+#pragma unroll
+            for (int i = 0; i < NREG; ++i) Lr[i] = Ln[i];
+            store_row<NREG, MODE>(Lb + (size_t)(uint32_t)pix * (uint32_t)D, lane, D, Lr);
+            prev_pix = pix;
+            restart = (--restart_in == 0);
+            if (restart) restart_in = W;
+        }
     }
 }
 
@@ -243,8 +357,8 @@ sweep_kernel(const SweepParams prm)
 template <int NREG, int MODE>
 static void sweep_dispatch2(const SweepParams& p, bool wrap, bool adapt, dim3 grid, cudaStream_t s)
 {
-    if (!wrap && !adapt) sweep_kernel<NREG, MODE, false, false><<<grid, SWEEP_WARPS * 32, 0, s>>>(p);
-    else if (!wrap && adapt) sweep_kernel<NREG, MODE, false, true><<<grid, SWEEP_WARPS * 32, 0, s>>>(p);
+    if (!wrap && !adapt) sweep_fast_kernel<NREG, MODE, false><<<grid, SWEEP_WARPS * 32, 0, s>>>(p);
+    else if (!wrap && adapt) sweep_fast_kernel<NREG, MODE, true><<<grid, SWEEP_WARPS * 32, 0, s>>>(p);
     else if (wrap && !adapt) sweep_kernel<NREG, MODE, true, false><<<grid, SWEEP_WARPS * 32, 0, s>>>(p);
     else sweep_kernel<NREG, MODE, true, true><<<grid, SWEEP_WARPS * 32, 0, s>>>(p);
 }

@@ -279,6 +279,8 @@ int fsgm_synchronize(fsgm_ctx* c)
     return FSGM_OK;
 }
 
+int fsgm_debug_max_clusters(int cs, size_t smem, int threads) { return fsgm::vsweep_max_clusters(cs, smem, threads); }
+
 int fsgm_tune(fsgm_ctx* c, int key, int value)
 {
     if (!c) return FSGM_ERR_ARG;

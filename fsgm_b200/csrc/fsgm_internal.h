@@ -107,6 +107,7 @@ int launch_sp_wta(fsgm_ctx* c, const uint16_t* Sp, const uint16_t* next0, size_t
 
 // ---- row-synchronous cluster path for the non-horizontal directions (vsweep.cu) --------------------------
 int vsweep_cluster_size(int W, int D, int ndir, int max_smem);
+int vsweep_max_clusters(int cs, size_t smem, int threads);
 int launch_vsweep(fsgm_ctx* c, int n, int cs, int ndir, bool final_, const uint8_t* C, const uint8_t* addA, const uint8_t* addB,
                   const uint16_t* Sin, uint16_t* Sout, uint32_t* minC, uint16_t* rec, int W, int H, int D, int P1, int P2, int up);
 int launch_vs_finalize(fsgm_ctx* c, int n, const uint16_t* rec, const uint32_t* minC, const double* O, int W, int H, int D,

@@ -26,11 +26,14 @@ __device__ __forceinline__ void pack_cost(const uint32_t (&L)[NREG], uint32_t* w
         w[k] = (2 * k + 1 < NREG) ? __byte_perm(L[2 * k], L[2 * k + 1], 0x6420) : __byte_perm(L[2 * k], 0, 0x6420);
 }
 
-// lo_mask / hi_mask: STEP_BIG2-style masks that are non-zero only in lane 0 (low half) / lane 31 (high half)
+// lo_mask / hi_mask: STEP_BIG2-style masks that are non-zero only in lane 0 (low half) / lane 31 (high half).
+// cP2 = c + P2 (packed).  The far term is applied on the output side:
+//   C + min(b, M+P2) - M  ==  min(C + (b - M), C + P2),        b = min(Lpre(d), min(Lpre(d-1), Lpre(d+1)) + P1) >= M
+// so a step costs per register two VIADDMNMX + one VIMNMX on the ALU pipe and one plain subtraction (b - M, free to
+// go to the FMA pipe as IMAD.IADD).  ALU-pipe instructions are what bounds the aggregation (ncu: alu pipe ~78 %).
 template <int NREG>
-__device__ __forceinline__ uint32_t sgm_step_u16(const uint32_t (&c)[NREG], const uint32_t (&Lpre)[NREG], uint32_t M,
-                                                 uint32_t P1P1, uint32_t P2P2, uint32_t lo_mask, uint32_t hi_mask,
-                                                 uint32_t (&L)[NREG])
+__device__ __forceinline__ uint32_t sgm_step_u16(const uint32_t (&c)[NREG], const uint32_t (&cP2)[NREG], const uint32_t (&Lpre)[NREG],
+                                                 uint32_t M, uint32_t P1P1, uint32_t lo_mask, uint32_t hi_mask, uint32_t (&L)[NREG])
 {
     uint32_t q[NREG + 1];
     const uint32_t up = __shfl_up_sync(0xffffffffu, Lpre[NREG - 1], 1);
@@ -40,14 +43,12 @@ __device__ __forceinline__ uint32_t sgm_step_u16(const uint32_t (&c)[NREG], cons
     for (int i = 1; i < NREG; ++i) q[i] = __byte_perm(Lpre[i - 1], Lpre[i], 0x5432);
     q[NREG] = __byte_perm(Lpre[NREG - 1], dn, 0x5432) | hi_mask;
     const uint32_t MM = M * 0x10001u;
-    const uint32_t far2 = MM + P2P2;
     uint32_t m = 0xFFFFFFFFu;
 #pragma unroll
     for (int i = 0; i < NREG; ++i) {
         const uint32_t nb = __vminu2(q[i], q[i + 1]);                 // min(Lpre(d-1), Lpre(d+1))
-        uint32_t b = __viaddmin_u16x2(nb, P1P1, Lpre[i]);             // min(nb + P1, Lpre(d))
-        b = __vminu2(b, far2);
-        L[i] = c[i] + b - MM;
+        const uint32_t b = __viaddmin_u16x2(nb, P1P1, Lpre[i]);       // min(nb + P1, Lpre(d))
+        L[i] = __viaddmin_u16x2(c[i], b - MM, cP2[i]);                // min(C + b - M, C + P2); b >= M in both halves: no borrow
         m = __vminu2(m, L[i]);
     }
     m = min(m & 0xFFFFu, m >> 16);

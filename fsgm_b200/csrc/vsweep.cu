@@ -156,8 +156,9 @@ vsweep_kernel(const VsParams prm)
             uint32_t cw[NW], c[NREG], acc[NREG];
             ld_row<NREG>(crow + (size_t)xl * D, lane, cw);
             unpack_cost<NREG>(cw, c);
+            uint32_t cP2[NREG];
 #pragma unroll
-            for (int i = 0; i < NREG; ++i) acc[i] = 0;
+            for (int i = 0; i < NREG; ++i) { acc[i] = 0; cP2[i] = c[i] + P2P2; }
 #pragma unroll
             for (int k = 0; k < NDIR; ++k) {
                 const int dx = k == 0 ? 0 : (k == 1 ? sdx : -sdx);
@@ -181,7 +182,7 @@ vsweep_kernel(const VsParams prm)
                     uint32_t lw[NW], Lpre[NREG];
                     ld_row<NREG>(src, lane, lw);
                     unpack_cost<NREG>(lw, Lpre);
-                    Mnew = sgm_step_u16<NREG>(c, Lpre, M, P1P1, P2P2, lo_mask, hi_mask, L);
+                    Mnew = sgm_step_u16<NREG>(c, cP2, Lpre, M, P1P1, lo_mask, hi_mask, L);
                 }
                 uint32_t pw[NW];
                 pack_cost<NREG>(L, pw);
@@ -348,6 +349,23 @@ int launch_vsweep(fsgm_ctx* c, int n, int cs, int ndir, bool final_, const uint8
         else        { if (nreg == 4) VS_GO(4, 1, false); if (nreg == 2) VS_GO(2, 1, false); VS_GO(1, 1, false); }
     }
 #undef VS_GO
+}
+
+// occupancy probe used by the tuning notes in DESIGN.md: how many clusters of `cs` CTAs with `smem` bytes can be resident
+int vsweep_max_clusters(int cs, size_t smem, int threads)
+{
+    auto kern = vsweep_kernel<4, 3, true>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (cs > 8) cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cs * 64); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = -1;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return n;
 }
 
 int launch_vs_finalize(fsgm_ctx* c, int n, const uint16_t* rec, const uint32_t* minC, const double* O, int W, int H, int D,

@@ -46,6 +46,8 @@ FSGM_API const char* fsgm_last_error(const fsgm_ctx* ctx);
 /* Tuning / A-B knobs (results never change).  key 1 = aggregation path of the epipolar variant: 0 auto (default),
  * -1 generic one-warp-per-scanline kernels only, 1/2/4/8 = thread-block-cluster size of the row-synchronous kernel. */
 FSGM_API int         fsgm_tune(fsgm_ctx* ctx, int key, int value);
+/* occupancy probe: resident clusters of `cluster_size` CTAs x `threads` threads with `smem_bytes` dynamic shared memory */
+FSGM_API int         fsgm_debug_max_clusters(int cluster_size, size_t smem_bytes, int threads);
 FSGM_API int         fsgm_abi_version(void);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 FSGM_API uint64_t    fsgm_launch_count(const fsgm_ctx* ctx);
