@@ -304,7 +304,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--pairs", type=int, default=16, help="pairs per step per GPU")
+    ap.add_argument("--pairs", type=int, default=30, help="pairs per step per GPU (30 = two full waves of the 15 resident clusters)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--tune-cluster", type=int, default=0,

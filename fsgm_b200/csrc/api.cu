@@ -137,13 +137,33 @@ static int fast_path_cluster(const fsgm_ctx* c, int W, int D, int P1, int P2, in
     return cs;
 }
 
-static size_t aggregate_scratch_bytes(const fsgm_ctx* c, int n, int W, int H, int D, int P1, int P2, int cmax, const fsgm_epi_opts& o)
+// How many of n pairs go through the cluster kernels.  Each pair occupies one cluster for a whole pass, so the work
+// comes in waves of K = resident clusters (15 clusters of 8 CTAs on a 148-SM B200): full waves take the fast path; a
+// partial wave costs as much as a full one (measured at KITTI size: ~6.6 ms per wave against ~0.65 ms per pair through
+// the generic kernels, which fill the whole GPU with independent scanlines), so it is only used when (almost) full.
+static int fast_pairs(fsgm_ctx* c, int n, int cs, int D, int W, int ndir)
+{
+    if (!cs) return 0;
+    if (c->clusters_cs != cs) {
+        const int Wk = (W + cs - 1) / cs;
+        int k = vsweep_max_clusters(cs, vsweep_smem_bytes(D, Wk, ndir), vsweep_threads());
+        c->clusters_cs = cs; c->clusters_max = k > 0 ? k : 1;
+    }
+    if (c->force_cluster > 0) return n;                 // explicit A/B request: everything through the cluster kernels
+    const int K = c->clusters_max, r = n % K;
+    return n - r + (r + 1 >= K ? r : 0);
+}
+
+static size_t aggregate_scratch_bytes(fsgm_ctx* c, int n, int W, int H, int D, int P1, int P2, int cmax, const fsgm_epi_opts& o)
 {
     const size_t N = (size_t)W * H, V = N * D;
-    if (fast_path_cluster(c, W, D, P1, P2, cmax, o))
-        return 2 * align256(n * V) + align256(n * V * 2) + align256(n * N * 8) + 1024;
+    const int cs = fast_path_cluster(c, W, D, P1, P2, cmax, o);
+    const int nf = fast_pairs(c, n, cs, D, W, o.paths == 8 ? 3 : 1), ng = n - nf;
     int dirs[8];
-    return (size_t)enabled_dirs(o, dirs) * align256(n * V) + 1024;
+    size_t b = 1024;
+    if (nf) b += 2 * align256(nf * V) + align256(nf * V * 2) + align256(nf * N * 8);
+    if (ng) b += (size_t)enabled_dirs(o, dirs) * align256(ng * V);
+    return b;
 }
 
 // sweeps + WTA + subpixel (+ vz): the row-synchronous cluster kernels when they apply, else generic sweeps + WTA kernel.
@@ -153,34 +173,40 @@ static int aggregate_and_wta(fsgm_ctx* c, int n, const uint8_t* C, const uint8_t
 {
     const size_t N = (size_t)W * H, V = N * D;
     const int cs = fast_path_cluster(c, W, D, P1, P2, cmax, o);
-    if (cs) {
-        const int ndir = o.paths == 8 ? 3 : 1;
+    const int ndir = o.paths == 8 ? 3 : 1;
+    const int nf = fast_pairs(c, n, cs, D, W, ndir), ng = n - nf;
+    if (nf) {
         uint8_t *Lh0, *Lh1 = nullptr; uint16_t *S1, *rec;
-        FSGM_TRY(arena_get(c, n * V, &Lh0));
-        FSGM_TRY(arena_get(c, n * V, &Lh1));
-        FSGM_TRY(arena_get(c, n * V, &S1));
-        FSGM_TRY(arena_get(c, n * N * 4, &rec));
+        FSGM_TRY(arena_get(c, nf * V, &Lh0));
+        FSGM_TRY(arena_get(c, nf * V, &Lh1));
+        FSGM_TRY(arena_get(c, nf * V, &S1));
+        FSGM_TRY(arena_get(c, nf * N * 4, &rec));
         const int hd[2] = {0, 4};
         uint8_t* Lh[2] = {Lh0, Lh1};
-        FSGM_TRY(launch_sweeps(c, n, C, I1, W, H, D, P1, P2, 0, cmax, hd, o.total_pass == 2 ? 2 : 1, Lh));
+        FSGM_TRY(launch_sweeps(c, nf, C, I1, W, H, D, P1, P2, 0, cmax, hd, o.total_pass == 2 ? 2 : 1, Lh));
         if (o.total_pass == 2) {
-            FSGM_TRY(launch_vsweep(c, n, cs, ndir, false, C, Lh0, Lh1, nullptr, S1, nullptr, nullptr, W, H, D, P1, P2, 0));
-            FSGM_TRY(launch_vsweep(c, n, cs, ndir, true, C, nullptr, nullptr, S1, Sp16, minC, rec, W, H, D, P1, P2, 1));
+            FSGM_TRY(launch_vsweep(c, nf, cs, ndir, false, C, Lh0, Lh1, nullptr, S1, nullptr, nullptr, W, H, D, P1, P2, 0));
+            FSGM_TRY(launch_vsweep(c, nf, cs, ndir, true, C, nullptr, nullptr, S1, Sp16, minC, rec, W, H, D, P1, P2, 1));
         } else {
-            FSGM_TRY(launch_vsweep(c, n, cs, ndir, true, C, Lh0, nullptr, nullptr, Sp16, minC, rec, W, H, D, P1, P2, 0));
+            FSGM_TRY(launch_vsweep(c, nf, cs, ndir, true, C, Lh0, nullptr, nullptr, Sp16, minC, rec, W, H, D, P1, P2, 0));
         }
-        return launch_vs_finalize(c, n, rec, minC, O, W, H, D, o.subpixel, o.vz_to_disp, vMax, bestD);
+        FSGM_TRY(launch_vs_finalize(c, nf, rec, minC, O, W, H, D, o.subpixel, o.vz_to_disp, vMax, bestD));
     }
-    int dirs[8];
-    const int nd = enabled_dirs(o, dirs);
-    uint8_t* L[8];
-    for (int k = 0; k < nd; ++k) FSGM_TRY(arena_get(c, n * V, &L[k]));
-    FSGM_TRY(launch_sweeps(c, n, C, I1, W, H, D, P1, P2, o.adaptive_p2 ? 25 : 0, cmax, dirs, nd, L));
-    return launch_epi_wta(c, n, L, nd, W, H, D, o.subpixel, o.vz_to_disp, O, vMax, Sp16, bestD, minC);
+    if (ng) {
+        int dirs[8];
+        const int nd = enabled_dirs(o, dirs);
+        uint8_t* L[8];
+        for (int k = 0; k < nd; ++k) FSGM_TRY(arena_get(c, ng * V, &L[k]));
+        const size_t po = (size_t)nf * N;                       // pair offset of the generic part
+        FSGM_TRY(launch_sweeps(c, ng, C + po * D, I1 ? I1 + po : nullptr, W, H, D, P1, P2, o.adaptive_p2 ? 25 : 0, cmax, dirs, nd, L));
+        FSGM_TRY(launch_epi_wta(c, ng, L, nd, W, H, D, o.subpixel, o.vz_to_disp, O ? O + po : nullptr, vMax,
+                                Sp16 ? Sp16 + po * D : nullptr, bestD + po, minC + po));
+    }
+    return FSGM_OK;
 }
 
 // scratch needed by the epipolar pipeline for `n` pairs
-static size_t epi_scratch_bytes(const fsgm_ctx* c, int n, int W, int H, int D, int P1, int P2, const fsgm_epi_opts& o)
+static size_t epi_scratch_bytes(fsgm_ctx* c, int n, int W, int H, int D, int P1, int P2, const fsgm_epi_opts& o)
 {
     const size_t N = (size_t)W * H, V = N * D;
     const bool fused = (D == 64 || D == 128 || D == 256);
@@ -466,7 +492,11 @@ int fsgm_calc_cost_sgm_batch(fsgm_ctx* c, int n, const uint8_t* I1, const uint8_
     // the kernels of chunk i (truly asynchronous only when the caller's buffers are pinned).
     const size_t in_pair = align256(N) * 2 + align256(2 * N * 8) * 2 + align256(N * 8);
     const size_t out_pair = 2 * align256(N * 4);
-    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n, (size_t(96) << 20) / (in_pair + out_pair) + 1));
+    int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n, (size_t(96) << 20) / (in_pair + out_pair) + 1));
+    {   // when the cluster kernels apply, feed them whole waves (one pair = one cluster for a whole pass)
+        const int cs = fast_path_cluster(c, W, D, P1, P2, 24, o);
+        if (cs) { fast_pairs(c, n, cs, D, W, o.paths == 8 ? 3 : 1); chunk = std::min(n, std::max(chunk, c->clusters_max)); }
+    }
     FSGM_TRY(pipe_reserve(c, (size_t)chunk * (in_pair + out_pair)));
     HostPipe& p = c->pipe;
     int rc = FSGM_OK;

@@ -31,6 +31,7 @@ struct fsgm_ctx {
     uint64_t launches = 0;
     int sm_count = 0;
     size_t mem_total = 0, mem_budget = 0;   // cudaMemGetInfo, queried once
+    int clusters_cs = 0, clusters_max = 0;   // resident clusters for the last queried cluster size
     int force_cluster = 0;                  // tuning/test knob: 0 auto, -1 generic path only, 1/2/4/8 forced cluster size
     std::string err;
     // profiling
@@ -108,6 +109,8 @@ int launch_sp_wta(fsgm_ctx* c, const uint16_t* Sp, const uint16_t* next0, size_t
 // ---- row-synchronous cluster path for the non-horizontal directions (vsweep.cu) --------------------------
 int vsweep_cluster_size(int W, int D, int ndir, int max_smem);
 int vsweep_max_clusters(int cs, size_t smem, int threads);
+size_t vsweep_smem_bytes(int D, int Wk, int ndir);
+int vsweep_threads();
 int launch_vsweep(fsgm_ctx* c, int n, int cs, int ndir, bool final_, const uint8_t* C, const uint8_t* addA, const uint8_t* addB,
                   const uint16_t* Sin, uint16_t* Sout, uint32_t* minC, uint16_t* rec, int W, int H, int D, int P1, int P2, int up);
 int launch_vs_finalize(fsgm_ctx* c, int n, const uint16_t* rec, const uint32_t* minC, const double* O, int W, int H, int D,

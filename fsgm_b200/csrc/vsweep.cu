@@ -30,7 +30,7 @@ namespace cg = cooperative_groups;
 
 namespace fsgm {
 
-constexpr int VS_WARPS = 32;
+constexpr int VS_WARPS = 16;
 
 struct VsParams {
     const uint8_t* C;            // [n][H][W][D]
@@ -87,6 +87,140 @@ template <int NREG> __device__ __forceinline__ void st_row(uint8_t* base, int la
     else reinterpret_cast<uint2*>(base)[lane] = make_uint2(w[0], w[1]);
 }
 
+template <int NREG>
+struct VsThread {
+    uint8_t* state_l; uint32_t* stmin; uint8_t* inbox; uint8_t* inbox_right; uint8_t* inbox_left;
+    const uint8_t* addA_l; const uint8_t* addB_l; const uint16_t* Sin_l; uint16_t* Sout_l;
+    uint32_t* minC; uint16_t* rec; uint16_t* ws;
+    int Wk, Wk_max, W, xb, lane, sdx;
+    uint32_t P1P1, P2P2, lo_mask, hi_mask;
+};
+
+// One pixel of one row: all NDIR directions, sum, output.  EDGE = the pixel may restart a path, take one from a
+// neighbour CTA's hand-over, or hand one over (first row, first / last column of the strip); interior pixels compile
+// to a straight line of LDS -> step -> STS per direction.
+template <int NREG, int NDIR, bool FINAL, bool EDGE>
+__device__ __forceinline__ void vs_pixel(const VsThread<NREG>& th, const uint8_t* crow_l, int xl, int yy, int par, int off, uint32_t pix)
+{
+    constexpr int D = 64 * NREG, NW = (NREG + 1) / 2, NB = 2 * NREG;
+    const int lane = th.lane, Wk = th.Wk;
+    const size_t vox = (size_t)pix * D;
+    uint32_t ga[NW], gb[NW], gs[NREG];
+    if (th.addA_l) ld_row<NREG>(th.addA_l + vox, 0, ga);
+    if (th.addB_l) ld_row<NREG>(th.addB_l + vox, 0, gb);
+    if (FINAL && th.Sin_l) {
+        const uint32_t* sp = reinterpret_cast<const uint32_t*>(th.Sin_l + vox);
+        if (NREG == 4) { uint4 v = *reinterpret_cast<const uint4*>(sp); gs[0] = v.x; gs[1] = v.y; gs[2] = v.z; gs[3] = v.w; }
+        else if (NREG == 2) { uint2 v = *reinterpret_cast<const uint2*>(sp); gs[0] = v.x; gs[1] = v.y; }
+        else gs[0] = *sp;
+    }
+    uint32_t cw[NW], c[NREG], cP2[NREG], acc[NREG];
+    ld_row<NREG>(crow_l + xl * D, 0, cw);
+    unpack_cost<NREG>(cw, c);
+#pragma unroll
+    for (int i = 0; i < NREG; ++i) { acc[i] = 0; cP2[i] = c[i] + th.P2P2; }
+#pragma unroll
+    for (int k = 0; k < NDIR; ++k) {
+        const int dx = k == 0 ? 0 : (k == 1 ? th.sdx : -th.sdx);
+        int slot = xl;
+        if (k > 0) {
+            if (dx > 0) { slot = xl - off; if (slot < 0) slot += Wk; }
+            else        { slot = xl + off; if (slot >= Wk) slot -= Wk; }
+        }
+        uint8_t* st = th.state_l + (k * th.Wk_max + slot) * D;
+        uint32_t* sm = th.stmin + k * th.Wk_max + slot;
+        uint32_t L[NREG], Mnew = 0;
+        bool restart = false;
+        if (EDGE) {
+            const int x = th.xb + xl;
+            restart = (yy == 0) || (dx > 0 && x == 0) || (dx < 0 && x == th.W - 1);
+        }
+        if (EDGE && restart) {
+#pragma unroll
+            for (int i = 0; i < NREG; ++i) L[i] = c[i];
+        } else {
+            const uint8_t* src = st;
+            uint32_t M;
+            bool boxed = false;
+            if (EDGE) {
+                const bool from_left = dx > 0 && xl == 0, from_right = dx < 0 && xl == Wk - 1;
+                if (from_left || from_right) {
+                    src = th.inbox + ((size_t)((yy - 1) & 1) * 2 + (from_right ? 1 : 0)) * (D + 16);
+                    M = *reinterpret_cast<const uint32_t*>(src + D);
+                    src += lane * NB;
+                    boxed = true;
+                }
+            }
+            if (!boxed) M = *sm;
+            uint32_t lw[NW], Lpre[NREG];
+            ld_row<NREG>(src, 0, lw);
+            unpack_cost<NREG>(lw, Lpre);
+            Mnew = sgm_step_u16<NREG>(c, cP2, Lpre, M, th.P1P1, th.lo_mask, th.hi_mask, L);
+        }
+        uint32_t pw[NW];
+        pack_cost<NREG>(L, pw);
+        st_row<NREG>(st, 0, pw);
+        *sm = Mnew;                                    // every lane writes the same value
+        if (EDGE) {
+            // hand the path over when it leaves the strip (it continues in the neighbour's column next row)
+            if (dx > 0 && xl == Wk - 1 && th.inbox_right) {
+                uint8_t* dst = th.inbox_right + ((size_t)par * 2 + 0) * (D + 16);
+                st_row<NREG>(dst + lane * NB, 0, pw);
+                if (lane == 0) *reinterpret_cast<uint32_t*>(dst + D) = Mnew;
+            }
+            if (dx < 0 && xl == 0 && th.inbox_left) {
+                uint8_t* dst = th.inbox_left + ((size_t)par * 2 + 1) * (D + 16);
+                st_row<NREG>(dst + lane * NB, 0, pw);
+                if (lane == 0) *reinterpret_cast<uint32_t*>(dst + D) = Mnew;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < NREG; ++i) acc[i] += L[i];
+    }
+    if (th.addA_l) { uint32_t t[NREG]; unpack_cost<NREG>(ga, t);
+#pragma unroll
+        for (int i = 0; i < NREG; ++i) acc[i] += t[i]; }
+    if (th.addB_l) { uint32_t t[NREG]; unpack_cost<NREG>(gb, t);
+#pragma unroll
+        for (int i = 0; i < NREG; ++i) acc[i] += t[i]; }
+    if (!FINAL) {
+        uint32_t* sp = reinterpret_cast<uint32_t*>(th.Sout_l + vox);
+        if (NREG == 4) *reinterpret_cast<uint4*>(sp) = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+        else if (NREG == 2) *reinterpret_cast<uint2*>(sp) = make_uint2(acc[0], acc[1]);
+        else *sp = acc[0];
+    } else {
+        if (th.Sin_l) {
+#pragma unroll
+            for (int i = 0; i < NREG; ++i) acc[i] += gs[i];
+        }
+        if (th.Sout_l) {
+            uint32_t* sp = reinterpret_cast<uint32_t*>(th.Sout_l + vox);
+#pragma unroll
+            for (int i = 0; i < NREG; ++i) sp[i] = acc[i];
+        }
+        // winner-take-all: first minimum (strict <, calc_cost_sgm.cpp:267) via (sum << 16 | label)
+        uint32_t key = 0xFFFFFFFFu;
+        uint16_t* ws = th.ws;
+#pragma unroll
+        for (int i = 0; i < NREG; ++i) {
+            const uint32_t d0 = (uint32_t)(lane * 2 * NREG + 2 * i);
+            key = min(key, ((acc[i] & 0xFFFFu) << 16) | d0);
+            key = min(key, (acc[i] & 0xFFFF0000u) | (d0 + 1));
+            reinterpret_cast<uint32_t*>(ws)[lane * NREG + i] = acc[i];
+        }
+        key = __reduce_min_sync(0xffffffffu, key);
+        __syncwarp();
+        if (lane == 0) {
+            const uint32_t idx = key & 0xFFFFu;
+            th.minC[pix] = key >> 16;
+            uint16_t* r = th.rec + (size_t)pix * 4;
+            const uint16_t c_1 = idx > 0 ? ws[idx - 1] : 0, c1 = idx + 1 < (uint32_t)D ? ws[idx + 1] : 0;
+            *reinterpret_cast<uint2*>(r) = make_uint2(idx | ((uint32_t)c_1 << 16), (uint32_t)c1 | ((uint32_t)ws[0] << 16));
+        }
+        __syncwarp();
+    }
+}
+
 // NDIR: 1 (vertical only, the reference's 4-path setting) or 3.  FINAL: add Sin and do WTA instead of writing Sout.
 template <int NREG, int NDIR, bool FINAL>
 __global__ void __launch_bounds__(VS_WARPS * 32, 1)
@@ -134,117 +268,31 @@ vsweep_kernel(const VsParams prm)
     const uint32_t lo_mask = lane == 0 ? (STEP_BIG2 & 0x0000FFFFu) : 0u, hi_mask = lane == 31 ? (STEP_BIG2 & 0xFFFF0000u) : 0u;
     const int sdx = prm.up ? -1 : 1;               // x direction of "direction 1" in this pass: (+1,+1) going down, (-1,-1) going up
 
+    // per-thread bases with the lane's byte offset folded in
+    constexpr int NB = 2 * NREG;
+    VsThread<NREG> th;
+    th.state_l = state + lane * NB; th.stmin = stmin; th.inbox = inbox; th.inbox_right = inbox_right; th.inbox_left = inbox_left;
+    th.addA_l = prm.addA ? prm.addA + pair * N * D + lane * NB : nullptr;
+    th.addB_l = prm.addB ? prm.addB + pair * N * D + lane * NB : nullptr;
+    th.Sin_l = prm.Sin ? prm.Sin + pair * N * D + lane * NB : nullptr;
+    th.Sout_l = prm.Sout ? prm.Sout + pair * N * D + lane * NB : nullptr;
+    th.minC = prm.minC ? prm.minC + pair * N : nullptr;
+    th.rec = prm.rec ? prm.rec + pair * N * 4 : nullptr;
+    th.ws = wsc + warp * D;
+    th.Wk = Wk; th.Wk_max = Wk_max; th.W = W; th.xb = xb; th.lane = lane;
+    th.P1P1 = P1P1; th.P2P2 = P2P2; th.lo_mask = lo_mask; th.hi_mask = hi_mask; th.sdx = sdx;
+
+    int off = 0;                                   // yy mod Wk, kept incrementally
     for (int yy = 0; yy < H; ++yy) {
         const int y = row_y(yy), par = yy & 1;
         mbar_wait(&bars[par], (uint32_t)((yy >> 1) & 1));
-        const uint8_t* crow = cbuf + (size_t)par * Wk_max * D;
-        const int off = yy % Wk;
+        const uint8_t* crow_l = cbuf + (size_t)par * Wk_max * D + lane * NB;
+        const uint32_t rowpix = (uint32_t)y * (uint32_t)W + (uint32_t)xb;
         for (int xl = warp; xl < Wk; xl += VS_WARPS) {
-            const int x = xb + xl;
-            const size_t pix = (size_t)y * W + x, vox = (pair * N + pix) * D;
-            // issue the global loads this pixel needs early
-            uint32_t ga[NW], gb[NW];
-            uint32_t gs[NREG];
-            if (prm.addA) ld_row<NREG>(prm.addA + vox, lane, ga);
-            if (prm.addB) ld_row<NREG>(prm.addB + vox, lane, gb);
-            if (FINAL && prm.Sin) {
-                const uint32_t* sp = reinterpret_cast<const uint32_t*>(prm.Sin + vox) + lane * NREG;
-                if (NREG == 4) { uint4 v = *reinterpret_cast<const uint4*>(sp); gs[0] = v.x; gs[1] = v.y; gs[2] = v.z; gs[3] = v.w; }
-                else if (NREG == 2) { uint2 v = *reinterpret_cast<const uint2*>(sp); gs[0] = v.x; gs[1] = v.y; }
-                else gs[0] = *sp;
-            }
-            uint32_t cw[NW], c[NREG], acc[NREG];
-            ld_row<NREG>(crow + (size_t)xl * D, lane, cw);
-            unpack_cost<NREG>(cw, c);
-            uint32_t cP2[NREG];
-#pragma unroll
-            for (int i = 0; i < NREG; ++i) { acc[i] = 0; cP2[i] = c[i] + P2P2; }
-#pragma unroll
-            for (int k = 0; k < NDIR; ++k) {
-                const int dx = k == 0 ? 0 : (k == 1 ? sdx : -sdx);
-                int slot = xl;
-                if (dx > 0) { slot = xl - off; if (slot < 0) slot += Wk; }
-                if (dx < 0) { slot = xl + off; if (slot >= Wk) slot -= Wk; }
-                const bool restart = (yy == 0) || (dx > 0 && x == 0) || (dx < 0 && x == W - 1);
-                uint8_t* st = state + ((size_t)k * Wk_max + slot) * D;
-                uint32_t L[NREG], Mnew = 0;
-                if (restart) {
-#pragma unroll
-                    for (int i = 0; i < NREG; ++i) L[i] = c[i];
-                } else {
-                    const bool from_left = dx > 0 && xl == 0, from_right = dx < 0 && xl == Wk - 1;
-                    const uint8_t* src = st;
-                    uint32_t M;
-                    if (from_left || from_right) {
-                        src = inbox + ((size_t)((yy - 1) & 1) * 2 + (from_right ? 1 : 0)) * (D + 16);
-                        M = *reinterpret_cast<const uint32_t*>(src + D);
-                    } else M = stmin[k * Wk_max + slot];
-                    uint32_t lw[NW], Lpre[NREG];
-                    ld_row<NREG>(src, lane, lw);
-                    unpack_cost<NREG>(lw, Lpre);
-                    Mnew = sgm_step_u16<NREG>(c, cP2, Lpre, M, P1P1, lo_mask, hi_mask, L);
-                }
-                uint32_t pw[NW];
-                pack_cost<NREG>(L, pw);
-                st_row<NREG>(st, lane, pw);
-                if (lane == 0) stmin[k * Wk_max + slot] = Mnew;
-                // hand the path over when it leaves the strip (it continues in the neighbour's column next row)
-                if (dx > 0 && xl == Wk - 1 && inbox_right) {
-                    uint8_t* dst = inbox_right + ((size_t)par * 2 + 0) * (D + 16);
-                    st_row<NREG>(dst, lane, pw);
-                    if (lane == 0) *reinterpret_cast<uint32_t*>(dst + D) = Mnew;
-                }
-                if (dx < 0 && xl == 0 && inbox_left) {
-                    uint8_t* dst = inbox_left + ((size_t)par * 2 + 1) * (D + 16);
-                    st_row<NREG>(dst, lane, pw);
-                    if (lane == 0) *reinterpret_cast<uint32_t*>(dst + D) = Mnew;
-                }
-#pragma unroll
-                for (int i = 0; i < NREG; ++i) acc[i] += L[i];
-            }
-            if (prm.addA) { uint32_t t[NREG]; unpack_cost<NREG>(ga, t);
-#pragma unroll
-                for (int i = 0; i < NREG; ++i) acc[i] += t[i]; }
-            if (prm.addB) { uint32_t t[NREG]; unpack_cost<NREG>(gb, t);
-#pragma unroll
-                for (int i = 0; i < NREG; ++i) acc[i] += t[i]; }
-            if (!FINAL) {
-                uint32_t* sp = reinterpret_cast<uint32_t*>(prm.Sout + vox) + lane * NREG;
-                if (NREG == 4) *reinterpret_cast<uint4*>(sp) = make_uint4(acc[0], acc[1], acc[2], acc[3]);
-                else if (NREG == 2) *reinterpret_cast<uint2*>(sp) = make_uint2(acc[0], acc[1]);
-                else *sp = acc[0];
-            } else {
-                if (prm.Sin) {
-#pragma unroll
-                    for (int i = 0; i < NREG; ++i) acc[i] += gs[i];
-                }
-                if (prm.Sout) {
-                    uint32_t* sp = reinterpret_cast<uint32_t*>(prm.Sout + vox) + lane * NREG;
-#pragma unroll
-                    for (int i = 0; i < NREG; ++i) sp[i] = acc[i];
-                }
-                // winner-take-all: first minimum (strict <, calc_cost_sgm.cpp:267) via (sum << 16 | label)
-                uint32_t key = 0xFFFFFFFFu;
-                uint16_t* ws = wsc + warp * D;
-#pragma unroll
-                for (int i = 0; i < NREG; ++i) {
-                    const uint32_t d0 = (uint32_t)(lane * 2 * NREG + 2 * i);
-                    key = min(key, ((acc[i] & 0xFFFFu) << 16) | d0);
-                    key = min(key, (acc[i] & 0xFFFF0000u) | (d0 + 1));
-                    reinterpret_cast<uint32_t*>(ws)[lane * NREG + i] = acc[i];
-                }
-                key = __reduce_min_sync(0xffffffffu, key);
-                __syncwarp();
-                if (lane == 0) {
-                    const uint32_t idx = key & 0xFFFFu;
-                    prm.minC[pair * N + pix] = key >> 16;
-                    uint16_t* r = prm.rec + (pair * N + pix) * 4;
-                    const uint16_t c_1 = idx > 0 ? ws[idx - 1] : 0, c1 = idx + 1 < (uint32_t)D ? ws[idx + 1] : 0;
-                    *reinterpret_cast<uint2*>(r) = make_uint2(idx | ((uint32_t)c_1 << 16), (uint32_t)c1 | ((uint32_t)ws[0] << 16));
-                }
-                __syncwarp();
-            }
+            if (yy == 0 || xl == 0 || xl == Wk - 1) vs_pixel<NREG, NDIR, FINAL, true>(th, crow_l, xl, yy, par, off, rowpix + xl);
+            else vs_pixel<NREG, NDIR, FINAL, false>(th, crow_l, xl, yy, par, off, rowpix + xl);
         }
+        if (++off == Wk) off = 0;
         // everyone is done with this row: cost buffer `par` is free, outgoing paths are visible after the barrier
         cluster.sync();
         if (threadIdx.x == 0 && yy + 2 < H) {
@@ -296,6 +344,9 @@ static size_t vs_smem_bytes(int D, int Wk, int ndir, bool final_)
     return 2 * (size_t)Wk * D + (size_t)ndir * Wk * D + (((size_t)ndir * Wk * 4 + 15) & ~(size_t)15) + 4 * (size_t)(D + 16) +
            (final_ ? (size_t)VS_WARPS * D * 2 : 0) + 64;
 }
+
+size_t vsweep_smem_bytes(int D, int Wk, int ndir) { return vs_smem_bytes(D, Wk, ndir, true); }
+int vsweep_threads() { return VS_WARPS * 32; }
 
 // cluster size (1,2,4,8) for which the state fits, or 0
 int vsweep_cluster_size(int W, int D, int ndir, int max_smem)
