@@ -171,10 +171,12 @@ class Context:
         return bestD, minC, conf, bestD2
 
     def calc_cost_sgm_batch(self, I1, I2, dMax, vMax, pixelPosD0, normlizeDirection, offsetFromPosD0, P1, P2, opts=None,
-                            out=None):
+                            out=None, asynchronous=False):
+        """Batch form; with asynchronous=True the call only enqueues (keep the arrays alive and call synchronize())."""
         n, H, W = I1.shape
         bestD, minC = out if out is not None else (np.empty((n, H, W), np.uint32), np.empty((n, H, W), np.uint32))
-        self._ck(self._l.fsgm_calc_cost_sgm_batch(
+        fn = self._l.fsgm_calc_cost_sgm_batch_async if asynchronous else self._l.fsgm_calc_cost_sgm_batch
+        self._ck(fn(
             self._h, n, _hp(I1, np.uint8), _hp(I2, np.uint8, (n, H, W)), W, H, int(dMax), C.c_double(vMax),
             _hp(pixelPosD0, np.float64, (n, 2, H, W)), _hp(normlizeDirection, np.float64, (n, 2, H, W)),
             _hp(offsetFromPosD0, np.float64, (n, H, W)), int(P1), int(P2), C.byref(opts) if opts is not None else None,

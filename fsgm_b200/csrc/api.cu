@@ -85,7 +85,7 @@ int pipe_reserve(fsgm_ctx* c, size_t bytes_per_slot)
     if (bytes_per_slot <= p.bytes) return FSGM_OK;
     FSGM_CUDA(c, cudaDeviceSynchronize());
     for (int i = 0; i < 2; ++i) { if (p.buf[i]) cudaFree(p.buf[i]); p.buf[i] = nullptr; }
-    p.bytes = 0;
+    p.bytes = 0; p.used[0] = p.used[1] = 0;
     for (int i = 0; i < 2; ++i)
         if (cudaMalloc(reinterpret_cast<void**>(&p.buf[i]), bytes_per_slot) != cudaSuccess) {
             cudaGetLastError();
@@ -301,7 +301,9 @@ int fsgm_set_stream(fsgm_ctx* c, void* s)
 int fsgm_synchronize(fsgm_ctx* c)
 {
     if (!c) return FSGM_ERR_ARG;
+    if (c->pipe.h2d) { FSGM_CUDA(c, cudaStreamSynchronize(c->pipe.h2d)); }
     FSGM_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->pipe.d2h) { FSGM_CUDA(c, cudaStreamSynchronize(c->pipe.d2h)); }
     return FSGM_OK;
 }
 
@@ -343,7 +345,7 @@ int fsgm_profile_read(fsgm_ctx* c, int stage, double* ms, uint64_t* launches)
 const char* fsgm_stage_name(int stage)
 {
     static const char* names[ST_COUNT] = { "census", "epi_cost", "sweep", "wta", "pyd_cost", "pyd_sweep", "pyd_wta",
-                                           "ng", "pydng_cost", "pydng_sweep", "pydng_wta", "misc" };
+                                           "ng", "pydng_cost", "pydng_sweep", "pydng_wta", "misc", "vsweep" };
     return (stage >= 0 && stage < ST_COUNT) ? names[stage] : nullptr;
 }
 int fsgm_stage_count(void) { return ST_COUNT; }
@@ -478,9 +480,12 @@ int fsgm_calc_cost_sgm_dev(fsgm_ctx* c, int n, const uint8_t* d_I1, const uint8_
     return FSGM_OK;
 }
 
-int fsgm_calc_cost_sgm_batch(fsgm_ctx* c, int n, const uint8_t* I1, const uint8_t* I2, int W, int H, int D, double vMax,
-                             const double* Pd0, const double* dirn, const double* O, int P1, int P2,
-                             const fsgm_epi_opts* opts, uint32_t* bestD, uint32_t* minC)
+// Enqueue-only form: returns once every copy and kernel of the batch is queued.  Host buffers must stay valid (and the
+// outputs unread) until fsgm_synchronize().  Back-to-back calls overlap: the H2D copies of call k+1 run while the
+// kernels of call k execute (the staging slots and their events persist in the context).
+int fsgm_calc_cost_sgm_batch_async(fsgm_ctx* c, int n, const uint8_t* I1, const uint8_t* I2, int W, int H, int D, double vMax,
+                                   const double* Pd0, const double* dirn, const double* O, int P1, int P2,
+                                   const fsgm_epi_opts* opts, uint32_t* bestD, uint32_t* minC)
 {
     FSGM_TRY(check_dims(c, n, W, H, D));
     fsgm_epi_opts o;
@@ -500,9 +505,9 @@ int fsgm_calc_cost_sgm_batch(fsgm_ctx* c, int n, const uint8_t* I1, const uint8_
     FSGM_TRY(pipe_reserve(c, (size_t)chunk * (in_pair + out_pair)));
     HostPipe& p = c->pipe;
     int rc = FSGM_OK;
-    int used[2] = {0, 0};
-    for (int i0 = 0, it = 0; i0 < n && rc == FSGM_OK; i0 += chunk, ++it) {
-        const int m = std::min(chunk, n - i0), slot = it & 1;
+    int* used = p.used;
+    for (int i0 = 0; i0 < n && rc == FSGM_OK; i0 += chunk, ++p.turn) {
+        const int m = std::min(chunk, n - i0), slot = p.turn & 1;
         char* base = p.buf[slot];
         uint8_t* dI1 = reinterpret_cast<uint8_t*>(base);                 base += align256(m * N);
         uint8_t* dI2 = reinterpret_cast<uint8_t*>(base);                 base += align256(m * N);
@@ -528,9 +533,16 @@ int fsgm_calc_cost_sgm_batch(fsgm_ctx* c, int n, const uint8_t* I1, const uint8_
             rc = fail(c, FSGM_ERR_CUDA, "D2H copy", cudaGetErrorString(cudaGetLastError()));
         used[slot] = 1;
     }
-    cudaError_t e1 = cudaStreamSynchronize(p.d2h), e2 = cudaStreamSynchronize(c->stream), e3 = cudaStreamSynchronize(p.h2d);
-    if (rc == FSGM_OK && (e1 || e2 || e3)) rc = fail(c, FSGM_ERR_CUDA, "pipeline sync", cudaGetErrorString(e1 ? e1 : (e2 ? e2 : e3)));
+    if (rc != FSGM_OK) { cudaStreamSynchronize(p.d2h); cudaStreamSynchronize(c->stream); cudaStreamSynchronize(p.h2d); }
     return rc;
+}
+
+int fsgm_calc_cost_sgm_batch(fsgm_ctx* c, int n, const uint8_t* I1, const uint8_t* I2, int W, int H, int D, double vMax,
+                             const double* Pd0, const double* dirn, const double* O, int P1, int P2,
+                             const fsgm_epi_opts* opts, uint32_t* bestD, uint32_t* minC)
+{
+    FSGM_TRY(fsgm_calc_cost_sgm_batch_async(c, n, I1, I2, W, H, D, vMax, Pd0, dirn, O, P1, P2, opts, bestD, minC));
+    return fsgm_synchronize(c);
 }
 
 int fsgm_calc_cost_sgm(fsgm_ctx* c, const uint8_t* I1, const uint8_t* I2, int W, int H, int D, double vMax,

@@ -10,7 +10,7 @@
 namespace fsgm {
 // pipeline stages, for the optional per-stage CUDA-event timing (fsgm_profile_*)
 enum Stage { ST_CENSUS = 0, ST_EPI_COST, ST_SWEEP, ST_WTA, ST_PYD_COST, ST_PYD_SWEEP, ST_PYD_WTA,
-             ST_NG, ST_PYDNG_COST, ST_PYDNG_SWEEP, ST_PYDNG_WTA, ST_MISC, ST_COUNT };
+             ST_NG, ST_PYDNG_COST, ST_PYDNG_SWEEP, ST_PYDNG_WTA, ST_MISC, ST_VSWEEP, ST_COUNT };
 struct StageTimer { cudaEvent_t a, b; int stage; };
 // double-buffered device staging + copy streams for the host-pointer gateways
 struct HostPipe {
@@ -18,6 +18,8 @@ struct HostPipe {
     cudaEvent_t in_ready[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr}, out_ready[2] = {nullptr, nullptr};
     char* buf[2] = {nullptr, nullptr};
     size_t bytes = 0;
+    int used[2] = {0, 0};        // slot has been used since the last (re)allocation: its out_ready event is meaningful
+    unsigned turn = 0;           // running chunk counter: slots alternate across calls
 };
 }  // namespace fsgm
 

@@ -96,29 +96,46 @@ struct VsThread {
     uint32_t P1P1, P2P2, lo_mask, hi_mask;
 };
 
+// the rows a pixel needs from global memory (horizontal volumes / the other pass's sum), fetched two pixels ahead
+template <int NREG>
+struct VsGlobals { uint32_t a[(NREG + 1) / 2], b[(NREG + 1) / 2], s[NREG]; };
+
+template <int NREG, bool FINAL>
+__device__ __forceinline__ void vs_fetch(const VsThread<NREG>& th, uint32_t pix, VsGlobals<NREG>& g)
+{
+    constexpr int D = 64 * NREG;
+    const size_t vox = (size_t)pix * D;
+    if (th.addA_l) ld_row<NREG>(th.addA_l + vox, 0, g.a);
+    if (th.addB_l) ld_row<NREG>(th.addB_l + vox, 0, g.b);
+    if (FINAL && th.Sin_l) {
+        const uint32_t* sp = reinterpret_cast<const uint32_t*>(th.Sin_l + vox);
+        if (NREG == 4) { uint4 v = *reinterpret_cast<const uint4*>(sp); g.s[0] = v.x; g.s[1] = v.y; g.s[2] = v.z; g.s[3] = v.w; }
+        else if (NREG == 2) { uint2 v = *reinterpret_cast<const uint2*>(sp); g.s[0] = v.x; g.s[1] = v.y; }
+        else g.s[0] = *sp;
+    }
+}
+
 // One pixel of one row: all NDIR directions, sum, output.  EDGE = the pixel may restart a path, take one from a
 // neighbour CTA's hand-over, or hand one over (first row, first / last column of the strip); interior pixels compile
 // to a straight line of LDS -> step -> STS per direction.
 template <int NREG, int NDIR, bool FINAL, bool EDGE>
-__device__ __forceinline__ void vs_pixel(const VsThread<NREG>& th, const uint8_t* crow_l, int xl, int yy, int par, int off, uint32_t pix)
+__device__ __forceinline__ void vs_pixel(const VsThread<NREG>& th, const uint8_t* crow_l, int xl, int yy, int par, int off, uint32_t pix,
+                                         const VsGlobals<NREG>& g)
 {
     constexpr int D = 64 * NREG, NW = (NREG + 1) / 2, NB = 2 * NREG;
     const int lane = th.lane, Wk = th.Wk;
     const size_t vox = (size_t)pix * D;
-    uint32_t ga[NW], gb[NW], gs[NREG];
-    if (th.addA_l) ld_row<NREG>(th.addA_l + vox, 0, ga);
-    if (th.addB_l) ld_row<NREG>(th.addB_l + vox, 0, gb);
-    if (FINAL && th.Sin_l) {
-        const uint32_t* sp = reinterpret_cast<const uint32_t*>(th.Sin_l + vox);
-        if (NREG == 4) { uint4 v = *reinterpret_cast<const uint4*>(sp); gs[0] = v.x; gs[1] = v.y; gs[2] = v.z; gs[3] = v.w; }
-        else if (NREG == 2) { uint2 v = *reinterpret_cast<const uint2*>(sp); gs[0] = v.x; gs[1] = v.y; }
-        else gs[0] = *sp;
-    }
     uint32_t cw[NW], c[NREG], cP2[NREG], acc[NREG];
     ld_row<NREG>(crow_l + xl * D, 0, cw);
     unpack_cost<NREG>(cw, c);
 #pragma unroll
     for (int i = 0; i < NREG; ++i) { acc[i] = 0; cP2[i] = c[i] + th.P2P2; }
+    // The three directions are independent.  All previous-state rows are loaded first and all new rows stored last:
+    // with the loads and stores of one direction between those of another the compiler must assume they alias and
+    // serialises the three dependency chains (ncu r1h: fixed-latency "wait" stalls were the largest stall class).
+    uint8_t* st[NDIR]; uint32_t* sm[NDIR];
+    uint32_t lw[NDIR][NW], Mv[NDIR];
+    bool restart[NDIR];
 #pragma unroll
     for (int k = 0; k < NDIR; ++k) {
         const int dx = k == 0 ? 0 : (k == 1 ? th.sdx : -th.sdx);
@@ -127,60 +144,65 @@ __device__ __forceinline__ void vs_pixel(const VsThread<NREG>& th, const uint8_t
             if (dx > 0) { slot = xl - off; if (slot < 0) slot += Wk; }
             else        { slot = xl + off; if (slot >= Wk) slot -= Wk; }
         }
-        uint8_t* st = th.state_l + (k * th.Wk_max + slot) * D;
-        uint32_t* sm = th.stmin + k * th.Wk_max + slot;
-        uint32_t L[NREG], Mnew = 0;
-        bool restart = false;
+        st[k] = th.state_l + (k * th.Wk_max + slot) * D;
+        sm[k] = th.stmin + k * th.Wk_max + slot;
+        restart[k] = false;
+        const uint8_t* src = st[k];
+        bool boxed = false;
         if (EDGE) {
             const int x = th.xb + xl;
-            restart = (yy == 0) || (dx > 0 && x == 0) || (dx < 0 && x == th.W - 1);
+            restart[k] = (yy == 0) || (dx > 0 && x == 0) || (dx < 0 && x == th.W - 1);
+            const bool from_left = dx > 0 && xl == 0, from_right = dx < 0 && xl == Wk - 1;
+            if (!restart[k] && (from_left || from_right)) {
+                src = th.inbox + ((size_t)((yy - 1) & 1) * 2 + (from_right ? 1 : 0)) * (D + 16);
+                Mv[k] = *reinterpret_cast<const uint32_t*>(src + D);
+                src += lane * NB;
+                boxed = true;
+            }
         }
-        if (EDGE && restart) {
+        if (!boxed) Mv[k] = *sm[k];
+        ld_row<NREG>(src, 0, lw[k]);
+    }
+    uint32_t pw[NDIR][NW], Mn[NDIR];
+#pragma unroll
+    for (int k = 0; k < NDIR; ++k) {
+        uint32_t L[NREG];
+        Mn[k] = 0;
+        if (EDGE && restart[k]) {
 #pragma unroll
             for (int i = 0; i < NREG; ++i) L[i] = c[i];
         } else {
-            const uint8_t* src = st;
-            uint32_t M;
-            bool boxed = false;
-            if (EDGE) {
-                const bool from_left = dx > 0 && xl == 0, from_right = dx < 0 && xl == Wk - 1;
-                if (from_left || from_right) {
-                    src = th.inbox + ((size_t)((yy - 1) & 1) * 2 + (from_right ? 1 : 0)) * (D + 16);
-                    M = *reinterpret_cast<const uint32_t*>(src + D);
-                    src += lane * NB;
-                    boxed = true;
-                }
-            }
-            if (!boxed) M = *sm;
-            uint32_t lw[NW], Lpre[NREG];
-            ld_row<NREG>(src, 0, lw);
-            unpack_cost<NREG>(lw, Lpre);
-            Mnew = sgm_step_u16<NREG>(c, cP2, Lpre, M, th.P1P1, th.lo_mask, th.hi_mask, L);
+            uint32_t Lpre[NREG];
+            unpack_cost<NREG>(lw[k], Lpre);
+            Mn[k] = sgm_step_u16<NREG>(c, cP2, Lpre, Mv[k], th.P1P1, th.lo_mask, th.hi_mask, L);
         }
-        uint32_t pw[NW];
-        pack_cost<NREG>(L, pw);
-        st_row<NREG>(st, 0, pw);
-        *sm = Mnew;                                    // every lane writes the same value
+        pack_cost<NREG>(L, pw[k]);
+#pragma unroll
+        for (int i = 0; i < NREG; ++i) acc[i] += L[i];
+    }
+#pragma unroll
+    for (int k = 0; k < NDIR; ++k) {
+        const int dx = k == 0 ? 0 : (k == 1 ? th.sdx : -th.sdx);
+        st_row<NREG>(st[k], 0, pw[k]);
+        *sm[k] = Mn[k];                                // every lane writes the same value
         if (EDGE) {
             // hand the path over when it leaves the strip (it continues in the neighbour's column next row)
             if (dx > 0 && xl == Wk - 1 && th.inbox_right) {
                 uint8_t* dst = th.inbox_right + ((size_t)par * 2 + 0) * (D + 16);
-                st_row<NREG>(dst + lane * NB, 0, pw);
-                if (lane == 0) *reinterpret_cast<uint32_t*>(dst + D) = Mnew;
+                st_row<NREG>(dst + lane * NB, 0, pw[k]);
+                if (lane == 0) *reinterpret_cast<uint32_t*>(dst + D) = Mn[k];
             }
             if (dx < 0 && xl == 0 && th.inbox_left) {
                 uint8_t* dst = th.inbox_left + ((size_t)par * 2 + 1) * (D + 16);
-                st_row<NREG>(dst + lane * NB, 0, pw);
-                if (lane == 0) *reinterpret_cast<uint32_t*>(dst + D) = Mnew;
+                st_row<NREG>(dst + lane * NB, 0, pw[k]);
+                if (lane == 0) *reinterpret_cast<uint32_t*>(dst + D) = Mn[k];
             }
         }
-#pragma unroll
-        for (int i = 0; i < NREG; ++i) acc[i] += L[i];
     }
-    if (th.addA_l) { uint32_t t[NREG]; unpack_cost<NREG>(ga, t);
+    if (th.addA_l) { uint32_t t[NREG]; unpack_cost<NREG>(g.a, t);
 #pragma unroll
         for (int i = 0; i < NREG; ++i) acc[i] += t[i]; }
-    if (th.addB_l) { uint32_t t[NREG]; unpack_cost<NREG>(gb, t);
+    if (th.addB_l) { uint32_t t[NREG]; unpack_cost<NREG>(g.b, t);
 #pragma unroll
         for (int i = 0; i < NREG; ++i) acc[i] += t[i]; }
     if (!FINAL) {
@@ -191,7 +213,7 @@ __device__ __forceinline__ void vs_pixel(const VsThread<NREG>& th, const uint8_t
     } else {
         if (th.Sin_l) {
 #pragma unroll
-            for (int i = 0; i < NREG; ++i) acc[i] += gs[i];
+            for (int i = 0; i < NREG; ++i) acc[i] += g.s[i];
         }
         if (th.Sout_l) {
             uint32_t* sp = reinterpret_cast<uint32_t*>(th.Sout_l + vox);
@@ -288,9 +310,26 @@ vsweep_kernel(const VsParams prm)
         mbar_wait(&bars[par], (uint32_t)((yy >> 1) & 1));
         const uint8_t* crow_l = cbuf + (size_t)par * Wk_max * D + lane * NB;
         const uint32_t rowpix = (uint32_t)y * (uint32_t)W + (uint32_t)xb;
-        for (int xl = warp; xl < Wk; xl += VS_WARPS) {
-            if (yy == 0 || xl == 0 || xl == Wk - 1) vs_pixel<NREG, NDIR, FINAL, true>(th, crow_l, xl, yy, par, off, rowpix + xl);
-            else vs_pixel<NREG, NDIR, FINAL, false>(th, crow_l, xl, yy, par, off, rowpix + xl);
+        // global rows are fetched PD pixels ahead (the warp's pixels are xl = warp, warp + VS_WARPS, ...): with only
+        // 16 warps per SM an L2-miss (~2 us) is not hidden by other warps (ncu r1g: 27 % of the stall samples of the
+        // down pass sat on the first use of the horizontal-volume row)
+        // The ring is indexed statically (inner loop unrolled by PD): copying a register that is still waiting for its
+        // load would stall on the copy, which is exactly what a rotating ring does.
+        constexpr int PD = FINAL ? 2 : 4;
+        VsGlobals<NREG> gq[PD];
+#pragma unroll
+        for (int u = 0; u < PD; ++u)
+            if (warp + u * VS_WARPS < Wk) vs_fetch<NREG, FINAL>(th, rowpix + warp + u * VS_WARPS, gq[u]);
+        for (int xl0 = warp; xl0 < Wk; xl0 += PD * VS_WARPS) {
+#pragma unroll
+            for (int u = 0; u < PD; ++u) {
+                const int xl = xl0 + u * VS_WARPS;
+                if (xl < Wk) {
+                    if (yy == 0 || xl == 0 || xl == Wk - 1) vs_pixel<NREG, NDIR, FINAL, true>(th, crow_l, xl, yy, par, off, rowpix + xl, gq[u]);
+                    else vs_pixel<NREG, NDIR, FINAL, false>(th, crow_l, xl, yy, par, off, rowpix + xl, gq[u]);
+                    if (xl + PD * VS_WARPS < Wk) vs_fetch<NREG, FINAL>(th, rowpix + xl + PD * VS_WARPS, gq[u]);
+                }
+            }
         }
         if (++off == Wk) off = 0;
         // everyone is done with this row: cost buffer `par` is free, outgoing paths are visible after the barrier
@@ -385,7 +424,7 @@ static int vs_launch_t(fsgm_ctx* c, int n, int cs, size_t smem, const VsParams& 
 int launch_vsweep(fsgm_ctx* c, int n, int cs, int ndir, bool final_, const uint8_t* C, const uint8_t* addA, const uint8_t* addB,
                   const uint16_t* Sin, uint16_t* Sout, uint32_t* minC, uint16_t* rec, int W, int H, int D, int P1, int P2, int up)
 {
-    StageScope ss(c, ST_SWEEP);
+    StageScope ss(c, ST_VSWEEP);
     VsParams p{};
     p.C = C; p.addA = addA; p.addB = addB; p.Sin = Sin; p.Sout = Sout; p.minC = minC; p.rec = rec;
     p.W = W; p.H = H; p.Wk = (W + cs - 1) / cs; p.P1 = P1; p.P2 = P2; p.up = up;

@@ -90,6 +90,14 @@ FSGM_API int fsgm_calc_cost_sgm_batch(fsgm_ctx* ctx, int n_pairs, const uint8_t*
                              const double* offsetFromPosD0, int P1, int P2, const fsgm_epi_opts* opts,
                              uint32_t* bestD, uint32_t* minC);
 
+/* Enqueue-only form of the batch call: returns when all copies and kernels are queued.  The host buffers must stay valid,
+ * and the outputs must not be read, until fsgm_synchronize(ctx).  Consecutive calls overlap (the host->device copies of one
+ * call run under the kernels of the previous one); use pinned host memory for the copies to be truly asynchronous. */
+FSGM_API int fsgm_calc_cost_sgm_batch_async(fsgm_ctx* ctx, int n_pairs, const uint8_t* I1, const uint8_t* I2, int width, int height,
+                             int dMax, double vMax, const double* pixelPosD0, const double* normlizeDirection,
+                             const double* offsetFromPosD0, int P1, int P2, const fsgm_epi_opts* opts,
+                             uint32_t* bestD, uint32_t* minC);
+
 /* Device-resident form: inputs and outputs already in HBM, asynchronous on the context's stream. */
 FSGM_API int fsgm_calc_cost_sgm_dev(fsgm_ctx* ctx, int n_pairs, const uint8_t* d_I1, const uint8_t* d_I2, int width, int height,
                            int dMax, double vMax, const double* d_pixelPosD0, const double* d_normlizeDirection,
