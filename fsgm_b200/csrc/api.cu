@@ -469,7 +469,16 @@ int fsgm_calc_cost_sgm_dev(fsgm_ctx* c, int n, const uint8_t* d_I1, const uint8_
     const size_t budget = std::max(c->arena_bytes, c->mem_budget);
     const size_t per_pair = epi_scratch_bytes(c, 1, W, H, D, P1, P2, o);
     int chunk = (int)std::min<size_t>(n, std::max<size_t>(1, budget / per_pair));
-    FSGM_TRY(arena_reserve(c, epi_scratch_bytes(c, chunk, W, H, D, P1, P2, o)));
+    {   // keep chunks at whole waves of the cluster kernels when they apply (see fast_pairs)
+        const int cs = fast_path_cluster(c, W, D, P1, P2, 24, o);
+        if (cs && chunk < n) {
+            fast_pairs(c, chunk, cs, D, W, o.paths == 8 ? 3 : 1);
+            if (chunk >= c->clusters_max) chunk -= chunk % c->clusters_max;
+        }
+    }
+    size_t need = 0;                                  // chunks differ in their fast/generic split: reserve the largest
+    for (int i0 = 0; i0 < n; i0 += chunk) need = std::max(need, epi_scratch_bytes(c, std::min(chunk, n - i0), W, H, D, P1, P2, o));
+    FSGM_TRY(arena_reserve(c, need));
     const size_t N = (size_t)W * H;
     for (int i0 = 0; i0 < n; i0 += chunk) {
         const int m = std::min(chunk, n - i0);

@@ -203,13 +203,21 @@ __device__ __forceinline__ uint32_t ref_round_clamp_w(double w, uint32_t hi)
     return min((f + 1u) >> 1, hi);
 }
 
+// (u8)(1.0*s/25 + 0.5) == (2s + 25)/50 == (s*2622 + 32775) >> 16 for s <= 600; the quotient (<= 24) is byte 2 of the product
+__device__ __forceinline__ uint32_t box_norm4_fast(uint32_t lo, uint32_t hi)   // lo: labels 0,2 as u16x2; hi: labels 1,3
+{
+    const uint32_t p0 = (lo & 0xFFFFu) * 2622u + 32775u, p2 = (lo >> 16) * 2622u + 32775u;
+    const uint32_t p1 = (hi & 0xFFFFu) * 2622u + 32775u, p3 = (hi >> 16) * 2622u + 32775u;
+    return __byte_perm(__byte_perm(p0, p1, 0x0062), __byte_perm(p2, p3, 0x0062), 0x5410);
+}
+
 template <int D4>      // D = 4*D4 labels, D4 in {16, 32, 64}
 __global__ void __launch_bounds__(FC_THREADS)
 epi_cost_fused_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restrict__ cen2,
                       const double* __restrict__ Pd0, const double* __restrict__ dirn, const double* __restrict__ O,
                       const double* __restrict__ vz, int W, int H, uint8_t* __restrict__ C)
 {
-    constexpr int D = 4 * D4, NPIX = FC_TX + 4, IPT = FC_THREADS / D4;     // IPT pixels are processed per pass
+    constexpr int NPIX = FC_TX + 4, IPT = FC_THREADS / D4, XP = FC_TX / IPT;   // XP consecutive output columns per thread
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* raw_row = reinterpret_cast<uint32_t*>(smem_raw);                              // [NPIX][D4]
     uint32_t* hring = raw_row + NPIX * D4;                                                  // [5][FC_TX][D4]
@@ -224,9 +232,15 @@ epi_cost_fused_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restr
     const double* PdX = Pd0 + (size_t)pair * 2 * N; const double* PdY = PdX + N;
     const double* DrX = dirn + (size_t)pair * 2 * N; const double* DrY = DrX + N;
     const double* Op = O + pair * N;
-    uint32_t* Cout = reinterpret_cast<uint32_t*>(C + pair * N * D);
+    uint32_t* Cout = reinterpret_cast<uint32_t*>(C + pair * N * (size_t)(4 * D4)) + q;
     const double vz0 = vz[4 * q], vz1 = vz[4 * q + 1], vz2 = vz[4 * q + 2], vz3 = vz[4 * q + 3];
     const int yend = min(y0 + FC_TY, H);
+    const uint32_t wmax = (uint32_t)(W - 1), hmax = (uint32_t)(H - 1);
+
+    for (int i = tid; i < 5 * FC_TX * D4; i += FC_THREADS) hring[i] = 0;      // rows before the window count as zero
+    uint32_t vlo[XP], vhi[XP];                                               // running vertical 5-sums (u16x2) per column
+#pragma unroll
+    for (int k = 0; k < XP; ++k) { vlo[k] = 0; vhi[k] = 0; }
 
     for (int r = y0 - 2; r < yend + 2; ++r) {
         const int yc = min(max(r, 0), H - 1);
@@ -234,11 +248,11 @@ epi_cost_fused_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restr
         if (tid < NPIX) {
             const int xc = min(max(x0 - 2 + tid, 0), W - 1);
             const size_t p = (size_t)yc * W + xc;
-            // doubled constants: w = 2*(b + (off*vz)*u) = 2b + ((2 off)*vz)*u exactly
-            geo[tid * 5 + 0] = __dmul_rn(__dsub_rn(PdX[p], 1.0), 2.0); geo[tid * 5 + 1] = __dmul_rn(__dsub_rn(PdY[p], 1.0), 2.0);
-            geo[tid * 5 + 2] = DrX[p]; geo[tid * 5 + 3] = DrY[p]; geo[tid * 5 + 4] = __dmul_rn(Op[p], 2.0);
-            gcen[tid] = cen1[pair * N + p];
             const double a0 = PdX[p], a1 = PdY[p], a2 = DrX[p], a3 = DrY[p], a4 = Op[p];
+            // doubled constants: w = 2*(b + (off*vz)*u) = 2b + ((2 off)*vz)*u exactly
+            geo[tid * 5 + 0] = __dmul_rn(__dsub_rn(a0, 1.0), 2.0); geo[tid * 5 + 1] = __dmul_rn(__dsub_rn(a1, 1.0), 2.0);
+            geo[tid * 5 + 2] = a2; geo[tid * 5 + 3] = a3; geo[tid * 5 + 4] = __dmul_rn(a4, 2.0);
+            gcen[tid] = cen1[pair * N + p];
             const bool fin = isfinite(a0) && isfinite(a1) && isfinite(a2) && isfinite(a3) && fabs(a4) <= 1e300;
             gslow[tid] = fin ? 0u : 1u;
         }
@@ -247,37 +261,46 @@ epi_cost_fused_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restr
         for (int i = i0; i < NPIX; i += IPT) {
             const double bx = geo[i * 5], by = geo[i * 5 + 1], ux = geo[i * 5 + 2], uy = geo[i * 5 + 3], off = geo[i * 5 + 4];
             const uint32_t c1 = gcen[i];
-            const bool slow = gslow[i] != 0;           // uniform across the threads that share pixel i
             uint32_t packed = 0;
             const double vzs[4] = {vz0, vz1, vz2, vz3};
+            if (gslow[i] == 0) {                       // uniform across the threads that share pixel i
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const double t = __dmul_rn(off, vzs[j]);
-                const double wx = __dadd_rn(bx, __dmul_rn(t, ux)), wy = __dadd_rn(by, __dmul_rn(t, uy));
-                uint32_t x2 = ref_round_clamp_w(wx, (uint32_t)(W - 1));
-                uint32_t y2 = ref_round_clamp_w(wy, (uint32_t)(H - 1));
-                if (slow) { if (wx != wx) x2 = 0; if (wy != wy) y2 = 0; }
-                packed |= (uint32_t)__popc(c1 ^ __ldg(c2 + (y2 * (uint32_t)W + x2))) << (8 * j);
+                for (int j = 0; j < 4; ++j) {
+                    const double t = __dmul_rn(off, vzs[j]);
+                    const uint32_t x2 = ref_round_clamp_w(__dadd_rn(bx, __dmul_rn(t, ux)), wmax);
+                    const uint32_t y2 = ref_round_clamp_w(__dadd_rn(by, __dmul_rn(t, uy)), hmax);
+                    packed |= (uint32_t)__popc(c1 ^ __ldg(c2 + (y2 * (uint32_t)W + x2))) << (8 * j);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const double t = __dmul_rn(off, vzs[j]);
+                    const double wx = __dadd_rn(bx, __dmul_rn(t, ux)), wy = __dadd_rn(by, __dmul_rn(t, uy));
+                    const uint32_t x2 = (wx != wx) ? 0u : ref_round_clamp_w(wx, wmax);
+                    const uint32_t y2 = (wy != wy) ? 0u : ref_round_clamp_w(wy, hmax);
+                    packed |= (uint32_t)__popc(c1 ^ __ldg(c2 + (y2 * (uint32_t)W + x2))) << (8 * j);
+                }
             }
             raw_row[i * D4 + q] = packed;
         }
         __syncthreads();
-        // (2) horizontal 5-sum -> ring; vertical 5-sum -> output row r-2
+        // (2) horizontal 5-sums by a sliding window over this thread's XP consecutive columns; vertical 5-sums as
+        //     running sums (add the new row, drop the row that leaves the window: it sits in the ring slot being rewritten)
         const int slot = (r + 10) % 5;
-        for (int xl = i0; xl < FC_TX; xl += IPT) {
-            const uint32_t* rr = raw_row + xl * D4 + q;
-            const uint32_t h = rr[0] + rr[D4] + rr[2 * D4] + rr[3 * D4] + rr[4 * D4];      // bytes <= 120: no carries
-            hring[(slot * FC_TX + xl) * D4 + q] = h;
-            const int yo = r - 2, xo = x0 + xl;
-            if (yo >= y0 && xo < W) {
-                uint32_t lo = h & 0x00FF00FFu, hi = (h >> 8) & 0x00FF00FFu;
+        const uint32_t* rr = raw_row + (i0 * XP) * D4 + q;
+        uint32_t* hr = hring + (slot * FC_TX + i0 * XP) * D4 + q;
+        uint32_t h = rr[0] + rr[D4] + rr[2 * D4] + rr[3 * D4] + rr[4 * D4];               // bytes <= 120: no carries
+        const int yo = r - 2;
+        const bool emit = yo >= y0;
+        uint32_t* crow = Cout + ((size_t)yo * W + x0 + i0 * XP) * D4;
 #pragma unroll
-                for (int k = 1; k < 5; ++k) {
-                    const uint32_t v = hring[(((slot + k) % 5) * FC_TX + xl) * D4 + q];
-                    lo += v & 0x00FF00FFu; hi += (v >> 8) & 0x00FF00FFu;
-                }
-                Cout[((size_t)yo * W + xo) * D4 + q] = box_norm4(lo, hi);
-            }
+        for (int k = 0; k < XP; ++k) {
+            if (k) h = h - rr[(k - 1) * D4] + rr[(k + 4) * D4];
+            const uint32_t old = hr[k * D4];
+            hr[k * D4] = h;
+            vlo[k] += (h & 0x00FF00FFu) - (old & 0x00FF00FFu);
+            vhi[k] += ((h >> 8) & 0x00FF00FFu) - ((old >> 8) & 0x00FF00FFu);
+            if (emit && x0 + i0 * XP + k < W) crow[k * D4] = box_norm4_fast(vlo[k], vhi[k]);
         }
         __syncthreads();
     }
