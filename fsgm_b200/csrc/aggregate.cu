@@ -217,6 +217,104 @@ sweep_fast_kernel(const SweepParams prm)
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Horizontal sweeps with TMA staging.  Along an image row the cost rows of consecutive steps are contiguous in memory,
+// so one elected lane fetches HCH steps (HCH*D bytes) per 1-D bulk copy (cp.async.bulk + mbarrier complete_tx) into a
+// per-warp two-chunk shared-memory ring; the serial chain then reads its cost row with one LDS and never waits on HBM
+// (the register-prefetch kernel spent most of its stall samples on the first use of the prefetched row: long scoreboard).
+// Used for the two horizontal directions next to the row-synchronous cluster kernels (D in {64,128,256}, no-wrap domain).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int HCH = 8;                       // steps per chunk
+
+__device__ __forceinline__ uint32_t hs_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int NREG>
+__global__ void __launch_bounds__(SWEEP_WARPS * 32)
+hsweep_tma_kernel(const SweepParams prm)
+{
+    constexpr int D = 64 * NREG, NB = 2 * NREG;
+    __shared__ __align__(128) uint8_t ring[SWEEP_WARPS][2][HCH * D];
+    __shared__ __align__(8) uint64_t bars[SWEEP_WARPS][2];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int gw = blockIdx.x * SWEEP_WARPS + wib;
+    const int W = prm.W, H = prm.H;
+    const size_t N = (size_t)W * H;
+    const bool active = gw < prm.line_start[prm.n_dirs];
+    int k = 0;
+    if (active) while (gw >= prm.line_start[k + 1]) ++k;
+    const int y = active ? gw - prm.line_start[k] : 0;
+    const int dx = dir_dx(prm.dir[k]);                        // +1 or -1 (dy == 0 for every direction of this launch)
+    const uint8_t* __restrict__ Crow = prm.C + (blockIdx.y * N + (size_t)y * W) * D;
+    uint8_t* __restrict__ Lrow = prm.L[k] + (blockIdx.y * N + (size_t)y * W) * D + lane * NB;
+    if (!active) return;
+
+    const int nch = (W + HCH - 1) / HCH;
+    // chunk c covers steps [c*HCH, min(W, (c+1)*HCH)); in memory that is a contiguous run of pixels in either direction
+    auto issue = [&](int c) {
+        const int t0 = c * HCH, cnt = min(HCH, W - t0);
+        const int xlo = dx > 0 ? t0 : W - t0 - cnt;
+        const uint32_t bytes = (uint32_t)cnt * D;
+        uint64_t* bar = &bars[wib][c & 1];
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(hs_smem_u32(bar)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(hs_smem_u32(ring[wib][c & 1])), "l"(Crow + (size_t)xlo * D), "r"(bytes), "r"(hs_smem_u32(bar)) : "memory");
+    };
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(hs_smem_u32(&bars[wib][0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(hs_smem_u32(&bars[wib][1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        issue(0);
+        if (nch > 1) issue(1);
+    }
+    __syncwarp();
+
+    const uint32_t lo_mask = (lane == 0) ? (STEP_BIG2 & 0x0000FFFFu) : 0u;
+    const uint32_t hi_mask = (lane == 31) ? (STEP_BIG2 & 0xFFFF0000u) : 0u;
+    const uint32_t P1P1 = (uint32_t)prm.P1 * 0x10001u, P2P2 = (uint32_t)prm.P2 * 0x10001u;
+    uint32_t Lr[NREG];
+#pragma unroll
+    for (int i = 0; i < NREG; ++i) Lr[i] = 0;
+    uint32_t M = 0;
+    bool first = true;
+    for (int c = 0; c < nch; ++c) {
+        const int t0 = c * HCH, cnt = min(HCH, W - t0);
+        {   // wait for the chunk (phase parity = number of earlier uses of this buffer, mod 2)
+            const uint32_t parity = (uint32_t)((c >> 1) & 1), bar = hs_smem_u32(&bars[wib][c & 1]);
+            asm volatile("{\n\t.reg .pred p;\n\tHW_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra HD_%=;\n\tbra HW_%=;\n\tHD_%=:\n\t}"
+                         ::"r"(bar), "r"(parity) : "memory");
+        }
+        const uint8_t* buf = ring[wib][c & 1] + lane * NB;
+        const int xlo = dx > 0 ? t0 : W - t0 - cnt;
+#pragma unroll 4
+        for (int s = 0; s < cnt; ++s) {
+            const int off = dx > 0 ? s : cnt - 1 - s;                    // position inside the chunk, memory order
+            uint32_t cw[(NREG + 1) / 2];
+            if (NREG == 1) cw[0] = *reinterpret_cast<const uint16_t*>(buf + off * D);
+            else if (NREG == 2) cw[0] = *reinterpret_cast<const uint32_t*>(buf + off * D);
+            else { const uint2 v = *reinterpret_cast<const uint2*>(buf + off * D); cw[0] = v.x; cw[1] = v.y; }
+            uint32_t cc[NREG], cP2[NREG], Ln[NREG];
+            unpack_cost<NREG>(cw, cc);
+#pragma unroll
+            for (int i = 0; i < NREG; ++i) cP2[i] = cc[i] + P2P2;
+            // at the path start the zero state with M = 0 makes the step return L = C; the minimum is then forced to 0
+            const uint32_t m = sgm_step_u16<NREG>(cc, cP2, Lr, M, P1P1, lo_mask, hi_mask, Ln);
+            M = first ? 0u : m;
+            first = false;
+#pragma unroll
+            for (int i = 0; i < NREG; ++i) Lr[i] = Ln[i];
+            uint32_t pw[(NREG + 1) / 2];
+            pack_cost<NREG>(Lr, pw);
+            uint8_t* dst = Lrow + (size_t)(xlo + off) * D;
+            if (NREG == 1) *reinterpret_cast<uint16_t*>(dst) = (uint16_t)pw[0];
+            else if (NREG == 2) *reinterpret_cast<uint32_t*>(dst) = pw[0];
+            else *reinterpret_cast<uint2*>(dst) = make_uint2(pw[0], pw[1]);
+        }
+        __syncwarp();                                                    // every lane is done reading this buffer
+        if (lane == 0 && c + 2 < nch) issue(c + 2);
+    }
+}
+
 template <int NREG, int MODE, bool WRAP, bool ADAPT>
 __global__ void __launch_bounds__(SWEEP_WARPS * 32)
 sweep_kernel(const SweepParams prm)
@@ -396,6 +494,15 @@ int launch_sweeps(fsgm_ctx* c, int n, const uint8_t* C, const uint8_t* I1, int W
     const bool wrap = sweep_needs_wrap(P1, P2, cmax);
     const bool adapt = adaptive_thr > 0;
     dim3 grid((p.line_start[n_dirs] + SWEEP_WARPS - 1) / SWEEP_WARPS, n);
+    bool all_horizontal = true;
+    for (int k = 0; k < n_dirs; ++k) all_horizontal &= dir_dy(dirs[k]) == 0;
+    if (all_horizontal && mode == LM_FULL && !wrap && !adapt && nreg <= 4) {
+        if (nreg == 4) hsweep_tma_kernel<4><<<grid, SWEEP_WARPS * 32, 0, c->stream>>>(p);
+        else if (nreg == 2) hsweep_tma_kernel<2><<<grid, SWEEP_WARPS * 32, 0, c->stream>>>(p);
+        else hsweep_tma_kernel<1><<<grid, SWEEP_WARPS * 32, 0, c->stream>>>(p);
+        FSGM_LAUNCHED(c);
+        return FSGM_OK;
+    }
     switch (nreg) {
         case 1: sweep_dispatch<1>(p, mode, wrap, adapt, grid, c->stream); break;
         case 2: sweep_dispatch<2>(p, mode, wrap, adapt, grid, c->stream); break;
