@@ -35,7 +35,7 @@ sys.path.insert(0, ROOT)
 
 W, H, D, PATHS, P1, P2, VMAX = 1242, 375, 256, 8, 6, 64, 0.3
 METRIC = "frame-pairs/s (KITTI 1242x375, 256 labels, 8 paths)"
-TRAFFIC_VSWEEP_P30 = None      # bytes per launch at 30 pairs, filled from the committed ncu capture
+TRAFFIC_VSWEEP_P30 = 14.38e9   # dram read+write bytes per launch at 30 pairs: mean of the down (17.85 GB) and up (10.90 GB) pass, profiles/r1i_kernels_p30.txt
 
 
 def hbm_peak():
@@ -272,7 +272,7 @@ def run_ours(args):
             k_ms, k_launches = stages["vsweep"]
             k_name = "vsweep_kernel (3 non-horizontal directions per pass; cost rows by TMA, path state in smem, WTA fused)"
             per_launch_bytes = P * N * D * 9
-            # dram__bytes_read+write per launch from profiles/r1g_vsweep_p30.txt (ncu --set full), mean of the two passes
+            # dram__bytes_read+write per launch from profiles/r1i_kernels_p30.txt (ncu --set full), mean of the two passes
             traffic = (TRAFFIC_VSWEEP_P30 * P / 30.0) if TRAFFIC_VSWEEP_P30 else None
         else:
             k_ms, k_launches = stages.get("sweep", (0.0, 0))
