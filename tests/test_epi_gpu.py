@@ -193,3 +193,33 @@ def test_cluster_path_equals_oracle_and_generic(ctx, oracle, W, H, D, paths, pas
         assert np.array_equal(outs[cluster][0].astype(np.uint32), ref["Sp"])
         assert np.array_equal(outs[cluster][1], ref["minC"])
         _cmp_bestD(outs[cluster][2], ref, D)
+
+
+def test_full_kitti_size_all_paths_agree(ctx, oracle):
+    """BASELINE.json's full size (1242x375, 256 labels, 8 paths): the cluster kernels (a full wave of pairs), the generic
+    kernels and the CPU oracle agree bit for bit; the batch result equals the single-pair results."""
+    from fsgm_b200 import api
+    W, H, D = 1242, 375, 256
+    o = api.epi_opts(paths=8)
+    p0 = synth.epipolar_pair(W, H, D, seed=77)
+    ref = _oracle_epi(oracle, p0, D, 6, 64, 8)                      # ~7 s with the reference build
+    n = 15                                                          # one full wave -> cluster path for every pair
+    ps = [p0] + [synth.epipolar_pair(W, H, D, seed=200 + i) for i in range(2)]
+    idx = [0, 1, 2] * 5
+    st = lambda k: np.ascontiguousarray(np.stack([ps[i][k] for i in idx]))
+    ctx.tune(1, 0)
+    bF, mF = ctx.calc_cost_sgm_batch(st("I1"), st("I2"), D, 0.3, st("Pd0"), st("dirn"), st("O"), 6, 64, opts=o)
+    assert np.array_equal(mF[0], ref["minC"])
+    _cmp_bestD(bF[0], ref, D)
+    for j in range(3, n):
+        assert np.array_equal(bF[j], bF[j % 3]) and np.array_equal(mF[j], mF[j % 3])
+    ctx.tune(1, -1)                                                 # generic kernels only
+    for i in range(3):
+        p = ps[i]
+        b, m, _, _ = ctx.calc_cost_sgm(p["I1"], p["I2"], D, 0.3, p["Pd0"], p["dirn"], p["O"], 6, 64, opts=o)
+        assert np.array_equal(b, bF[i]) and np.array_equal(m, mF[i])
+    ctx.tune(1, 0)
+    # sanity of the synthetic scene itself (not a parity statement): a large share of the pixels recovers the ground-truth
+    # label to within two labels (near the epipole neighbouring labels map to the same pixel, so it cannot be all)
+    lab = ref["Sp"].argmin(-1)
+    assert (np.abs(lab - p0["gt_label"]) <= 2).mean() > 0.3
