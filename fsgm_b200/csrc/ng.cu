@@ -18,7 +18,7 @@
 namespace fsgm {
 
 constexpr int NGD = 108;              // DIRECTION_NUM * (N + M) * MV_PER_HINT (:194)
-constexpr int NG_THREADS = 256;
+constexpr int NG_THREADS = 512;
 
 struct Top2 { int mvx[2], mvy[2], cost[2]; };       // the two extra slots L[D], L[D+1] of the reference (:196)
 
@@ -55,8 +55,9 @@ ng_kernel(const NgParams prm)
     __shared__ int cmx[2][NGD], cmy[2][NGD];            // candidate mvs: [pixel parity] (cur / previous pixel)
     __shared__ int ccost[NGD];
     __shared__ int Lc[4][NGD];                          // this pixel's path costs, directions L1,L2,L3,L4
-    __shared__ int L1prev[NGD];                         // L1 costs of the previous pixel
-    __shared__ int pmx[3][NGD], pmy[3][NGD], pco[3][NGD];   // predecessors of L2 (x-1,y-1), L3 (x,y-1), L4 (x+1,y-1)
+    // predecessor entries (mvx, mvy, path cost, -) of the four directions: [0] L1 = previous pixel, [1] L2 = (x-1,y-1),
+    // [2] L3 = (x,y-1), [3] L4 = (x+1,y-1); one LDS.128 per compatibility test
+    __shared__ int4 pent[4][NGD];
     __shared__ Top2 top1[2];                            // L1's two ring slots
     __shared__ Top2 tcur[4];                            // top-2 being built for this pixel
     __shared__ int preMin[4];
@@ -66,7 +67,7 @@ ng_kernel(const NgParams prm)
     __shared__ int rf, rr;
 
     if (tid < 2) { for (int i = 0; i < 2; ++i) { top1[tid].mvx[i] = 0; top1[tid].mvy[i] = 0; top1[tid].cost[i] = 0; } }
-    if (tid < NGD) { L1prev[tid] = 0; cmx[0][tid] = cmx[1][tid] = cmy[0][tid] = cmy[1][tid] = 0; }
+    if (tid < NGD) { pent[0][tid] = make_int4(0, 0, 0, 0); cmx[0][tid] = cmx[1][tid] = cmy[0][tid] = cmy[1][tid] = 0; }
     if (tid < 31 && !prm.rand_stream) rstate[tid] = prm.rng_state[pair * 31 + tid];
     if (tid == 0) { rf = 3; rr = 0; }                   // glibc TYPE_3: front = state + SEP_3, rear = state
     __syncthreads();
@@ -103,9 +104,8 @@ ng_kernel(const NgParams prm)
                     const int q = i / NGD, d = i - q * NGD, xs = x + q - 1;
                     if (xs >= 0 && xs < W) {
                         const size_t cell = (size_t)preRow * W + xs;
-                        pmx[q][d] = mvrow[(cell * NGD + d) * 2];
-                        pmy[q][d] = mvrow[(cell * NGD + d) * 2 + 1];
-                        pco[q][d] = Lrow[((size_t)q * 2 * W + cell) * NGD + d];
+                        const int2 mv = *reinterpret_cast<const int2*>(mvrow + (cell * NGD + d) * 2);
+                        pent[1 + q][d] = make_int4(mv.x, mv.y, (int)Lrow[((size_t)q * 2 * W + cell) * NGD + d], 0);
                     }
                 }
             }
@@ -156,20 +156,23 @@ ng_kernel(const NgParams prm)
                 int out;
                 if (start) out = ccost[d];
                 else {
-                    const int* qx; const int* qy; const int* qc; int pixPre;
-                    if (dir == 0) { qx = cmx[cp ^ 1]; qy = cmy[cp ^ 1]; qc = L1prev; pixPre = I1[p - 1]; }
-                    else { qx = pmx[dir - 1]; qy = pmy[dir - 1]; qc = pco[dir - 1]; pixPre = I1[p - W + (dir - 2)]; }
+                    const int4* q = pent[dir];
+                    const int pixPre = dir == 0 ? I1[p - 1] : I1[p - W + (dir - 2)];
                     const int P2 = abs(pixCur - pixPre) > 50 ? prm.P2 / 8 : prm.P2;          // :101-105
                     const uint32_t pm = (uint32_t)preMin[dir];
                     const uint32_t far_ = (pm + (uint32_t)P2) & 0xFFu;
                     uint32_t same = far_, near_ = far_;
                     const int mx = cmx[cp][d], my = cmy[cp][d];
+#pragma unroll 4
                     for (int d2 = 0; d2 < NGD; ++d2) {
-                        const int ax = qx[d2], ay = qy[d2];
-                        const uint32_t c2 = (uint32_t)qc[d2];
-                        if (ax == mx && ay == my) same = c2 & 0xFFu;                          // last match wins (:71-72)
-                        else if ((uint32_t)(ax - mx + 2) <= 4u && (uint32_t)(ay - my + 2) <= 4u)
-                            near_ = min(near_, (c2 + (uint32_t)prm.P1) & 0xFFu);
+                        // branch-free: data-dependent branches here cost more than the work they skip
+                        const int4 e = q[d2];
+                        const uint32_t c2 = (uint32_t)e.z;
+                        const bool eq = (e.x == mx) & (e.y == my);
+                        const bool nr = ((uint32_t)(e.x - mx + 2) <= 4u) & ((uint32_t)(e.y - my + 2) <= 4u);
+                        same = eq ? (c2 & 0xFFu) : same;                                      // last match wins (:71-72)
+                        const uint32_t cand = (nr & !eq) ? ((c2 + (uint32_t)prm.P1) & 0xFFu) : 0xFFu;
+                        near_ = min(near_, cand);
                     }
                     out = ccost[d] + (int)min(min(far_, same), near_) - (int)pm;                // int, not truncated (:80)
                 }
@@ -240,9 +243,8 @@ ng_kernel(const NgParams prm)
             {
                 const size_t cell = (size_t)curRow * W + x;
                 for (int i = tid; i < NGD; i += NG_THREADS) {
-                    mvrow[(cell * NGD + i) * 2] = cmx[cp][i];
-                    mvrow[(cell * NGD + i) * 2 + 1] = cmy[cp][i];
-                    L1prev[i] = Lc[0][i];
+                    *reinterpret_cast<int2*>(mvrow + (cell * NGD + i) * 2) = make_int2(cmx[cp][i], cmy[cp][i]);
+                    pent[0][i] = make_int4(cmx[cp][i], cmy[cp][i], Lc[0][i], 0);
                 }
                 for (int i = tid; i < 3 * NGD; i += NG_THREADS) {
                     const int q = i / NGD, d = i - q * NGD;

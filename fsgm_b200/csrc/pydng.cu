@@ -156,11 +156,12 @@ pydng_sweep_kernel(const NgSweepParams prm)
                 const uint32_t cs = c2 & 0xFFu, cn = (c2 + (uint32_t)prm.P1) & 0xFFu;
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) {
-                    const bool eq = (ax == mx[j]) && (ay == my[j]);
+                    // branch-free (data-dependent branches cost more than the work they skip)
+                    const bool eq = (ax == mx[j]) & (ay == my[j]);
                     // |a-b| <= 2 in wrap-around int arithmetic, like abs(int - int) in the reference
-                    const bool nr = (uint32_t)(ax - mx[j] + 2) <= 4u && (uint32_t)(ay - my[j] + 2) <= 4u;
-                    if (eq) same[j] = cs;
-                    else if (nr) near_[j] = min(near_[j], cn);
+                    const bool nr = ((uint32_t)(ax - mx[j] + 2) <= 4u) & ((uint32_t)(ay - my[j] + 2) <= 4u);
+                    same[j] = eq ? cs : same[j];
+                    near_[j] = min(near_[j], (nr & !eq) ? cn : 0xFFu);
                 }
             }
             uint32_t m = 255;
