@@ -49,9 +49,16 @@ class GpuBackend:
         self.ctx = ctx
         self.device = torch.device("cuda", ctx.device)
 
+    def upload(self, pair):
+        """copy a pair's arrays to this GPU once (device-resident measurements reuse the result)"""
+        dev = {k: torch.from_numpy(np.ascontiguousarray(pair[k][None])).to(self.device) for k in ("I1", "I2", "Pd0", "dirn", "O")}
+        dev["_device"] = True
+        return dev
+
     def cost_volume(self, pair, D, vMax):
-        I1, I2 = (torch.from_numpy(pair[k][None]).to(self.device) for k in ("I1", "I2"))
-        Pd0, dirn, O = (torch.from_numpy(pair[k][None]).to(self.device) for k in ("Pd0", "dirn", "O"))
+        if not pair.get("_device"):
+            pair = self.upload(pair)
+        I1, I2, Pd0, dirn, O = (pair[k] for k in ("I1", "I2", "Pd0", "dirn", "O"))
         _, H, W = I1.shape
         cen1 = torch.empty((1, H, W), dtype=torch.int32, device=self.device)
         cen2 = torch.empty_like(cen1)
@@ -63,9 +70,12 @@ class GpuBackend:
 
     def partial(self, Cvol, I1, P1, P2, dirs, n_pad):
         H, W, D = Cvol.shape
-        out = torch.zeros(n_pad * D, dtype=torch.int16, device=self.device)
-        self.ctx.epi_partial_dev(Cvol, I1, P1, P2, dirs, out)
-        return out
+        key = (n_pad, D)
+        if getattr(self, "_partial_key", None) != key:       # reused across calls: the kernel rewrites every real voxel,
+            self._partial = torch.zeros(n_pad * D, dtype=torch.int16, device=self.device)   # the padding stays zero
+            self._partial_key = key
+        self.ctx.epi_partial_dev(Cvol, I1, P1, P2, dirs, self._partial)
+        return self._partial
 
     def wta(self, Sp_slab, next0, D, O_slab, vMax):
         n = Sp_slab.numel() // D
@@ -82,7 +92,7 @@ def epi_direction_split(backend, pair, D, vMax, P1, P2, paths=8, group=None):
     """calc_cost_sgm for ONE pair with the scan directions split over the ranks of `group`.
     Returns (bestD, minC) as uint32 numpy arrays [H][W], identical on every rank and identical to the single-GPU call."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    H, W = pair["I1"].shape
+    H, W = pair["I1"].shape[-2:]
     N = H * W
     slab = slab_pixels(N, world)
     n_pad = slab * world
@@ -101,11 +111,21 @@ def epi_direction_split(backend, pair, D, vMax, P1, P2, paths=8, group=None):
     firsts = [torch.empty(1, dtype=torch.int32, device=Sp_slab.device) for _ in range(world)]
     dist.all_gather(firsts, Sp_slab[:1].to(torch.int32) & 0xFFFF, group=group)
     next0 = firsts[rank + 1].to(torch.int16) if rank + 1 < world else None
-    O_pad = np.zeros(n_pad, np.float64)
-    O_pad[:N] = pair["O"].reshape(-1)
-    bestD, minC = backend.wta(Sp_slab, next0, D, backend.to_device(O_pad[rank * slab:(rank + 1) * slab]), vMax)
+    if pair.get("_device"):
+        O_slab = torch.zeros(slab, dtype=torch.float64, device=pair["O"].device)
+        lo, hi = rank * slab, min(N, (rank + 1) * slab)
+        if hi > lo:
+            O_slab[:hi - lo] = pair["O"].reshape(-1)[lo:hi]
+    else:
+        O_pad = np.zeros(n_pad, np.float64)
+        O_pad[:N] = pair["O"].reshape(-1)
+        O_slab = backend.to_device(O_pad[rank * slab:(rank + 1) * slab])
+    bestD, minC = backend.wta(Sp_slab, next0, D, O_slab, vMax)
     out = torch.stack([bestD, minC])                                                            # [2][slab]
     gathered = [torch.empty_like(out) for _ in range(world)]
     dist.all_gather(gathered, out, group=group)
-    full = torch.cat(gathered, dim=1)[:, :N].cpu().numpy().view(np.uint32)
+    full = torch.cat(gathered, dim=1)[:, :N]
+    if pair.get("_device") and pair.get("_keep_on_device"):
+        return full[0].reshape(H, W), full[1].reshape(H, W)          # int32 CUDA tensors (u32 bit patterns)
+    full = full.cpu().numpy().view(np.uint32)
     return full[0].reshape(H, W), full[1].reshape(H, W)
