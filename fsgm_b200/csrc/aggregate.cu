@@ -41,12 +41,6 @@ struct SweepParams {
     int P1, P2, adaptive_thr;
 };
 
-template <int NREG> struct Row;
-template <> struct Row<1> { using T = uint16_t; };
-template <> struct Row<2> { using T = uint32_t; };
-template <> struct Row<4> { using T = uint2; };
-template <> struct Row<8> { using T = uint4; };
-
 template <int NREG> struct Words { uint32_t w[(NREG + 1) / 2]; };
 
 template <int NREG, int MODE>

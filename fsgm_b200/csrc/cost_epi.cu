@@ -324,10 +324,10 @@ int launch_epi_cost_fused(fsgm_ctx* c, int n, const double* d_vz, const uint32_t
     dim3 grid((W + FC_TX - 1) / FC_TX, (H + FC_TY - 1) / FC_TY, n);
 #define FSGM_FC(D4V)                                                                                              \
     do {                                                                                                          \
-        static bool attr_set = false;                                                                             \
-        if (!attr_set) {                                                                                          \
+        const unsigned bit = 1u << (D4V == 16 ? 0 : D4V == 32 ? 1 : 2);                                           \
+        if (!(c->attr_mask & bit)) {                                                                              \
             FSGM_CUDA(c, cudaFuncSetAttribute(epi_cost_fused_kernel<D4V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            attr_set = true;                                                                                      \
+            c->attr_mask |= bit;                                                                                  \
         }                                                                                                         \
         epi_cost_fused_kernel<D4V><<<grid, FC_THREADS, smem, c->stream>>>(cen1, cen2, Pd0, dirn, O, d_vz, W, H, C);    \
     } while (0)

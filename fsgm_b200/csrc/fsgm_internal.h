@@ -33,6 +33,7 @@ struct fsgm_ctx {
     uint64_t launches = 0;
     int sm_count = 0;
     size_t mem_total = 0, mem_budget = 0;   // cudaMemGetInfo, queried once
+    unsigned attr_mask = 0;                 // which kernels already had their max-dynamic-smem attribute set on this device
     int clusters_cs = 0, clusters_max = 0;   // resident clusters for the last queried cluster size
     int force_cluster = 0;                  // tuning/test knob: 0 auto, -1 generic path only, 1/2/4/8 forced cluster size
     std::string err;

@@ -69,11 +69,6 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-template <int NREG> struct RowT;
-template <> struct RowT<1> { using T = uint16_t; };
-template <> struct RowT<2> { using T = uint32_t; };
-template <> struct RowT<4> { using T = uint2; };
-
 template <int NREG> __device__ __forceinline__ void ld_row(const uint8_t* base, int lane, uint32_t (&w)[(NREG + 1) / 2])
 {
     if (NREG == 1) w[0] = reinterpret_cast<const uint16_t*>(base)[lane];
@@ -404,10 +399,10 @@ template <int NREG, int NDIR, bool FINAL>
 static int vs_launch_t(fsgm_ctx* c, int n, int cs, size_t smem, const VsParams& p)
 {
     auto kern = vsweep_kernel<NREG, NDIR, FINAL>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    const unsigned bit = 1u << (3 + (NREG == 1 ? 0 : NREG == 2 ? 1 : 2) * 4 + (NDIR == 3 ? 2 : 0) + (FINAL ? 1 : 0));
+    if (!(c->attr_mask & bit)) {
         FSGM_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
+        c->attr_mask |= bit;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(cs * n); cfg.blockDim = dim3(VS_WARPS * 32); cfg.dynamicSmemBytes = smem; cfg.stream = c->stream;

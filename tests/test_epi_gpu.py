@@ -223,3 +223,22 @@ def test_full_kitti_size_all_paths_agree(ctx, oracle):
     # label to within two labels (near the epipole neighbouring labels map to the same pixel, so it cannot be all)
     lab = ref["Sp"].argmin(-1)
     assert (np.abs(lab - p0["gt_label"]) <= 2).mean() > 0.3
+
+
+def test_async_batch_calls_overlap_correctly(ctx):
+    """Two enqueue-only batch calls back to back (different inputs, different outputs), one synchronize: both results equal
+    the synchronous call.  Exercises the persistent staging slots and their events across calls."""
+    from fsgm_b200 import api
+    W, H, D = 96, 40, 64
+    o = api.epi_opts(paths=8)
+    sets = []
+    for s0 in (300, 400, 500):
+        ps = [synth.epipolar_pair(W, H, D, seed=s0 + i) for i in range(3)]
+        sets.append([np.ascontiguousarray(np.stack([p[k] for p in ps])) for k in ("I1", "I2", "Pd0", "dirn", "O")])
+    want = [ctx.calc_cost_sgm_batch(a[0], a[1], D, 0.3, a[2], a[3], a[4], 6, 64, opts=o) for a in sets]
+    outs = [(np.zeros((3, H, W), np.uint32), np.zeros((3, H, W), np.uint32)) for _ in sets]
+    for a, out in zip(sets, outs):
+        ctx.calc_cost_sgm_batch(a[0], a[1], D, 0.3, a[2], a[3], a[4], 6, 64, opts=o, out=out, asynchronous=True)
+    ctx.synchronize()
+    for (b, m), (wb, wm) in zip(outs, want):
+        assert np.array_equal(b, wb) and np.array_equal(m, wm)
