@@ -30,7 +30,7 @@ namespace cg = cooperative_groups;
 
 namespace fsgm {
 
-constexpr int VS_WARPS = 16;
+constexpr int VS_WARPS = 20;      // measured at KITTI size (156 columns per CTA): 13/16/18/20/24/26 warps -> 14.9/13.1/13.5/12.7/13.3/14.2 ms per 30 pairs
 
 struct VsParams {
     const uint8_t* C;            // [n][H][W][D]
