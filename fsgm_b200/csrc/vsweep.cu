@@ -89,6 +89,7 @@ struct VsThread {
     uint32_t* minC; uint16_t* rec; uint16_t* ws;
     int Wk, Wk_max, W, xb, lane, sdx;
     uint32_t P1P1, P2P2, lo_mask, hi_mask;
+    bool preadd;
 };
 
 // the rows a pixel needs from global memory (horizontal volumes / the other pass's sum), fetched two pixels ahead
@@ -194,12 +195,22 @@ __device__ __forceinline__ void vs_pixel(const VsThread<NREG>& th, const uint8_t
             }
         }
     }
-    if (th.addA_l) { uint32_t t[NREG]; unpack_cost<NREG>(g.a, t);
+    if (th.addA_l && th.addB_l && th.preadd) {
+        // both horizontal rows present and their byte-wise sum cannot carry (2*(cmax+P2) <= 255): add first, unpack once
+        uint32_t ab[NW], t[NREG];
 #pragma unroll
-        for (int i = 0; i < NREG; ++i) acc[i] += t[i]; }
-    if (th.addB_l) { uint32_t t[NREG]; unpack_cost<NREG>(g.b, t);
+        for (int i = 0; i < NW; ++i) ab[i] = g.a[i] + g.b[i];
+        unpack_cost<NREG>(ab, t);
 #pragma unroll
-        for (int i = 0; i < NREG; ++i) acc[i] += t[i]; }
+        for (int i = 0; i < NREG; ++i) acc[i] += t[i];
+    } else {
+        if (th.addA_l) { uint32_t t[NREG]; unpack_cost<NREG>(g.a, t);
+#pragma unroll
+            for (int i = 0; i < NREG; ++i) acc[i] += t[i]; }
+        if (th.addB_l) { uint32_t t[NREG]; unpack_cost<NREG>(g.b, t);
+#pragma unroll
+            for (int i = 0; i < NREG; ++i) acc[i] += t[i]; }
+    }
     if (!FINAL) {
         uint32_t* sp = reinterpret_cast<uint32_t*>(th.Sout_l + vox);
         if (NREG == 4) *reinterpret_cast<uint4*>(sp) = make_uint4(acc[0], acc[1], acc[2], acc[3]);
@@ -218,13 +229,16 @@ __device__ __forceinline__ void vs_pixel(const VsThread<NREG>& th, const uint8_t
         // winner-take-all: first minimum (strict <, calc_cost_sgm.cpp:267) via (sum << 16 | label)
         uint32_t key = 0xFFFFFFFFu;
         uint16_t* ws = th.ws;
+        const uint32_t lbl = (uint32_t)(lane * 2 * NREG);
 #pragma unroll
         for (int i = 0; i < NREG; ++i) {
-            const uint32_t d0 = (uint32_t)(lane * 2 * NREG + 2 * i);
-            key = min(key, ((acc[i] & 0xFFFFu) << 16) | d0);
-            key = min(key, (acc[i] & 0xFFFF0000u) | (d0 + 1));
-            reinterpret_cast<uint32_t*>(ws)[lane * NREG + i] = acc[i];
+            // (sum << 16 | label) for the two labels of this register: one PRMT each
+            key = min(key, __byte_perm(acc[i], lbl + 2 * i, 0x1054));
+            key = min(key, __byte_perm(acc[i], lbl + 2 * i + 1, 0x3254));
         }
+        if (NREG == 4) reinterpret_cast<uint4*>(ws)[lane] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+        else if (NREG == 2) reinterpret_cast<uint2*>(ws)[lane] = make_uint2(acc[0], acc[1]);
+        else reinterpret_cast<uint32_t*>(ws)[lane] = acc[0];
         key = __reduce_min_sync(0xffffffffu, key);
         __syncwarp();
         if (lane == 0) {
@@ -298,6 +312,7 @@ vsweep_kernel(const VsParams prm)
     th.ws = wsc + warp * D;
     th.Wk = Wk; th.Wk_max = Wk_max; th.W = W; th.xb = xb; th.lane = lane;
     th.P1P1 = P1P1; th.P2P2 = P2P2; th.lo_mask = lo_mask; th.hi_mask = hi_mask; th.sdx = sdx;
+    th.preadd = 2 * (24 + prm.P2) <= 255;          // cost values are <= 24 on this path (no-wrap domain precondition)
 
     int off = 0;                                   // yy mod Wk, kept incrementally
     for (int yy = 0; yy < H; ++yy) {
