@@ -187,6 +187,7 @@ def run_ours(args):
     ctx = api.Context(local)
     ctx.use_torch_stream()
     ctx.tune(1, args.tune_cluster)
+    ctx.tune(2, int(args.no_overlap))
     opts = api.epi_opts(paths=PATHS)
     P = args.pairs
     N = W * H
@@ -324,9 +325,10 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--pairs", type=int, default=30, help="pairs per step per GPU (30 = two full waves of the 15 resident clusters)")
+    ap.add_argument("--pairs", type=int, default=60, help="pairs per step per GPU (60 = four full waves of the 15 resident clusters)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-overlap", action="store_true", help="A/B knob (fsgm_tune key 2): disable the two-stream wave pipeline")
     ap.add_argument("--tune-cluster", type=int, default=0,
                     help="A/B knob (fsgm_tune key 1): 0 auto, -1 generic sweeps only, 1/2/4/8 cluster size")
     args = ap.parse_args()

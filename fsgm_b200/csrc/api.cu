@@ -238,6 +238,90 @@ static int epi_pipeline_dev(fsgm_ctx* c, int n, const uint8_t* I1, const uint8_t
     return FSGM_OK;
 }
 
+
+// ---- wave-pipelined epipolar path -----------------------------------------------------------------------------
+// The cluster kernels keep 15 x 8 = 120 of the 148 SMs busy and a pair occupies a cluster for a whole pass, so a batch
+// runs in waves of K pairs.  While wave i is in its two cluster passes (stream A), the front-end of wave i+1 (census,
+// cost volume, horizontal sweeps) runs on a second stream and fills the SMs the clusters leave idle.
+struct StreamSwap {
+    fsgm_ctx* c; cudaStream_t saved;
+    StreamSwap(fsgm_ctx* ctx, cudaStream_t s) : c(ctx), saved(ctx->stream) { c->stream = s; }
+    ~StreamSwap() { c->stream = saved; }
+};
+
+static int epi_pipeline_waves(fsgm_ctx* c, int n, int cs, const uint8_t* I1, const uint8_t* I2, int W, int H, int D, double vMax,
+                              const double* Pd0, const double* dirn, const double* O, int P1, int P2,
+                              const fsgm_epi_opts& o, uint32_t* bestD, uint32_t* minC)
+{
+    const size_t N = (size_t)W * H, V = N * D;
+    const int ndir = o.paths == 8 ? 3 : 1;
+    const int nf = fast_pairs(c, n, cs, D, W, ndir), ng = n - nf, K = c->clusters_max;
+    if (!c->aux_stream) {
+        FSGM_CUDA(c, cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+        FSGM_CUDA(c, cudaEventCreateWithFlags(&c->ev_entry, cudaEventDisableTiming));
+        FSGM_CUDA(c, cudaEventCreateWithFlags(&c->ev_front[0], cudaEventDisableTiming));
+        FSGM_CUDA(c, cudaEventCreateWithFlags(&c->ev_front[1], cudaEventDisableTiming));
+    }
+    uint32_t *cen1, *cen2; uint8_t *C, *Lh0, *Lh1; uint16_t *S1, *rec; double* vz;
+    FSGM_TRY(arena_get(c, (size_t)D, &vz));
+    FSGM_TRY(arena_get(c, n * N, &cen1));
+    FSGM_TRY(arena_get(c, n * N, &cen2));
+    FSGM_TRY(arena_get(c, n * V, &C));
+    FSGM_TRY(arena_get(c, nf * V, &Lh0));
+    FSGM_TRY(arena_get(c, nf * V, &Lh1));
+    FSGM_TRY(arena_get(c, nf * V, &S1));
+    FSGM_TRY(arena_get(c, nf * N * 4, &rec));
+    cudaStream_t A = c->stream, B = c->aux_stream;
+    FSGM_TRY(launch_vz_table(c, D, vMax, vz));
+    FSGM_CUDA(c, cudaEventRecord(c->ev_entry, A));            // everything queued so far (inputs, vz) precedes stream B
+    FSGM_CUDA(c, cudaStreamWaitEvent(B, c->ev_entry, 0));
+    const int hd[2] = {0, 4};
+    auto front = [&](int p0, int m, cudaStream_t st) -> int {
+        StreamSwap sw(c, st);
+        FSGM_TRY(launch_census(c, m, I1 + p0 * N, W, H, cen1 + p0 * N));
+        FSGM_TRY(launch_census(c, m, I2 + p0 * N, W, H, cen2 + p0 * N));
+        bool fused = false;
+        FSGM_TRY(launch_epi_cost_fused(c, m, vz, cen1 + p0 * N, cen2 + p0 * N, W, H, D, Pd0 + p0 * 2 * N, dirn + p0 * 2 * N,
+                                       O + p0 * N, C + p0 * V, &fused));
+        if (!fused) return fail(c, FSGM_ERR_DOMAIN, "wave pipeline needs the fused cost kernel");
+        uint8_t* Lh[2] = {Lh0 + p0 * V, Lh1 + p0 * V};
+        return launch_sweeps(c, m, C + p0 * V, I1 + p0 * N, W, H, D, P1, P2, 0, 24, hd, 2, Lh);
+    };
+    auto back = [&](int p0, int m) -> int {
+        FSGM_TRY(launch_vsweep(c, m, cs, ndir, false, C + p0 * V, Lh0 + p0 * V, Lh1 + p0 * V, nullptr, S1 + p0 * V, nullptr, nullptr,
+                               W, H, D, P1, P2, 0));
+        FSGM_TRY(launch_vsweep(c, m, cs, ndir, true, C + p0 * V, nullptr, nullptr, S1 + p0 * V, nullptr, minC + p0 * N, rec + p0 * N * 4,
+                               W, H, D, P1, P2, 1));
+        return launch_vs_finalize(c, m, rec + p0 * N * 4, minC + p0 * N, O + p0 * N, W, H, D, o.subpixel, o.vz_to_disp, vMax, bestD + p0 * N);
+    };
+    const int waves = (nf + K - 1) / K;
+    FSGM_TRY(front(0, std::min(K, nf), A));
+    for (int i = 0; i < waves; ++i) {
+        const int p0 = i * K, m = std::min(K, nf - p0);
+        if (i + 1 < waves) {
+            const int q0 = (i + 1) * K, qm = std::min(K, nf - q0);
+            FSGM_TRY(front(q0, qm, B));
+            FSGM_CUDA(c, cudaEventRecord(c->ev_front[(i + 1) & 1], B));
+        }
+        if (i > 0) FSGM_CUDA(c, cudaStreamWaitEvent(A, c->ev_front[i & 1], 0));
+        FSGM_TRY(back(p0, m));
+    }
+    if (ng) {                                                 // partial wave: generic kernels on the main stream
+        const size_t po = (size_t)nf * N;
+        FSGM_TRY(launch_census(c, ng, I1 + po, W, H, cen1 + po));
+        FSGM_TRY(launch_census(c, ng, I2 + po, W, H, cen2 + po));
+        bool fused = false;
+        FSGM_TRY(launch_epi_cost_fused(c, ng, vz, cen1 + po, cen2 + po, W, H, D, Pd0 + 2 * po, dirn + 2 * po, O + po, C + po * D, &fused));
+        fsgm_epi_opts og = o;
+        const int saved = c->force_cluster;
+        c->force_cluster = -1;                                // generic path for these pairs
+        int rc = aggregate_and_wta(c, ng, C + po * D, I1 + po, W, H, D, P1, P2, 24, og, O + po, vMax, nullptr, bestD + po, minC + po);
+        c->force_cluster = saved;
+        FSGM_TRY(rc);
+    }
+    return FSGM_OK;
+}
+
 }  // namespace fsgm
 
 using namespace fsgm;
@@ -286,6 +370,7 @@ void fsgm_destroy(fsgm_ctx* c)
         if (c->pipe.in_ready[i]) { cudaEventDestroy(c->pipe.in_ready[i]); cudaEventDestroy(c->pipe.done[i]); cudaEventDestroy(c->pipe.out_ready[i]); }
     }
     if (c->pipe.h2d) { cudaStreamDestroy(c->pipe.h2d); cudaStreamDestroy(c->pipe.d2h); }
+    if (c->aux_stream) { cudaStreamDestroy(c->aux_stream); cudaEventDestroy(c->ev_entry); cudaEventDestroy(c->ev_front[0]); cudaEventDestroy(c->ev_front[1]); }
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -313,6 +398,7 @@ int fsgm_tune(fsgm_ctx* c, int key, int value)
 {
     if (!c) return FSGM_ERR_ARG;
     if (key == 1) { c->force_cluster = value; return FSGM_OK; }
+    if (key == 2) { c->no_overlap = value != 0; return FSGM_OK; }
     return fail(c, FSGM_ERR_ARG, "unknown tuning key");
 }
 
@@ -483,6 +569,13 @@ int fsgm_calc_cost_sgm_dev(fsgm_ctx* c, int n, const uint8_t* d_I1, const uint8_
     for (int i0 = 0; i0 < n; i0 += chunk) {
         const int m = std::min(chunk, n - i0);
         ArenaScope scope(c);
+        const int cs = c->no_overlap ? 0 : fast_path_cluster(c, W, D, P1, P2, 24, o);
+        const bool waves = cs && o.total_pass == 2 && (D == 64 || D == 128 || D == 256) &&
+                           fast_pairs(c, m, cs, D, W, o.paths == 8 ? 3 : 1) >= 2 * c->clusters_max - 1;
+        if (waves)
+            FSGM_TRY(epi_pipeline_waves(c, m, cs, d_I1 + i0 * N, d_I2 + i0 * N, W, H, D, vMax, d_Pd0 + i0 * 2 * N, d_dir + i0 * 2 * N,
+                                        d_O + i0 * N, P1, P2, o, d_bestD + i0 * N, d_minC + i0 * N));
+        else
         FSGM_TRY(epi_pipeline_dev(c, m, d_I1 + i0 * N, d_I2 + i0 * N, W, H, D, vMax, d_Pd0 + i0 * 2 * N, d_dir + i0 * 2 * N,
                                   d_O + i0 * N, P1, P2, o, d_bestD + i0 * N, d_minC + i0 * N));
     }
@@ -509,7 +602,10 @@ int fsgm_calc_cost_sgm_batch_async(fsgm_ctx* c, int n, const uint8_t* I1, const 
     int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n, (size_t(96) << 20) / (in_pair + out_pair) + 1));
     {   // when the cluster kernels apply, feed them whole waves (one pair = one cluster for a whole pass)
         const int cs = fast_path_cluster(c, W, D, P1, P2, 24, o);
-        if (cs) { fast_pairs(c, n, cs, D, W, o.paths == 8 ? 3 : 1); chunk = std::min(n, std::max(chunk, c->clusters_max)); }
+        if (cs) {                                    // two waves per chunk so that the wave pipeline has something to overlap
+            fast_pairs(c, n, cs, D, W, o.paths == 8 ? 3 : 1);
+            chunk = std::min(n, std::max(chunk, (c->no_overlap ? 1 : 2) * c->clusters_max));
+        }
     }
     FSGM_TRY(pipe_reserve(c, (size_t)chunk * (in_pair + out_pair)));
     HostPipe& p = c->pipe;

@@ -33,6 +33,9 @@ struct fsgm_ctx {
     uint64_t launches = 0;
     int sm_count = 0;
     size_t mem_total = 0, mem_budget = 0;   // cudaMemGetInfo, queried once
+    cudaStream_t aux_stream = nullptr;      // second stream: front-end of wave i+1 under the cluster kernels of wave i
+    cudaEvent_t ev_entry = nullptr, ev_front[2] = {nullptr, nullptr};
+    int no_overlap = 0;                     // tuning knob (fsgm_tune key 2)
     unsigned attr_mask = 0;                 // which kernels already had their max-dynamic-smem attribute set on this device
     int clusters_cs = 0, clusters_max = 0;   // resident clusters for the last queried cluster size
     int force_cluster = 0;                  // tuning/test knob: 0 auto, -1 generic path only, 1/2/4/8 forced cluster size

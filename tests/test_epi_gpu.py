@@ -242,3 +242,25 @@ def test_async_batch_calls_overlap_correctly(ctx):
     ctx.synchronize()
     for (b, m), (wb, wm) in zip(outs, want):
         assert np.array_equal(b, wb) and np.array_equal(m, wm)
+
+
+def test_wave_pipeline_equals_plain_path(ctx):
+    """Two-stream wave pipeline (front-end of wave i+1 under the cluster passes of wave i): 34 pairs = two full waves of
+    15 clusters plus a partial one, against the same batch with the pipeline switched off and against single-pair calls."""
+    from fsgm_b200 import api
+    W, H, D, n = 96, 40, 64, 34
+    o = api.epi_opts(paths=8)
+    ps = [synth.epipolar_pair(W, H, D, seed=700 + i) for i in range(n)]
+    a = [np.ascontiguousarray(np.stack([p[k] for p in ps])) for k in ("I1", "I2", "Pd0", "dirn", "O")]
+    ctx.tune(1, 2)                                   # force the cluster kernels (these images are tiny)
+    ctx.tune(2, 0)
+    b1, m1 = ctx.calc_cost_sgm_batch(a[0], a[1], D, 0.3, a[2], a[3], a[4], 6, 64, opts=o)
+    ctx.tune(2, 1)
+    b0, m0 = ctx.calc_cost_sgm_batch(a[0], a[1], D, 0.3, a[2], a[3], a[4], 6, 64, opts=o)
+    ctx.tune(1, 0)
+    ctx.tune(2, 0)
+    assert np.array_equal(b1, b0) and np.array_equal(m1, m0)
+    for i in (0, 14, 15, 29, 30, 33):
+        p = ps[i]
+        b, m, _, _ = ctx.calc_cost_sgm(p["I1"], p["I2"], D, 0.3, p["Pd0"], p["dirn"], p["O"], 6, 64, opts=o)
+        assert np.array_equal(b, b1[i]) and np.array_equal(m, m1[i]), i
