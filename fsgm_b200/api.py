@@ -217,6 +217,17 @@ class Context:
         self._ck(self._l.fsgm_epi_partial_dev(self._h, _dp(Cvol), _dp(I1), W, H, D, int(P1), int(P2), int(adaptive_p2),
                                               dirs, len(directions), _dp(Sp_partial)))
 
+    def epi_partial_u8_dev(self, Cvol, I1, P1, P2, directions, partial, adaptive_p2=0):
+        H, W, D = Cvol.shape
+        dirs = (C.c_int * max(1, len(directions)))(*[int(d) for d in directions])
+        self._ck(self._l.fsgm_epi_partial_u8_dev(self._h, _dp(Cvol), _dp(I1), W, H, D, int(P1), int(P2), int(adaptive_p2),
+                                                 dirs, len(directions), _dp(partial)))
+
+    def epi_wta_slabs_dev(self, slabs, n_slabs, next0, D, O, vMax, bestD, minC, subpixel=1, vz_to_disp=1):
+        n_pixels = slabs.numel() // (D * n_slabs)
+        self._ck(self._l.fsgm_epi_wta_slabs_dev(self._h, _dp(slabs), int(n_slabs), _dp(next0), C.c_size_t(n_pixels), int(D),
+                                                int(subpixel), int(vz_to_disp), _dp(O), C.c_double(vMax), _dp(bestD), _dp(minC)))
+
     def epi_wta_sp_dev(self, Sp, next0, D, O, vMax, bestD, minC, subpixel=1, vz_to_disp=1):
         n_pixels = Sp.numel() // D
         self._ck(self._l.fsgm_epi_wta_sp_dev(self._h, _dp(Sp), _dp(next0), C.c_size_t(n_pixels), int(D), int(subpixel),

@@ -521,6 +521,40 @@ int fsgm_epi_partial_dev(fsgm_ctx* c, const uint8_t* d_C, const uint8_t* d_I1, i
     return launch_epi_wta(c, 1, L, n_dirs, W, H, D, 0, 0, nullptr, 0.0, d_Sp_partial, b, m);
 }
 
+// u8 form of the partial volume: valid when the rank's directions cannot exceed 255 together (n_dirs*(24+P2) <= 255, i.e. up
+// to two directions at P2 = 64).  Exchanged with an all-to-all instead of a u16 reduce-scatter: half the NVLink bytes.
+int fsgm_epi_partial_u8_dev(fsgm_ctx* c, const uint8_t* d_C, const uint8_t* d_I1, int W, int H, int D, int P1, int P2,
+                            int adaptive_p2, const int* directions, int n_dirs, uint8_t* d_partial)
+{
+    FSGM_TRY(check_dims(c, 1, W, H, D));
+    if (!d_C || !d_partial || !directions || (adaptive_p2 && !d_I1)) return fail(c, FSGM_ERR_ARG, "null pointer");
+    if (n_dirs < 0 || n_dirs > 8) return fail(c, FSGM_ERR_ARG, "n_dirs must be 0..8");
+    if (sweep_needs_wrap(P1, P2, 24) || n_dirs * (24 + P2) > 255) return fail(c, FSGM_ERR_DOMAIN, "partial sums do not fit 8 bits");
+    if (D % 16) return fail(c, FSGM_ERR_DOMAIN, "dMax must be a multiple of 16 for the u8 partial form");
+    FSGM_CUDA(c, cudaSetDevice(c->device));
+    const size_t V = (size_t)W * H * D;
+    if (n_dirs == 0) { FSGM_CUDA(c, cudaMemsetAsync(d_partial, 0, V, c->stream)); return FSGM_OK; }
+    FSGM_TRY(arena_reserve(c, (size_t)(n_dirs - 1) * align256(V)));
+    ArenaScope scope(c);
+    uint8_t* L[8];
+    L[0] = d_partial;
+    for (int k = 1; k < n_dirs; ++k) FSGM_TRY(arena_get(c, V, &L[k]));
+    FSGM_TRY(launch_sweeps(c, 1, d_C, d_I1, W, H, D, P1, P2, adaptive_p2 ? 25 : 0, 24, directions, n_dirs, L));
+    for (int k = 1; k < n_dirs; ++k) FSGM_TRY(launch_add_u8(c, d_partial, L[k], V));
+    return FSGM_OK;
+}
+
+int fsgm_epi_wta_slabs_dev(fsgm_ctx* c, const uint8_t* d_slabs, int n_slabs, const uint16_t* d_next_label0, size_t n_pixels, int D,
+                           int subpixel, int vz_to_disp, const double* d_O, double vMax, uint32_t* d_bestD, uint32_t* d_minC)
+{
+    if (!c) return FSGM_ERR_ARG;
+    if (!d_slabs || !d_bestD || !d_minC || (vz_to_disp && !d_O) || n_pixels < 1 || n_slabs < 1 || n_slabs > 8)
+        return fail(c, FSGM_ERR_ARG, "bad argument");
+    if (D < 1 || D > 512) return fail(c, FSGM_ERR_DOMAIN, "dMax must be in 1..512");
+    FSGM_CUDA(c, cudaSetDevice(c->device));
+    return launch_slab_wta(c, d_slabs, n_slabs, d_next_label0, n_pixels, D, subpixel, vz_to_disp, d_O, vMax, d_bestD, d_minC);
+}
+
 int fsgm_epi_wta_sp_dev(fsgm_ctx* c, const uint16_t* d_Sp, const uint16_t* d_next_label0, size_t n_pixels, int D,
                         int subpixel, int vz_to_disp, const double* d_O, double vMax, uint32_t* d_bestD, uint32_t* d_minC)
 {

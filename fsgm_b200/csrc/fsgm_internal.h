@@ -109,6 +109,9 @@ bool sweep_needs_wrap(int P1, int P2, int cmax);
 int launch_epi_wta(fsgm_ctx* c, int n, uint8_t* const* Lvols, int n_dirs, int W, int H, int D, int subpixel,
                    int vz_to_disp, const double* O, double vMax, uint16_t* Sp16, uint32_t* bestD, uint32_t* minC);
 
+int launch_slab_wta(fsgm_ctx* c, const uint8_t* vols, int n_vols, const uint16_t* next0, size_t npix, int D, int subpixel,
+                    int vz_to_disp, const double* O, double vMax, uint32_t* bestD, uint32_t* minC);
+int launch_add_u8(fsgm_ctx* c, uint8_t* a, const uint8_t* b, size_t bytes);
 int launch_sp_wta(fsgm_ctx* c, const uint16_t* Sp, const uint16_t* next0, size_t npix, int D, int subpixel,
                   int vz_to_disp, const double* O, double vMax, uint32_t* bestD, uint32_t* minC);
 

@@ -105,10 +105,10 @@ epi_wta_kernel(const WtaParams prm)
             if (idx + 1 < (uint32_t)D) c1 = s[idx + 1];
             else if (prm.Sp_in) {
                 c1 = (p + 1 < N) ? __ldg(prm.Sp_in + vol + (p + 1) * D) : (prm.next0 ? __ldg(prm.next0) : 0u);
-            } else {
-                uint32_t v = (lane < R && p + 1 < N) ? __ldg(prm.L[lane] + vol + (p + 1) * D) : 0u;
+            } else if (p + 1 < N) {
+                uint32_t v = (lane < R) ? __ldg(prm.L[lane] + vol + (p + 1) * D) : 0u;
                 c1 = __reduce_add_sync(0xffffffffu, v);
-            }
+            } else c1 = prm.next0 ? __ldg(prm.next0) : 0u;
         }
         if (lane == i) { my_idx = idx; my_min = best; my_c_1 = c_1; my_c = best; my_c1 = c1; my_refine = refine; }
         __syncwarp();
@@ -148,6 +148,41 @@ int launch_epi_wta(fsgm_ctx* c, int n, uint8_t* const* Lvols, int n_dirs, int W,
     dim3 grid((unsigned)((N + WTA_WARPS * 32 - 1) / (WTA_WARPS * 32)), n);
     if (D % 8 == 0) epi_wta_kernel<true><<<grid, WTA_WARPS * 32, 0, c->stream>>>(p);
     else epi_wta_kernel<false><<<grid, WTA_WARPS * 32, 0, c->stream>>>(p);
+    FSGM_LAUNCHED(c);
+    return FSGM_OK;
+}
+
+// WTA over one slab of pixels from n_vols u8 partial volumes (the all-to-all form of the direction-split path)
+int launch_slab_wta(fsgm_ctx* c, const uint8_t* vols, int n_vols, const uint16_t* next0, size_t npix, int D, int subpixel,
+                    int vz_to_disp, const double* O, double vMax, uint32_t* bestD, uint32_t* minC)
+{
+    if (D > WTA_MAXD) return fail(c, FSGM_ERR_DOMAIN, "label count must be <= 512");
+    StageScope ss(c, ST_WTA);
+    WtaParams p{};
+    for (int k = 0; k < n_vols; ++k) p.L[k] = vols + (size_t)k * npix * D;
+    p.n_dirs = n_vols; p.W = (int)npix; p.H = 1; p.D = D; p.subpixel = subpixel; p.vz_to_disp = vz_to_disp;
+    p.O = O; p.vMax = vMax; p.Sp16 = nullptr; p.Sp_in = nullptr; p.next0 = next0; p.bestD = bestD; p.minC = minC;
+    dim3 grid((unsigned)((npix + WTA_WARPS * 32 - 1) / (WTA_WARPS * 32)), 1);
+    if (D % 8 == 0) epi_wta_kernel<true><<<grid, WTA_WARPS * 32, 0, c->stream>>>(p);
+    else epi_wta_kernel<false><<<grid, WTA_WARPS * 32, 0, c->stream>>>(p);
+    FSGM_LAUNCHED(c);
+    return FSGM_OK;
+}
+
+__global__ void add_u8_kernel(uint4* __restrict__ a, const uint4* __restrict__ b, size_t n16)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n16) return;
+    uint4 x = a[i]; const uint4 y = b[i];
+    x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;          // byte sums stay below 256 (caller checks): no carries
+    a[i] = x;
+}
+
+int launch_add_u8(fsgm_ctx* c, uint8_t* a, const uint8_t* b, size_t bytes)
+{
+    StageScope ss(c, ST_MISC);
+    const size_t n16 = bytes / 16;
+    add_u8_kernel<<<(unsigned)((n16 + 255) / 256), 256, 0, c->stream>>>(reinterpret_cast<uint4*>(a), reinterpret_cast<const uint4*>(b), n16);
     FSGM_LAUNCHED(c);
     return FSGM_OK;
 }

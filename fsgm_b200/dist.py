@@ -16,6 +16,8 @@ fsgm_b200.api) and, in the CPU test-suite, over gloo with a checker backend supp
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -77,6 +79,22 @@ class GpuBackend:
         self.ctx.epi_partial_dev(Cvol, I1, P1, P2, dirs, self._partial)
         return self._partial
 
+    def partial_u8(self, Cvol, I1, P1, P2, dirs, n_pad):
+        H, W, D = Cvol.shape
+        key = ("u8", n_pad, D)
+        if getattr(self, "_partial8_key", None) != key:
+            self._partial8 = torch.zeros(n_pad * D, dtype=torch.uint8, device=self.device)
+            self._partial8_key = key
+        self.ctx.epi_partial_u8_dev(Cvol, I1, P1, P2, dirs, self._partial8)
+        return self._partial8
+
+    def wta_slabs(self, slabs, n_slabs, next0, D, O_slab, vMax):
+        n = slabs.numel() // (D * n_slabs)
+        bestD = torch.empty(n, dtype=torch.int32, device=self.device)
+        minC = torch.empty_like(bestD)
+        self.ctx.epi_wta_slabs_dev(slabs, n_slabs, next0, D, O_slab, vMax, bestD, minC)
+        return bestD, minC
+
     def wta(self, Sp_slab, next0, D, O_slab, vMax):
         n = Sp_slab.numel() // D
         bestD = torch.empty(n, dtype=torch.int32, device=self.device)
@@ -97,7 +115,24 @@ def epi_direction_split(backend, pair, D, vMax, P1, P2, paths=8, group=None):
     slab = slab_pixels(N, world)
     n_pad = slab * world
     Cvol, I1 = backend.cost_volume(pair, D, vMax)
-    part = backend.partial(Cvol, I1, P1, P2, split_directions(paths, rank, world), n_pad)    # int16 bits = u16
+    my_dirs = split_directions(paths, rank, world)
+    k_max = -(-(8 if paths == 8 else 4) // world)
+    use_u8 = (P1 >= 0 and P2 >= 0 and 24 + P1 + P2 <= 255 and 48 + P2 <= 255 and k_max * (24 + P2) <= 255 and D % 16 == 0
+              and hasattr(backend, "partial_u8") and os.environ.get("FSGM_DIRSPLIT_U16") != "1")
+    if use_u8:
+        # every rank's directions fit a byte together: exchange u8 pixel slabs with ONE all-to-all (half the bytes of the
+        # u16 reduce-scatter) and sum the received slabs inside the WTA kernel
+        part8 = backend.partial_u8(Cvol, I1, P1, P2, my_dirs, n_pad)
+        recv = torch.empty_like(part8)
+        dist.all_to_all_single(recv, part8, group=group)                  # recv[j] = rank j's partial of OUR slab
+        first = recv.view(world, slab * D)[:, 0].to(torch.int32).sum().to(torch.int32).reshape(1)
+        firsts = [torch.empty(1, dtype=torch.int32, device=recv.device) for _ in range(world)]
+        dist.all_gather(firsts, first, group=group)
+        next0 = firsts[rank + 1].to(torch.int16) if rank + 1 < world else None
+        O_slab = _o_slab(backend, pair, N, slab, n_pad, rank)
+        bestD, minC = backend.wta_slabs(recv, world, next0, D, O_slab, vMax)
+        return _gather_outputs(pair, bestD, minC, world, N, H, W, group)
+    part = backend.partial(Cvol, I1, P1, P2, my_dirs, n_pad)    # int16 bits = u16
     words = part.view(torch.int32)                                                               # two u16 per word
     per = slab * D // 2
     if dist.get_backend(group) == "nccl":
@@ -111,16 +146,24 @@ def epi_direction_split(backend, pair, D, vMax, P1, P2, paths=8, group=None):
     firsts = [torch.empty(1, dtype=torch.int32, device=Sp_slab.device) for _ in range(world)]
     dist.all_gather(firsts, Sp_slab[:1].to(torch.int32) & 0xFFFF, group=group)
     next0 = firsts[rank + 1].to(torch.int16) if rank + 1 < world else None
+    O_slab = _o_slab(backend, pair, N, slab, n_pad, rank)
+    bestD, minC = backend.wta(Sp_slab, next0, D, O_slab, vMax)
+    return _gather_outputs(pair, bestD, minC, world, N, H, W, group)
+
+
+def _o_slab(backend, pair, N, slab, n_pad, rank):
     if pair.get("_device"):
         O_slab = torch.zeros(slab, dtype=torch.float64, device=pair["O"].device)
         lo, hi = rank * slab, min(N, (rank + 1) * slab)
         if hi > lo:
             O_slab[:hi - lo] = pair["O"].reshape(-1)[lo:hi]
-    else:
-        O_pad = np.zeros(n_pad, np.float64)
-        O_pad[:N] = pair["O"].reshape(-1)
-        O_slab = backend.to_device(O_pad[rank * slab:(rank + 1) * slab])
-    bestD, minC = backend.wta(Sp_slab, next0, D, O_slab, vMax)
+        return O_slab
+    O_pad = np.zeros(n_pad, np.float64)
+    O_pad[:N] = pair["O"].reshape(-1)
+    return backend.to_device(O_pad[rank * slab:(rank + 1) * slab])
+
+
+def _gather_outputs(pair, bestD, minC, world, N, H, W, group):
     out = torch.stack([bestD, minC])                                                            # [2][slab]
     gathered = [torch.empty_like(out) for _ in range(world)]
     dist.all_gather(gathered, out, group=group)

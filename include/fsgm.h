@@ -129,6 +129,14 @@ FSGM_API int fsgm_epi_aggregate_dev(fsgm_ctx* ctx, int n_pairs, const uint8_t* d
  *             NULL = 0 (end of image) */
 FSGM_API int fsgm_epi_partial_dev(fsgm_ctx* ctx, const uint8_t* d_C, const uint8_t* d_I1, int width, int height, int dMax,
                          int P1, int P2, int adaptive_p2, const int* directions, int n_dirs, uint16_t* d_Sp_partial);
+/* 8-bit form for >= 4 GPUs (each rank owns at most two directions: their sum fits a byte when n_dirs*(24+P2) <= 255):
+ *   partial_u8 : the listed directions summed into u8 [H*W][dMax]; ranks exchange pixel slabs with an all-to-all
+ *   wta_slabs  : WTA over n_pixels pixels from n_slabs received u8 slabs laid out back to back */
+FSGM_API int fsgm_epi_partial_u8_dev(fsgm_ctx* ctx, const uint8_t* d_C, const uint8_t* d_I1, int width, int height, int dMax,
+                         int P1, int P2, int adaptive_p2, const int* directions, int n_dirs, uint8_t* d_partial);
+FSGM_API int fsgm_epi_wta_slabs_dev(fsgm_ctx* ctx, const uint8_t* d_slabs, int n_slabs, const uint16_t* d_next_label0,
+                         size_t n_pixels, int dMax, int subpixel, int vz_to_disp, const double* d_offsetFromPosD0, double vMax,
+                         uint32_t* d_bestD, uint32_t* d_minC);
 FSGM_API int fsgm_epi_wta_sp_dev(fsgm_ctx* ctx, const uint16_t* d_Sp, const uint16_t* d_next_label0, size_t n_pixels, int dMax,
                          int subpixel, int vz_to_disp, const double* d_offsetFromPosD0, double vMax,
                          uint32_t* d_bestD, uint32_t* d_minC);

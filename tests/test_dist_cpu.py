@@ -38,7 +38,7 @@ class OracleBackend:
         self.po = po
 
     def cost_volume(self, pair, D, vMax):
-        r = self.po.port_epi(pair["I1"], pair["I2"], D, vMax, pair["Pd0"], pair["dirn"], pair["O"], 6, 64, paths=4)
+        r = self.po.port_epi(pair["I1"], pair["I2"], D, vMax, pair["Pd0"], pair["dirn"], pair["O"], 6, 32, paths=4)
         return r["C"], pair["I1"]
 
     def partial(self, Cvol, I1, P1, P2, dirs, n_pad):
@@ -47,6 +47,17 @@ class OracleBackend:
         for r in dirs:
             acc[:H * W * D] += self.po.port_sweep1d(Cvol, I1, P1, P2, r).reshape(-1)
         return torch.from_numpy(acc.view(np.int16))
+
+    def partial_u8(self, Cvol, I1, P1, P2, dirs, n_pad):
+        H, W, D = Cvol.shape
+        acc = np.zeros(n_pad * D, np.uint8)
+        for r in dirs:
+            acc[:H * W * D] += self.po.port_sweep1d(Cvol, I1, P1, P2, r).reshape(-1)
+        return torch.from_numpy(acc)
+
+    def wta_slabs(self, slabs, n_slabs, next0, D, O_slab, vMax):
+        sp = slabs.numpy().reshape(n_slabs, -1).astype(np.uint16).sum(0).astype(np.uint16)
+        return self.wta(torch.from_numpy(sp.view(np.int16)), next0, D, O_slab, vMax)
 
     def wta(self, Sp_slab, next0, D, O_slab, vMax):
         sp = Sp_slab.numpy().view(np.uint16).astype(np.uint32).reshape(1, -1, D)
@@ -65,32 +76,33 @@ class OracleBackend:
         return torch.from_numpy(np.ascontiguousarray(a))
 
 
-def _worker(rank, world, port, W, H, D, paths, q):
+def _worker(rank, world, port, W, H, D, paths, P2, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from oracle import pyoracle as po
     p = synth.epipolar_pair(W, H, D, seed=5)
-    bestD, minC = fd.epi_direction_split(OracleBackend(po), p, D, p["vMax"], 6, 64, paths=paths)
+    bestD, minC = fd.epi_direction_split(OracleBackend(po), p, D, p["vMax"], 6, P2, paths=paths)
     q.put((rank, bestD, minC))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("W,H,D,paths", [(37, 23, 16, 8), (20, 15, 8, 4)])
-def test_direction_split_gloo_world2(oracle, W, H, D, paths):
+# world 2, P2 = 64: four directions per rank do not fit a byte -> u16 reduce path; the other cases take the u8 all-to-all path
+@pytest.mark.parametrize("W,H,D,paths,P2,world", [(37, 23, 16, 8, 64, 2), (20, 15, 8, 4, 64, 2), (29, 19, 16, 8, 32, 2), (31, 17, 16, 8, 64, 4)])
+def test_direction_split_gloo(oracle, W, H, D, paths, P2, world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + (os.getpid() % 300)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, W, H, D, paths, q)) for r in range(2)]
+    port = 29600 + (os.getpid() % 300) + world
+    procs = [ctx.Process(target=_worker, args=(r, world, port, W, H, D, paths, P2, q)) for r in range(world)]
     for pr in procs:
         pr.start()
-    res = [q.get(timeout=120) for _ in range(2)]
+    res = [q.get(timeout=120) for _ in range(world)]
     for pr in procs:
         pr.join(timeout=60)
         assert pr.exitcode == 0
     p = synth.epipolar_pair(W, H, D, seed=5)
-    want = oracle.port_epi(p["I1"], p["I2"], D, p["vMax"], p["Pd0"], p["dirn"], p["O"], 6, 64, paths=paths)
+    want = oracle.port_epi(p["I1"], p["I2"], D, p["vMax"], p["Pd0"], p["dirn"], p["O"], 6, P2, paths=paths)
     for rank, bestD, minC in res:
         assert np.array_equal(minC, want["minC"]), rank
         a, b = bestD.copy(), want["bestD"].copy()
