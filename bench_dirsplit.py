@@ -58,7 +58,10 @@ def main():
         print(json.dumps({"metric": "ms per 3840x2160 pair (256 labels, 8 paths), directions split over GPUs",
                           "n_gpus": world, "value": float(ms.item()), "unit": "ms", "higher_is_better": False,
                           "gde_per_s": N * D / (float(ms.item()) * 1e-3) / 1e9,
-                          "nvlink_bytes_reduce_scatter_per_rank": int((world - 1) / world * N * D * 2) if world > 1 else 0}), flush=True)
+                          "exchange": ("none" if world == 1 else
+                                       "u16 reduce-scatter" if (world < 4 or os.environ.get("FSGM_DIRSPLIT_U16") == "1") else "u8 all-to-all"),
+                          "nvlink_bytes_per_rank": 0 if world == 1 else int((world - 1) / world * N * D *
+                                                   (2 if (world < 4 or os.environ.get("FSGM_DIRSPLIT_U16") == "1") else 1))}), flush=True)
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
     ctx.close()
