@@ -272,13 +272,16 @@ def run_ours(args):
         if "vsweep" in stages:
             k_ms, k_launches = stages["vsweep"]
             k_name = "vsweep_kernel (3 non-horizontal directions per pass; cost rows by TMA, path state in smem, WTA fused)"
-            per_launch_bytes = P * N * D * 9
-            # dram__bytes_read+write per launch from profiles/r1i_kernels_p30.txt (ncu --set full), mean of the two passes
-            traffic = (TRAFFIC_VSWEEP_P30 * P / 30.0) if TRAFFIC_VSWEEP_P30 else None
+            # launches are per wave and per pass: pairs per launch = (pairs in the timed region * 2 passes) / launches
+            pairs_per_launch = P * args.steps * 2.0 / k_launches
+            per_launch_bytes = pairs_per_launch * N * D * 9
+            # dram__bytes_read+write per launch from profiles/r1i_kernels_p30.txt (ncu --set full, 30 pairs per launch),
+            # mean of the two passes, scaled to the pairs one launch handles
+            traffic = (TRAFFIC_VSWEEP_P30 * pairs_per_launch / 30.0) if TRAFFIC_VSWEEP_P30 else None
         else:
             k_ms, k_launches = stages.get("sweep", (0.0, 0))
             k_name = "sweep_fast_kernel (path aggregation, all 8 directions in one launch)"
-            per_launch_bytes = P * N * D * 2 * PATHS
+            per_launch_bytes = P * N * D * 2 * PATHS * args.steps / max(1, k_launches)
             traffic = None
         ach = (per_launch_bytes / (k_ms / k_launches * 1e-3) / 1e9) if k_launches else None
         balg_pair = N * D * (1 + 3 * PATHS) + 50 * N

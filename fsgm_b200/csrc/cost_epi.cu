@@ -228,7 +228,8 @@ epi_cost_fused_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restr
     const size_t N = (size_t)W * H;
     const int pair = blockIdx.z, x0 = blockIdx.x * FC_TX, y0 = blockIdx.y * FC_TY;
     const int tid = threadIdx.x, q = tid % D4, i0 = tid / D4;
-    const uint32_t* c2 = cen2 + pair * N;
+    const char* c2b = reinterpret_cast<const char*>(cen2 + pair * N);          // gathers use a 32-bit BYTE offset from this base
+    const uint32_t W4 = (uint32_t)W * 4u;
     const double* PdX = Pd0 + (size_t)pair * 2 * N; const double* PdY = PdX + N;
     const double* DrX = dirn + (size_t)pair * 2 * N; const double* DrY = DrX + N;
     const double* Op = O + pair * N;
@@ -269,7 +270,7 @@ epi_cost_fused_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restr
                     const double t = __dmul_rn(off, vzs[j]);
                     const uint32_t x2 = ref_round_clamp_w(__dadd_rn(bx, __dmul_rn(t, ux)), wmax);
                     const uint32_t y2 = ref_round_clamp_w(__dadd_rn(by, __dmul_rn(t, uy)), hmax);
-                    packed |= (uint32_t)__popc(c1 ^ __ldg(c2 + (y2 * (uint32_t)W + x2))) << (8 * j);
+                    packed |= (uint32_t)__popc(c1 ^ __ldg(reinterpret_cast<const uint32_t*>(c2b + (y2 * W4 + x2 * 4u)))) << (8 * j);
                 }
             } else {
 #pragma unroll
@@ -278,7 +279,7 @@ epi_cost_fused_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restr
                     const double wx = __dadd_rn(bx, __dmul_rn(t, ux)), wy = __dadd_rn(by, __dmul_rn(t, uy));
                     const uint32_t x2 = (wx != wx) ? 0u : ref_round_clamp_w(wx, wmax);
                     const uint32_t y2 = (wy != wy) ? 0u : ref_round_clamp_w(wy, hmax);
-                    packed |= (uint32_t)__popc(c1 ^ __ldg(c2 + (y2 * (uint32_t)W + x2))) << (8 * j);
+                    packed |= (uint32_t)__popc(c1 ^ __ldg(reinterpret_cast<const uint32_t*>(c2b + (y2 * W4 + x2 * 4u)))) << (8 * j);
                 }
             }
             raw_row[i * D4 + q] = packed;
