@@ -195,7 +195,7 @@ int launch_epi_cost(fsgm_ctx* c, int n, const double* d_vz, const uint32_t* cen1
 // so one unsigned conversion, an add, a shift and an unsigned min reproduce all of it — except NaN, for which the
 // hardware conversion does not return 0.  NaN can only appear when an input is non-finite or |offset| is so large
 // that offset*vz overflows (inf*0); such pixels are flagged while staging and take a checked path.
-constexpr int FC_TX = 32, FC_TY = 128, FC_THREADS = 256;
+constexpr int FC_TX = 32, FC_THREADS = 256;      // strip width; rows per CTA are chosen at launch (32..128)
 
 __device__ __forceinline__ uint32_t ref_round_clamp_w(double w, uint32_t hi)
 {
@@ -215,7 +215,7 @@ template <int D4>      // D = 4*D4 labels, D4 in {16, 32, 64}
 __global__ void __launch_bounds__(FC_THREADS)
 epi_cost_fused_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restrict__ cen2,
                       const double* __restrict__ Pd0, const double* __restrict__ dirn, const double* __restrict__ O,
-                      const double* __restrict__ vz, int W, int H, uint8_t* __restrict__ C)
+                      const double* __restrict__ vz, int W, int H, int FC_TY, uint8_t* __restrict__ C)
 {
     constexpr int NPIX = FC_TX + 4, IPT = FC_THREADS / D4, XP = FC_TX / IPT;   // XP consecutive output columns per thread
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -322,7 +322,10 @@ int launch_epi_cost_fused(fsgm_ctx* c, int n, const double* d_vz, const uint32_t
     StageScope ss(c, ST_EPI_COST);
     const int D4 = D / 4;
     const size_t smem = fused_cost_smem(D4);
-    dim3 grid((W + FC_TX - 1) / FC_TX, (H + FC_TY - 1) / FC_TY, n);
+    // rows per CTA: tall strips waste less on the 4 warm-up rows, but a small batch needs enough CTAs to fill the GPU
+    int ty = 128;
+    while (ty > 32 && (size_t)((W + FC_TX - 1) / FC_TX) * ((H + ty - 1) / ty) * n < (size_t)c->sm_count * 8) ty >>= 1;
+    dim3 grid((W + FC_TX - 1) / FC_TX, (H + ty - 1) / ty, n);
 #define FSGM_FC(D4V)                                                                                              \
     do {                                                                                                          \
         const unsigned bit = 1u << (D4V == 16 ? 0 : D4V == 32 ? 1 : 2);                                           \
@@ -330,7 +333,7 @@ int launch_epi_cost_fused(fsgm_ctx* c, int n, const double* d_vz, const uint32_t
             FSGM_CUDA(c, cudaFuncSetAttribute(epi_cost_fused_kernel<D4V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
             c->attr_mask |= bit;                                                                                  \
         }                                                                                                         \
-        epi_cost_fused_kernel<D4V><<<grid, FC_THREADS, smem, c->stream>>>(cen1, cen2, Pd0, dirn, O, d_vz, W, H, C);    \
+        epi_cost_fused_kernel<D4V><<<grid, FC_THREADS, smem, c->stream>>>(cen1, cen2, Pd0, dirn, O, d_vz, W, H, ty, C); \
     } while (0)
     if (D4 == 16) FSGM_FC(16); else if (D4 == 32) FSGM_FC(32); else FSGM_FC(64);
 #undef FSGM_FC
