@@ -111,3 +111,17 @@ def test_pyd_bad_arguments(ctx):
     with pytest.raises(api.FsgmError) as e:     # 33*33 labels
         ctx.calc_pyd_cost_sgm(fp["I1"], fp["I2"], np.zeros((2, 12, 16)), 16, 16, 2, 1, 6, 32)
     assert e.value.code == api.FSGM_ERR_DOMAIN
+
+
+def test_pyd_half_kitti_size_vs_oracle(ctx, oracle):
+    """Config C's middle pyramid level at its real size (621x188, r = 5 -> 121 labels, 8 paths, 2 passes): the whole
+    gateway against the CPU oracle (about 10 s of CPU with the reference build)."""
+    W, H = 621, 188
+    fp = synth.flow_pair(W, H, seed=21, umax=4, vmax=3)
+    rng = np.random.default_rng(2)
+    mv = np.round(rng.normal(0, 1.5, (2, H, W)))
+    want = _oracle_pyd(oracle, fp["I1"], fp["I2"], mv, 5, 5, 2, 1, 6, 32, 1, 2, 0, stages=False)
+    bestD, minC, mvSub = ctx.calc_pyd_cost_sgm(fp["I1"], fp["I2"], mv, 5, 5, 2, 1, 6, 32, 1, 2, 0)
+    assert np.array_equal(minC, want["minC"])
+    assert np.array_equal(bestD, want["bestD"])
+    assert np.array_equal(mvSub, want["mvSub"])
