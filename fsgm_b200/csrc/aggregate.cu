@@ -17,8 +17,14 @@
 // and direction.  u16 exists only in registers.
 //
 // Arithmetic: the reference computes in unsigned char with mod-256 truncation (common.h:4-8).  When
-// P1,P2 >= 0, cmax+P1+P2 <= 255 and 2*cmax+P2 <= 255 no truncation can fire and the u16 lanes are exact
-// (WRAP=false); otherwise the WRAP=true instantiation reproduces every truncation explicitly.
+// P1,P2 >= 0, cmax+P1+P2 <= 255 and 2*cmax+P2 <= 255 no truncation can fire and the u16 lanes are exact;
+// otherwise the WRAP=true instantiation of sweep_kernel reproduces every truncation explicitly.
+//
+// Kernels in this file (launch_sweeps picks one):
+//   hsweep_tma_kernel  horizontal directions only, no-wrap domain, D in {64,128,256}: cost rows staged by 1-D bulk TMA
+//   sweep_fast_kernel  any set of directions, no-wrap domain: register prefetch ring, branch-free path restarts
+//   sweep_kernel       WRAP=true: explicit mod-256 emulation (parameters or cost values outside the no-wrap domain)
+// The three non-horizontal directions of a pass have a faster, row-synchronous implementation in vsweep.cu.
 #include "fsgm_internal.h"
 #include "sgm_step.cuh"
 
