@@ -264,3 +264,24 @@ def test_wave_pipeline_equals_plain_path(ctx):
         p = ps[i]
         b, m, _, _ = ctx.calc_cost_sgm(p["I1"], p["I2"], D, 0.3, p["Pd0"], p["dirn"], p["O"], 6, 64, opts=o)
         assert np.array_equal(b, b1[i]) and np.array_equal(m, m1[i]), i
+
+
+def test_config_a_full_size(ctx, oracle):
+    """BASELINE.json configs[0] at its real size (640x480, 128 labels, 8 paths): gateway (generic kernels for a single pair),
+    forced cluster kernels (cluster of 2 CTAs at this width) and the CPU oracle agree bit for bit."""
+    from fsgm_b200 import api
+    W, H, D = 640, 480, 128
+    o = api.epi_opts(paths=8)
+    p = synth.epipolar_pair(W, H, D, seed=1)
+    ref = _oracle_epi(oracle, p, D, 6, 64, 8)
+    for mode in (0, 2, 4):
+        ctx.tune(1, mode)
+        b, m, _, _ = ctx.calc_cost_sgm(p["I1"], p["I2"], D, 0.3, p["Pd0"], p["dirn"], p["O"], 6, 64, opts=o)
+        assert np.array_equal(m, ref["minC"]), mode
+        _cmp_bestD(b, ref, D)
+    ctx.tune(1, 0)
+    # the shipped 4-path setting too
+    ref4 = _oracle_epi(oracle, p, D, 6, 64, 4)
+    b, m, _, _ = ctx.calc_cost_sgm(p["I1"], p["I2"], D, 0.3, p["Pd0"], p["dirn"], p["O"], 6, 64)
+    assert np.array_equal(m, ref4["minC"])
+    _cmp_bestD(b, ref4, D)
