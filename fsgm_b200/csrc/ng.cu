@@ -258,6 +258,237 @@ ng_kernel(const NgParams prm)
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Pipelined variant (W >= 4).  Same arithmetic, two block barriers per pixel instead of five:
+//   phase X: warps 0-13 run the 4 x 108 compatibility searches of pixel p; warps 14-15 build the candidates of pixel
+//            p+1 (they only need ring slots written before pixel p: the L1 slot of p-1 and rows y-1 / y-2), and the
+//            global rows pixel p+1 / p+2 will need are fetched into registers;
+//   phase Y: top-2 per direction, Sp + WTA and the ring commits of pixel p, plus the prefetched rows go to shared memory.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NG_THREADS)
+ng_pipe_kernel(const NgParams prm)
+{
+    const int W = prm.W, H = prm.H;
+    const size_t N = (size_t)W * H;
+    const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint8_t* I1 = prm.I1 + pair * N;
+    const uint32_t* cen1 = prm.cen1 + pair * N;
+    const uint32_t* cen2 = prm.cen2 + pair * N;
+    int* mvrow = prm.mvrow + (size_t)pair * 2 * W * NGD * 2;
+    int16_t* Lrow = prm.Lrow + (size_t)pair * 3 * 2 * W * NGD;
+    Top2* toprow = prm.toprow + (size_t)pair * 3 * 2 * W;
+
+    __shared__ int cmx[2][NGD], cmy[2][NGD], ccost[2][NGD];   // candidates of pixel p (parity p&1) and p+1
+    __shared__ int Lc[4][NGD];
+    __shared__ int4 pent[4][NGD];                             // predecessor entries of the pixel being stepped
+    __shared__ Top2 top1[2];
+    __shared__ Top2 hint[2][3];                               // stale ring slots of L2,L3,L4 for pixel q (parity q&1)
+    __shared__ int preMin[4];
+    __shared__ uint32_t c1win[2][25];
+    __shared__ int rnd[2][8];
+    __shared__ uint32_t rstate[31];
+    __shared__ int rf, rr;
+
+    auto gen_rnd = [&](size_t q) {                            // thread 0 only: the 8 rand() values of pixel q
+        int* out = rnd[q & 1];
+        if (prm.rand_stream) { for (int i = 0; i < 8; ++i) out[i] = prm.rand_stream[(pair * N + q) * 8 + i]; return; }
+        int f = rf, r = rr;
+        for (int i = 0; i < 8; ++i) {
+            const uint32_t v = rstate[f] + rstate[r];
+            rstate[f] = v;
+            out[i] = (int)((v >> 1) & 0x7FFFFFFFu);
+            f = (f + 1 == 31) ? 0 : f + 1; r = (r + 1 == 31) ? 0 : r + 1;
+        }
+        rf = f; rr = r;
+    };
+    auto load_c1 = [&](size_t q, int k) {
+        const int x = (int)(q % W), y = (int)(q / W);
+        return cen1[(size_t)clampi(y + k / 5 - 2, 0, H - 1) * W + clampi(x + k % 5 - 2, 0, W - 1)];
+    };
+    // candidates of pixel q by `nthr` cooperating threads (thread index t), one candidate at a time per thread
+    auto make_candidates = [&](size_t q, int t, int nthr) {
+        const int x = (int)(q % W), y = (int)(q / W), qp = (int)(q & 1);
+        const int cur1q = (int)((q + 1) & 1);
+        for (int c = t; c < NGD; c += nthr) {
+            const int l = c / 27, i = (c % 27) / 9, off = c % 9, oy = off / 3 - 1, ox = off % 3 - 1;
+            int hx, hy;
+            if (i < 2) {
+                const Top2& tt = (l == 0) ? top1[cur1q] : hint[qp][l - 1];
+                hx = tt.mvx[i]; hy = tt.mvy[i];
+            } else { hx = rnd[qp][2 * l] % 256 - 128; hy = rnd[qp][2 * l + 1] % 128 - 64; }
+            uint32_t s = 0;
+#pragma unroll 5
+            for (int k = 0; k < 25; ++k) {
+                const int y1 = clampi(y + k / 5 - 2, 0, H - 1), x1 = clampi(x + k % 5 - 2, 0, W - 1);
+                const int y2 = clampi((int)((uint32_t)(oy + y1) + (uint32_t)hy), 0, H - 1);
+                const int x2 = clampi((int)((uint32_t)(ox + x1) + (uint32_t)hx), 0, W - 1);
+                s += __popc(c1win[qp][k] ^ __ldg(cen2 + (size_t)W * y2 + x2));
+            }
+            ccost[qp][c] = (int)((2 * s + 25) / 50);
+            cmx[qp][c] = (int)((uint32_t)hx + (uint32_t)ox);
+            cmy[qp][c] = (int)((uint32_t)hy + (uint32_t)oy);
+        }
+    };
+
+    // ---- prologue: everything pixel 0 and pixel 1 need ------------------------------------------------------
+    if (tid < 2) { for (int i = 0; i < 2; ++i) { top1[tid].mvx[i] = 0; top1[tid].mvy[i] = 0; top1[tid].cost[i] = 0; } }
+    if (tid < 6) { Top2 z; for (int i = 0; i < 2; ++i) { z.mvx[i] = z.mvy[i] = z.cost[i] = 0; } hint[tid / 3][tid % 3] = z; }   // ring rows start zeroed
+    if (tid < NGD) { pent[0][tid] = make_int4(0, 0, 0, 0); }
+    if (tid < 31 && !prm.rand_stream) rstate[tid] = prm.rng_state[pair * 31 + tid];
+    if (tid == 0) { rf = 3; rr = 0; }
+    if (tid >= 64 && tid < 89) c1win[0][tid - 64] = load_c1(0, tid - 64);
+    if (tid >= 96 && tid < 121 && N > 1) c1win[1][tid - 96] = load_c1(1, tid - 96);
+    __syncthreads();
+    if (tid == 0) { gen_rnd(0); if (N > 1) gen_rnd(1); }
+    __syncthreads();
+    make_candidates(0, tid, NG_THREADS);
+    __syncthreads();
+
+    for (size_t p = 0; p < N; ++p) {
+        const int x = (int)(p % W), y = (int)(p / W);
+        const int curRow = (y + 1) & 1;
+        const int cp = (int)(p & 1), cur1 = (int)((p + 1) & 1);
+        const bool startX = (x == 0), startY = (y == 0), startR = (x == W - 1);
+        const size_t p1 = p + 1, p2 = p + 2;
+        const int x1n = (int)(p1 % W), y1n = (int)(p1 / W);
+
+        // ---- phase X ----------------------------------------------------------------------------------------------
+        // register prefetch (consumed in phase Y): predecessor rows + previous minima of p+1, stale hints + census of p+2
+        int2 pf_mv = make_int2(0, 0); int pf_c = 0; bool pf_ok = false;
+        Top2 pf_hint; uint32_t pf_c1 = 0; int pf_min = 0;
+        if (p1 < N && y1n > 0) {
+            const int preRow1 = y1n & 1;
+            if (tid < 3 * NGD) {
+                const int q = tid / NGD, d = tid - q * NGD, xs = x1n + q - 1;
+                if (xs >= 0 && xs < W) {
+                    const size_t cell = (size_t)preRow1 * W + xs;
+                    pf_mv = *reinterpret_cast<const int2*>(mvrow + (cell * NGD + d) * 2);
+                    pf_c = (int)Lrow[((size_t)q * 2 * W + cell) * NGD + d];
+                    pf_ok = true;
+                }
+            } else if (tid >= 400 && tid < 403) {
+                const int q = tid - 400, xs = x1n + q - 1;
+                if (xs >= 0 && xs < W) pf_min = toprow[((size_t)q * 2 + preRow1) * W + xs].cost[0] & 0xFF;
+            }
+        }
+        if (p2 < N) {
+            const int x2n = (int)(p2 % W), y2n = (int)(p2 / W);
+            if (tid >= 324 && tid < 327) pf_hint = toprow[((size_t)(tid - 324) * 2 + ((y2n + 1) & 1)) * W + x2n];
+            if (tid >= 352 && tid < 377) pf_c1 = load_c1(p2, tid - 352);
+        }
+        if (warp < 14) {
+            const int pixCur = I1[p];
+            if (tid < 4 * NGD) {
+                const int dir = tid / NGD, d = tid - dir * NGD;    // 0 L1, 1 L2, 2 L3, 3 L4
+                const bool start = dir == 0 ? startX : dir == 1 ? (startX || startY) : dir == 2 ? startY : (startY || startR);
+                int out;
+                if (start) out = ccost[cp][d];
+                else {
+                    const int4* q = pent[dir];
+                    const int pixPre = dir == 0 ? I1[p - 1] : I1[p - W + (dir - 2)];
+                    const int P2 = abs(pixCur - pixPre) > 50 ? prm.P2 / 8 : prm.P2;          // :101-105
+                    const uint32_t pm = (uint32_t)preMin[dir];
+                    const uint32_t far_ = (pm + (uint32_t)P2) & 0xFFu;
+                    uint32_t same = far_, near_ = far_;
+                    const int mx = cmx[cp][d], my = cmy[cp][d];
+#pragma unroll 4
+                    for (int d2 = 0; d2 < NGD; ++d2) {
+                        const int4 e = q[d2];
+                        const uint32_t c2 = (uint32_t)e.z;
+                        const bool eq = (e.x == mx) & (e.y == my);
+                        const bool nr = ((uint32_t)(e.x - mx + 2) <= 4u) & ((uint32_t)(e.y - my + 2) <= 4u);
+                        same = eq ? (c2 & 0xFFu) : same;                                      // last match wins (:71-72)
+                        near_ = min(near_, (nr & !eq) ? ((c2 + (uint32_t)prm.P1) & 0xFFu) : 0xFFu);
+                    }
+                    out = ccost[cp][d] + (int)min(min(far_, same), near_) - (int)pm;           // int, not truncated (:80)
+                }
+                Lc[dir][d] = out;
+            }
+        } else if (p1 < N) {
+            make_candidates(p1, tid - 14 * 32, NG_THREADS - 14 * 32);
+        }
+        __syncthreads();
+
+        // ---- phase Y ----------------------------------------------------------------------------------------------
+        if (warp < 4) {
+            const int dir = warp;
+            const bool start = dir == 0 ? startX : dir == 1 ? (startX || startY) : dir == 2 ? startY : (startY || startR);
+            Top2* slot = (dir == 0) ? &top1[cur1] : &toprow[((size_t)(dir - 1) * 2 + curRow) * W + x];
+            const Top2 old = *slot;                                   // stale content is part of the reference's behaviour
+            Top2 nw = old;
+            if (start) nw.cost[0] = 0;
+            else {
+                uint32_t k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
+                for (int d = lane; d < NGD; d += 32) {
+                    const int cst = Lc[dir][d];
+                    if (cst < 255) {
+                        const uint32_t key = ((uint32_t)(cst + 1024) << 8) | (uint32_t)d;
+                        if (key < k1) { k2 = k1; k1 = key; } else if (key < k2) k2 = key;
+                    }
+                }
+                const uint32_t g1 = __reduce_min_sync(0xffffffffu, k1);
+                const uint32_t g2 = __reduce_min_sync(0xffffffffu, k1 == g1 ? k2 : k1);
+                nw.cost[0] = 255; nw.cost[1] = 255;
+                if (g1 != 0xFFFFFFFFu) {
+                    const int d1 = g1 & 0xFF;
+                    nw.mvx[1] = old.mvx[0]; nw.mvy[1] = old.mvy[0];
+                    nw.mvx[0] = cmx[cp][d1]; nw.mvy[0] = cmy[cp][d1]; nw.cost[0] = Lc[dir][d1];
+                    if (g2 != 0xFFFFFFFFu) {
+                        const int d2 = g2 & 0xFF;
+                        nw.mvx[1] = cmx[cp][d2]; nw.mvy[1] = cmy[cp][d2]; nw.cost[1] = Lc[dir][d2];
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                *slot = nw;
+                if (dir == 0) preMin[0] = nw.cost[0] & 0xFF;          // L1's predecessor of pixel p+1 is this pixel
+            }
+        } else if (warp == 4) {
+            unsigned long long key = ~0ull;
+            for (int d = lane; d < NGD; d += 32) {
+                const uint32_t a = (uint32_t)(Lc[0][d] + Lc[2][d]) + (uint32_t)(Lc[1][d] + Lc[3][d]);   // :357-362
+                if (prm.Sp32) prm.Sp32[(pair * N + p) * NGD + d] = a;
+                const unsigned long long kk = ((unsigned long long)a << 32) | (uint32_t)d;
+                key = kk < key ? kk : key;
+            }
+            for (int o = 16; o; o >>= 1) {
+                const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+                key = other < key ? other : key;
+            }
+            if (lane == 0) {
+                const int d = (int)(key & 0xFFFFFFFFu);
+                prm.minC[pair * N + p] = (uint32_t)(key >> 32);
+                prm.flow[(size_t)pair * 2 * N + p] = (double)cmx[cp][d];
+                prm.flow[(size_t)pair * 2 * N + N + p] = (double)cmy[cp][d];
+            }
+        } else if (warp == 5 || warp == 6 || warp == 7 || warp == 8) {
+            // ring commits of pixel p: candidate mvs + L2,L3,L4 costs to the row rings, L1 entries for the next pixel
+            const size_t cell = (size_t)curRow * W + x;
+            for (int i = tid - 160; i < NGD; i += 128) {
+                *reinterpret_cast<int2*>(mvrow + (cell * NGD + i) * 2) = make_int2(cmx[cp][i], cmy[cp][i]);
+                pent[0][i] = make_int4(cmx[cp][i], cmy[cp][i], Lc[0][i], 0);
+#pragma unroll
+                for (int q = 0; q < 3; ++q) Lrow[((size_t)q * 2 * W + cell) * NGD + i] = (int16_t)Lc[q + 1][i];
+                if (prm.Cent) {
+                    int* e = prm.Cent + ((pair * N + p) * NGD + i) * 3;
+                    e[0] = cmx[cp][i]; e[1] = cmy[cp][i]; e[2] = ccost[cp][i];
+                }
+            }
+        }
+        // prefetched rows -> shared memory (pent[1..3] were last read in phase X of this pixel)
+        if (pf_ok) pent[1 + tid / NGD][tid % NGD] = make_int4(pf_mv.x, pf_mv.y, pf_c, 0);
+        if (tid >= 400 && tid < 403) preMin[1 + tid - 400] = pf_min;
+        if (p2 < N) {
+            if (tid >= 324 && tid < 327) hint[p2 & 1][tid - 324] = pf_hint;
+            if (tid >= 352 && tid < 377) c1win[p2 & 1][tid - 352] = pf_c1;
+            if (tid == 384) gen_rnd(p2);
+        }
+        __syncthreads();
+    }
+}
+
 size_t ng_scratch_bytes(int n, int W)
 {
     return align256((size_t)n * 2 * W * NGD * 2 * sizeof(int)) + align256((size_t)n * 3 * 2 * W * NGD * sizeof(int16_t)) +
@@ -287,7 +518,8 @@ int launch_ng(fsgm_ctx* c, int n, const uint8_t* I1, const uint32_t* cen1, const
         FSGM_CUDA(c, cudaStreamSynchronize(c->stream));       // host_rng_states is a caller temporary
     }
     p.rng_state = d_state;
-    ng_kernel<<<n, NG_THREADS, 0, c->stream>>>(p);
+    if (W >= 4) ng_pipe_kernel<<<n, NG_THREADS, 0, c->stream>>>(p);      // pipelined phases need p+1 / p+2 to lie outside the cells pixel p commits
+    else ng_kernel<<<n, NG_THREADS, 0, c->stream>>>(p);
     FSGM_LAUNCHED(c);
     return FSGM_OK;
 }
