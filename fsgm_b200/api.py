@@ -28,7 +28,7 @@ class FsgmError(RuntimeError):
 
 class EpiOpts(C.Structure):
     _fields_ = [("paths", C.c_int), ("total_pass", C.c_int), ("subpixel", C.c_int),
-                ("adaptive_p2", C.c_int), ("vz_to_disp", C.c_int)]
+                ("adaptive_p2", C.c_int), ("vz_to_disp", C.c_int), ("fb_check", C.c_int), ("fb_thr", C.c_int)]
 
 
 def load_library() -> C.CDLL:
@@ -86,8 +86,8 @@ def glibc_rand(seed: int, count: int) -> np.ndarray:
     return out
 
 
-def epi_opts(paths=4, total_pass=2, subpixel=1, adaptive_p2=0, vz_to_disp=1) -> EpiOpts:
-    return EpiOpts(paths, total_pass, subpixel, adaptive_p2, vz_to_disp)
+def epi_opts(paths=4, total_pass=2, subpixel=1, adaptive_p2=0, vz_to_disp=1, fb_check=0, fb_thr=2) -> EpiOpts:
+    return EpiOpts(paths, total_pass, subpixel, adaptive_p2, vz_to_disp, fb_check, fb_thr)
 
 
 class Context:
@@ -189,6 +189,17 @@ class Context:
         self._ck(self._l.fsgm_calc_cost_sgm_dev(
             self._h, n, _dp(I1), _dp(I2), W, H, int(dMax), C.c_double(vMax), _dp(Pd0), _dp(dirn), _dp(O), int(P1), int(P2),
             C.byref(opts) if opts is not None else None, _dp(bestD), _dp(minC)))
+
+    def forward_backward_check_dev(self, bestD, Pd0, dirn, O, vMax, n, conf, bestD2, thr=2, use_vzind=1):
+        """forward_backward_check (calc_cost_sgm.cpp:488-536) on the x256 label map (before the vz conversion)"""
+        npairs, H, W = bestD.shape
+        self._ck(self._l.fsgm_forward_backward_check_dev(self._h, npairs, _dp(bestD), W, H, _dp(Pd0), _dp(dirn), _dp(O),
+                                                         C.c_double(vMax), int(n), int(thr), int(use_vzind), _dp(conf), _dp(bestD2)))
+
+    def convert_vzind_to_disp_dev(self, bestD, O, vMax, n):
+        """convert_vzInd_to_disp (calc_cost_sgm.cpp:414-426), in place"""
+        npairs, H, W = bestD.shape
+        self._ck(self._l.fsgm_convert_vzind_to_disp_dev(self._h, npairs, _dp(bestD), W, H, _dp(O), C.c_double(vMax), int(n)))
 
     def census_dev(self, img, cen):
         n, H, W = img.shape

@@ -328,12 +328,12 @@ using namespace fsgm;
 
 extern "C" {
 
-int fsgm_abi_version(void) { return 1; }
+int fsgm_abi_version(void) { return 2; }
 
 void fsgm_epi_opts_default(fsgm_epi_opts* o)
 {
     if (!o) return;
-    o->paths = 4; o->total_pass = 2; o->subpixel = 1; o->adaptive_p2 = 0; o->vz_to_disp = 1;
+    o->paths = 4; o->total_pass = 2; o->subpixel = 1; o->adaptive_p2 = 0; o->vz_to_disp = 1; o->fb_check = 0; o->fb_thr = 2;
 }
 
 int fsgm_create(int device, fsgm_ctx** out)
@@ -684,10 +684,73 @@ int fsgm_calc_cost_sgm_batch(fsgm_ctx* c, int n, const uint8_t* I1, const uint8_
     return fsgm_synchronize(c);
 }
 
+int fsgm_forward_backward_check_dev(fsgm_ctx* c, int n, const uint32_t* d_bestD, int W, int H, const double* d_Pd0, const double* d_dir,
+                                    const double* d_O, double vMax, int nlab, int thr, int use_vzind, uint8_t* d_conf, uint32_t* d_bestD2)
+{
+    FSGM_TRY(check_dims(c, n, W, H, 1));
+    if (!d_bestD || !d_Pd0 || !d_dir || !d_O || !d_conf || !d_bestD2) return fail(c, FSGM_ERR_ARG, "null pointer");
+    if (nlab < 1) return fail(c, FSGM_ERR_ARG, "n must be positive");
+    FSGM_CUDA(c, cudaSetDevice(c->device));
+    return launch_fb_check(c, n, d_bestD, W, H, d_Pd0, d_dir, d_O, vMax, nlab, thr, use_vzind, d_conf, d_bestD2);
+}
+
+int fsgm_convert_vzind_to_disp_dev(fsgm_ctx* c, int n, uint32_t* d_bestD, int W, int H, const double* d_O, double vMax, int nlab)
+{
+    FSGM_TRY(check_dims(c, n, W, H, 1));
+    if (!d_bestD || !d_O) return fail(c, FSGM_ERR_ARG, "null pointer");
+    if (nlab < 1) return fail(c, FSGM_ERR_ARG, "n must be positive");
+    FSGM_CUDA(c, cudaSetDevice(c->device));
+    return launch_vz_to_disp(c, d_bestD, d_O, (size_t)n * W * H, vMax, nlab);
+}
+
+// One pair with the reference's commented-out call (calc_cost_sgm.cpp:589-590) switched back on: labels without the vz
+// conversion, the check, then the conversion (:592-594).  Synchronous, plain copies: this is not the throughput path.
+static int epi_with_fb_check(fsgm_ctx* c, const uint8_t* I1, const uint8_t* I2, int W, int H, int D, double vMax,
+                             const double* Pd0, const double* dirn, const double* O, int P1, int P2, fsgm_epi_opts o,
+                             uint32_t* bestD, uint32_t* minC, uint8_t* conf, uint32_t* bestD2)
+{
+    FSGM_TRY(check_dims(c, 1, W, H, D));
+    if (!I1 || !I2 || !Pd0 || !dirn || !O || !bestD || !minC) return fail(c, FSGM_ERR_ARG, "null pointer");
+    FSGM_CUDA(c, cudaSetDevice(c->device));
+    const size_t N = (size_t)W * H;
+    const size_t in_b = align256(N) * 2 + align256(2 * N * 8) * 2 + align256(N * 8);
+    const size_t out_b = 3 * align256(N * 4) + align256(N);
+    FSGM_TRY(pipe_reserve(c, in_b + out_b));
+    FSGM_TRY(fsgm_synchronize(c));                               // an earlier asynchronous call may still own the slot
+    char* base = c->pipe.buf[0];
+    uint8_t* dI1 = reinterpret_cast<uint8_t*>(base);   base += align256(N);
+    uint8_t* dI2 = reinterpret_cast<uint8_t*>(base);   base += align256(N);
+    double* dPd0 = reinterpret_cast<double*>(base);    base += align256(2 * N * 8);
+    double* dDir = reinterpret_cast<double*>(base);    base += align256(2 * N * 8);
+    double* dO = reinterpret_cast<double*>(base);      base += align256(N * 8);
+    uint32_t* dBest = reinterpret_cast<uint32_t*>(base); base += align256(N * 4);
+    uint32_t* dMin = reinterpret_cast<uint32_t*>(base);  base += align256(N * 4);
+    uint32_t* dB2 = reinterpret_cast<uint32_t*>(base);   base += align256(N * 4);
+    uint8_t* dConf = reinterpret_cast<uint8_t*>(base);
+    cudaStream_t s = c->stream;
+    FSGM_CUDA(c, cudaMemcpyAsync(dI1, I1, N, cudaMemcpyHostToDevice, s));
+    FSGM_CUDA(c, cudaMemcpyAsync(dI2, I2, N, cudaMemcpyHostToDevice, s));
+    FSGM_CUDA(c, cudaMemcpyAsync(dPd0, Pd0, 2 * N * 8, cudaMemcpyHostToDevice, s));
+    FSGM_CUDA(c, cudaMemcpyAsync(dDir, dirn, 2 * N * 8, cudaMemcpyHostToDevice, s));
+    FSGM_CUDA(c, cudaMemcpyAsync(dO, O, N * 8, cudaMemcpyHostToDevice, s));
+    const int vz = o.vz_to_disp;
+    o.vz_to_disp = 0; o.fb_check = 0;
+    FSGM_TRY(fsgm_calc_cost_sgm_dev(c, 1, dI1, dI2, W, H, D, vMax, dPd0, dDir, dO, P1, P2, &o, dBest, dMin));
+    FSGM_TRY(launch_fb_check(c, 1, dBest, W, H, dPd0, dDir, dO, vMax, D + 1, o.fb_thr, /*USE_VZIND :4*/ 1, dConf, dB2));
+    if (vz) FSGM_TRY(launch_vz_to_disp(c, dBest, dO, N, vMax, D + 1));
+    FSGM_CUDA(c, cudaMemcpyAsync(bestD, dBest, N * 4, cudaMemcpyDeviceToHost, s));
+    FSGM_CUDA(c, cudaMemcpyAsync(minC, dMin, N * 4, cudaMemcpyDeviceToHost, s));
+    if (conf) FSGM_CUDA(c, cudaMemcpyAsync(conf, dConf, N, cudaMemcpyDeviceToHost, s));
+    if (bestD2) FSGM_CUDA(c, cudaMemcpyAsync(bestD2, dB2, N * 4, cudaMemcpyDeviceToHost, s));
+    FSGM_CUDA(c, cudaStreamSynchronize(s));
+    return FSGM_OK;
+}
+
 int fsgm_calc_cost_sgm(fsgm_ctx* c, const uint8_t* I1, const uint8_t* I2, int W, int H, int D, double vMax,
                        const double* Pd0, const double* dirn, const double* O, int P1, int P2,
                        const fsgm_epi_opts* opts, uint32_t* bestD, uint32_t* minC, uint8_t* conf, uint32_t* bestD2)
 {
+    if (opts && opts->fb_check) return epi_with_fb_check(c, I1, I2, W, H, D, vMax, Pd0, dirn, O, P1, P2, *opts, bestD, minC, conf, bestD2);
     int rc = fsgm_calc_cost_sgm_batch(c, 1, I1, I2, W, H, D, vMax, Pd0, dirn, O, P1, P2, opts, bestD, minC);
     if (rc != FSGM_OK) return rc;
     // outputs 3 and 4 of the gateway are allocated but never written by the reference (:571-572, :589-590)

@@ -115,6 +115,11 @@ int launch_add_u8(fsgm_ctx* c, uint8_t* a, const uint8_t* b, size_t bytes);
 int launch_sp_wta(fsgm_ctx* c, const uint16_t* Sp, const uint16_t* next0, size_t npix, int D, int subpixel,
                   int vz_to_disp, const double* O, double vMax, uint32_t* bestD, uint32_t* minC);
 
+// ---- forward/backward check and the stand-alone vz conversion (fbcheck.cu) ---------------------------------
+int launch_fb_check(fsgm_ctx* c, int n_pairs, const uint32_t* D1, int W, int H, const double* Pd0, const double* dirn, const double* O,
+                    double vMax, int n, int thr, int use_vzind, uint8_t* conf, uint32_t* D2);
+int launch_vz_to_disp(fsgm_ctx* c, uint32_t* D, const double* O, size_t total, double vMax, int n);
+
 // ---- row-synchronous cluster path for the non-horizontal directions (vsweep.cu) --------------------------
 int vsweep_cluster_size(int W, int D, int ndir, int max_smem);
 int vsweep_max_clusters(int cs, size_t smem, int threads);

@@ -69,8 +69,11 @@ typedef struct fsgm_epi_opts {
     int subpixel;     /* calc_cost_sgm.cpp:560, reference value 1 (always on)                               */
     int adaptive_p2;  /* calc_cost_sgm.cpp:102, reference value 0; threshold 25 (:68-72)                    */
     int vz_to_disp;   /* calc_cost_sgm.cpp:592-594 (USE_VZIND), reference value 1                           */
+    int fb_check;     /* calc_cost_sgm.cpp:589-590: the forward/backward check the reference ships commented
+                         out; 0 = as shipped (conf, bestD2 stay zero), 1 = run it and fill conf / bestD2    */
+    int fb_thr;       /* calc_cost_sgm.cpp:489 default argument thr = 2 (x256 label units)                  */
 } fsgm_epi_opts;
-FSGM_API void fsgm_epi_opts_default(fsgm_epi_opts* o);   /* {4, 2, 1, 0, 1} — the reference as shipped */
+FSGM_API void fsgm_epi_opts_default(fsgm_epi_opts* o);   /* {4, 2, 1, 0, 1, 0, 2} — the reference as shipped */
 
 /* ---- gateway 1: calc_cost_sgm (calc_cost_sgm.cpp:539-598) ----------------------------------
  * [bestD, minC, conf, bestD2] = calc_cost_sgm(I1, I2, dMax, vMax, pixelPosD0, normlizeDirection,
@@ -78,7 +81,8 @@ FSGM_API void fsgm_epi_opts_default(fsgm_epi_opts* o);   /* {4, 2, 1, 0, 1} — 
  * I1,I2 u8[H][W]; pixelPosD0 f64[2][H][W] (1-based); normlizeDirection f64[2][H][W];
  * offsetFromPosD0 f64[H][W].  bestD u32[H][W] = pixel disparity x256, minC u32[H][W];
  * conf u8[H][W] and bestD2 u32[H][W] may be NULL, otherwise they are zero-filled exactly as the
- * reference leaves them (its forward/backward check is commented out, :589-590).
+ * reference leaves them (its forward/backward check is commented out, :589-590) — unless opts->fb_check
+ * is set, which runs that check (on the label map, before the vz conversion) and fills both.
  * opts == NULL means the reference as shipped. */
 FSGM_API int fsgm_calc_cost_sgm(fsgm_ctx* ctx, const uint8_t* I1, const uint8_t* I2, int width, int height,
                        int dMax, double vMax, const double* pixelPosD0, const double* normlizeDirection,
@@ -120,6 +124,17 @@ FSGM_API int fsgm_sweep_dev(fsgm_ctx* ctx, int n_pairs, const uint8_t* d_C, cons
 FSGM_API int fsgm_epi_aggregate_dev(fsgm_ctx* ctx, int n_pairs, const uint8_t* d_C, const uint8_t* d_I1, int width, int height,
                            int dMax, int P1, int P2, const fsgm_epi_opts* opts, uint16_t* d_Sp /* may be NULL */,
                            const double* d_offsetFromPosD0, double vMax, uint32_t* d_bestD, uint32_t* d_minC);
+
+/* forward_backward_check (calc_cost_sgm.cpp:488-536) with calc_disp_from_first (:429-486) inlined, and
+ * convert_vzInd_to_disp (:414-426) as a stage of its own.  d_bestD is the x256 label map BEFORE the vz conversion (that is
+ * where the reference's call sits, :589-593), values < 512*256; n = dMax + 1 (:590, :593); use_vzind = 1 is the reference's
+ * build (#define USE_VZIND, :4).  d_conf u8 [n_pairs][H][W] (1 = consistent), d_bestD2 u32 [n_pairs][H][W] (the map
+ * projected into image 2, 512<<8 where nothing landed). */
+FSGM_API int fsgm_forward_backward_check_dev(fsgm_ctx* ctx, int n_pairs, const uint32_t* d_bestD, int width, int height,
+                         const double* d_pixelPosD0, const double* d_normlizeDirection, const double* d_offsetFromPosD0,
+                         double vMax, int n, int thr, int use_vzind, uint8_t* d_conf, uint32_t* d_bestD2);
+FSGM_API int fsgm_convert_vzind_to_disp_dev(fsgm_ctx* ctx, int n_pairs, uint32_t* d_bestD, int width, int height,
+                         const double* d_offsetFromPosD0, double vMax, int n);
 
 /* direction-split building blocks for ONE large pair (the R scan directions spread over GPUs, volumes reduced over
  * NVLink by the caller — fsgm_b200/dist.py does it with an NCCL reduce-scatter on the u16 pairs viewed as u32):

@@ -223,6 +223,65 @@ void orc_vz_to_disp(u32* bestD, int W, int H, const double* O, double vMax, int 
     }
 }
 
+/* N3  forward/backward consistency (calc_cost_sgm.cpp:488-536) with calc_disp_from_first (:429-486): the call the
+ * reference ships commented out (:589-590).  D1 = x256 label map before the vz conversion, n = D+1.
+ * Restated as two gathers-by-scatter over a "largest offer" map instead of the reference's in-place update rule
+ * ("== INVALID || D2 < D1" keeps the maximum, so the result does not depend on the visiting order as long as
+ * D1 < INVALID_DISPARITY = 512<<8). */
+#define ORC_INVALID_DISPARITY (512u << 8)
+static inline double fb_disp(u32 D1, double O, double vMax, int n, int use_vzind)
+{
+    double d = (double)D1 / 256.0;
+    if (use_vzind) { double r = d / n * vMax; d = O * (r / (1 - r)); }
+    return d;
+}
+void orc_fb_check(const u32* D1, int W, int H, const double* Pd0, const double* dirn, const double* O,
+                  double vMax, int n, int thr, int use_vzind, u8* conf, u32* D2)
+{
+    const size_t N = (size_t)W * H;
+    long long* top = (long long*)malloc(N * sizeof(long long));          /* -1 = nothing landed here */
+    for (size_t i = 0; i < N; ++i) top[i] = -1;
+    for (size_t i = 0; i < N; ++i) {
+        const double d = fb_disp(D1[i], O[i], vMax, n, use_vzind);
+        const int px = d2i((Pd0[i] - 1) + d * dirn[i]), py = d2i((Pd0[N + i] - 1) + d * dirn[N + i]);   /* truncation, :459-460 */
+        for (int k = 0; k < 4; ++k) {
+            const long long tx = (long long)px + (k & 1), ty = (long long)py + (k >> 1);
+            if (tx < 0 || tx >= W || ty < 0 || ty >= H) continue;
+            if (top[ty * W + tx] < (long long)D1[i]) top[ty * W + tx] = D1[i];
+        }
+    }
+    for (size_t i = 0; i < N; ++i) D2[i] = top[i] < 0 ? ORC_INVALID_DISPARITY : (u32)top[i];
+    free(top);
+    for (size_t i = 0; i < N; ++i) {
+        const double d = fb_disp(D1[i], O[i], vMax, n, use_vzind);
+        const int px = d2i(round((Pd0[i] - 1) + d * dirn[i])), py = d2i(round((Pd0[N + i] - 1) + d * dirn[N + i]));   /* :516-517 */
+        u8 ok = 1;
+        if (px < 0 || px > W - 1 || py < 0 || py > H - 1) ok = 0;
+        else if (D2[(size_t)py * W + px] == ORC_INVALID_DISPARITY) ok = 0;
+        else if (abs((int)D1[i] - (int)D2[(size_t)py * W + px]) > thr) ok = 0;
+        conf[i] = ok;
+    }
+}
+
+/* a-6 with the commented-out call switched on: labels, check, then the vz conversion (:581-594) */
+void orc_epi_fb(const u8* I1, const u8* I2, int W, int H, int D, double vMax,
+                const double* Pd0, const double* dirn, const double* O, int P1, int P2, int paths, int thr,
+                u32* bestD, u32* minC, u8* conf, u32* bestD2)
+{
+    const size_t N = (size_t)W * H, V = N * D;
+    u32 *cen1 = (u32*)malloc(N * 4), *cen2 = (u32*)malloc(N * 4), *Sp = (u32*)malloc(V * 4);
+    u8 *raw = (u8*)malloc(V), *C = (u8*)malloc(V);
+    orc_census(I1, cen1, W, H);
+    orc_census(I2, cen2, W, H);
+    orc_epi_cost_raw(cen1, cen2, W, H, D, vMax, Pd0, dirn, O, raw);
+    orc_box5(raw, W, H, D, C);
+    orc_epi_aggregate(C, I1, W, H, D, P1, P2, 2, paths == 8, 0, Sp);
+    orc_epi_wta(Sp, W, H, D, 1, bestD, minC);
+    orc_fb_check(bestD, W, H, Pd0, dirn, O, vMax, D + 1, thr, 1, conf, bestD2);
+    orc_vz_to_disp(bestD, W, H, O, vMax, D);
+    free(cen1); free(cen2); free(Sp); free(raw); free(C);
+}
+
 /* a-6  whole gateway (calc_cost_sgm.cpp:539-598); paths = 4 (as shipped, :102-104) or 8.
  * Any of the stage outputs may be NULL. */
 void orc_epi(const u8* I1, const u8* I2, int W, int H, int D, double vMax,

@@ -86,6 +86,35 @@ def ref_epi_stage_times(I1, I2, D, vMax, Pd0, dirn, O, P1, P2, paths=8):
     return dict(total=tot, cost=tc.value, sgm=ts.value)
 
 
+def ref_epi_fb(I1, I2, D, vMax, Pd0, dirn, O, P1, P2):
+    """8-path build with the commented-out forward_backward_check call (calc_cost_sgm.cpp:589-590) re-enabled."""
+    H, W = I1.shape
+    lib = _ref("epi8fb")
+    lib.ref_epi_all.restype = C.c_double
+    out = dict(bestD=np.empty((H, W), np.uint32), minC=np.empty((H, W), np.uint32),
+               conf=np.empty((H, W), np.uint8), bestD2=np.empty((H, W), np.uint32))
+    out["seconds"] = lib.ref_epi_all(_ptr(I1, _u8p), _ptr(I2, _u8p), W, H, D, C.c_double(vMax), _ptr(Pd0, _f64p),
+                                     _ptr(dirn, _f64p), _ptr(O, _f64p), P1, P2, _ptr(out["bestD"], _u32p),
+                                     _ptr(out["minC"], _u32p), _ptr(out["conf"], _u8p), _ptr(out["bestD2"], _u32p))
+    return out
+
+
+def ref_fb_check(D1, Pd0, dirn, O, vMax, n, thr=2):
+    """forward_backward_check (calc_cost_sgm.cpp:488-536) called directly on a x256 label map."""
+    H, W = D1.shape
+    conf, D2 = np.empty((H, W), np.uint8), np.empty((H, W), np.uint32)
+    _ref("epi4").ref_fb_check(_ptr(D1, _u32p), W, H, _ptr(Pd0, _f64p), _ptr(dirn, _f64p), _ptr(O, _f64p),
+                              C.c_double(vMax), n, thr, _ptr(conf, _u8p), _ptr(D2, _u32p))
+    return conf, D2
+
+
+def ref_vz_to_disp(D1, O, vMax, n):
+    H, W = D1.shape
+    out = np.ascontiguousarray(D1).copy()
+    _ref("epi4").ref_vz_to_disp(_ptr(out, _u32p), W, H, _ptr(O, _f64p), C.c_double(vMax), n)
+    return out
+
+
 def ref_census(I):
     H, W = I.shape
     cen = np.empty((H, W), np.uint32)
@@ -163,6 +192,31 @@ def port_epi(I1, I2, D, vMax, Pd0, dirn, O, P1, P2, paths=8, stages=True):
                     _ptr(O, _f64p), P1, P2, paths, _ptr(out["bestD"], _u32p), _ptr(out["minC"], _u32p),
                     _ptr(g("cen1"), _u32p), _ptr(g("cen2"), _u32p), _ptr(g("Craw"), _u8p), _ptr(g("C"), _u8p),
                     _ptr(g("Sp"), _u32p))
+    return out
+
+
+def port_fb_check(D1, Pd0, dirn, O, vMax, n, thr=2, use_vzind=1):
+    H, W = D1.shape
+    conf, D2 = np.empty((H, W), np.uint8), np.empty((H, W), np.uint32)
+    _port().orc_fb_check(_ptr(D1, _u32p), W, H, _ptr(Pd0, _f64p), _ptr(dirn, _f64p), _ptr(O, _f64p),
+                         C.c_double(vMax), n, thr, use_vzind, _ptr(conf, _u8p), _ptr(D2, _u32p))
+    return conf, D2
+
+
+def port_vz_to_disp(D1, O, vMax, D):
+    H, W = D1.shape
+    out = np.ascontiguousarray(D1).copy()
+    _port().orc_vz_to_disp(_ptr(out, _u32p), W, H, _ptr(O, _f64p), C.c_double(vMax), D)
+    return out
+
+
+def port_epi_fb(I1, I2, D, vMax, Pd0, dirn, O, P1, P2, paths=8, thr=2):
+    H, W = I1.shape
+    out = dict(bestD=np.empty((H, W), np.uint32), minC=np.empty((H, W), np.uint32),
+               conf=np.empty((H, W), np.uint8), bestD2=np.empty((H, W), np.uint32))
+    _port().orc_epi_fb(_ptr(I1, _u8p), _ptr(I2, _u8p), W, H, D, C.c_double(vMax), _ptr(Pd0, _f64p), _ptr(dirn, _f64p),
+                       _ptr(O, _f64p), P1, P2, paths, thr, _ptr(out["bestD"], _u32p), _ptr(out["minC"], _u32p),
+                       _ptr(out["conf"], _u8p), _ptr(out["bestD2"], _u32p))
     return out
 
 

@@ -75,6 +75,38 @@ double ref_epi_stage_times(const uint8_t* I1, const uint8_t* I2, int W, int H, i
     return t2 - t0;
 }
 void ref_census(const uint8_t* I, uint32_t* cen, int W, int H) { census((PixelType*)I, cen, W, H, 2); }
+/* forward_backward_check (calc_cost_sgm.cpp:488) and convert_vzInd_to_disp (:414) called directly */
+void ref_fb_check(const uint32_t* D1, int W, int H, const double* Pd0, const double* dir, const double* O,
+                  double vMax, int n, int thr, uint8_t* conf, uint32_t* D2)
+{
+    forward_backward_check(conf, D2, (unsigned*)D1, W, H, (double*)Pd0, (double*)dir, (double*)O, vMax, n, thr);
+}
+void ref_vz_to_disp(uint32_t* D, int W, int H, const double* O, double vMax, int n)
+{
+    convert_vzInd_to_disp(D, W, H, (double*)O, vMax, n);
+}
+/* all four gateway outputs (conf and bestD2 are zeros unless the build re-enables the call at :589-590, see Makefile) */
+double ref_epi_all(const uint8_t* I1, const uint8_t* I2, int W, int H, int D, double vMax,
+                   const double* Pd0, const double* dir, const double* O, int P1, int P2,
+                   uint32_t* bestD, uint32_t* minC, uint8_t* conf, uint32_t* bestD2)
+{
+    size_t N = (size_t)W * H;
+    In i1(I1, W, H, mxUINT8_CLASS), i2(I2, W, H, mxUINT8_CLASS);
+    In pd(Pd0, W, (mwSize)H * 2, mxDOUBLE_CLASS), dr(dir, W, (mwSize)H * 2, mxDOUBLE_CLASS), of(O, W, H, mxDOUBLE_CLASS);
+    Scalar sD(D), sV(vMax), sP1(P1), sP2(P2);
+    const mxArray* prhs[9] = { &i1.a, &i2.a, &sD.a, &sV.a, &pd.a, &dr.a, &of.a, &sP1.a, &sP2.a };
+    mxArray* plhs[4] = { 0, 0, 0, 0 };
+    double t0 = now_s();
+    mexFunction(4, plhs, 9, prhs);
+    double dt = now_s() - t0;
+    std::memcpy(bestD, plhs[0]->data, N * 4);
+    std::memcpy(minC, plhs[1]->data, N * 4);
+    std::memcpy(conf, plhs[2]->data, N);
+    std::memcpy(bestD2, plhs[3]->data, N * 4);
+    for (int i = 0; i < 4; ++i) shim_destroy(plhs[i]);
+    ref_shim_release();
+    return dt;
+}
 #endif
 
 #if defined(REF_VARIANT_PYD)

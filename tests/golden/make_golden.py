@@ -15,7 +15,12 @@ from fsgm_b200 import synth          # noqa: E402
 from oracle import pyoracle as po    # noqa: E402
 
 
+ONLY = [a for a in sys.argv[1:] if not a.startswith("-")]     # fixture names to (re)write; default all
+
+
 def save(name, **arrs):
+    if ONLY and name not in ONLY:
+        return
     path = os.path.join(HERE, name + ".npz")
     np.savez_compressed(path, **arrs)
     print(f"{name}: {os.path.getsize(path) / 1024:.1f} KiB")
@@ -34,6 +39,15 @@ def main():
         save(name, I1=p["I1"], I2=p["I2"], Pd0=p["Pd0"], dirn=p["dirn"], O=p["O"], vMax=p["vMax"], D=D, P1=P1, P2=P2,
              paths=paths, cen1=r["cen1"], cen2=r["cen2"], Craw=r["Craw"], C=r["C"], Sp=r["Sp"].astype(np.uint16),
              bestD=r["bestD"], minC=r["minC"])
+    # ---- forward/backward check: the 8-path build with the call at calc_cost_sgm.cpp:589-590 re-enabled, and the function
+    #      called directly on a random x256 label map with a loose threshold -------------------------------------------------
+    p = synth.epipolar_pair(56, 36, 32, seed=7)
+    r = po.ref_epi_fb(p["I1"], p["I2"], 32, p["vMax"], p["Pd0"], p["dirn"], p["O"], 6, 64)
+    D1 = np.random.default_rng(77).integers(0, 32 * 256, (36, 56)).astype(np.uint32)
+    conf_d, D2_d = po.ref_fb_check(D1, p["Pd0"], p["dirn"], p["O"], p["vMax"], 33, thr=600)
+    save("epi_fb", I1=p["I1"], I2=p["I2"], Pd0=p["Pd0"], dirn=p["dirn"], O=p["O"], vMax=p["vMax"], D=32, P1=6, P2=64,
+         bestD=r["bestD"], minC=r["minC"], conf=r["conf"], bestD2=r["bestD2"], D1=D1, thr_d=600, conf_d=conf_d, bestD2_d=D2_d,
+         disp_d=po.ref_vz_to_disp(D1, p["O"], p["vMax"], 33))
     # ---- pyramidal: integer prior, fractional prior with adaptive P2, single pass without diagonals ---------
     fp = synth.flow_pair(48, 32, seed=5, umax=3, vmax=2)
     for name, (rx, ry, sub, diag, passes, adp, kind) in {

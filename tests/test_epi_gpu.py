@@ -285,3 +285,63 @@ def test_config_a_full_size(ctx, oracle):
     b, m, _, _ = ctx.calc_cost_sgm(p["I1"], p["I2"], D, 0.3, p["Pd0"], p["dirn"], p["O"], 6, 64)
     assert np.array_equal(m, ref4["minC"])
     _cmp_bestD(b, ref4, D)
+
+
+# ---- N3: forward/backward check, conf / bestD2 outputs (calc_cost_sgm.cpp:414-536, call site :589-593) -----------------
+def _gold(name):
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+    return {k: z[k] for k in z.files}
+
+
+def test_fb_check_golden(ctx):
+    """the gateway with opts.fb_check fills conf / bestD2 exactly as the reference does with its call re-enabled"""
+    import torch
+    from fsgm_b200 import api
+    g = _gold("epi_fb")
+    D, vMax = int(g["D"]), float(g["vMax"])
+    bestD, minC, conf, bestD2 = ctx.calc_cost_sgm(g["I1"], g["I2"], D, vMax, g["Pd0"], g["dirn"], g["O"], int(g["P1"]), int(g["P2"]),
+                                                  opts=api.epi_opts(paths=8, fb_check=1))
+    assert np.array_equal(minC, g["minC"]) and np.array_equal(conf, g["conf"]) and np.array_equal(bestD2, g["bestD2"])
+    assert np.array_equal(bestD.ravel()[:-1], g["bestD"].ravel()[:-1])
+    # as shipped: zeros
+    _, _, conf0, b20 = ctx.calc_cost_sgm(g["I1"], g["I2"], D, vMax, g["Pd0"], g["dirn"], g["O"], int(g["P1"]), int(g["P2"]),
+                                         opts=api.epi_opts(paths=8))
+    assert not conf0.any() and not b20.any()
+    # stage entry points on the committed random label map
+    H, W = g["D1"].shape
+    D1 = _t(g["D1"].astype(np.int32)[None])
+    cf = torch.empty((1, H, W), dtype=torch.uint8, device="cuda")
+    d2 = torch.empty((1, H, W), dtype=torch.int32, device="cuda")
+    ctx.forward_backward_check_dev(D1, _t(g["Pd0"][None]), _t(g["dirn"][None]), _t(g["O"][None]), vMax, D + 1, cf, d2, thr=int(g["thr_d"]))
+    assert np.array_equal(cf.cpu().numpy()[0], g["conf_d"])
+    assert np.array_equal(d2.cpu().numpy().view(np.uint32)[0], g["bestD2_d"])
+    ctx.convert_vzind_to_disp_dev(D1, _t(g["O"][None]), vMax, D + 1)
+    assert np.array_equal(D1.cpu().numpy().view(np.uint32)[0], g["disp_d"])
+
+
+@pytest.mark.parametrize("W,H,D,thr,bad,vz", [(200, 120, 64, 2, False, 1), (333, 97, 256, 400, False, 1), (64, 40, 16, 100, True, 1),
+                                              (80, 50, 32, 50, False, 0)])
+def test_fb_check_vs_oracle(ctx, oracle, W, H, D, thr, bad, vz):
+    """batched, NaN / out-of-range geometry (x86 conversion semantics), and the non-USE_VZIND form (port only)"""
+    import torch
+    n = 3
+    ps = [synth.epipolar_pair(W, H, D, seed=W + i) for i in range(n)]
+    Pd0 = np.stack([p["Pd0"] for p in ps]); dirn = np.stack([p["dirn"] for p in ps]); O = np.stack([p["O"] for p in ps])
+    if bad:
+        Pd0[0, 0, 3, 5] = np.nan; dirn[1, 1, 7, 7] = 1e300; O[2, 9, 9] = -1e200; Pd0[1, 1, 2, 2] = 3e9; O[0, 11, 3] = np.inf
+    D1 = np.random.default_rng(W).integers(0, D * 256, (n, H, W)).astype(np.uint32)
+    cf = torch.empty((n, H, W), dtype=torch.uint8, device="cuda")
+    d2 = torch.empty((n, H, W), dtype=torch.int32, device="cuda")
+    ctx.forward_backward_check_dev(_t(D1.view(np.int32)), _t(Pd0), _t(dirn), _t(O), ps[0]["vMax"], D + 1, cf, d2, thr=thr, use_vzind=vz)
+    for i in range(n):
+        if vz and oracle.have_ref("epi8fb"):
+            a = oracle.ref_fb_check(D1[i], Pd0[i], dirn[i], O[i], ps[0]["vMax"], D + 1, thr)
+        else:
+            a = oracle.port_fb_check(D1[i], Pd0[i], dirn[i], O[i], ps[0]["vMax"], D + 1, thr, use_vzind=vz)
+        assert np.array_equal(cf.cpu().numpy()[i], a[0]), i
+        assert np.array_equal(d2.cpu().numpy().view(np.uint32)[i], a[1]), i
+    t = _t(D1.view(np.int32))
+    ctx.convert_vzind_to_disp_dev(t, _t(O), ps[0]["vMax"], D + 1)
+    for i in range(n):
+        assert np.array_equal(t.cpu().numpy().view(np.uint32)[i], oracle.port_vz_to_disp(D1[i], O[i], ps[0]["vMax"], D)), i

@@ -31,6 +31,19 @@ def test_port_epi_vs_golden(oracle, name):
     assert np.array_equal(r["Sp"], g["Sp"].astype(np.uint32))
 
 
+def test_port_fb_check_vs_golden(oracle):
+    """forward_backward_check / calc_disp_from_first / convert_vzInd_to_disp (calc_cost_sgm.cpp:414-536)"""
+    g = _g("epi_fb")
+    D, vMax = int(g["D"]), float(g["vMax"])
+    r = oracle.port_epi_fb(g["I1"], g["I2"], D, vMax, g["Pd0"], g["dirn"], g["O"], int(g["P1"]), int(g["P2"]), paths=8, thr=2)
+    for k in ("bestD", "minC", "conf", "bestD2"):
+        assert np.array_equal(r[k], g[k]), k
+    conf, D2 = oracle.port_fb_check(g["D1"], g["Pd0"], g["dirn"], g["O"], vMax, D + 1, thr=int(g["thr_d"]))
+    assert np.array_equal(conf, g["conf_d"]) and np.array_equal(D2, g["bestD2_d"])
+    assert 0 < conf.mean() < 1 and (D2 == 512 << 8).any()                # the case exercises every branch
+    assert np.array_equal(oracle.port_vz_to_disp(g["D1"], g["O"], vMax, D), g["disp_d"])
+
+
 @pytest.mark.parametrize("name", ["pyd_a", "pyd_b", "pyd_c"])
 def test_port_pyd_vs_golden(oracle, name):
     g = _g(name)
@@ -63,6 +76,25 @@ def test_port_pydng_vs_golden(oracle, name):
 def _need_ref(oracle, v):
     if not oracle.have_ref(v):
         pytest.skip("oracle/_ref not built here")
+
+
+@pytest.mark.parametrize("W,H,D,thr,bad", [(64, 40, 16, 2, False), (50, 33, 64, 300, False), (40, 24, 8, 100, True)])
+def test_port_vs_ref_fb_check(oracle, W, H, D, thr, bad):
+    _need_ref(oracle, "epi8fb")
+    p = synth.epipolar_pair(W, H, D, seed=W + 1)
+    Pd0, dirn, O = p["Pd0"].copy(), p["dirn"].copy(), p["O"].copy()
+    if bad:                                                  # NaN / huge geometry: x86 conversions give INT_MIN
+        Pd0[0, 3, 5] = np.nan; dirn[1, 7, 7] = 1e300; O[9, 9] = -1e200; Pd0[1, 2, 2] = 3e9; O[11, 3] = np.inf
+    D1 = np.random.default_rng(W).integers(0, D * 256, (H, W)).astype(np.uint32)
+    a = oracle.ref_fb_check(D1, Pd0, dirn, O, p["vMax"], D + 1, thr)
+    b = oracle.port_fb_check(D1, Pd0, dirn, O, p["vMax"], D + 1, thr)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert np.array_equal(oracle.ref_vz_to_disp(D1, O, p["vMax"], D + 1), oracle.port_vz_to_disp(D1, O, p["vMax"], D))
+    if not bad:
+        r = oracle.ref_epi_fb(p["I1"], p["I2"], D, p["vMax"], Pd0, dirn, O, 6, 64)
+        q = oracle.port_epi_fb(p["I1"], p["I2"], D, p["vMax"], Pd0, dirn, O, 6, 64, paths=8, thr=2)
+        for k in ("bestD", "minC", "conf", "bestD2"):
+            assert np.array_equal(r[k], q[k]), k
 
 
 @pytest.mark.parametrize("W,H,D,P1,P2,paths", [(72, 40, 24, 6, 64, 8), (33, 21, 64, 6, 32, 4), (30, 20, 9, 250, 250, 8)])
