@@ -73,6 +73,25 @@ def _dp(t):
     return C.c_void_p(t.data_ptr())
 
 
+class PydOpts(C.Structure):
+    """constants of the MATLAB pyramid driver (pyramidal_sgm.m:12-22)"""
+    _fields_ = [("numPyd", C.c_int), ("P1", C.c_int), ("P2", C.c_int), ("aggHalfWinSize", C.c_int),
+                ("verSearchHalfWinSize", C.c_int), ("horSearchHalfWinSize", C.c_int), ("enableDiagonal", C.c_int),
+                ("totalPass", C.c_int), ("adaptiveP2", C.c_int)]
+
+
+def pyd_opts(numPyd=5, P1=6, P2=32, agg=2, ver=5, hor=5, diag=1, passes=2, adaptive=0) -> PydOpts:
+    return PydOpts(numPyd, P1, P2, agg, ver, hor, diag, passes, adaptive)
+
+
+def pyramid_dims(W: int, H: int, numPyd: int):
+    ws, hs = (C.c_int * numPyd)(), (C.c_int * numPyd)()
+    rc = lib().fsgm_pyramid_dims(int(W), int(H), int(numPyd), ws, hs)
+    if rc:
+        raise FsgmError(rc, "fsgm_pyramid_dims")
+    return list(ws), list(hs)
+
+
 class NgOpts(C.Structure):
     _fields_ = [("seed", C.c_uint), ("rand_stream", C.c_void_p)]
 
@@ -284,6 +303,34 @@ class Context:
         self._ck(self._l.fsgm_pyd_aggregate_dev(self._h, n, _dp(Cvol), _dp(I1), _dp(preMv), mvW, mvH, W, H, int(rx), int(ry),
                                                 int(sub), int(P1), int(P2), int(diag), int(passes), int(adaptive), _dp(Sp),
                                                 _dp(bestD), _dp(minC), _dp(mvSub)))
+
+    # ------------------------------------------------------------------ pyramid driver (pyramidal_sgm.m)
+    def impyramid_reduce_dev(self, img, out):
+        n, H, W = img.shape
+        self._ck(self._l.fsgm_impyramid_reduce_dev(self._h, n, _dp(img), W, H, _dp(out)))
+
+    def pyramidal_sgm_dev(self, I0, I1, mv, minC, opts=None, mvPyd=None):
+        n, H, W = I0.shape
+        self._ck(self._l.fsgm_pyramidal_sgm_dev(self._h, n, _dp(I0), _dp(I1), W, H, C.byref(opts) if opts is not None else None,
+                                                _dp(mv), _dp(minC), _dp(mvPyd)))
+
+    def pyramidal_sgm(self, I0, I1, opts=None, levels=False):
+        """[mv, minC(, mvPyd)] = pyramidal_sgm(I0, I1, numPyd) on host arrays; mvPyd = list of per-level flows, finest first"""
+        H, W = I0.shape
+        o = opts if opts is not None else pyd_opts()
+        ws, hs = pyramid_dims(W, H, o.numPyd)
+        mv, minC = np.empty((2, H, W), np.float64), np.empty((H, W), np.uint32)
+        flat = np.empty(sum(2 * w * h for w, h in zip(ws, hs)), np.float64) if levels else None
+        self._ck(self._l.fsgm_pyramidal_sgm(self._h, _hp(I0, np.uint8), _hp(I1, np.uint8, (H, W)), W, H, C.byref(o),
+                                            _hp(mv, np.float64), _hp(minC, np.uint32),
+                                            _hp(flat, np.float64) if levels else None))
+        if not levels:
+            return mv, minC
+        out, off = [], 0
+        for w, h in zip(ws, hs):
+            out.append(flat[off:off + 2 * w * h].reshape(2, h, w))
+            off += 2 * w * h
+        return mv, minC, out
 
     # ------------------------------------------------------------------ gateway 3: calc_cost_sgm_ng
     def calc_cost_sgm_ng(self, I1, I2, preMv=None, halfSearchWinSize=1, aggSize=2, subPixelRefine=0, P1=6, P2=32,

@@ -431,7 +431,7 @@ int fsgm_profile_read(fsgm_ctx* c, int stage, double* ms, uint64_t* launches)
 const char* fsgm_stage_name(int stage)
 {
     static const char* names[ST_COUNT] = { "census", "epi_cost", "sweep", "wta", "pyd_cost", "pyd_sweep", "pyd_wta",
-                                           "ng", "pydng_cost", "pydng_sweep", "pydng_wta", "misc", "vsweep" };
+                                           "ng", "pydng_cost", "pydng_sweep", "pydng_wta", "misc", "vsweep", "pyramid", "geometry" };
     return (stage >= 0 && stage < ST_COUNT) ? names[stage] : nullptr;
 }
 int fsgm_stage_count(void) { return ST_COUNT; }

@@ -47,6 +47,30 @@ int pyd_aggregate(fsgm_ctx* c, int n, const uint8_t* C, const uint8_t* I1, const
     return launch_pyd_wta(c, n, L, weights, nd, W, H, g.Sx, g.Sy, g.subpixel, Sp16, bestD, minC, mvSub);
 }
 
+size_t pyd_scratch_bytes(int n, int W, int H, int D)
+{
+    const size_t N = (size_t)W * H;
+    return 2 * align256(n * N * 4) + 9 * align256(n * N * D);
+}
+
+// census -> cost -> sweeps -> WTA for one level; the caller has reserved pyd_scratch_bytes() and holds the arena scope
+int pyd_pipeline(fsgm_ctx* c, int n, const uint8_t* d_I1, const uint8_t* d_I2, int W, int H, const double* d_preMv, int mvW, int mvH,
+                 const PydCfg& g, uint32_t* d_bestD, uint32_t* d_minC, double* d_mvSub)
+{
+    const size_t N = (size_t)W * H, V = N * g.D;
+    ArenaScope scope(c);
+    uint32_t *cen1, *cen2; uint8_t* C;
+    FSGM_TRY(arena_get(c, n * N, &cen1));
+    FSGM_TRY(arena_get(c, n * N, &cen2));
+    FSGM_TRY(arena_get(c, n * V, &C));
+    FSGM_TRY(launch_census(c, n, d_I1, W, H, cen1));
+    FSGM_TRY(launch_census(c, n, d_I2, W, H, cen2));
+    FSGM_TRY(launch_pyd_cost(c, n, cen1, cen2, W, H, d_preMv, mvW, mvH, g.agg, g.rx, g.ry, C));
+    return pyd_aggregate(c, n, C, d_I1, d_preMv, mvW, mvH, W, H, g, nullptr, d_bestD, d_minC, d_mvSub);
+}
+
+constexpr int PYR_MAX_LEVELS = 16;
+
 }  // namespace
 
 extern "C" {
@@ -97,17 +121,8 @@ int fsgm_calc_pyd_cost_sgm_dev(fsgm_ctx* c, int n, const uint8_t* d_I1, const ui
     if (!d_I1 || !d_I2 || !d_preMv || !d_bestD || !d_minC || !d_mvSub) return fail(c, FSGM_ERR_ARG, "null pointer");
     g.subpixel = subPixelRefine; g.P1 = P1; g.P2 = P2; g.diag = enableDiagnalPath != 0; g.adaptive = adpativeP2 != 0;
     FSGM_CUDA(c, cudaSetDevice(c->device));
-    const size_t N = (size_t)W * H, V = N * g.D;
-    FSGM_TRY(arena_reserve(c, 2 * align256(n * N * 4) + 9 * align256(n * V)));
-    ArenaScope scope(c);
-    uint32_t *cen1, *cen2; uint8_t* C;
-    FSGM_TRY(arena_get(c, n * N, &cen1));
-    FSGM_TRY(arena_get(c, n * N, &cen2));
-    FSGM_TRY(arena_get(c, n * V, &C));
-    FSGM_TRY(launch_census(c, n, d_I1, W, H, cen1));
-    FSGM_TRY(launch_census(c, n, d_I2, W, H, cen2));
-    FSGM_TRY(launch_pyd_cost(c, n, cen1, cen2, W, H, d_preMv, mvW, mvH, agg, rx, ry, C));
-    return pyd_aggregate(c, n, C, d_I1, d_preMv, mvW, mvH, W, H, g, nullptr, d_bestD, d_minC, d_mvSub);
+    FSGM_TRY(arena_reserve(c, pyd_scratch_bytes(n, W, H, g.D)));
+    return pyd_pipeline(c, n, d_I1, d_I2, W, H, d_preMv, mvW, mvH, g, d_bestD, d_minC, d_mvSub);
 }
 
 int fsgm_calc_pyd_cost_sgm(fsgm_ctx* c, const uint8_t* I1, const uint8_t* I2, int W, int H,
@@ -139,6 +154,127 @@ int fsgm_calc_pyd_cost_sgm(fsgm_ctx* c, const uint8_t* I1, const uint8_t* I2, in
     FSGM_CUDA(c, cudaMemcpyAsync(bestD, dB, N * 4, cudaMemcpyDeviceToHost, s));
     FSGM_CUDA(c, cudaMemcpyAsync(minC, dM, N * 4, cudaMemcpyDeviceToHost, s));
     FSGM_CUDA(c, cudaMemcpyAsync(mvSub, dS, 2 * N * 8, cudaMemcpyDeviceToHost, s));
+    FSGM_CUDA(c, cudaStreamSynchronize(s));
+    return FSGM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// N1: the pyramid driver (pyramidal_sgm.m:1-77) with every level resident on the device
+// ---------------------------------------------------------------------------------------------------------------------
+void fsgm_pyd_opts_default(fsgm_pyd_opts* o)
+{
+    if (!o) return;
+    o->numPyd = 5; o->P1 = 6; o->P2 = 32; o->aggHalfWinSize = 2; o->verSearchHalfWinSize = 5; o->horSearchHalfWinSize = 5;
+    o->enableDiagonal = 1; o->totalPass = 2; o->adaptiveP2 = 0;
+}
+
+int fsgm_pyramid_dims(int W, int H, int numPyd, int* widths, int* heights)
+{
+    if (W < 1 || H < 1 || numPyd < 1 || numPyd > PYR_MAX_LEVELS || !widths || !heights) return FSGM_ERR_ARG;
+    for (int l = 0; l < numPyd; ++l) {
+        widths[l] = W; heights[l] = H;
+        W = (W + 1) / 2; H = (H + 1) / 2;
+    }
+    return FSGM_OK;
+}
+
+int fsgm_impyramid_reduce_dev(fsgm_ctx* c, int n_images, const uint8_t* d_img, int W, int H, uint8_t* d_out)
+{
+    if (!c) return FSGM_ERR_ARG;
+    if (n_images < 1 || W < 1 || H < 1 || !d_img || !d_out) return fail(c, FSGM_ERR_ARG, "bad argument");
+    FSGM_CUDA(c, cudaSetDevice(c->device));
+    return launch_pyr_reduce(c, n_images, d_img, W, H, d_out);
+}
+
+int fsgm_pyramidal_sgm_dev(fsgm_ctx* c, int n, const uint8_t* d_I0, const uint8_t* d_I1, int W, int H, const fsgm_pyd_opts* opts,
+                           double* d_mv, uint32_t* d_minC, double* d_mvPyd)
+{
+    if (!c) return FSGM_ERR_ARG;
+    fsgm_pyd_opts o;
+    if (opts) o = *opts; else fsgm_pyd_opts_default(&o);
+    if (o.numPyd < 1 || o.numPyd > PYR_MAX_LEVELS) return fail(c, FSGM_ERR_ARG, "numPyd must be in 1..16");
+    if (!d_I0 || !d_I1 || !d_mv || !d_minC) return fail(c, FSGM_ERR_ARG, "null pointer");
+    int Ws[PYR_MAX_LEVELS], Hs[PYR_MAX_LEVELS];
+    if (fsgm_pyramid_dims(W, H, o.numPyd, Ws, Hs) != FSGM_OK) return fail(c, FSGM_ERR_ARG, "bad size");
+    PydCfg g{};
+    FSGM_TRY(pyd_check(c, n, W, H, W, H, o.horSearchHalfWinSize, o.verSearchHalfWinSize, o.aggHalfWinSize, o.totalPass, &g));
+    g.P1 = o.P1; g.P2 = o.P2; g.diag = o.enableDiagonal != 0; g.adaptive = o.adaptiveP2 != 0;
+    FSGM_CUDA(c, cudaSetDevice(c->device));
+    const int L = o.numPyd;
+    const size_t N0 = (size_t)W * H;
+    // driver-owned buffers: both image pyramids above level 0, labels + mvSub + mvCur at the largest level, and the two
+    // prior-flow maps (current and next) at up to (W+1) x (H+1)
+    size_t own = 0;
+    for (int l = 1; l < L; ++l) own += 2 * align256((size_t)n * Ws[l] * Hs[l]);
+    own += align256(n * N0 * 4) + 2 * align256(n * 2 * N0 * 8) + 2 * align256((size_t)n * 2 * (W + 1) * (H + 1) * 8);
+    FSGM_TRY(arena_reserve(c, own + pyd_scratch_bytes(n, W, H, g.D)));
+    ArenaScope scope(c);
+    const uint8_t *I0l[PYR_MAX_LEVELS], *I1l[PYR_MAX_LEVELS];
+    I0l[0] = d_I0; I1l[0] = d_I1;
+    for (int l = 1; l < L; ++l) {                                        // pyramidal_sgm.m:27-30
+        uint8_t *a, *b;
+        FSGM_TRY(arena_get(c, (size_t)n * Ws[l] * Hs[l], &a));
+        FSGM_TRY(arena_get(c, (size_t)n * Ws[l] * Hs[l], &b));
+        FSGM_TRY(launch_pyr_reduce(c, n, I0l[l - 1], Ws[l - 1], Hs[l - 1], a));
+        FSGM_TRY(launch_pyr_reduce(c, n, I1l[l - 1], Ws[l - 1], Hs[l - 1], b));
+        I0l[l] = a; I1l[l] = b;
+    }
+    uint32_t* label; double *mvSub, *mvCur, *pre[2];
+    FSGM_TRY(arena_get(c, n * N0, &label));
+    FSGM_TRY(arena_get(c, n * 2 * N0, &mvSub));
+    FSGM_TRY(arena_get(c, n * 2 * N0, &mvCur));
+    FSGM_TRY(arena_get(c, (size_t)n * 2 * (W + 1) * (H + 1), &pre[0]));
+    FSGM_TRY(arena_get(c, (size_t)n * 2 * (W + 1) * (H + 1), &pre[1]));
+    int mvW = Ws[L - 1], mvH = Hs[L - 1];
+    FSGM_CUDA(c, cudaMemsetAsync(pre[0], 0, (size_t)n * 2 * mvW * mvH * 8, c->stream));   // :33 zero prior at the coarsest level
+    size_t pyd_off = 0;
+    for (int l = 0; l < L; ++l) pyd_off += (size_t)n * 2 * Ws[l] * Hs[l];                   // d_mvPyd is finest-first
+    for (int l = L - 1, k = 0; l >= 0; --l, k ^= 1) {                                        // :36-75
+        const int Wl = Ws[l], Hl = Hs[l];
+        g.subpixel = l == 0;                                                                 // :48
+        FSGM_TRY(pyd_pipeline(c, n, I0l[l], I1l[l], Wl, Hl, pre[k], mvW, mvH, g, label, d_minC, mvSub));
+        double* out = l == 0 ? d_mv : mvCur;
+        FSGM_TRY(launch_pyr_label_to_mv(c, n, label, pre[k], mvW, mvH, mvSub, Wl, Hl, g.rx, g.ry, out));   // :57-64
+        pyd_off -= (size_t)n * 2 * Wl * Hl;
+        if (d_mvPyd)
+            FSGM_CUDA(c, cudaMemcpyAsync(d_mvPyd + pyd_off, out, (size_t)n * 2 * Wl * Hl * 8, cudaMemcpyDeviceToDevice, c->stream));
+        if (l > 0) {                                                                         // :72
+            FSGM_TRY(launch_pyr_upsample2(c, n, out, Wl, Hl, pre[k ^ 1]));
+            mvW = 2 * Wl; mvH = 2 * Hl;
+        }
+    }
+    return FSGM_OK;
+}
+
+int fsgm_pyramidal_sgm(fsgm_ctx* c, const uint8_t* I0, const uint8_t* I1, int W, int H, const fsgm_pyd_opts* opts,
+                       double* mv, uint32_t* minC, double* mvPyd)
+{
+    if (!c) return FSGM_ERR_ARG;
+    if (!I0 || !I1 || !mv || !minC || W < 1 || H < 1) return fail(c, FSGM_ERR_ARG, "bad argument");
+    fsgm_pyd_opts o;
+    if (opts) o = *opts; else fsgm_pyd_opts_default(&o);
+    int Ws[PYR_MAX_LEVELS], Hs[PYR_MAX_LEVELS];
+    if (fsgm_pyramid_dims(W, H, o.numPyd, Ws, Hs) != FSGM_OK) return fail(c, FSGM_ERR_ARG, "numPyd must be in 1..16");
+    FSGM_CUDA(c, cudaSetDevice(c->device));
+    FSGM_TRY(fsgm_synchronize(c));
+    const size_t N = (size_t)W * H;
+    size_t all = 0;
+    for (int l = 0; l < o.numPyd; ++l) all += (size_t)2 * Ws[l] * Hs[l];
+    FSGM_TRY(pipe_reserve(c, 2 * align256(N) + align256(2 * N * 8) + align256(N * 4) + align256(all * 8)));
+    char* base = c->pipe.buf[0];
+    uint8_t* dI0 = (uint8_t*)base;  base += align256(N);
+    uint8_t* dI1 = (uint8_t*)base;  base += align256(N);
+    double* dMv = (double*)base;    base += align256(2 * N * 8);
+    uint32_t* dM = (uint32_t*)base; base += align256(N * 4);
+    double* dAll = (double*)base;
+    cudaStream_t s = c->stream;
+    FSGM_CUDA(c, cudaMemcpyAsync(dI0, I0, N, cudaMemcpyHostToDevice, s));
+    FSGM_CUDA(c, cudaMemcpyAsync(dI1, I1, N, cudaMemcpyHostToDevice, s));
+    int rc = fsgm_pyramidal_sgm_dev(c, 1, dI0, dI1, W, H, &o, dMv, dM, mvPyd ? dAll : nullptr);
+    if (rc != FSGM_OK) { cudaStreamSynchronize(s); return rc; }
+    FSGM_CUDA(c, cudaMemcpyAsync(mv, dMv, 2 * N * 8, cudaMemcpyDeviceToHost, s));
+    FSGM_CUDA(c, cudaMemcpyAsync(minC, dM, N * 4, cudaMemcpyDeviceToHost, s));
+    if (mvPyd) FSGM_CUDA(c, cudaMemcpyAsync(mvPyd, dAll, all * 8, cudaMemcpyDeviceToHost, s));
     FSGM_CUDA(c, cudaStreamSynchronize(s));
     return FSGM_OK;
 }

@@ -10,7 +10,7 @@
 namespace fsgm {
 // pipeline stages, for the optional per-stage CUDA-event timing (fsgm_profile_*)
 enum Stage { ST_CENSUS = 0, ST_EPI_COST, ST_SWEEP, ST_WTA, ST_PYD_COST, ST_PYD_SWEEP, ST_PYD_WTA,
-             ST_NG, ST_PYDNG_COST, ST_PYDNG_SWEEP, ST_PYDNG_WTA, ST_MISC, ST_VSWEEP, ST_COUNT };
+             ST_NG, ST_PYDNG_COST, ST_PYDNG_SWEEP, ST_PYDNG_WTA, ST_MISC, ST_VSWEEP, ST_PYRAMID, ST_GEOMETRY, ST_COUNT };
 struct StageTimer { cudaEvent_t a, b; int stage; };
 // double-buffered device staging + copy streams for the host-pointer gateways
 struct HostPipe {
@@ -138,5 +138,10 @@ int launch_pyd_sweeps(fsgm_ctx* c, int n, const uint8_t* C, const uint8_t* I1, c
 int launch_pyd_wta(fsgm_ctx* c, int n, uint8_t* const* Lvols, const int* weights, int n_dirs, int W, int H, int Sx, int Sy,
                    int subpixel, uint16_t* Sp16, uint32_t* bestD, uint32_t* minC, double* mvSub);
 
+// ---- pyramid driver (pyramid.cu): impyramid 'reduce', label -> mv, 2 x nearest upsample ------------------------
+int launch_pyr_reduce(fsgm_ctx* c, int n_images, const uint8_t* in, int W, int H, uint8_t* out);
+int launch_pyr_label_to_mv(fsgm_ctx* c, int n, const uint32_t* label, const double* preMv, int mvW, int mvH, const double* mvSub,
+                           int W, int H, int rx, int ry, double* mv);
+int launch_pyr_upsample2(fsgm_ctx* c, int n, const double* mv, int W, int H, double* out);
 
 }  // namespace fsgm

@@ -184,6 +184,36 @@ FSGM_API int fsgm_pyd_aggregate_dev(fsgm_ctx* ctx, int n_pairs, const uint8_t* d
                            int subPixelRefine, int P1, int P2, int enableDiagnalPath, int totalPass, int adpativeP2,
                            uint16_t* d_Sp /* may be NULL */, uint32_t* d_bestD, uint32_t* d_minC, double* d_mvSub);
 
+/* ---- pyramid driver: the MATLAB loop around gateway 2 (pyramidal_sgm.m:1-77), every level resident on the device ----------
+ * [mvCurLevel, mvPyd, minC] = pyramidal_sgm(I0, I1, numPyd)
+ * Builds both image pyramids with impyramid(.,'reduce') (:28-29), then from the coarsest level down (:36-75): calc_pyd_cost_sgm
+ * with the previous level's flow as prior (zeros at the top, :33), subpixel refinement only at the finest level (:48),
+ * label -> motion vector (:57-64), and 2*imresize(mv, 2, 'nearest') as the next prior (:72; its size 2*ceil(n/2) >= n is the
+ * reason preMv has its own stride).  impyramid belongs to MATLAB's Image Processing Toolbox, not to the reference tree: its
+ * published algorithm is restated in csrc/pyramid.cu (5-tap [1 4 6 4 1]/16, ceil(n/2), symmetric border, uint8 rounding after
+ * each of the two passes).  The struct carries the constants the script hard-codes (:14-22). */
+typedef struct fsgm_pyd_opts {
+    int numPyd;                  /* pyramidal_sgm.m:12  5  (1..16) */
+    int P1, P2;                  /* :14-15  6, 32 */
+    int aggHalfWinSize;          /* :16  2 */
+    int verSearchHalfWinSize;    /* :17  5 */
+    int horSearchHalfWinSize;    /* :18  5 */
+    int enableDiagonal;          /* :19  1 */
+    int totalPass;               /* :20  2 */
+    int adaptiveP2;              /* :21  0 */
+} fsgm_pyd_opts;
+FSGM_API void fsgm_pyd_opts_default(fsgm_pyd_opts* o);
+/* level sizes, finest first: widths[0] = width, widths[l] = ceil(widths[l-1] / 2) */
+FSGM_API int fsgm_pyramid_dims(int width, int height, int numPyd, int* widths, int* heights);
+/* impyramid(img, 'reduce') on n_images u8 images: d_out is u8 [n_images][ceil(H/2)][ceil(W/2)] */
+FSGM_API int fsgm_impyramid_reduce_dev(fsgm_ctx* ctx, int n_images, const uint8_t* d_img, int width, int height, uint8_t* d_out);
+/* mv f64 [n_pairs][2][H][W] (plane 0 = x, 1 = y) and minC u32 [n_pairs][H][W] of the finest level; mvPyd (optional, may be NULL)
+ * receives every level's flow back to back, finest first, level l as f64 [n_pairs][2][Hl][Wl]. */
+FSGM_API int fsgm_pyramidal_sgm_dev(fsgm_ctx* ctx, int n_pairs, const uint8_t* d_I0, const uint8_t* d_I1, int width, int height,
+                           const fsgm_pyd_opts* opts, double* d_mv, uint32_t* d_minC, double* d_mvPyd);
+FSGM_API int fsgm_pyramidal_sgm(fsgm_ctx* ctx, const uint8_t* I0, const uint8_t* I1, int width, int height,
+                           const fsgm_pyd_opts* opts, double* mv, uint32_t* minC, double* mvPyd);
+
 /* ---- gateway 3: calc_cost_sgm_ng (calc_cost_sgm_ng.cpp:484-527) ----------------------------------
  * [minC, flow] = calc_cost_sgm_ng(I1, I2, preMv, halfSearchWinSize, aggSize, subPixelRefine, P1, P2)
  * The reference reads and ignores preMv, halfSearchWinSize, aggSize and subPixelRefine (:497-503); they are accepted

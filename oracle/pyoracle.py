@@ -21,7 +21,11 @@ _u8p, _u32p, _i32p, _f64p = (C.POINTER(t) for t in (C.c_uint8, C.c_uint32, C.c_i
 
 
 def _ptr(a, ty):
-    return a.ctypes.data_as(ty) if a is not None else ty()
+    if a is None:
+        return ty()
+    if not a.flags["C_CONTIGUOUS"]:
+        raise TypeError("oracle arrays must be C-contiguous")
+    return a.ctypes.data_as(ty)
 
 
 def build(port: bool = True, ref: bool = True) -> None:

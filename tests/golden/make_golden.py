@@ -58,6 +58,12 @@ def main():
         r = po.ref_pyd(fp["I1"], fp["I2"], mv, rx, ry, 2, sub, 6, 32, diag, passes, adp)
         save(name, I1=fp["I1"], I2=fp["I2"], preMv=mv, rx=rx, ry=ry, agg=2, sub=sub, P1=6, P2=32, diag=diag, passes=passes,
              adaptive=adp, C=r["C"], Sp=r["Sp"].astype(np.uint16), bestD=r["bestD"], minC=r["minC"], mvSub=r["mvSub"])
+    # ---- pyramid driver (pyramidal_sgm.m): per-level solver = the reference build; impyramid restated (oracle/pyramid_oracle.py) ----
+    from oracle import pyramid_oracle as pyo
+    fpp = synth.flow_pair(90, 58, seed=21, umax=9, vmax=5)
+    mv, mc, lv = pyo.pyramidal_sgm(fpp["I1"], fpp["I2"], lambda *a: po.ref_pyd(*a, stages=False), numPyd=3, ver=2, hor=3)
+    save("pyramid_a", I0=fpp["I1"], I1=fpp["I2"], numPyd=3, ver=2, hor=3, mv=mv, minC=mc,
+         **{f"mv_l{i}": m for i, m in enumerate(lv)}, **{f"img_l{i}": m for i, m in enumerate(pyo.pyramid(fpp["I1"], 3))})
     # ---- neighbour guided (glibc rand(), srand(1)) ---------------------------------------------------------
     fq = synth.flow_pair(28, 20, seed=9, umax=3, vmax=2)
     r = po.ref_ng(fq["I1"], fq["I2"], 6, 32, seed=1, stages=True)
