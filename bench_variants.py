@@ -60,6 +60,42 @@ def main():
         tot_ms += ms / n; evals += w * h * 121
     out["pyd_3level_pairs_per_s"] = 1e3 / tot_ms
     out["pyd_3level_gde_per_s"] = evals / (tot_ms * 1e-3) / 1e9
+    # ---- N1: the whole pyramid loop on the device (pyramidal_sgm.m), 3 and 5 levels, r = 5 ---------------------------------
+    n = 4 if args.quick else 8
+    I0 = t(np.stack([fp["I1"]] * n)); I1b = t(np.stack([fp["I2"]] * n))
+    mvo = torch.empty((n, 2, H, W), dtype=torch.float64, device="cuda")
+    mCo = torch.empty((n, H, W), dtype=torch.int32, device="cuda")
+    for L in (3, 5):
+        o = api.pyd_opts(numPyd=L)
+        ms = timed(lambda: ctx.pyramidal_sgm_dev(I0, I1b, mvo, mCo, opts=o), 3)
+        out[f"pyramid_driver_{L}level_pairs_per_s"] = n / (ms * 1e-3)
+    del I0, I1b, mvo, mCo
+    # ---- N2: F/H/epipole -> flow through the host-image call (2 B/px up, 20 B/px back) vs gateway 1 (42 up, 8 back) ---------
+    if not args.quick:
+        npairs, D = 60, 256
+        ep = synth.epipolar_pair(W, H, D, seed=1)
+        cam = synth.epipolar_camera(W, H, seed=2, rot_deg=0.05)
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        hI0 = pin(np.stack([ep["I1"]] * npairs)); hI1 = pin(np.stack([ep["I2"]] * npairs))
+        hflow = torch.empty((npairs, 2, H, W), dtype=torch.float64).pin_memory()
+        hmin = torch.empty((npairs, H, W), dtype=torch.int32).pin_memory()
+        Fs, Hs, es, ds = [cam["F"]] * npairs, [cam["H"]] * npairs, [cam["epi"]] * npairs, [cam["direction"]] * npairs
+        outs = (hflow.numpy(), hmin.numpy().view(np.uint32))
+        o8 = api.epi_opts(paths=8)
+        call = lambda: ctx.epipolar_sgm_of_batch(hI0.numpy(), hI1.numpy(), Fs, Hs, es, ds, D, 0.3, 6, 64, opts=o8, out=outs, asynchronous=True)
+        for _ in range(3):
+            call()
+        ctx.synchronize()
+        t0 = time.perf_counter()
+        reps = 8
+        for _ in range(reps):
+            call()
+        ctx.synchronize()
+        dt = time.perf_counter() - t0
+        out["epipolar_sgm_of_e2e_pairs_per_s"] = npairs * reps / dt
+        out["epipolar_sgm_of_h2d_bytes_per_pair"] = 2 * W * H
+        out["epipolar_sgm_of_d2h_bytes_per_pair"] = 20 * W * H
+        del hI0, hI1, hflow, hmin
     # ---- pyd_ng r = 1 (D = 81 candidates), aggSize 5 -----------------------------------------------------------
     n = 4 if args.quick else 8
     I1 = t(np.stack([fp["I1"]] * n)); I2 = t(np.stack([fp["I2"]] * n))

@@ -304,6 +304,50 @@ class Context:
                                                 int(sub), int(P1), int(P2), int(diag), int(passes), int(adaptive), _dp(Sp),
                                                 _dp(bestD), _dp(minC), _dp(mvSub)))
 
+    # ------------------------------------------------------------------ dense epipolar prologue / epilogue
+    @staticmethod
+    def _geo_args(F, Hm, epi, direction, n):
+        F = np.ascontiguousarray(np.asarray(F, np.float64).reshape(n, 9))
+        Hm = np.ascontiguousarray(np.asarray(Hm, np.float64).reshape(n, 9))
+        epi = np.ascontiguousarray(np.asarray(epi, np.float64).reshape(n, 2))
+        dr = np.ascontiguousarray(np.asarray(direction, np.int32).reshape(n))
+        return F, Hm, epi, dr
+
+    def epipolar_geometry_dev(self, F, Hm, epi, direction, Pd0, dirn, O, Rflow=None):
+        """epipolar_geometry.m:104-119 + rotation_motion.m on the device; F, Hm, epi, direction are host arrays"""
+        n, H, W = O.shape
+        F, Hm, epi, dr = self._geo_args(F, Hm, epi, direction, n)
+        self._ck(self._l.fsgm_epipolar_geometry_dev(self._h, n, _hp(F, np.float64), _hp(Hm, np.float64), _hp(epi, np.float64),
+                                                    _hp(dr, np.int32), W, H, _dp(Pd0), _dp(dirn), _dp(O), _dp(Rflow)))
+
+    def epipolar_flow_dev(self, bestD, dirn, Rflow, flow):
+        n, H, W = bestD.shape
+        self._ck(self._l.fsgm_epipolar_flow_dev(self._h, n, _dp(bestD), _dp(dirn), _dp(Rflow), W, H, _dp(flow)))
+
+    def epipolar_sgm_of_dev(self, I0, I1, F, Hm, epi, direction, dMax, vMax, P1, P2, work, flow, minC, opts=None):
+        n, H, W = I0.shape
+        F, Hm, epi, dr = self._geo_args(F, Hm, epi, direction, n)
+        self._l.fsgm_epipolar_sgm_of_work_bytes.restype = C.c_size_t
+        if work.numel() * work.element_size() < self._l.fsgm_epipolar_sgm_of_work_bytes(n, W, H):
+            raise ValueError("work buffer too small")
+        self._ck(self._l.fsgm_epipolar_sgm_of_dev(self._h, n, _dp(I0), _dp(I1), W, H, _hp(F, np.float64), _hp(Hm, np.float64),
+                                                  _hp(epi, np.float64), _hp(dr, np.int32), int(dMax), C.c_double(vMax), int(P1), int(P2),
+                                                  C.byref(opts) if opts is not None else None, _dp(work), _dp(flow), _dp(minC)))
+
+    def epipolar_sgm_of_batch(self, I0, I1, F, Hm, epi, direction, dMax, vMax, P1, P2, opts=None, out=None, asynchronous=False):
+        """[flow, minC] = epipolar_sgm_of(...) from F, H, epipole on host images (epipolar_sgm_of.m:23-51 after the geometry fit)"""
+        n, H, W = I0.shape
+        F, Hm, epi, dr = self._geo_args(F, Hm, epi, direction, n)
+        flow, minC = out if out is not None else (np.empty((n, 2, H, W), np.float64), np.empty((n, H, W), np.uint32))
+        self._keep = (F, Hm, epi, dr)                    # host matrices are consumed at enqueue time, images are not
+        self._ck(self._l.fsgm_epipolar_sgm_of_batch_async(
+            self._h, n, _hp(I0, np.uint8), _hp(I1, np.uint8, (n, H, W)), W, H, _hp(F, np.float64), _hp(Hm, np.float64),
+            _hp(epi, np.float64), _hp(dr, np.int32), int(dMax), C.c_double(vMax), int(P1), int(P2),
+            C.byref(opts) if opts is not None else None, _hp(flow, np.float64), _hp(minC, np.uint32)))
+        if not asynchronous:
+            self.synchronize()
+        return flow, minC
+
     # ------------------------------------------------------------------ pyramid driver (pyramidal_sgm.m)
     def impyramid_reduce_dev(self, img, out):
         n, H, W = img.shape

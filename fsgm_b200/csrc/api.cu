@@ -363,6 +363,7 @@ void fsgm_destroy(fsgm_ctx* c)
     cudaStreamSynchronize(c->stream);
     cudaDeviceSynchronize();
     if (c->arena) cudaFree(c->arena);
+    if (c->geo_params) cudaFree(c->geo_params);
     for (auto& t : c->timers) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     for (auto e : c->event_pool) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) {
@@ -757,6 +758,114 @@ int fsgm_calc_cost_sgm(fsgm_ctx* c, const uint8_t* I1, const uint8_t* I2, int W,
     if (conf) std::memset(conf, 0, (size_t)W * H);
     if (bestD2) std::memset(bestD2, 0, (size_t)W * H * sizeof(uint32_t));
     return FSGM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// N2: dense epipolar prologue / epilogue (rotation_motion.m, epipolar_geometry.m:104-119, epipolar_sgm_of.m:46-51)
+// ---------------------------------------------------------------------------------------------
+int fsgm_epipolar_geometry_dev(fsgm_ctx* c, int n, const double* F, const double* Hm, const double* epipole, const int* direction,
+                               int W, int H, double* d_Pd0, double* d_dir, double* d_O, double* d_Rflow)
+{
+    FSGM_TRY(check_dims(c, n, W, H, 1));
+    if (!F || !Hm || !epipole || !d_Pd0 || !d_dir || !d_O) return fail(c, FSGM_ERR_ARG, "null pointer");
+    FSGM_CUDA(c, cudaSetDevice(c->device));
+    return launch_geo_prologue(c, n, F, Hm, epipole, direction, W, H, d_Pd0, d_dir, d_O, d_Rflow);
+}
+
+int fsgm_epipolar_flow_dev(fsgm_ctx* c, int n, const uint32_t* d_bestD, const double* d_dir, const double* d_Rflow, int W, int H,
+                           double* d_flow)
+{
+    FSGM_TRY(check_dims(c, n, W, H, 1));
+    if (!d_bestD || !d_dir || !d_Rflow || !d_flow) return fail(c, FSGM_ERR_ARG, "null pointer");
+    FSGM_CUDA(c, cudaSetDevice(c->device));
+    return launch_geo_epilogue(c, n, d_bestD, d_dir, d_Rflow, W, H, d_flow);
+}
+
+// d_work: 60 bytes per pixel and pair of caller-provided scratch (Pd0 16, direction 16, offset 8, Rflow 16, bestD 4)
+int fsgm_epipolar_sgm_of_dev(fsgm_ctx* c, int n, const uint8_t* d_I0, const uint8_t* d_I1, int W, int H,
+                             const double* F, const double* Hm, const double* epipole, const int* direction,
+                             int D, double vMax, int P1, int P2, const fsgm_epi_opts* opts, void* d_work, double* d_flow, uint32_t* d_minC)
+{
+    FSGM_TRY(check_dims(c, n, W, H, D));
+    if (!d_I0 || !d_I1 || !F || !Hm || !epipole || !d_work || !d_flow || !d_minC) return fail(c, FSGM_ERR_ARG, "null pointer");
+    fsgm_epi_opts o;
+    FSGM_TRY(check_opts(c, opts, &o));
+    if (!o.vz_to_disp) return fail(c, FSGM_ERR_ARG, "epipolar_sgm_of needs pixel disparities (opts.vz_to_disp = 1)");
+    FSGM_CUDA(c, cudaSetDevice(c->device));
+    const size_t N = (size_t)W * H;
+    char* base = static_cast<char*>(d_work);
+    double* Pd0 = reinterpret_cast<double*>(base);   base += (size_t)n * 2 * N * 8;
+    double* dirn = reinterpret_cast<double*>(base);  base += (size_t)n * 2 * N * 8;
+    double* Rf = reinterpret_cast<double*>(base);    base += (size_t)n * 2 * N * 8;
+    double* O = reinterpret_cast<double*>(base);     base += (size_t)n * N * 8;
+    uint32_t* best = reinterpret_cast<uint32_t*>(base);
+    FSGM_TRY(launch_geo_prologue(c, n, F, Hm, epipole, direction, W, H, Pd0, dirn, O, Rf));
+    FSGM_TRY(fsgm_calc_cost_sgm_dev(c, n, d_I0, d_I1, W, H, D, vMax, Pd0, dirn, O, P1, P2, &o, best, d_minC));
+    return launch_geo_epilogue(c, n, best, dirn, Rf, W, H, d_flow);
+}
+
+size_t fsgm_epipolar_sgm_of_work_bytes(int n_pairs, int W, int H) { return (size_t)n_pairs * W * H * 60; }
+
+// Host-pointer form, enqueue-only like fsgm_calc_cost_sgm_batch_async: 2 bytes per pixel go up, 20 come back.
+int fsgm_epipolar_sgm_of_batch_async(fsgm_ctx* c, int n, const uint8_t* I0, const uint8_t* I1, int W, int H,
+                                     const double* F, const double* Hm, const double* epipole, const int* direction,
+                                     int D, double vMax, int P1, int P2, const fsgm_epi_opts* opts, double* flow, uint32_t* minC)
+{
+    FSGM_TRY(check_dims(c, n, W, H, D));
+    fsgm_epi_opts o;
+    FSGM_TRY(check_opts(c, opts, &o));
+    if (!I0 || !I1 || !F || !Hm || !epipole || !flow || !minC) return fail(c, FSGM_ERR_ARG, "null pointer");
+    FSGM_CUDA(c, cudaSetDevice(c->device));
+    const size_t N = (size_t)W * H;
+    const size_t per_pair = 2 * align256(N) + 60 * N + 256 + align256(2 * N * 8) + align256(N * 4);
+    int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n, (size_t(96) << 20) / per_pair + 1));
+    {
+        const int cs = fast_path_cluster(c, W, D, P1, P2, 24, o);
+        if (cs) {
+            fast_pairs(c, n, cs, D, W, o.paths == 8 ? 3 : 1);
+            chunk = std::min(n, std::max(chunk, (c->no_overlap ? 1 : 2) * c->clusters_max));
+        }
+    }
+    FSGM_TRY(pipe_reserve(c, (size_t)chunk * per_pair));
+    HostPipe& p = c->pipe;
+    int rc = FSGM_OK;
+    for (int i0 = 0; i0 < n && rc == FSGM_OK; i0 += chunk, ++p.turn) {
+        const int m = std::min(chunk, n - i0), slot = p.turn & 1;
+        char* base = p.buf[slot];
+        uint8_t* dI0 = reinterpret_cast<uint8_t*>(base);   base += align256(m * N);
+        uint8_t* dI1 = reinterpret_cast<uint8_t*>(base);   base += align256(m * N);
+        void* work = base;                                 base += align256(m * N * 60);
+        double* dFlow = reinterpret_cast<double*>(base);   base += align256(m * 2 * N * 8);
+        uint32_t* dMin = reinterpret_cast<uint32_t*>(base);
+        if (p.used[slot]) cudaStreamWaitEvent(p.h2d, p.out_ready[slot], 0);
+        if (cudaMemcpyAsync(dI0, I0 + i0 * N, m * N, cudaMemcpyHostToDevice, p.h2d) ||
+            cudaMemcpyAsync(dI1, I1 + i0 * N, m * N, cudaMemcpyHostToDevice, p.h2d) ||
+            cudaEventRecord(p.in_ready[slot], p.h2d) || cudaStreamWaitEvent(c->stream, p.in_ready[slot], 0)) {
+            rc = fail(c, FSGM_ERR_CUDA, "H2D copy", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        // the slot's scratch is rewritten by this chunk's kernels: they must not start before the slot's previous outputs left
+        if (p.used[slot]) cudaStreamWaitEvent(c->stream, p.out_ready[slot], 0);
+        rc = fsgm_epipolar_sgm_of_dev(c, m, dI0, dI1, W, H, F + (size_t)i0 * 9, Hm + (size_t)i0 * 9, epipole + (size_t)i0 * 2,
+                                      direction ? direction + i0 : nullptr, D, vMax, P1, P2, &o, work, dFlow, dMin);
+        if (rc != FSGM_OK) break;
+        if (cudaEventRecord(p.done[slot], c->stream) || cudaStreamWaitEvent(p.d2h, p.done[slot], 0) ||
+            cudaMemcpyAsync(flow + (size_t)i0 * 2 * N, dFlow, m * 2 * N * 8, cudaMemcpyDeviceToHost, p.d2h) ||
+            cudaMemcpyAsync(minC + i0 * N, dMin, m * N * 4, cudaMemcpyDeviceToHost, p.d2h) ||
+            cudaEventRecord(p.out_ready[slot], p.d2h))
+            rc = fail(c, FSGM_ERR_CUDA, "D2H copy", cudaGetErrorString(cudaGetLastError()));
+        p.used[slot] = 1;
+    }
+    if (rc != FSGM_OK) { cudaStreamSynchronize(p.d2h); cudaStreamSynchronize(c->stream); cudaStreamSynchronize(p.h2d); }
+    return rc;
+}
+
+int fsgm_epipolar_sgm_of(fsgm_ctx* c, const uint8_t* I0, const uint8_t* I1, int W, int H, const double* F, const double* Hm,
+                         const double* epipole, int direction, int D, double vMax, int P1, int P2, const fsgm_epi_opts* opts,
+                         double* flow, uint32_t* minC)
+{
+    FSGM_TRY(fsgm_epipolar_sgm_of_batch_async(c, 1, I0, I1, W, H, F, Hm, epipole, &direction, D, vMax, P1, P2, opts, flow, minC));
+    return fsgm_synchronize(c);
 }
 
 }  // extern "C"

@@ -47,6 +47,8 @@ struct fsgm_ctx {
     double stage_ms[fsgm::ST_COUNT] = {};
     uint64_t stage_launches[fsgm::ST_COUNT] = {};
     fsgm::HostPipe pipe;
+    void* geo_params = nullptr;             // per-pair F, H, epipole, direction of the dense-geometry prologue (geometry.cu)
+    size_t geo_cap = 0;
 };
 
 namespace fsgm {
@@ -137,6 +139,11 @@ int launch_pyd_sweeps(fsgm_ctx* c, int n, const uint8_t* C, const uint8_t* I1, c
                       int W, int H, int Sx, int Sy, int P1, int P2, int adaptive, const int* dirs, int n_dirs, uint8_t* const* Lvols);
 int launch_pyd_wta(fsgm_ctx* c, int n, uint8_t* const* Lvols, const int* weights, int n_dirs, int W, int H, int Sx, int Sy,
                    int subpixel, uint16_t* Sp16, uint32_t* bestD, uint32_t* minC, double* mvSub);
+
+// ---- dense epipolar prologue / epilogue (geometry.cu): F, H, epipole -> Pd0, direction, offset, Rflow; labels -> flow ------
+int launch_geo_prologue(fsgm_ctx* c, int n, const double* F, const double* Hm, const double* epi, const int* direction, int W, int H,
+                        double* Pd0, double* dirn, double* O, double* Rflow);
+int launch_geo_epilogue(fsgm_ctx* c, int n, const uint32_t* bestD, const double* dirn, const double* Rflow, int W, int H, double* flow);
 
 // ---- pyramid driver (pyramid.cu): impyramid 'reduce', label -> mv, 2 x nearest upsample ------------------------
 int launch_pyr_reduce(fsgm_ctx* c, int n_images, const uint8_t* in, int W, int H, uint8_t* out);

@@ -107,3 +107,26 @@ def upsample_mv(mv: np.ndarray, Hn: int, Wn: int) -> np.ndarray:
     out = np.zeros((2, max(Hn, up.shape[1]), max(Wn, up.shape[2])), np.float64)
     out[:, :up.shape[1], :up.shape[2]] = up
     return np.ascontiguousarray(out)
+
+
+def epipolar_camera(W: int, H: int, seed: int = 1, rot_deg: float = 0.4):
+    """Two-view geometry for the dense prologue: pinhole K, a small rotation R and a mostly-forward
+    translation t.  Returns dict(F [9], H [9] = K R K^-1 (row-major), epi [2] (1-based pixel position of the epipole in
+    image 2, as MATLAB's epi(1:2)), direction)."""
+    rng = np.random.default_rng(seed)
+    f = 0.9 * W
+    K = np.array([[f, 0, W / 2 + 0.37], [0, f, H / 2 + 0.21], [0, 0, 1.0]])
+    a = np.deg2rad(rot_deg) * rng.uniform(-1, 1, 3)
+    Rx = np.array([[1, 0, 0], [0, np.cos(a[0]), -np.sin(a[0])], [0, np.sin(a[0]), np.cos(a[0])]])
+    Ry = np.array([[np.cos(a[1]), 0, np.sin(a[1])], [0, 1, 0], [-np.sin(a[1]), 0, np.cos(a[1])]])
+    Rz = np.array([[np.cos(a[2]), -np.sin(a[2]), 0], [np.sin(a[2]), np.cos(a[2]), 0], [0, 0, 1]])
+    R = Rz @ Ry @ Rx
+    t = np.array([0.03 * rng.uniform(-1, 1), 0.02 * rng.uniform(-1, 1), 1.0])
+    tx = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]])
+    Ki = np.linalg.inv(K)
+    F = Ki.T @ tx @ R @ Ki
+    F = F / np.abs(F).max()
+    Hm = K @ R @ Ki
+    e = K @ t
+    epi = np.array([e[0] / e[2] + 1.0, e[1] / e[2] + 1.0])
+    return dict(F=np.ascontiguousarray(F.reshape(9)), H=np.ascontiguousarray(Hm.reshape(9)), epi=epi, direction=int(seed % 2))

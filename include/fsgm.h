@@ -184,6 +184,36 @@ FSGM_API int fsgm_pyd_aggregate_dev(fsgm_ctx* ctx, int n_pairs, const uint8_t* d
                            int subPixelRefine, int P1, int P2, int enableDiagnalPath, int totalPass, int adpativeP2,
                            uint16_t* d_Sp /* may be NULL */, uint32_t* d_bestD, uint32_t* d_minC, double* d_mvSub);
 
+/* ---- dense epipolar prologue / epilogue: the per-pixel part of the MATLAB driver around gateway 1 --------------------------
+ * epipolar_geometry.m:104-119 (with rotation_motion.m:7-35) and epipolar_sgm_of.m:46-51.  F (fundamental matrix), H (rotation
+ * homography K*R/K), the epipole in image 2 (1-based pixel coordinates, as MATLAB's epi(1:2)) and the expansion/contraction
+ * flag `direction` (epipolar_geometry.m:94-98) are HOST arrays: F and H row-major 3x3 per pair ([n_pairs][9]), epipole
+ * [n_pairs][2], direction [n_pairs] (NULL = all 0).  Feature matching, LMedS and the SVDs that produce them stay on the host.
+ *   geometry : -> pixelPosD0 f64 [n][2][H][W] (1-based), normlizeDirection f64 [n][2][H][W], offsetFromPosD0 f64 [n][H][W],
+ *              Rflow f64 [n][2][H][W] (may be NULL)
+ *   flow     : flow = (bestD / 256) * normlizeDirection + Rflow, f64 [n][2][H][W]
+ *   sgm_of   : geometry -> calc_cost_sgm -> flow in one call; the 40-byte-per-pixel fp64 operands of gateway 1 never cross
+ *              PCIe.  d_work = fsgm_epipolar_sgm_of_work_bytes() bytes of device scratch.
+ * MATLAB evaluates F*p and H*p through BLAS (summation order / FMA unspecified): the order is fixed here as
+ * (m1*x + m2*y) + m3, separately rounded, and restated in oracle/geometry_oracle.py. */
+FSGM_API int fsgm_epipolar_geometry_dev(fsgm_ctx* ctx, int n_pairs, const double* F, const double* H, const double* epipole,
+                           const int* direction, int width, int height, double* d_pixelPosD0, double* d_normlizeDirection,
+                           double* d_offsetFromPosD0, double* d_Rflow);
+FSGM_API int fsgm_epipolar_flow_dev(fsgm_ctx* ctx, int n_pairs, const uint32_t* d_bestD, const double* d_normlizeDirection,
+                           const double* d_Rflow, int width, int height, double* d_flow);
+FSGM_API size_t fsgm_epipolar_sgm_of_work_bytes(int n_pairs, int width, int height);
+FSGM_API int fsgm_epipolar_sgm_of_dev(fsgm_ctx* ctx, int n_pairs, const uint8_t* d_I0, const uint8_t* d_I1, int width, int height,
+                           const double* F, const double* H, const double* epipole, const int* direction,
+                           int dMax, double vMax, int P1, int P2, const fsgm_epi_opts* opts, void* d_work,
+                           double* d_flow, uint32_t* d_minC);
+/* host images in, host flow out; enqueue-only (fsgm_synchronize before reading), consecutive calls overlap */
+FSGM_API int fsgm_epipolar_sgm_of_batch_async(fsgm_ctx* ctx, int n_pairs, const uint8_t* I0, const uint8_t* I1, int width, int height,
+                           const double* F, const double* H, const double* epipole, const int* direction,
+                           int dMax, double vMax, int P1, int P2, const fsgm_epi_opts* opts, double* flow, uint32_t* minC);
+FSGM_API int fsgm_epipolar_sgm_of(fsgm_ctx* ctx, const uint8_t* I0, const uint8_t* I1, int width, int height,
+                           const double* F, const double* H, const double* epipole, int direction,
+                           int dMax, double vMax, int P1, int P2, const fsgm_epi_opts* opts, double* flow, uint32_t* minC);
+
 /* ---- pyramid driver: the MATLAB loop around gateway 2 (pyramidal_sgm.m:1-77), every level resident on the device ----------
  * [mvCurLevel, mvPyd, minC] = pyramidal_sgm(I0, I1, numPyd)
  * Builds both image pyramids with impyramid(.,'reduce') (:28-29), then from the coarsest level down (:36-75): calc_pyd_cost_sgm
