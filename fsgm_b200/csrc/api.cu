@@ -123,18 +123,19 @@ static int check_opts(fsgm_ctx* c, const fsgm_epi_opts* in, fsgm_epi_opts* o)
 constexpr int VS_MAX_SMEM = 227 * 1024;
 
 // cluster size of the row-synchronous fast path for this problem, or 0 if it does not apply
-static int fast_path_cluster(const fsgm_ctx* c, int W, int D, int P1, int P2, int cmax, const fsgm_epi_opts& o)
+static int fast_path_cluster(fsgm_ctx* c, int W, int D, int P1, int P2, int cmax, const fsgm_epi_opts& o)
 {
     if (c->force_cluster < 0) return 0;
     if (o.adaptive_p2 || sweep_needs_wrap(P1, P2, cmax)) return 0;
     if (o.total_pass < 1 || o.total_pass > 2) return 0;
     const int ndir = o.paths == 8 ? 3 : 1;
-    const int cs = vsweep_cluster_size(W, D, ndir, VS_MAX_SMEM);
-    if (cs && c->force_cluster > 0) {          // forced size must still fit and leave every CTA >= 2 columns
-        const int f = c->force_cluster, Wk = (W + f - 1) / f;
-        if (f >= cs && f <= 8 && (f & (f - 1)) == 0 && (f - 1) * Wk < W && W - (f - 1) * Wk >= 2) return f;
+    if (c->force_cluster > 0)                  // A/B knob: the forced size must fit and leave every CTA >= 2 columns
+        return vsweep_cluster_ok(W, D, ndir, c->force_cluster, VS_MAX_SMEM) ? c->force_cluster : vsweep_cluster_size(W, D, ndir, VS_MAX_SMEM);
+    if (c->best_key[0] != W || c->best_key[1] != D || c->best_key[2] != ndir) {      // occupancy queries: once per problem shape
+        c->best_cs = vsweep_best_cluster(W, D, ndir, VS_MAX_SMEM, &c->best_clusters);
+        c->best_key[0] = W; c->best_key[1] = D; c->best_key[2] = ndir;
     }
-    return cs;
+    return c->best_cs;
 }
 
 // How many of n pairs go through the cluster kernels.  Each pair occupies one cluster for a whole pass, so the work

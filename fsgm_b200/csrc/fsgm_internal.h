@@ -38,6 +38,7 @@ struct fsgm_ctx {
     int no_overlap = 0;                     // tuning knob (fsgm_tune key 2)
     unsigned attr_mask = 0;                 // which kernels already had their max-dynamic-smem attribute set on this device
     int clusters_cs = 0, clusters_max = 0;   // resident clusters for the last queried cluster size
+    int best_key[3] = {0, 0, 0}, best_cs = 0, best_clusters = 0;   // cached vsweep_best_cluster() decision for (W, D, ndir)
     int force_cluster = 0;                  // tuning/test knob: 0 auto, -1 generic path only, 1/2/4/8 forced cluster size
     std::string err;
     // profiling
@@ -124,6 +125,8 @@ int launch_vz_to_disp(fsgm_ctx* c, uint32_t* D, const double* O, size_t total, d
 
 // ---- row-synchronous cluster path for the non-horizontal directions (vsweep.cu) --------------------------
 int vsweep_cluster_size(int W, int D, int ndir, int max_smem);
+bool vsweep_cluster_ok(int W, int D, int ndir, int cs, int max_smem);
+int vsweep_best_cluster(int W, int D, int ndir, int max_smem, int* clusters);
 int vsweep_max_clusters(int cs, size_t smem, int threads);
 size_t vsweep_smem_bytes(int D, int Wk, int ndir);
 int vsweep_threads();

@@ -25,6 +25,7 @@
 #include "fsgm_internal.h"
 #include "sgm_step.cuh"
 #include <cooperative_groups.h>
+#include <algorithm>
 
 namespace cg = cooperative_groups;
 
@@ -68,6 +69,11 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+// for warps that publish nothing: a release would also wait for their global stores to reach L2
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
 template <int NREG> __device__ __forceinline__ void ld_row(const uint8_t* base, int lane, uint32_t (&w)[(NREG + 1) / 2])
 {
@@ -116,7 +122,7 @@ __device__ __forceinline__ void vs_fetch(const VsThread<NREG>& th, uint32_t pix,
 // to a straight line of LDS -> step -> STS per direction.
 template <int NREG, int NDIR, bool FINAL, bool EDGE>
 __device__ __forceinline__ void vs_pixel(const VsThread<NREG>& th, const uint8_t* crow_l, int xl, int yy, int par, int off, uint32_t pix,
-                                         const VsGlobals<NREG>& g)
+                                         const VsGlobals<NREG>& g, bool arrive)
 {
     constexpr int D = 64 * NREG, NW = (NREG + 1) / 2, NB = 2 * NREG;
     const int lane = th.lane, Wk = th.Wk;
@@ -195,6 +201,9 @@ __device__ __forceinline__ void vs_pixel(const VsThread<NREG>& th, const uint8_t
             }
         }
     }
+    // the row's hand-overs are written: publish them before this pixel's global stores are issued (an arrive.release
+    // after those would wait for them to reach L2)
+    if (EDGE && arrive) cluster_arrive();
     if (th.addA_l && th.addB_l && th.preadd) {
         // both horizontal rows present and their byte-wise sum cannot carry (2*(cmax+P2) <= 255): add first, unpack once
         uint32_t ab[NW], t[NREG];
@@ -314,41 +323,60 @@ vsweep_kernel(const VsParams prm)
     th.P1P1 = P1P1; th.P2P2 = P2P2; th.lo_mask = lo_mask; th.hi_mask = hi_mask; th.sdx = sdx;
     th.preadd = 2 * (24 + prm.P2) <= 255;          // cost values are <= 24 on this path (no-wrap domain precondition)
 
+    // Pixel order inside a row is free (every path slot is touched by exactly one pixel per row), so the strip is split in
+    // two halves walked from the outside in: warps 0..HW-1 take xl = 0, HW, 2*HW, ... of the lower half, warps HW..2*HW-1 take
+    // xl = Wk-1, Wk-1-HW, ... of the upper half.  The two pixels that exchange paths with the neighbour CTAs (xl = 0 and
+    // xl = Wk-1) are then the FIRST pixels of warps 0 and HW, and the cluster barrier is split around them: every warp
+    // arrives right after its first pixel of the row and waits at the start of the next row, so the hand-over of row yy is
+    // ordered (arrive.release / wait.acquire) while the rest of the row overlaps the neighbours' progress.  What remains
+    // per row inside the CTA is one bar.sync (state slots move between warps from row to row; the cost buffer is reused).
+    constexpr int HW = VS_WARPS / 2;
+    const int wsub = warp % HW;
+    const bool upper = warp >= HW;
+    const int n_lo = (Wk + 1) / 2, cnt = upper ? Wk - n_lo : n_lo;
+    auto xl_of = [&](int i) { return upper ? Wk - 1 - i : i; };
+
     int off = 0;                                   // yy mod Wk, kept incrementally
     for (int yy = 0; yy < H; ++yy) {
         const int y = row_y(yy), par = yy & 1;
+        if (yy > 0) cluster_wait();                // hand-overs of row yy-1 are visible; neighbours are done reading inbox[par]
         mbar_wait(&bars[par], (uint32_t)((yy >> 1) & 1));
         const uint8_t* crow_l = cbuf + (size_t)par * Wk_max * D + lane * NB;
         const uint32_t rowpix = (uint32_t)y * (uint32_t)W + (uint32_t)xb;
-        // global rows are fetched PD pixels ahead (the warp's pixels are xl = warp, warp + VS_WARPS, ...): with only
-        // 16 warps per SM an L2-miss (~2 us) is not hidden by other warps (ncu r1g: 27 % of the stall samples of the
-        // down pass sat on the first use of the horizontal-volume row)
+        // global rows are fetched PD pixels ahead: with only 20 warps per SM an L2-miss (~2 us) is not hidden by other warps
+        // (ncu r1g: 27 % of the stall samples of the down pass sat on the first use of the horizontal-volume row).
         // The ring is indexed statically (inner loop unrolled by PD): copying a register that is still waiting for its
         // load would stall on the copy, which is exactly what a rotating ring does.
         constexpr int PD = FINAL ? 2 : 4;
         VsGlobals<NREG> gq[PD];
 #pragma unroll
         for (int u = 0; u < PD; ++u)
-            if (warp + u * VS_WARPS < Wk) vs_fetch<NREG, FINAL>(th, rowpix + warp + u * VS_WARPS, gq[u]);
-        for (int xl0 = warp; xl0 < Wk; xl0 += PD * VS_WARPS) {
+            if (wsub + u * HW < cnt) vs_fetch<NREG, FINAL>(th, rowpix + xl_of(wsub + u * HW), gq[u]);
+        if (wsub >= cnt) cluster_arrive_relaxed();  // a warp without pixels has nothing to hand over
+        for (int i0 = wsub; i0 < cnt; i0 += PD * HW) {
 #pragma unroll
             for (int u = 0; u < PD; ++u) {
-                const int xl = xl0 + u * VS_WARPS;
-                if (xl < Wk) {
-                    if (yy == 0 || xl == 0 || xl == Wk - 1) vs_pixel<NREG, NDIR, FINAL, true>(th, crow_l, xl, yy, par, off, rowpix + xl, gq[u]);
-                    else vs_pixel<NREG, NDIR, FINAL, false>(th, crow_l, xl, yy, par, off, rowpix + xl, gq[u]);
-                    if (xl + PD * VS_WARPS < Wk) vs_fetch<NREG, FINAL>(th, rowpix + xl + PD * VS_WARPS, gq[u]);
+                const int i = i0 + u * HW;
+                if (i < cnt) {
+                    const int xl = xl_of(i);
+                    if (yy == 0 || xl == 0 || xl == Wk - 1) vs_pixel<NREG, NDIR, FINAL, true>(th, crow_l, xl, yy, par, off, rowpix + xl, gq[u], i == wsub);
+                    else {
+                        if (i == wsub) cluster_arrive_relaxed();
+                        vs_pixel<NREG, NDIR, FINAL, false>(th, crow_l, xl, yy, par, off, rowpix + xl, gq[u], false);
+                    }
+                    if (i + PD * HW < cnt) vs_fetch<NREG, FINAL>(th, rowpix + xl_of(i + PD * HW), gq[u]);
                 }
             }
         }
         if (++off == Wk) off = 0;
-        // everyone is done with this row: cost buffer `par` is free, outgoing paths are visible after the barrier
-        cluster.sync();
+        // everyone in this CTA is done with the row: cost buffer `par` is free, state slots may change hands
+        __syncthreads();
         if (threadIdx.x == 0 && yy + 2 < H) {
             mbar_expect_tx(&bars[par], row_bytes);
             tma_load_1d(cbuf + (size_t)par * Wk_max * D, Cb + ((size_t)row_y(yy + 2) * W + xb) * D, row_bytes, &bars[par]);
         }
     }
+    cluster_wait();                                // nobody writes into this CTA's shared memory after this point
 }
 
 // subpixel + vz -> disparity from the WTA records (calc_cost_sgm.cpp:278-308, :414-426); the value the reference reads
@@ -397,17 +425,47 @@ static size_t vs_smem_bytes(int D, int Wk, int ndir, bool final_)
 size_t vsweep_smem_bytes(int D, int Wk, int ndir) { return vs_smem_bytes(D, Wk, ndir, true); }
 int vsweep_threads() { return VS_WARPS * 32; }
 
-// cluster size (1,2,4,8) for which the state fits, or 0
+static bool vs_cluster_fits(int W, int D, int ndir, int cs, int max_smem)
+{
+    const int Wk = (W + cs - 1) / cs;
+    if (Wk < 2 || (cs - 1) * Wk >= W) return false;                        // every CTA needs at least one column ...
+    if (cs > 1 && W - (cs - 1) * Wk < 2) return false;                     // ... and the last one two
+    return vs_smem_bytes(D, Wk, ndir, true) <= (size_t)max_smem;
+}
+
+// smallest cluster size (1..16) for which the state fits, or 0
 int vsweep_cluster_size(int W, int D, int ndir, int max_smem)
 {
     if (D != 64 && D != 128 && D != 256) return 0;
-    for (int cs = 1; cs <= 8; cs *= 2) {
-        const int Wk = (W + cs - 1) / cs;
-        if (Wk < 2 || (cs - 1) * Wk >= W) continue;                        // every CTA needs at least one column
-        if (W - (cs - 1) * Wk < 2 && cs > 1) continue;
-        if (vs_smem_bytes(D, Wk, ndir, true) <= (size_t)max_smem) return cs;
-    }
+    for (int cs = 1; cs <= 16; ++cs)
+        if (vs_cluster_fits(W, D, ndir, cs, max_smem)) return cs;
     return 0;
+}
+bool vsweep_cluster_ok(int W, int D, int ndir, int cs, int max_smem)
+{
+    return (D == 64 || D == 128 || D == 256) && cs >= 1 && cs <= 16 && vs_cluster_fits(W, D, ndir, cs, max_smem);
+}
+
+// The cluster size that finishes a full wave of pairs soonest: a pair's pass takes (rows x pixel rounds per row), a round
+// being one pixel per warp (each half of the strip is walked by VS_WARPS/2 warps); resident clusters run concurrently.
+// Sizes above the smallest that fits are worth it when they keep more SMs busy (KITTI: 9 x 15 clusters = 135 SMs with 7
+// rounds per row against 8 x 15 = 120 SMs with 8 rounds).  *clusters receives the resident-cluster count of the choice.
+int vsweep_best_cluster(int W, int D, int ndir, int max_smem, int* clusters)
+{
+    const int cs0 = vsweep_cluster_size(W, D, ndir, max_smem);
+    *clusters = 1;
+    if (!cs0) return 0;
+    int best = 0; double best_score = 0;
+    for (int cs = cs0; cs <= std::min(16, cs0 + 3); ++cs) {
+        if (!vs_cluster_fits(W, D, ndir, cs, max_smem)) continue;
+        const int Wk = (W + cs - 1) / cs;
+        const int k = vsweep_max_clusters(cs, vs_smem_bytes(D, Wk, ndir, true), VS_WARPS * 32);
+        if (k < 1) continue;
+        const int rounds = ((Wk + 1) / 2 + VS_WARPS / 2 - 1) / (VS_WARPS / 2);
+        const double score = (double)rounds / k;                           // time per pair, arbitrary units
+        if (!best || score < best_score * 0.97) { best = cs; best_score = score; *clusters = k; }
+    }
+    return best;
 }
 
 template <int NREG, int NDIR, bool FINAL>
@@ -417,6 +475,7 @@ static int vs_launch_t(fsgm_ctx* c, int n, int cs, size_t smem, const VsParams& 
     const unsigned bit = 1u << (3 + (NREG == 1 ? 0 : NREG == 2 ? 1 : 2) * 4 + (NDIR == 3 ? 2 : 0) + (FINAL ? 1 : 0));
     if (!(c->attr_mask & bit)) {
         FSGM_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        FSGM_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         c->attr_mask |= bit;
     }
     cudaLaunchConfig_t cfg = {};
@@ -456,7 +515,7 @@ int vsweep_max_clusters(int cs, size_t smem, int threads)
 {
     auto kern = vsweep_kernel<4, 3, true>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (cs > 8) cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(cs * 64); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem;
     cudaLaunchAttribute at[1];

@@ -168,6 +168,8 @@ def test_fused_cost_kernel_wild_geometry(ctx, oracle, W, H, D):
     (150, 40, 64, 8, 2, 1), (150, 40, 64, 8, 2, 2), (150, 40, 64, 8, 2, 4), (151, 37, 64, 8, 2, 8),
     (97, 33, 128, 8, 2, 4), (64, 50, 256, 8, 2, 8), (90, 30, 256, 4, 2, 4), (90, 30, 128, 8, 1, 2), (33, 70, 64, 4, 1, 8),
     (40, 3, 64, 8, 2, 4), (16, 1, 64, 8, 2, 8), (300, 20, 256, 8, 2, 8),
+    (151, 37, 64, 8, 2, 3), (200, 25, 128, 8, 2, 5), (333, 21, 256, 8, 2, 9), (400, 18, 256, 8, 2, 12), (500, 12, 256, 4, 2, 16),
+    (140, 30, 256, 8, 2, 7),
 ])
 def test_cluster_path_equals_oracle_and_generic(ctx, oracle, W, H, D, paths, passes, cluster):
     """Row-synchronous cluster kernels (vsweep.cu) at every cluster size: Sp, minC, bestD vs the oracle and vs the
