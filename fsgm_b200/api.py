@@ -32,6 +32,8 @@ class EpiOpts(C.Structure):
 
 
 def load_library() -> C.CDLL:
+    global _LIB_PATH
+    _LIB_PATH = os.environ.get("FSGM_LIB", _LIB_PATH)          # A/B builds of the same ABI (kernel experiments)
     if not os.path.exists(_LIB_PATH):
         raise ImportError(f"{_LIB_PATH} is missing: build it with `python fsgm_b200/build.py` "
                           "(there is no CPU fallback for the fSGM hot path)")

@@ -269,13 +269,15 @@ hsweep_tma_kernel(const SweepParams prm)
     }
     __syncwarp();
 
-    const uint32_t lo_mask = (lane == 0) ? (STEP_BIG2 & 0x0000FFFFu) : 0u;
-    const uint32_t hi_mask = (lane == 31) ? (STEP_BIG2 & 0xFFFF0000u) : 0u;
-    const uint32_t P1P1 = (uint32_t)prm.P1 * 0x10001u, P2P2 = (uint32_t)prm.P2 * 0x10001u;
+    // biased fp16x2 arithmetic (sgm_step.cuh): min on the ALU pipe, additions on the FMA pipe
+    const uint32_t lo_mask = (lane == 0) ? H2_BIG_LO : 0u;
+    const uint32_t hi_mask = (lane == 31) ? H2_BIG_HI : 0u;
+    const uint32_t P1h = h2_const(prm.P1), P2h = h2_const(prm.P2);
+    constexpr uint32_t ZERO_B = H2_BIAS2 & 0xFFFFu;                      // biased 0
     uint32_t Lr[NREG];
 #pragma unroll
-    for (int i = 0; i < NREG; ++i) Lr[i] = 0;
-    uint32_t M = 0;
+    for (int i = 0; i < NREG; ++i) Lr[i] = H2_BIAS2;
+    uint32_t M = ZERO_B;
     bool first = true;
     for (int c = 0; c < nch; ++c) {
         const int t0 = c * HCH, cnt = min(HCH, W - t0);
@@ -294,12 +296,12 @@ hsweep_tma_kernel(const SweepParams prm)
             else if (NREG == 2) cw[0] = *reinterpret_cast<const uint32_t*>(buf + off * D);
             else { const uint2 v = *reinterpret_cast<const uint2*>(buf + off * D); cw[0] = v.x; cw[1] = v.y; }
             uint32_t cc[NREG], cP2[NREG], Ln[NREG];
-            unpack_cost<NREG>(cw, cc);
+            unpack_cost_h2<NREG>(cw, cc);
 #pragma unroll
-            for (int i = 0; i < NREG; ++i) cP2[i] = cc[i] + P2P2;
-            // at the path start the zero state with M = 0 makes the step return L = C; the minimum is then forced to 0
-            const uint32_t m = sgm_step_u16<NREG>(cc, cP2, Lr, M, P1P1, lo_mask, hi_mask, Ln);
-            M = first ? 0u : m;
+            for (int i = 0; i < NREG; ++i) cP2[i] = h2_add(cc[i], P2h);
+            // at the path start the (biased) zero state with M = 0 makes the step return L = C; the minimum is then forced to 0
+            const uint32_t m = sgm_step_h2<NREG>(cP2, Lr, M, P1h, P2h, lo_mask, hi_mask, Ln);
+            M = first ? ZERO_B : m;
             first = false;
 #pragma unroll
             for (int i = 0; i < NREG; ++i) Lr[i] = Ln[i];

@@ -4,6 +4,7 @@
 // row-synchronous cluster kernel (vsweep.cu).
 #pragma once
 #include <stdint.h>
+#include <cuda_fp16.h>
 
 namespace fsgm {
 
@@ -49,6 +50,72 @@ __device__ __forceinline__ uint32_t sgm_step_u16(const uint32_t (&c)[NREG], cons
         const uint32_t nb = __vminu2(q[i], q[i + 1]);                 // min(Lpre(d-1), Lpre(d+1))
         const uint32_t b = __viaddmin_u16x2(nb, P1P1, Lpre[i]);       // min(nb + P1, Lpre(d))
         L[i] = __viaddmin_u16x2(c[i], b - MM, cP2[i]);                // min(C + b - M, C + P2); b >= M in both halves: no borrow
+        m = __vminu2(m, L[i]);
+    }
+    m = min(m & 0xFFFFu, m >> 16);
+    return __reduce_min_sync(0xffffffffu, m);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// The same step with the additions on the FMA pipe.  ncu shows every aggregation kernel bound by the integer ALU pipe
+// (VIMNMX / VIADDMNMX / PRMT / LOP3 issue there, one warp instruction per two cycles per sub-partition) while the FMA pipe,
+// which has the same issue rate, idles.  Values are therefore carried as fp16x2 numbers with a bias of 1024:
+//     v  <->  half(1024 + v),  bit pattern 0x6400 | v   (exact for 0 <= v < 1024: the ulp in [1024, 2048) is 1)
+//   * min() still runs on the ALU pipe, on the BIT PATTERNS (positive halves order like unsigned integers): VIMNMX.U16x2;
+//   * +P1 and +P2 are HADD2 on the FMA pipe (adding a small integer keeps the bias and stays below 2048);
+//   * the far term  C + min(b - M, P2)  =  (C + P2) - relu((P2 + M) - b)  is HFMA2.RELU + HADD2: two FMA-pipe instructions and
+//     no ALU-pipe instruction (the integer form spends a VIADDMNMX on it);
+//   * bytes <-> biased halves cost nothing extra: unpacking is the same PRMT with 0x64 as the high byte, packing takes the
+//     low bytes as before.
+// Per u16x2 register the ALU pipe issues 3 instructions instead of 4 and the FMA pipe 3 instead of 1.  Every intermediate is an
+// integer below 2048 in magnitude, so the fp16 arithmetic is exact and the results are bit-identical to the integer step.
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr uint32_t H2_BIAS2 = 0x64006400u;       // half2(1024, 1024)
+constexpr uint32_t H2_NEG1 = 0xBC00BC00u;        // half2(-1, -1)
+constexpr uint32_t H2_BIG_LO = 0x00000800u;      // OR-ed into a biased half: exponent 27, value >= 4096 — never wins a min
+constexpr uint32_t H2_BIG_HI = 0x08000000u;
+
+__device__ __forceinline__ uint32_t h2_add(uint32_t a, uint32_t b) { uint32_t r; asm("add.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t h2_sub(uint32_t a, uint32_t b) { uint32_t r; asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+// relu(k - b)
+__device__ __forceinline__ uint32_t h2_relu_diff(uint32_t k, uint32_t b)
+{
+    uint32_t r;
+    asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(b), "r"(H2_NEG1), "r"(k));
+    return r;
+}
+// small non-negative integer (< 1024) -> half2(v, v), unbiased
+__device__ __forceinline__ uint32_t h2_const(int v) { return (uint32_t)__half_as_ushort(__int2half_rn(v)) * 0x10001u; }
+
+// bytes -> biased halves
+template <int NREG>
+__device__ __forceinline__ void unpack_cost_h2(const uint32_t* w, uint32_t (&c)[NREG])
+{
+#pragma unroll
+    for (int i = 0; i < NREG; ++i) c[i] = __byte_perm(w[i >> 1], 0x64646464u, (i & 1) ? 0x4342 : 0x4140);
+}
+// biased halves (values <= 255) -> bytes: pack_cost<NREG>() as it is (it keeps the low byte of every half)
+
+// c, cP2 = c + P2, Lpre biased; M = biased minimum of Lpre in the low 16 bits; P1h/P2h = h2_const(P1/P2);
+// lo_mask / hi_mask = H2_BIG_LO in lane 0 / H2_BIG_HI in lane 31, else 0.  Returns the biased minimum of L.
+template <int NREG>
+__device__ __forceinline__ uint32_t sgm_step_h2(const uint32_t (&cP2)[NREG], const uint32_t (&Lpre)[NREG], uint32_t M, uint32_t P1h,
+                                                uint32_t P2h, uint32_t lo_mask, uint32_t hi_mask, uint32_t (&L)[NREG])
+{
+    uint32_t q[NREG + 1];
+    const uint32_t up = __shfl_up_sync(0xffffffffu, Lpre[NREG - 1], 1);
+    const uint32_t dn = __shfl_down_sync(0xffffffffu, Lpre[0], 1);
+    q[0] = __byte_perm(up, Lpre[0], 0x5432) | lo_mask;               // (label 2i-1, label 2i)
+#pragma unroll
+    for (int i = 1; i < NREG; ++i) q[i] = __byte_perm(Lpre[i - 1], Lpre[i], 0x5432);
+    q[NREG] = __byte_perm(Lpre[NREG - 1], dn, 0x5432) | hi_mask;
+    const uint32_t K = h2_add(M * 0x10001u, P2h);                     // 1024 + M + P2
+    uint32_t m = 0xFFFFFFFFu;
+#pragma unroll
+    for (int i = 0; i < NREG; ++i) {
+        const uint32_t nb = __vminu2(q[i], q[i + 1]);                 // min(Lpre(d-1), Lpre(d+1))
+        const uint32_t b = __vminu2(h2_add(nb, P1h), Lpre[i]);        // min(nb + P1, Lpre(d))
+        L[i] = h2_sub(cP2[i], h2_relu_diff(K, b));                    // (C + P2) - relu(P2 + M - b)
         m = __vminu2(m, L[i]);
     }
     m = min(m & 0xFFFFu, m >> 16);

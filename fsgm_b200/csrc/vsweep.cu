@@ -127,11 +127,12 @@ __device__ __forceinline__ void vs_pixel(const VsThread<NREG>& th, const uint8_t
     constexpr int D = 64 * NREG, NW = (NREG + 1) / 2, NB = 2 * NREG;
     const int lane = th.lane, Wk = th.Wk;
     const size_t vox = (size_t)pix * D;
+    // cost, path state and minima are biased fp16x2 numbers (sgm_step.cuh): min on the ALU pipe, add on the FMA pipe
     uint32_t cw[NW], c[NREG], cP2[NREG], acc[NREG];
     ld_row<NREG>(crow_l + xl * D, 0, cw);
-    unpack_cost<NREG>(cw, c);
+    unpack_cost_h2<NREG>(cw, c);
 #pragma unroll
-    for (int i = 0; i < NREG; ++i) { acc[i] = 0; cP2[i] = c[i] + th.P2P2; }
+    for (int i = 0; i < NREG; ++i) cP2[i] = h2_add(c[i], th.P2P2);
     // The three directions are independent.  All previous-state rows are loaded first and all new rows stored last:
     // with the loads and stores of one direction between those of another the compiler must assume they alias and
     // serialises the three dependency chains (ncu r1h: fixed-latency "wait" stalls were the largest stall class).
@@ -166,22 +167,29 @@ __device__ __forceinline__ void vs_pixel(const VsThread<NREG>& th, const uint8_t
         ld_row<NREG>(src, 0, lw[k]);
     }
     uint32_t pw[NDIR][NW], Mn[NDIR];
+    static_assert(NDIR == 1 || NDIR == 3, "accumulator bias below assumes one or three directions");
+    constexpr uint32_t ACC0 = 0xE800E800u;             // half2(-2048) = -1024 * (NDIR - 1) for three directions
 #pragma unroll
     for (int k = 0; k < NDIR; ++k) {
         uint32_t L[NREG];
-        Mn[k] = 0;
+        Mn[k] = H2_BIAS2 & 0xFFFFu;                    // biased 0: the minimum a restarted path hands to its next step
         if (EDGE && restart[k]) {
 #pragma unroll
             for (int i = 0; i < NREG; ++i) L[i] = c[i];
         } else {
             uint32_t Lpre[NREG];
-            unpack_cost<NREG>(lw[k], Lpre);
-            Mn[k] = sgm_step_u16<NREG>(c, cP2, Lpre, Mv[k], th.P1P1, th.lo_mask, th.hi_mask, L);
+            unpack_cost_h2<NREG>(lw[k], Lpre);
+            Mn[k] = sgm_step_h2<NREG>(cP2, Lpre, Mv[k], th.P1P1, th.P2P2, th.lo_mask, th.hi_mask, L);
         }
         pack_cost<NREG>(L, pw[k]);
+        // sum of the directions, still on the FMA pipe: -1024*(NDIR-1) + sum(1024 + L_k) = 1024 + sum(L_k) < 2048, every
+        // partial sum is an integer of magnitude <= 2048
 #pragma unroll
-        for (int i = 0; i < NREG; ++i) acc[i] += L[i];
+        for (int i = 0; i < NREG; ++i) acc[i] = k == 0 ? (NDIR == 1 ? L[i] : h2_add(L[i], ACC0)) : h2_add(acc[i], L[i]);
     }
+    // biased half -> integer u16x2
+#pragma unroll
+    for (int i = 0; i < NREG; ++i) acc[i] -= H2_BIAS2;
 #pragma unroll
     for (int k = 0; k < NDIR; ++k) {
         const int dx = k == 0 ? 0 : (k == 1 ? th.sdx : -th.sdx);
@@ -304,8 +312,8 @@ vsweep_kernel(const VsParams prm)
     uint8_t* inbox_right = (rank + 1 < CS) ? cluster.map_shared_rank(inbox, rank + 1) : nullptr;   // we write slot "from left" there
     uint8_t* inbox_left = (rank > 0) ? cluster.map_shared_rank(inbox, rank - 1) : nullptr;        // we write slot "from right" there
 
-    const uint32_t P1P1 = (uint32_t)prm.P1 * 0x10001u, P2P2 = (uint32_t)prm.P2 * 0x10001u;
-    const uint32_t lo_mask = lane == 0 ? (STEP_BIG2 & 0x0000FFFFu) : 0u, hi_mask = lane == 31 ? (STEP_BIG2 & 0xFFFF0000u) : 0u;
+    const uint32_t P1P1 = h2_const(prm.P1), P2P2 = h2_const(prm.P2);          // fp16x2 constants (sgm_step.cuh)
+    const uint32_t lo_mask = lane == 0 ? H2_BIG_LO : 0u, hi_mask = lane == 31 ? H2_BIG_HI : 0u;
     const int sdx = prm.up ? -1 : 1;               // x direction of "direction 1" in this pass: (+1,+1) going down, (-1,-1) going up
 
     // per-thread bases with the lane's byte offset folded in
@@ -336,6 +344,14 @@ vsweep_kernel(const VsParams prm)
     const int n_lo = (Wk + 1) / 2, cnt = upper ? Wk - n_lo : n_lo;
     auto xl_of = [&](int i) { return upper ? Wk - 1 - i : i; };
 
+    // global rows (horizontal volumes / the other pass's sum) are fetched PD pixels ahead: with only 20 warps per SM an
+    // L2 miss (~2 us) is not hidden by other warps (ncu r1g: 27 % of the stall samples of the down pass sat on the first use
+    // of the horizontal-volume row).  The ring is indexed statically (inner loop unrolled by PD): copying a register that is
+    // still waiting for its load would stall on the copy, which is exactly what a rotating ring does.  The first PD pixels
+    // of the NEXT row are requested before the row-end barrier, so the misses overlap the synchronisation.
+    constexpr int PD = FINAL ? 2 : 4;
+    VsGlobals<NREG> gq[PD];
+
     int off = 0;                                   // yy mod Wk, kept incrementally
     for (int yy = 0; yy < H; ++yy) {
         const int y = row_y(yy), par = yy & 1;
@@ -343,15 +359,11 @@ vsweep_kernel(const VsParams prm)
         mbar_wait(&bars[par], (uint32_t)((yy >> 1) & 1));
         const uint8_t* crow_l = cbuf + (size_t)par * Wk_max * D + lane * NB;
         const uint32_t rowpix = (uint32_t)y * (uint32_t)W + (uint32_t)xb;
-        // global rows are fetched PD pixels ahead: with only 20 warps per SM an L2-miss (~2 us) is not hidden by other warps
-        // (ncu r1g: 27 % of the stall samples of the down pass sat on the first use of the horizontal-volume row).
-        // The ring is indexed statically (inner loop unrolled by PD): copying a register that is still waiting for its
-        // load would stall on the copy, which is exactly what a rotating ring does.
-        constexpr int PD = FINAL ? 2 : 4;
-        VsGlobals<NREG> gq[PD];
+        if (yy == 0) {
 #pragma unroll
-        for (int u = 0; u < PD; ++u)
-            if (wsub + u * HW < cnt) vs_fetch<NREG, FINAL>(th, rowpix + xl_of(wsub + u * HW), gq[u]);
+            for (int u = 0; u < PD; ++u)
+                if (wsub + u * HW < cnt) vs_fetch<NREG, FINAL>(th, rowpix + xl_of(wsub + u * HW), gq[u]);
+        }
         if (wsub >= cnt) cluster_arrive_relaxed();  // a warp without pixels has nothing to hand over
         for (int i0 = wsub; i0 < cnt; i0 += PD * HW) {
 #pragma unroll
@@ -369,6 +381,12 @@ vsweep_kernel(const VsParams prm)
             }
         }
         if (++off == Wk) off = 0;
+        if (yy + 1 < H) {
+            const uint32_t nextpix = (uint32_t)row_y(yy + 1) * (uint32_t)W + (uint32_t)xb;
+#pragma unroll
+            for (int u = 0; u < PD; ++u)
+                if (wsub + u * HW < cnt) vs_fetch<NREG, FINAL>(th, nextpix + xl_of(wsub + u * HW), gq[u]);
+        }
         // everyone in this CTA is done with the row: cost buffer `par` is free, state slots may change hands
         __syncthreads();
         if (threadIdx.x == 0 && yy + 2 < H) {
