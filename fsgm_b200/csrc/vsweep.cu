@@ -344,14 +344,6 @@ vsweep_kernel(const VsParams prm)
     const int n_lo = (Wk + 1) / 2, cnt = upper ? Wk - n_lo : n_lo;
     auto xl_of = [&](int i) { return upper ? Wk - 1 - i : i; };
 
-    // global rows (horizontal volumes / the other pass's sum) are fetched PD pixels ahead: with only 20 warps per SM an
-    // L2 miss (~2 us) is not hidden by other warps (ncu r1g: 27 % of the stall samples of the down pass sat on the first use
-    // of the horizontal-volume row).  The ring is indexed statically (inner loop unrolled by PD): copying a register that is
-    // still waiting for its load would stall on the copy, which is exactly what a rotating ring does.  The first PD pixels
-    // of the NEXT row are requested before the row-end barrier, so the misses overlap the synchronisation.
-    constexpr int PD = FINAL ? 2 : 4;
-    VsGlobals<NREG> gq[PD];
-
     int off = 0;                                   // yy mod Wk, kept incrementally
     for (int yy = 0; yy < H; ++yy) {
         const int y = row_y(yy), par = yy & 1;
@@ -359,11 +351,16 @@ vsweep_kernel(const VsParams prm)
         mbar_wait(&bars[par], (uint32_t)((yy >> 1) & 1));
         const uint8_t* crow_l = cbuf + (size_t)par * Wk_max * D + lane * NB;
         const uint32_t rowpix = (uint32_t)y * (uint32_t)W + (uint32_t)xb;
-        if (yy == 0) {
+        // global rows (horizontal volumes / the other pass's sum) are fetched PD pixels ahead: with only 20 warps per SM an
+        // L2 miss (~2 us) is not hidden by other warps (ncu r1g: 27 % of the stall samples of the down pass sat on the first
+        // use of the horizontal-volume row).  The ring is indexed statically (inner loop unrolled by PD): copying a register
+        // that is still waiting for its load would stall on the copy, which is exactly what a rotating ring does.
+        // (Requesting the next row's first pixels before the row-end barrier was measured slower: 21.9 -> 23.3 ms per 60 pairs.)
+        constexpr int PD = FINAL ? 2 : 4;
+        VsGlobals<NREG> gq[PD];
 #pragma unroll
-            for (int u = 0; u < PD; ++u)
-                if (wsub + u * HW < cnt) vs_fetch<NREG, FINAL>(th, rowpix + xl_of(wsub + u * HW), gq[u]);
-        }
+        for (int u = 0; u < PD; ++u)
+            if (wsub + u * HW < cnt) vs_fetch<NREG, FINAL>(th, rowpix + xl_of(wsub + u * HW), gq[u]);
         if (wsub >= cnt) cluster_arrive_relaxed();  // a warp without pixels has nothing to hand over
         for (int i0 = wsub; i0 < cnt; i0 += PD * HW) {
 #pragma unroll
@@ -381,12 +378,6 @@ vsweep_kernel(const VsParams prm)
             }
         }
         if (++off == Wk) off = 0;
-        if (yy + 1 < H) {
-            const uint32_t nextpix = (uint32_t)row_y(yy + 1) * (uint32_t)W + (uint32_t)xb;
-#pragma unroll
-            for (int u = 0; u < PD; ++u)
-                if (wsub + u * HW < cnt) vs_fetch<NREG, FINAL>(th, nextpix + xl_of(wsub + u * HW), gq[u]);
-        }
         // everyone in this CTA is done with the row: cost buffer `par` is free, state slots may change hands
         __syncthreads();
         if (threadIdx.x == 0 && yy + 2 < H) {
