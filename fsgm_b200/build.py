@@ -54,5 +54,28 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+PROJ = os.path.join(HERE, "proj")
+PROJ_LIB = os.path.join(HERE, "libfsgm_proj.so")
+PROJ_BIN = os.path.join(HERE, "sgmof")
+
+
+def build_proj(force: bool = False) -> str:
+    """C++ facade of the reference's proj/ library (EpiSGM / PydSGM, KITTI flow PNG, calib reader) + the sgmof command line.
+    Plain host C++ on top of libfsgm.so's C ABI; zlib for PNG."""
+    srcs = [os.path.join(PROJ, f) for f in ("png_io.cpp", "flow_io.cpp", "sgm_facade.cpp")]
+    main = os.path.join(PROJ, "sgmof_main.cpp")
+    deps = srcs + [main, os.path.join(HERE, "..", "include", "fsgm_proj.hpp"), LIB]
+    if not force and os.path.exists(PROJ_LIB) and os.path.exists(PROJ_BIN) and \
+            all(os.path.getmtime(p) <= min(os.path.getmtime(PROJ_LIB), os.path.getmtime(PROJ_BIN)) for p in deps):
+        return PROJ_BIN
+    cxx = os.environ.get("FSGM_CXX", "g++")        # the system g++ (shared libstdc++), not $CXX: a static libstdc++ inside a dlopen-ed library breaks iostreams
+    common = ["-O2", "-std=c++17", "-Wall", "-fPIC"]
+    link = ["-L" + HERE, "-lfsgm", "-lz", "-Wl,-rpath,$ORIGIN"]
+    subprocess.run([cxx] + common + ["-shared", "-o", PROJ_LIB] + srcs + link, check=True)
+    subprocess.run([cxx] + common + ["-o", PROJ_BIN, main, "-L" + HERE, "-lfsgm_proj"] + link, check=True)
+    return PROJ_BIN
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_proj(force="--force" in sys.argv))
