@@ -195,7 +195,10 @@ int launch_epi_cost(fsgm_ctx* c, int n, const double* d_vz, const uint32_t* cen1
 // so one unsigned conversion, an add, a shift and an unsigned min reproduce all of it — except NaN, for which the
 // hardware conversion does not return 0.  NaN can only appear when an input is non-finite or |offset| is so large
 // that offset*vz overflows (inf*0); such pixels are flagged while staging and take a checked path.
-constexpr int FC_TX = 32, FC_THREADS = 256;      // strip width; rows per CTA are chosen at launch (32..128)
+#ifndef FSGM_FC_TX
+#define FSGM_FC_TX 32
+#endif
+constexpr int FC_TX = FSGM_FC_TX, FC_THREADS = 256;      // strip width; rows per CTA are chosen at launch (32..128)
 
 __device__ __forceinline__ uint32_t ref_round_clamp_w(double w, uint32_t hi)
 {
