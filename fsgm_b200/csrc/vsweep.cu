@@ -102,14 +102,17 @@ struct VsThread {
 template <int NREG>
 struct VsGlobals { uint32_t a[(NREG + 1) / 2], b[(NREG + 1) / 2], s[NREG]; };
 
-template <int NREG, bool FINAL>
+// FAST = the operand configuration of the standard two-pass run is known at compile time: the first pass (!FINAL) adds both
+// horizontal volumes (byte-wise pre-add valid) and writes the u16 sum; the second (FINAL) adds that sum and does WTA with no
+// Sp dump.  Every other combination (single pass, 4 paths with one horizontal volume, stage dumps) takes the run-time checks.
+template <int NREG, bool FINAL, bool FAST>
 __device__ __forceinline__ void vs_fetch(const VsThread<NREG>& th, uint32_t pix, VsGlobals<NREG>& g)
 {
     constexpr int D = 64 * NREG;
     const size_t vox = (size_t)pix * D;
-    if (th.addA_l) ld_row<NREG>(th.addA_l + vox, 0, g.a);
-    if (th.addB_l) ld_row<NREG>(th.addB_l + vox, 0, g.b);
-    if (FINAL && th.Sin_l) {
+    if (FAST ? !FINAL : th.addA_l != nullptr) ld_row<NREG>(th.addA_l + vox, 0, g.a);
+    if (FAST ? !FINAL : th.addB_l != nullptr) ld_row<NREG>(th.addB_l + vox, 0, g.b);
+    if (FAST ? FINAL : (FINAL && th.Sin_l)) {
         const uint32_t* sp = reinterpret_cast<const uint32_t*>(th.Sin_l + vox);
         if (NREG == 4) { uint4 v = *reinterpret_cast<const uint4*>(sp); g.s[0] = v.x; g.s[1] = v.y; g.s[2] = v.z; g.s[3] = v.w; }
         else if (NREG == 2) { uint2 v = *reinterpret_cast<const uint2*>(sp); g.s[0] = v.x; g.s[1] = v.y; }
@@ -120,7 +123,7 @@ __device__ __forceinline__ void vs_fetch(const VsThread<NREG>& th, uint32_t pix,
 // One pixel of one row: all NDIR directions, sum, output.  EDGE = the pixel may restart a path, take one from a
 // neighbour CTA's hand-over, or hand one over (first row, first / last column of the strip); interior pixels compile
 // to a straight line of LDS -> step -> STS per direction.
-template <int NREG, int NDIR, bool FINAL, bool EDGE>
+template <int NREG, int NDIR, bool FINAL, bool EDGE, bool FAST>
 __device__ __forceinline__ void vs_pixel(const VsThread<NREG>& th, const uint8_t* crow_l, int xl, int yy, int par, int off, uint32_t pix,
                                          const VsGlobals<NREG>& g, bool arrive)
 {
@@ -212,7 +215,8 @@ __device__ __forceinline__ void vs_pixel(const VsThread<NREG>& th, const uint8_t
     // the row's hand-overs are written: publish them before this pixel's global stores are issued (an arrive.release
     // after those would wait for them to reach L2)
     if (EDGE && arrive) cluster_arrive();
-    if (th.addA_l && th.addB_l && th.preadd) {
+    const bool hasA = FAST ? !FINAL : th.addA_l != nullptr, hasB = FAST ? !FINAL : th.addB_l != nullptr;
+    if (hasA && hasB && (FAST || th.preadd)) {
         // both horizontal rows present and their byte-wise sum cannot carry (2*(cmax+P2) <= 255): add first, unpack once
         uint32_t ab[NW], t[NREG];
 #pragma unroll
@@ -221,10 +225,10 @@ __device__ __forceinline__ void vs_pixel(const VsThread<NREG>& th, const uint8_t
 #pragma unroll
         for (int i = 0; i < NREG; ++i) acc[i] += t[i];
     } else {
-        if (th.addA_l) { uint32_t t[NREG]; unpack_cost<NREG>(g.a, t);
+        if (hasA) { uint32_t t[NREG]; unpack_cost<NREG>(g.a, t);
 #pragma unroll
             for (int i = 0; i < NREG; ++i) acc[i] += t[i]; }
-        if (th.addB_l) { uint32_t t[NREG]; unpack_cost<NREG>(g.b, t);
+        if (hasB) { uint32_t t[NREG]; unpack_cost<NREG>(g.b, t);
 #pragma unroll
             for (int i = 0; i < NREG; ++i) acc[i] += t[i]; }
     }
@@ -234,11 +238,11 @@ __device__ __forceinline__ void vs_pixel(const VsThread<NREG>& th, const uint8_t
         else if (NREG == 2) *reinterpret_cast<uint2*>(sp) = make_uint2(acc[0], acc[1]);
         else *sp = acc[0];
     } else {
-        if (th.Sin_l) {
+        if (FAST || th.Sin_l) {
 #pragma unroll
             for (int i = 0; i < NREG; ++i) acc[i] += g.s[i];
         }
-        if (th.Sout_l) {
+        if (!FAST && th.Sout_l) {
             uint32_t* sp = reinterpret_cast<uint32_t*>(th.Sout_l + vox);
 #pragma unroll
             for (int i = 0; i < NREG; ++i) sp[i] = acc[i];
@@ -246,13 +250,14 @@ __device__ __forceinline__ void vs_pixel(const VsThread<NREG>& th, const uint8_t
         // winner-take-all: first minimum (strict <, calc_cost_sgm.cpp:267) via (sum << 16 | label)
         uint32_t key = 0xFFFFFFFFu;
         uint16_t* ws = th.ws;
-        const uint32_t lbl = (uint32_t)(lane * 2 * NREG);
 #pragma unroll
         for (int i = 0; i < NREG; ++i) {
-            // (sum << 16 | label) for the two labels of this register: one PRMT each
-            key = min(key, __byte_perm(acc[i], lbl + 2 * i, 0x1054));
-            key = min(key, __byte_perm(acc[i], lbl + 2 * i + 1, 0x3254));
+            // (sum << 16 | position inside the lane) for the two labels of this register: one PRMT each, the position an
+            // immediate; the lane's first label (a multiple of 2*NREG) is OR-ed in once after the lane-level minimum
+            key = min(key, __byte_perm(acc[i], 2 * i, 0x1054));
+            key = min(key, __byte_perm(acc[i], 2 * i + 1, 0x3254));
         }
+        key |= (uint32_t)(lane * 2 * NREG);
         if (NREG == 4) reinterpret_cast<uint4*>(ws)[lane] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
         else if (NREG == 2) reinterpret_cast<uint2*>(ws)[lane] = make_uint2(acc[0], acc[1]);
         else reinterpret_cast<uint32_t*>(ws)[lane] = acc[0];
@@ -263,7 +268,7 @@ __device__ __forceinline__ void vs_pixel(const VsThread<NREG>& th, const uint8_t
             th.minC[pix] = key >> 16;
             uint16_t* r = th.rec + (size_t)pix * 4;
             const uint16_t c_1 = idx > 0 ? ws[idx - 1] : 0, c1 = idx + 1 < (uint32_t)D ? ws[idx + 1] : 0;
-            *reinterpret_cast<uint2*>(r) = make_uint2(idx | ((uint32_t)c_1 << 16), (uint32_t)c1 | ((uint32_t)ws[0] << 16));
+            *reinterpret_cast<uint2*>(r) = make_uint2(idx | ((uint32_t)c_1 << 16), (uint32_t)c1 | (acc[0] << 16));      // lane 0's acc[0] low half = Sp[0]
         }
         __syncwarp();
     }
@@ -272,7 +277,7 @@ __device__ __forceinline__ void vs_pixel(const VsThread<NREG>& th, const uint8_t
 // NDIR: 1 (vertical only, the reference's 4-path setting) or 3.  FINAL: add Sin and do WTA instead of writing Sout.
 // (Capping the registers at 72 so that a front-end CTA of the next wave could share the SM was measured: the cap costs the
 // cluster kernel 8 % and the co-resident kernels give nothing back — 1549 -> 1475 pairs/s.)
-template <int NREG, int NDIR, bool FINAL>
+template <int NREG, int NDIR, bool FINAL, bool FAST>
 __global__ void __launch_bounds__(VS_WARPS * 32, 1)
 vsweep_kernel(const VsParams prm)
 {
@@ -362,7 +367,7 @@ vsweep_kernel(const VsParams prm)
         VsGlobals<NREG> gq[PD];
 #pragma unroll
         for (int u = 0; u < PD; ++u)
-            if (wsub + u * HW < cnt) vs_fetch<NREG, FINAL>(th, rowpix + xl_of(wsub + u * HW), gq[u]);
+            if (wsub + u * HW < cnt) vs_fetch<NREG, FINAL, FAST>(th, rowpix + xl_of(wsub + u * HW), gq[u]);
         if (wsub >= cnt) cluster_arrive_relaxed();  // a warp without pixels has nothing to hand over
         for (int i0 = wsub; i0 < cnt; i0 += PD * HW) {
 #pragma unroll
@@ -370,12 +375,12 @@ vsweep_kernel(const VsParams prm)
                 const int i = i0 + u * HW;
                 if (i < cnt) {
                     const int xl = xl_of(i);
-                    if (yy == 0 || xl == 0 || xl == Wk - 1) vs_pixel<NREG, NDIR, FINAL, true>(th, crow_l, xl, yy, par, off, rowpix + xl, gq[u], i == wsub);
+                    if (yy == 0 || xl == 0 || xl == Wk - 1) vs_pixel<NREG, NDIR, FINAL, true, FAST>(th, crow_l, xl, yy, par, off, rowpix + xl, gq[u], i == wsub);
                     else {
                         if (i == wsub) cluster_arrive_relaxed();
-                        vs_pixel<NREG, NDIR, FINAL, false>(th, crow_l, xl, yy, par, off, rowpix + xl, gq[u], false);
+                        vs_pixel<NREG, NDIR, FINAL, false, FAST>(th, crow_l, xl, yy, par, off, rowpix + xl, gq[u], false);
                     }
-                    if (i + PD * HW < cnt) vs_fetch<NREG, FINAL>(th, rowpix + xl_of(i + PD * HW), gq[u]);
+                    if (i + PD * HW < cnt) vs_fetch<NREG, FINAL, FAST>(th, rowpix + xl_of(i + PD * HW), gq[u]);
                 }
             }
         }
@@ -479,11 +484,11 @@ int vsweep_best_cluster(int W, int D, int ndir, int max_smem, int* clusters)
     return best;
 }
 
-template <int NREG, int NDIR, bool FINAL>
+template <int NREG, int NDIR, bool FINAL, bool FAST>
 static int vs_launch_t(fsgm_ctx* c, int n, int cs, size_t smem, const VsParams& p)
 {
-    auto kern = vsweep_kernel<NREG, NDIR, FINAL>;
-    const unsigned bit = 1u << (3 + (NREG == 1 ? 0 : NREG == 2 ? 1 : 2) * 4 + (NDIR == 3 ? 2 : 0) + (FINAL ? 1 : 0));
+    auto kern = vsweep_kernel<NREG, NDIR, FINAL, FAST>;
+    const unsigned bit = 1u << (3 + ((NREG == 1 ? 0 : NREG == 2 ? 1 : 2) * 4 + (NDIR == 3 ? 2 : 0) + (FINAL ? 1 : 0)) * 2 + (FAST ? 1 : 0));
     if (!(c->attr_mask & bit)) {
         FSGM_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         FSGM_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -510,7 +515,10 @@ int launch_vsweep(fsgm_ctx* c, int n, int cs, int ndir, bool final_, const uint8
     p.W = W; p.H = H; p.Wk = (W + cs - 1) / cs; p.P1 = P1; p.P2 = P2; p.up = up;
     const size_t smem = vs_smem_bytes(D, p.Wk, ndir, final_);
     const int nreg = D / 64;
-#define VS_GO(NR, ND, FN) return vs_launch_t<NR, ND, FN>(c, n, cs, smem, p)
+    // compile-time operand configuration of the standard two-pass run (see vs_fetch)
+    const bool preadd = 2 * (24 + P2) <= 255;
+    const bool fast = final_ ? (Sin && !addA && !addB && !Sout) : (addA && addB && preadd && !Sin && Sout);
+#define VS_GO(NR, ND, FN) do { if (fast) return vs_launch_t<NR, ND, FN, true>(c, n, cs, smem, p); return vs_launch_t<NR, ND, FN, false>(c, n, cs, smem, p); } while (0)
     if (ndir == 3) {
         if (final_) { if (nreg == 4) VS_GO(4, 3, true); if (nreg == 2) VS_GO(2, 3, true); VS_GO(1, 3, true); }
         else        { if (nreg == 4) VS_GO(4, 3, false); if (nreg == 2) VS_GO(2, 3, false); VS_GO(1, 3, false); }
@@ -524,7 +532,7 @@ int launch_vsweep(fsgm_ctx* c, int n, int cs, int ndir, bool final_, const uint8
 // occupancy probe used by the tuning notes in DESIGN.md: how many clusters of `cs` CTAs with `smem` bytes can be resident
 int vsweep_max_clusters(int cs, size_t smem, int threads)
 {
-    auto kern = vsweep_kernel<4, 3, true>;
+    auto kern = vsweep_kernel<4, 3, true, true>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     cudaLaunchConfig_t cfg = {};
