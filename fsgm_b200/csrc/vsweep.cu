@@ -88,12 +88,30 @@ template <int NREG> __device__ __forceinline__ void st_row(uint8_t* base, int la
     else reinterpret_cast<uint2*>(base)[lane] = make_uint2(w[0], w[1]);
 }
 
+// Shared-memory accesses of the pixel body go through 32-bit shared-space addresses: with generic pointers the compiler rebuilds
+// the CTA's shared window base from %cluster_ctaid for every pixel (S2R + LEA in front of the first LDS of the dependency chain).
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v)); }
+template <int NREG> __device__ __forceinline__ void lds_row(uint32_t a, uint32_t (&w)[(NREG + 1) / 2])
+{
+    if (NREG == 1) { uint16_t h; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(a)); w[0] = h; }
+    else if (NREG == 2) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[0]) : "r"(a));
+    else asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w[0]), "=r"(w[(NREG + 1) / 2 - 1]) : "r"(a));
+}
+template <int NREG> __device__ __forceinline__ void sts_row(uint32_t a, const uint32_t (&w)[(NREG + 1) / 2])
+{
+    if (NREG == 1) asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)w[0]));
+    else if (NREG == 2) asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(w[0]));
+    else asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(w[0]), "r"(w[(NREG + 1) / 2 - 1]));
+}
+
 template <int NREG>
 struct VsThread {
-    uint8_t* state_l; uint32_t* stmin; uint8_t* inbox; uint8_t* inbox_right; uint8_t* inbox_left;
+    uint32_t state_s, stmin_s, inbox_s;            // shared-space addresses (state_s with the lane's byte offset folded in)
+    uint8_t* inbox_right; uint8_t* inbox_left;     // neighbours' inboxes: distributed shared memory, generic pointers
     const uint8_t* addA_l; const uint8_t* addB_l; const uint16_t* Sin_l; uint16_t* Sout_l;
     uint32_t* minC; uint16_t* rec; uint16_t* ws;
-    int Wk, Wk_max, W, xb, lane, sdx;
+    int Wk, Wk_max, W, xb, lane;
     uint32_t P1P1, P2P2, lo_mask, hi_mask;
     bool preadd;
 };
@@ -124,7 +142,7 @@ __device__ __forceinline__ void vs_fetch(const VsThread<NREG>& th, uint32_t pix,
 // neighbour CTA's hand-over, or hand one over (first row, first / last column of the strip); interior pixels compile
 // to a straight line of LDS -> step -> STS per direction.
 template <int NREG, int NDIR, bool FINAL, bool EDGE, bool FAST>
-__device__ __forceinline__ void vs_pixel(const VsThread<NREG>& th, const uint8_t* crow_l, int xl, int yy, int par, int off, uint32_t pix,
+__device__ __forceinline__ void vs_pixel(const VsThread<NREG>& th, uint32_t crow_s, int xl, int yy, int par, int off, uint32_t pix,
                                          const VsGlobals<NREG>& g, bool arrive)
 {
     constexpr int D = 64 * NREG, NW = (NREG + 1) / 2, NB = 2 * NREG;
@@ -132,42 +150,43 @@ __device__ __forceinline__ void vs_pixel(const VsThread<NREG>& th, const uint8_t
     const size_t vox = (size_t)pix * D;
     // cost, path state and minima are biased fp16x2 numbers (sgm_step.cuh): min on the ALU pipe, add on the FMA pipe
     uint32_t cw[NW], c[NREG], cP2[NREG], acc[NREG];
-    ld_row<NREG>(crow_l + xl * D, 0, cw);
+    lds_row<NREG>(crow_s + xl * D, cw);
     unpack_cost_h2<NREG>(cw, c);
 #pragma unroll
     for (int i = 0; i < NREG; ++i) cP2[i] = h2_add(c[i], th.P2P2);
     // The three directions are independent.  All previous-state rows are loaded first and all new rows stored last:
     // with the loads and stores of one direction between those of another the compiler must assume they alias and
     // serialises the three dependency chains (ncu r1h: fixed-latency "wait" stalls were the largest stall class).
-    uint8_t* st[NDIR]; uint32_t* sm[NDIR];
+    // k = 0 is the vertical direction, k = 1 the diagonal with dx = +1, k = 2 the one with dx = -1 (in both passes: which of the
+    // two is "L2" and which "L4" does not matter, only their sum leaves the kernel)
+    uint32_t st[NDIR], sm[NDIR];
     uint32_t lw[NDIR][NW], Mv[NDIR];
     bool restart[NDIR];
 #pragma unroll
     for (int k = 0; k < NDIR; ++k) {
-        const int dx = k == 0 ? 0 : (k == 1 ? th.sdx : -th.sdx);
+        constexpr int dxs[3] = {0, 1, -1};
+        const int dx = dxs[k];
         int slot = xl;
-        if (k > 0) {
-            if (dx > 0) { slot = xl - off; if (slot < 0) slot += Wk; }
-            else        { slot = xl + off; if (slot >= Wk) slot -= Wk; }
-        }
-        st[k] = th.state_l + (k * th.Wk_max + slot) * D;
-        sm[k] = th.stmin + k * th.Wk_max + slot;
+        if (dx > 0) { slot = xl - off; if (slot < 0) slot += Wk; }
+        if (dx < 0) { slot = xl + off; if (slot >= Wk) slot -= Wk; }
+        st[k] = th.state_s + (k * th.Wk_max + slot) * D;
+        sm[k] = th.stmin_s + (k * th.Wk_max + slot) * 4;
         restart[k] = false;
-        const uint8_t* src = st[k];
+        uint32_t src = st[k];
         bool boxed = false;
         if (EDGE) {
             const int x = th.xb + xl;
             restart[k] = (yy == 0) || (dx > 0 && x == 0) || (dx < 0 && x == th.W - 1);
             const bool from_left = dx > 0 && xl == 0, from_right = dx < 0 && xl == Wk - 1;
             if (!restart[k] && (from_left || from_right)) {
-                src = th.inbox + ((size_t)((yy - 1) & 1) * 2 + (from_right ? 1 : 0)) * (D + 16);
-                Mv[k] = *reinterpret_cast<const uint32_t*>(src + D);
+                src = th.inbox_s + (uint32_t)((((yy - 1) & 1) * 2 + (from_right ? 1 : 0)) * (D + 16));
+                Mv[k] = lds_u32(src + D);
                 src += lane * NB;
                 boxed = true;
             }
         }
-        if (!boxed) Mv[k] = *sm[k];
-        ld_row<NREG>(src, 0, lw[k]);
+        if (!boxed) Mv[k] = lds_u32(sm[k]);
+        lds_row<NREG>(src, lw[k]);
     }
     uint32_t pw[NDIR][NW], Mn[NDIR];
     static_assert(NDIR == 1 || NDIR == 3, "accumulator bias below assumes one or three directions");
@@ -195,9 +214,10 @@ __device__ __forceinline__ void vs_pixel(const VsThread<NREG>& th, const uint8_t
     for (int i = 0; i < NREG; ++i) acc[i] -= H2_BIAS2;
 #pragma unroll
     for (int k = 0; k < NDIR; ++k) {
-        const int dx = k == 0 ? 0 : (k == 1 ? th.sdx : -th.sdx);
-        st_row<NREG>(st[k], 0, pw[k]);
-        *sm[k] = Mn[k];                                // every lane writes the same value
+        constexpr int dxs[3] = {0, 1, -1};
+        const int dx = dxs[k];
+        sts_row<NREG>(st[k], pw[k]);
+        sts_u32(sm[k], Mn[k]);                         // every lane writes the same value
         if (EDGE) {
             // hand the path over when it leaves the strip (it continues in the neighbour's column next row)
             if (dx > 0 && xl == Wk - 1 && th.inbox_right) {
@@ -321,12 +341,12 @@ vsweep_kernel(const VsParams prm)
 
     const uint32_t P1P1 = h2_const(prm.P1), P2P2 = h2_const(prm.P2);          // fp16x2 constants (sgm_step.cuh)
     const uint32_t lo_mask = lane == 0 ? H2_BIG_LO : 0u, hi_mask = lane == 31 ? H2_BIG_HI : 0u;
-    const int sdx = prm.up ? -1 : 1;               // x direction of "direction 1" in this pass: (+1,+1) going down, (-1,-1) going up
-
     // per-thread bases with the lane's byte offset folded in
     constexpr int NB = 2 * NREG;
     VsThread<NREG> th;
-    th.state_l = state + lane * NB; th.stmin = stmin; th.inbox = inbox; th.inbox_right = inbox_right; th.inbox_left = inbox_left;
+    const uint32_t cbuf_s = smem_u32(cbuf) + lane * NB;
+    th.state_s = smem_u32(state) + lane * NB; th.stmin_s = smem_u32(stmin); th.inbox_s = smem_u32(inbox);
+    th.inbox_right = inbox_right; th.inbox_left = inbox_left;
     th.addA_l = prm.addA ? prm.addA + pair * N * D + lane * NB : nullptr;
     th.addB_l = prm.addB ? prm.addB + pair * N * D + lane * NB : nullptr;
     th.Sin_l = prm.Sin ? prm.Sin + pair * N * D + lane * NB : nullptr;
@@ -335,7 +355,7 @@ vsweep_kernel(const VsParams prm)
     th.rec = prm.rec ? prm.rec + pair * N * 4 : nullptr;
     th.ws = wsc + warp * D;
     th.Wk = Wk; th.Wk_max = Wk_max; th.W = W; th.xb = xb; th.lane = lane;
-    th.P1P1 = P1P1; th.P2P2 = P2P2; th.lo_mask = lo_mask; th.hi_mask = hi_mask; th.sdx = sdx;
+    th.P1P1 = P1P1; th.P2P2 = P2P2; th.lo_mask = lo_mask; th.hi_mask = hi_mask;
     th.preadd = 2 * (24 + prm.P2) <= 255;          // cost values are <= 24 on this path (no-wrap domain precondition)
 
     // Pixel order inside a row is free (every path slot is touched by exactly one pixel per row), so the strip is split in
@@ -356,7 +376,7 @@ vsweep_kernel(const VsParams prm)
         const int y = row_y(yy), par = yy & 1;
         if (yy > 0) cluster_wait();                // hand-overs of row yy-1 are visible; neighbours are done reading inbox[par]
         mbar_wait(&bars[par], (uint32_t)((yy >> 1) & 1));
-        const uint8_t* crow_l = cbuf + (size_t)par * Wk_max * D + lane * NB;
+        const uint32_t crow_l = cbuf_s + (uint32_t)(par * Wk_max * D);
         const uint32_t rowpix = (uint32_t)y * (uint32_t)W + (uint32_t)xb;
         // global rows (horizontal volumes / the other pass's sum) are fetched PD pixels ahead: with only 20 warps per SM an
         // L2 miss (~2 us) is not hidden by other warps (ncu r1g: 27 % of the stall samples of the down pass sat on the first
@@ -368,18 +388,17 @@ vsweep_kernel(const VsParams prm)
 #pragma unroll
         for (int u = 0; u < PD; ++u)
             if (wsub + u * HW < cnt) vs_fetch<NREG, FINAL, FAST>(th, rowpix + xl_of(wsub + u * HW), gq[u]);
-        if (wsub >= cnt) cluster_arrive_relaxed();  // a warp without pixels has nothing to hand over
+        // warps 0 and HW publish the row's hand-overs from inside their first (edge) pixel; every other warp has nothing to
+        // publish and arrives right away
+        if (wsub != 0 || cnt == 0) cluster_arrive_relaxed();
         for (int i0 = wsub; i0 < cnt; i0 += PD * HW) {
 #pragma unroll
             for (int u = 0; u < PD; ++u) {
                 const int i = i0 + u * HW;
                 if (i < cnt) {
                     const int xl = xl_of(i);
-                    if (yy == 0 || xl == 0 || xl == Wk - 1) vs_pixel<NREG, NDIR, FINAL, true, FAST>(th, crow_l, xl, yy, par, off, rowpix + xl, gq[u], i == wsub);
-                    else {
-                        if (i == wsub) cluster_arrive_relaxed();
-                        vs_pixel<NREG, NDIR, FINAL, false, FAST>(th, crow_l, xl, yy, par, off, rowpix + xl, gq[u], false);
-                    }
+                    if (yy == 0 || xl == 0 || xl == Wk - 1) vs_pixel<NREG, NDIR, FINAL, true, FAST>(th, crow_l, xl, yy, par, off, rowpix + xl, gq[u], i == 0);
+                    else vs_pixel<NREG, NDIR, FINAL, false, FAST>(th, crow_l, xl, yy, par, off, rowpix + xl, gq[u], false);
                     if (i + PD * HW < cnt) vs_fetch<NREG, FINAL, FAST>(th, rowpix + xl_of(i + PD * HW), gq[u]);
                 }
             }
