@@ -300,7 +300,7 @@ hsweep_tma_kernel(const SweepParams prm)
 #pragma unroll
             for (int i = 0; i < NREG; ++i) cP2[i] = h2_add(cc[i], P2h);
             // at the path start the (biased) zero state with M = 0 makes the step return L = C; the minimum is then forced to 0
-            const uint32_t m = sgm_step_h2<NREG>(cP2, Lr, M, P1h, P2h, lo_mask, hi_mask, Ln);
+            const uint32_t m = sgm_step_h2<NREG>(cP2, Lr, M * 0x10001u, P1h, P2h, lo_mask, hi_mask, Ln);
             M = first ? ZERO_B : m;
             first = false;
 #pragma unroll

@@ -96,10 +96,10 @@ __device__ __forceinline__ void unpack_cost_h2(const uint32_t* w, uint32_t (&c)[
 }
 // biased halves (values <= 255) -> bytes: pack_cost<NREG>() as it is (it keeps the low byte of every half)
 
-// c, cP2 = c + P2, Lpre biased; M = biased minimum of Lpre in the low 16 bits; P1h/P2h = h2_const(P1/P2);
-// lo_mask / hi_mask = H2_BIG_LO in lane 0 / H2_BIG_HI in lane 31, else 0.  Returns the biased minimum of L.
+// c, cP2 = c + P2, Lpre biased; MM = biased minimum of Lpre in BOTH halves; P1h/P2h = h2_const(P1/P2);
+// lo_mask / hi_mask = H2_BIG_LO in lane 0 / H2_BIG_HI in lane 31, else 0.  Returns the biased minimum of L (low 16 bits).
 template <int NREG>
-__device__ __forceinline__ uint32_t sgm_step_h2(const uint32_t (&cP2)[NREG], const uint32_t (&Lpre)[NREG], uint32_t M, uint32_t P1h,
+__device__ __forceinline__ uint32_t sgm_step_h2(const uint32_t (&cP2)[NREG], const uint32_t (&Lpre)[NREG], uint32_t MM, uint32_t P1h,
                                                 uint32_t P2h, uint32_t lo_mask, uint32_t hi_mask, uint32_t (&L)[NREG])
 {
     uint32_t q[NREG + 1];
@@ -109,7 +109,7 @@ __device__ __forceinline__ uint32_t sgm_step_h2(const uint32_t (&cP2)[NREG], con
 #pragma unroll
     for (int i = 1; i < NREG; ++i) q[i] = __byte_perm(Lpre[i - 1], Lpre[i], 0x5432);
     q[NREG] = __byte_perm(Lpre[NREG - 1], dn, 0x5432) | hi_mask;
-    const uint32_t K = h2_add(M * 0x10001u, P2h);                     // 1024 + M + P2
+    const uint32_t K = h2_add(MM, P2h);                               // 1024 + M + P2
     uint32_t m = 0xFFFFFFFFu;
 #pragma unroll
     for (int i = 0; i < NREG; ++i) {

@@ -194,14 +194,15 @@ __device__ __forceinline__ void vs_pixel(const VsThread<NREG>& th, uint32_t crow
 #pragma unroll
     for (int k = 0; k < NDIR; ++k) {
         uint32_t L[NREG];
-        Mn[k] = H2_BIAS2 & 0xFFFFu;                    // biased 0: the minimum a restarted path hands to its next step
+        Mn[k] = H2_BIAS2;                              // biased 0 (both halves): the minimum a restarted path hands to its next step
         if (EDGE && restart[k]) {
 #pragma unroll
             for (int i = 0; i < NREG; ++i) L[i] = c[i];
         } else {
             uint32_t Lpre[NREG];
             unpack_cost_h2<NREG>(lw[k], Lpre);
-            Mn[k] = sgm_step_h2<NREG>(cP2, Lpre, Mv[k], th.P1P1, th.P2P2, th.lo_mask, th.hi_mask, L);
+            // minima travel duplicated in both halves (state, inbox), ready for the fp16x2 add inside the step
+            Mn[k] = sgm_step_h2<NREG>(cP2, Lpre, Mv[k], th.P1P1, th.P2P2, th.lo_mask, th.hi_mask, L) * 0x10001u;
         }
         pack_cost<NREG>(L, pw[k]);
         // sum of the directions, still on the FMA pipe: -1024*(NDIR-1) + sum(1024 + L_k) = 1024 + sum(L_k) < 2048, every
@@ -369,7 +370,8 @@ vsweep_kernel(const VsParams prm)
     const int wsub = warp % HW;
     const bool upper = warp >= HW;
     const int n_lo = (Wk + 1) / 2, cnt = upper ? Wk - n_lo : n_lo;
-    auto xl_of = [&](int i) { return upper ? Wk - 1 - i : i; };
+    const int xfirst = upper ? Wk - 1 : 0, xstep = upper ? -1 : 1;
+    auto xl_of = [&](int i) { return xfirst + xstep * i; };
 
     int off = 0;                                   // yy mod Wk, kept incrementally
     for (int yy = 0; yy < H; ++yy) {
@@ -391,15 +393,26 @@ vsweep_kernel(const VsParams prm)
         // warps 0 and HW publish the row's hand-overs from inside their first (edge) pixel; every other warp has nothing to
         // publish and arrives right away
         if (wsub != 0 || cnt == 0) cluster_arrive_relaxed();
-        for (int i0 = wsub; i0 < cnt; i0 += PD * HW) {
+        if (yy == 0) {
+            // first row: every path starts here (edge body for every pixel); one row, so no software pipelining
+            for (int i = wsub; i < cnt; i += HW) {
+                const int xl = xl_of(i);
+                if (i != wsub) vs_fetch<NREG, FINAL, FAST>(th, rowpix + xl, gq[0]);
+                vs_pixel<NREG, NDIR, FINAL, true, FAST>(th, crow_l, xl, yy, par, off, rowpix + xl, gq[0], i == 0);
+            }
+        } else {
+            // the only edge pixels of a later row are xl = 0 and xl = Wk-1: pixel i = 0 of warps 0 and HW, i.e. ring slot 0 of
+            // their first round
+            for (int i0 = wsub; i0 < cnt; i0 += PD * HW) {
 #pragma unroll
-            for (int u = 0; u < PD; ++u) {
-                const int i = i0 + u * HW;
-                if (i < cnt) {
-                    const int xl = xl_of(i);
-                    if (yy == 0 || xl == 0 || xl == Wk - 1) vs_pixel<NREG, NDIR, FINAL, true, FAST>(th, crow_l, xl, yy, par, off, rowpix + xl, gq[u], i == 0);
-                    else vs_pixel<NREG, NDIR, FINAL, false, FAST>(th, crow_l, xl, yy, par, off, rowpix + xl, gq[u], false);
-                    if (i + PD * HW < cnt) vs_fetch<NREG, FINAL, FAST>(th, rowpix + xl_of(i + PD * HW), gq[u]);
+                for (int u = 0; u < PD; ++u) {
+                    const int i = i0 + u * HW;
+                    if (i < cnt) {
+                        const int xl = xl_of(i);
+                        if (u == 0 && i == 0) vs_pixel<NREG, NDIR, FINAL, true, FAST>(th, crow_l, xl, yy, par, off, rowpix + xl, gq[u], true);
+                        else vs_pixel<NREG, NDIR, FINAL, false, FAST>(th, crow_l, xl, yy, par, off, rowpix + xl, gq[u], false);
+                        if (i + PD * HW < cnt) vs_fetch<NREG, FINAL, FAST>(th, rowpix + xl_of(i + PD * HW), gq[u]);
+                    }
                 }
             }
         }
