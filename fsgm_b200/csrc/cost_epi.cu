@@ -224,9 +224,8 @@ epi_cost_fused_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restr
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* raw_row = reinterpret_cast<uint32_t*>(smem_raw);                              // [NPIX][D4]
     uint32_t* hring = raw_row + NPIX * D4;                                                  // [5][FC_TX][D4]
-    double* geo = reinterpret_cast<double*>(hring + 5 * FC_TX * D4);                        // [NPIX][5]
-    uint32_t* gcen = reinterpret_cast<uint32_t*>(geo + NPIX * 5);                           // [NPIX]
-    uint32_t* gslow = gcen + NPIX;                                                          // [NPIX] NaN-capable pixel
+    double* geo = reinterpret_cast<double*>(hring + 5 * FC_TX * D4);                        // [2][NPIX][5]
+    uint32_t* gcen = reinterpret_cast<uint32_t*>(geo + 2 * NPIX * 5);                       // [2][NPIX]
 
     const size_t N = (size_t)W * H;
     const int pair = blockIdx.z, x0 = blockIdx.x * FC_TX, y0 = blockIdx.y * FC_TY;
@@ -246,28 +245,44 @@ epi_cost_fused_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restr
 #pragma unroll
     for (int k = 0; k < XP; ++k) { vlo[k] = 0; vhi[k] = 0; }
 
+    // Geometry of a row is staged in a double buffer: the global loads for row r+1 are issued before the raw-cost phase of row r
+    // and written to shared memory after its box phase, so their latency hides under the arithmetic and a row needs two
+    // barriers instead of three.  `slow` = some pixel of the strip row can produce NaN (checked path, CTA-uniform branch).
+    auto load_geo = [&](int r, double (&a)[5], uint32_t& cen) {
+        const int yc = min(max(r, 0), H - 1), xc = min(max(x0 - 2 + tid, 0), W - 1);
+        const size_t p = (size_t)yc * W + xc;
+        a[0] = PdX[p]; a[1] = PdY[p]; a[2] = DrX[p]; a[3] = DrY[p]; a[4] = Op[p];
+        cen = cen1[pair * N + p];
+    };
+    auto store_geo = [&](int buf, const double (&a)[5], uint32_t cen) -> int {
+        double* g = geo + (buf * NPIX + tid) * 5;
+        // doubled constants: w = 2*(b + (off*vz)*u) = 2b + ((2 off)*vz)*u exactly
+        g[0] = __dmul_rn(__dsub_rn(a[0], 1.0), 2.0); g[1] = __dmul_rn(__dsub_rn(a[1], 1.0), 2.0);
+        g[2] = a[2]; g[3] = a[3]; g[4] = __dmul_rn(a[4], 2.0);
+        gcen[buf * NPIX + tid] = cen;
+        const bool fin = isfinite(a[0]) && isfinite(a[1]) && isfinite(a[2]) && isfinite(a[3]) && fabs(a[4]) <= 1e300;
+        return fin ? 0 : 1;
+    };
+    double ga[5] = {0, 0, 0, 0, 0};
+    uint32_t gc = 0;
+    int slow_mine = 0;
+    if (tid < NPIX) { load_geo(y0 - 2, ga, gc); slow_mine = store_geo(0, ga, gc); }
+    int slow = __syncthreads_or(slow_mine);
+
     for (int r = y0 - 2; r < yend + 2; ++r) {
-        const int yc = min(max(r, 0), H - 1);
-        // stage the strip's geometry for this row
-        if (tid < NPIX) {
-            const int xc = min(max(x0 - 2 + tid, 0), W - 1);
-            const size_t p = (size_t)yc * W + xc;
-            const double a0 = PdX[p], a1 = PdY[p], a2 = DrX[p], a3 = DrY[p], a4 = Op[p];
-            // doubled constants: w = 2*(b + (off*vz)*u) = 2b + ((2 off)*vz)*u exactly
-            geo[tid * 5 + 0] = __dmul_rn(__dsub_rn(a0, 1.0), 2.0); geo[tid * 5 + 1] = __dmul_rn(__dsub_rn(a1, 1.0), 2.0);
-            geo[tid * 5 + 2] = a2; geo[tid * 5 + 3] = a3; geo[tid * 5 + 4] = __dmul_rn(a4, 2.0);
-            gcen[tid] = cen1[pair * N + p];
-            const bool fin = isfinite(a0) && isfinite(a1) && isfinite(a2) && isfinite(a3) && fabs(a4) <= 1e300;
-            gslow[tid] = fin ? 0u : 1u;
-        }
-        __syncthreads();
+        const int buf = (r - (y0 - 2)) & 1;
+        const bool more = r + 1 < yend + 2;
+        if (tid < NPIX && more) load_geo(r + 1, ga, gc);
+        const double* geo_r = geo + buf * NPIX * 5;
+        const uint32_t* gcen_r = gcen + buf * NPIX;
         // (1) raw cost of NPIX pixels x D labels
-        for (int i = i0; i < NPIX; i += IPT) {
-            const double bx = geo[i * 5], by = geo[i * 5 + 1], ux = geo[i * 5 + 2], uy = geo[i * 5 + 3], off = geo[i * 5 + 4];
-            const uint32_t c1 = gcen[i];
-            uint32_t packed = 0;
-            const double vzs[4] = {vz0, vz1, vz2, vz3};
-            if (gslow[i] == 0) {                       // uniform across the threads that share pixel i
+        if (!slow) {
+#pragma unroll 3
+            for (int i = i0; i < NPIX; i += IPT) {
+                const double bx = geo_r[i * 5], by = geo_r[i * 5 + 1], ux = geo_r[i * 5 + 2], uy = geo_r[i * 5 + 3], off = geo_r[i * 5 + 4];
+                const uint32_t c1 = gcen_r[i];
+                uint32_t packed = 0;
+                const double vzs[4] = {vz0, vz1, vz2, vz3};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const double t = __dmul_rn(off, vzs[j]);
@@ -275,7 +290,14 @@ epi_cost_fused_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restr
                     const uint32_t y2 = ref_round_clamp_w(__dadd_rn(by, __dmul_rn(t, uy)), hmax);
                     packed |= (uint32_t)__popc(c1 ^ __ldg(reinterpret_cast<const uint32_t*>(c2b + (y2 * W4 + x2 * 4u)))) << (8 * j);
                 }
-            } else {
+                raw_row[i * D4 + q] = packed;
+            }
+        } else {
+            for (int i = i0; i < NPIX; i += IPT) {
+                const double bx = geo_r[i * 5], by = geo_r[i * 5 + 1], ux = geo_r[i * 5 + 2], uy = geo_r[i * 5 + 3], off = geo_r[i * 5 + 4];
+                const uint32_t c1 = gcen_r[i];
+                uint32_t packed = 0;
+                const double vzs[4] = {vz0, vz1, vz2, vz3};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const double t = __dmul_rn(off, vzs[j]);
@@ -284,8 +306,8 @@ epi_cost_fused_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restr
                     const uint32_t y2 = (wy != wy) ? 0u : ref_round_clamp_w(wy, hmax);
                     packed |= (uint32_t)__popc(c1 ^ __ldg(reinterpret_cast<const uint32_t*>(c2b + (y2 * W4 + x2 * 4u)))) << (8 * j);
                 }
+                raw_row[i * D4 + q] = packed;
             }
-            raw_row[i * D4 + q] = packed;
         }
         __syncthreads();
         // (2) horizontal 5-sums by a sliding window over this thread's XP consecutive columns; vertical 5-sums as
@@ -306,13 +328,14 @@ epi_cost_fused_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restr
             vhi[k] += ((h >> 8) & 0x00FF00FFu) - ((old >> 8) & 0x00FF00FFu);
             if (emit && x0 + i0 * XP + k < W) crow[k * D4] = box_norm4_fast(vlo[k], vhi[k]);
         }
-        __syncthreads();
+        slow_mine = (tid < NPIX && more) ? store_geo(buf ^ 1, ga, gc) : 0;
+        slow = __syncthreads_or(slow_mine);           // also: everyone is done with raw_row
     }
 }
 
 static size_t fused_cost_smem(int D4)
 {
-    return (size_t)(FC_TX + 4) * D4 * 4 + (size_t)5 * FC_TX * D4 * 4 + (size_t)(FC_TX + 4) * 5 * 8 + (size_t)(FC_TX + 4) * 8 + 64;
+    return (size_t)(FC_TX + 4) * D4 * 4 + (size_t)5 * FC_TX * D4 * 4 + 2 * ((size_t)(FC_TX + 4) * 5 * 8 + (size_t)(FC_TX + 4) * 4) + 64;
 }
 
 // returns FSGM_OK and sets *done = true if the fused kernel handles this label count
