@@ -214,8 +214,16 @@ __device__ __forceinline__ uint32_t box_norm4_fast(uint32_t lo, uint32_t hi)   /
     return __byte_perm(__byte_perm(p0, p1, 0x0062), __byte_perm(p2, p3, 0x0062), 0x5410);
 }
 
+// measured (60 pairs, cost stage): 4 CTAs/SM + full unroll 11.17 ms, 4 + unroll 3 11.75, 3 CTAs/SM 11.29, no unroll at 108 registers 13.9
+#ifndef FSGM_FC_MINB
+#define FSGM_FC_MINB 4
+#endif
+#ifndef FSGM_FC_UNROLL
+#define FSGM_FC_UNROLL 9
+#endif
+constexpr int FC_UNROLL = FSGM_FC_UNROLL;
 template <int D4>      // D = 4*D4 labels, D4 in {16, 32, 64}
-__global__ void __launch_bounds__(FC_THREADS)
+__global__ void __launch_bounds__(FC_THREADS, FSGM_FC_MINB)
 epi_cost_fused_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restrict__ cen2,
                       const double* __restrict__ Pd0, const double* __restrict__ dirn, const double* __restrict__ O,
                       const double* __restrict__ vz, int W, int H, int FC_TY, uint8_t* __restrict__ C)
@@ -277,7 +285,7 @@ epi_cost_fused_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restr
         const uint32_t* gcen_r = gcen + buf * NPIX;
         // (1) raw cost of NPIX pixels x D labels
         if (!slow) {
-#pragma unroll 3
+#pragma unroll FC_UNROLL
             for (int i = i0; i < NPIX; i += IPT) {
                 const double bx = geo_r[i * 5], by = geo_r[i * 5 + 1], ux = geo_r[i * 5 + 2], uy = geo_r[i * 5 + 3], off = geo_r[i * 5 + 4];
                 const uint32_t c1 = gcen_r[i];

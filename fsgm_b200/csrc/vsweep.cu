@@ -384,7 +384,8 @@ vsweep_kernel(const VsParams prm)
         // L2 miss (~2 us) is not hidden by other warps (ncu r1g: 27 % of the stall samples of the down pass sat on the first
         // use of the horizontal-volume row).  The ring is indexed statically (inner loop unrolled by PD): copying a register
         // that is still waiting for its load would stall on the copy, which is exactly what a rotating ring does.
-        // (Requesting the next row's first pixels before the row-end barrier was measured slower: 21.9 -> 23.3 ms per 60 pairs.)
+        // (Requesting the next row's first pixels before the row-end barrier was measured slower, 21.9 -> 23.3 ms per 60 pairs;
+        // an L2 prefetch of the same rows at that point changes nothing.)
         constexpr int PD = FINAL ? 2 : 4;
         VsGlobals<NREG> gq[PD];
 #pragma unroll
