@@ -270,10 +270,9 @@ hsweep_tma_kernel(const SweepParams prm)
     __syncwarp();
 
     // biased fp16x2 arithmetic (sgm_step.cuh): min on the ALU pipe, additions on the FMA pipe
-    const uint32_t lo_mask = (lane == 0) ? H2_BIG_LO : 0u;
-    const uint32_t hi_mask = (lane == 31) ? H2_BIG_HI : 0u;
+    const uint32_t sel_lo = h2_edge_sel_lo(lane), sel_hi = h2_edge_sel_hi(lane);
     const uint32_t P1h = h2_const(prm.P1), P2h = h2_const(prm.P2);
-    constexpr uint32_t ZERO_B = H2_BIAS2 & 0xFFFFu;                      // biased 0
+    constexpr uint32_t ZERO_B = H2_BIAS2;                                // biased 0 in both halves (minima travel duplicated)
     uint32_t Lr[NREG];
 #pragma unroll
     for (int i = 0; i < NREG; ++i) Lr[i] = H2_BIAS2;
@@ -300,7 +299,7 @@ hsweep_tma_kernel(const SweepParams prm)
 #pragma unroll
             for (int i = 0; i < NREG; ++i) cP2[i] = h2_add(cc[i], P2h);
             // at the path start the (biased) zero state with M = 0 makes the step return L = C; the minimum is then forced to 0
-            const uint32_t m = sgm_step_h2<NREG>(cP2, Lr, M * 0x10001u, P1h, P2h, lo_mask, hi_mask, Ln);
+            const uint32_t m = sgm_step_h2<NREG>(cP2, Lr, M, P1h, P2h, sel_lo, sel_hi, Ln);
             M = first ? ZERO_B : m;
             first = false;
 #pragma unroll

@@ -185,13 +185,14 @@ static int aggregate_and_wta(fsgm_ctx* c, int n, const uint8_t* C, const uint8_t
         const int hd[2] = {0, 4};
         uint8_t* Lh[2] = {Lh0, Lh1};
         FSGM_TRY(launch_sweeps(c, nf, C, I1, W, H, D, P1, P2, 0, cmax, hd, o.total_pass == 2 ? 2 : 1, Lh));
+        int biased = 0;                    // the FAST cluster passes keep their sums as biased fp16 bit patterns (vsweep.cu)
         if (o.total_pass == 2) {
-            FSGM_TRY(launch_vsweep(c, nf, cs, ndir, false, C, Lh0, Lh1, nullptr, S1, nullptr, nullptr, W, H, D, P1, P2, 0));
-            FSGM_TRY(launch_vsweep(c, nf, cs, ndir, true, C, nullptr, nullptr, S1, Sp16, minC, rec, W, H, D, P1, P2, 1));
+            FSGM_TRY(launch_vsweep(c, nf, cs, ndir, false, C, Lh0, Lh1, nullptr, S1, nullptr, nullptr, W, H, D, P1, P2, 0, &biased));
+            FSGM_TRY(launch_vsweep(c, nf, cs, ndir, true, C, nullptr, nullptr, S1, Sp16, minC, rec, W, H, D, P1, P2, 1, &biased));
         } else {
-            FSGM_TRY(launch_vsweep(c, nf, cs, ndir, true, C, Lh0, nullptr, nullptr, Sp16, minC, rec, W, H, D, P1, P2, 0));
+            FSGM_TRY(launch_vsweep(c, nf, cs, ndir, true, C, Lh0, nullptr, nullptr, Sp16, minC, rec, W, H, D, P1, P2, 0, &biased));
         }
-        FSGM_TRY(launch_vs_finalize(c, nf, rec, minC, O, W, H, D, o.subpixel, o.vz_to_disp, vMax, bestD));
+        FSGM_TRY(launch_vs_finalize(c, nf, rec, minC, O, W, H, D, o.subpixel, o.vz_to_disp, vMax, biased, bestD));
     }
     if (ng) {
         int dirs[8];
@@ -289,11 +290,13 @@ static int epi_pipeline_waves(fsgm_ctx* c, int n, int cs, const uint8_t* I1, con
         return launch_sweeps(c, m, C + p0 * V, I1 + p0 * N, W, H, D, P1, P2, 0, 24, hd, 2, Lh);
     };
     auto back = [&](int p0, int m) -> int {
+        int biased = 0;
         FSGM_TRY(launch_vsweep(c, m, cs, ndir, false, C + p0 * V, Lh0 + p0 * V, Lh1 + p0 * V, nullptr, S1 + p0 * V, nullptr, nullptr,
-                               W, H, D, P1, P2, 0));
+                               W, H, D, P1, P2, 0, &biased));
         FSGM_TRY(launch_vsweep(c, m, cs, ndir, true, C + p0 * V, nullptr, nullptr, S1 + p0 * V, nullptr, minC + p0 * N, rec + p0 * N * 4,
-                               W, H, D, P1, P2, 1));
-        return launch_vs_finalize(c, m, rec + p0 * N * 4, minC + p0 * N, O + p0 * N, W, H, D, o.subpixel, o.vz_to_disp, vMax, bestD + p0 * N);
+                               W, H, D, P1, P2, 1, &biased));
+        return launch_vs_finalize(c, m, rec + p0 * N * 4, minC + p0 * N, O + p0 * N, W, H, D, o.subpixel, o.vz_to_disp, vMax, biased,
+                                  bestD + p0 * N);
     };
     const int waves = (nf + K - 1) / K;
     FSGM_TRY(front(0, std::min(K, nf), A));

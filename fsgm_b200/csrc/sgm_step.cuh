@@ -67,13 +67,10 @@ __device__ __forceinline__ uint32_t sgm_step_u16(const uint32_t (&c)[NREG], cons
 //     no ALU-pipe instruction (the integer form spends a VIADDMNMX on it);
 //   * bytes <-> biased halves cost nothing extra: unpacking is the same PRMT with 0x64 as the high byte, packing takes the
 //     low bytes as before.
-// Per u16x2 register the ALU pipe issues 3 instructions instead of 4 and the FMA pipe 3 instead of 1.  Every intermediate is an
-// integer below 2048 in magnitude, so the fp16 arithmetic is exact and the results are bit-identical to the integer step.
+// Every intermediate is an integer below 2048 in magnitude, so the fp16 arithmetic is exact and the results are bit-identical to the integer step.
 // ---------------------------------------------------------------------------------------------------------------------------
 constexpr uint32_t H2_BIAS2 = 0x64006400u;       // half2(1024, 1024)
 constexpr uint32_t H2_NEG1 = 0xBC00BC00u;        // half2(-1, -1)
-constexpr uint32_t H2_BIG_LO = 0x00000800u;      // OR-ed into a biased half: exponent 27, value >= 4096 — never wins a min
-constexpr uint32_t H2_BIG_HI = 0x08000000u;
 
 __device__ __forceinline__ uint32_t h2_add(uint32_t a, uint32_t b) { uint32_t r; asm("add.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 __device__ __forceinline__ uint32_t h2_sub(uint32_t a, uint32_t b) { uint32_t r; asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
@@ -96,29 +93,40 @@ __device__ __forceinline__ void unpack_cost_h2(const uint32_t* w, uint32_t (&c)[
 }
 // biased halves (values <= 255) -> bytes: pack_cost<NREG>() as it is (it keeps the low byte of every half)
 
-// c, cP2 = c + P2, Lpre biased; MM = biased minimum of Lpre in BOTH halves; P1h/P2h = h2_const(P1/P2);
-// lo_mask / hi_mask = H2_BIG_LO in lane 0 / H2_BIG_HI in lane 31, else 0.  Returns the biased minimum of L (low 16 bits).
+// cP2 = C + P2 and Lpre biased; MM = biased minimum of Lpre in BOTH halves; P1h/P2h = h2_const(P1/P2).
+// sel_lo / sel_hi = h2_edge_sel_lo/hi(lane): PRMT selectors of the two words that cross the lane boundary.  Label 0 has no
+// neighbour below and label D-1 none above: lane 0 / lane 31 select the label's OWN value there instead of the shuffled one,
+// which never wins (min(l + P1, l) = l), so no "infinity" has to be OR-ed in.
+// Instruction diet (the aggregation kernels are bound by instruction issue): P1 is added to the whole previous row once, the
+// neighbour words are built from that row, and min(Lpre(d-1)+P1, Lpre(d+1)+P1, Lpre(d)) is ONE 3-input VIMNMX3.U16x2; the
+// minimum over the lane's labels is folded to both halves (PRMT swap + VIMNMX) so that the 32-bit CREDUX.MIN of the bit
+// patterns returns it duplicated, ready to be the next step's MM.  Per u16x2 register: 1 ALU-pipe + 3 FMA-pipe instructions.
+// Returns the biased minimum of L in both halves.
+__device__ __forceinline__ uint32_t h2_edge_sel_lo(int lane) { return lane == 0 ? 0x5454u : 0x5432u; }
+__device__ __forceinline__ uint32_t h2_edge_sel_hi(int lane) { return lane == 31 ? 0x3232u : 0x5432u; }
+
 template <int NREG>
 __device__ __forceinline__ uint32_t sgm_step_h2(const uint32_t (&cP2)[NREG], const uint32_t (&Lpre)[NREG], uint32_t MM, uint32_t P1h,
-                                                uint32_t P2h, uint32_t lo_mask, uint32_t hi_mask, uint32_t (&L)[NREG])
+                                                uint32_t P2h, uint32_t sel_lo, uint32_t sel_hi, uint32_t (&L)[NREG])
 {
-    uint32_t q[NREG + 1];
-    const uint32_t up = __shfl_up_sync(0xffffffffu, Lpre[NREG - 1], 1);
-    const uint32_t dn = __shfl_down_sync(0xffffffffu, Lpre[0], 1);
-    q[0] = __byte_perm(up, Lpre[0], 0x5432) | lo_mask;               // (label 2i-1, label 2i)
+    uint32_t Lp[NREG], q[NREG + 1];
 #pragma unroll
-    for (int i = 1; i < NREG; ++i) q[i] = __byte_perm(Lpre[i - 1], Lpre[i], 0x5432);
-    q[NREG] = __byte_perm(Lpre[NREG - 1], dn, 0x5432) | hi_mask;
+    for (int i = 0; i < NREG; ++i) Lp[i] = h2_add(Lpre[i], P1h);      // Lpre + P1
+    const uint32_t up = __shfl_up_sync(0xffffffffu, Lp[NREG - 1], 1);
+    const uint32_t dn = __shfl_down_sync(0xffffffffu, Lp[0], 1);
+    q[0] = __byte_perm(up, Lp[0], sel_lo);                            // (label 2i-1, label 2i) + P1
+#pragma unroll
+    for (int i = 1; i < NREG; ++i) q[i] = __byte_perm(Lp[i - 1], Lp[i], 0x5432);
+    q[NREG] = __byte_perm(Lp[NREG - 1], dn, sel_hi);
     const uint32_t K = h2_add(MM, P2h);                               // 1024 + M + P2
     uint32_t m = 0xFFFFFFFFu;
 #pragma unroll
     for (int i = 0; i < NREG; ++i) {
-        const uint32_t nb = __vminu2(q[i], q[i + 1]);                 // min(Lpre(d-1), Lpre(d+1))
-        const uint32_t b = __vminu2(h2_add(nb, P1h), Lpre[i]);        // min(nb + P1, Lpre(d))
+        const uint32_t b = __vminu2(__vminu2(q[i], q[i + 1]), Lpre[i]);   // min(Lpre(d-1) + P1, Lpre(d+1) + P1, Lpre(d))
         L[i] = h2_sub(cP2[i], h2_relu_diff(K, b));                    // (C + P2) - relu(P2 + M - b)
         m = __vminu2(m, L[i]);
     }
-    m = min(m & 0xFFFFu, m >> 16);
+    m = __vminu2(m, __byte_perm(m, m, 0x1032));
     return __reduce_min_sync(0xffffffffu, m);
 }
 

@@ -43,6 +43,7 @@ struct VsParams {
     uint16_t* rec;               //        [n][N][4] = argmin, Sp[argmin-1], Sp[argmin+1] (0 if argmin == D-1), Sp[0]
     int W, H, Wk, P1, P2;
     int up;                      // 0: rows 0..H-1 with directions (0,+1)(+1,+1)(-1,+1); 1: rows H-1..0, negated
+    uint32_t sin_bias;           // H2_BIAS2 when Sin was written by a FAST first pass (biased fp16 bit patterns), else 0
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -112,7 +113,8 @@ struct VsThread {
     const uint8_t* addA_l; const uint8_t* addB_l; const uint16_t* Sin_l; uint16_t* Sout_l;
     uint32_t* minC; uint16_t* rec; uint16_t* ws;
     int Wk, Wk_max, W, xb, lane;
-    uint32_t P1P1, P2P2, lo_mask, hi_mask;
+    uint32_t P1P1, P2P2, sel_lo, sel_hi;
+    uint32_t sin_bias;
     bool preadd;
 };
 
@@ -123,6 +125,10 @@ struct VsGlobals { uint32_t a[(NREG + 1) / 2], b[(NREG + 1) / 2], s[NREG]; };
 // FAST = the operand configuration of the standard two-pass run is known at compile time: the first pass (!FINAL) adds both
 // horizontal volumes (byte-wise pre-add valid) and writes the u16 sum; the second (FINAL) adds that sum and does WTA with no
 // Sp dump.  Every other combination (single pass, 4 paths with one horizontal volume, stage dumps) takes the run-time checks.
+// The FAST passes never leave the biased fp16 domain: the intermediate sum volume holds the bit patterns 0x6400 | s (s < 1024:
+// at most 8 * (24 + P2) with P2 <= 103), the second pass adds them as halves and runs winner-take-all on the patterns, which
+// order like the sums; the bias comes off the three values per pixel that leave the kernel (minC here, the subpixel
+// neighbours in vs_finalize_kernel).
 template <int NREG, bool FINAL, bool FAST>
 __device__ __forceinline__ void vs_fetch(const VsThread<NREG>& th, uint32_t pix, VsGlobals<NREG>& g)
 {
@@ -190,7 +196,9 @@ __device__ __forceinline__ void vs_pixel(const VsThread<NREG>& th, uint32_t crow
     }
     uint32_t pw[NDIR][NW], Mn[NDIR];
     static_assert(NDIR == 1 || NDIR == 3, "accumulator bias below assumes one or three directions");
-    constexpr uint32_t ACC0 = 0xE800E800u;             // half2(-2048) = -1024 * (NDIR - 1) for three directions
+    // FAST: -1024 * NDIR, so that adding one more biased operand (horizontal rows / the first pass's sum) gives 1024 + total;
+    // otherwise -1024 * (NDIR - 1): the sum of the directions alone is 1024 + sum and is turned into an integer below
+    constexpr uint32_t ACC0 = FAST ? (NDIR == 3 ? 0xEA00EA00u : 0xE400E400u) : 0xE800E800u;
 #pragma unroll
     for (int k = 0; k < NDIR; ++k) {
         uint32_t L[NREG];
@@ -202,17 +210,19 @@ __device__ __forceinline__ void vs_pixel(const VsThread<NREG>& th, uint32_t crow
             uint32_t Lpre[NREG];
             unpack_cost_h2<NREG>(lw[k], Lpre);
             // minima travel duplicated in both halves (state, inbox), ready for the fp16x2 add inside the step
-            Mn[k] = sgm_step_h2<NREG>(cP2, Lpre, Mv[k], th.P1P1, th.P2P2, th.lo_mask, th.hi_mask, L) * 0x10001u;
+            Mn[k] = sgm_step_h2<NREG>(cP2, Lpre, Mv[k], th.P1P1, th.P2P2, th.sel_lo, th.sel_hi, L);
         }
         pack_cost<NREG>(L, pw[k]);
         // sum of the directions, still on the FMA pipe: -1024*(NDIR-1) + sum(1024 + L_k) = 1024 + sum(L_k) < 2048, every
         // partial sum is an integer of magnitude <= 2048
 #pragma unroll
-        for (int i = 0; i < NREG; ++i) acc[i] = k == 0 ? (NDIR == 1 ? L[i] : h2_add(L[i], ACC0)) : h2_add(acc[i], L[i]);
+        for (int i = 0; i < NREG; ++i) acc[i] = k == 0 ? ((NDIR == 1 && !FAST) ? L[i] : h2_add(L[i], ACC0)) : h2_add(acc[i], L[i]);
     }
     // biased half -> integer u16x2
+    if (!FAST) {
 #pragma unroll
-    for (int i = 0; i < NREG; ++i) acc[i] -= H2_BIAS2;
+        for (int i = 0; i < NREG; ++i) acc[i] -= H2_BIAS2;
+    }
 #pragma unroll
     for (int k = 0; k < NDIR; ++k) {
         constexpr int dxs[3] = {0, 1, -1};
@@ -237,7 +247,17 @@ __device__ __forceinline__ void vs_pixel(const VsThread<NREG>& th, uint32_t crow
     // after those would wait for them to reach L2)
     if (EDGE && arrive) cluster_arrive();
     const bool hasA = FAST ? !FINAL : th.addA_l != nullptr, hasB = FAST ? !FINAL : th.addB_l != nullptr;
-    if (hasA && hasB && (FAST || th.preadd)) {
+    if (FAST) {
+        if (!FINAL) {
+            // both horizontal rows: their byte-wise sum cannot carry (2*(cmax+P2) <= 255); add, unpack once, stay biased
+            uint32_t ab[NW], t[NREG];
+#pragma unroll
+            for (int i = 0; i < NW; ++i) ab[i] = g.a[i] + g.b[i];
+            unpack_cost_h2<NREG>(ab, t);
+#pragma unroll
+            for (int i = 0; i < NREG; ++i) acc[i] = h2_add(acc[i], t[i]);
+        }
+    } else if (hasA && hasB && th.preadd) {
         // both horizontal rows present and their byte-wise sum cannot carry (2*(cmax+P2) <= 255): add first, unpack once
         uint32_t ab[NW], t[NREG];
 #pragma unroll
@@ -259,9 +279,12 @@ __device__ __forceinline__ void vs_pixel(const VsThread<NREG>& th, uint32_t crow
         else if (NREG == 2) *reinterpret_cast<uint2*>(sp) = make_uint2(acc[0], acc[1]);
         else *sp = acc[0];
     } else {
-        if (FAST || th.Sin_l) {
+        if (FAST) {
 #pragma unroll
-            for (int i = 0; i < NREG; ++i) acc[i] += g.s[i];
+            for (int i = 0; i < NREG; ++i) acc[i] = h2_add(acc[i], g.s[i]);
+        } else if (th.Sin_l) {
+#pragma unroll
+            for (int i = 0; i < NREG; ++i) acc[i] += g.s[i] - th.sin_bias;
         }
         if (!FAST && th.Sout_l) {
             uint32_t* sp = reinterpret_cast<uint32_t*>(th.Sout_l + vox);
@@ -286,7 +309,7 @@ __device__ __forceinline__ void vs_pixel(const VsThread<NREG>& th, uint32_t crow
         __syncwarp();
         if (lane == 0) {
             const uint32_t idx = key & 0xFFFFu;
-            th.minC[pix] = key >> 16;
+            th.minC[pix] = (key >> 16) - (FAST ? (H2_BIAS2 & 0xFFFFu) : 0u);
             uint16_t* r = th.rec + (size_t)pix * 4;
             const uint16_t c_1 = idx > 0 ? ws[idx - 1] : 0, c1 = idx + 1 < (uint32_t)D ? ws[idx + 1] : 0;
             *reinterpret_cast<uint2*>(r) = make_uint2(idx | ((uint32_t)c_1 << 16), (uint32_t)c1 | (acc[0] << 16));      // lane 0's acc[0] low half = Sp[0]
@@ -341,7 +364,6 @@ vsweep_kernel(const VsParams prm)
     uint8_t* inbox_left = (rank > 0) ? cluster.map_shared_rank(inbox, rank - 1) : nullptr;        // we write slot "from right" there
 
     const uint32_t P1P1 = h2_const(prm.P1), P2P2 = h2_const(prm.P2);          // fp16x2 constants (sgm_step.cuh)
-    const uint32_t lo_mask = lane == 0 ? H2_BIG_LO : 0u, hi_mask = lane == 31 ? H2_BIG_HI : 0u;
     // per-thread bases with the lane's byte offset folded in
     constexpr int NB = 2 * NREG;
     VsThread<NREG> th;
@@ -356,7 +378,8 @@ vsweep_kernel(const VsParams prm)
     th.rec = prm.rec ? prm.rec + pair * N * 4 : nullptr;
     th.ws = wsc + warp * D;
     th.Wk = Wk; th.Wk_max = Wk_max; th.W = W; th.xb = xb; th.lane = lane;
-    th.P1P1 = P1P1; th.P2P2 = P2P2; th.lo_mask = lo_mask; th.hi_mask = hi_mask;
+    th.P1P1 = P1P1; th.P2P2 = P2P2; th.sel_lo = h2_edge_sel_lo(lane); th.sel_hi = h2_edge_sel_hi(lane);
+    th.sin_bias = prm.sin_bias;
     th.preadd = 2 * (24 + prm.P2) <= 255;          // cost values are <= 24 on this path (no-wrap domain precondition)
 
     // Pixel order inside a row is free (every path slot is touched by exactly one pixel per row), so the strip is split in
@@ -437,7 +460,7 @@ __device__ __forceinline__ uint32_t vs_x86_d2u(double v)
 }
 
 __global__ void vs_finalize_kernel(const uint16_t* __restrict__ rec, const uint32_t* __restrict__ minC, const double* __restrict__ O,
-                                   size_t N, int D, int subpixel, int vz_to_disp, double vMax, uint32_t* __restrict__ bestD)
+                                   size_t N, int D, int subpixel, int vz_to_disp, double vMax, uint32_t bias, uint32_t* __restrict__ bestD)
 {
     const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= N) return;
@@ -447,9 +470,10 @@ __global__ void vs_finalize_kernel(const uint16_t* __restrict__ rec, const uint3
     uint32_t q = idx;
     if (subpixel) {
         if (idx > 1) {
-            const double c_1 = (double)(r.x >> 16), c = (double)minC[gp];
-            double c1 = (double)(r.y & 0xFFFFu);
-            if (idx + 1 >= (uint32_t)D) c1 = (p + 1 < N) ? (double)(rec[(gp + 1) * 4 + 3]) : 0.0;
+            // `bias`: the FAST cluster passes record the neighbours as biased fp16 bit patterns (0x6400 | value)
+            const double c_1 = (double)((r.x >> 16) - bias), c = (double)minC[gp];
+            double c1 = (double)((r.y & 0xFFFFu) - bias);
+            if (idx + 1 >= (uint32_t)D) c1 = (p + 1 < N) ? (double)(rec[(gp + 1) * 4 + 3] - bias) : 0.0;
             const double num = __dsub_rn(c1, c_1);
             const double den = (c1 < c_1) ? __dsub_rn(c, c_1) : __dsub_rn(c, c1);
             q = vs_x86_d2u(__dmul_rn(__dadd_rn((double)idx, __ddiv_rn(__ddiv_rn(num, den), 2.0)), 256.0));
@@ -539,8 +563,11 @@ static int vs_launch_t(fsgm_ctx* c, int n, int cs, size_t smem, const VsParams& 
 }
 
 // one pass (down or up) over n pairs; see VsParams
+// *biased (in/out): a first pass sets it when its Sout holds biased fp16 patterns; a FINAL pass reads it for Sin and sets it
+// when its WTA records (rec) are biased — launch_vs_finalize takes the same flag.
 int launch_vsweep(fsgm_ctx* c, int n, int cs, int ndir, bool final_, const uint8_t* C, const uint8_t* addA, const uint8_t* addB,
-                  const uint16_t* Sin, uint16_t* Sout, uint32_t* minC, uint16_t* rec, int W, int H, int D, int P1, int P2, int up)
+                  const uint16_t* Sin, uint16_t* Sout, uint32_t* minC, uint16_t* rec, int W, int H, int D, int P1, int P2, int up,
+                  int* biased)
 {
     StageScope ss(c, ST_VSWEEP);
     VsParams p{};
@@ -550,7 +577,9 @@ int launch_vsweep(fsgm_ctx* c, int n, int cs, int ndir, bool final_, const uint8
     const int nreg = D / 64;
     // compile-time operand configuration of the standard two-pass run (see vs_fetch)
     const bool preadd = 2 * (24 + P2) <= 255;
-    const bool fast = final_ ? (Sin && !addA && !addB && !Sout) : (addA && addB && preadd && !Sin && Sout);
+    const bool fast = final_ ? (Sin && *biased && !addA && !addB && !Sout) : (addA && addB && preadd && !Sin && Sout);
+    p.sin_bias = (Sin && *biased) ? H2_BIAS2 : 0u;
+    *biased = fast ? 1 : 0;
 #define VS_GO(NR, ND, FN) do { if (fast) return vs_launch_t<NR, ND, FN, true>(c, n, cs, smem, p); return vs_launch_t<NR, ND, FN, false>(c, n, cs, smem, p); } while (0)
     if (ndir == 3) {
         if (final_) { if (nreg == 4) VS_GO(4, 3, true); if (nreg == 2) VS_GO(2, 3, true); VS_GO(1, 3, true); }
@@ -580,12 +609,12 @@ int vsweep_max_clusters(int cs, size_t smem, int threads)
 }
 
 int launch_vs_finalize(fsgm_ctx* c, int n, const uint16_t* rec, const uint32_t* minC, const double* O, int W, int H, int D,
-                       int subpixel, int vz_to_disp, double vMax, uint32_t* bestD)
+                       int subpixel, int vz_to_disp, double vMax, int biased, uint32_t* bestD)
 {
     StageScope ss(c, ST_WTA);
     const size_t N = (size_t)W * H;
     dim3 grid((unsigned)((N + 255) / 256), n);
-    vs_finalize_kernel<<<grid, 256, 0, c->stream>>>(rec, minC, O, N, D, subpixel, vz_to_disp, vMax, bestD);
+    vs_finalize_kernel<<<grid, 256, 0, c->stream>>>(rec, minC, O, N, D, subpixel, vz_to_disp, vMax, biased ? (H2_BIAS2 & 0xFFFFu) : 0u, bestD);
     FSGM_LAUNCHED(c);
     return FSGM_OK;
 }
