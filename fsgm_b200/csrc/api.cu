@@ -185,14 +185,18 @@ static int aggregate_and_wta(fsgm_ctx* c, int n, const uint8_t* C, const uint8_t
         const int hd[2] = {0, 4};
         uint8_t* Lh[2] = {Lh0, Lh1};
         FSGM_TRY(launch_sweeps(c, nf, C, I1, W, H, D, P1, P2, 0, cmax, hd, o.total_pass == 2 ? 2 : 1, Lh));
-        int biased = 0;                    // the FAST cluster passes keep their sums as biased fp16 bit patterns (vsweep.cu)
-        if (o.total_pass == 2) {
-            FSGM_TRY(launch_vsweep(c, nf, cs, ndir, false, C, Lh0, Lh1, nullptr, S1, nullptr, nullptr, W, H, D, P1, P2, 0, &biased));
-            FSGM_TRY(launch_vsweep(c, nf, cs, ndir, true, C, nullptr, nullptr, S1, Sp16, minC, rec, W, H, D, P1, P2, 1, &biased));
+        // FAST operand configuration of the two cluster passes (vsweep.cu): byte volume between them, biased WTA records
+        const bool fast = o.total_pass == 2 && !Sp16 && vsweep_fast_ok(ndir, P2);
+        if (fast) {
+            FSGM_TRY(launch_vsweep(c, nf, cs, ndir, false, C, nullptr, nullptr, nullptr, S1, nullptr, nullptr, W, H, D, P1, P2, 0, true));
+            FSGM_TRY(launch_vsweep(c, nf, cs, ndir, true, C, Lh0, Lh1, S1, nullptr, minC, rec, W, H, D, P1, P2, 1, true));
+        } else if (o.total_pass == 2) {
+            FSGM_TRY(launch_vsweep(c, nf, cs, ndir, false, C, Lh0, Lh1, nullptr, S1, nullptr, nullptr, W, H, D, P1, P2, 0, false));
+            FSGM_TRY(launch_vsweep(c, nf, cs, ndir, true, C, nullptr, nullptr, S1, Sp16, minC, rec, W, H, D, P1, P2, 1, false));
         } else {
-            FSGM_TRY(launch_vsweep(c, nf, cs, ndir, true, C, Lh0, nullptr, nullptr, Sp16, minC, rec, W, H, D, P1, P2, 0, &biased));
+            FSGM_TRY(launch_vsweep(c, nf, cs, ndir, true, C, Lh0, nullptr, nullptr, Sp16, minC, rec, W, H, D, P1, P2, 0, false));
         }
-        FSGM_TRY(launch_vs_finalize(c, nf, rec, minC, O, W, H, D, o.subpixel, o.vz_to_disp, vMax, biased, bestD));
+        FSGM_TRY(launch_vs_finalize(c, nf, rec, minC, O, W, H, D, o.subpixel, o.vz_to_disp, vMax, fast ? 1 : 0, bestD));
     }
     if (ng) {
         int dirs[8];
@@ -278,6 +282,7 @@ static int epi_pipeline_waves(fsgm_ctx* c, int n, int cs, const uint8_t* I1, con
     FSGM_CUDA(c, cudaEventRecord(c->ev_entry, A));            // everything queued so far (inputs, vz) precedes stream B
     FSGM_CUDA(c, cudaStreamWaitEvent(B, c->ev_entry, 0));
     const int hd[2] = {0, 4};
+    const bool fast = vsweep_fast_ok(ndir, P2);         // FAST operand configuration of the two cluster passes (vsweep.cu)
     auto front = [&](int p0, int m, cudaStream_t st) -> int {
         StreamSwap sw(c, st);
         FSGM_TRY(launch_census(c, m, I1 + p0 * N, W, H, cen1 + p0 * N));
@@ -290,12 +295,18 @@ static int epi_pipeline_waves(fsgm_ctx* c, int n, int cs, const uint8_t* I1, con
         return launch_sweeps(c, m, C + p0 * V, I1 + p0 * N, W, H, D, P1, P2, 0, 24, hd, 2, Lh);
     };
     auto back = [&](int p0, int m) -> int {
-        int biased = 0;
-        FSGM_TRY(launch_vsweep(c, m, cs, ndir, false, C + p0 * V, Lh0 + p0 * V, Lh1 + p0 * V, nullptr, S1 + p0 * V, nullptr, nullptr,
-                               W, H, D, P1, P2, 0, &biased));
-        FSGM_TRY(launch_vsweep(c, m, cs, ndir, true, C + p0 * V, nullptr, nullptr, S1 + p0 * V, nullptr, minC + p0 * N, rec + p0 * N * 4,
-                               W, H, D, P1, P2, 1, &biased));
-        return launch_vs_finalize(c, m, rec + p0 * N * 4, minC + p0 * N, O + p0 * N, W, H, D, o.subpixel, o.vz_to_disp, vMax, biased,
+        if (fast) {
+            FSGM_TRY(launch_vsweep(c, m, cs, ndir, false, C + p0 * V, nullptr, nullptr, nullptr, S1 + p0 * V, nullptr, nullptr,
+                                   W, H, D, P1, P2, 0, true));
+            FSGM_TRY(launch_vsweep(c, m, cs, ndir, true, C + p0 * V, Lh0 + p0 * V, Lh1 + p0 * V, S1 + p0 * V, nullptr, minC + p0 * N,
+                                   rec + p0 * N * 4, W, H, D, P1, P2, 1, true));
+        } else {
+            FSGM_TRY(launch_vsweep(c, m, cs, ndir, false, C + p0 * V, Lh0 + p0 * V, Lh1 + p0 * V, nullptr, S1 + p0 * V, nullptr, nullptr,
+                                   W, H, D, P1, P2, 0, false));
+            FSGM_TRY(launch_vsweep(c, m, cs, ndir, true, C + p0 * V, nullptr, nullptr, S1 + p0 * V, nullptr, minC + p0 * N,
+                                   rec + p0 * N * 4, W, H, D, P1, P2, 1, false));
+        }
+        return launch_vs_finalize(c, m, rec + p0 * N * 4, minC + p0 * N, O + p0 * N, W, H, D, o.subpixel, o.vz_to_disp, vMax, fast ? 1 : 0,
                                   bestD + p0 * N);
     };
     const int waves = (nf + K - 1) / K;

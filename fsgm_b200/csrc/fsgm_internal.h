@@ -131,7 +131,8 @@ int vsweep_max_clusters(int cs, size_t smem, int threads);
 size_t vsweep_smem_bytes(int D, int Wk, int ndir);
 int vsweep_threads();
 int launch_vsweep(fsgm_ctx* c, int n, int cs, int ndir, bool final_, const uint8_t* C, const uint8_t* addA, const uint8_t* addB,
-                  const uint16_t* Sin, uint16_t* Sout, uint32_t* minC, uint16_t* rec, int W, int H, int D, int P1, int P2, int up, int* biased);
+                  const uint16_t* Sin, uint16_t* Sout, uint32_t* minC, uint16_t* rec, int W, int H, int D, int P1, int P2, int up, bool fast);
+bool vsweep_fast_ok(int ndir, int P2);
 int launch_vs_finalize(fsgm_ctx* c, int n, const uint16_t* rec, const uint32_t* minC, const double* O, int W, int H, int D,
                        int subpixel, int vz_to_disp, double vMax, int biased, uint32_t* bestD);
 

@@ -31,6 +31,15 @@ namespace cg = cooperative_groups;
 
 namespace fsgm {
 
+#ifndef FSGM_VS_CARRY
+#define FSGM_VS_CARRY 0
+#endif
+#ifndef FSGM_VS_PDF
+#define FSGM_VS_PDF 3
+#endif
+#ifndef FSGM_VS_RELIEF
+#define FSGM_VS_RELIEF 1
+#endif
 constexpr int VS_WARPS = 20;      // measured at KITTI size (156 columns per CTA): 13/16/18/20/24/26 warps -> 14.9/13.1/13.5/12.7/13.3/14.2 ms per 30 pairs
 
 struct VsParams {
@@ -43,7 +52,7 @@ struct VsParams {
     uint16_t* rec;               //        [n][N][4] = argmin, Sp[argmin-1], Sp[argmin+1] (0 if argmin == D-1), Sp[0]
     int W, H, Wk, P1, P2;
     int up;                      // 0: rows 0..H-1 with directions (0,+1)(+1,+1)(-1,+1); 1: rows H-1..0, negated
-    uint32_t sin_bias;           // H2_BIAS2 when Sin was written by a FAST first pass (biased fp16 bit patterns), else 0
+    int fast;                    // the FAST operand configuration (see vs_fetch): Sin / Sout are BYTE volumes
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -114,29 +123,41 @@ struct VsThread {
     uint32_t* minC; uint16_t* rec; uint16_t* ws;
     int Wk, Wk_max, W, xb, lane;
     uint32_t P1P1, P2P2, sel_lo, sel_hi;
-    uint32_t sin_bias;
     bool preadd;
 };
 
 // the rows a pixel needs from global memory (horizontal volumes / the other pass's sum), fetched two pixels ahead
 template <int NREG>
-struct VsGlobals { uint32_t a[(NREG + 1) / 2], b[(NREG + 1) / 2], s[NREG]; };
+struct VsGlobals { uint32_t a[(NREG + 1) / 2], b[(NREG + 1) / 2], s[NREG], s8[(NREG + 1) / 2]; };     // s8: the FAST byte volume
 
-// FAST = the operand configuration of the standard two-pass run is known at compile time: the first pass (!FINAL) adds both
-// horizontal volumes (byte-wise pre-add valid) and writes the u16 sum; the second (FINAL) adds that sum and does WTA with no
-// Sp dump.  Every other combination (single pass, 4 paths with one horizontal volume, stage dumps) takes the run-time checks.
-// The FAST passes never leave the biased fp16 domain: the intermediate sum volume holds the bit patterns 0x6400 | s (s < 1024:
-// at most 8 * (24 + P2) with P2 <= 103), the second pass adds them as halves and runs winner-take-all on the patterns, which
-// order like the sums; the bias comes off the three values per pixel that leave the kernel (minC here, the subpixel
-// neighbours in vs_finalize_kernel).
+// FAST = the standard two-pass run (both horizontal volumes present, no Sp dump, 3*P2 <= 255, 8*(24+P2) < 1024), with the
+// operand configuration known at compile time and the HBM traffic of the first pass cut to the minimum:
+//   * first pass (!FINAL): NO global loads at all.  It writes ONE BYTE per voxel, sum_k (L_k - C): every L_k - C is
+//     min(b - M, P2) in [0, P2], so three of them fit a byte, and the subtraction is byte-wise on the packed words
+//     (three IADD3 per word).  ncu (r1n): with the horizontal rows read here the pass spent a third of its stall samples
+//     waiting for them although they were requested four pixels ahead (mixed read/write DRAM traffic at 4 TB/s).
+//   * final pass: reads that byte volume and the two horizontal volumes (3 B per voxel, read-only traffic), rebuilds
+//     1024 + 3*C + sum of all eight directions as a biased fp16 pattern (one HFMA2 for 3*C - 2048, the byte rows added as
+//     integers onto the pattern: it stays below 0x6800) and runs winner-take-all on the patterns, which order like the sums;
+//     the bias comes off the values that leave the kernel (minC here, the subpixel neighbours in vs_finalize_kernel).
+// Every other combination (single pass, one horizontal volume, stage dumps, larger P2) takes the run-time checks and the
+// u16 sum volume.
 template <int NREG, bool FINAL, bool FAST>
 __device__ __forceinline__ void vs_fetch(const VsThread<NREG>& th, uint32_t pix, VsGlobals<NREG>& g)
 {
     constexpr int D = 64 * NREG;
     const size_t vox = (size_t)pix * D;
-    if (FAST ? !FINAL : th.addA_l != nullptr) ld_row<NREG>(th.addA_l + vox, 0, g.a);
-    if (FAST ? !FINAL : th.addB_l != nullptr) ld_row<NREG>(th.addB_l + vox, 0, g.b);
-    if (FAST ? FINAL : (FINAL && th.Sin_l)) {
+    if (FAST) {
+        if (FINAL) {
+            ld_row<NREG>(th.addA_l + vox, 0, g.a);
+            ld_row<NREG>(th.addB_l + vox, 0, g.b);
+            ld_row<NREG>(reinterpret_cast<const uint8_t*>(th.Sin_l) + vox, 0, g.s8);     // byte volume: Sin_l carries a BYTE lane offset here
+        }
+        return;
+    }
+    if (th.addA_l != nullptr) ld_row<NREG>(th.addA_l + vox, 0, g.a);
+    if (th.addB_l != nullptr) ld_row<NREG>(th.addB_l + vox, 0, g.b);
+    if (FINAL && th.Sin_l) {
         const uint32_t* sp = reinterpret_cast<const uint32_t*>(th.Sin_l + vox);
         if (NREG == 4) { uint4 v = *reinterpret_cast<const uint4*>(sp); g.s[0] = v.x; g.s[1] = v.y; g.s[2] = v.z; g.s[3] = v.w; }
         else if (NREG == 2) { uint2 v = *reinterpret_cast<const uint2*>(sp); g.s[0] = v.x; g.s[1] = v.y; }
@@ -196,9 +217,17 @@ __device__ __forceinline__ void vs_pixel(const VsThread<NREG>& th, uint32_t crow
     }
     uint32_t pw[NDIR][NW], Mn[NDIR];
     static_assert(NDIR == 1 || NDIR == 3, "accumulator bias below assumes one or three directions");
-    // FAST: -1024 * NDIR, so that adding one more biased operand (horizontal rows / the first pass's sum) gives 1024 + total;
-    // otherwise -1024 * (NDIR - 1): the sum of the directions alone is 1024 + sum and is turned into an integer below
-    constexpr uint32_t ACC0 = FAST ? (NDIR == 3 ? 0xEA00EA00u : 0xE400E400u) : 0xE800E800u;
+    // !FAST: -1024 * (NDIR - 1): the sum of the directions alone is 1024 + sum and is turned into an integer below.
+    // FAST FINAL: the accumulator starts at NDIR*C + 1024 - NDIR*1024 (one HFMA2 on the biased cost: (1024 + C)*NDIR - 2*NDIR*1024
+    // + 1024, exact: a single rounding of an integer of magnitude <= 2048), so that after the NDIR biased rows it holds
+    // 1024 + NDIR*C + sum_k L_k with every partial sum an integer of magnitude <= 2048.
+    constexpr uint32_t ACC0 = 0xE800E800u;
+    constexpr uint32_t H2_NDIR = NDIR == 3 ? 0x42004200u : 0x3C003C00u;       // half2(3) / half2(1)
+    constexpr uint32_t H2_K0 = NDIR == 3 ? 0xED00ED00u : 0xE400E400u;         // half2(-5120) / half2(-1024)
+    if (FAST && FINAL) {
+#pragma unroll
+        for (int i = 0; i < NREG; ++i) asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(acc[i]) : "r"(c[i]), "r"(H2_NDIR), "r"(H2_K0));
+    }
 #pragma unroll
     for (int k = 0; k < NDIR; ++k) {
         uint32_t L[NREG];
@@ -216,7 +245,10 @@ __device__ __forceinline__ void vs_pixel(const VsThread<NREG>& th, uint32_t crow
         // sum of the directions, still on the FMA pipe: -1024*(NDIR-1) + sum(1024 + L_k) = 1024 + sum(L_k) < 2048, every
         // partial sum is an integer of magnitude <= 2048
 #pragma unroll
-        for (int i = 0; i < NREG; ++i) acc[i] = k == 0 ? ((NDIR == 1 && !FAST) ? L[i] : h2_add(L[i], ACC0)) : h2_add(acc[i], L[i]);
+        for (int i = 0; i < NREG; ++i) {
+            if (FAST) { if (FINAL) acc[i] = h2_add(acc[i], L[i]); }
+            else acc[i] = k == 0 ? (NDIR == 1 ? L[i] : h2_add(L[i], ACC0)) : h2_add(acc[i], L[i]);
+        }
     }
     // biased half -> integer u16x2
     if (!FAST) {
@@ -246,17 +278,30 @@ __device__ __forceinline__ void vs_pixel(const VsThread<NREG>& th, uint32_t crow
     // the row's hand-overs are written: publish them before this pixel's global stores are issued (an arrive.release
     // after those would wait for them to reach L2)
     if (EDGE && arrive) cluster_arrive();
-    const bool hasA = FAST ? !FINAL : th.addA_l != nullptr, hasB = FAST ? !FINAL : th.addB_l != nullptr;
+    const bool hasA = !FAST && th.addA_l != nullptr, hasB = !FAST && th.addB_l != nullptr;
     if (FAST) {
         if (!FINAL) {
-            // both horizontal rows: their byte-wise sum cannot carry (2*(cmax+P2) <= 255); add, unpack once, stay biased
-            uint32_t ab[NW], t[NREG];
+            // one byte per voxel: sum_k (L_k - C), byte-wise on the packed words (each byte of the result is in [0, NDIR*P2];
+            // borrows and carries of the partial sums cancel in the 32-bit arithmetic)
+            uint32_t sb[NW];
 #pragma unroll
-            for (int i = 0; i < NW; ++i) ab[i] = g.a[i] + g.b[i];
-            unpack_cost_h2<NREG>(ab, t);
+            for (int i = 0; i < NW; ++i) {
+                sb[i] = pw[0][i] - cw[i];
 #pragma unroll
-            for (int i = 0; i < NREG; ++i) acc[i] = h2_add(acc[i], t[i]);
+                for (int k = 1; k < NDIR; ++k) sb[i] += pw[k][i] - cw[i];
+            }
+            st_row<NREG>(reinterpret_cast<uint8_t*>(th.Sout_l) + vox, 0, sb);      // Sout_l carries a BYTE lane offset here
+            return;
         }
+        // both horizontal rows (their byte-wise sum cannot carry: 2*(cmax+P2) <= 255) and the first pass's byte row are added
+        // as integers onto the biased pattern
+        uint32_t ab[NW], t[NREG], u[NREG];
+#pragma unroll
+        for (int i = 0; i < NW; ++i) ab[i] = g.a[i] + g.b[i];
+        unpack_cost<NREG>(ab, t);
+        unpack_cost<NREG>(g.s8, u);
+#pragma unroll
+        for (int i = 0; i < NREG; ++i) acc[i] += t[i] + u[i];
     } else if (hasA && hasB && th.preadd) {
         // both horizontal rows present and their byte-wise sum cannot carry (2*(cmax+P2) <= 255): add first, unpack once
         uint32_t ab[NW], t[NREG];
@@ -279,12 +324,9 @@ __device__ __forceinline__ void vs_pixel(const VsThread<NREG>& th, uint32_t crow
         else if (NREG == 2) *reinterpret_cast<uint2*>(sp) = make_uint2(acc[0], acc[1]);
         else *sp = acc[0];
     } else {
-        if (FAST) {
+        if (!FAST && th.Sin_l) {
 #pragma unroll
-            for (int i = 0; i < NREG; ++i) acc[i] = h2_add(acc[i], g.s[i]);
-        } else if (th.Sin_l) {
-#pragma unroll
-            for (int i = 0; i < NREG; ++i) acc[i] += g.s[i] - th.sin_bias;
+            for (int i = 0; i < NREG; ++i) acc[i] += g.s[i];
         }
         if (!FAST && th.Sout_l) {
             uint32_t* sp = reinterpret_cast<uint32_t*>(th.Sout_l + vox);
@@ -372,14 +414,18 @@ vsweep_kernel(const VsParams prm)
     th.inbox_right = inbox_right; th.inbox_left = inbox_left;
     th.addA_l = prm.addA ? prm.addA + pair * N * D + lane * NB : nullptr;
     th.addB_l = prm.addB ? prm.addB + pair * N * D + lane * NB : nullptr;
-    th.Sin_l = prm.Sin ? prm.Sin + pair * N * D + lane * NB : nullptr;
-    th.Sout_l = prm.Sout ? prm.Sout + pair * N * D + lane * NB : nullptr;
+    if (FAST) {      // byte volumes behind the u16 pointers: offsets in bytes
+        th.Sin_l = prm.Sin ? reinterpret_cast<const uint16_t*>(reinterpret_cast<const uint8_t*>(prm.Sin) + pair * N * D + lane * NB) : nullptr;
+        th.Sout_l = prm.Sout ? reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(prm.Sout) + pair * N * D + lane * NB) : nullptr;
+    } else {
+        th.Sin_l = prm.Sin ? prm.Sin + pair * N * D + lane * NB : nullptr;
+        th.Sout_l = prm.Sout ? prm.Sout + pair * N * D + lane * NB : nullptr;
+    }
     th.minC = prm.minC ? prm.minC + pair * N : nullptr;
     th.rec = prm.rec ? prm.rec + pair * N * 4 : nullptr;
     th.ws = wsc + warp * D;
     th.Wk = Wk; th.Wk_max = Wk_max; th.W = W; th.xb = xb; th.lane = lane;
     th.P1P1 = P1P1; th.P2P2 = P2P2; th.sel_lo = h2_edge_sel_lo(lane); th.sel_hi = h2_edge_sel_hi(lane);
-    th.sin_bias = prm.sin_bias;
     th.preadd = 2 * (24 + prm.P2) <= 255;          // cost values are <= 24 on this path (no-wrap domain precondition)
 
     // Pixel order inside a row is free (every path slot is touched by exactly one pixel per row), so the strip is split in
@@ -394,9 +440,26 @@ vsweep_kernel(const VsParams prm)
     const bool upper = warp >= HW;
     const int n_lo = (Wk + 1) / 2, cnt = upper ? Wk - n_lo : n_lo;
     const int xfirst = upper ? Wk - 1 : 0, xstep = upper ? -1 : 1;
-    auto xl_of = [&](int i) { return xfirst + xstep * i; };
+    // Warp w walks the pixels i = w, w + HW, w + 2*HW, ... of its half.  The warp that owns the edge pixel (w = 0) also pays for
+    // the hand-over and the releasing cluster arrive, and every other warp waits for it at the row-end barrier; when the half
+    // does not divide evenly (KITTI: 69 pixels over 10 warps) its last pixel is therefore given to the first warp that would
+    // otherwise have one pixel less.  `lim` is the exclusive bound of the warp's natural sequence, `imax` clamps the index of
+    // the receiving warp's extra step onto the moved pixel.
+    int lim = cnt, imax = 0x7FFFFFFF;
+#if FSGM_VS_RELIEF
+    {
+        const int full = cnt / HW, rem = cnt % HW;
+        if (full >= 1 && rem > 0) {
+            if (wsub == 0) lim = full * HW;                              // drops i = full*HW
+            if (wsub == rem) { lim = cnt + HW; imax = full * HW; }       // one more step, clamped onto that pixel
+        }
+    }
+#endif
+    auto xl_of = [&](int i) { return xfirst + xstep * min(i, imax); };
 
     int off = 0;                                   // yy mod Wk, kept incrementally
+    constexpr int PD = FINAL ? FSGM_VS_PDF : 4;
+    VsGlobals<NREG> gq[PD];
     for (int yy = 0; yy < H; ++yy) {
         const int y = row_y(yy), par = yy & 1;
         if (yy > 0) cluster_wait();                // hand-overs of row yy-1 are visible; neighbours are done reading inbox[par]
@@ -409,33 +472,50 @@ vsweep_kernel(const VsParams prm)
         // that is still waiting for its load would stall on the copy, which is exactly what a rotating ring does.
         // (Requesting the next row's first pixels before the row-end barrier was measured slower, 21.9 -> 23.3 ms per 60 pairs;
         // an L2 prefetch of the same rows at that point changes nothing.)
-        constexpr int PD = FINAL ? 2 : 4;
-        VsGlobals<NREG> gq[PD];
+#if FSGM_VS_CARRY
+        // the ring is carried across the row barrier: after a slot's last pixel of this row it is refilled with the warp's
+        // pixel of the same slot in the NEXT row, so no load is issued (and waited for) right behind the barrier
+        const uint32_t rowpix_next = (uint32_t)row_y(yy + 1 < H ? yy + 1 : yy) * (uint32_t)W + (uint32_t)xb;
+        const bool has_next = yy + 1 < H;
+        if (yy == 0)
+#endif
+        {
 #pragma unroll
-        for (int u = 0; u < PD; ++u)
-            if (wsub + u * HW < cnt) vs_fetch<NREG, FINAL, FAST>(th, rowpix + xl_of(wsub + u * HW), gq[u]);
+            for (int u = 0; u < PD; ++u)
+                if (wsub + u * HW < lim) vs_fetch<NREG, FINAL, FAST>(th, rowpix + xl_of(wsub + u * HW), gq[u]);
+        }
         // warps 0 and HW publish the row's hand-overs from inside their first (edge) pixel; every other warp has nothing to
         // publish and arrives right away
-        if (wsub != 0 || cnt == 0) cluster_arrive_relaxed();
+        if (wsub != 0 || lim == 0) cluster_arrive_relaxed();
         if (yy == 0) {
             // first row: every path starts here (edge body for every pixel); one row, so no software pipelining
-            for (int i = wsub; i < cnt; i += HW) {
+            for (int i = wsub; i < lim; i += HW) {
                 const int xl = xl_of(i);
                 if (i != wsub) vs_fetch<NREG, FINAL, FAST>(th, rowpix + xl, gq[0]);
                 vs_pixel<NREG, NDIR, FINAL, true, FAST>(th, crow_l, xl, yy, par, off, rowpix + xl, gq[0], i == 0);
             }
+#if FSGM_VS_CARRY
+            if (has_next) {
+#pragma unroll
+                for (int u = 0; u < PD; ++u)
+                    if (wsub + u * HW < lim) vs_fetch<NREG, FINAL, FAST>(th, rowpix_next + xl_of(wsub + u * HW), gq[u]);
+            }
+#endif
         } else {
             // the only edge pixels of a later row are xl = 0 and xl = Wk-1: pixel i = 0 of warps 0 and HW, i.e. ring slot 0 of
             // their first round
-            for (int i0 = wsub; i0 < cnt; i0 += PD * HW) {
+            for (int i0 = wsub; i0 < lim; i0 += PD * HW) {
 #pragma unroll
                 for (int u = 0; u < PD; ++u) {
                     const int i = i0 + u * HW;
-                    if (i < cnt) {
+                    if (i < lim) {
                         const int xl = xl_of(i);
                         if (u == 0 && i == 0) vs_pixel<NREG, NDIR, FINAL, true, FAST>(th, crow_l, xl, yy, par, off, rowpix + xl, gq[u], true);
                         else vs_pixel<NREG, NDIR, FINAL, false, FAST>(th, crow_l, xl, yy, par, off, rowpix + xl, gq[u], false);
-                        if (i + PD * HW < cnt) vs_fetch<NREG, FINAL, FAST>(th, rowpix + xl_of(i + PD * HW), gq[u]);
+                        if (i + PD * HW < lim) vs_fetch<NREG, FINAL, FAST>(th, rowpix + xl_of(i + PD * HW), gq[u]);
+#if FSGM_VS_CARRY
+                        else if (has_next) vs_fetch<NREG, FINAL, FAST>(th, rowpix_next + xl_of(wsub + u * HW), gq[u]);
+#endif
                     }
                 }
             }
@@ -563,11 +643,14 @@ static int vs_launch_t(fsgm_ctx* c, int n, int cs, size_t smem, const VsParams& 
 }
 
 // one pass (down or up) over n pairs; see VsParams
-// *biased (in/out): a first pass sets it when its Sout holds biased fp16 patterns; a FINAL pass reads it for Sin and sets it
-// when its WTA records (rec) are biased — launch_vs_finalize takes the same flag.
+// fast = the FAST operand configuration (vsweep_fast_ok() must hold): the first pass takes no addA / addB / Sin and writes a
+// BYTE volume through Sout; the final pass takes addA, addB and that byte volume as Sin, no Sout; its WTA records are biased
+// (launch_vs_finalize takes the same flag).
+bool vsweep_fast_ok(int ndir, int P2) { return ndir * P2 <= 255 && 2 * (24 + P2) <= 255 && 8 * (24 + P2) < 1024; }
+
 int launch_vsweep(fsgm_ctx* c, int n, int cs, int ndir, bool final_, const uint8_t* C, const uint8_t* addA, const uint8_t* addB,
                   const uint16_t* Sin, uint16_t* Sout, uint32_t* minC, uint16_t* rec, int W, int H, int D, int P1, int P2, int up,
-                  int* biased)
+                  bool fast)
 {
     StageScope ss(c, ST_VSWEEP);
     VsParams p{};
@@ -576,10 +659,11 @@ int launch_vsweep(fsgm_ctx* c, int n, int cs, int ndir, bool final_, const uint8
     const size_t smem = vs_smem_bytes(D, p.Wk, ndir, final_);
     const int nreg = D / 64;
     // compile-time operand configuration of the standard two-pass run (see vs_fetch)
-    const bool preadd = 2 * (24 + P2) <= 255;
-    const bool fast = final_ ? (Sin && *biased && !addA && !addB && !Sout) : (addA && addB && preadd && !Sin && Sout);
-    p.sin_bias = (Sin && *biased) ? H2_BIAS2 : 0u;
-    *biased = fast ? 1 : 0;
+    if (fast) {
+        const bool ok = vsweep_fast_ok(ndir, P2) && (final_ ? (addA && addB && Sin && !Sout) : (!addA && !addB && !Sin && Sout));
+        if (!ok) return fail(c, FSGM_ERR_DOMAIN, "vsweep: operands do not match the FAST configuration");
+    }
+    p.fast = fast;
 #define VS_GO(NR, ND, FN) do { if (fast) return vs_launch_t<NR, ND, FN, true>(c, n, cs, smem, p); return vs_launch_t<NR, ND, FN, false>(c, n, cs, smem, p); } while (0)
     if (ndir == 3) {
         if (final_) { if (nreg == 4) VS_GO(4, 3, true); if (nreg == 2) VS_GO(2, 3, true); VS_GO(1, 3, true); }
