@@ -35,7 +35,7 @@ sys.path.insert(0, ROOT)
 
 W, H, D, PATHS, P1, P2, VMAX = 1242, 375, 256, 8, 6, 64, 0.3
 METRIC = "frame-pairs/s (KITTI 1242x375, 256 labels, 8 paths)"
-TRAFFIC_VSWEEP_P30 = 14.38e9   # dram read+write bytes per launch at 30 pairs: mean of the down (17.85 GB) and up (10.90 GB) pass, profiles/r1i_kernels_p30.txt
+TRAFFIC_VSWEEP_P15 = 5.387e9   # dram read+write bytes per launch at 15 pairs: mean of the first (1.79 + 1.74 GB) and final (7.15 + 0.09 GB) pass, profiles/r1p_vsweep_kernels_p15.txt
 
 
 def hbm_peak():
@@ -275,9 +275,9 @@ def run_ours(args):
             # launches are per wave and per pass: pairs per launch = (pairs in the timed region * 2 passes) / launches
             pairs_per_launch = P * args.steps * 2.0 / k_launches
             per_launch_bytes = pairs_per_launch * N * D * 9
-            # dram__bytes_read+write per launch from profiles/r1i_kernels_p30.txt (ncu --set full, 30 pairs per launch),
+            # dram__bytes_read+write per launch from profiles/r1p_vsweep_kernels_p15.txt (ncu --set full, 15 pairs per launch),
             # mean of the two passes, scaled to the pairs one launch handles
-            traffic = (TRAFFIC_VSWEEP_P30 * pairs_per_launch / 30.0) if TRAFFIC_VSWEEP_P30 else None
+            traffic = (TRAFFIC_VSWEEP_P15 * pairs_per_launch / 15.0) if TRAFFIC_VSWEEP_P15 else None
         else:
             k_ms, k_launches = stages.get("sweep", (0.0, 0))
             k_name = "sweep_fast_kernel (path aggregation, all 8 directions in one launch)"
@@ -298,8 +298,9 @@ def run_ours(args):
                          "frac": (ach / peak) if ach else None, "traffic": traffic,
                          "algorithmic_bytes_per_launch": per_launch_bytes,
                          "kernel_ms_per_launch": (k_ms / k_launches) if k_launches else None,
-                         "note": "the kernel is bound by the integer ALU pipe (ncu: ~70 % alu-pipe active), not by HBM: it moves "
-                                 "fewer DRAM bytes than the algorithmic count because C is read once for three directions",
+                         "note": "the kernel is bound by instruction issue (ncu: 74-77 % issue slots, 61-68 % alu pipe), not by HBM: it moves "
+                                 "fewer DRAM bytes than the algorithmic count because C is read once for three directions and "
+                                 "neither the six L volumes nor Sp are materialised",
                          "whole_step_frac": balg_pair * value / world / 1e9 / peak,
                          "whole_step_algorithmic_bytes_per_pair": balg_pair},
             "stage_ms_per_step": {k: v[0] / args.steps for k, v in stages.items()},

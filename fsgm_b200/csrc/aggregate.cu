@@ -27,6 +27,7 @@
 // The three non-horizontal directions of a pass have a faster, row-synchronous implementation in vsweep.cu.
 #include "fsgm_internal.h"
 #include "sgm_step.cuh"
+#include <type_traits>
 
 namespace fsgm {
 
@@ -287,30 +288,37 @@ hsweep_tma_kernel(const SweepParams prm)
         }
         const uint8_t* buf = ring[wib][c & 1] + lane * NB;
         const int xlo = dx > 0 ? t0 : W - t0 - cnt;
+        // the chunk is walked with running pointers whose stride sign is a compile-time constant (one loop per direction), so
+        // the unrolled steps address the ring and the output row with immediate offsets
+        auto walk = [&](auto fwd_tag) {
+            constexpr bool FWD = decltype(fwd_tag)::value;
+            constexpr int STEP = FWD ? D : -D;
+            const uint8_t* bp = buf + (FWD ? 0 : (cnt - 1) * D);
+            uint8_t* dp = Lrow + (size_t)(xlo + (FWD ? 0 : cnt - 1)) * D;
 #pragma unroll 4
-        for (int s = 0; s < cnt; ++s) {
-            const int off = dx > 0 ? s : cnt - 1 - s;                    // position inside the chunk, memory order
-            uint32_t cw[(NREG + 1) / 2];
-            if (NREG == 1) cw[0] = *reinterpret_cast<const uint16_t*>(buf + off * D);
-            else if (NREG == 2) cw[0] = *reinterpret_cast<const uint32_t*>(buf + off * D);
-            else { const uint2 v = *reinterpret_cast<const uint2*>(buf + off * D); cw[0] = v.x; cw[1] = v.y; }
-            uint32_t cc[NREG], cP2[NREG], Ln[NREG];
-            unpack_cost_h2<NREG>(cw, cc);
+            for (int s = 0; s < cnt; ++s, bp += STEP, dp += STEP) {
+                uint32_t cw[(NREG + 1) / 2];
+                if (NREG == 1) cw[0] = *reinterpret_cast<const uint16_t*>(bp);
+                else if (NREG == 2) cw[0] = *reinterpret_cast<const uint32_t*>(bp);
+                else { const uint2 v = *reinterpret_cast<const uint2*>(bp); cw[0] = v.x; cw[1] = v.y; }
+                uint32_t cc[NREG], cP2[NREG], Ln[NREG];
+                unpack_cost_h2<NREG>(cw, cc);
 #pragma unroll
-            for (int i = 0; i < NREG; ++i) cP2[i] = h2_add(cc[i], P2h);
-            // at the path start the (biased) zero state with M = 0 makes the step return L = C; the minimum is then forced to 0
-            const uint32_t m = sgm_step_h2<NREG>(cP2, Lr, M, P1h, P2h, sel_lo, sel_hi, Ln);
-            M = first ? ZERO_B : m;
-            first = false;
+                for (int i = 0; i < NREG; ++i) cP2[i] = h2_add(cc[i], P2h);
+                // at the path start the (biased) zero state with M = 0 makes the step return L = C; the minimum is then forced to 0
+                const uint32_t m = sgm_step_h2<NREG>(cP2, Lr, M, P1h, P2h, sel_lo, sel_hi, Ln);
+                M = first ? ZERO_B : m;
+                first = false;
 #pragma unroll
-            for (int i = 0; i < NREG; ++i) Lr[i] = Ln[i];
-            uint32_t pw[(NREG + 1) / 2];
-            pack_cost<NREG>(Lr, pw);
-            uint8_t* dst = Lrow + (size_t)(xlo + off) * D;
-            if (NREG == 1) *reinterpret_cast<uint16_t*>(dst) = (uint16_t)pw[0];
-            else if (NREG == 2) *reinterpret_cast<uint32_t*>(dst) = pw[0];
-            else *reinterpret_cast<uint2*>(dst) = make_uint2(pw[0], pw[1]);
-        }
+                for (int i = 0; i < NREG; ++i) Lr[i] = Ln[i];
+                uint32_t pw[(NREG + 1) / 2];
+                pack_cost<NREG>(Lr, pw);
+                if (NREG == 1) *reinterpret_cast<uint16_t*>(dp) = (uint16_t)pw[0];
+                else if (NREG == 2) *reinterpret_cast<uint32_t*>(dp) = pw[0];
+                else *reinterpret_cast<uint2*>(dp) = make_uint2(pw[0], pw[1]);
+            }
+        };
+        if (dx > 0) walk(std::true_type{}); else walk(std::false_type{});
         __syncwarp();                                                    // every lane is done reading this buffer
         if (lane == 0 && c + 2 < nch) issue(c + 2);
     }

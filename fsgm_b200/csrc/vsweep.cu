@@ -31,9 +31,6 @@ namespace cg = cooperative_groups;
 
 namespace fsgm {
 
-#ifndef FSGM_VS_CARRY
-#define FSGM_VS_CARRY 0
-#endif
 #ifndef FSGM_VS_PDF
 #define FSGM_VS_PDF 3
 #endif
@@ -470,20 +467,15 @@ vsweep_kernel(const VsParams prm)
         // L2 miss (~2 us) is not hidden by other warps (ncu r1g: 27 % of the stall samples of the down pass sat on the first
         // use of the horizontal-volume row).  The ring is indexed statically (inner loop unrolled by PD): copying a register
         // that is still waiting for its load would stall on the copy, which is exactly what a rotating ring does.
-        // (Requesting the next row's first pixels before the row-end barrier was measured slower, 21.9 -> 23.3 ms per 60 pairs;
-        // an L2 prefetch of the same rows at that point changes nothing.)
-#if FSGM_VS_CARRY
-        // the ring is carried across the row barrier: after a slot's last pixel of this row it is refilled with the warp's
-        // pixel of the same slot in the NEXT row, so no load is issued (and waited for) right behind the barrier
-        const uint32_t rowpix_next = (uint32_t)row_y(yy + 1 < H ? yy + 1 : yy) * (uint32_t)W + (uint32_t)xb;
-        const bool has_next = yy + 1 < H;
-        if (yy == 0)
-#endif
-        {
+        // All warps start a row together behind the barrier and wait for their first pixel's rows (ncu r1p: 15 % of the final
+        // pass's stall samples), yet every way of requesting those rows EARLIER was measured slower: the next row's first pixels
+        // before the row-end barrier (21.9 -> 23.3 ms per 60 pairs), the whole ring carried across the barrier (each slot
+        // refilled with its next-row pixel after its last use: 1837 -> 1814 pairs/s, the same with ld.global.cg), the first
+        // pixels' rows staged by bulk copies next to the cost row two rows ahead (1821 -> 1776); an L2 prefetch changes nothing.
+        // The row-synchronous bursts are what DRAM serves best here.
 #pragma unroll
-            for (int u = 0; u < PD; ++u)
-                if (wsub + u * HW < lim) vs_fetch<NREG, FINAL, FAST>(th, rowpix + xl_of(wsub + u * HW), gq[u]);
-        }
+        for (int u = 0; u < PD; ++u)
+            if (wsub + u * HW < lim) vs_fetch<NREG, FINAL, FAST>(th, rowpix + xl_of(wsub + u * HW), gq[u]);
         // warps 0 and HW publish the row's hand-overs from inside their first (edge) pixel; every other warp has nothing to
         // publish and arrives right away
         if (wsub != 0 || lim == 0) cluster_arrive_relaxed();
@@ -494,13 +486,6 @@ vsweep_kernel(const VsParams prm)
                 if (i != wsub) vs_fetch<NREG, FINAL, FAST>(th, rowpix + xl, gq[0]);
                 vs_pixel<NREG, NDIR, FINAL, true, FAST>(th, crow_l, xl, yy, par, off, rowpix + xl, gq[0], i == 0);
             }
-#if FSGM_VS_CARRY
-            if (has_next) {
-#pragma unroll
-                for (int u = 0; u < PD; ++u)
-                    if (wsub + u * HW < lim) vs_fetch<NREG, FINAL, FAST>(th, rowpix_next + xl_of(wsub + u * HW), gq[u]);
-            }
-#endif
         } else {
             // the only edge pixels of a later row are xl = 0 and xl = Wk-1: pixel i = 0 of warps 0 and HW, i.e. ring slot 0 of
             // their first round
@@ -513,9 +498,6 @@ vsweep_kernel(const VsParams prm)
                         if (u == 0 && i == 0) vs_pixel<NREG, NDIR, FINAL, true, FAST>(th, crow_l, xl, yy, par, off, rowpix + xl, gq[u], true);
                         else vs_pixel<NREG, NDIR, FINAL, false, FAST>(th, crow_l, xl, yy, par, off, rowpix + xl, gq[u], false);
                         if (i + PD * HW < lim) vs_fetch<NREG, FINAL, FAST>(th, rowpix + xl_of(i + PD * HW), gq[u]);
-#if FSGM_VS_CARRY
-                        else if (has_next) vs_fetch<NREG, FINAL, FAST>(th, rowpix_next + xl_of(wsub + u * HW), gq[u]);
-#endif
                     }
                 }
             }
