@@ -197,6 +197,38 @@ def test_cluster_path_equals_oracle_and_generic(ctx, oracle, W, H, D, paths, pas
         _cmp_bestD(outs[cluster][2], ref, D)
 
 
+@pytest.mark.parametrize("W,H,D,paths,P1,P2,cluster", [
+    (150, 40, 64, 8, 6, 64, 2), (151, 37, 64, 8, 6, 64, 3), (97, 33, 128, 8, 6, 32, 4), (140, 30, 256, 8, 6, 64, 7),
+    (333, 21, 256, 8, 6, 64, 9), (90, 30, 256, 4, 6, 64, 4), (500, 12, 256, 4, 6, 64, 16), (40, 3, 64, 8, 6, 64, 4),
+    (16, 1, 64, 8, 6, 64, 8), (41, 19, 64, 8, 6, 64, 1),
+    (120, 25, 256, 8, 10, 85, 4),      # 3*P2 = 255: last P2 of the one-byte first pass
+    (120, 25, 256, 8, 10, 86, 4),      # first P2 of the u16 sum volume
+    (120, 25, 128, 8, 0, 103, 5),      # last P2 with the byte-wise pre-add of the horizontal rows
+    (120, 25, 128, 8, 3, 104, 5),      # separate adds
+    (120, 25, 64, 4, 30, 200, 3),      # 4 paths (one direction per pass), large P2: u16 volume, separate adds
+])
+def test_cluster_fast_passes_equal_oracle(ctx, oracle, W, H, D, paths, P1, P2, cluster):
+    """The cluster passes in the configuration the gateways use (no Sp dump): first pass without global loads writing the
+    one-byte sum of L - C, final pass adding the horizontal volumes, winner-take-all on biased fp16 patterns (vsweep.cu
+    FAST), and its fall-backs at the P2 boundaries.  minC and bestD against the oracle and the generic path."""
+    import torch
+    from fsgm_b200 import api
+    p = synth.epipolar_pair(W, H, D, seed=3 * W + cluster)
+    ref = _oracle_epi(oracle, p, D, P1, P2, paths)
+    o = api.epi_opts(paths=paths)
+    Cin, I1, O = _t(ref["C"][None]), _t(p["I1"][None]), _t(p["O"][None])
+    outs = {}
+    for mode in (cluster, -1):
+        ctx.tune(1, mode)
+        b = torch.empty((1, H, W), dtype=torch.int32, device="cuda"); m = torch.empty_like(b)
+        ctx.epi_aggregate_dev(Cin, I1, P1, P2, O, 0.3, b, m, Sp=None, opts=o)
+        outs[mode] = (m.cpu().numpy().view(np.uint32)[0], b.cpu().numpy().view(np.uint32)[0])
+    ctx.tune(1, 0)
+    assert np.array_equal(outs[cluster][0], outs[-1][0]) and np.array_equal(outs[cluster][1], outs[-1][1])
+    assert np.array_equal(outs[cluster][0], ref["minC"])
+    _cmp_bestD(outs[cluster][1], ref, D)
+
+
 def test_full_kitti_size_all_paths_agree(ctx, oracle):
     """BASELINE.json's full size (1242x375, 256 labels, 8 paths): the cluster kernels (a full wave of pairs), the generic
     kernels and the CPU oracle agree bit for bit; the batch result equals the single-pair results."""
