@@ -179,6 +179,11 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly one JSON line: anything a library prints to file descriptor 1 (NCCL's "NCCL version ..." banner
+    # on this image) is sent to stderr, and the line is written through a private duplicate of the original stdout
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if not torch.cuda.is_available():
@@ -316,7 +321,7 @@ def run_ours(args):
             dt = _cpu_one((rows, 1000, use_ref))
             line["cpu_baseline"] = {"value": (rows / H) / dt, "unit": "pairs/s", "cores": 1, "kind": kind,
                                     "sample": f"one {W}x{rows} strip ({rows}/{H} of a pair), D={D}, {PATHS} paths, single thread, {dt:.1f} s"}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
