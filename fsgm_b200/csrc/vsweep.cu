@@ -46,7 +46,7 @@ struct VsParams {
     const uint16_t* Sin;         // optional u16 volume added to the sum (the other pass)
     uint16_t* Sout;              // !FINAL: u16 sum volume; FINAL: optional dump of the total Sp (stage parity), may be null
     uint32_t* minC;              // FINAL: winner-take-all outputs
-    uint16_t* rec;               //        [n][N][4] = argmin, Sp[argmin-1], Sp[argmin+1] (0 if argmin == D-1), Sp[0]
+    uint16_t* rec;               //        [n][N][4] = argmin, Sp[argmin-1], Sp[argmin+1] (don't-care at argmin 0 / D-1), Sp[0]
     int W, H, Wk, P1, P2;
     int up;                      // 0: rows 0..H-1 with directions (0,+1)(+1,+1)(-1,+1); 1: rows H-1..0, negated
     int fast;                    // the FAST operand configuration (see vs_fetch): Sin / Sout are BYTE volumes
@@ -350,7 +350,10 @@ __device__ __forceinline__ void vs_pixel(const VsThread<NREG>& th, uint32_t crow
             const uint32_t idx = key & 0xFFFFu;
             th.minC[pix] = (key >> 16) - (FAST ? (H2_BIAS2 & 0xFFFFu) : 0u);
             uint16_t* r = th.rec + (size_t)pix * 4;
-            const uint16_t c_1 = idx > 0 ? ws[idx - 1] : 0, c1 = idx + 1 < (uint32_t)D ? ws[idx + 1] : 0;
+            // unconditional neighbour reads: for idx == 0 / idx == D-1 they land in the adjacent shared-memory words (inside the
+            // allocation) and vs_finalize_kernel never looks at those fields (label 0 and 1 are not refined, label D-1 takes the
+            // next pixel's Sp[0]) — two predicated branches less in a section the whole warp waits for
+            const uint16_t c_1 = ws[(int)idx - 1], c1 = ws[idx + 1];
             *reinterpret_cast<uint2*>(r) = make_uint2(idx | ((uint32_t)c_1 << 16), (uint32_t)c1 | (acc[0] << 16));      // lane 0's acc[0] low half = Sp[0]
         }
         __syncwarp();
