@@ -180,8 +180,8 @@ int launch_epi_cost(fsgm_ctx* c, int n, const double* d_vz, const uint32_t* cen1
 // =====================================================================================================
 // Fused cost kernel: raw Hamming cost and the 5x5 box filter in one pass, the raw volume never touches HBM.
 //
-// A CTA owns a strip of FC_TX output columns and marches down FC_TY rows.  Per image row it (1) evaluates the raw
-// cost of the FC_TX+4 columns (2-px halo, replicate border = clamped coordinates) for all D labels into shared
+// A CTA owns a strip of TX = fc_tx(D/4) output columns and marches down FC_TY rows.  Per image row it (1) evaluates the raw
+// cost of the TX+4 columns (2-px halo, replicate border = clamped coordinates) for all D labels into shared
 // memory, (2) forms the horizontal 5-sums, keeps them in a 5-row shared-memory ring and, once five rows are in,
 // emits the vertical sum normalised to (2*s+25)/50 as u8, label-contiguous.  Redundant work: (TX+4)/TX * (TY+4)/TY.
 //
@@ -195,10 +195,13 @@ int launch_epi_cost(fsgm_ctx* c, int n, const double* d_vz, const uint32_t* cen1
 // so one unsigned conversion, an add, a shift and an unsigned min reproduce all of it — except NaN, for which the
 // hardware conversion does not return 0.  NaN can only appear when an input is non-finite or |offset| is so large
 // that offset*vz overflows (inf*0); such pixels are flagged while staging and take a checked path.
-#ifndef FSGM_FC_TX
-#define FSGM_FC_TX 32
-#endif
-constexpr int FC_TX = FSGM_FC_TX, FC_THREADS = 256;      // strip width; rows per CTA are chosen at launch (32..128)
+// Raw-cost phase mapping: LANE = PIXEL of the strip row (strip + halo = 32 pixels at D = 256), warp = a set of label quads.
+// Neighbouring pixels look at neighbouring census words for the same label, so one gather instruction touches 4-5 sectors; with
+// the former mapping (lane = label quad of ONE pixel) a warp's 32 addresses were strung along the epipolar line, 17 sectors
+// and 5.6 L1 wavefronts per request, and the L1 data pipe (67 % busy, ncu r1q) limited the kernel as much as instruction issue.
+// The pixel's geometry stays in registers for the whole row; the labels' vz values are warp-uniform shared-memory reads.
+constexpr int FC_THREADS = 256;                          // rows per CTA are chosen at launch (32..128)
+__host__ __device__ constexpr int fc_tx(int D4) { return D4 == 64 ? 28 : D4 == 32 ? 24 : 16; }      // strip width: TX + 4 <= 32 lanes, TX % (256 / D4) == 0
 
 __device__ __forceinline__ uint32_t ref_round_clamp_w(double w, uint32_t hi)
 {
@@ -214,26 +217,27 @@ __device__ __forceinline__ uint32_t box_norm4_fast(uint32_t lo, uint32_t hi)   /
     return __byte_perm(__byte_perm(p0, p1, 0x0062), __byte_perm(p2, p3, 0x0062), 0x5410);
 }
 
-// measured (60 pairs, cost stage): 4 CTAs/SM + full unroll 11.17 ms, 4 + unroll 3 11.75, 3 CTAs/SM 11.29, no unroll at 108 registers 13.9
+// measured (60 pairs, cost stage, former lane = label-quad mapping): 4 CTAs/SM + full unroll 11.17 ms, 4 + unroll 3 11.75, 3 CTAs/SM 11.29,
+// no unroll at 108 registers 13.9
 #ifndef FSGM_FC_MINB
 #define FSGM_FC_MINB 4
 #endif
-#ifndef FSGM_FC_UNROLL
-#define FSGM_FC_UNROLL 9
-#endif
-constexpr int FC_UNROLL = FSGM_FC_UNROLL;
 template <int D4>      // D = 4*D4 labels, D4 in {16, 32, 64}
 __global__ void __launch_bounds__(FC_THREADS, FSGM_FC_MINB)
 epi_cost_fused_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restrict__ cen2,
                       const double* __restrict__ Pd0, const double* __restrict__ dirn, const double* __restrict__ O,
                       const double* __restrict__ vz, int W, int H, int FC_TY, uint8_t* __restrict__ C)
 {
-    constexpr int NPIX = FC_TX + 4, IPT = FC_THREADS / D4, XP = FC_TX / IPT;   // XP consecutive output columns per thread
+    constexpr int FC_TX = fc_tx(D4), NPIX = FC_TX + 4, IPT = FC_THREADS / D4, XP = FC_TX / IPT;   // XP consecutive output columns per thread
+    constexpr int D4S = D4 + 1;                      // raw-row pitch in words: lanes write different pixels of one quad (bank = pixel + quad)
+    constexpr int QPW = D4 / (FC_THREADS / 32);      // label quads per warp in the raw-cost phase
+    static_assert(NPIX <= 32 && FC_TX % IPT == 0 && QPW >= 1, "strip geometry");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t* raw_row = reinterpret_cast<uint32_t*>(smem_raw);                              // [NPIX][D4]
-    uint32_t* hring = raw_row + NPIX * D4;                                                  // [5][FC_TX][D4]
-    double* geo = reinterpret_cast<double*>(hring + 5 * FC_TX * D4);                        // [2][NPIX][5]
-    uint32_t* gcen = reinterpret_cast<uint32_t*>(geo + 2 * NPIX * 5);                       // [2][NPIX]
+    double* vzs = reinterpret_cast<double*>(smem_raw);                                      // [4*D4]
+    double* geo = vzs + 4 * D4;                                                             // [2][NPIX][5]
+    uint32_t* raw_row = reinterpret_cast<uint32_t*>(geo + 2 * NPIX * 5);                    // [NPIX][D4S]
+    uint32_t* hring = raw_row + NPIX * D4S;                                                 // [5][FC_TX][D4]
+    uint32_t* gcen = hring + 5 * FC_TX * D4;                                                // [2][NPIX]
 
     const size_t N = (size_t)W * H;
     const int pair = blockIdx.z, x0 = blockIdx.x * FC_TX, y0 = blockIdx.y * FC_TY;
@@ -244,7 +248,8 @@ epi_cost_fused_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restr
     const double* DrX = dirn + (size_t)pair * 2 * N; const double* DrY = DrX + N;
     const double* Op = O + pair * N;
     uint32_t* Cout = reinterpret_cast<uint32_t*>(C + pair * N * (size_t)(4 * D4)) + q;
-    const double vz0 = vz[4 * q], vz1 = vz[4 * q + 1], vz2 = vz[4 * q + 2], vz3 = vz[4 * q + 3];
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 4 * D4; i += FC_THREADS) vzs[i] = vz[i];
     const int yend = min(y0 + FC_TY, H);
     const uint32_t wmax = (uint32_t)(W - 1), hmax = (uint32_t)(H - 1);
 
@@ -283,53 +288,54 @@ epi_cost_fused_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restr
         if (tid < NPIX && more) load_geo(r + 1, ga, gc);
         const double* geo_r = geo + buf * NPIX * 5;
         const uint32_t* gcen_r = gcen + buf * NPIX;
-        // (1) raw cost of NPIX pixels x D labels
-        if (!slow) {
-#pragma unroll FC_UNROLL
-            for (int i = i0; i < NPIX; i += IPT) {
-                const double bx = geo_r[i * 5], by = geo_r[i * 5 + 1], ux = geo_r[i * 5 + 2], uy = geo_r[i * 5 + 3], off = geo_r[i * 5 + 4];
-                const uint32_t c1 = gcen_r[i];
-                uint32_t packed = 0;
-                const double vzs[4] = {vz0, vz1, vz2, vz3};
+        // (1) raw cost of NPIX pixels x D labels: this lane's pixel, this warp's label quads
+        if (lane < NPIX) {
+            const double bx = geo_r[lane * 5], by = geo_r[lane * 5 + 1], ux = geo_r[lane * 5 + 2], uy = geo_r[lane * 5 + 3], off = geo_r[lane * 5 + 4];
+            const uint32_t c1 = gcen_r[lane];
+            uint32_t* rr_out = raw_row + lane * D4S;
+            if (!slow) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const double t = __dmul_rn(off, vzs[j]);
-                    const uint32_t x2 = ref_round_clamp_w(__dadd_rn(bx, __dmul_rn(t, ux)), wmax);
-                    const uint32_t y2 = ref_round_clamp_w(__dadd_rn(by, __dmul_rn(t, uy)), hmax);
-                    packed |= (uint32_t)__popc(c1 ^ __ldg(reinterpret_cast<const uint32_t*>(c2b + (y2 * W4 + x2 * 4u)))) << (8 * j);
-                }
-                raw_row[i * D4 + q] = packed;
-            }
-        } else {
-            for (int i = i0; i < NPIX; i += IPT) {
-                const double bx = geo_r[i * 5], by = geo_r[i * 5 + 1], ux = geo_r[i * 5 + 2], uy = geo_r[i * 5 + 3], off = geo_r[i * 5 + 4];
-                const uint32_t c1 = gcen_r[i];
-                uint32_t packed = 0;
-                const double vzs[4] = {vz0, vz1, vz2, vz3};
+                for (int k = 0; k < QPW; ++k) {
+                    const int qq = warp * QPW + k;
+                    uint32_t packed = 0;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const double t = __dmul_rn(off, vzs[j]);
-                    const double wx = __dadd_rn(bx, __dmul_rn(t, ux)), wy = __dadd_rn(by, __dmul_rn(t, uy));
-                    const uint32_t x2 = (wx != wx) ? 0u : ref_round_clamp_w(wx, wmax);
-                    const uint32_t y2 = (wy != wy) ? 0u : ref_round_clamp_w(wy, hmax);
-                    packed |= (uint32_t)__popc(c1 ^ __ldg(reinterpret_cast<const uint32_t*>(c2b + (y2 * W4 + x2 * 4u)))) << (8 * j);
+                    for (int j = 0; j < 4; ++j) {
+                        const double t = __dmul_rn(off, vzs[4 * qq + j]);
+                        const uint32_t x2 = ref_round_clamp_w(__dadd_rn(bx, __dmul_rn(t, ux)), wmax);
+                        const uint32_t y2 = ref_round_clamp_w(__dadd_rn(by, __dmul_rn(t, uy)), hmax);
+                        packed |= (uint32_t)__popc(c1 ^ __ldg(reinterpret_cast<const uint32_t*>(c2b + (y2 * W4 + x2 * 4u)))) << (8 * j);
+                    }
+                    rr_out[qq] = packed;
                 }
-                raw_row[i * D4 + q] = packed;
+            } else {
+                for (int k = 0; k < QPW; ++k) {
+                    const int qq = warp * QPW + k;
+                    uint32_t packed = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const double t = __dmul_rn(off, vzs[4 * qq + j]);
+                        const double wx = __dadd_rn(bx, __dmul_rn(t, ux)), wy = __dadd_rn(by, __dmul_rn(t, uy));
+                        const uint32_t x2 = (wx != wx) ? 0u : ref_round_clamp_w(wx, wmax);
+                        const uint32_t y2 = (wy != wy) ? 0u : ref_round_clamp_w(wy, hmax);
+                        packed |= (uint32_t)__popc(c1 ^ __ldg(reinterpret_cast<const uint32_t*>(c2b + (y2 * W4 + x2 * 4u)))) << (8 * j);
+                    }
+                    rr_out[qq] = packed;
+                }
             }
         }
         __syncthreads();
         // (2) horizontal 5-sums by a sliding window over this thread's XP consecutive columns; vertical 5-sums as
         //     running sums (add the new row, drop the row that leaves the window: it sits in the ring slot being rewritten)
         const int slot = (r + 10) % 5;
-        const uint32_t* rr = raw_row + (i0 * XP) * D4 + q;
+        const uint32_t* rr = raw_row + (i0 * XP) * D4S + q;
         uint32_t* hr = hring + (slot * FC_TX + i0 * XP) * D4 + q;
-        uint32_t h = rr[0] + rr[D4] + rr[2 * D4] + rr[3 * D4] + rr[4 * D4];               // bytes <= 120: no carries
+        uint32_t h = rr[0] + rr[D4S] + rr[2 * D4S] + rr[3 * D4S] + rr[4 * D4S];           // bytes <= 120: no carries
         const int yo = r - 2;
         const bool emit = yo >= y0;
         uint32_t* crow = Cout + ((size_t)yo * W + x0 + i0 * XP) * D4;
 #pragma unroll
         for (int k = 0; k < XP; ++k) {
-            if (k) h = h - rr[(k - 1) * D4] + rr[(k + 4) * D4];
+            if (k) h = h - rr[(k - 1) * D4S] + rr[(k + 4) * D4S];
             const uint32_t old = hr[k * D4];
             hr[k * D4] = h;
             vlo[k] += (h & 0x00FF00FFu) - (old & 0x00FF00FFu);
@@ -343,7 +349,8 @@ epi_cost_fused_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restr
 
 static size_t fused_cost_smem(int D4)
 {
-    return (size_t)(FC_TX + 4) * D4 * 4 + (size_t)5 * FC_TX * D4 * 4 + 2 * ((size_t)(FC_TX + 4) * 5 * 8 + (size_t)(FC_TX + 4) * 4) + 64;
+    const size_t tx = fc_tx(D4), npix = tx + 4;
+    return (size_t)4 * D4 * 8 + 2 * npix * 5 * 8 + npix * (D4 + 1) * 4 + 5 * tx * D4 * 4 + 2 * npix * 4 + 64;
 }
 
 // returns FSGM_OK and sets *done = true if the fused kernel handles this label count
@@ -358,8 +365,9 @@ int launch_epi_cost_fused(fsgm_ctx* c, int n, const double* d_vz, const uint32_t
     const size_t smem = fused_cost_smem(D4);
     // rows per CTA: tall strips waste less on the 4 warm-up rows, but a small batch needs enough CTAs to fill the GPU
     int ty = 128;
-    while (ty > 32 && (size_t)((W + FC_TX - 1) / FC_TX) * ((H + ty - 1) / ty) * n < (size_t)c->sm_count * 8) ty >>= 1;
-    dim3 grid((W + FC_TX - 1) / FC_TX, (H + ty - 1) / ty, n);
+    const int tx = fc_tx(D4);
+    while (ty > 32 && (size_t)((W + tx - 1) / tx) * ((H + ty - 1) / ty) * n < (size_t)c->sm_count * 8) ty >>= 1;
+    dim3 grid((W + tx - 1) / tx, (H + ty - 1) / ty, n);
 #define FSGM_FC(D4V)                                                                                              \
     do {                                                                                                          \
         const unsigned bit = 1u << (D4V == 16 ? 0 : D4V == 32 ? 1 : 2);                                           \
