@@ -35,7 +35,7 @@ sys.path.insert(0, ROOT)
 
 W, H, D, PATHS, P1, P2, VMAX = 1242, 375, 256, 8, 6, 64, 0.3
 METRIC = "frame-pairs/s (KITTI 1242x375, 256 labels, 8 paths)"
-TRAFFIC_VSWEEP_P15 = 5.387e9   # dram read+write bytes per launch at 15 pairs: mean of the first (1.79 + 1.74 GB) and final (7.15 + 0.09 GB) pass, profiles/r1p_vsweep_kernels_p15.txt
+TRAFFIC_VSWEEP_P15 = 5.387e9   # dram read+write bytes per launch at 15 pairs: mean of the first (1.79 + 1.74 GB) and final (7.15 + 0.09 GB) pass, profiles/r1s_kernels_p15.txt
 
 
 def hbm_peak():
@@ -280,7 +280,7 @@ def run_ours(args):
             # launches are per wave and per pass: pairs per launch = (pairs in the timed region * 2 passes) / launches
             pairs_per_launch = P * args.steps * 2.0 / k_launches
             per_launch_bytes = pairs_per_launch * N * D * 9
-            # dram__bytes_read+write per launch from profiles/r1p_vsweep_kernels_p15.txt (ncu --set full, 15 pairs per launch),
+            # dram__bytes_read+write per launch from profiles/r1s_kernels_p15.txt (ncu --set full, 15 pairs per launch),
             # mean of the two passes, scaled to the pairs one launch handles
             traffic = (TRAFFIC_VSWEEP_P15 * pairs_per_launch / 15.0) if TRAFFIC_VSWEEP_P15 else None
         else:
