@@ -261,6 +261,8 @@ epi_cost_fused_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restr
     // Geometry of a row is staged in a double buffer: the global loads for row r+1 are issued before the raw-cost phase of row r
     // and written to shared memory after its box phase, so their latency hides under the arithmetic and a row needs two
     // barriers instead of three.  `slow` = some pixel of the strip row can produce NaN (checked path, CTA-uniform branch).
+    // (One barrier per row — raw row double-buffered, geometry staged two rows ahead, vz read with __ldg — was measured slower,
+    // 10.15 -> 10.59 ms per 60 pairs: at four CTAs per SM the extra 7 KB per CTA leave the gathers half the L1.)
     auto load_geo = [&](int r, double (&a)[5], uint32_t& cen) {
         const int yc = min(max(r, 0), H - 1), xc = min(max(x0 - 2 + tid, 0), W - 1);
         const size_t p = (size_t)yc * W + xc;
