@@ -240,6 +240,122 @@ pyd_sweep_kernel(const PydSweepParams prm)
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// cost volume, lane = pixel: a warp owns 32 consecutive pixels of a row.  For one label and one window tap the 32 lanes read
+// neighbouring census words (the prior is piecewise constant over a warp in practice), so a gather touches 4-5 sectors
+// instead of the ~20 of the one-warp-per-pixel kernel above, whose lanes spread over the search window.  Per label column ox
+// the T x (2ry+T) reference census words the column needs are gathered ONCE into shared memory ([row][tap][lane], conflict
+// free); the T*T taps of its Sy labels are then LDS + XOR + POPC + IADD each.  The constant-5 rule (sample or window pixel
+// outside the image, calc_pyd_cost_sgm.cpp:405-421) is a per-lane validity word per row / column, all-ones in the interior,
+// so the inner loop stays branch-free.  Results go through a shared-memory tile and leave as one contiguous run of bytes.
+// ------------------------------------------------------------------------------------------------
+constexpr int PYC_WARPS = 4;
+template <int AGG>
+__global__ void __launch_bounds__(PYC_WARPS * 32)
+pyd_cost_px_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restrict__ cen2, int W, int H,
+                   const double* __restrict__ preMv, int mvW, int mvH, int rx, int ry, uint8_t* __restrict__ C)
+{
+    constexpr int T = 2 * AGG + 1, WPX = T * T;
+    extern __shared__ __align__(16) unsigned char pyc_smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int Sx = 2 * rx + 1, Sy = 2 * ry + 1, D = Sx * Sy, SX2 = Sx + T - 1, SY2 = Sy + T - 1;
+    // per warp: fx[SX2][32], fy[SY2][32] (int), V[SY2][T][32] (u32), tile[32][D] (u8, padded to 16 bytes)
+    const size_t per_warp = (size_t)(SX2 + SY2) * 32 * 4 + (size_t)SY2 * T * 32 * 4 + (((size_t)32 * D + 15) & ~(size_t)15);
+    unsigned char* base = pyc_smem + wib * per_warp;
+    int* fx = reinterpret_cast<int*>(base);
+    int* fy = fx + SX2 * 32;
+    uint32_t* V = reinterpret_cast<uint32_t*>(fy + SY2 * 32);
+    uint8_t* tile = reinterpret_cast<uint8_t*>(V + SY2 * T * 32);
+
+    const int xblocks = (W + 31) / 32;
+    const int job = blockIdx.x * PYC_WARPS + wib;
+    if (job >= xblocks * H) return;                      // warps are independent (only __syncwarp below)
+    const int y = job / xblocks, x0 = (job - y * xblocks) * 32, x = min(x0 + lane, W - 1);      // lanes past the row end repeat its last pixel
+    const int nlive = min(32, W - x0);
+    const size_t N = (size_t)W * H;
+    const int pair = blockIdx.y;
+    const double* mvp = preMv + (size_t)pair * 2 * mvW * mvH;
+    const double mvx = mvp[(size_t)mvW * y + x], mvy = mvp[(size_t)mvW * mvH + (size_t)mvW * y + x];
+    const uint32_t* c1 = cen1 + pair * N;
+    const uint32_t* c2 = cen2 + pair * N;
+
+    // sample coordinates: x2 depends only on s = offx + ax (tabulated per lane), -1 = outside the image; same for y
+    for (int sI = 0; sI < SX2; ++sI) {
+        const int v = x86_d2i(__dadd_rn(__dadd_rn((double)(sI - rx - AGG + x), mvx), 0.5));
+        fx[sI * 32 + lane] = (v < 0 || v > W - 1) ? -1 : v;
+    }
+    for (int sI = 0; sI < SY2; ++sI) {
+        const int v = x86_d2i(__dadd_rn(__dadd_rn((double)(sI - ry - AGG + y), mvy), 0.5));
+        fy[sI * 32 + lane] = (v < 0 || v > H - 1) ? -1 : v;
+    }
+    // window taps of the current image; a tap outside the image contributes the constant
+    uint32_t t1[T][T];
+    uint32_t tapok = 0;                                   // bit ay*T+ax
+#pragma unroll
+    for (int ay = 0; ay < T; ++ay)
+#pragma unroll
+        for (int ax = 0; ax < T; ++ax) {
+            const int x1 = x + ax - AGG, y1 = y + ay - AGG;
+            const bool in = x1 >= 0 && x1 < W && y1 >= 0 && y1 < H;
+            t1[ay][ax] = in ? __ldg(c1 + (size_t)W * y1 + x1) : 0u;
+            tapok |= (in ? 1u : 0u) << (ay * T + ax);
+        }
+    __syncwarp();
+    bool rows_ok = tapok == (1u << WPX) - 1u;             // every window tap inside the image and every sample row valid
+    for (int sI = 0; sI < SY2; ++sI) rows_ok &= fy[sI * 32 + lane] >= 0;
+
+    for (int ox = 0; ox < Sx; ++ox) {
+        // column validity (bit ax) and the T x SY2 reference words of this label column
+        int fxv[T];
+        uint32_t colok = 0;
+#pragma unroll
+        for (int ax = 0; ax < T; ++ax) { fxv[ax] = fx[(ox + ax) * 32 + lane]; colok |= (fxv[ax] >= 0 ? 1u : 0u) << ax; }
+        for (int sy = 0; sy < SY2; ++sy) {
+            const int yy = fy[sy * 32 + lane];
+            const uint32_t* row = c2 + (size_t)W * max(yy, 0);
+#pragma unroll
+            for (int ax = 0; ax < T; ++ax) V[(sy * T + ax) * 32 + lane] = __ldg(row + max(fxv[ax], 0));
+        }
+        __syncwarp();
+        // every tap of every label of the column is valid for every lane -> no checks (the interior of the image)
+        const bool clean = __all_sync(0xffffffffu, rows_ok && colok == (1u << T) - 1u);
+        for (int oy = 0; oy < Sy; ++oy) {
+            uint32_t sum = 0;
+            const uint32_t* Vl = V + (oy * T) * 32 + lane;
+            if (clean) {
+#pragma unroll
+                for (int ay = 0; ay < T; ++ay)
+#pragma unroll
+                    for (int ax = 0; ax < T; ++ax) sum += __popc(t1[ay][ax] ^ Vl[(ay * T + ax) * 32]);
+            } else {
+#pragma unroll
+                for (int ay = 0; ay < T; ++ay) {
+                    const bool rowok = fy[(oy + ay) * 32 + lane] >= 0;
+#pragma unroll
+                    for (int ax = 0; ax < T; ++ax) {
+                        const bool ok = rowok && ((colok >> ax) & 1u) && ((tapok >> (ay * T + ax)) & 1u);
+                        sum += ok ? (uint32_t)__popc(t1[ay][ax] ^ Vl[(ay * T + ax) * 32]) : 5u;
+                    }
+                }
+            }
+            // (u8)(1.0*s/wp + 0.5) == (2s + wp) / (2wp) in integers (see pyd_cost_kernel)
+            tile[lane * D + ox * Sy + oy] = (uint8_t)((2 * sum + WPX) / (2 * WPX));
+        }
+        __syncwarp();
+    }
+    // the warp's pixels are consecutive and so are their label rows: one contiguous run of nlive * D bytes
+    uint8_t* out = C + (pair * N + (size_t)y * W + x0) * D;
+    const int nbytes = nlive * D;
+    for (int i = lane; i < nbytes; i += 32) out[i] = tile[i];
+}
+
+static size_t pyd_cost_px_smem(int agg, int rx, int ry)
+{
+    const int T = 2 * agg + 1, Sx = 2 * rx + 1, Sy = 2 * ry + 1, SX2 = Sx + T - 1, SY2 = Sy + T - 1;
+    const size_t per_warp = (size_t)(SX2 + SY2) * 32 * 4 + (size_t)SY2 * T * 32 * 4 + (((size_t)32 * Sx * Sy + 15) & ~(size_t)15);
+    return per_warp * PYC_WARPS;
+}
+
 int launch_pyd_cost(fsgm_ctx* c, int n, const uint32_t* cen1, const uint32_t* cen2, int W, int H,
                     const double* preMv, int mvW, int mvH, int agg, int rx, int ry, uint8_t* C)
 {
@@ -247,6 +363,21 @@ int launch_pyd_cost(fsgm_ctx* c, int n, const uint32_t* cen1, const uint32_t* ce
     if (2 * (rx + agg) + 1 > PYD_MAXS + 32 || 2 * (ry + agg) + 1 > PYD_MAXS + 32)
         return fail(c, FSGM_ERR_DOMAIN, "search + aggregation window too large");
     const size_t N = (size_t)W * H;
+    // lane = pixel kernel for the aggregation windows in use (5x5, 3x3) when its per-warp staging fits; else one warp per pixel
+    const size_t smem = (agg == 1 || agg == 2) ? pyd_cost_px_smem(agg, rx, ry) : 0;
+    if (smem && smem <= 100 * 1024) {
+        const int jobs = ((W + 31) / 32) * H;
+        dim3 grid((unsigned)((jobs + PYC_WARPS - 1) / PYC_WARPS), n);
+        if (agg == 2) {
+            FSGM_CUDA(c, cudaFuncSetAttribute(pyd_cost_px_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            pyd_cost_px_kernel<2><<<grid, PYC_WARPS * 32, smem, c->stream>>>(cen1, cen2, W, H, preMv, mvW, mvH, rx, ry, C);
+        } else {
+            FSGM_CUDA(c, cudaFuncSetAttribute(pyd_cost_px_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            pyd_cost_px_kernel<1><<<grid, PYC_WARPS * 32, smem, c->stream>>>(cen1, cen2, W, H, preMv, mvW, mvH, rx, ry, C);
+        }
+        FSGM_LAUNCHED(c);
+        return FSGM_OK;
+    }
     dim3 grid((unsigned)((N + 7) / 8), n);
     pyd_cost_kernel<<<grid, 256, 0, c->stream>>>(cen1, cen2, W, H, preMv, mvW, mvH, agg, rx, ry, C);
     FSGM_LAUNCHED(c);
