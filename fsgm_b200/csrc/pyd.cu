@@ -96,12 +96,20 @@ struct PydSweepParams {
 // include the centre of the 5x5 label neighbourhood (min(Lc, min(Lc, rest)+P1) == min(Lc, rest+P1) for P1 >= 0), which
 // makes it a separable 5+5 minimum: R[tx][sy] = min over the y-window of column tx, then a min over the x-window of R.
 // 10 shared-memory taps per label instead of 24.  Outside the domain the direct form reproduces every u8 truncation.
+// Shared-memory layout: the previous row lives in a PADDED label grid, column pitch P = Sy + 2 with two leading pad bytes per
+// column (the two trailing pads of a column are the leading pads of the next) and the y-window minima R in the same grid with
+// two more pad columns on either side; pads hold 255, which never beats the far term (M + P2 <= 255 - P1 in the FAST domain).
+// When the prior does not change between the two pixels of a step (ddx = ddy = 0: always at the coarsest level, and wherever
+// the 2x-upsampled prior is locally constant) the predecessor of label (sx, sy) is (sx, sy) itself and both 5-tap minima
+// are five unconditional byte loads at fixed offsets — no coordinate tables, no bounds tests.
 template <int NJ, bool FAST>
 __global__ void __launch_bounds__(PYD_WARPS * 32)
 pyd_sweep_kernel(const PydSweepParams prm)
 {
-    __shared__ uint8_t Ls[PYD_WARPS][2][NJ * 32];
-    __shared__ uint8_t Rs[PYD_WARPS][FAST ? NJ * 32 : 4];
+    constexpr int LS_SZ = NJ * 32 + 2 * PYD_MAXS + 8;              // Sx * (Sy + 2) + 2
+    constexpr int RS_SZ = NJ * 32 + 6 * PYD_MAXS + 16;             // (Sx + 4) * (Sy + 2) + 2
+    __shared__ uint8_t Ls[PYD_WARPS][2][LS_SZ];
+    __shared__ uint8_t Rs[PYD_WARPS][FAST ? RS_SZ : 4];
     __shared__ int xt[PYD_WARPS][PYD_MAXS], yt[PYD_WARPS][PYD_MAXS];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int gw = blockIdx.x * PYD_WARPS + wib;
@@ -111,6 +119,7 @@ pyd_sweep_kernel(const PydSweepParams prm)
     const int line = gw - prm.line_start[k], r = prm.dir[k];
     const int dx = dir_dx(r), dy = dir_dy(r);
     const int W = prm.W, H = prm.H, Sx = prm.Sx, Sy = prm.Sy, D = Sx * Sy, mvW = prm.mvW;
+    const int P = Sy + 2;                                          // column pitch of the padded grids
     const size_t N = (size_t)W * H, mvN = (size_t)mvW * prm.mvH;
     const uint8_t* __restrict__ Cb = prm.C + blockIdx.y * N * D;
     uint8_t* __restrict__ Lb = prm.L[k] + blockIdx.y * N * D;
@@ -122,27 +131,33 @@ pyd_sweep_kernel(const PydSweepParams prm)
     if (dy == 0) { y = line; x = dx > 0 ? 0 : W - 1; len = W; }
     else         { x = line; y = dy > 0 ? 0 : H - 1; len = H; }
 
-    // per-lane label geometry (d = lane + 32 j)
-    int lsx[NJ], lsy[NJ];
+    // per-lane label geometry (d = lane + 32 j) and the label's place in the padded grid
+    int lsx[NJ], lsy[NJ], pidx[NJ];
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) { int d = lane + 32 * j; lsx[j] = d / Sy; lsy[j] = d - lsx[j] * Sy; }
+    for (int j = 0; j < NJ; ++j) { int d = lane + 32 * j; lsx[j] = d / Sy; lsy[j] = d - lsx[j] * Sy; pidx[j] = lsx[j] * P + 2 + lsy[j]; }
+    for (int i = lane; i < 2 * LS_SZ; i += 32) (&Ls[wib][0][0])[i] = 255;
+    if (FAST) for (int i = lane; i < RS_SZ; i += 32) Rs[wib][i] = 255;
+    __syncwarp();
 
     uint32_t M = 0;
     int cur = 0, px = 0, py = 0;
     uint8_t cnext[NJ];
 #pragma unroll
     for (int j = 0; j < NJ; ++j) { int d = lane + 32 * j; cnext[j] = d < D ? __ldg(Cb + ((size_t)y * W + x) * D + d) : 0; }
+    // the prior at the current pixel travels with the cost row: loaded one step ahead, handed on to the next step as "previous"
+    double mxc = mvx[(size_t)y * mvW + x], myc = mvy[(size_t)y * mvW + x], mxp = 0.0, myp = 0.0, mxn = 0.0, myn = 0.0;
 
     for (int t = 0; t < len; ++t) {
         uint8_t c[NJ];
 #pragma unroll
         for (int j = 0; j < NJ; ++j) c[j] = cnext[j];
-        // next position + prefetch of its cost row
+        // next position + prefetch of its cost row and prior
         int nx = x, ny = y;
         if (dy == 0) nx += dx; else { ny += dy; nx += dx; nx = nx < 0 ? W - 1 : (nx >= W ? 0 : nx); }
         if (t + 1 < len) {
 #pragma unroll
             for (int j = 0; j < NJ; ++j) { int d = lane + 32 * j; cnext[j] = d < D ? __ldg(Cb + ((size_t)ny * W + nx) * D + d) : 0; }
+            mxn = mvx[(size_t)ny * mvW + nx]; myn = mvy[(size_t)ny * mvW + nx];
         }
         const size_t pix = (size_t)y * W + x;
         const bool start = (t == 0) || (dy != 0 && dx != 0 && x == (dx > 0 ? 0 : W - 1));
@@ -151,14 +166,38 @@ pyd_sweep_kernel(const PydSweepParams prm)
         uint32_t m = 255;
         if (start) {
 #pragma unroll
-            for (int j = 0; j < NJ; ++j) Lnew[lane + 32 * j] = c[j];
+            for (int j = 0; j < NJ; ++j) if (lane + 32 * j < D) Lnew[pidx[j]] = c[j];
             M = 0;
             __syncwarp();
         } else {
             int P2 = prm.P2;
             if (prm.adaptive && abs((int)Ib[pix] - (int)Ib[(size_t)py * W + px]) > 50) P2 = P2 / 8;
-            const double ddx = __dsub_rn(mvx[(size_t)y * mvW + x], mvx[(size_t)py * mvW + px]);
-            const double ddy = __dsub_rn(mvy[(size_t)y * mvW + x], mvy[(size_t)py * mvW + px]);
+            const double ddx = __dsub_rn(mxc, mxp), ddy = __dsub_rn(myc, myp);
+            const uint32_t far_ = (M + (uint32_t)P2) & 0xFFu;
+            if (FAST && ddx == 0.0 && ddy == 0.0) {
+                // predecessor label = the label itself ((int)(s + 0.0 + 0.5) == s): fixed offsets in the padded grids
+                uint8_t* R = Rs[wib] + 2 * P;                        // skip the two pad columns
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    if (lane + 32 * j < D) {
+                        const uint8_t* q = Lpre + pidx[j];
+                        const uint32_t r5 = min(min(min((uint32_t)q[-2], (uint32_t)q[-1]), min((uint32_t)q[0], (uint32_t)q[1])), (uint32_t)q[2]);
+                        R[pidx[j]] = (uint8_t)r5;
+                    }
+                }
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    if (lane + 32 * j < D) {
+                        const uint8_t* q = R + pidx[j];
+                        const uint32_t m5 = min(min(min((uint32_t)q[-2 * P], (uint32_t)q[-P]), min((uint32_t)q[0], (uint32_t)q[P])), (uint32_t)q[2 * P]);
+                        const uint32_t best = min(min(far_, m5 + (uint32_t)prm.P1), (uint32_t)Lpre[pidx[j]]);
+                        const uint32_t l = c[j] + best - M;
+                        Lnew[pidx[j]] = (uint8_t)l;
+                        m = min(m, l);
+                    }
+                }
+            } else {
             for (int s = lane; s < Sx; s += 32) {
                 int v = x86_d2i(__dadd_rn(__dadd_rn((double)s, ddx), 0.5));
                 xt[wib][s] = min(max(v, -8), Sx + 8);          // anything further out behaves the same: no neighbour inside
@@ -168,22 +207,21 @@ pyd_sweep_kernel(const PydSweepParams prm)
                 yt[wib][s] = min(max(v, -8), Sy + 8);
             }
             __syncwarp();
-            const uint32_t far_ = (M + (uint32_t)P2) & 0xFFu;
             if (FAST) {
-                uint8_t* R = Rs[wib];
+                uint8_t* R = Rs[wib] + 2 * P;
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) {                       // pass 1: y-window minimum for cell (tx, sy')
                     const int d = lane + 32 * j;
                     if (d < D) {
                         const int yp = yt[wib][lsy[j]];
-                        const uint8_t* col = Lpre + lsx[j] * Sy;
+                        const uint8_t* col = Lpre + lsx[j] * P + 2;
                         uint32_t r = 255;
 #pragma unroll
                         for (int kk = -2; kk <= 2; ++kk) {
                             const int ty = yp + kk;
                             if ((unsigned)ty < (unsigned)Sy) r = min(r, (uint32_t)col[ty]);
                         }
-                        R[d] = (uint8_t)r;
+                        R[pidx[j]] = (uint8_t)r;
                     }
                 }
                 __syncwarp();
@@ -196,12 +234,12 @@ pyd_sweep_kernel(const PydSweepParams prm)
 #pragma unroll
                         for (int mm = -2; mm <= 2; ++mm) {
                             const int tx = xp + mm;
-                            if ((unsigned)tx < (unsigned)Sx) m5 = min(m5, (uint32_t)R[tx * Sy + lsy[j]]);
+                            if ((unsigned)tx < (unsigned)Sx) m5 = min(m5, (uint32_t)R[tx * P + 2 + lsy[j]]);
                         }
                         uint32_t best = min(far_, m5 + (uint32_t)prm.P1);
-                        if ((unsigned)xp < (unsigned)Sx && (unsigned)yp < (unsigned)Sy) best = min(best, (uint32_t)Lpre[xp * Sy + yp]);
+                        if ((unsigned)xp < (unsigned)Sx && (unsigned)yp < (unsigned)Sy) best = min(best, (uint32_t)Lpre[xp * P + 2 + yp]);
                         const uint32_t l = c[j] + best - M;
-                        Lnew[d] = (uint8_t)l;
+                        Lnew[pidx[j]] = (uint8_t)l;
                         m = min(m, l);
                     }
                 }
@@ -218,15 +256,16 @@ pyd_sweep_kernel(const PydSweepParams prm)
                         for (int kk = -2; kk <= 2; ++kk) {
                             const int ty = yp + kk;
                             if (ty < 0 || ty >= Sy) continue;
-                            const uint32_t v = Lpre[tx * Sy + ty];
+                            const uint32_t v = Lpre[tx * P + 2 + ty];
                             const uint32_t cand = (mm == 0 && kk == 0) ? v : ((v + (uint32_t)prm.P1) & 0xFFu);
                             best = min(best, cand);
                         }
                     }
                     const uint32_t l = (c[j] + best - M) & 0xFFu;
-                    Lnew[d] = (uint8_t)l;
+                    Lnew[pidx[j]] = (uint8_t)l;
                     m = min(m, l);
                 }
+            }
             }
             }
             M = __reduce_min_sync(0xffffffffu, m);
@@ -234,9 +273,10 @@ pyd_sweep_kernel(const PydSweepParams prm)
         }
         // store this pixel's L row (coalesced bytes)
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) { int d = lane + 32 * j; if (d < D) Lb[pix * D + d] = Lnew[d]; }
+        for (int j = 0; j < NJ; ++j) { int d = lane + 32 * j; if (d < D) Lb[pix * D + d] = Lnew[pidx[j]]; }
         cur ^= 1;
         px = x; py = y; x = nx; y = ny;
+        mxp = mxc; myp = myc; mxc = mxn; myc = myn;
     }
 }
 
