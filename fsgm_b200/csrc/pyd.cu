@@ -108,10 +108,12 @@ template <int NJ, bool FAST>
 __global__ void __launch_bounds__(PYD_WARPS * 32)
 pyd_sweep_kernel(const PydSweepParams prm)
 {
-    constexpr int LS_SZ = NJ * 32 + 2 * PYD_MAXS + 8;              // Sx * (Sy + 2) + 2
+    constexpr int LS_SZ = NJ * 32 + 2 * PYD_MAXS + 32;             // 8 lead + Sx * P + 8 (P = Sy + 2, or 16 in vector mode: Sx <= 16)
     constexpr int RS_SZ = NJ * 32 + 6 * PYD_MAXS + 16;             // (Sx + 4) * (Sy + 2) + 2
-    __shared__ uint8_t Ls[PYD_WARPS][2][LS_SZ];
+    __shared__ __align__(16) uint8_t Ls[PYD_WARPS][2][LS_SZ];
     __shared__ uint8_t Rs[PYD_WARPS][FAST ? RS_SZ : 4];
+    __shared__ __align__(16) uint16_t Rv[PYD_WARPS][FAST ? 20 * 16 : 8];   // vector mode: y-window minima, [Sx + 4][16] u16
+    __shared__ __align__(16) uint8_t Cp[PYD_WARPS][FAST ? 16 * 16 + 16 : 16];  // vector mode: the cost row in the padded grid
     __shared__ int xt[PYD_WARPS][PYD_MAXS], yt[PYD_WARPS][PYD_MAXS];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int gw = blockIdx.x * PYD_WARPS + wib;
@@ -121,7 +123,11 @@ pyd_sweep_kernel(const PydSweepParams prm)
     const int line = gw - prm.line_start[k], r = prm.dir[k];
     const int dx = dir_dx(r), dy = dir_dy(r);
     const int W = prm.W, H = prm.H, Sx = prm.Sx, Sy = prm.Sy, D = Sx * Sy, mvW = prm.mvW;
-    const int P = Sy + 2;                                          // column pitch of the padded grids
+    // Vector mode (Sy <= 12, Sx <= 16, e.g. the reference's 11 x 11 and BASELINE's 9 x 9 windows): column pitch 16, so a lane
+    // owns 8 aligned slots (half a column: two leading pads, Sy labels, trailing pads) and the zero-shift step runs on u16x2
+    // registers: y-window from the lane's own 8 bytes + 4 on either side, x-window through a u16 grid in shared memory.
+    const bool vec = FAST && Sy <= 12 && Sx <= 16;
+    const int P = vec ? 16 : Sy + 2;                               // column pitch of the padded grids
     const size_t N = (size_t)W * H, mvN = (size_t)mvW * prm.mvH;
     const uint8_t* __restrict__ Cb = prm.C + blockIdx.y * N * D;
     uint8_t* __restrict__ Lb = prm.L[k] + blockIdx.y * N * D;
@@ -138,8 +144,14 @@ pyd_sweep_kernel(const PydSweepParams prm)
 #pragma unroll
     for (int j = 0; j < NJ; ++j) { int d = lane + 32 * j; lsx[j] = d / Sy; lsy[j] = d - lsx[j] * Sy; pidx[j] = lsx[j] * P + 2 + lsy[j]; }
     for (int i = lane; i < 2 * LS_SZ; i += 32) (&Ls[wib][0][0])[i] = 255;
-    if (FAST) for (int i = lane; i < RS_SZ; i += 32) Rs[wib][i] = 255;
+    if (FAST) {
+        for (int i = lane; i < RS_SZ; i += 32) Rs[wib][i] = 255;
+        for (int i = lane; i < 20 * 16; i += 32) Rv[wib][i] = 255;
+        for (int i = lane; i < 16 * 16 + 16; i += 32) Cp[wib][i] = 255;
+    }
     __syncwarp();
+    const int vc = lane >> 1, vh = lane & 1;                       // vector mode: column and half of this lane
+    const bool vact = vec && vc < Sx;
 
     uint32_t M = 0;
     int cur = 0, px = 0, py = 0;
@@ -163,8 +175,8 @@ pyd_sweep_kernel(const PydSweepParams prm)
         }
         const size_t pix = (size_t)y * W + x;
         const bool start = (t == 0) || (dy != 0 && dx != 0 && x == (dx > 0 ? 0 : W - 1));
-        uint8_t* Lnew = Ls[wib][cur];
-        const uint8_t* Lpre = Ls[wib][cur ^ 1];
+        uint8_t* Lnew = Ls[wib][cur] + 8;                    // grid base: 8 pad bytes in front, 8-byte aligned
+        const uint8_t* Lpre = Ls[wib][cur ^ 1] + 8;
         uint32_t m = 255;
         if (start) {
 #pragma unroll
@@ -176,8 +188,57 @@ pyd_sweep_kernel(const PydSweepParams prm)
             if (prm.adaptive && abs((int)Ib[pix] - (int)Ib[(size_t)py * W + px]) > 50) P2 = P2 / 8;
             const double ddx = __dsub_rn(mxc, mxp), ddy = __dsub_rn(myc, myp);
             const uint32_t far_ = (M + (uint32_t)P2) & 0xFFu;
-            if (FAST && ddx == 0.0 && ddy == 0.0) {
-                // predecessor label = the label itself ((int)(s + 0.0 + 0.5) == s): fixed offsets in the padded grids
+            if (FAST && vec && ddx == 0.0 && ddy == 0.0) {
+                // predecessor label = the label itself ((int)(s + 0.0 + 0.5) == s); u16x2 registers, 8 slots per lane
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) if (lane + 32 * j < D) Cp[wib][pidx[j]] = c[j];
+                uint32_t E[6];
+                if (vact) {
+                    const uint8_t* g = Lpre + vc * 16 + 8 * vh;
+                    const uint2 w = *reinterpret_cast<const uint2*>(g);
+                    const uint32_t wl = *reinterpret_cast<const uint32_t*>(g - 4), wr = *reinterpret_cast<const uint32_t*>(g + 8);
+                    E[0] = __byte_perm(wl, 0, 0x4342);               // slots (-2,-1) of this lane's 8, zero-extended
+                    E[1] = __byte_perm(w.x, 0, 0x4140); E[2] = __byte_perm(w.x, 0, 0x4342);
+                    E[3] = __byte_perm(w.y, 0, 0x4140); E[4] = __byte_perm(w.y, 0, 0x4342);
+                    E[5] = __byte_perm(wr, 0, 0x4140);               // slots (8,9)
+                    uint32_t O[5], rr[4];
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) O[i] = __byte_perm(E[i], E[i + 1], 0x5432);     // odd-aligned pairs (2i-1, 2i)
+                    // slots (2i, 2i+1): windows [2i-2, 2i+2] and [2i-1, 2i+3] = min(E_i, O_i, E_i+1, O_i+1, E_i+2) half by half
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        rr[i] = __vminu2(__vminu2(__vminu2(E[i], O[i]), __vminu2(E[i + 1], O[i + 1])), E[i + 2]);
+                    *reinterpret_cast<uint4*>(&Rv[wib][(vc + 2) * 16 + 8 * vh]) = make_uint4(rr[0], rr[1], rr[2], rr[3]);
+                }
+                __syncwarp();
+                uint32_t mm2 = 0xFFFFFFFFu;
+                if (vact) {
+                    const uint16_t* rq = &Rv[wib][vc * 16 + 8 * vh];                    // column c-2 in the padded R grid
+                    const uint4 a0 = *reinterpret_cast<const uint4*>(rq), a1 = *reinterpret_cast<const uint4*>(rq + 16),
+                                a2 = *reinterpret_cast<const uint4*>(rq + 32), a3 = *reinterpret_cast<const uint4*>(rq + 48),
+                                a4 = *reinterpret_cast<const uint4*>(rq + 64);
+                    const uint32_t m5[4] = {
+                        __vminu2(__vminu2(__vminu2(a0.x, a1.x), __vminu2(a2.x, a3.x)), a4.x),
+                        __vminu2(__vminu2(__vminu2(a0.y, a1.y), __vminu2(a2.y, a3.y)), a4.y),
+                        __vminu2(__vminu2(__vminu2(a0.z, a1.z), __vminu2(a2.z, a3.z)), a4.z),
+                        __vminu2(__vminu2(__vminu2(a0.w, a1.w), __vminu2(a2.w, a3.w)), a4.w)};
+                    const uint2 cw = *reinterpret_cast<const uint2*>(&Cp[wib][vc * 16 + 8 * vh]);
+                    const uint32_t cc[4] = {__byte_perm(cw.x, 0, 0x4140), __byte_perm(cw.x, 0, 0x4342),
+                                            __byte_perm(cw.y, 0, 0x4140), __byte_perm(cw.y, 0, 0x4342)};
+                    const uint32_t far2 = far_ * 0x10001u, P1P1 = (uint32_t)prm.P1 * 0x10001u, MM = M * 0x10001u;
+                    uint32_t l[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint32_t best = __vminu2(__vminu2(far2, m5[i] + P1P1), E[i + 1]);   // every candidate >= M: no borrow below
+                        l[i] = __vminu2(cc[i] + best - MM, 0x00FF00FFu);                          // pad slots (cost 255) saturate back to 255
+                        mm2 = __vminu2(mm2, l[i]);
+                    }
+                    *reinterpret_cast<uint2*>(Lnew + vc * 16 + 8 * vh) =
+                        make_uint2(__byte_perm(l[0], l[1], 0x6420), __byte_perm(l[2], l[3], 0x6420));
+                }
+                m = min(mm2 & 0xFFFFu, mm2 >> 16);
+            } else if (FAST && ddx == 0.0 && ddy == 0.0) {
+                // predecessor label = the label itself: fixed offsets in the padded grids
                 uint8_t* R = Rs[wib] + 2 * P;                        // skip the two pad columns
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) {
