@@ -156,10 +156,15 @@ pyd_sweep_kernel(const PydSweepParams prm)
     uint32_t M = 0;
     int cur = 0, px = 0, py = 0;
     uint8_t cnext[NJ];
+    // 32-bit pixel indices, one 64-bit row pointer per step (the per-label offsets lane + 32 j are immediates)
+    {
+        const uint8_t* crow = Cb + (size_t)((uint32_t)y * (uint32_t)W + (uint32_t)x) * D + lane;
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) { int d = lane + 32 * j; cnext[j] = d < D ? __ldg(Cb + ((size_t)y * W + x) * D + d) : 0; }
+        for (int j = 0; j < NJ; ++j) cnext[j] = lane + 32 * j < D ? __ldg(crow + 32 * j) : 0;
+    }
     // the prior at the current pixel travels with the cost row: loaded one step ahead, handed on to the next step as "previous"
-    double mxc = mvx[(size_t)y * mvW + x], myc = mvy[(size_t)y * mvW + x], mxp = 0.0, myp = 0.0, mxn = 0.0, myn = 0.0;
+    double mxc = mvx[(uint32_t)y * (uint32_t)mvW + (uint32_t)x], myc = mvy[(uint32_t)y * (uint32_t)mvW + (uint32_t)x];
+    double mxp = 0.0, myp = 0.0, mxn = 0.0, myn = 0.0;
 
     for (int t = 0; t < len; ++t) {
         uint8_t c[NJ];
@@ -169,11 +174,13 @@ pyd_sweep_kernel(const PydSweepParams prm)
         int nx = x, ny = y;
         if (dy == 0) nx += dx; else { ny += dy; nx += dx; nx = nx < 0 ? W - 1 : (nx >= W ? 0 : nx); }
         if (t + 1 < len) {
+            const uint8_t* crow = Cb + (size_t)((uint32_t)ny * (uint32_t)W + (uint32_t)nx) * D + lane;
 #pragma unroll
-            for (int j = 0; j < NJ; ++j) { int d = lane + 32 * j; cnext[j] = d < D ? __ldg(Cb + ((size_t)ny * W + nx) * D + d) : 0; }
-            mxn = mvx[(size_t)ny * mvW + nx]; myn = mvy[(size_t)ny * mvW + nx];
+            for (int j = 0; j < NJ; ++j) cnext[j] = lane + 32 * j < D ? __ldg(crow + 32 * j) : 0;
+            const uint32_t mi = (uint32_t)ny * (uint32_t)mvW + (uint32_t)nx;
+            mxn = mvx[mi]; myn = mvy[mi];
         }
-        const size_t pix = (size_t)y * W + x;
+        const uint32_t pix = (uint32_t)y * (uint32_t)W + (uint32_t)x;
         const bool start = (t == 0) || (dy != 0 && dx != 0 && x == (dx > 0 ? 0 : W - 1));
         uint8_t* Lnew = Ls[wib][cur] + 8;                    // grid base: 8 pad bytes in front, 8-byte aligned
         const uint8_t* Lpre = Ls[wib][cur ^ 1] + 8;
@@ -185,7 +192,7 @@ pyd_sweep_kernel(const PydSweepParams prm)
             __syncwarp();
         } else {
             int P2 = prm.P2;
-            if (prm.adaptive && abs((int)Ib[pix] - (int)Ib[(size_t)py * W + px]) > 50) P2 = P2 / 8;
+            if (prm.adaptive && abs((int)Ib[pix] - (int)Ib[(uint32_t)py * (uint32_t)W + (uint32_t)px]) > 50) P2 = P2 / 8;
             const double ddx = __dsub_rn(mxc, mxp), ddy = __dsub_rn(myc, myp);
             const uint32_t far_ = (M + (uint32_t)P2) & 0xFFu;
             if (FAST && vec && ddx == 0.0 && ddy == 0.0) {
@@ -335,8 +342,11 @@ pyd_sweep_kernel(const PydSweepParams prm)
             __syncwarp();
         }
         // store this pixel's L row (coalesced bytes)
+        {
+            uint8_t* lrow = Lb + (size_t)pix * D + lane;
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) { int d = lane + 32 * j; if (d < D) Lb[pix * D + d] = Lnew[pidx[j]]; }
+            for (int j = 0; j < NJ; ++j) if (lane + 32 * j < D) lrow[32 * j] = Lnew[pidx[j]];
+        }
         cur ^= 1;
         px = x; py = y; x = nx; y = ny;
         mxp = mxc; myp = myc; mxc = mxn; myc = myn;
@@ -534,8 +544,13 @@ pyd_wta_kernel(const PydWtaParams prm)
     uint16_t* s = sums[wib];
     uint32_t key = 0xFFFFFFFFu;
     for (int d = lane; d < D; d += 32) {
+        // all (up to 8) direction volumes are requested before the first is used: the kernel is bound by load latency
+        uint32_t v[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) v[r] = r < R ? (uint32_t)__ldg(prm.L[r] + vol + p * D + d) : 0u;
         uint32_t a = 0;
-        for (int r = 0; r < R; ++r) a += prm.weight[r] * (uint32_t)__ldg(prm.L[r] + vol + p * D + d);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) a += r < R ? prm.weight[r] * v[r] : 0u;
         s[d] = (uint16_t)a;
         if (prm.Sp16) prm.Sp16[vol + p * D + d] = (uint16_t)a;
         key = min(key, (a << 16) | (uint32_t)d);
