@@ -357,8 +357,8 @@ pyd_sweep_kernel(const PydSweepParams prm)
 // cost volume, lane = pixel: a warp owns 32 consecutive pixels of a row.  For one label and one window tap the 32 lanes read
 // neighbouring census words (the prior is piecewise constant over a warp in practice), so a gather touches 4-5 sectors
 // instead of the ~20 of the one-warp-per-pixel kernel above, whose lanes spread over the search window.  Per label column ox
-// the T x (2ry+T) reference census words the column needs are gathered ONCE into shared memory ([row][tap][lane], conflict
-// free); the T*T taps of its Sy labels are then LDS + XOR + POPC + IADD each.  The constant-5 rule (sample or window pixel
+// the T x (2ry+T) reference census words the column needs are gathered ONCE, row by row, into a shared-memory ring of T rows
+// ([row][tap][lane], lane-private, conflict free); the T*T taps of its Sy labels are then LDS + XOR + POPC + IADD each.  The constant-5 rule (sample or window pixel
 // outside the image, calc_pyd_cost_sgm.cpp:405-421) is a per-lane validity word per row / column, all-ones in the interior,
 // so the inner loop stays branch-free.  Results go through a shared-memory tile and leave as one contiguous run of bytes.
 // ------------------------------------------------------------------------------------------------
@@ -372,13 +372,13 @@ pyd_cost_px_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restrict
     extern __shared__ __align__(16) unsigned char pyc_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int Sx = 2 * rx + 1, Sy = 2 * ry + 1, D = Sx * Sy, SX2 = Sx + T - 1, SY2 = Sy + T - 1;
-    // per warp: fx[SX2][32], fy[SY2][32] (int), V[SY2][T][32] (u32), tile[32][D] (u8, padded to 16 bytes)
-    const size_t per_warp = (size_t)(SX2 + SY2) * 32 * 4 + (size_t)SY2 * T * 32 * 4 + (((size_t)32 * D + 15) & ~(size_t)15);
+    // per warp: fx[SX2][32], fy[SY2][32] (int), V[T][T][32] (u32: a ring of T sample rows), tile[32][D] (u8, padded to 16 bytes)
+    const size_t per_warp = (size_t)(SX2 + SY2) * 32 * 4 + (size_t)T * T * 32 * 4 + (((size_t)32 * D + 15) & ~(size_t)15);
     unsigned char* base = pyc_smem + wib * per_warp;
     int* fx = reinterpret_cast<int*>(base);
     int* fy = fx + SX2 * 32;
     uint32_t* V = reinterpret_cast<uint32_t*>(fy + SY2 * 32);
-    uint8_t* tile = reinterpret_cast<uint8_t*>(V + SY2 * T * 32);
+    uint8_t* tile = reinterpret_cast<uint8_t*>(V + T * T * 32);
 
     const int xblocks = (W + 31) / 32;
     const int job = blockIdx.x * PYC_WARPS + wib;
@@ -423,23 +423,30 @@ pyd_cost_px_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restrict
         uint32_t colok = 0;
 #pragma unroll
         for (int ax = 0; ax < T; ++ax) { fxv[ax] = fx[(ox + ax) * 32 + lane]; colok |= (fxv[ax] >= 0 ? 1u : 0u) << ax; }
-        for (int sy = 0; sy < SY2; ++sy) {
+        // sample rows live in a ring of T rows (every entry is private to its lane: no synchronisation): rows 0 .. T-2 now,
+        // row oy + T - 1 at the head of label oy
+        auto load_row = [&](int sy) {
             const int yy = fy[sy * 32 + lane];
             const uint32_t* row = c2 + (size_t)W * max(yy, 0);
+            uint32_t* dst = V + ((sy % T) * T) * 32 + lane;
 #pragma unroll
-            for (int ax = 0; ax < T; ++ax) V[(sy * T + ax) * 32 + lane] = __ldg(row + max(fxv[ax], 0));
-        }
-        __syncwarp();
+            for (int ax = 0; ax < T; ++ax) dst[ax * 32] = __ldg(row + max(fxv[ax], 0));
+        };
+        for (int sy = 0; sy < T - 1; ++sy) load_row(sy);
         // every tap of every label of the column is valid for every lane -> no checks (the interior of the image)
         const bool clean = __all_sync(0xffffffffu, rows_ok && colok == (1u << T) - 1u);
+        int r0 = 0;                                       // oy % T: ring slot of sample row oy
         for (int oy = 0; oy < Sy; ++oy) {
+            load_row(oy + T - 1);
             uint32_t sum = 0;
-            const uint32_t* Vl = V + (oy * T) * 32 + lane;
+            const uint32_t* Vr[T];
+#pragma unroll
+            for (int ay = 0; ay < T; ++ay) { int q = r0 + ay; q -= q >= T ? T : 0; Vr[ay] = V + (q * T) * 32 + lane; }
             if (clean) {
 #pragma unroll
                 for (int ay = 0; ay < T; ++ay)
 #pragma unroll
-                    for (int ax = 0; ax < T; ++ax) sum += __popc(t1[ay][ax] ^ Vl[(ay * T + ax) * 32]);
+                    for (int ax = 0; ax < T; ++ax) sum += __popc(t1[ay][ax] ^ Vr[ay][ax * 32]);
             } else {
 #pragma unroll
                 for (int ay = 0; ay < T; ++ay) {
@@ -447,10 +454,11 @@ pyd_cost_px_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restrict
 #pragma unroll
                     for (int ax = 0; ax < T; ++ax) {
                         const bool ok = rowok && ((colok >> ax) & 1u) && ((tapok >> (ay * T + ax)) & 1u);
-                        sum += ok ? (uint32_t)__popc(t1[ay][ax] ^ Vl[(ay * T + ax) * 32]) : 5u;
+                        sum += ok ? (uint32_t)__popc(t1[ay][ax] ^ Vr[ay][ax * 32]) : 5u;
                     }
                 }
             }
+            r0 = r0 + 1 == T ? 0 : r0 + 1;
             // (u8)(1.0*s/wp + 0.5) == (2s + wp) / (2wp) in integers (see pyd_cost_kernel)
             tile[lane * D + ox * Sy + oy] = (uint8_t)((2 * sum + WPX) / (2 * WPX));
         }
@@ -465,7 +473,7 @@ pyd_cost_px_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restrict
 static size_t pyd_cost_px_smem(int agg, int rx, int ry)
 {
     const int T = 2 * agg + 1, Sx = 2 * rx + 1, Sy = 2 * ry + 1, SX2 = Sx + T - 1, SY2 = Sy + T - 1;
-    const size_t per_warp = (size_t)(SX2 + SY2) * 32 * 4 + (size_t)SY2 * T * 32 * 4 + (((size_t)32 * Sx * Sy + 15) & ~(size_t)15);
+    const size_t per_warp = (size_t)(SX2 + SY2) * 32 * 4 + (size_t)T * T * 32 * 4 + (((size_t)32 * Sx * Sy + 15) & ~(size_t)15);
     return per_warp * PYC_WARPS;
 }
 
