@@ -242,9 +242,14 @@ hsweep_tma_kernel(const SweepParams prm)
     const int W = prm.W, H = prm.H;
     const size_t N = (size_t)W * H;
     const bool active = gw < prm.line_start[prm.n_dirs];
-    int k = 0;
-    if (active) while (gw >= prm.line_start[k + 1]) ++k;
-    const int y = active ? gw - prm.line_start[k] : 0;
+    // Both horizontal directions of a launch read the same cost rows: the two sweeps of one image row sit in neighbouring
+    // warps, so the second reading of a chunk follows the first within one row sweep instead of a whole volume later
+    // (measured: 4.53 -> 4.49 ms per 60 pairs; the reuse distance, ~90 MB of traffic, is still at the edge of the 126 MB L2).
+    int k = 0, y = 0;
+    if (active) {
+        if (prm.n_dirs == 2) { k = gw & 1; y = gw >> 1; }
+        else { while (gw >= prm.line_start[k + 1]) ++k; y = gw - prm.line_start[k]; }
+    }
     const int dx = dir_dx(prm.dir[k]);                        // +1 or -1 (dy == 0 for every direction of this launch)
     const uint8_t* __restrict__ Crow = prm.C + (blockIdx.y * N + (size_t)y * W) * D;
     uint8_t* __restrict__ Lrow = prm.L[k] + (blockIdx.y * N + (size_t)y * W) * D + lane * NB;
