@@ -44,7 +44,7 @@ FSGM_API int         fsgm_set_stream(fsgm_ctx* ctx, void* cuda_stream);
 FSGM_API int         fsgm_synchronize(fsgm_ctx* ctx);
 FSGM_API const char* fsgm_last_error(const fsgm_ctx* ctx);
 /* Tuning / A-B knobs (results never change).  key 1 = aggregation path of the epipolar variant: 0 auto (default),
- * -1 generic one-warp-per-scanline kernels only, 1/2/4/8 = thread-block-cluster size of the row-synchronous kernel.
+ * -1 generic one-warp-per-scanline kernels only, 1..16 = thread-block-cluster size of the row-synchronous kernel.
  * key 2 = 1 disables the two-stream wave pipeline (front-end of wave i+1 under the cluster passes of wave i). */
 FSGM_API int         fsgm_tune(fsgm_ctx* ctx, int key, int value);
 /* occupancy probe: resident clusters of `cluster_size` CTAs x `threads` threads with `smem_bytes` dynamic shared memory */
