@@ -336,16 +336,23 @@ class Context:
                                                   _hp(epi, np.float64), _hp(dr, np.int32), int(dMax), C.c_double(vMax), int(P1), int(P2),
                                                   C.byref(opts) if opts is not None else None, _dp(work), _dp(flow), _dp(minC)))
 
-    def epipolar_sgm_of_batch(self, I0, I1, F, Hm, epi, direction, dMax, vMax, P1, P2, opts=None, out=None, asynchronous=False):
-        """[flow, minC] = epipolar_sgm_of(...) from F, H, epipole on host images (epipolar_sgm_of.m:23-51 after the geometry fit)"""
+    def epipolar_sgm_of_batch(self, I0, I1, F, Hm, epi, direction, dMax, vMax, P1, P2, opts=None, out=None, asynchronous=False,
+                              f32=False):
+        """[flow, minC] = epipolar_sgm_of(...) from F, H, epipole on host images (epipolar_sgm_of.m:23-51 after the geometry fit).
+        f32=True: flow as float32 [n][H][W][2] (CV_32FC2, proj/include/epi_sgm.h:6-12); minC may then be None in `out`."""
         n, H, W = I0.shape
         F, Hm, epi, dr = self._geo_args(F, Hm, epi, direction, n)
-        flow, minC = out if out is not None else (np.empty((n, 2, H, W), np.float64), np.empty((n, H, W), np.uint32))
+        if f32:
+            flow, minC = out if out is not None else (np.empty((n, H, W, 2), np.float32), np.empty((n, H, W), np.uint32))
+            fn, fdt = self._l.fsgm_epipolar_sgm_of_f32_batch_async, np.float32
+        else:
+            flow, minC = out if out is not None else (np.empty((n, 2, H, W), np.float64), np.empty((n, H, W), np.uint32))
+            fn, fdt = self._l.fsgm_epipolar_sgm_of_batch_async, np.float64
         self._keep = (F, Hm, epi, dr)                    # host matrices are consumed at enqueue time, images are not
-        self._ck(self._l.fsgm_epipolar_sgm_of_batch_async(
+        self._ck(fn(
             self._h, n, _hp(I0, np.uint8), _hp(I1, np.uint8, (n, H, W)), W, H, _hp(F, np.float64), _hp(Hm, np.float64),
             _hp(epi, np.float64), _hp(dr, np.int32), int(dMax), C.c_double(vMax), int(P1), int(P2),
-            C.byref(opts) if opts is not None else None, _hp(flow, np.float64), _hp(minC, np.uint32)))
+            C.byref(opts) if opts is not None else None, _hp(flow, fdt), _hp(minC, np.uint32) if minC is not None else None))
         if not asynchronous:
             self.synchronize()
         return flow, minC

@@ -122,6 +122,14 @@ static int check_opts(fsgm_ctx* c, const fsgm_epi_opts* in, fsgm_epi_opts* o)
 
 constexpr int VS_MAX_SMEM = 227 * 1024;
 
+// largest byte of a caller-supplied cost volume, never reported below the 5x5-census bound the kernels are tuned for
+static int caller_volume_cmax(fsgm_ctx* c, const uint8_t* d_C, size_t bytes, int* cmax)
+{
+    FSGM_TRY(launch_max_u8(c, d_C, bytes, cmax));
+    *cmax = std::max(*cmax, 24);
+    return FSGM_OK;
+}
+
 // cluster size of the row-synchronous fast path for this problem, or 0 if it does not apply
 static int fast_path_cluster(fsgm_ctx* c, int W, int D, int P1, int P2, int cmax, const fsgm_epi_opts& o)
 {
@@ -145,10 +153,11 @@ static int fast_path_cluster(fsgm_ctx* c, int W, int D, int P1, int P2, int cmax
 static int fast_pairs(fsgm_ctx* c, int n, int cs, int D, int W, int ndir)
 {
     if (!cs) return 0;
-    if (c->clusters_cs != cs) {
-        const int Wk = (W + cs - 1) / cs;
+    if (c->clusters_key[0] != cs || c->clusters_key[1] != W || c->clusters_key[2] != D || c->clusters_key[3] != ndir) {
+        const int Wk = (W + cs - 1) / cs;                // resident clusters depend on the smem footprint: key on the whole shape
         int k = vsweep_max_clusters(cs, vsweep_smem_bytes(D, Wk, ndir), vsweep_threads());
-        c->clusters_cs = cs; c->clusters_max = k > 0 ? k : 1;
+        c->clusters_key[0] = cs; c->clusters_key[1] = W; c->clusters_key[2] = D; c->clusters_key[3] = ndir;
+        c->clusters_max = k > 0 ? k : 1;
     }
     if (c->force_cluster > 0) return n;                 // explicit A/B request: everything through the cluster kernels
     const int K = c->clusters_max, r = n % K;
@@ -343,7 +352,7 @@ using namespace fsgm;
 
 extern "C" {
 
-int fsgm_abi_version(void) { return 2; }
+int fsgm_abi_version(void) { return 3; }
 
 void fsgm_epi_opts_default(fsgm_epi_opts* o)
 {
@@ -379,6 +388,9 @@ void fsgm_destroy(fsgm_ctx* c)
     cudaDeviceSynchronize();
     if (c->arena) cudaFree(c->arena);
     if (c->geo_params) cudaFree(c->geo_params);
+    if (c->d_scalar) cudaFree(c->d_scalar);
+    if (c->geo_host) cudaFreeHost(c->geo_host);
+    for (auto e : c->geo_ev) if (e) cudaEventDestroy(e);
     for (auto& t : c->timers) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     for (auto e : c->event_pool) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) {
@@ -506,11 +518,21 @@ int fsgm_epi_aggregate_dev(fsgm_ctx* c, int n, const uint8_t* d_C, const uint8_t
     FSGM_TRY(check_opts(c, opts, &o));
     if (!d_C || !d_bestD || !d_minC || (o.vz_to_disp && !d_O) || (o.adaptive_p2 && !d_I1)) return fail(c, FSGM_ERR_ARG, "null pointer");
     FSGM_CUDA(c, cudaSetDevice(c->device));
-    // cost volumes handed to this stage entry are expected to come from fsgm_epi_cost_dev (values <= 24).  A caller
-    // with arbitrary u8 volumes uses fsgm_sweep_dev, which assumes nothing about the range.
-    FSGM_TRY(arena_reserve(c, aggregate_scratch_bytes(c, n, W, H, D, P1, P2, 24, o)));
-    ArenaScope scope(c);
-    return aggregate_and_wta(c, n, d_C, d_I1, W, H, D, P1, P2, 24, o, d_O, vMax, d_Sp, d_bestD, d_minC);
+    // The caller owns this volume: measure its largest byte instead of assuming the 5x5-census bound.  Up to 24 (anything
+    // fsgm_epi_cost_dev produces) every kernel family applies; above it the row-synchronous cluster kernels (whose byte-sum
+    // and biased-fp16 forms are derived for C <= 24) are skipped and the generic sweeps pick the exact or the explicit
+    // mod-256 form from the measured bound, as the reference's unsigned char arithmetic requires.
+    int cmax = 0;
+    FSGM_TRY(caller_volume_cmax(c, d_C, (size_t)n * W * H * D, &cmax));
+    const int saved = c->force_cluster;
+    if (cmax > 24 || (reinterpret_cast<uintptr_t>(d_C) & 15)) c->force_cluster = -1;    // bulk copies need 16-byte alignment
+    int rc = arena_reserve(c, aggregate_scratch_bytes(c, n, W, H, D, P1, P2, cmax, o));
+    if (rc == FSGM_OK) {
+        ArenaScope scope(c);
+        rc = aggregate_and_wta(c, n, d_C, d_I1, W, H, D, P1, P2, cmax, o, d_O, vMax, d_Sp, d_bestD, d_minC);
+    }
+    c->force_cluster = saved;
+    return rc;
 }
 
 // Direction-split building blocks (one large pair, the R directions spread over GPUs):
@@ -533,7 +555,9 @@ int fsgm_epi_partial_dev(fsgm_ctx* c, const uint8_t* d_C, const uint8_t* d_I1, i
     for (int k = 0; k < n_dirs; ++k) FSGM_TRY(arena_get(c, V, &L[k]));
     FSGM_TRY(arena_get(c, N, &b));
     FSGM_TRY(arena_get(c, N, &m));
-    FSGM_TRY(launch_sweeps(c, 1, d_C, d_I1, W, H, D, P1, P2, adaptive_p2 ? 25 : 0, 24, directions, n_dirs, L));
+    int cmax = 0;
+    FSGM_TRY(caller_volume_cmax(c, d_C, V, &cmax));
+    FSGM_TRY(launch_sweeps(c, 1, d_C, d_I1, W, H, D, P1, P2, adaptive_p2 ? 25 : 0, cmax, directions, n_dirs, L));
     return launch_epi_wta(c, 1, L, n_dirs, W, H, D, 0, 0, nullptr, 0.0, d_Sp_partial, b, m);
 }
 
@@ -545,17 +569,20 @@ int fsgm_epi_partial_u8_dev(fsgm_ctx* c, const uint8_t* d_C, const uint8_t* d_I1
     FSGM_TRY(check_dims(c, 1, W, H, D));
     if (!d_C || !d_partial || !directions || (adaptive_p2 && !d_I1)) return fail(c, FSGM_ERR_ARG, "null pointer");
     if (n_dirs < 0 || n_dirs > 8) return fail(c, FSGM_ERR_ARG, "n_dirs must be 0..8");
-    if (sweep_needs_wrap(P1, P2, 24) || n_dirs * (24 + P2) > 255) return fail(c, FSGM_ERR_DOMAIN, "partial sums do not fit 8 bits");
     if (D % 16) return fail(c, FSGM_ERR_DOMAIN, "dMax must be a multiple of 16 for the u8 partial form");
+    if ((reinterpret_cast<uintptr_t>(d_partial) & 15)) return fail(c, FSGM_ERR_ARG, "d_partial must be 16-byte aligned");
     FSGM_CUDA(c, cudaSetDevice(c->device));
     const size_t V = (size_t)W * H * D;
+    int cmax = 0;
+    FSGM_TRY(caller_volume_cmax(c, d_C, V, &cmax));
+    if (sweep_needs_wrap(P1, P2, cmax) || n_dirs * (cmax + P2) > 255) return fail(c, FSGM_ERR_DOMAIN, "partial sums do not fit 8 bits");
     if (n_dirs == 0) { FSGM_CUDA(c, cudaMemsetAsync(d_partial, 0, V, c->stream)); return FSGM_OK; }
     FSGM_TRY(arena_reserve(c, (size_t)(n_dirs - 1) * align256(V)));
     ArenaScope scope(c);
     uint8_t* L[8];
     L[0] = d_partial;
     for (int k = 1; k < n_dirs; ++k) FSGM_TRY(arena_get(c, V, &L[k]));
-    FSGM_TRY(launch_sweeps(c, 1, d_C, d_I1, W, H, D, P1, P2, adaptive_p2 ? 25 : 0, 24, directions, n_dirs, L));
+    FSGM_TRY(launch_sweeps(c, 1, d_C, d_I1, W, H, D, P1, P2, adaptive_p2 ? 25 : 0, cmax, directions, n_dirs, L));
     for (int k = 1; k < n_dirs; ++k) FSGM_TRY(launch_add_u8(c, d_partial, L[k], V));
     return FSGM_OK;
 }
@@ -605,6 +632,7 @@ int fsgm_calc_cost_sgm_dev(fsgm_ctx* c, int n, const uint8_t* d_I1, const uint8_
     const size_t budget = std::max(c->arena_bytes, c->mem_budget);
     const size_t per_pair = epi_scratch_bytes(c, 1, W, H, D, P1, P2, o);
     int chunk = (int)std::min<size_t>(n, std::max<size_t>(1, budget / per_pair));
+    chunk = std::min(chunk, 65535);                   // pairs ride on grid.y / grid.z of the kernels
     {   // keep chunks at whole waves of the cluster kernels when they apply (see fast_pairs)
         const int cs = fast_path_cluster(c, W, D, P1, P2, 24, o);
         if (cs && chunk < n) {
@@ -783,6 +811,7 @@ int fsgm_epipolar_geometry_dev(fsgm_ctx* c, int n, const double* F, const double
 {
     FSGM_TRY(check_dims(c, n, W, H, 1));
     if (!F || !Hm || !epipole || !d_Pd0 || !d_dir || !d_O) return fail(c, FSGM_ERR_ARG, "null pointer");
+    if (n > 65535) return fail(c, FSGM_ERR_DOMAIN, "at most 65535 pairs per geometry call");
     FSGM_CUDA(c, cudaSetDevice(c->device));
     return launch_geo_prologue(c, n, F, Hm, epipole, direction, W, H, d_Pd0, d_dir, d_O, d_Rflow);
 }
@@ -792,20 +821,24 @@ int fsgm_epipolar_flow_dev(fsgm_ctx* c, int n, const uint32_t* d_bestD, const do
 {
     FSGM_TRY(check_dims(c, n, W, H, 1));
     if (!d_bestD || !d_dir || !d_Rflow || !d_flow) return fail(c, FSGM_ERR_ARG, "null pointer");
+    if (n > 65535) return fail(c, FSGM_ERR_DOMAIN, "at most 65535 pairs per geometry call");
     FSGM_CUDA(c, cudaSetDevice(c->device));
     return launch_geo_epilogue(c, n, d_bestD, d_dir, d_Rflow, W, H, d_flow);
 }
 
-// d_work: 60 bytes per pixel and pair of caller-provided scratch (Pd0 16, direction 16, offset 8, Rflow 16, bestD 4)
-int fsgm_epipolar_sgm_of_dev(fsgm_ctx* c, int n, const uint8_t* d_I0, const uint8_t* d_I1, int W, int H,
-                             const double* F, const double* Hm, const double* epipole, const int* direction,
-                             int D, double vMax, int P1, int P2, const fsgm_epi_opts* opts, void* d_work, double* d_flow, uint32_t* d_minC)
+// d_work: 60 bytes per pixel and pair of caller-provided scratch (Pd0 16, direction 16, offset 8, Rflow 16, bestD 4);
+// exactly one of d_flow (f64 planes) and d_flow32 (float, interleaved u,v) is set
+static int sgm_of_dev(fsgm_ctx* c, int n, const uint8_t* d_I0, const uint8_t* d_I1, int W, int H,
+                      const double* F, const double* Hm, const double* epipole, const int* direction,
+                      int D, double vMax, int P1, int P2, const fsgm_epi_opts* opts, void* d_work, double* d_flow, float* d_flow32,
+                      uint32_t* d_minC)
 {
     FSGM_TRY(check_dims(c, n, W, H, D));
-    if (!d_I0 || !d_I1 || !F || !Hm || !epipole || !d_work || !d_flow || !d_minC) return fail(c, FSGM_ERR_ARG, "null pointer");
+    if (!d_I0 || !d_I1 || !F || !Hm || !epipole || !d_work || (!d_flow && !d_flow32) || !d_minC) return fail(c, FSGM_ERR_ARG, "null pointer");
     fsgm_epi_opts o;
     FSGM_TRY(check_opts(c, opts, &o));
     if (!o.vz_to_disp) return fail(c, FSGM_ERR_ARG, "epipolar_sgm_of needs pixel disparities (opts.vz_to_disp = 1)");
+    if (n > 65535) return fail(c, FSGM_ERR_DOMAIN, "at most 65535 pairs per call of the device form (the host form chunks)");
     FSGM_CUDA(c, cudaSetDevice(c->device));
     const size_t N = (size_t)W * H;
     char* base = static_cast<char*>(d_work);
@@ -816,20 +849,36 @@ int fsgm_epipolar_sgm_of_dev(fsgm_ctx* c, int n, const uint8_t* d_I0, const uint
     uint32_t* best = reinterpret_cast<uint32_t*>(base);
     FSGM_TRY(launch_geo_prologue(c, n, F, Hm, epipole, direction, W, H, Pd0, dirn, O, Rf));
     FSGM_TRY(fsgm_calc_cost_sgm_dev(c, n, d_I0, d_I1, W, H, D, vMax, Pd0, dirn, O, P1, P2, &o, best, d_minC));
+    if (d_flow32) return launch_geo_epilogue_f32(c, n, best, dirn, Rf, W, H, d_flow32);
     return launch_geo_epilogue(c, n, best, dirn, Rf, W, H, d_flow);
+}
+
+int fsgm_epipolar_sgm_of_dev(fsgm_ctx* c, int n, const uint8_t* d_I0, const uint8_t* d_I1, int W, int H,
+                             const double* F, const double* Hm, const double* epipole, const int* direction,
+                             int D, double vMax, int P1, int P2, const fsgm_epi_opts* opts, void* d_work, double* d_flow, uint32_t* d_minC)
+{
+    return sgm_of_dev(c, n, d_I0, d_I1, W, H, F, Hm, epipole, direction, D, vMax, P1, P2, opts, d_work, d_flow, nullptr, d_minC);
+}
+
+int fsgm_epipolar_sgm_of_f32_dev(fsgm_ctx* c, int n, const uint8_t* d_I0, const uint8_t* d_I1, int W, int H,
+                                 const double* F, const double* Hm, const double* epipole, const int* direction,
+                                 int D, double vMax, int P1, int P2, const fsgm_epi_opts* opts, void* d_work, float* d_flow, uint32_t* d_minC)
+{
+    return sgm_of_dev(c, n, d_I0, d_I1, W, H, F, Hm, epipole, direction, D, vMax, P1, P2, opts, d_work, nullptr, d_flow, d_minC);
 }
 
 size_t fsgm_epipolar_sgm_of_work_bytes(int n_pairs, int W, int H) { return (size_t)n_pairs * W * H * 60; }
 
 // Host-pointer form, enqueue-only like fsgm_calc_cost_sgm_batch_async: 2 bytes per pixel go up, 20 come back.
-int fsgm_epipolar_sgm_of_batch_async(fsgm_ctx* c, int n, const uint8_t* I0, const uint8_t* I1, int W, int H,
-                                     const double* F, const double* Hm, const double* epipole, const int* direction,
-                                     int D, double vMax, int P1, int P2, const fsgm_epi_opts* opts, double* flow, uint32_t* minC)
+// The float form returns 8 (flow, interleaved like CV_32FC2) + 4 (minC, optional) bytes per pixel.
+static int sgm_of_batch_async(fsgm_ctx* c, int n, const uint8_t* I0, const uint8_t* I1, int W, int H,
+                              const double* F, const double* Hm, const double* epipole, const int* direction,
+                              int D, double vMax, int P1, int P2, const fsgm_epi_opts* opts, double* flow, float* flow32, uint32_t* minC)
 {
     FSGM_TRY(check_dims(c, n, W, H, D));
     fsgm_epi_opts o;
     FSGM_TRY(check_opts(c, opts, &o));
-    if (!I0 || !I1 || !F || !Hm || !epipole || !flow || !minC) return fail(c, FSGM_ERR_ARG, "null pointer");
+    if (!I0 || !I1 || !F || !Hm || !epipole || (!flow && !flow32) || (!minC && !flow32)) return fail(c, FSGM_ERR_ARG, "null pointer");
     FSGM_CUDA(c, cudaSetDevice(c->device));
     const size_t N = (size_t)W * H;
     const size_t per_pair = 2 * align256(N) + 60 * N + 256 + align256(2 * N * 8) + align256(N * 4);
@@ -861,18 +910,34 @@ int fsgm_epipolar_sgm_of_batch_async(fsgm_ctx* c, int n, const uint8_t* I0, cons
         }
         // the slot's scratch is rewritten by this chunk's kernels: they must not start before the slot's previous outputs left
         if (p.used[slot]) cudaStreamWaitEvent(c->stream, p.out_ready[slot], 0);
-        rc = fsgm_epipolar_sgm_of_dev(c, m, dI0, dI1, W, H, F + (size_t)i0 * 9, Hm + (size_t)i0 * 9, epipole + (size_t)i0 * 2,
-                                      direction ? direction + i0 : nullptr, D, vMax, P1, P2, &o, work, dFlow, dMin);
+        rc = sgm_of_dev(c, m, dI0, dI1, W, H, F + (size_t)i0 * 9, Hm + (size_t)i0 * 9, epipole + (size_t)i0 * 2,
+                        direction ? direction + i0 : nullptr, D, vMax, P1, P2, &o, work, flow32 ? nullptr : dFlow,
+                        flow32 ? reinterpret_cast<float*>(dFlow) : nullptr, dMin);
         if (rc != FSGM_OK) break;
         if (cudaEventRecord(p.done[slot], c->stream) || cudaStreamWaitEvent(p.d2h, p.done[slot], 0) ||
-            cudaMemcpyAsync(flow + (size_t)i0 * 2 * N, dFlow, m * 2 * N * 8, cudaMemcpyDeviceToHost, p.d2h) ||
-            cudaMemcpyAsync(minC + i0 * N, dMin, m * N * 4, cudaMemcpyDeviceToHost, p.d2h) ||
+            (flow32 ? cudaMemcpyAsync(flow32 + (size_t)i0 * 2 * N, dFlow, m * 2 * N * 4, cudaMemcpyDeviceToHost, p.d2h)
+                    : cudaMemcpyAsync(flow + (size_t)i0 * 2 * N, dFlow, m * 2 * N * 8, cudaMemcpyDeviceToHost, p.d2h)) ||
+            (minC ? cudaMemcpyAsync(minC + i0 * N, dMin, m * N * 4, cudaMemcpyDeviceToHost, p.d2h) : cudaSuccess) ||
             cudaEventRecord(p.out_ready[slot], p.d2h))
             rc = fail(c, FSGM_ERR_CUDA, "D2H copy", cudaGetErrorString(cudaGetLastError()));
         p.used[slot] = 1;
     }
     if (rc != FSGM_OK) { cudaStreamSynchronize(p.d2h); cudaStreamSynchronize(c->stream); cudaStreamSynchronize(p.h2d); }
     return rc;
+}
+
+int fsgm_epipolar_sgm_of_batch_async(fsgm_ctx* c, int n, const uint8_t* I0, const uint8_t* I1, int W, int H,
+                                     const double* F, const double* Hm, const double* epipole, const int* direction,
+                                     int D, double vMax, int P1, int P2, const fsgm_epi_opts* opts, double* flow, uint32_t* minC)
+{
+    return sgm_of_batch_async(c, n, I0, I1, W, H, F, Hm, epipole, direction, D, vMax, P1, P2, opts, flow, nullptr, minC);
+}
+
+int fsgm_epipolar_sgm_of_f32_batch_async(fsgm_ctx* c, int n, const uint8_t* I0, const uint8_t* I1, int W, int H,
+                                         const double* F, const double* Hm, const double* epipole, const int* direction,
+                                         int D, double vMax, int P1, int P2, const fsgm_epi_opts* opts, float* flow, uint32_t* minC)
+{
+    return sgm_of_batch_async(c, n, I0, I1, W, H, F, Hm, epipole, direction, D, vMax, P1, P2, opts, nullptr, flow, minC);
 }
 
 int fsgm_epipolar_sgm_of(fsgm_ctx* c, const uint8_t* I0, const uint8_t* I1, int W, int H, const double* F, const double* Hm,

@@ -90,6 +90,7 @@ int fsgm_calc_cost_sgm_ng(fsgm_ctx* c, const uint8_t* I1, const uint8_t* I2, int
     const size_t N = (size_t)W * H;
     const size_t bytes = 2 * align256(N) + align256(N * 4) + align256(2 * N * 8) + (o.rand_stream ? align256(N * 8 * 4) : 0);
     FSGM_TRY(pipe_reserve(c, bytes));
+    FSGM_TRY(fsgm_synchronize(c));               // an earlier enqueue-only call may still own staging slot 0
     char* base = c->pipe.buf[0];
     uint8_t* dI1 = (uint8_t*)base;  base += align256(N);
     uint8_t* dI2 = (uint8_t*)base;  base += align256(N);
@@ -145,6 +146,7 @@ int fsgm_calc_pyd_cost_sgm_ng(fsgm_ctx* c, const uint8_t* I1, const uint8_t* I2,
     FSGM_CUDA(c, cudaSetDevice(c->device));
     const size_t N = (size_t)W * H, mvN = (size_t)mvW * mvH;
     FSGM_TRY(pipe_reserve(c, 2 * align256(N) + align256(2 * mvN * 8) + align256(N * 4) + align256(2 * N * 8)));
+    FSGM_TRY(fsgm_synchronize(c));               // an earlier enqueue-only call may still own staging slot 0
     char* base = c->pipe.buf[0];
     uint8_t* dI1 = (uint8_t*)base;  base += align256(N);
     uint8_t* dI2 = (uint8_t*)base;  base += align256(N);

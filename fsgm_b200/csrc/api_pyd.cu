@@ -137,6 +137,7 @@ int fsgm_calc_pyd_cost_sgm(fsgm_ctx* c, const uint8_t* I1, const uint8_t* I2, in
     const size_t N = (size_t)W * H, mvN = (size_t)mvW * mvH;
     const size_t bytes = 2 * align256(N) + align256(2 * mvN * 8) + 2 * align256(N * 4) + align256(2 * N * 8);
     FSGM_TRY(pipe_reserve(c, bytes));
+    FSGM_TRY(fsgm_synchronize(c));               // an earlier enqueue-only call may still own staging slot 0
     char* base = c->pipe.buf[0];
     uint8_t* dI1 = (uint8_t*)base;  base += align256(N);
     uint8_t* dI2 = (uint8_t*)base;  base += align256(N);

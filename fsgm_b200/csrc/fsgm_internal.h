@@ -37,7 +37,7 @@ struct fsgm_ctx {
     cudaEvent_t ev_entry = nullptr, ev_front[2] = {nullptr, nullptr};
     int no_overlap = 0;                     // tuning knob (fsgm_tune key 2)
     unsigned attr_mask = 0;                 // which kernels already had their max-dynamic-smem attribute set on this device
-    int clusters_cs = 0, clusters_max = 0;   // resident clusters for the last queried cluster size
+    int clusters_key[4] = {0, 0, 0, 0}, clusters_max = 0;   // resident clusters for the last queried (cluster size, W, D, ndir)
     int best_key[3] = {0, 0, 0}, best_cs = 0, best_clusters = 0;   // cached vsweep_best_cluster() decision for (W, D, ndir)
     int force_cluster = 0;                  // tuning/test knob: 0 auto, -1 generic path only, 1/2/4/8 forced cluster size
     std::string err;
@@ -48,8 +48,13 @@ struct fsgm_ctx {
     double stage_ms[fsgm::ST_COUNT] = {};
     uint64_t stage_launches[fsgm::ST_COUNT] = {};
     fsgm::HostPipe pipe;
+    void* d_scalar = nullptr;               // 256 B of device memory for small read-backs (launch_max_u8)
     void* geo_params = nullptr;             // per-pair F, H, epipole, direction of the dense-geometry prologue (geometry.cu)
     size_t geo_cap = 0;
+    void* geo_host = nullptr;               // pinned staging ring for them (4 slots of geo_host_cap pairs)
+    size_t geo_host_cap = 0;
+    cudaEvent_t geo_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    unsigned geo_turn = 0;
 };
 
 namespace fsgm {
@@ -115,6 +120,7 @@ int launch_epi_wta(fsgm_ctx* c, int n, uint8_t* const* Lvols, int n_dirs, int W,
 int launch_slab_wta(fsgm_ctx* c, const uint8_t* vols, int n_vols, const uint16_t* next0, size_t npix, int D, int subpixel,
                     int vz_to_disp, const double* O, double vMax, uint32_t* bestD, uint32_t* minC);
 int launch_add_u8(fsgm_ctx* c, uint8_t* a, const uint8_t* b, size_t bytes);
+int launch_max_u8(fsgm_ctx* c, const uint8_t* v, size_t bytes, int* cmax);   // synchronous read-back
 int launch_sp_wta(fsgm_ctx* c, const uint16_t* Sp, const uint16_t* next0, size_t npix, int D, int subpixel,
                   int vz_to_disp, const double* O, double vMax, uint32_t* bestD, uint32_t* minC);
 
@@ -148,6 +154,7 @@ int launch_pyd_wta(fsgm_ctx* c, int n, uint8_t* const* Lvols, const int* weights
 int launch_geo_prologue(fsgm_ctx* c, int n, const double* F, const double* Hm, const double* epi, const int* direction, int W, int H,
                         double* Pd0, double* dirn, double* O, double* Rflow);
 int launch_geo_epilogue(fsgm_ctx* c, int n, const uint32_t* bestD, const double* dirn, const double* Rflow, int W, int H, double* flow);
+int launch_geo_epilogue_f32(fsgm_ctx* c, int n, const uint32_t* bestD, const double* dirn, const double* Rflow, int W, int H, float* flow);
 
 // ---- pyramid driver (pyramid.cu): impyramid 'reduce', label -> mv, 2 x nearest upsample ------------------------
 int launch_pyr_reduce(fsgm_ctx* c, int n_images, const uint8_t* in, int W, int H, uint8_t* out);

@@ -66,6 +66,20 @@ __global__ void geo_epilogue_kernel(const uint32_t* __restrict__ bestD, const do
     flow[b2 + N] = __dadd_rn(__dmul_rn(d, dirn[b2 + N]), Rflow[b2 + N]);
 }
 
+// the same flow rounded to float and interleaved (u, v) per pixel: the layout of the reference's return type, CV_32FC2
+// (proj/include/epi_sgm.h:6-12).  8 instead of 16 bytes per pixel on the way back to the host.
+__global__ void geo_epilogue_f32_kernel(const uint32_t* __restrict__ bestD, const double* __restrict__ dirn, const double* __restrict__ Rflow,
+                                        size_t N, float2* __restrict__ flow)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const size_t b2 = blockIdx.y * 2 * N + i;
+    const double d = __ddiv_rn((double)bestD[blockIdx.y * N + i], 256.0);
+    const double u = __dadd_rn(__dmul_rn(d, dirn[b2]), Rflow[b2]);
+    const double v = __dadd_rn(__dmul_rn(d, dirn[b2 + N]), Rflow[b2 + N]);
+    flow[blockIdx.y * N + i] = make_float2(__double2float_rn(u), __double2float_rn(v));
+}
+
 int launch_geo_prologue(fsgm_ctx* c, int n, const double* F, const double* Hm, const double* epi, const int* direction, int W, int H,
                         double* Pd0, double* dirn, double* O, double* Rflow)
 {
@@ -76,13 +90,27 @@ int launch_geo_prologue(fsgm_ctx* c, int n, const double* F, const double* Hm, c
         if (cudaMalloc(&c->geo_params, cap * sizeof(GeoPair)) != cudaSuccess) { cudaGetLastError(); return fail(c, FSGM_ERR_NOMEM, "cudaMalloc(geometry parameters)"); }
         c->geo_cap = cap;
     }
-    std::vector<GeoPair> h(n);
+    // Pinned staging ring (4 slots of geo_cap pairs, an event per slot): the copy is truly asynchronous, so the call stays
+    // enqueue-only, and a slot is rewritten only after the copy that read it has executed.
+    if (c->geo_host_cap < c->geo_cap) {
+        FSGM_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (c->geo_host) cudaFreeHost(c->geo_host);
+        c->geo_host = nullptr; c->geo_host_cap = 0;
+        if (cudaMallocHost(&c->geo_host, 4 * c->geo_cap * sizeof(GeoPair)) != cudaSuccess) { cudaGetLastError(); return fail(c, FSGM_ERR_NOMEM, "cudaMallocHost(geometry parameters)"); }
+        c->geo_host_cap = c->geo_cap;
+        for (int k = 0; k < 4; ++k)
+            if (!c->geo_ev[k]) FSGM_CUDA(c, cudaEventCreateWithFlags(&c->geo_ev[k], cudaEventDisableTiming));
+        c->geo_turn = 0;
+    }
+    const int slot = c->geo_turn++ & 3;
+    if (c->geo_turn > 4) FSGM_CUDA(c, cudaEventSynchronize(c->geo_ev[slot]));
+    GeoPair* h = static_cast<GeoPair*>(c->geo_host) + (size_t)slot * c->geo_host_cap;
     for (int i = 0; i < n; ++i) {
         for (int k = 0; k < 9; ++k) { h[i].F[k] = F[i * 9 + k]; h[i].H[k] = Hm[i * 9 + k]; }
         h[i].ex = epi[i * 2]; h[i].ey = epi[i * 2 + 1]; h[i].direction = direction ? direction[i] != 0 : 0; h[i].pad = 0;
     }
-    // pageable source: the runtime stages it before returning, so the vector may go out of scope
-    FSGM_CUDA(c, cudaMemcpyAsync(c->geo_params, h.data(), n * sizeof(GeoPair), cudaMemcpyHostToDevice, c->stream));
+    FSGM_CUDA(c, cudaMemcpyAsync(c->geo_params, h, n * sizeof(GeoPair), cudaMemcpyHostToDevice, c->stream));
+    FSGM_CUDA(c, cudaEventRecord(c->geo_ev[slot], c->stream));
     const size_t N = (size_t)W * H;
     geo_prologue_kernel<<<dim3((unsigned)((N + 255) / 256), n), 256, 0, c->stream>>>(static_cast<const GeoPair*>(c->geo_params), W, H, Pd0, dirn, O, Rflow);
     FSGM_LAUNCHED(c);
@@ -94,6 +122,15 @@ int launch_geo_epilogue(fsgm_ctx* c, int n, const uint32_t* bestD, const double*
     StageScope ts(c, ST_GEOMETRY);
     const size_t N = (size_t)W * H;
     geo_epilogue_kernel<<<dim3((unsigned)((N + 255) / 256), n), 256, 0, c->stream>>>(bestD, dirn, Rflow, N, flow);
+    FSGM_LAUNCHED(c);
+    return FSGM_OK;
+}
+
+int launch_geo_epilogue_f32(fsgm_ctx* c, int n, const uint32_t* bestD, const double* dirn, const double* Rflow, int W, int H, float* flow)
+{
+    StageScope ts(c, ST_GEOMETRY);
+    const size_t N = (size_t)W * H;
+    geo_epilogue_f32_kernel<<<dim3((unsigned)((N + 255) / 256), n), 256, 0, c->stream>>>(bestD, dirn, Rflow, N, reinterpret_cast<float2*>(flow));
     FSGM_LAUNCHED(c);
     return FSGM_OK;
 }

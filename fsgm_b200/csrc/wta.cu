@@ -187,6 +187,44 @@ int launch_add_u8(fsgm_ctx* c, uint8_t* a, const uint8_t* b, size_t bytes)
     return FSGM_OK;
 }
 
+// Largest byte of a caller-supplied u8 volume (stage entry points: decides between the exact-u16 / biased-fp16 kernels and the
+// explicit mod-256 form).  Grid-stride 128-bit loads, byte-wise maxima, one atomicMax per warp; the head and tail that are
+// not 16-byte aligned are read byte-wise by the first block.
+__global__ void max_u8_kernel(const uint8_t* __restrict__ v, size_t bytes, unsigned* __restrict__ out)
+{
+    const size_t head = min(bytes, (size_t)((16 - (reinterpret_cast<uintptr_t>(v) & 15)) & 15));
+    const uint4* q = reinterpret_cast<const uint4*>(v + head);
+    const size_t n16 = (bytes - head) / 16;
+    unsigned m = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 x = q[i];
+        m = __vmaxu4(m, __vmaxu4(__vmaxu4(x.x, x.y), __vmaxu4(x.z, x.w)));
+    }
+    if (blockIdx.x == 0) {
+        for (size_t i = threadIdx.x; i < head; i += blockDim.x) m = __vmaxu4(m, v[i]);
+        for (size_t i = head + n16 * 16 + threadIdx.x; i < bytes; i += blockDim.x) m = __vmaxu4(m, v[i]);
+    }
+    m = max(max(m & 255u, (m >> 8) & 255u), max((m >> 16) & 255u, m >> 24));
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+// synchronous (the host needs the value to pick a kernel): cmax = max byte of v[0..bytes)
+int launch_max_u8(fsgm_ctx* c, const uint8_t* v, size_t bytes, int* cmax)
+{
+    if (!c->d_scalar) FSGM_CUDA(c, cudaMalloc(&c->d_scalar, 256));
+    StageScope ss(c, ST_MISC);
+    FSGM_CUDA(c, cudaMemsetAsync(c->d_scalar, 0, 4, c->stream));
+    const unsigned blocks = (unsigned)std::min<size_t>((bytes / 16 + 255) / 256 + 1, (size_t)c->sm_count * 8);
+    max_u8_kernel<<<blocks, 256, 0, c->stream>>>(v, bytes, static_cast<unsigned*>(c->d_scalar));
+    FSGM_LAUNCHED(c);
+    unsigned h = 0;
+    FSGM_CUDA(c, cudaMemcpyAsync(&h, c->d_scalar, 4, cudaMemcpyDeviceToHost, c->stream));
+    FSGM_CUDA(c, cudaStreamSynchronize(c->stream));
+    *cmax = (int)h;
+    return FSGM_OK;
+}
+
 // WTA from an already-summed u16 volume covering `npix` consecutive pixels (one slab of the direction-split path)
 int launch_sp_wta(fsgm_ctx* c, const uint16_t* Sp, const uint16_t* next0, size_t npix, int D, int subpixel,
                   int vz_to_disp, const double* O, double vMax, uint32_t* bestD, uint32_t* minC)

@@ -50,6 +50,10 @@ class GpuBackend:
     def __init__(self, ctx):
         self.ctx = ctx
         self.device = torch.device("cuda", ctx.device)
+        # the collectives and the torch fills around the C-ABI kernels run on torch's current stream: the kernels
+        # must be ordered on that same stream, not on the context's private one
+        with torch.cuda.device(self.device):
+            ctx.use_torch_stream()
 
     def upload(self, pair):
         """copy a pair's arrays to this GPU once (device-resident measurements reuse the result)"""

@@ -78,12 +78,16 @@ FlowField EpiSGM::compute(const Image& I1, const Image& I2)
     fsgm_epi_opts_default(&o);
     o.paths = enableDiagonal ? 8 : 4;
     (void)vzIndex;                                // the reference has no non-vz-index cost (USE_VZIND is always defined, calc_cost_sgm.cpp:4)
-    std::vector<double> flow((size_t)2 * W * H);
-    std::vector<uint32_t> minC((size_t)W * H);
-    const int rc = fsgm_epipolar_sgm_of(ctx_, g1.data.data(), g2.data.data(), W, H, F_, H_, epi_, direction_, dMax, vMax, P1, P2, &o,
-                                        flow.data(), minC.data());
-    if (rc != FSGM_OK) raise(ctx_, "fsgm_epipolar_sgm_of", rc);
-    return to_field(H, W, flow, std::move(minC));
+    // the float form of the fused call returns the field in FlowField's own layout (CV_32FC2: u, v interleaved)
+    FlowField f;
+    const size_t n = (size_t)W * H;
+    f.rows = H; f.cols = W;
+    f.uv.resize(2 * n); f.valid.assign(n, 1); f.cost.resize(n);
+    int rc = fsgm_epipolar_sgm_of_f32_batch_async(ctx_, 1, g1.data.data(), g2.data.data(), W, H, F_, H_, epi_, &direction_, dMax, vMax,
+                                                  P1, P2, &o, f.uv.data(), f.cost.data());
+    if (rc == FSGM_OK) rc = fsgm_synchronize(ctx_);
+    if (rc != FSGM_OK) raise(ctx_, "fsgm_epipolar_sgm_of_f32_batch_async", rc);
+    return f;
 }
 
 }  // namespace fsgm_proj

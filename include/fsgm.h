@@ -121,6 +121,11 @@ FSGM_API int fsgm_epi_cost_dev(fsgm_ctx* ctx, int n_pairs, const uint32_t* d_cen
                       const double* d_offsetFromPosD0, uint8_t* d_raw, uint8_t* d_C);
 FSGM_API int fsgm_sweep_dev(fsgm_ctx* ctx, int n_pairs, const uint8_t* d_C, const uint8_t* d_I1, int width, int height, int dMax,
                    int P1, int P2, int adaptive_thr, int direction, uint8_t* d_L);
+/* fsgm_epi_aggregate_dev / fsgm_epi_partial*_dev take a caller-owned cost volume: its largest byte is measured on the device
+ * (one extra pass over d_C and a stream synchronisation).  Up to 24 — anything fsgm_epi_cost_dev produces — all kernel families
+ * apply; above it the generic sweeps run in the exact or explicit mod-256 form the measured bound requires (the reference's
+ * unsigned char arithmetic, common.h:4-8), never the forms derived for C <= 24.  A d_C that is not 16-byte aligned also takes
+ * the generic sweeps (the row-synchronous kernels move cost rows with bulk copies). */
 FSGM_API int fsgm_epi_aggregate_dev(fsgm_ctx* ctx, int n_pairs, const uint8_t* d_C, const uint8_t* d_I1, int width, int height,
                            int dMax, int P1, int P2, const fsgm_epi_opts* opts, uint16_t* d_Sp /* may be NULL */,
                            const double* d_offsetFromPosD0, double vMax, uint32_t* d_bestD, uint32_t* d_minC);
@@ -210,6 +215,16 @@ FSGM_API int fsgm_epipolar_sgm_of_dev(fsgm_ctx* ctx, int n_pairs, const uint8_t*
 FSGM_API int fsgm_epipolar_sgm_of_batch_async(fsgm_ctx* ctx, int n_pairs, const uint8_t* I0, const uint8_t* I1, int width, int height,
                            const double* F, const double* H, const double* epipole, const int* direction,
                            int dMax, double vMax, int P1, int P2, const fsgm_epi_opts* opts, double* flow, uint32_t* minC);
+/* float forms: flow as float [n][H][W][2], (u, v) interleaved per pixel — the reference's own return type, CV_32FC2
+ * (proj/include/epi_sgm.h:6-12) — each component the fp64 value rounded to nearest.  8 instead of 16 bytes per pixel come
+ * back over PCIe; minC may be NULL in the host form (then 8 B/px down in total). */
+FSGM_API int fsgm_epipolar_sgm_of_f32_dev(fsgm_ctx* ctx, int n_pairs, const uint8_t* d_I0, const uint8_t* d_I1, int width, int height,
+                           const double* F, const double* H, const double* epipole, const int* direction,
+                           int dMax, double vMax, int P1, int P2, const fsgm_epi_opts* opts, void* d_work,
+                           float* d_flow, uint32_t* d_minC);
+FSGM_API int fsgm_epipolar_sgm_of_f32_batch_async(fsgm_ctx* ctx, int n_pairs, const uint8_t* I0, const uint8_t* I1, int width, int height,
+                           const double* F, const double* H, const double* epipole, const int* direction,
+                           int dMax, double vMax, int P1, int P2, const fsgm_epi_opts* opts, float* flow, uint32_t* minC);
 FSGM_API int fsgm_epipolar_sgm_of(fsgm_ctx* ctx, const uint8_t* I0, const uint8_t* I1, int width, int height,
                            const double* F, const double* H, const double* epipole, int direction,
                            int dMax, double vMax, int P1, int P2, const fsgm_epi_opts* opts, double* flow, uint32_t* minC);

@@ -3,7 +3,7 @@
  * This is the CPU checker ("port" oracle) for the CUDA library in fsgm_b200/csrc.  It is a
  * restatement, in different structure, of the arithmetic in the reference's four MEX files;
  * every function cites the reference lines it follows.  It is pinned against the reference's
- * own C++ compiled in place (oracle/_ref, see Makefile) by tests/test_oracle_pin.py and by the
+ * own C++ compiled in place (oracle/_ref, see Makefile) by tests/test_oracle_cpu.py and by the
  * golden fixtures under tests/golden/ (generated from oracle/_ref by tests/golden/make_golden.py).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may

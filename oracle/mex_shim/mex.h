@@ -2,7 +2,7 @@
  *
  * It exists so that the reference's four MEX translation units
  * (/root/reference/calc_*sgm*.cpp) compile unmodified with g++ into
- * oracle/_ref/*.so.  Only the handful of symbols those files touch are
+ * oracle/_ref (libref_<variant>.so).  Only the handful of symbols those files touch are
  * provided.  Two deliberate twists for the parity harness:
  *   - mxMalloc logs every allocation and mxFree only *marks* it, so the driver
  *     can read intermediate buffers (census, raw cost, C, Sp) after
@@ -19,6 +19,7 @@
 #include <cstdio>
 #include <cmath>
 #include <vector>
+#include <stdexcept>
 
 typedef size_t mwSize;
 typedef enum { mxUINT8_CLASS = 9, mxUINT32_CLASS = 13, mxDOUBLE_CLASS = 6 } mxClassID;
@@ -67,6 +68,14 @@ inline double* mxGetPr(const mxArray* a) { return (double*)a->data; }
 inline double mxGetScalar(const mxArray* a) { return *(const double*)a->data; }
 inline mwSize mxGetM(const mxArray* a) { return a->m; }
 inline mwSize mxGetN(const mxArray* a) { return a->n; }
+
+/* Used by the replacement gateways under integration/mex/ (the reference itself signals nothing):
+ *   mexErrMsgTxt leaves the MEX function (MATLAB longjmps; here a C++ exception the harness catches);
+ *   mexAtExit registers a clean-up MATLAB runs when the MEX file is cleared: the harness runs it from shim_run_atexit(). */
+inline void mexErrMsgTxt(const char* msg) { throw std::runtime_error(msg ? msg : "mexErrMsgTxt"); }
+inline std::vector<void (*)(void)>& shim_atexit() { static std::vector<void (*)(void)> v; return v; }
+inline int mexAtExit(void (*fn)(void)) { shim_atexit().push_back(fn); return 0; }
+inline void shim_run_atexit() { for (auto f : shim_atexit()) f(); shim_atexit().clear(); }
 
 #define mxAssert(cond, msg) ((void)0)          /* release-MEX behaviour: compiled out */
 inline int mexPrintf(const char*, ...) { return 0; }

@@ -73,3 +73,23 @@ def test_epipolar_sgm_of_fused_call(ctx, oracle, W, H, D, n):
             assert np.array_equal(minC[i], ref["minC"])
             want = go.epipolar_flow(ref["bestD"], dirn, Rf)
             assert np.array_equal(flow[i].reshape(2, -1)[:, :-1], want.reshape(2, -1)[:, :-1])
+
+
+def test_epipolar_sgm_of_float_form_is_the_rounded_fp64_flow(ctx):
+    """The CV_32FC2 form (float, u/v interleaved; proj/include/epi_sgm.h:6-12) is the fp64 flow rounded to nearest, with and
+    without the optional minC, through the same enqueue-only pipeline."""
+    from fsgm_b200 import api
+    W, H, D, n = 150, 64, 64, 3
+    o = api.epi_opts(paths=8)
+    ps = [synth.epipolar_pair(W, H, D, seed=70 + i) for i in range(n)]
+    cams = [synth.epipolar_camera(W, H, seed=80 + i, rot_deg=0.05) for i in range(n)]
+    I0 = np.stack([p["I1"] for p in ps]); I1 = np.stack([p["I2"] for p in ps])
+    g = ([c["F"] for c in cams], [c["H"] for c in cams], [c["epi"] for c in cams], [c["direction"] for c in cams])
+    flow, minC = ctx.epipolar_sgm_of_batch(I0, I1, *g, D, 0.3, 6, 64, opts=o)
+    f32, m32 = ctx.epipolar_sgm_of_batch(I0, I1, *g, D, 0.3, 6, 64, opts=o, f32=True)
+    assert f32.shape == (n, H, W, 2) and f32.dtype == np.float32
+    assert np.array_equal(m32, minC)
+    assert np.array_equal(f32, np.moveaxis(flow, 1, -1).astype(np.float32))
+    only = np.zeros((n, H, W, 2), np.float32)
+    ctx.epipolar_sgm_of_batch(I0, I1, *g, D, 0.3, 6, 64, opts=o, f32=True, out=(only, None))
+    assert np.array_equal(only, f32)

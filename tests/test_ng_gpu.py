@@ -108,3 +108,29 @@ def test_pydng_vs_oracle(ctx, oracle, W, H, r, aggSize, sub, P1, P2, prior):
     minC, flow = ctx.calc_pyd_cost_sgm_ng(fp["I1"], fp["I2"], mv, r, aggSize, sub, P1, P2)
     assert np.array_equal(minC, want["minC"])
     assert np.array_equal(flow, want["flow"], equal_nan=True)
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("W,H,seed", [(160, 64, 1), (131, 77, 4)])
+def test_ng_larger_image_vs_oracle(ctx, oracle, W, H, seed):
+    """calc_cost_sgm_ng beyond toy sizes (nothing above 40x28 was compared): ~10 k pixels, i.e. 80 k rand() draws and
+    every ring-buffer wrap of the L1 / row hints exercised thousands of times."""
+    fp = synth.flow_pair(W, H, seed=W + 1, umax=6, vmax=3)
+    f = oracle.ref_ng if oracle.have_ref("ng") else oracle.port_ng
+    want = f(fp["I1"], fp["I2"], 6, 32, seed=seed)
+    minC, flow = ctx.calc_cost_sgm_ng(fp["I1"], fp["I2"], None, 1, 2, 0, 6, 32, seed=seed)
+    assert np.array_equal(minC, want["minC"])
+    assert np.array_equal(flow, want["flow"])
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("W,H,r,sub", [(160, 72, 1, 1), (128, 64, 2, 1)])
+def test_pydng_larger_image_vs_oracle(ctx, oracle, W, H, r, sub):
+    fp = synth.flow_pair(W, H, seed=W + r, umax=5, vmax=3)
+    rng = np.random.default_rng(W + 7)
+    mv = rng.normal(0, 2.0, (2, H, W))
+    f = oracle.ref_pydng if oracle.have_ref("pydng") else oracle.port_pydng
+    want = f(fp["I1"], fp["I2"], mv, r, 5, sub, 6, 32)
+    minC, flow = ctx.calc_pyd_cost_sgm_ng(fp["I1"], fp["I2"], mv, r, 5, sub, 6, 32)
+    assert np.array_equal(minC, want["minC"])
+    assert np.array_equal(flow, want["flow"])

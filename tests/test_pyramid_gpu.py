@@ -81,3 +81,21 @@ def test_pyramid_driver_matches_per_level_gateway_calls(ctx):
     rmv, rmc, _ = pyo.pyramidal_sgm(fp["I1"], fp["I2"], solver, numPyd=L)
     mv, minC = ctx.pyramidal_sgm(fp["I1"], fp["I2"], opts=api.pyd_opts(numPyd=L))
     assert np.array_equal(mv, rmv) and np.array_equal(minC, rmc)
+
+
+@pytest.mark.timeout(900)
+def test_config_c_three_levels_full_kitti_size_vs_oracle(ctx, oracle):
+    """BASELINE.json configs[2] at its real size: 3 levels of 1242x375 (-> 621x188 -> 311x94), r = 5 (121 labels), 8 paths,
+    2 passes (pyramidal_sgm.m:14-22, :36-75), the on-device driver against the numpy restatement of the MATLAB loop whose
+    per-level solver is the reference's own calc_pyd_cost_sgm build.  Level 0 alone is ~35 s of one host core."""
+    from fsgm_b200 import api
+    from oracle import pyramid_oracle as pyo
+    solver = (lambda *a: oracle.ref_pyd(*a, stages=False)) if oracle.have_ref("pyd") else (lambda *a: oracle.port_pyd(*a, stages=False))
+    W, H, L = 1242, 375, 3
+    fp = synth.flow_pair(W, H, seed=1, umax=20, vmax=10)
+    rmv, rmc, rlv = pyo.pyramidal_sgm(fp["I1"], fp["I2"], solver, numPyd=L)
+    mv, minC, lv = ctx.pyramidal_sgm(fp["I1"], fp["I2"], opts=api.pyd_opts(numPyd=L), levels=True)
+    assert np.array_equal(minC, rmc)
+    for l in range(L):
+        assert np.array_equal(lv[l], rlv[l]), l
+    assert np.array_equal(mv, rmv)
