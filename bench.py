@@ -2,21 +2,28 @@
 """bench.py — throughput of the fSGM hot path on B200 (BASELINE.json metric: frame-pairs/s and GDE/s at
 KITTI size 1242x375, 256 labels, 8 paths).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--pairs P] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--pairs P] [--impl ours|reference] [--skip a,b,..]
 
 One "step" = the whole hot path (census -> cost volume -> 8-direction aggregation -> WTA/subpixel/vz) over a
 batch of P synthetic KITTI-size pairs per GPU.  For N > 1 launch under torchrun: every rank owns one GPU and
 its own P pairs (weak scaling, no data-path collective: pairs are independent), timing = max over ranks.
 
-Printed JSON (rank 0, one line):
+Printed JSON (rank 0, one line).  The headline keys are BASELINE.json configs[1] (config B):
   value      device-resident throughput (inputs already in HBM), CUDA events on the launch stream
   e2e        same metric through the host-pointer gateway fsgm_calc_cost_sgm_batch with pinned HOST buffers,
-             H2D and D2H inside the timed region
-  roofline   the dominant kernel (the path-aggregation sweep): algorithmic bytes / measured kernel time / HBM peak
-  cpu_baseline  the reference's own C++ (oracle/_ref) or the C restatement, timed on one host core, bounded sample
+             H2D and D2H inside the timed region (42 B/px up: the gateway's operands are fp64 planes)
+  e2e_fused  the same pairs through fsgm_epipolar_sgm_of[_f32]_batch_async (images + F/H/epipole up, flow down)
+  host_h2d_gbs  pinned host->device copy bandwidth measured on every rank at the same time: the ceiling of `e2e`
+  roofline   the dominant kernel (the path-aggregation cluster pass): algorithmic bytes / measured kernel time / HBM peak
+  cpu_baseline  the reference's own C++ (oracle/_ref) or the C restatement, timed on one host core, one full pair
+  latency_ms_single_pair  one pair alone: device-resident call and the host gateway
+  workloads  the other BASELINE.json configs, each with value / roofline / cpu_baseline:
+             A (640x480, D=128), C (3-level pyramidal, r=5 and r=4), D (ng and pyd_ng r=1,2 at 1242x375)  [N = 1]
+             strong_256 (256 KITTI pairs sharded over the ranks) and dirsplit_4k (one 3840x2160 pair, the eight
+             scan directions split over the ranks, verified bit-equal to the single-GPU call)              [N > 1]
 
---impl reference times the reference CPU implementation instead (one process per host core, bounded sample).
-Nothing here reads /root/reference at run time.
+--impl reference times the reference CPU implementation instead (one process per host core, one FULL pair per
+process and step).  Nothing here reads /root/reference at run time.
 """
 from __future__ import annotations
 
@@ -35,15 +42,28 @@ sys.path.insert(0, ROOT)
 
 W, H, D, PATHS, P1, P2, VMAX = 1242, 375, 256, 8, 6, 64, 0.3
 METRIC = "frame-pairs/s (KITTI 1242x375, 256 labels, 8 paths)"
-TRAFFIC_VSWEEP_P15 = 5.387e9   # dram read+write bytes per launch at 15 pairs: mean of the first (1.79 + 1.74 GB) and final (7.15 + 0.09 GB) pass, profiles/r1s_kernels_p15.txt
+# integer issue peak used for the ng variants (integer-bound): the alu pipe issues one warp instruction every
+# two cycles per SM sub-partition (B300_MICROARCH.md "Pipe rates": rt_SMSP = 2) = 64 lane-ops per clock and SM
+INT_OPS_PER_CLK_SM = 64
 
 
-def hbm_peak():
+def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+            j = json.load(f)
+        return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", float(j.get("sm_max_mhz", 1965.0))
     except Exception:
-        return 6650.0, "fallback (B200_PROFILING.md)"
+        return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+def measured_traffic():
+    """dram bytes per pair and launch of the dominant kernel from this round's `ncu --set full` capture, recorded by
+    profiles/summarize.py in profiles/traffic.json together with the capture it came from; None when there is none."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -102,25 +122,25 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_pairs(n: int, seed0: int):
+def make_pairs(n: int, seed0: int, w=W, h=H, d=D):
     from fsgm_b200 import synth
-    ps = [synth.epipolar_pair(W, H, D, seed=seed0 + i, vMax=VMAX) for i in range(n)]
+    ps = [synth.epipolar_pair(w, h, d, seed=seed0 + i, vMax=VMAX) for i in range(n)]
     st = lambda k: np.ascontiguousarray(np.stack([p[k] for p in ps]))
     return st("I1"), st("I2"), st("Pd0"), st("dirn"), st("O")
 
 
 # ------------------------------------------------------------------------------------------------------
-# reference arm: the reference's CPU implementation on the host cores
+# reference arm: the reference's CPU implementation on the host cores, one FULL pair per process and step
 # ------------------------------------------------------------------------------------------------------
-def _cpu_one(args):
-    """worker: one oracle call on a row strip of a synthetic pair; returns seconds"""
-    rows, seed, use_ref = args
+def _cpu_epi(args):
+    """worker: one oracle call on a synthetic pair of `rows` rows; returns seconds"""
+    w, rows, d, seed, use_ref = args
     from fsgm_b200 import synth
     from oracle import pyoracle as po
-    p = synth.epipolar_pair(W, rows, D, seed=seed, vMax=VMAX)
+    p = synth.epipolar_pair(w, rows, d, seed=seed, vMax=VMAX)
     f = po.ref_epi if use_ref else po.port_epi
     t0 = time.perf_counter()
-    f(p["I1"], p["I2"], D, VMAX, p["Pd0"], p["dirn"], p["O"], P1, P2, paths=PATHS, stages=False)
+    f(p["I1"], p["I2"], d, VMAX, p["Pd0"], p["dirn"], p["O"], P1, P2, paths=PATHS, stages=False)
     return time.perf_counter() - t0
 
 
@@ -137,29 +157,38 @@ def run_reference(args):
     if rank != 0:
         return 0
     from concurrent.futures import ProcessPoolExecutor
+    from oracle import pyoracle as po
     kind, use_ref = cpu_kind()
+    # the parent maps the checker library too (the workers are separate processes): one tiny call
+    _cpu_epi((32, 16, 16, 1, use_ref))
     cores = os.cpu_count() or 1
     total_steps = args.steps + args.warmup
-    # one full pair costs ~13-20 s on one core; bound the whole run to ~150 s by timing a row strip per step
-    budget_per_step = 150.0 / max(1, total_steps)
-    rows = int(max(16, min(H, H * budget_per_step / 20.0)))
+    # one full pair is ~6.5 s of one core with the reference build: the whole run (K + W steps) stays within a few minutes up to
+    # ~30 steps; beyond that the steps are capped (reported in "steps") rather than the pair being cut into strips
+    max_steps = max(2, int(240.0 / 7.0))
+    if total_steps > max_steps:
+        warm = min(args.warmup, 2)
+        steps = max_steps - warm
+    else:
+        warm, steps = args.warmup, args.steps
     times = []
     with ProcessPoolExecutor(cores) as ex:
-        for s in range(total_steps):
+        for s in range(warm + steps):
             t0 = time.perf_counter()
-            list(ex.map(_cpu_one, [(rows, 5000 + s * cores + i, use_ref) for i in range(cores)]))
+            list(ex.map(_cpu_epi, [(W, H, D, 5000 + s * cores + i, use_ref) for i in range(cores)]))
             dt = time.perf_counter() - t0
-            if s >= args.warmup:
+            if s >= warm:
                 times.append(dt)
     step_s = float(np.mean(times))
-    pairs_per_s = cores * (rows / H) / step_s
-    sample = f"{cores} processes x one {W}x{rows} row strip ({rows}/{H} of a pair) per step, D={D}, {PATHS} paths"
+    pairs_per_s = cores / step_s
+    sample = (f"{cores} processes x one full {W}x{H} pair per step, D={D}, {PATHS} paths "
+              f"({'oracle/_ref: the reference C++ compiled in place' if use_ref else 'oracle port'}); {steps} timed steps")
     line = {
         "impl": "reference", "metric": METRIC, "value": pairs_per_s, "unit": "pairs/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
+        "steps": steps, "warmup": warm, "ms_per_step": step_s * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"B: KITTI-size {W}x{H}, D={D}, R={PATHS}, epipolar (calc_cost_sgm), CPU reference arm",
-                   "sample": sample},
+        "config": {"workload": f"B: KITTI-size {W}x{H}, D={D}, R={PATHS}, epipolar (calc_cost_sgm), P1={P1} P2={P2} vMax={VMAX}",
+                   "sample": sample, "same_config": True},
         "gde_per_s": pairs_per_s * W * H * D / 1e9,
         "cpu_baseline": {"value": pairs_per_s, "unit": "pairs/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": pairs_per_s, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -171,33 +200,101 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    from fsgm_b200 import api
+class Env:
+    """per-rank state shared by the measurement legs"""
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    # stdout carries exactly one JSON line: anything a library prints to file descriptor 1 (NCCL's "NCCL version ..." banner
-    # on this image) is sent to stderr, and the line is written through a private duplicate of the original stdout
-    sys.stdout.flush()
-    json_out = os.fdopen(os.dup(1), "w")
-    os.dup2(2, 1)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the fSGM hot path has no CPU fallback")
-    torch.cuda.set_device(local)
-    ctx = api.Context(local)
-    ctx.use_torch_stream()
-    ctx.tune(1, args.tune_cluster)
-    ctx.tune(2, int(args.no_overlap))
-    opts = api.epi_opts(paths=PATHS)
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        from fsgm_b200 import api
+        self.torch, self.dist, self.api, self.args = torch, dist, api, args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the fSGM hot path has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        self.ctx = api.Context(self.local)
+        self.ctx.use_torch_stream()
+        self.ctx.tune(1, args.tune_cluster)
+        self.ctx.tune(2, int(args.no_overlap))
+        self.opts = api.epi_opts(paths=PATHS)
+        self.peak, self.peak_src, self.sm_mhz = peaks()
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x: float) -> float:
+        t = self.torch.tensor([x], device="cuda", dtype=self.torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def gather(self, x: float):
+        t = self.torch.tensor([x], device="cuda", dtype=self.torch.float64)
+        if self.world == 1:
+            return [float(x)]
+        out = [self.torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return [float(o.item()) for o in out]
+
+    def timed(self, fn, reps, warm=1):
+        """device time per call in ms (CUDA events on torch's current stream = the context's launch stream)"""
+        torch = self.torch
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+
+def balg_epi(n_px, d, r=PATHS):
+    """C written once, every sweep reads C and writes L, WTA reads the R volumes, + 50 B/px of images/geometry/outputs"""
+    return n_px * d * (1 + 3 * r) + 50 * n_px
+
+
+def balg_pyd(n_px, d, r=8, finest=False):
+    return n_px * d * (1 + 3 * r) + (26 + (16 if finest else 0)) * n_px
+
+
+def probe_h2d(env: Env):
+    """pinned host -> device copy bandwidth with every rank copying at the same time (the ceiling of the gateway-shaped e2e)"""
+    torch = env.torch
+    nbytes = 512 << 20
+    h = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    d = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    d.copy_(h, non_blocking=True)
+    env.barrier()
+    t0 = time.perf_counter()
+    for _ in range(4):
+        d.copy_(h, non_blocking=True)
+    torch.cuda.synchronize()
+    gbs = 4 * nbytes / (time.perf_counter() - t0) / 1e9
+    h2 = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    env.barrier()
+    t0 = time.perf_counter()
+    for _ in range(4):
+        h2.copy_(d, non_blocking=True)
+    torch.cuda.synchronize()
+    d2h = 4 * nbytes / (time.perf_counter() - t0) / 1e9
+    return env.gather(gbs), env.gather(d2h)
+
+
+def headline(env: Env, line: dict):
+    torch, ctx, args, opts = env.torch, env.ctx, env.args, env.opts
     P = args.pairs
     N = W * H
-
-    hI1, hI2, hPd0, hDir, hO = make_pairs(P, 1000 + rank * P)
+    hI1, hI2, hPd0, hDir, hO = make_pairs(P, 1000 + env.rank * P)
     pin = lambda a: torch.from_numpy(a).pin_memory()
     pI1, pI2, pPd0, pDir, pO = (pin(a) for a in (hI1, hI2, hPd0, hDir, hO))
     dI1, dI2, dPd0, dDir, dO = (t.cuda() for t in (pI1, pI2, pPd0, pDir, pO))
@@ -205,12 +302,6 @@ def run_ours(args):
     dMin = torch.empty_like(dBest)
     pBest = torch.empty((P, H, W), dtype=torch.int32).pin_memory()
     pMin = torch.empty((P, H, W), dtype=torch.int32).pin_memory()
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     def step_dev():
         ctx.calc_cost_sgm_dev(dI1, dI2, D, VMAX, dPd0, dDir, dO, P1, P2, dBest, dMin, opts=opts)
@@ -226,10 +317,10 @@ def run_ours(args):
 
     # ---- device-resident throughput -------------------------------------------------------------
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:           # nvidia-smi needs ~1 s to start: launch it before the warm-up
+    with ClockSampler(env.local) as clocks:           # nvidia-smi needs ~1 s to start: launch it before the warm-up
         for _ in range(max(3, args.warmup)):
             step_dev()
-        barrier()
+        env.barrier()
         ctx.profile(True)
         ctx.profile_reset()
         l0 = ctx.launch_count
@@ -240,92 +331,363 @@ def run_ours(args):
         e1.record()
         torch.cuda.synchronize()
         clocks.mark_stop()
-    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
+    ms_total = env.max_over_ranks(e0.elapsed_time(e1))
     launches = ctx.launch_count - l0
     stages = ctx.profile_read()
     ctx.profile(False)
-    barrier()
+    env.barrier()
 
     # ---- end to end through the host gateway (pinned host buffers, copies inside the timed region) ------
-    for _ in range(2):
-        step_e2e()
-    ctx.synchronize()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
-    ctx.synchronize()
-    torch.cuda.synchronize()
-    e2e_s = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_s = float(e2e_s.item())
-    # cheap self-check: host-gateway output equals the device-resident output
-    same = bool(np.array_equal(pBest.numpy(), dBest.cpu().numpy()))
+    def timed_host(step, sync):
+        for _ in range(2):
+            step()
+        sync()
+        env.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step()
+        sync()
+        torch.cuda.synchronize()
+        return env.max_over_ranks(time.perf_counter() - t0)
 
-    if rank == 0:
-        pairs = world * P * args.steps
-        value = pairs / (ms_total / 1e3)
-        peak, peak_src = hbm_peak()
-        # dominant kernel: the row-synchronous cluster kernel (two launches per step: down and up pass, three directions
-        # each, winner-take-all fused into the second).  Its share of SURVEY §8d's algorithmic bytes is 3 B per voxel
-        # and direction (C read + L write + WTA read) = 9*N*D per pair and launch.  When the cluster path is not used
-        # (A/B knob, other shapes) the dominant kernel is the generic sweep: 2*R*N*D per pair and launch.
-        if "vsweep" in stages:
-            k_ms, k_launches = stages["vsweep"]
-            k_name = "vsweep_kernel (3 non-horizontal directions per pass; cost rows by TMA, path state in smem, WTA fused)"
-            # launches are per wave and per pass: pairs per launch = (pairs in the timed region * 2 passes) / launches
-            pairs_per_launch = P * args.steps * 2.0 / k_launches
-            per_launch_bytes = pairs_per_launch * N * D * 9
-            # dram__bytes_read+write per launch from profiles/r1s_kernels_p15.txt (ncu --set full, 15 pairs per launch),
-            # mean of the two passes, scaled to the pairs one launch handles
-            traffic = (TRAFFIC_VSWEEP_P15 * pairs_per_launch / 15.0) if TRAFFIC_VSWEEP_P15 else None
-        else:
-            k_ms, k_launches = stages.get("sweep", (0.0, 0))
-            k_name = "sweep_fast_kernel (path aggregation, all 8 directions in one launch)"
-            per_launch_bytes = P * N * D * 2 * PATHS * args.steps / max(1, k_launches)
-            traffic = None
-        ach = (per_launch_bytes / (k_ms / k_launches * 1e-3) / 1e9) if k_launches else None
-        balg_pair = N * D * (1 + 3 * PATHS) + 50 * N
-        line = {
-            "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"B: KITTI-size {W}x{H}, D={D}, R={PATHS}, epipolar (calc_cost_sgm), P1={P1} P2={P2} vMax={VMAX}",
-                       "pairs_per_step_per_gpu": P, "parallelism": f"batch-dp{world}",
-                       "l2": "per-step working set (>= 1 GB of volumes per pair) is far larger than the 126 MB L2; no flush needed"},
-            "gde_per_s": value * N * D / 1e9,
-            "roofline": {"bound": "hbm", "kernel": k_name,
-                         "achieved": ach, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                         "frac": (ach / peak) if ach else None, "traffic": traffic,
-                         "algorithmic_bytes_per_launch": per_launch_bytes,
-                         "kernel_ms_per_launch": (k_ms / k_launches) if k_launches else None,
-                         "note": "the kernel is bound by instruction issue (ncu: 74-77 % issue slots, 61-68 % alu pipe), not by HBM: it moves "
-                                 "fewer DRAM bytes than the algorithmic count because C is read once for three directions and "
-                                 "neither the six L volumes nor Sp are materialised",
-                         "whole_step_frac": balg_pair * value / world / 1e9 / peak,
-                         "whole_step_algorithmic_bytes_per_pair": balg_pair},
-            "stage_ms_per_step": {k: v[0] / args.steps for k, v in stages.items()},
-            "e2e": {"value": world * P * args.steps / e2e_s, "unit": "pairs/s",
-                    "h2d_bytes_per_step": int(P * N * 42), "d2h_bytes_per_step": int(P * N * 8),
-                    "matches_device_path": same},
-            "gpu_launches": int(launches),
-            "clocks": clocks.summary(),
-        }
-        if world == 1 and not args.no_cpu:
+    e2e_s = timed_host(step_e2e, ctx.synchronize)
+    same = bool(np.array_equal(pBest.numpy(), dBest.cpu().numpy()))     # host-gateway output equals the device-resident output
+
+    # ---- the same pairs through the fused call: images + F, H, epipole up; flow (+ minC) down ---------------------------
+    from fsgm_b200 import synth
+    cams = [synth.epipolar_camera(W, H, seed=2 + i, rot_deg=0.05) for i in range(4)]
+    Fs = [cams[i % 4]["F"] for i in range(P)]; Hs = [cams[i % 4]["H"] for i in range(P)]
+    es = [cams[i % 4]["epi"] for i in range(P)]; ds = [cams[i % 4]["direction"] for i in range(P)]
+    fused = {}
+    hflow64 = torch.empty((P, 2, H, W), dtype=torch.float64).pin_memory()
+    o64 = (hflow64.numpy(), out_views[1])
+    t64 = timed_host(lambda: ctx.epipolar_sgm_of_batch(np_views[0], np_views[1], Fs, Hs, es, ds, D, VMAX, P1, P2, opts=opts,
+                                                       out=o64, asynchronous=True), ctx.synchronize)
+    hflow32 = torch.empty((P, H, W, 2), dtype=torch.float32).pin_memory()
+    o32 = (hflow32.numpy(), out_views[1])
+    t32 = timed_host(lambda: ctx.epipolar_sgm_of_batch(np_views[0], np_views[1], Fs, Hs, es, ds, D, VMAX, P1, P2, opts=opts,
+                                                       out=o32, asynchronous=True, f32=True), ctx.synchronize)
+    same32 = bool(np.array_equal(hflow32.numpy(), np.moveaxis(hflow64.numpy(), 1, -1).astype(np.float32)))
+    tot = env.world * P * args.steps
+    fused = {"value": tot / t32, "unit": "pairs/s", "h2d_bytes_per_step": int(P * N * 2), "d2h_bytes_per_step": int(P * N * 12),
+             "call": "fsgm_epipolar_sgm_of_f32_batch_async: images + F/H/epipole up, CV_32FC2 flow + minC down",
+             "f64_flow": {"value": tot / t64, "d2h_bytes_per_step": int(P * N * 20), "call": "fsgm_epipolar_sgm_of_batch_async"},
+             "f32_equals_rounded_f64": same32}
+    del hflow64, hflow32
+
+    pairs = env.world * P * args.steps
+    value = pairs / (ms_total / 1e3)
+    # dominant kernel: the row-synchronous cluster kernel (two launches per wave: down and up pass, three directions
+    # each, winner-take-all fused into the second).  Its share of SURVEY §8d's algorithmic bytes is 3 B per voxel
+    # and direction (C read + L write + WTA read) = 9*N*D per pair and launch.  When the cluster path is not used
+    # (A/B knob, other shapes) the dominant kernel is the generic sweep: 2*R*N*D per pair and launch.
+    traffic, traffic_src = None, None
+    if "vsweep" in stages:
+        k_ms, k_launches = stages["vsweep"]
+        k_name = "vsweep_kernel (3 non-horizontal directions per pass; cost rows by TMA, path state in smem, WTA fused)"
+        pairs_per_launch = P * args.steps * 2.0 / k_launches       # launches are per wave and per pass
+        per_launch_bytes = pairs_per_launch * N * D * 9
+        tr = measured_traffic()
+        if tr and tr.get("kernel") == "vsweep_kernel":
+            traffic = tr["dram_bytes_per_pair_per_launch"] * pairs_per_launch
+            traffic_src = tr.get("source")
+    else:
+        k_ms, k_launches = stages.get("sweep", (0.0, 0))
+        k_name = "sweep_fast_kernel (path aggregation, all 8 directions in one launch)"
+        per_launch_bytes = P * N * D * 2 * PATHS * args.steps / max(1, k_launches)
+    ach = (per_launch_bytes / (k_ms / k_launches * 1e-3) / 1e9) if k_launches else None
+    balg_pair = balg_epi(N, D)
+    line.update({
+        "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": env.world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": f"B: KITTI-size {W}x{H}, D={D}, R={PATHS}, epipolar (calc_cost_sgm), P1={P1} P2={P2} vMax={VMAX}",
+                   "pairs_per_step_per_gpu": P, "parallelism": f"batch-dp{env.world}",
+                   "l2": "per-step working set (>= 1 GB of volumes per pair) is far larger than the 126 MB L2; no flush needed"},
+        "gde_per_s": value * N * D / 1e9,
+        "roofline": {"bound": "hbm", "kernel": k_name,
+                     "achieved": ach, "peak": env.peak, "peak_source": env.peak_src, "unit": "GB/s",
+                     "frac": (ach / env.peak) if ach else None, "traffic": traffic, "traffic_source": traffic_src,
+                     "algorithmic_bytes_per_launch": per_launch_bytes,
+                     "kernel_ms_per_launch": (k_ms / k_launches) if k_launches else None,
+                     "physical_dram_frac": (traffic / (k_ms / k_launches * 1e-3) / 1e9 / env.peak) if (traffic and k_launches) else None,
+                     "note": "algorithmic bytes per SURVEY.md 8d (C read + L written + L read for WTA, per direction); the kernel is bound by "
+                             "instruction issue, not by HBM: it moves fewer DRAM bytes than the algorithmic count because C is read once for "
+                             "three directions and neither the six L volumes nor Sp are materialised (physical_dram_frac)",
+                     "whole_step_frac": balg_pair * value / env.world / 1e9 / env.peak,
+                     "whole_step_algorithmic_bytes_per_pair": balg_pair},
+        "stage_ms_per_step": {k: v[0] / args.steps for k, v in stages.items()},
+        "e2e": {"value": env.world * P * args.steps / e2e_s, "unit": "pairs/s",
+                "h2d_bytes_per_step": int(P * N * 42), "d2h_bytes_per_step": int(P * N * 8),
+                "matches_device_path": same,
+                "call": "fsgm_calc_cost_sgm_batch_async (the gateway's operands: two u8 images + five fp64 planes per pair)"},
+        "e2e_fused": fused,
+        "gpu_launches": int(launches),
+        "clocks": clocks.summary(),
+    })
+    # single-pair latency (SURVEY.md §7 hard part 1): one pair is a partial wave -> generic one-warp-per-scanline kernels
+    one = [t[:1].contiguous() for t in (dI1, dI2, dPd0, dDir, dO)]
+    b1, m1 = dBest[:1], dMin[:1]
+    lat_dev = env.timed(lambda: ctx.calc_cost_sgm_dev(one[0], one[1], D, VMAX, one[2], one[3], one[4], P1, P2, b1, m1, opts=opts), 10, 3)
+    hv = [v[:1] for v in np_views]
+    ov = (out_views[0][:1], out_views[1][:1])
+    for _ in range(2):
+        ctx.calc_cost_sgm_batch(hv[0], hv[1], D, VMAX, hv[2], hv[3], hv[4], P1, P2, opts=opts, out=ov)
+    t0 = time.perf_counter()
+    for _ in range(10):
+        ctx.calc_cost_sgm_batch(hv[0], hv[1], D, VMAX, hv[2], hv[3], hv[4], P1, P2, opts=opts, out=ov)
+    lat_host = (time.perf_counter() - t0) / 10 * 1e3
+    line["latency_ms_single_pair"] = {"device_resident": lat_dev, "host_gateway": lat_host,
+                                      "note": "one KITTI pair alone on the GPU (a partial wave: generic one-warp-per-scanline kernels); "
+                                              "host_gateway includes the 42 B/px upload from pinned memory and the 8 B/px download"}
+    return dict(dI1=dI1, dI2=dI2, dPd0=dPd0, dDir=dDir, dO=dO)
+
+
+def workload_A(env: Env):
+    """BASELINE.json configs[0]: 640x480, 128 labels, 8 paths (the reference's CPU-runnable case; calc_cost_sgm.cpp:539)"""
+    torch, ctx, opts = env.torch, env.ctx, env.opts
+    w, h, d = 640, 480, 128
+    K = ctx.epi_wave_pairs(w, d, P1, P2, opts) or 16
+    n = 4 * K
+    I1, I2, Pd0, Dir, O = (torch.from_numpy(a).cuda() for a in make_pairs(8, 300, w, h, d))
+    rep = lambda t: t.repeat((n // 8 + 1,) + (1,) * (t.dim() - 1))[:n].contiguous()
+    I1, I2, Pd0, Dir, O = (rep(t) for t in (I1, I2, Pd0, Dir, O))
+    b = torch.empty((n, h, w), dtype=torch.int32, device="cuda"); m = torch.empty_like(b)
+    ms = env.timed(lambda: ctx.calc_cost_sgm_dev(I1, I2, d, VMAX, Pd0, Dir, O, P1, P2, b, m, opts=opts), 5, 2)
+    value = n / (ms * 1e-3)
+    balg = balg_epi(w * h, d)
+    out = {"workload": f"A: {w}x{h}, D={d}, R=8, epipolar (calc_cost_sgm)", "value": value, "unit": "pairs/s",
+           "pairs_per_step": n, "wave_pairs": K, "ms_per_step": ms, "gde_per_s": value * w * h * d / 1e9,
+           "roofline": {"bound": "hbm", "achieved": balg * value / 1e9, "peak": env.peak, "unit": "GB/s",
+                        "frac": balg * value / 1e9 / env.peak, "algorithmic_bytes_per_pair": balg, "traffic": None,
+                        "basis": "whole path: N*D*(1+3R) + 50*N bytes per pair (SURVEY.md 8d) / step time"}}
+    if not env.args.no_cpu:
+        kind, use_ref = cpu_kind()
+        dt = _cpu_epi((w, h, d, 300, use_ref))
+        out["cpu_baseline"] = {"value": 1.0 / dt, "unit": "pairs/s", "cores": 1, "kind": kind,
+                               "sample": f"one full {w}x{h} pair, D={d}, 8 paths, single thread, {dt:.1f} s"}
+    return out
+
+
+def workload_C(env: Env):
+    """BASELINE.json configs[2]: pyramidal SGM, 3 levels of 1242x375, through the on-device driver (pyramidal_sgm.m:36-75 ->
+    calc_pyd_cost_sgm.cpp:439 per level), reference window r=5 (121 labels) and BASELINE's +-4 (81 labels)"""
+    torch, ctx, api = env.torch, env.ctx, env.api
+    from fsgm_b200 import synth
+    n = 8
+    fps = [synth.flow_pair(W, H, seed=1 + i, umax=20, vmax=10) for i in range(n)]
+    I0 = torch.from_numpy(np.stack([f["I1"] for f in fps])).cuda(); I1 = torch.from_numpy(np.stack([f["I2"] for f in fps])).cuda()
+    mv = torch.empty((n, 2, H, W), dtype=torch.float64, device="cuda"); mC = torch.empty((n, H, W), dtype=torch.int32, device="cuda")
+    ws, hs = api.pyramid_dims(W, H, 3)
+    out = {}
+    for r in (5, 4):
+        o = api.pyd_opts(numPyd=3, ver=r, hor=r)
+        ctx.profile(True); ctx.profile_reset()
+        ms = env.timed(lambda: ctx.pyramidal_sgm_dev(I0, I1, mv, mC, opts=o), 3, 1)
+        st = ctx.profile_read(); ctx.profile(False)
+        dl = (2 * r + 1) ** 2
+        value = n / (ms * 1e-3)
+        balg = sum(balg_pyd(w_ * h_, dl, finest=(l == 0)) for l, (w_, h_) in enumerate(zip(ws, hs)))
+        evals = sum(w_ * h_ for w_, h_ in zip(ws, hs)) * dl
+        out[f"r{r}"] = {"workload": f"C: pyramidal SGM, 3 levels {list(zip(ws, hs))}, r={r} (D={dl}), R=8, 2 passes, on-device driver "
+                                    "(fsgm_pyramidal_sgm_dev)", "value": value, "unit": "pairs/s", "pairs_per_step": n,
+                        "ms_per_step": ms, "gde_per_s": value * evals / 1e9,
+                        "stage_ms_per_step": {k: v[0] / 4 for k, v in st.items()},
+                        "roofline": {"bound": "hbm", "achieved": balg * value / 1e9, "peak": env.peak, "unit": "GB/s",
+                                     "frac": balg * value / 1e9 / env.peak, "algorithmic_bytes_per_pair": balg, "traffic": None,
+                                     "basis": "sum over levels of N*D*(1+3R) + 26*N (+16*N mvSub at level 0) (SURVEY.md 8d) / step time"}}
+    if not env.args.no_cpu:
+        from oracle import pyoracle as po
+        use_ref = po.have_ref("pyd")
+        f = po.ref_pyd if use_ref else po.port_pyd
+        a = (fps[0]["I1"], fps[0]["I2"])
+        lv = [a]
+        for _ in range(2):
+            lv.append((synth.reduce2(lv[-1][0]), synth.reduce2(lv[-1][1])))
+        t0 = time.perf_counter()
+        for l in (2, 1):
+            hh, ww = lv[l][0].shape
+            f(lv[l][0], lv[l][1], np.zeros((2, hh, ww)), 5, 5, 2, 0, 6, 32, 1, 2, 0, stages=False)
+        dt = time.perf_counter() - t0
+        px = sum(lv[l][0].size for l in (1, 2)); allpx = sum(x[0].size for x in lv)
+        out["r5"]["cpu_baseline"] = {"value": 1.0 / (dt * allpx / px), "unit": "pairs/s", "cores": 1, "kind": "reference" if use_ref else "port",
+                                     "sample": f"levels 1 and 2 of one pair (621x188 + 311x94, r=5, 8 paths, 2 passes) in {dt:.1f} s on one thread, "
+                                               f"scaled by pixels to the three levels (x{allpx / px:.2f}); the cost per pixel does not depend on the level"}
+    return out
+
+
+def workload_D(env: Env):
+    """BASELINE.json configs[3]: neighbour-guided variants at 1242x375 (ng_sgm.m:20 -> calc_cost_sgm_ng.cpp:484;
+    calc_pyd_cost_sgm_ng.cpp:448), measured on whole images.  Integer-bound: ops/s against the integer-issue peak."""
+    torch, ctx = env.torch, env.ctx
+    from fsgm_b200 import synth
+    sm = torch.cuda.get_device_properties(env.local).multi_processor_count
+    int_peak = sm * INT_OPS_PER_CLK_SM * env.sm_mhz * 1e6
+    fp = synth.flow_pair(W, H, seed=2, umax=20, vmax=10)
+    out = {}
+    # ---- ng: one pair per CTA (raster-serial chain inside a pair), so a step is a batch of >= one pair per SM ----------------------
+    n = env.args.ng_pairs or 2 * sm
+    I1 = torch.from_numpy(np.stack([fp["I1"]] * n)).cuda(); I2 = torch.from_numpy(np.stack([fp["I2"]] * n)).cuda()
+    mC = torch.empty((n, H, W), dtype=torch.int32, device="cuda"); fl = torch.empty((n, 2, H, W), dtype=torch.float64, device="cuda")
+    seeds = list(range(1, n + 1))
+    ms = env.timed(lambda: ctx.calc_cost_sgm_ng_dev(I1, I2, 6, 32, mC, fl, seeds=seeds), 1, 0)
+    I1a, I2a = I1[:1].contiguous(), I2[:1].contiguous()
+    lat = env.timed(lambda: ctx.calc_cost_sgm_ng_dev(I1a, I2a, 6, 32, mC[:1], fl[:1], seeds=[1]), 1, 0)
+    value = n / (ms * 1e-3)
+    ops_px = 4 * 108 * 108 + 108 * 25                    # label-compatibility tests + census Hamming taps per pixel (SURVEY.md 8d)
+    out["ng"] = {"workload": f"D: calc_cost_sgm_ng at {W}x{H} (108 candidates, 4 paths, 1 pass), {n} whole pairs per step", "value": value,
+                 "unit": "pairs/s", "pairs_per_step": n, "ms_per_step": ms, "latency_ms_single_pair": lat,
+                 "roofline": {"bound": "integer issue", "achieved": value * W * H * ops_px / 1e12, "peak": int_peak / 1e12, "unit": "Tops/s",
+                              "frac": value * W * H * ops_px / int_peak, "ops_per_pixel": ops_px, "traffic": None,
+                              "basis": "4*108^2 candidate-compatibility tests + 108*25 Hamming taps per pixel against 64 integer lane-ops "
+                                       "per clock and SM (alu pipe)"}}
+    del I1, I2, mC, fl
+    # ---- pyd_ng: r = 1 (81 candidates) and r = 2 (225) ----------------------------------------------------------------------------
+    for r, n in ((1, 8), (2, 4)):
+        dl = 9 * (2 * r + 1) ** 2
+        I1 = torch.from_numpy(np.stack([fp["I1"]] * n)).cuda(); I2 = torch.from_numpy(np.stack([fp["I2"]] * n)).cuda()
+        mv = torch.zeros((n, 2, H, W), dtype=torch.float64, device="cuda")
+        mC = torch.empty((n, H, W), dtype=torch.int32, device="cuda"); fl = torch.empty((n, 2, H, W), dtype=torch.float64, device="cuda")
+        ms = env.timed(lambda: ctx.calc_pyd_cost_sgm_ng_dev(I1, I2, mv, r, 5, 1, 6, 32, mC, fl), 2, 1)
+        value = n / (ms * 1e-3)
+        ops_px = 4 * dl * dl + dl * 25
+        out[f"pydng_r{r}"] = {"workload": f"D: calc_pyd_cost_sgm_ng at {W}x{H}, r={r} ({dl} candidates, 4 paths, 2 passes)", "value": value,
+                              "unit": "pairs/s", "pairs_per_step": n, "ms_per_step": ms,
+                              "roofline": {"bound": "integer issue", "achieved": value * W * H * ops_px / 1e12, "peak": int_peak / 1e12,
+                                           "unit": "Tops/s", "frac": value * W * H * ops_px / int_peak, "ops_per_pixel": ops_px, "traffic": None,
+                                           "basis": "the reference's O(D^2) formulation: 4*D^2 compatibility tests + 25*D Hamming taps per pixel"}}
+        del I1, I2, mv, mC, fl
+    if not env.args.no_cpu:
+        from oracle import pyoracle as po
+        use_ref = po.have_ref("ng")
+        kind = "reference" if use_ref else "port"
+        ws, hs = 311, 94
+        s2 = synth.flow_pair(ws, hs, seed=3, umax=8, vmax=4)
+        f = po.ref_ng if use_ref else po.port_ng
+        t0 = time.perf_counter(); f(s2["I1"], s2["I2"], 6, 32, seed=1); dt = time.perf_counter() - t0
+        out["ng"]["cpu_baseline"] = {"value": ws * hs / dt / (W * H), "unit": "pairs/s", "cores": 1, "kind": kind,
+                                     "sample": f"one {ws}x{hs} image ({ws * hs / (W * H):.3f} of a KITTI pair) in {dt:.1f} s on one thread, scaled by pixels"}
+        f = po.ref_pydng if use_ref else po.port_pydng
+        t0 = time.perf_counter(); f(s2["I1"], s2["I2"], np.zeros((2, hs, ws)), 1, 5, 1, 6, 32); dt = time.perf_counter() - t0
+        out["pydng_r1"]["cpu_baseline"] = {"value": ws * hs / dt / (W * H), "unit": "pairs/s", "cores": 1, "kind": kind,
+                                           "sample": f"one {ws}x{hs} image, r=1, in {dt:.1f} s on one thread, scaled by pixels"}
+    return out
+
+
+def strong_256(env: Env, dev):
+    """BASELINE.json configs[4], first half: a FIXED batch of 256 KITTI pairs sharded over the ranks (strong scaling).  Rank r owns
+    shard_range(256, r, world) pairs (no data-path collective); time = max over ranks.  256/8 = 32 pairs per rank = two waves of 15
+    + two pairs through the generic kernels: the tail the fixed batch exposes."""
+    torch, ctx, opts = env.torch, env.ctx, env.opts
+    from fsgm_b200.dist import shard_range
+    mine = shard_range(256, env.rank, env.world)
+    n = len(mine)
+    have = dev["dI1"].shape[0]
+    idx = torch.tensor([i % have for i in mine], device="cuda")
+    I1, I2, Pd0, Dir, O = (dev[k].index_select(0, idx) for k in ("dI1", "dI2", "dPd0", "dDir", "dO"))
+    b = torch.empty((n, H, W), dtype=torch.int32, device="cuda"); m = torch.empty_like(b)
+    f = lambda: ctx.calc_cost_sgm_dev(I1, I2, D, VMAX, Pd0, Dir, O, P1, P2, b, m, opts=opts)
+    for _ in range(2):
+        f()
+    env.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 3
+    e0.record()
+    for _ in range(reps):
+        f()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = env.max_over_ranks(e0.elapsed_time(e1) / reps)
+    return {"workload": "E: fixed batch of 256 KITTI pairs (1242x375, D=256, R=8) sharded over the ranks, device-resident", "scaling": "strong",
+            "value": 256 / (ms * 1e-3), "unit": "pairs/s", "ms_per_batch": ms, "pairs_per_rank": n,
+            "pair_content": f"pairs 0..255 map onto this rank's {have} distinct synthetic pairs (index mod {have})"}
+
+
+def dirsplit_4k(env: Env):
+    """BASELINE.json configs[4], second half: ONE 3840x2160 pair, 256 labels, 8 paths, the scan directions split over the ranks and
+    the per-direction volumes reduced over NVLink; verified bit-equal to the single-GPU call on rank 0's copy."""
+    torch, ctx = env.torch, env.ctx
+    from fsgm_b200 import synth
+    from fsgm_b200 import dist as fd
+    w4, h4 = 3840, 2160
+    p = synth.epipolar_pair(w4, h4, D, seed=9)
+    be = fd.GpuBackend(ctx)
+    dev = be.upload(p)
+    dev["_keep_on_device"] = True
+    o8 = env.api.epi_opts(paths=8)
+    b1 = torch.empty((1, h4, w4), dtype=torch.int32, device="cuda"); m1 = torch.empty_like(b1)
+    single = lambda: ctx.calc_cost_sgm_dev(dev["I1"], dev["I2"], D, 0.3, dev["Pd0"], dev["dirn"], dev["O"], P1, P2, b1, m1, opts=o8)
+    ms1 = env.timed(single, 2, 1)
+    split = lambda: fd.epi_direction_split(be, dev, D, 0.3, P1, P2, paths=8)
+    bs, msplit = split()
+    same = bool(torch.equal(bs.reshape(-1), b1.reshape(-1)) and torch.equal(msplit.reshape(-1), m1.reshape(-1)))
+    env.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 3
+    e0.record()
+    for _ in range(reps):
+        split()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = env.max_over_ranks(e0.elapsed_time(e1) / reps)
+    same = env.max_over_ranks(0.0 if same else 1.0) == 0.0
+    n4 = w4 * h4
+    return {"workload": f"E: one {w4}x{h4} pair, D={D}, R=8, directions split over {env.world} GPUs", "value": ms, "unit": "ms",
+            "higher_is_better": False, "single_gpu_ms_same_box": env.max_over_ranks(ms1), "speedup_vs_single_gpu": ms1 / ms,
+            "bit_equal_to_single_gpu_call": same, "gde_per_s": n4 * D / (ms * 1e-3) / 1e9}
+
+
+def run_ours(args):
+    # stdout carries exactly one JSON line: anything a library prints to file descriptor 1 (NCCL's "NCCL version ..." banner
+    # on this image) is sent to stderr, and the line is written through a private duplicate of the original stdout
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    env = Env(args)
+    skip = set(filter(None, args.skip.split(",")))
+    line = {}
+    t_start = time.time()
+    h2d, d2h = probe_h2d(env)
+    dev = headline(env, line)
+    line["host_h2d_gbs"] = {"per_rank": h2d, "sum": sum(h2d), "min": min(h2d), "d2h_per_rank": d2h, "d2h_sum": sum(d2h),
+                            "note": "512 MiB pinned copies, all ranks at the same time"}
+    # the gateway-shaped e2e against its ceiling: 42 B/px up per pair at the slowest rank's copy bandwidth
+    ceil = min(h2d) * 1e9 / (W * H * 42) * env.world
+    line["e2e"]["h2d_ceiling_pairs_per_s"] = ceil
+    line["e2e"]["frac_of_h2d_ceiling"] = line["e2e"]["value"] / ceil
+    wl = {}
+    if env.world == 1:
+        for name, fn in (("A", workload_A), ("C", workload_C), ("D", workload_D)):
+            if name in skip:
+                continue
+            try:
+                wl[name] = fn(env)
+            except Exception as e:                      # a failed side workload is reported, it does not take the headline with it
+                wl[name] = {"error": f"{type(e).__name__}: {e}"}
+            env.torch.cuda.empty_cache()
+    if "strong_256" not in skip:
+        wl["strong_256"] = strong_256(env, dev)
+    del dev
+    env.torch.cuda.empty_cache()
+    if env.world > 1 and "dirsplit_4k" not in skip:
+        try:
+            wl["dirsplit_4k"] = dirsplit_4k(env)
+        except Exception as e:
+            wl["dirsplit_4k"] = {"error": f"{type(e).__name__}: {e}"}
+    line["workloads"] = wl
+    if env.rank == 0:
+        if env.world == 1 and not args.no_cpu:
             kind, use_ref = cpu_kind()
             rows = 375 if use_ref else 96
-            dt = _cpu_one((rows, 1000, use_ref))
+            dt = _cpu_epi((W, rows, D, 1000, use_ref))
             line["cpu_baseline"] = {"value": (rows / H) / dt, "unit": "pairs/s", "cores": 1, "kind": kind,
                                     "sample": f"one {W}x{rows} strip ({rows}/{H} of a pair), D={D}, {PATHS} paths, single thread, {dt:.1f} s"}
+        line["bench_wall_s"] = time.time() - t_start
         print(json.dumps(line), file=json_out, flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-    ctx.close()
+    if env.world > 1:
+        env.dist.barrier()
+        env.dist.destroy_process_group()
+    env.ctx.close()
     return 0
 
 
@@ -336,7 +698,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--pairs", type=int, default=60, help="pairs per step per GPU (60 = four full waves of the 15 resident clusters)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
+    ap.add_argument("--skip", default="", help="comma-separated side workloads to skip: A,C,D,strong_256,dirsplit_4k")
+    ap.add_argument("--ng-pairs", type=int, default=0, help="pairs per step of the ng workload (default: two per SM)")
     ap.add_argument("--no-overlap", action="store_true", help="A/B knob (fsgm_tune key 2): disable the two-stream wave pipeline")
     ap.add_argument("--tune-cluster", type=int, default=0,
                     help="A/B knob (fsgm_tune key 1): 0 auto, -1 generic sweeps only, 1/2/4/8 cluster size")

@@ -150,6 +150,10 @@ class Context:
     def tune(self, key: int, value: int):
         self._ck(self._l.fsgm_tune(self._h, int(key), int(value)))
 
+    def epi_wave_pairs(self, W, D, P1, P2, opts=None) -> int:
+        """pairs per wave of the cluster kernels for this shape (0 = generic kernels only)"""
+        return int(self._l.fsgm_epi_wave_pairs(self._h, int(W), int(D), int(P1), int(P2), C.byref(opts) if opts is not None else None))
+
     def synchronize(self):
         self._ck(self._l.fsgm_synchronize(self._h))
 

@@ -420,6 +420,18 @@ int fsgm_synchronize(fsgm_ctx* c)
     return FSGM_OK;
 }
 
+int fsgm_epi_wave_pairs(fsgm_ctx* c, int W, int D, int P1, int P2, const fsgm_epi_opts* opts)
+{
+    if (!c || W < 1 || D < 1) return 0;
+    fsgm_epi_opts o;
+    if (check_opts(c, opts, &o) != FSGM_OK) return 0;
+    if (cudaSetDevice(c->device) != cudaSuccess) return 0;
+    const int cs = fast_path_cluster(c, W, D, P1, P2, 24, o);
+    if (!cs) return 0;
+    fast_pairs(c, 1, cs, D, W, o.paths == 8 ? 3 : 1);
+    return c->clusters_max;
+}
+
 int fsgm_debug_max_clusters(int cs, size_t smem, int threads) { return fsgm::vsweep_max_clusters(cs, smem, threads); }
 
 int fsgm_tune(fsgm_ctx* c, int key, int value)

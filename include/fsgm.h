@@ -74,6 +74,11 @@ typedef struct fsgm_epi_opts {
     int fb_thr;       /* calc_cost_sgm.cpp:489 default argument thr = 2 (x256 label units)                  */
 } fsgm_epi_opts;
 FSGM_API void fsgm_epi_opts_default(fsgm_epi_opts* o);   /* {4, 2, 1, 0, 1, 0, 2} — the reference as shipped */
+/* Wave size of the epipolar throughput path for this problem shape: the row-synchronous aggregation kernels give every pair one
+ * thread-block cluster for a whole pass, so pairs go through in waves of this many (15 at KITTI width, 256 labels, 8 paths).
+ * Batches that are a multiple of it have no partial wave (which takes the generic kernels).  0 = those kernels do not apply
+ * (label count not 64/128/256, parameters outside the no-wrap domain, adaptive P2, image too wide for the on-chip path state). */
+FSGM_API int         fsgm_epi_wave_pairs(fsgm_ctx* ctx, int width, int dMax, int P1, int P2, const fsgm_epi_opts* opts);
 
 /* ---- gateway 1: calc_cost_sgm (calc_cost_sgm.cpp:539-598) ----------------------------------
  * [bestD, minC, conf, bestD2] = calc_cost_sgm(I1, I2, dMax, vMax, pixelPosD0, normlizeDirection,
