@@ -482,6 +482,7 @@ def workload_C(env: Env):
     out = {}
     for r in (5, 4):
         o = api.pyd_opts(numPyd=3, ver=r, hor=r)
+        ctx.pyramidal_sgm_dev(I0, I1, mv, mC, opts=o)          # first launches (module load, arena growth) stay out of the stage timers
         ctx.profile(True); ctx.profile_reset()
         ms = env.timed(lambda: ctx.pyramidal_sgm_dev(I0, I1, mv, mC, opts=o), 3, 1)
         st = ctx.profile_read(); ctx.profile(False)
@@ -526,7 +527,7 @@ def workload_D(env: Env):
     fp = synth.flow_pair(W, H, seed=2, umax=20, vmax=10)
     out = {}
     # ---- ng: one pair per CTA (raster-serial chain inside a pair), so a step is a batch of >= one pair per SM ----------------------
-    n = env.args.ng_pairs or 2 * sm
+    n = env.args.ng_pairs or 3 * sm                      # three pairs resident per SM (fsgm_tune key 3 picks it from the batch size)
     I1 = torch.from_numpy(np.stack([fp["I1"]] * n)).cuda(); I2 = torch.from_numpy(np.stack([fp["I2"]] * n)).cuda()
     mC = torch.empty((n, H, W), dtype=torch.int32, device="cuda"); fl = torch.empty((n, 2, H, W), dtype=torch.float64, device="cuda")
     seeds = list(range(1, n + 1))
@@ -700,7 +701,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--skip", default="", help="comma-separated side workloads to skip: A,C,D,strong_256,dirsplit_4k")
-    ap.add_argument("--ng-pairs", type=int, default=0, help="pairs per step of the ng workload (default: two per SM)")
+    ap.add_argument("--ng-pairs", type=int, default=0, help="pairs per step of the ng workload (default: three per SM)")
     ap.add_argument("--no-overlap", action="store_true", help="A/B knob (fsgm_tune key 2): disable the two-stream wave pipeline")
     ap.add_argument("--tune-cluster", type=int, default=0,
                     help="A/B knob (fsgm_tune key 1): 0 auto, -1 generic sweeps only, 1/2/4/8 cluster size")

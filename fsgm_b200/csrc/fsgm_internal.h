@@ -39,6 +39,7 @@ struct fsgm_ctx {
     unsigned attr_mask = 0;                 // which kernels already had their max-dynamic-smem attribute set on this device
     int clusters_key[4] = {0, 0, 0, 0}, clusters_max = 0;   // resident clusters for the last queried (cluster size, W, D, ndir)
     int best_key[3] = {0, 0, 0}, best_cs = 0, best_clusters = 0;   // cached vsweep_best_cluster() decision for (W, D, ndir)
+    int ng_occupancy = 0;                   // tuning knob (fsgm_tune key 3): resident pairs per SM of the ng kernel, 0 = by batch size
     int force_cluster = 0;                  // tuning/test knob: 0 auto, -1 generic path only, 1/2/4/8 forced cluster size
     std::string err;
     // profiling

@@ -266,7 +266,11 @@ ng_kernel(const NgParams prm)
 //            global rows pixel p+1 / p+2 will need are fetched into registers;
 //   phase Y: top-2 per direction, Sp + WTA and the ring commits of pixel p, plus the prefetched rows go to shared memory.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NG_THREADS)
+// OCC = CTAs (pairs) resident per SM.  The walk is a chain of dependent phases separated by block barriers, so one CTA leaves most
+// issue slots empty; a second and third pair on the same SM fill them.  OCC = 2 fits without spills (64 registers per thread),
+// OCC = 3 caps the kernel at 40 registers (a few spilled words in the candidate builder).
+template <int OCC>
+__global__ void __launch_bounds__(NG_THREADS, OCC)
 ng_pipe_kernel(const NgParams prm)
 {
     const int W = prm.W, H = prm.H;
@@ -518,7 +522,13 @@ int launch_ng(fsgm_ctx* c, int n, const uint8_t* I1, const uint32_t* cen1, const
         FSGM_CUDA(c, cudaStreamSynchronize(c->stream));       // host_rng_states is a caller temporary
     }
     p.rng_state = d_state;
-    if (W >= 4) ng_pipe_kernel<<<n, NG_THREADS, 0, c->stream>>>(p);      // pipelined phases need p+1 / p+2 to lie outside the cells pixel p commits
+    if (W >= 4) {                                    // pipelined phases need p+1 / p+2 to lie outside the cells pixel p commits
+        // resident pairs per SM: as many as the batch can use (a single pair runs fastest with all the registers)
+        const int occ = c->ng_occupancy > 0 ? c->ng_occupancy : (n > 2 * c->sm_count ? 3 : n > c->sm_count ? 2 : 1);
+        if (occ >= 3) ng_pipe_kernel<3><<<n, NG_THREADS, 0, c->stream>>>(p);
+        else if (occ == 2) ng_pipe_kernel<2><<<n, NG_THREADS, 0, c->stream>>>(p);
+        else ng_pipe_kernel<1><<<n, NG_THREADS, 0, c->stream>>>(p);
+    }
     else ng_kernel<<<n, NG_THREADS, 0, c->stream>>>(p);
     FSGM_LAUNCHED(c);
     return FSGM_OK;

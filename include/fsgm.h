@@ -45,7 +45,8 @@ FSGM_API int         fsgm_synchronize(fsgm_ctx* ctx);
 FSGM_API const char* fsgm_last_error(const fsgm_ctx* ctx);
 /* Tuning / A-B knobs (results never change).  key 1 = aggregation path of the epipolar variant: 0 auto (default),
  * -1 generic one-warp-per-scanline kernels only, 1..16 = thread-block-cluster size of the row-synchronous kernel.
- * key 2 = 1 disables the two-stream wave pipeline (front-end of wave i+1 under the cluster passes of wave i). */
+ * key 2 = 1 disables the two-stream wave pipeline (front-end of wave i+1 under the cluster passes of wave i).
+ * key 3 = pairs resident per SM in the calc_cost_sgm_ng kernel (1..3; 0 = chosen from the batch size). */
 FSGM_API int         fsgm_tune(fsgm_ctx* ctx, int key, int value);
 /* occupancy probe: resident clusters of `cluster_size` CTAs x `threads` threads with `smem_bytes` dynamic shared memory */
 FSGM_API int         fsgm_debug_max_clusters(int cluster_size, size_t smem_bytes, int threads);
