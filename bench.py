@@ -606,23 +606,28 @@ def strong_256(env: Env, dev):
 
 def dirsplit_4k(env: Env):
     """BASELINE.json configs[4], second half: ONE 3840x2160 pair, 256 labels, 8 paths, the scan directions split over the ranks and
-    the per-direction volumes reduced over NVLink; verified bit-equal to the single-GPU call on rank 0's copy."""
+    the per-direction volumes reduced over NVLink (fsgm_calc_cost_sgm_dirsplit_dev: NCCL issued from the C++ host layer); verified
+    bit-equal to the single-GPU call of the same box."""
     torch, ctx = env.torch, env.ctx
     from fsgm_b200 import synth
     from fsgm_b200 import dist as fd
     w4, h4 = 3840, 2160
     p = synth.epipolar_pair(w4, h4, D, seed=9)
-    be = fd.GpuBackend(ctx)
-    dev = be.upload(p)
-    dev["_keep_on_device"] = True
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a[None])).cuda()
+    I1, I2, Pd0, Dir, O = (t(p[k]) for k in ("I1", "I2", "Pd0", "dirn", "O"))
     o8 = env.api.epi_opts(paths=8)
     b1 = torch.empty((1, h4, w4), dtype=torch.int32, device="cuda"); m1 = torch.empty_like(b1)
-    single = lambda: ctx.calc_cost_sgm_dev(dev["I1"], dev["I2"], D, 0.3, dev["Pd0"], dev["dirn"], dev["O"], P1, P2, b1, m1, opts=o8)
+    bs = torch.empty_like(b1); ms_ = torch.empty_like(b1)
+    single = lambda: ctx.calc_cost_sgm_dev(I1, I2, D, 0.3, Pd0, Dir, O, P1, P2, b1, m1, opts=o8)
     ms1 = env.timed(single, 2, 1)
-    split = lambda: fd.epi_direction_split(be, dev, D, 0.3, P1, P2, paths=8)
-    bs, msplit = split()
-    same = bool(torch.equal(bs.reshape(-1), b1.reshape(-1)) and torch.equal(msplit.reshape(-1), m1.reshape(-1)))
+    fd.nccl_init(ctx)
+    split = lambda: ctx.calc_cost_sgm_dirsplit_dev(I1, I2, D, 0.3, Pd0, Dir, O, P1, P2, bs, ms_, opts=o8)
+    split()
+    torch.cuda.synchronize()
+    same = bool(torch.equal(bs, b1) and torch.equal(ms_, m1))
+    split()
     env.barrier()
+    ctx.profile(True); ctx.profile_reset()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = 3
     e0.record()
@@ -630,12 +635,22 @@ def dirsplit_4k(env: Env):
         split()
     e1.record()
     torch.cuda.synchronize()
+    st = ctx.profile_read(); ctx.profile(False)
     ms = env.max_over_ranks(e0.elapsed_time(e1) / reps)
     same = env.max_over_ranks(0.0 if same else 1.0) == 0.0
+    ms1 = env.max_over_ranks(ms1)
+    plan = env.api.dirsplit_plan(w4, h4, D, 8, P1, P2, env.rank, env.world)
     n4 = w4 * h4
-    return {"workload": f"E: one {w4}x{h4} pair, D={D}, R=8, directions split over {env.world} GPUs", "value": ms, "unit": "ms",
-            "higher_is_better": False, "single_gpu_ms_same_box": env.max_over_ranks(ms1), "speedup_vs_single_gpu": ms1 / ms,
-            "bit_equal_to_single_gpu_call": same, "gde_per_s": n4 * D / (ms * 1e-3) / 1e9}
+    sent = (env.world - 1) / env.world * n4 * D * (1 if plan.exchange_u8 else 2)
+    ex_ms = st.get("exchange", (0.0, 0))[0] / reps
+    ctx.dist_finalize()
+    return {"workload": f"E: one {w4}x{h4} pair, D={D}, R=8, directions split over {env.world} GPUs (fsgm_calc_cost_sgm_dirsplit_dev)",
+            "value": ms, "unit": "ms", "higher_is_better": False, "single_gpu_ms_same_box": ms1, "speedup_vs_single_gpu": ms1 / ms,
+            "bit_equal_to_single_gpu_call": same, "gde_per_s": n4 * D / (ms * 1e-3) / 1e9,
+            "exchange": "u8 slabs, grouped ncclSend/ncclRecv" if plan.exchange_u8 else "u16 pairs as ncclUint32, ncclReduceScatter",
+            "nvlink_bytes_sent_per_rank": int(sent), "stage_ms_rank0": {k: v[0] / reps for k, v in st.items()},
+            "exchange_gbs_per_rank": (sent / (ex_ms * 1e-3) / 1e9) if ex_ms else None,
+            "nvlink_peak_gbs_per_direction": 900.0}
 
 
 def run_ours(args):

@@ -94,6 +94,41 @@ def pyramid_dims(W: int, H: int, numPyd: int):
     return list(ws), list(hs)
 
 
+class DirsplitInfo(C.Structure):
+    """fsgm_dirsplit_info: the plan of the direction-split path for one rank (include/fsgm.h)"""
+    _fields_ = [("slab_pixels", C.c_size_t), ("padded_pixels", C.c_size_t), ("first_pixel", C.c_size_t), ("n_pixels", C.c_size_t),
+                ("dirs", C.c_int * 8), ("n_dirs", C.c_int), ("exchange_u8", C.c_int)]
+
+
+def shard_range(n: int, rank: int, world: int) -> range:
+    """fsgm_shard_range: contiguous block of n independent units (pairs) owned by `rank`"""
+    lo, cnt = C.c_int(), C.c_int()
+    rc = lib().fsgm_shard_range(int(n), int(rank), int(world), C.byref(lo), C.byref(cnt))
+    if rc != FSGM_OK:
+        raise FsgmError(rc, "fsgm_shard_range")
+    return range(lo.value, lo.value + cnt.value)
+
+
+def dirsplit_plan(W: int, H: int, D: int, paths: int, P1: int, P2: int, rank: int, world: int) -> DirsplitInfo:
+    info = DirsplitInfo()
+    rc = lib().fsgm_dirsplit_plan(int(W), int(H), int(D), int(paths), int(P1), int(P2), int(rank), int(world), C.byref(info))
+    if rc != FSGM_OK:
+        raise FsgmError(rc, "fsgm_dirsplit_plan")
+    return info
+
+
+DIST_ID_BYTES = 128
+
+
+def dist_unique_id() -> bytes:
+    """fsgm_dist_unique_id: the NCCL rendezvous id rank 0 creates and hands to the other ranks"""
+    buf = C.create_string_buffer(DIST_ID_BYTES)
+    rc = lib().fsgm_dist_unique_id(buf, C.c_size_t(DIST_ID_BYTES))
+    if rc != FSGM_OK:
+        raise FsgmError(rc, "fsgm_dist_unique_id (is libnccl.so.2 loadable?)")
+    return buf.raw
+
+
 class NgOpts(C.Structure):
     _fields_ = [("seed", C.c_uint), ("rand_stream", C.c_void_p)]
 
@@ -149,6 +184,25 @@ class Context:
 
     def tune(self, key: int, value: int):
         self._ck(self._l.fsgm_tune(self._h, int(key), int(value)))
+
+    # ------------------------------------------------------------------ multi-GPU (NCCL communicator owned by the context)
+    def dist_init(self, unique_id: bytes, rank: int, world: int):
+        """fsgm_dist_init: collective over all ranks (ncclCommInitRank on this context's device)"""
+        self._ck(self._l.fsgm_dist_init(self._h, C.c_char_p(unique_id), C.c_size_t(len(unique_id)), int(rank), int(world)))
+
+    def dist_finalize(self):
+        self._ck(self._l.fsgm_dist_finalize(self._h))
+
+    def dist_allgather_u32(self, send, recv):
+        self._ck(self._l.fsgm_dist_allgather_u32(self._h, _dp(send), C.c_size_t(send.numel()), _dp(recv)))
+
+    def calc_cost_sgm_dirsplit_dev(self, I1, I2, dMax, vMax, Pd0, dirn, O, P1, P2, bestD, minC, opts=None):
+        """ONE pair ([1][H][W] tensors, the same on every rank), scan directions split over the ranks of the communicator;
+        bestD / minC are complete and identical on every rank"""
+        H, W = I1.shape[-2:]
+        self._ck(self._l.fsgm_calc_cost_sgm_dirsplit_dev(
+            self._h, _dp(I1), _dp(I2), W, H, int(dMax), C.c_double(vMax), _dp(Pd0), _dp(dirn), _dp(O), int(P1), int(P2),
+            C.byref(opts) if opts is not None else None, _dp(bestD), _dp(minC)))
 
     def epi_wave_pairs(self, W, D, P1, P2, opts=None) -> int:
         """pairs per wave of the cluster kernels for this shape (0 = generic kernels only)"""

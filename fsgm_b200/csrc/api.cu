@@ -95,7 +95,7 @@ int pipe_reserve(fsgm_ctx* c, size_t bytes_per_slot)
     return FSGM_OK;
 }
 
-static int check_dims(fsgm_ctx* c, int n, int W, int H, int D)
+int check_dims(fsgm_ctx* c, int n, int W, int H, int D)
 {
     if (!c) return FSGM_ERR_ARG;
     if (n < 1 || W < 1 || H < 1) return fail(c, FSGM_ERR_ARG, "n_pairs, width and height must be positive");
@@ -104,7 +104,7 @@ static int check_dims(fsgm_ctx* c, int n, int W, int H, int D)
     return FSGM_OK;
 }
 
-static int enabled_dirs(const fsgm_epi_opts& o, int* dirs)
+int enabled_dirs(const fsgm_epi_opts& o, int* dirs)
 {
     int k = 0;
     for (int r = 0; r < 8; ++r)
@@ -112,7 +112,7 @@ static int enabled_dirs(const fsgm_epi_opts& o, int* dirs)
     return k;
 }
 
-static int check_opts(fsgm_ctx* c, const fsgm_epi_opts* in, fsgm_epi_opts* o)
+int check_opts(fsgm_ctx* c, const fsgm_epi_opts* in, fsgm_epi_opts* o)
 {
     if (in) *o = *in; else fsgm_epi_opts_default(o);
     if (o->paths != 4 && o->paths != 8) return fail(c, FSGM_ERR_ARG, "opts.paths must be 4 or 8");
@@ -389,6 +389,7 @@ void fsgm_destroy(fsgm_ctx* c)
     if (c->arena) cudaFree(c->arena);
     if (c->geo_params) cudaFree(c->geo_params);
     if (c->d_scalar) cudaFree(c->d_scalar);
+    dist_release(c);
     if (c->geo_host) cudaFreeHost(c->geo_host);
     for (auto e : c->geo_ev) if (e) cudaEventDestroy(e);
     for (auto& t : c->timers) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
@@ -472,7 +473,7 @@ int fsgm_profile_read(fsgm_ctx* c, int stage, double* ms, uint64_t* launches)
 const char* fsgm_stage_name(int stage)
 {
     static const char* names[ST_COUNT] = { "census", "epi_cost", "sweep", "wta", "pyd_cost", "pyd_sweep", "pyd_wta",
-                                           "ng", "pydng_cost", "pydng_sweep", "pydng_wta", "misc", "vsweep", "pyramid", "geometry" };
+                                           "ng", "pydng_cost", "pydng_sweep", "pydng_wta", "misc", "vsweep", "pyramid", "geometry", "exchange" };
     return (stage >= 0 && stage < ST_COUNT) ? names[stage] : nullptr;
 }
 int fsgm_stage_count(void) { return ST_COUNT; }
@@ -608,7 +609,7 @@ int fsgm_epi_wta_slabs_dev(fsgm_ctx* c, const uint8_t* d_slabs, int n_slabs, con
         return fail(c, FSGM_ERR_ARG, "bad argument");
     if (D < 1 || D > 512) return fail(c, FSGM_ERR_DOMAIN, "dMax must be in 1..512");
     FSGM_CUDA(c, cudaSetDevice(c->device));
-    return launch_slab_wta(c, d_slabs, n_slabs, d_next_label0, n_pixels, D, subpixel, vz_to_disp, d_O, vMax, d_bestD, d_minC);
+    return launch_slab_wta(c, d_slabs, n_slabs, n_pixels * (size_t)D, d_next_label0, n_pixels, D, subpixel, vz_to_disp, d_O, vMax, d_bestD, d_minC);
 }
 
 int fsgm_epi_wta_sp_dev(fsgm_ctx* c, const uint16_t* d_Sp, const uint16_t* d_next_label0, size_t n_pixels, int D,

@@ -10,7 +10,7 @@
 namespace fsgm {
 // pipeline stages, for the optional per-stage CUDA-event timing (fsgm_profile_*)
 enum Stage { ST_CENSUS = 0, ST_EPI_COST, ST_SWEEP, ST_WTA, ST_PYD_COST, ST_PYD_SWEEP, ST_PYD_WTA,
-             ST_NG, ST_PYDNG_COST, ST_PYDNG_SWEEP, ST_PYDNG_WTA, ST_MISC, ST_VSWEEP, ST_PYRAMID, ST_GEOMETRY, ST_COUNT };
+             ST_NG, ST_PYDNG_COST, ST_PYDNG_SWEEP, ST_PYDNG_WTA, ST_MISC, ST_VSWEEP, ST_PYRAMID, ST_GEOMETRY, ST_EXCHANGE, ST_COUNT };
 struct StageTimer { cudaEvent_t a, b; int stage; };
 // double-buffered device staging + copy streams for the host-pointer gateways
 struct HostPipe {
@@ -49,6 +49,10 @@ struct fsgm_ctx {
     double stage_ms[fsgm::ST_COUNT] = {};
     uint64_t stage_launches[fsgm::ST_COUNT] = {};
     fsgm::HostPipe pipe;
+    // multi-GPU (dist.cu): the context's NCCL communicator, one rank per context
+    void* nccl_comm = nullptr;
+    bool nccl_owned = false;
+    int rank = 0, world = 1;
     void* d_scalar = nullptr;               // 256 B of device memory for small read-backs (launch_max_u8)
     void* geo_params = nullptr;             // per-pair F, H, epipole, direction of the dense-geometry prologue (geometry.cu)
     size_t geo_cap = 0;
@@ -101,6 +105,12 @@ inline bool dir_enabled(int r, int total_pass, bool diag) {
     return total_pass >= 1;
 }
 
+// ---- argument checks shared by the entry points (api.cu) -----------------------------------------------
+int check_dims(fsgm_ctx* c, int n, int W, int H, int D);
+int check_opts(fsgm_ctx* c, const fsgm_epi_opts* in, fsgm_epi_opts* o);
+int enabled_dirs(const fsgm_epi_opts& o, int* dirs);
+void dist_release(fsgm_ctx* c);                                 // dist.cu: drops the context's NCCL communicator
+
 // ---- kernel launchers (definitions in the .cu files) -------------------------------------------
 int launch_census(fsgm_ctx* c, int n_images, const uint8_t* img, int W, int H, uint32_t* cen);
 int launch_epi_cost_fused(fsgm_ctx* c, int n, const double* d_vz, const uint32_t* cen1, const uint32_t* cen2, int W, int H, int D,
@@ -118,7 +128,7 @@ bool sweep_needs_wrap(int P1, int P2, int cmax);
 int launch_epi_wta(fsgm_ctx* c, int n, uint8_t* const* Lvols, int n_dirs, int W, int H, int D, int subpixel,
                    int vz_to_disp, const double* O, double vMax, uint16_t* Sp16, uint32_t* bestD, uint32_t* minC);
 
-int launch_slab_wta(fsgm_ctx* c, const uint8_t* vols, int n_vols, const uint16_t* next0, size_t npix, int D, int subpixel,
+int launch_slab_wta(fsgm_ctx* c, const uint8_t* vols, int n_vols, size_t vol_stride, const uint16_t* next0, size_t npix, int D, int subpixel,
                     int vz_to_disp, const double* O, double vMax, uint32_t* bestD, uint32_t* minC);
 int launch_add_u8(fsgm_ctx* c, uint8_t* a, const uint8_t* b, size_t bytes);
 int launch_max_u8(fsgm_ctx* c, const uint8_t* v, size_t bytes, int* cmax);   // synchronous read-back

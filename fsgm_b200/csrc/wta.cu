@@ -153,13 +153,13 @@ int launch_epi_wta(fsgm_ctx* c, int n, uint8_t* const* Lvols, int n_dirs, int W,
 }
 
 // WTA over one slab of pixels from n_vols u8 partial volumes (the all-to-all form of the direction-split path)
-int launch_slab_wta(fsgm_ctx* c, const uint8_t* vols, int n_vols, const uint16_t* next0, size_t npix, int D, int subpixel,
+int launch_slab_wta(fsgm_ctx* c, const uint8_t* vols, int n_vols, size_t vol_stride, const uint16_t* next0, size_t npix, int D, int subpixel,
                     int vz_to_disp, const double* O, double vMax, uint32_t* bestD, uint32_t* minC)
 {
     if (D > WTA_MAXD) return fail(c, FSGM_ERR_DOMAIN, "label count must be <= 512");
     StageScope ss(c, ST_WTA);
     WtaParams p{};
-    for (int k = 0; k < n_vols; ++k) p.L[k] = vols + (size_t)k * npix * D;
+    for (int k = 0; k < n_vols; ++k) p.L[k] = vols + (size_t)k * vol_stride;      // slabs may be padded past npix pixels
     p.n_dirs = n_vols; p.W = (int)npix; p.H = 1; p.D = D; p.subpixel = subpixel; p.vz_to_disp = vz_to_disp;
     p.O = O; p.vMax = vMax; p.Sp16 = nullptr; p.Sp_in = nullptr; p.next0 = next0; p.bestD = bestD; p.minC = minC;
     dim3 grid((unsigned)((npix + WTA_WARPS * 32 - 1) / (WTA_WARPS * 32)), 1);

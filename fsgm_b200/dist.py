@@ -1,4 +1,13 @@
-"""Multi-GPU host logic for the fSGM hot path.  One process per GPU, torch.distributed for the plumbing.
+"""Multi-GPU harness for the fSGM hot path.  One process per GPU.
+
+The product path lives in the C ABI (csrc/dist.cu): `fsgm_dist_init` gives every context an NCCL communicator and
+`fsgm_calc_cost_sgm_dirsplit_dev` runs the direction split with the collectives issued from C++; `nccl_init()` below only carries
+the 128-byte rendezvous id from rank 0 to the others over torch.distributed, and `shard_range` / `split_directions` /
+`slab_pixels` are views of the library's own plan (`fsgm_shard_range`, `fsgm_dirsplit_plan`).
+
+`epi_direction_split` is the same data flow written against a small backend interface with torch.distributed collectives: it is
+what the CPU test-suite runs over gloo (world_size 2 and 4) with the oracle as compute backend, slab by slab against the
+single-process oracle, and it can drive the library's stage seams on GPUs (GpuBackend).
 
 Two partitionings, nothing else:
 
@@ -22,26 +31,35 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
+from . import api
+
 ALL_DIRS_8 = (0, 1, 2, 3, 4, 5, 6, 7)       # L1(+x) L3(+y) L2(+x+y) L4(-x+y), then reversed (include/fsgm.h)
 ALL_DIRS_4 = (0, 1, 4, 5)
 
 
 def shard_range(n: int, rank: int, world: int) -> range:
-    """contiguous block partition of n independent units (pairs) over `world` ranks"""
-    base, rem = divmod(n, world)
-    lo = rank * base + min(rank, rem)
-    return range(lo, lo + base + (1 if rank < rem else 0))
+    """contiguous block partition of n independent units (pairs) over `world` ranks (fsgm_shard_range)"""
+    return api.shard_range(n, rank, world)
 
 
 def split_directions(paths: int, rank: int, world: int):
-    dirs = ALL_DIRS_8 if paths == 8 else ALL_DIRS_4
-    return tuple(dirs[rank::world])
+    """this rank's scan directions (fsgm_dirsplit_plan)"""
+    info = api.dirsplit_plan(2, 2, 16, paths, 0, 0, rank, world)
+    return tuple(info.dirs[:info.n_dirs])
 
 
 def slab_pixels(N: int, world: int) -> int:
-    """pixels per rank after the reduce-scatter: equal slabs, even so that slab*D u16 values pack into whole u32 words"""
-    s = -(-N // world)
-    return s + (s & 1)
+    """pixels per rank after the reduction: equal slabs, even so that slab*D u16 values pack into whole u32 words"""
+    return int(api.dirsplit_plan(N, 1, 16, 8, 0, 0, 0, world).slab_pixels)
+
+
+def nccl_init(ctx, group=None):
+    """Give `ctx` its NCCL communicator (fsgm_dist_init): rank 0 creates the rendezvous id, torch.distributed carries the 128
+    bytes to the other ranks (any backend), every rank joins."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    box = [api.dist_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    ctx.dist_init(box[0], rank, world)
 
 
 class GpuBackend:
@@ -116,13 +134,11 @@ def epi_direction_split(backend, pair, D, vMax, P1, P2, paths=8, group=None):
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     H, W = pair["I1"].shape[-2:]
     N = H * W
-    slab = slab_pixels(N, world)
-    n_pad = slab * world
+    plan = api.dirsplit_plan(W, H, D, paths, P1, P2, rank, world)          # the library's own plan (csrc/dist.cu)
+    slab, n_pad = int(plan.slab_pixels), int(plan.padded_pixels)
     Cvol, I1 = backend.cost_volume(pair, D, vMax)
-    my_dirs = split_directions(paths, rank, world)
-    k_max = -(-(8 if paths == 8 else 4) // world)
-    use_u8 = (P1 >= 0 and P2 >= 0 and 24 + P1 + P2 <= 255 and 48 + P2 <= 255 and k_max * (24 + P2) <= 255 and D % 16 == 0
-              and hasattr(backend, "partial_u8") and os.environ.get("FSGM_DIRSPLIT_U16") != "1")
+    my_dirs = tuple(plan.dirs[:plan.n_dirs])
+    use_u8 = bool(plan.exchange_u8) and hasattr(backend, "partial_u8") and os.environ.get("FSGM_DIRSPLIT_U16") != "1"
     if use_u8:
         # every rank's directions fit a byte together: exchange u8 pixel slabs with ONE all-to-all (half the bytes of the
         # u16 reduce-scatter) and sum the received slabs inside the WTA kernel

@@ -32,7 +32,7 @@ extern "C" {
 #define FSGM_ERR_DOMAIN    -2   /* parameter combination outside what the kernels implement    */
 #define FSGM_ERR_CUDA      -3   /* CUDA runtime / launch failure (see fsgm_last_error)          */
 #define FSGM_ERR_NOMEM     -4   /* scratch arena could not be grown                            */
-#define FSGM_ERR_NCCL      -5
+#define FSGM_ERR_NCCL      -5   /* NCCL missing, no communicator on the context, or a collective failed           */
 
 typedef struct fsgm_ctx fsgm_ctx;
 
@@ -148,7 +148,7 @@ FSGM_API int fsgm_convert_vzind_to_disp_dev(fsgm_ctx* ctx, int n_pairs, uint32_t
                          const double* d_offsetFromPosD0, double vMax, int n);
 
 /* direction-split building blocks for ONE large pair (the R scan directions spread over GPUs, volumes reduced over
- * NVLink by the caller — fsgm_b200/dist.py does it with an NCCL reduce-scatter on the u16 pairs viewed as u32):
+ * NVLink) — the stage seams of fsgm_calc_cost_sgm_dirsplit_dev below, for callers that issue the collectives themselves:
  *   partial : sweeps (calc_cost_sgm.cpp:114-257) for the listed directions, summed into u16 [H*W][dMax]
  *   wta_sp  : calc_cost_sgm.cpp:259-308 + :414-426 over n_pixels consecutive pixels of a reduced volume;
  *             d_next_label0 = Sp[.][0] of the pixel after the slab (the value the reference reads for label dMax-1),
@@ -166,6 +166,46 @@ FSGM_API int fsgm_epi_wta_slabs_dev(fsgm_ctx* ctx, const uint8_t* d_slabs, int n
 FSGM_API int fsgm_epi_wta_sp_dev(fsgm_ctx* ctx, const uint16_t* d_Sp, const uint16_t* d_next_label0, size_t n_pixels, int dMax,
                          int subpixel, int vz_to_disp, const double* d_offsetFromPosD0, double vMax,
                          uint32_t* d_bestD, uint32_t* d_minC);
+
+/* ---- multi-GPU (one fsgm_ctx per GPU / rank; NCCL over NVLink) ---------------------------------------------------
+ * The library binds NCCL at run time (dlopen of libnccl.so.2) and owns, or is lent, one communicator per context.  All failures on
+ * this side return FSGM_ERR_NCCL (fsgm_last_error has NCCL's text).
+ *   fsgm_dist_unique_id   rank 0 creates the rendezvous id (128 bytes, ncclUniqueId) and hands it to the other ranks by any channel
+ *   fsgm_dist_init        ncclCommInitRank on the context's device; collective over all `world` ranks
+ *   fsgm_dist_adopt_comm  use a caller-owned ncclComm_t instead (not destroyed by the library)
+ *   fsgm_dist_finalize    drop the communicator (fsgm_destroy does it too)
+ * Two partitionings exist for this path:
+ *   batch of independent pairs : rank r takes the block fsgm_shard_range() gives it and calls the ordinary gateways — no data-path
+ *                                collective; fsgm_dist_allgather_u32 is there for callers that want the sharded outputs everywhere
+ *   one large pair             : fsgm_calc_cost_sgm_dirsplit_dev — every rank passes the SAME pair; the scan directions of sgm()
+ *                                (calc_cost_sgm.cpp:114-257) are split over the ranks, the per-direction volumes are reduced over
+ *                                NVLink per pixel slab (u8 slabs through one grouped send/recv exchange when every rank's
+ *                                directions fit a byte together, else ncclReduceScatter on u16 pairs typed ncclUint32), every rank
+ *                                runs WTA on its slab and the outputs are all-gathered: d_bestD / d_minC are complete and
+ *                                identical on every rank, and bit-identical to fsgm_calc_cost_sgm_dev on one GPU. */
+#define FSGM_DIST_ID_BYTES 128
+typedef struct fsgm_dirsplit_info {
+    size_t slab_pixels;      /* pixels per rank after the reduction (even; the last slabs may reach past the image)          */
+    size_t padded_pixels;    /* slab_pixels * world                                                                         */
+    size_t first_pixel;      /* this rank's slab: pixels [first_pixel, first_pixel + n_pixels) of the row-major image       */
+    size_t n_pixels;
+    int    dirs[8];          /* this rank's scan directions (order of fsgm_sweep_dev), n_dirs of them                       */
+    int    n_dirs;
+    int    exchange_u8;      /* 1: u8 slabs, grouped send/recv; 0: u16 reduce-scatter                                       */
+} fsgm_dirsplit_info;
+FSGM_API int fsgm_shard_range(int n, int rank, int world, int* first, int* count);
+FSGM_API int fsgm_dirsplit_plan(int width, int height, int dMax, int paths, int P1, int P2, int rank, int world, fsgm_dirsplit_info* out);
+FSGM_API int fsgm_dist_unique_id(void* id, size_t bytes);
+FSGM_API int fsgm_dist_init(fsgm_ctx* ctx, const void* id, size_t bytes, int rank, int world);
+FSGM_API int fsgm_dist_adopt_comm(fsgm_ctx* ctx, void* nccl_comm, int rank, int world);
+FSGM_API int fsgm_dist_finalize(fsgm_ctx* ctx);
+FSGM_API int fsgm_dist_rank(const fsgm_ctx* ctx);
+FSGM_API int fsgm_dist_world(const fsgm_ctx* ctx);
+FSGM_API int fsgm_dist_allgather_u32(fsgm_ctx* ctx, const uint32_t* d_send, size_t count, uint32_t* d_recv /* [world][count] */);
+FSGM_API int fsgm_calc_cost_sgm_dirsplit_dev(fsgm_ctx* ctx, const uint8_t* d_I1, const uint8_t* d_I2, int width, int height,
+                           int dMax, double vMax, const double* d_pixelPosD0, const double* d_normlizeDirection,
+                           const double* d_offsetFromPosD0, int P1, int P2, const fsgm_epi_opts* opts,
+                           uint32_t* d_bestD, uint32_t* d_minC);
 
 /* ---- gateway 2: calc_pyd_cost_sgm (calc_pyd_cost_sgm.cpp:439-510) ------------------------------
  * [bestD, minC, mvSub] = calc_pyd_cost_sgm(I1, I2, preMv, halfSearchWinSizeX, halfSearchWinSizeY, aggHalfWinSize,

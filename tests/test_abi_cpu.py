@@ -61,3 +61,28 @@ def test_glibc_rand_matches_libc():
         libc.srand(ctypes.c_uint(seed))
         want = np.array([libc.rand() for _ in range(2000)], np.int32)
         assert np.array_equal(api.glibc_rand(seed, 2000), want), seed
+
+
+def test_multi_gpu_plan_helpers_are_host_only():
+    """fsgm_shard_range / fsgm_dirsplit_plan (csrc/dist.cu) need no GPU: block partition of a batch, and the direction-split plan
+    (slabs even and covering the image, every direction owned exactly once, u8 exchange exactly when every rank's directions fit a
+    byte together)."""
+    from fsgm_b200 import api
+    for n in (0, 1, 7, 256):
+        for world in (1, 2, 3, 8):
+            seen = [i for r in range(world) for i in api.shard_range(n, r, world)]
+            assert seen == list(range(n))
+    for world in (1, 2, 3, 4, 8):
+        for paths in (4, 8):
+            infos = [api.dirsplit_plan(1242, 375, 256, paths, 6, 64, r, world) for r in range(world)]
+            dirs = sorted(d for i in infos for d in i.dirs[:i.n_dirs])
+            assert dirs == ([0, 1, 2, 3, 4, 5, 6, 7] if paths == 8 else [0, 1, 4, 5])
+            assert all(i.slab_pixels % 2 == 0 and i.padded_pixels == i.slab_pixels * world for i in infos)
+            assert sum(i.n_pixels for i in infos) == 1242 * 375
+            assert [i.first_pixel for i in infos] == [min(1242 * 375, r * infos[0].slab_pixels) for r in range(world)]
+            kmax = -(-paths // world)
+            assert all(i.exchange_u8 == int(kmax * (24 + 64) <= 255) for i in infos)
+    assert api.dirsplit_plan(64, 64, 40, 8, 6, 64, 0, 8).exchange_u8 == 0          # label count not a multiple of 16
+    assert api.dirsplit_plan(64, 64, 64, 8, 200, 250, 0, 8).exchange_u8 == 0       # mod-256 parameter domain
+    with pytest.raises(api.FsgmError):
+        api.dirsplit_plan(64, 64, 64, 5, 6, 64, 0, 2)
