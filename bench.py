@@ -643,14 +643,30 @@ def dirsplit_4k(env: Env):
     n4 = w4 * h4
     sent = (env.world - 1) / env.world * n4 * D * (1 if plan.exchange_u8 else 2)
     ex_ms = st.get("exchange", (0.0, 0))[0] / reps
+    # A/B: the same call with the peer-store form switched off (partial volumes exchanged by NCCL after the sweeps)
+    ctx.tune(4, 1)
+    split(); split()
+    env.barrier()
+    e0.record()
+    for _ in range(reps):
+        split()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_nccl = env.max_over_ranks(e0.elapsed_time(e1) / reps)
+    same_nccl = env.max_over_ranks(0.0 if bool(torch.equal(bs, b1) and torch.equal(ms_, m1)) else 1.0) == 0.0
+    ctx.tune(4, 0)
     ctx.dist_finalize()
     return {"workload": f"E: one {w4}x{h4} pair, D={D}, R=8, directions split over {env.world} GPUs (fsgm_calc_cost_sgm_dirsplit_dev)",
             "value": ms, "unit": "ms", "higher_is_better": False, "single_gpu_ms_same_box": ms1, "speedup_vs_single_gpu": ms1 / ms,
             "bit_equal_to_single_gpu_call": same, "gde_per_s": n4 * D / (ms * 1e-3) / 1e9,
-            "exchange": "u8 slabs, grouped ncclSend/ncclRecv" if plan.exchange_u8 else "u16 pairs as ncclUint32, ncclReduceScatter",
-            "nvlink_bytes_sent_per_rank": int(sent), "stage_ms_rank0": {k: v[0] / reps for k, v in st.items()},
-            "exchange_gbs_per_rank": (sent / (ex_ms * 1e-3) / 1e9) if ex_ms else None,
-            "nvlink_peak_gbs_per_direction": 900.0}
+            "exchange": "none: the sweep kernel stores every L row into the peer-mapped memory of the slab's owner (NVLink) while it computes",
+            "nvlink_bytes_sent_per_rank": int((env.world - 1) / env.world * n4 * D * plan.n_dirs),
+            "stage_ms_rank0": {k: v[0] / reps for k, v in st.items()},
+            "nvlink_gbs_per_rank_during_sweeps": ((env.world - 1) / env.world * n4 * D * plan.n_dirs / (st["sweep"][0] / reps * 1e-3) / 1e9) if "sweep" in st else None,
+            "nvlink_peak_gbs_per_direction": 900.0,
+            "nccl_exchange_form": {"value": ms_nccl, "unit": "ms", "bit_equal_to_single_gpu_call": same_nccl,
+                                   "exchange": "u8 slabs, grouped ncclSend/ncclRecv" if plan.exchange_u8 else "u16 pairs as ncclUint32, ncclReduceScatter",
+                                   "nvlink_bytes_sent_per_rank": int(sent)}}
 
 
 def run_ours(args):

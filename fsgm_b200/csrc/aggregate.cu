@@ -46,6 +46,12 @@ struct SweepParams {
     int n_dirs;
     int W, H, D;
     int P1, P2, adaptive_thr;
+    // SCATTER (direction split over GPUs, dist.cu): a pixel's L row goes straight into the memory of the rank that owns the pixel's
+    // slab — peer[j] is rank j's receive buffer (peer-mapped over NVLink, or local for j == this rank), laid out
+    // [direction slot][slab_pixels][D]; direction k of this launch writes slot slot[k].
+    uint8_t* peer[16];
+    int slot[8];
+    unsigned slab_pixels;
 };
 
 template <int NREG> struct Words { uint32_t w[(NREG + 1) / 2]; };
@@ -113,7 +119,7 @@ __device__ __forceinline__ void store_row(uint8_t* __restrict__ pix, int lane, i
 //   * a path restart is branch-free: the previous state is replaced by zeros with M = 0, for which the step formula
 //     yields L = C, and the new minimum is forced to 0 afterwards (the reference's path-start rule, :152-180).
 // ------------------------------------------------------------------------------------------------------------
-template <int NREG, int MODE, bool ADAPT>
+template <int NREG, int MODE, bool ADAPT, bool SCATTER = false>
 __global__ void __launch_bounds__(SWEEP_WARPS * 32)
 sweep_fast_kernel(const SweepParams prm)
 {
@@ -174,6 +180,10 @@ sweep_fast_kernel(const SweepParams prm)
     uint32_t M = 0;
     int prev_pix = 0;
     bool restart = true;
+    // SCATTER: the slab [own_lo, own_hi) the cursor is in and the base its rows are written against; a scanline changes slab a
+    // handful of times (horizontal: at most once), so the division runs only then
+    unsigned own_lo = 1, own_hi = 0;
+    uint8_t* own_base = nullptr;
 
     for (int t0 = 0; t0 < len; t0 += PF) {
 #pragma unroll
@@ -210,6 +220,15 @@ sweep_fast_kernel(const SweepParams prm)
             M = restart ? 0u : m;
 #pragma unroll
             for (int i = 0; i < NREG; ++i) Lr[i] = Ln[i];
+            if (SCATTER) {
+                const unsigned up = (unsigned)pix;
+                if (up < own_lo || up >= own_hi) {
+                    const unsigned j = up / prm.slab_pixels;
+                    own_lo = j * prm.slab_pixels; own_hi = own_lo + prm.slab_pixels;
+                    own_base = prm.peer[j] + ((size_t)prm.slot[k] * prm.slab_pixels - own_lo) * (size_t)D;
+                }
+                store_row<NREG, MODE>(own_base + (size_t)up * (uint32_t)D, lane, D, Lr);
+            } else
             store_row<NREG, MODE>(Lb + (size_t)(uint32_t)pix * (uint32_t)D, lane, D, Lr);
             prev_pix = pix;
             restart = (--restart_in == 0);
@@ -523,6 +542,39 @@ int launch_sweeps(fsgm_ctx* c, int n, const uint8_t* C, const uint8_t* I1, int W
         case 4: sweep_dispatch<4>(p, mode, wrap, adapt, grid, c->stream); break;
         default: sweep_dispatch<8>(p, mode, wrap, adapt, grid, c->stream); break;
     }
+    FSGM_LAUNCHED(c);
+    return FSGM_OK;
+}
+
+// Direction-split form (dist.cu): the listed directions of ONE pair, every pixel's L row written into the receive buffer of the
+// rank that owns the pixel's slab (see SweepParams).  No-wrap domain, no adaptive P2 (the caller falls back to local volumes +
+// an NCCL exchange otherwise).
+int launch_sweeps_scatter(fsgm_ctx* c, const uint8_t* C, int W, int H, int D, int P1, int P2, const int* dirs, const int* slots,
+                          int n_dirs, uint8_t* const* peer, int world, size_t slab_pixels)
+{
+    if (D < 1 || D > 512) return fail(c, FSGM_ERR_DOMAIN, "label count must be in 1..512");
+    if (n_dirs < 1 || n_dirs > 8 || world < 1 || world > 16) return fail(c, FSGM_ERR_ARG, "n_dirs / world");
+    if (sweep_needs_wrap(P1, P2, 24)) return fail(c, FSGM_ERR_DOMAIN, "scatter sweeps need the no-wrap parameter domain");
+    StageScope ss(c, ST_SWEEP);
+    SweepParams p{};
+    p.C = C; p.n_dirs = n_dirs; p.W = W; p.H = H; p.D = D; p.P1 = P1; p.P2 = P2; p.adaptive_thr = 0;
+    p.slab_pixels = (unsigned)slab_pixels;
+    for (int j = 0; j < world; ++j) p.peer[j] = peer[j];
+    p.line_start[0] = 0;
+    for (int k = 0; k < n_dirs; ++k) {
+        p.dir[k] = dirs[k]; p.slot[k] = slots[k]; p.L[k] = nullptr;
+        p.line_start[k + 1] = p.line_start[k] + (dir_dy(dirs[k]) == 0 ? H : W);
+    }
+    const int nreg = D <= 64 ? 1 : D <= 128 ? 2 : D <= 256 ? 4 : 8;
+    const int nb = 2 * nreg;
+    const int mode = (D == 32 * nb) ? LM_FULL : (D % nb == 0 ? LM_VECPAD : LM_BYTES);
+    dim3 grid((p.line_start[n_dirs] + SWEEP_WARPS - 1) / SWEEP_WARPS, 1);
+#define SC_GO(NR) do { \
+        if (mode == LM_FULL) sweep_fast_kernel<NR, LM_FULL, false, true><<<grid, SWEEP_WARPS * 32, 0, c->stream>>>(p); \
+        else if (mode == LM_VECPAD) sweep_fast_kernel<NR, LM_VECPAD, false, true><<<grid, SWEEP_WARPS * 32, 0, c->stream>>>(p); \
+        else sweep_fast_kernel<NR, LM_BYTES, false, true><<<grid, SWEEP_WARPS * 32, 0, c->stream>>>(p); } while (0)
+    switch (nreg) { case 1: SC_GO(1); break; case 2: SC_GO(2); break; case 4: SC_GO(4); break; default: SC_GO(8); break; }
+#undef SC_GO
     FSGM_LAUNCHED(c);
     return FSGM_OK;
 }

@@ -12,6 +12,12 @@
 //         bytes of the u16 reduce-scatter) and the received slabs are summed inside the WTA kernel;
 //       - u16 exchange otherwise: ncclReduceScatter(sum) on the u16 pairs typed ncclUint32 — per-voxel totals are at most
 //         8*255 < 65536, so no carry crosses a half-word and the integer sum is exact.
+//       - peer-store form (default when the GPUs can map each other's memory, i.e. one NVSwitch box): no exchange step at all.
+//         Every rank's receive buffer is mapped into the other ranks (cudaIpc), and the sweep kernel writes each pixel's L row
+//         straight into the memory of the rank that owns the pixel's slab (sweep_fast_kernel<.., SCATTER>, aggregate.cu): the
+//         NVLink transfer runs under the sweep's own arithmetic, tile by tile, instead of after it.  One 4-byte all-gather
+//         orders the stores before the owners' WTA.  The two exchange forms above remain as the fallback (no peer access,
+//         mod-256 parameter domain, adaptive P2) and for A/B (fsgm_tune key 4).
 //     The reference's read of the NEXT pixel's label 0 for argmin == dMax-1 (:293-296) crosses slab boundaries: the first voxel
 //     of every slab is all-gathered (one word per rank) and handed to the previous rank's WTA.
 //
@@ -95,10 +101,84 @@ __global__ void first_voxel_kernel(const uint8_t* slabs, int n_vols, size_t stri
     *out = a;
 }
 
+struct P2PMsg { cudaIpcMemHandle_t h; int ok; int pad[15]; };
+static_assert(sizeof(P2PMsg) == 128, "P2PMsg is exchanged as 128 bytes");
+
+void p2p_drop(fsgm_ctx* c)
+{
+    for (int j = 0; j < 16; ++j) {
+        if (c->p2p_peer[j] && c->p2p_peer[j] != c->p2p_local) cudaIpcCloseMemHandle(c->p2p_peer[j]);
+        c->p2p_peer[j] = nullptr;
+    }
+    if (c->p2p_local) cudaFree(c->p2p_local);
+    c->p2p_local = nullptr; c->p2p_bytes = 0;
+}
+
+// Collective: make sure every rank owns a receive buffer of >= bytes that all other ranks have mapped.  Returns FSGM_OK with
+// *usable = false when peer mapping is not available anywhere (the decision is agreed between the ranks: all or none).
+int p2p_ensure(fsgm_ctx* c, NcclApi* a, size_t bytes, bool* usable)
+{
+    *usable = false;
+    if (c->p2p_state < 0 || c->no_p2p || c->world > 16) return FSGM_OK;
+    if (bytes <= c->p2p_bytes) { *usable = true; return FSGM_OK; }
+    ncclComm_t comm = static_cast<ncclComm_t>(c->nccl_comm);
+    const int world = c->world, rank = c->rank;
+    FSGM_CUDA(c, cudaStreamSynchronize(c->stream));
+    p2p_drop(c);
+    P2PMsg mine{};
+    void* local = nullptr;
+    mine.ok = cudaMalloc(&local, bytes) == cudaSuccess && cudaIpcGetMemHandle(&mine.h, local) == cudaSuccess;
+    cudaGetLastError();
+    P2PMsg* stage = nullptr;                                   // [1 + world] messages in device memory
+    if (cudaMalloc(reinterpret_cast<void**>(&stage), sizeof(P2PMsg) * (world + 1)) != cudaSuccess) {
+        cudaGetLastError(); if (local) cudaFree(local);
+        return fail(c, FSGM_ERR_NOMEM, "cudaMalloc(peer handle staging)");
+    }
+    std::vector<P2PMsg> all(world);
+    auto agree = [&](bool* everyone) -> int {                 // all-gather `mine`, AND the ok flags
+        FSGM_CUDA(c, cudaMemcpyAsync(stage, &mine, sizeof mine, cudaMemcpyHostToDevice, c->stream));
+        FSGM_NCCL(c, a->AllGather(stage, stage + 1, sizeof(P2PMsg), ncclUint8, comm, c->stream));
+        FSGM_CUDA(c, cudaMemcpyAsync(all.data(), stage + 1, sizeof(P2PMsg) * world, cudaMemcpyDeviceToHost, c->stream));
+        FSGM_CUDA(c, cudaStreamSynchronize(c->stream));
+        *everyone = true;
+        for (int j = 0; j < world; ++j) *everyone &= all[j].ok != 0;
+        return FSGM_OK;
+    };
+    bool ok_all = false;
+    int rc = agree(&ok_all);
+    if (rc == FSGM_OK && ok_all) {
+        c->p2p_local = local; c->p2p_bytes = bytes; local = nullptr;
+        for (int j = 0; j < world && mine.ok; ++j) {
+            if (j == rank) { c->p2p_peer[j] = c->p2p_local; continue; }
+            void* ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, all[j].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); mine.ok = 0; }
+            else c->p2p_peer[j] = ptr;
+        }
+        rc = agree(&ok_all);                                   // second round: did every rank map every buffer?
+    }
+    cudaFree(stage);
+    if (local) cudaFree(local);
+    if (rc != FSGM_OK) { p2p_drop(c); return rc; }
+    if (!ok_all) { p2p_drop(c); c->p2p_state = -1; return FSGM_OK; }
+    c->p2p_state = 1;
+    *usable = true;
+    return FSGM_OK;
+}
+
+// word[0] = total of the first voxel (label 0 of the first pixel) of the NEXT rank's slab, read through its peer mapping
+__global__ void first_voxel_peer_kernel(const uint8_t* next_rank_buf, int n_vols, size_t stride, uint32_t* out)
+{
+    uint32_t a = 0;
+    for (int k = 0; k < n_vols; ++k) a += next_rank_buf[(size_t)k * stride];
+    *out = a;
+}
+
 }  // namespace
 
 void dist_release(fsgm_ctx* c)
 {
+    p2p_drop(c);
+    c->p2p_state = 0;
     if (c->nccl_comm && c->nccl_owned) { NcclApi* a = nccl_api(); if (a->CommDestroy) a->CommDestroy(static_cast<ncclComm_t>(c->nccl_comm)); }
     c->nccl_comm = nullptr; c->nccl_owned = false; c->rank = 0; c->world = 1;
 }
@@ -255,7 +335,29 @@ int fsgm_calc_cost_sgm_dirsplit_dev(fsgm_ctx* c, const uint8_t* d_I1, const uint
     FSGM_TRY(arena_get(c, npad, &allM));
     FSGM_TRY(arena_get(c, (size_t)world + 1, &firsts));
     const uint16_t* next0 = (rank + 1 < world) ? reinterpret_cast<const uint16_t*>(firsts + 1 + rank + 1) : nullptr;   // low half of the word
-    if (u8x) {
+    int all_dirs[8];
+    const int nd_all = enabled_dirs(o, all_dirs);
+    bool scatter = !adaptive && !sweep_needs_wrap(P1, P2, 24) && D % 16 == 0;
+    if (scatter) FSGM_TRY(p2p_ensure(c, a, (size_t)nd_all * slab * D, &scatter));
+    if (scatter) {
+        // ---- peer-store form: the sweeps write every L row into its slab owner's buffer; no exchange step -------------------------
+        int slots[8];
+        for (int i = 0; i < nmy; ++i) slots[i] = rank + i * world;           // position of my i-th direction in the enabled list
+        uint8_t* peers[16];
+        for (int j = 0; j < world; ++j) peers[j] = static_cast<uint8_t*>(c->p2p_peer[j]);
+        if (nmy) FSGM_TRY(launch_sweeps_scatter(c, C, W, H, D, P1, P2, my, slots, nmy, peers, world, slab));
+        {
+            StageScope ss(c, ST_EXCHANGE);
+            // every rank's stores have landed once every rank has passed this point (kernel completion makes them visible)
+            FSGM_NCCL(c, a->AllGather(firsts, firsts + 1, 1, ncclUint32, comm, c->stream));
+            if (rank + 1 < world) {
+                first_voxel_peer_kernel<<<1, 1, 0, c->stream>>>(peers[rank + 1], nd_all, slab * D, firsts + 1 + rank + 1);
+                FSGM_LAUNCHED(c);
+            }
+        }
+        if (cnt) FSGM_TRY(launch_slab_wta(c, static_cast<const uint8_t*>(c->p2p_local), nd_all, slab * D, next0, cnt, D, o.subpixel,
+                                          o.vz_to_disp, d_O + plan.first_pixel, vMax, slabB, slabM));
+    } else if (u8x) {
         // ---- this rank's directions summed into one u8 volume, exchanged slab-wise, summed inside the WTA kernel -------------------
         uint8_t *part, *recv, *L[8];
         FSGM_TRY(arena_get(c, npad * D, &part));

@@ -53,6 +53,12 @@ struct fsgm_ctx {
     void* nccl_comm = nullptr;
     bool nccl_owned = false;
     int rank = 0, world = 1;
+    // peer-mapped receive buffers of the direction split: p2p_peer[j] = rank j's buffer (cudaIpc mapping; [rank] = p2p_local)
+    void* p2p_local = nullptr;
+    size_t p2p_bytes = 0;
+    void* p2p_peer[16] = {};
+    int p2p_state = 0;                      // 0 untried, 1 usable, -1 peer access unavailable (NCCL exchange instead)
+    int no_p2p = 0;                         // tuning knob (fsgm_tune key 4): 1 = never use the peer-store form
     void* d_scalar = nullptr;               // 256 B of device memory for small read-backs (launch_max_u8)
     void* geo_params = nullptr;             // per-pair F, H, epipole, direction of the dense-geometry prologue (geometry.cu)
     size_t geo_cap = 0;
@@ -124,6 +130,8 @@ int launch_epi_cost(fsgm_ctx* c, int n, const double* d_vz, const uint32_t* cen1
 int launch_sweeps(fsgm_ctx* c, int n, const uint8_t* C, const uint8_t* I1, int W, int H, int D,
                   int P1, int P2, int adaptive_thr, int cmax, const int* dirs, int n_dirs, uint8_t* const* Lvols);
 bool sweep_needs_wrap(int P1, int P2, int cmax);
+int launch_sweeps_scatter(fsgm_ctx* c, const uint8_t* C, int W, int H, int D, int P1, int P2, const int* dirs, const int* slots,
+                          int n_dirs, uint8_t* const* peer, int world, size_t slab_pixels);
 // sum of n_dirs L volumes -> WTA -> subpixel -> (optionally) vz->disparity; Sp16 (u16 [n][N][D]) may be null
 int launch_epi_wta(fsgm_ctx* c, int n, uint8_t* const* Lvols, int n_dirs, int W, int H, int D, int subpixel,
                    int vz_to_disp, const double* O, double vMax, uint16_t* Sp16, uint32_t* bestD, uint32_t* minC);

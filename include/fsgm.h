@@ -46,7 +46,8 @@ FSGM_API const char* fsgm_last_error(const fsgm_ctx* ctx);
 /* Tuning / A-B knobs (results never change).  key 1 = aggregation path of the epipolar variant: 0 auto (default),
  * -1 generic one-warp-per-scanline kernels only, 1..16 = thread-block-cluster size of the row-synchronous kernel.
  * key 2 = 1 disables the two-stream wave pipeline (front-end of wave i+1 under the cluster passes of wave i).
- * key 3 = pairs resident per SM in the calc_cost_sgm_ng kernel (1..3; 0 = chosen from the batch size). */
+ * key 3 = pairs resident per SM in the calc_cost_sgm_ng kernel (1..3; 0 = chosen from the batch size).
+ * key 4 = 1: the direction split never uses the peer-store form (NCCL exchange of the partial volumes instead). */
 FSGM_API int         fsgm_tune(fsgm_ctx* ctx, int key, int value);
 /* occupancy probe: resident clusters of `cluster_size` CTAs x `threads` threads with `smem_bytes` dynamic shared memory */
 FSGM_API int         fsgm_debug_max_clusters(int cluster_size, size_t smem_bytes, int threads);
@@ -179,9 +180,11 @@ FSGM_API int fsgm_epi_wta_sp_dev(fsgm_ctx* ctx, const uint16_t* d_Sp, const uint
  *                                collective; fsgm_dist_allgather_u32 is there for callers that want the sharded outputs everywhere
  *   one large pair             : fsgm_calc_cost_sgm_dirsplit_dev — every rank passes the SAME pair; the scan directions of sgm()
  *                                (calc_cost_sgm.cpp:114-257) are split over the ranks, the per-direction volumes are reduced over
- *                                NVLink per pixel slab (u8 slabs through one grouped send/recv exchange when every rank's
- *                                directions fit a byte together, else ncclReduceScatter on u16 pairs typed ncclUint32), every rank
- *                                runs WTA on its slab and the outputs are all-gathered: d_bestD / d_minC are complete and
+ *                                NVLink per pixel slab — by the sweep kernel itself, which stores every pixel's row into the
+ *                                peer-mapped memory of the slab's owner while it computes (fallback without peer access: u8
+ *                                slabs through one grouped send/recv exchange when every rank's directions fit a byte
+ *                                together, else ncclReduceScatter on u16 pairs typed ncclUint32) — every rank runs WTA on
+ *                                its slab and the outputs are all-gathered: d_bestD / d_minC are complete and
  *                                identical on every rank, and bit-identical to fsgm_calc_cost_sgm_dev on one GPU. */
 #define FSGM_DIST_ID_BYTES 128
 typedef struct fsgm_dirsplit_info {

@@ -27,7 +27,10 @@ def main():
     # a label count the fused cost kernel does not take, an image smaller than the rank count's slabs
     cases = ((97, 61, 64, 8, 6, 64, 0), (130, 75, 256, 8, 6, 32, 0), (64, 48, 128, 4, 6, 64, 0), (50, 33, 40, 8, 200, 250, 0),
              (71, 40, 64, 8, 6, 64, 1), (3, 1, 16, 8, 6, 64, 0), (1242, 375, 256, 8, 6, 64, 0))
-    for (W, H, D, paths, P1, P2, adp) in cases:
+    # every case twice: the peer-store form (sweeps write into the slab owners' memory over NVLink) and, with fsgm_tune key 4, the
+    # NCCL exchange of partial volumes that stands behind it
+    for no_p2p, (W, H, D, paths, P1, P2, adp) in [(m, cs) for m in (0, 1) for cs in cases]:
+        ctx.tune(4, no_p2p)
         p = synth.epipolar_pair(W, H, D, seed=3)
         o = api.epi_opts(paths=paths, adaptive_p2=adp)
         dev = [t(p[k]) for k in ("I1", "I2", "Pd0", "dirn", "O")]
@@ -41,8 +44,11 @@ def main():
         ok &= same
         plan = api.dirsplit_plan(W, H, D, paths, P1, P2, rank, world)
         if rank == 0:
-            print(f"dirsplit(C ABI) {W}x{H} D={D} paths={paths} P=({P1},{P2}) adaptive={adp} world={world} "
-                  f"{'u8 exchange' if plan.exchange_u8 else 'u16 reduce-scatter'}: {'OK' if same else 'MISMATCH'} ({dt * 1e3:.1f} ms)", flush=True)
+            form = ("peer stores" if (not no_p2p and not adp and D % 16 == 0 and P1 + P2 + 24 <= 255) else
+                    "u8 exchange" if plan.exchange_u8 else "u16 reduce-scatter")
+            print(f"dirsplit(C ABI) {W}x{H} D={D} paths={paths} P=({P1},{P2}) adaptive={adp} world={world} {form}: "
+                  f"{'OK' if same else 'MISMATCH'} ({dt * 1e3:.1f} ms)", flush=True)
+    ctx.tune(4, 0)
     # the stage seams with torch.distributed collectives
     be = fd.GpuBackend(ctx)
     W, H, D, paths = 130, 75, 256, 8
