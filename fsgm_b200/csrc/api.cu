@@ -441,6 +441,7 @@ int fsgm_tune(fsgm_ctx* c, int key, int value)
     if (key == 1) { c->force_cluster = value; return FSGM_OK; }
     if (key == 2) { c->no_overlap = value != 0; return FSGM_OK; }
     if (key == 4) { c->no_p2p = value != 0; return FSGM_OK; }
+    if (key == 5) { c->pyd_cluster = value; return FSGM_OK; }
     if (key == 3) { c->ng_occupancy = value < 0 ? 0 : value > 3 ? 3 : value; return FSGM_OK; }
     return fail(c, FSGM_ERR_ARG, "unknown tuning key");
 }

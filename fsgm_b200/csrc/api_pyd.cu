@@ -50,7 +50,32 @@ int pyd_aggregate(fsgm_ctx* c, int n, const uint8_t* C, const uint8_t* I1, const
 size_t pyd_scratch_bytes(int n, int W, int H, int D)
 {
     const size_t N = (size_t)W * H;
-    return 2 * align256(n * N * 4) + 9 * align256(n * N * D);
+    // generic path: C + 8 L volumes of D bytes per pixel; cluster path: 4 padded volumes (<= 176 B per pixel) + records + flags
+    return 2 * align256(n * N * 4) + std::max(9 * align256(n * N * D), 4 * align256(n * N * 176) + align256(n * N * 16) + align256(n * N));
+}
+
+// The row-synchronous cluster path (pydv.cu): padded-grid cost volume, the two horizontal directions through the scanline kernel
+// (padded in and out), down pass -> byte volume, up pass + WTA -> records, finalize.
+int pyd_pipeline_cluster(fsgm_ctx* c, int n, int cs, const uint32_t* cen1, const uint32_t* cen2, const uint8_t* d_I1, int W, int H,
+                         const double* d_preMv, int mvW, int mvH, const PydCfg& g, uint32_t* d_bestD, uint32_t* d_minC, double* d_mvSub)
+{
+    const size_t N = (size_t)W * H;
+    const int PITCH = 16 * g.Sx;
+    uint8_t *C, *H0, *H1, *S1, *flags; uint4* rec;
+    FSGM_TRY(arena_get(c, n * N * PITCH, &C));
+    FSGM_TRY(arena_get(c, n * N * PITCH, &H0));
+    FSGM_TRY(arena_get(c, n * N * PITCH, &H1));
+    FSGM_TRY(arena_get(c, n * N * PITCH, &S1));
+    FSGM_TRY(arena_get(c, n * N, &rec));
+    FSGM_TRY(arena_get(c, n * N, &flags));
+    FSGM_TRY(launch_pyd_cost(c, n, cen1, cen2, W, H, d_preMv, mvW, mvH, g.agg, g.rx, g.ry, C, PITCH));
+    FSGM_TRY(launch_pyd_shift_flags(c, n, d_preMv, mvW, mvH, W, H, flags));
+    const int hd[2] = {0, 4};
+    uint8_t* Lh[2] = {H0, H1};
+    FSGM_TRY(launch_pyd_sweeps(c, n, C, d_I1, d_preMv, mvW, mvH, W, H, g.Sx, g.Sy, g.P1, g.P2, 0, hd, 2, Lh, PITCH));
+    FSGM_TRY(launch_pydv(c, n, cs, false, C, nullptr, nullptr, nullptr, S1, nullptr, flags, d_preMv, mvW, mvH, W, H, g.Sx, g.Sy, g.P1, g.P2));
+    FSGM_TRY(launch_pydv(c, n, cs, true, C, H0, H1, S1, nullptr, rec, flags, d_preMv, mvW, mvH, W, H, g.Sx, g.Sy, g.P1, g.P2));
+    return launch_pydv_finalize(c, n, rec, W, H, g.Sx, g.Sy, g.subpixel, d_bestD, d_minC, d_mvSub);
 }
 
 // census -> cost -> sweeps -> WTA for one level; the caller has reserved pyd_scratch_bytes() and holds the arena scope
@@ -62,9 +87,13 @@ int pyd_pipeline(fsgm_ctx* c, int n, const uint8_t* d_I1, const uint8_t* d_I2, i
     uint32_t *cen1, *cen2; uint8_t* C;
     FSGM_TRY(arena_get(c, n * N, &cen1));
     FSGM_TRY(arena_get(c, n * N, &cen2));
-    FSGM_TRY(arena_get(c, n * V, &C));
     FSGM_TRY(launch_census(c, n, d_I1, W, H, cen1));
     FSGM_TRY(launch_census(c, n, d_I2, W, H, cen2));
+    if (c->pyd_cluster >= 0 && (g.agg == 1 || g.agg == 2) && pydv_applicable(g.Sx, g.Sy, g.P1, g.P2, g.diag, g.passes, g.adaptive)) {
+        const int cs = pydv_pick_cluster(c, n, W, g.Sx, c->pyd_cluster);
+        if (cs) return pyd_pipeline_cluster(c, n, cs, cen1, cen2, d_I1, W, H, d_preMv, mvW, mvH, g, d_bestD, d_minC, d_mvSub);
+    }
+    FSGM_TRY(arena_get(c, n * V, &C));
     FSGM_TRY(launch_pyd_cost(c, n, cen1, cen2, W, H, d_preMv, mvW, mvH, g.agg, g.rx, g.ry, C));
     return pyd_aggregate(c, n, C, d_I1, d_preMv, mvW, mvH, W, H, g, nullptr, d_bestD, d_minC, d_mvSub);
 }

@@ -5,6 +5,7 @@
 #include <stddef.h>
 #include <string>
 #include <vector>
+#include <utility>
 #include "../../include/fsgm.h"
 
 namespace fsgm {
@@ -39,6 +40,8 @@ struct fsgm_ctx {
     unsigned attr_mask = 0;                 // which kernels already had their max-dynamic-smem attribute set on this device
     int clusters_key[4] = {0, 0, 0, 0}, clusters_max = 0;   // resident clusters for the last queried (cluster size, W, D, ndir)
     int best_key[3] = {0, 0, 0}, best_cs = 0, best_clusters = 0;   // cached vsweep_best_cluster() decision for (W, D, ndir)
+    int pyd_cluster = 0;                    // tuning knob (fsgm_tune key 5): cluster size of the pyd row-synchronous kernels, 0 auto, -1 off
+    std::vector<std::pair<int, int>> pv_occ;   // cached cudaOccupancyMaxActiveClusters answers of pydv_kernel
     int ng_occupancy = 0;                   // tuning knob (fsgm_tune key 3): resident pairs per SM of the ng kernel, 0 = by batch size
     int force_cluster = 0;                  // tuning/test knob: 0 auto, -1 generic path only, 1/2/4/8 forced cluster size
     std::string err;
@@ -163,11 +166,22 @@ int launch_vs_finalize(fsgm_ctx* c, int n, const uint16_t* rec, const uint32_t* 
 
 // ---- pyramidal 2-D-window variant (pyd.cu) ----------------------------------------------------------
 int launch_pyd_cost(fsgm_ctx* c, int n, const uint32_t* cen1, const uint32_t* cen2, int W, int H,
-                    const double* preMv, int mvW, int mvH, int agg, int rx, int ry, uint8_t* C);
+                    const double* preMv, int mvW, int mvH, int agg, int rx, int ry, uint8_t* C, int pitch = 0);
 int launch_pyd_sweeps(fsgm_ctx* c, int n, const uint8_t* C, const uint8_t* I1, const double* preMv, int mvW, int mvH,
-                      int W, int H, int Sx, int Sy, int P1, int P2, int adaptive, const int* dirs, int n_dirs, uint8_t* const* Lvols);
+                      int W, int H, int Sx, int Sy, int P1, int P2, int adaptive, const int* dirs, int n_dirs, uint8_t* const* Lvols,
+                      int pitch = 0);
 int launch_pyd_wta(fsgm_ctx* c, int n, uint8_t* const* Lvols, const int* weights, int n_dirs, int W, int H, int Sx, int Sy,
                    int subpixel, uint16_t* Sp16, uint32_t* bestD, uint32_t* minC, double* mvSub);
+
+// ---- row-synchronous cluster path of the pyramidal variant (pydv.cu) -----------------------------------------------
+bool pydv_applicable(int Sx, int Sy, int P1, int P2, int diag, int passes, int adaptive);
+int pydv_pick_cluster(fsgm_ctx* c, int n, int W, int Sx, int forced);
+int launch_pyd_shift_flags(fsgm_ctx* c, int n, const double* preMv, int mvW, int mvH, int W, int H, uint8_t* flags);
+int launch_pydv(fsgm_ctx* c, int n, int cs, bool final_, const uint8_t* C, const uint8_t* H0, const uint8_t* H1, const uint8_t* S1in,
+                uint8_t* S1out, uint4* rec, const uint8_t* flags, const double* preMv, int mvW, int mvH, int W, int H, int Sx, int Sy,
+                int P1, int P2);
+int launch_pydv_finalize(fsgm_ctx* c, int n, const uint4* rec, int W, int H, int Sx, int Sy, int subpixel,
+                         uint32_t* bestD, uint32_t* minC, double* mvSub);
 
 // ---- dense epipolar prologue / epilogue (geometry.cu): F, H, epipole -> Pd0, direction, offset, Rflow; labels -> flow ------
 int launch_geo_prologue(fsgm_ctx* c, int n, const double* F, const double* Hm, const double* epi, const int* direction, int W, int H,

@@ -91,6 +91,7 @@ struct PydSweepParams {
     const uint8_t* C; const uint8_t* I1; const double* preMv;
     uint8_t* L[8]; int dir[8]; int line_start[9]; int n_dirs;
     int W, H, Sx, Sy, mvW, mvH, P1, P2, adaptive;
+    int pitch;            // 0: compact volumes (D bytes per pixel); 16*Sx: C and L in the padded grid layout (vector mode only)
 };
 
 // FAST: parameters inside the no-wrap domain (P1,P2 >= 0, cmax+P1+P2 <= 255, 2*cmax+P2 <= 255).  There the P1 term may
@@ -156,8 +157,15 @@ pyd_sweep_kernel(const PydSweepParams prm)
     uint32_t M = 0;
     int cur = 0, px = 0, py = 0;
     uint8_t cnext[NJ];
+    // padded volumes (prm.pitch): a lane's 8 grid slots travel as one 64-bit word in both directions
+    const int PT = prm.pitch;
+    const uint8_t* __restrict__ Cq = prm.C + blockIdx.y * N * (size_t)PT + vc * 16 + 8 * vh;
+    uint8_t* __restrict__ Lq = prm.L[k] + blockIdx.y * N * (size_t)PT + vc * 16 + 8 * vh;
+    uint2 cqn = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
     // 32-bit pixel indices, one 64-bit row pointer per step (the per-label offsets lane + 32 j are immediates)
-    {
+    if (PT) {
+        if (vact) cqn = __ldg(reinterpret_cast<const uint2*>(Cq + (size_t)((uint32_t)y * (uint32_t)W + (uint32_t)x) * PT));
+    } else {
         const uint8_t* crow = Cb + (size_t)((uint32_t)y * (uint32_t)W + (uint32_t)x) * D + lane;
 #pragma unroll
         for (int j = 0; j < NJ; ++j) cnext[j] = lane + 32 * j < D ? __ldg(crow + 32 * j) : 0;
@@ -168,15 +176,27 @@ pyd_sweep_kernel(const PydSweepParams prm)
 
     for (int t = 0; t < len; ++t) {
         uint8_t c[NJ];
+        if (PT) {
+            // the padded cost row goes straight into the padded grid; the byte-wise paths read their labels back from there
+            if (vact) *reinterpret_cast<uint2*>(&Cp[wib][vc * 16 + 8 * vh]) = cqn;
+            __syncwarp();
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) c[j] = cnext[j];
+            for (int j = 0; j < NJ; ++j) c[j] = lane + 32 * j < D ? Cp[wib][pidx[j]] : 0;
+        } else {
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) c[j] = cnext[j];
+        }
         // next position + prefetch of its cost row and prior
         int nx = x, ny = y;
         if (dy == 0) nx += dx; else { ny += dy; nx += dx; nx = nx < 0 ? W - 1 : (nx >= W ? 0 : nx); }
         if (t + 1 < len) {
-            const uint8_t* crow = Cb + (size_t)((uint32_t)ny * (uint32_t)W + (uint32_t)nx) * D + lane;
+            if (PT) {
+                if (vact) cqn = __ldg(reinterpret_cast<const uint2*>(Cq + (size_t)((uint32_t)ny * (uint32_t)W + (uint32_t)nx) * PT));
+            } else {
+                const uint8_t* crow = Cb + (size_t)((uint32_t)ny * (uint32_t)W + (uint32_t)nx) * D + lane;
 #pragma unroll
-            for (int j = 0; j < NJ; ++j) cnext[j] = lane + 32 * j < D ? __ldg(crow + 32 * j) : 0;
+                for (int j = 0; j < NJ; ++j) cnext[j] = lane + 32 * j < D ? __ldg(crow + 32 * j) : 0;
+            }
             const uint32_t mi = (uint32_t)ny * (uint32_t)mvW + (uint32_t)nx;
             mxn = mvx[mi]; myn = mvy[mi];
         }
@@ -197,8 +217,10 @@ pyd_sweep_kernel(const PydSweepParams prm)
             const uint32_t far_ = (M + (uint32_t)P2) & 0xFFu;
             if (FAST && vec && ddx == 0.0 && ddy == 0.0) {
                 // predecessor label = the label itself ((int)(s + 0.0 + 0.5) == s); u16x2 registers, 8 slots per lane
+                if (!PT) {
 #pragma unroll
-                for (int j = 0; j < NJ; ++j) if (lane + 32 * j < D) Cp[wib][pidx[j]] = c[j];
+                    for (int j = 0; j < NJ; ++j) if (lane + 32 * j < D) Cp[wib][pidx[j]] = c[j];
+                }
                 uint32_t E[6];
                 if (vact) {
                     const uint8_t* g = Lpre + vc * 16 + 8 * vh;
@@ -341,8 +363,10 @@ pyd_sweep_kernel(const PydSweepParams prm)
             M = __reduce_min_sync(0xffffffffu, m);
             __syncwarp();
         }
-        // store this pixel's L row (coalesced bytes)
-        {
+        // store this pixel's L row (coalesced bytes; padded volumes: the lane's 8 grid slots as one word)
+        if (PT) {
+            if (vact) *reinterpret_cast<uint2*>(Lq + (size_t)pix * PT) = *reinterpret_cast<const uint2*>(Lnew + vc * 16 + 8 * vh);
+        } else {
             uint8_t* lrow = Lb + (size_t)pix * D + lane;
 #pragma unroll
             for (int j = 0; j < NJ; ++j) if (lane + 32 * j < D) lrow[32 * j] = Lnew[pidx[j]];
@@ -366,14 +390,18 @@ constexpr int PYC_WARPS = 4;
 template <int AGG>
 __global__ void __launch_bounds__(PYC_WARPS * 32)
 pyd_cost_px_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restrict__ cen2, int W, int H,
-                   const double* __restrict__ preMv, int mvW, int mvH, int rx, int ry, uint8_t* __restrict__ C)
+                   const double* __restrict__ preMv, int mvW, int mvH, int rx, int ry, int pitch, uint8_t* __restrict__ C)
 {
+    // pitch == 0: compact label rows (D bytes per pixel, the reference's layout).  pitch == 16*Sx: the PADDED GRID of the
+    // row-synchronous aggregation kernels (pydv.cu): column ox at byte 16*ox, two leading pad bytes, Sy labels, trailing pads,
+    // every pad byte 255.
     constexpr int T = 2 * AGG + 1, WPX = T * T;
     extern __shared__ __align__(16) unsigned char pyc_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int Sx = 2 * rx + 1, Sy = 2 * ry + 1, D = Sx * Sy, SX2 = Sx + T - 1, SY2 = Sy + T - 1;
     // per warp: fx[SX2][32], fy[SY2][32] (int), V[T][T][32] (u32: a ring of T sample rows), tile[32][D] (u8, padded to 16 bytes)
-    const size_t per_warp = (size_t)(SX2 + SY2) * 32 * 4 + (size_t)T * T * 32 * 4 + (((size_t)32 * D + 15) & ~(size_t)15);
+    const int PT = pitch ? pitch : D;                     // bytes per pixel in the output tile
+    const size_t per_warp = (size_t)(SX2 + SY2) * 32 * 4 + (size_t)T * T * 32 * 4 + (((size_t)32 * PT + 15) & ~(size_t)15);
     unsigned char* base = pyc_smem + wib * per_warp;
     int* fx = reinterpret_cast<int*>(base);
     int* fy = fx + SX2 * 32;
@@ -392,6 +420,9 @@ pyd_cost_px_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restrict
     const uint32_t* c1 = cen1 + pair * N;
     const uint32_t* c2 = cen2 + pair * N;
 
+    if (pitch) {                                          // pad bytes of the grid
+        for (int i = lane; i < 32 * PT / 4; i += 32) reinterpret_cast<uint32_t*>(tile)[i] = 0xFFFFFFFFu;
+    }
     // sample coordinates: x2 depends only on s = offx + ax (tabulated per lane), -1 = outside the image; same for y
     for (int sI = 0; sI < SX2; ++sI) {
         const int v = x86_d2i(__dadd_rn(__dadd_rn((double)(sI - rx - AGG + x), mvx), 0.5));
@@ -460,41 +491,47 @@ pyd_cost_px_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restrict
             }
             r0 = r0 + 1 == T ? 0 : r0 + 1;
             // (u8)(1.0*s/wp + 0.5) == (2s + wp) / (2wp) in integers (see pyd_cost_kernel)
-            tile[lane * D + ox * Sy + oy] = (uint8_t)((2 * sum + WPX) / (2 * WPX));
+            tile[lane * PT + (pitch ? ox * 16 + 2 + oy : ox * Sy + oy)] = (uint8_t)((2 * sum + WPX) / (2 * WPX));
         }
         __syncwarp();
     }
     // the warp's pixels are consecutive and so are their label rows: one contiguous run of nlive * D bytes
-    uint8_t* out = C + (pair * N + (size_t)y * W + x0) * D;
-    const int nbytes = nlive * D;
-    for (int i = lane; i < nbytes; i += 32) out[i] = tile[i];
+    uint8_t* out = C + (pair * N + (size_t)y * W + x0) * PT;
+    const int nbytes = nlive * PT;
+    if (pitch) {                                          // 16-byte aligned on both sides
+        for (int i = lane; i < nbytes / 16; i += 32) reinterpret_cast<uint4*>(out)[i] = reinterpret_cast<const uint4*>(tile)[i];
+    } else {
+        for (int i = lane; i < nbytes; i += 32) out[i] = tile[i];
+    }
 }
 
-static size_t pyd_cost_px_smem(int agg, int rx, int ry)
+static size_t pyd_cost_px_smem(int agg, int rx, int ry, int pitch)
 {
     const int T = 2 * agg + 1, Sx = 2 * rx + 1, Sy = 2 * ry + 1, SX2 = Sx + T - 1, SY2 = Sy + T - 1;
-    const size_t per_warp = (size_t)(SX2 + SY2) * 32 * 4 + (size_t)T * T * 32 * 4 + (((size_t)32 * Sx * Sy + 15) & ~(size_t)15);
+    const size_t PT = pitch ? pitch : Sx * Sy;
+    const size_t per_warp = (size_t)(SX2 + SY2) * 32 * 4 + (size_t)T * T * 32 * 4 + (((size_t)32 * PT + 15) & ~(size_t)15);
     return per_warp * PYC_WARPS;
 }
 
 int launch_pyd_cost(fsgm_ctx* c, int n, const uint32_t* cen1, const uint32_t* cen2, int W, int H,
-                    const double* preMv, int mvW, int mvH, int agg, int rx, int ry, uint8_t* C)
+                    const double* preMv, int mvW, int mvH, int agg, int rx, int ry, uint8_t* C, int pitch)
 {
     StageScope ss(c, ST_PYD_COST);
     if (2 * (rx + agg) + 1 > PYD_MAXS + 32 || 2 * (ry + agg) + 1 > PYD_MAXS + 32)
         return fail(c, FSGM_ERR_DOMAIN, "search + aggregation window too large");
     const size_t N = (size_t)W * H;
     // lane = pixel kernel for the aggregation windows in use (5x5, 3x3) when its per-warp staging fits; else one warp per pixel
-    const size_t smem = (agg == 1 || agg == 2) ? pyd_cost_px_smem(agg, rx, ry) : 0;
+    const size_t smem = (agg == 1 || agg == 2) ? pyd_cost_px_smem(agg, rx, ry, pitch) : 0;
+    if (pitch && !(smem && smem <= 100 * 1024)) return fail(c, FSGM_ERR_DOMAIN, "padded cost volume needs the lane = pixel cost kernel");
     if (smem && smem <= 100 * 1024) {
         const int jobs = ((W + 31) / 32) * H;
         dim3 grid((unsigned)((jobs + PYC_WARPS - 1) / PYC_WARPS), n);
         if (agg == 2) {
             FSGM_CUDA(c, cudaFuncSetAttribute(pyd_cost_px_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            pyd_cost_px_kernel<2><<<grid, PYC_WARPS * 32, smem, c->stream>>>(cen1, cen2, W, H, preMv, mvW, mvH, rx, ry, C);
+            pyd_cost_px_kernel<2><<<grid, PYC_WARPS * 32, smem, c->stream>>>(cen1, cen2, W, H, preMv, mvW, mvH, rx, ry, pitch, C);
         } else {
             FSGM_CUDA(c, cudaFuncSetAttribute(pyd_cost_px_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            pyd_cost_px_kernel<1><<<grid, PYC_WARPS * 32, smem, c->stream>>>(cen1, cen2, W, H, preMv, mvW, mvH, rx, ry, C);
+            pyd_cost_px_kernel<1><<<grid, PYC_WARPS * 32, smem, c->stream>>>(cen1, cen2, W, H, preMv, mvW, mvH, rx, ry, pitch, C);
         }
         FSGM_LAUNCHED(c);
         return FSGM_OK;
@@ -506,14 +543,15 @@ int launch_pyd_cost(fsgm_ctx* c, int n, const uint32_t* cen1, const uint32_t* ce
 }
 
 int launch_pyd_sweeps(fsgm_ctx* c, int n, const uint8_t* C, const uint8_t* I1, const double* preMv, int mvW, int mvH,
-                      int W, int H, int Sx, int Sy, int P1, int P2, int adaptive, const int* dirs, int n_dirs, uint8_t* const* Lvols)
+                      int W, int H, int Sx, int Sy, int P1, int P2, int adaptive, const int* dirs, int n_dirs, uint8_t* const* Lvols,
+                      int pitch)
 {
     StageScope ss(c, ST_PYD_SWEEP);
     const int D = Sx * Sy;
     if (D > PYD_MAXD || Sx > PYD_MAXS || Sy > PYD_MAXS) return fail(c, FSGM_ERR_DOMAIN, "search window too large (<= 1024 labels)");
     PydSweepParams p{};
     p.C = C; p.I1 = I1; p.preMv = preMv; p.n_dirs = n_dirs; p.W = W; p.H = H; p.Sx = Sx; p.Sy = Sy; p.mvW = mvW; p.mvH = mvH;
-    p.P1 = P1; p.P2 = P2; p.adaptive = adaptive;
+    p.P1 = P1; p.P2 = P2; p.adaptive = adaptive; p.pitch = pitch;
     p.line_start[0] = 0;
     for (int k = 0; k < n_dirs; ++k) {
         p.dir[k] = dirs[k]; p.L[k] = Lvols[k];
@@ -522,6 +560,7 @@ int launch_pyd_sweeps(fsgm_ctx* c, int n, const uint8_t* C, const uint8_t* I1, c
     dim3 grid((p.line_start[n_dirs] + PYD_WARPS - 1) / PYD_WARPS, n);
     // cost values of this variant are <= 24 (mean of 5x5 Hamming distances <= 23 and the constant 5)
     const bool fast = P1 >= 0 && P2 >= 0 && 25 + P1 + P2 <= 255 && 50 + P2 <= 255;
+    if (pitch && !(fast && Sy <= 12 && Sx <= 16 && pitch == 16 * Sx)) return fail(c, FSGM_ERR_DOMAIN, "padded volumes need the vector mode of the pyd sweep");
 #define PYD_GO(NJV)                                                                                   \
     do { if (fast) pyd_sweep_kernel<NJV, true><<<grid, PYD_WARPS * 32, 0, c->stream>>>(p);             \
          else pyd_sweep_kernel<NJV, false><<<grid, PYD_WARPS * 32, 0, c->stream>>>(p); } while (0)

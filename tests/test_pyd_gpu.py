@@ -125,3 +125,70 @@ def test_pyd_half_kitti_size_vs_oracle(ctx, oracle):
     assert np.array_equal(minC, want["minC"])
     assert np.array_equal(bestD, want["bestD"])
     assert np.array_equal(mvSub, want["mvSub"])
+
+
+def _prior(kind, rng, H, W, pad=(3, 5)):
+    mv = np.zeros((2, H + pad[0], W + pad[1]))
+    if kind == "blocks":          # what the pyramid driver produces: 2 x integer flow, constant on 2x2 blocks (mostly zero shifts)
+        coarse = rng.integers(-2, 3, (2, (H + pad[0] + 1) // 2, (W + pad[1] + 1) // 2))
+        mv[:] = 2.0 * np.repeat(np.repeat(coarse, 2, axis=1), 2, axis=2)[:, :mv.shape[1], :mv.shape[2]]
+    elif kind == "int":
+        mv[:] = rng.integers(-4, 5, mv.shape)
+    elif kind == "frac":
+        mv[:] = rng.normal(0, 2.0, mv.shape)
+    elif kind == "far":           # shifts far beyond the window in both signs, exact .5 ties, NaN / inf / huge
+        mv[:] = rng.integers(-40, 41, mv.shape) * 0.5
+        mv[0, 2, 3], mv[1, 4, 5], mv[0, 6, 7], mv[1, 1, 1], mv[0, 5, 1] = np.nan, 1e300, -1e300, 3e9, np.inf
+    return mv
+
+
+# (W, H, rx, ry, agg, sub, P1, P2, prior kind, forced cluster size): the row-synchronous cluster kernels of pydv.cu at every
+# cluster shape they can take (1 = one CTA per pair, non-portable sizes above 8), window shapes up to 11 x 11, strips of 2 columns
+CLUSTER_CASES = [
+    (60, 40, 5, 5, 2, 1, 6, 32, "zero", 1), (60, 40, 5, 5, 2, 1, 6, 32, "blocks", 2), (61, 33, 5, 5, 2, 1, 6, 32, "int", 3),
+    (75, 28, 4, 4, 2, 1, 6, 32, "frac", 4), (90, 24, 5, 4, 1, 0, 6, 32, "blocks", 9), (64, 20, 3, 5, 2, 1, 6, 32, "far", 16),
+    (33, 27, 2, 1, 2, 1, 10, 60, "frac", 8), (40, 30, 0, 5, 1, 1, 6, 32, "int", 5), (40, 30, 5, 0, 2, 1, 0, 0, "int", 2),
+    (21, 50, 1, 1, 2, 1, 6, 32, "far", 7), (130, 21, 5, 5, 2, 1, 6, 32, "blocks", 0), (47, 47, 4, 5, 2, 1, 6, 32, "far", 0),
+]
+
+
+@pytest.mark.parametrize("W,H,rx,ry,agg,sub,P1,P2,prior,cs", CLUSTER_CASES)
+def test_pyd_cluster_path_vs_oracle(ctx, oracle, W, H, rx, ry, agg, sub, P1, P2, prior, cs):
+    """The cluster path (padded-grid volumes, three directions per pass in shared memory, WTA fused) against the reference build,
+    and against the one-warp-per-scanline kernels it replaces (fsgm_tune key 5 = -1)."""
+    fp = synth.flow_pair(W, H, seed=W + rx, umax=max(1, rx - 1), vmax=max(1, ry - 1))
+    mv = _prior(prior, np.random.default_rng(W * 3 + H + cs), H, W)
+    want = _oracle_pyd(oracle, fp["I1"], fp["I2"], mv, rx, ry, agg, sub, P1, P2, 1, 2, 0)
+    try:
+        ctx.tune(5, cs)
+        ctx.profile(True); ctx.profile_reset()
+        bestD, minC, mvSub = ctx.calc_pyd_cost_sgm(fp["I1"], fp["I2"], mv, rx, ry, agg, sub, P1, P2, 1, 2, 0)
+        st = ctx.profile_read(); ctx.profile(False)
+        assert st["pyd_sweep"][1] == 4, st                  # shift flags, horizontal pair, down pass, up pass: the cluster path ran
+        assert "pyd_wta" in st and st["pyd_wta"][1] == 1
+        ctx.tune(5, -1)
+        b2, m2, s2 = ctx.calc_pyd_cost_sgm(fp["I1"], fp["I2"], mv, rx, ry, agg, sub, P1, P2, 1, 2, 0)
+    finally:
+        ctx.profile(False)
+        ctx.tune(5, 0)
+    assert np.array_equal(minC, want["minC"])
+    assert np.array_equal(bestD, want["bestD"])
+    assert np.array_equal(mvSub, want["mvSub"], equal_nan=True)
+    assert np.array_equal(minC, m2) and np.array_equal(bestD, b2) and np.array_equal(mvSub, s2, equal_nan=True)
+
+
+def test_pyd_cluster_batch_pairs_are_independent(ctx, oracle):
+    import torch
+    W, H, n = 70, 26, 5
+    fps = [synth.flow_pair(W, H, seed=30 + i, umax=3, vmax=2) for i in range(n)]
+    rng = np.random.default_rng(4)
+    mvs = [_prior(k, rng, H, W, pad=(0, 0)) for k in ("zero", "blocks", "int", "frac", "far")]
+    I1 = _t(np.stack([f["I1"] for f in fps])); I2 = _t(np.stack([f["I2"] for f in fps])); mv = _t(np.stack(mvs))
+    bD = torch.empty((n, H, W), dtype=torch.int32, device="cuda"); mC = torch.empty_like(bD)
+    sub = torch.empty((n, 2, H, W), dtype=torch.float64, device="cuda")
+    ctx.calc_pyd_cost_sgm_dev(I1, I2, mv, 5, 5, 2, 1, 6, 32, 1, 2, 0, bD, mC, sub)
+    for i in range(n):
+        want = _oracle_pyd(oracle, fps[i]["I1"], fps[i]["I2"], mvs[i], 5, 5, 2, 1, 6, 32, 1, 2, 0)
+        assert np.array_equal(mC.cpu().numpy()[i].view(np.uint32), want["minC"]), i
+        assert np.array_equal(bD.cpu().numpy()[i].view(np.uint32), want["bestD"]), i
+        assert np.array_equal(sub.cpu().numpy()[i], want["mvSub"], equal_nan=True), i
