@@ -147,7 +147,7 @@ def _prior(kind, rng, H, W, pad=(3, 5)):
 CLUSTER_CASES = [
     (60, 40, 5, 5, 2, 1, 6, 32, "zero", 1), (60, 40, 5, 5, 2, 1, 6, 32, "blocks", 2), (61, 33, 5, 5, 2, 1, 6, 32, "int", 3),
     (75, 28, 4, 4, 2, 1, 6, 32, "frac", 4), (90, 24, 5, 4, 1, 0, 6, 32, "blocks", 9), (64, 20, 3, 5, 2, 1, 6, 32, "far", 16),
-    (33, 27, 2, 1, 2, 1, 10, 60, "frac", 8), (40, 30, 0, 5, 1, 1, 6, 32, "int", 5), (40, 30, 5, 0, 2, 1, 0, 0, "int", 2),
+    (48, 27, 2, 1, 2, 1, 10, 60, "frac", 8), (40, 30, 0, 5, 1, 1, 6, 32, "int", 5), (40, 30, 5, 0, 2, 1, 0, 0, "int", 2),
     (21, 50, 1, 1, 2, 1, 6, 32, "far", 7), (130, 21, 5, 5, 2, 1, 6, 32, "blocks", 0), (47, 47, 4, 5, 2, 1, 6, 32, "far", 0),
 ]
 
