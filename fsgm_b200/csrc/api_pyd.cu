@@ -51,7 +51,25 @@ size_t pyd_scratch_bytes(int n, int W, int H, int D)
 {
     const size_t N = (size_t)W * H;
     // generic path: C + 8 L volumes of D bytes per pixel; cluster path: 4 padded volumes (<= 176 B per pixel) + records + flags
-    return 2 * align256(n * N * 4) + std::max(9 * align256(n * N * D), 4 * align256(n * N * 176) + align256(n * N * 16) + align256(n * N));
+    return 2 * align256(n * N * 4) + std::max(std::max(9 * align256(n * N * D), 4 * align256(n * N * 176) + align256(n * N * 16) + align256(n * N)),
+                                              9 * align256(n * N * 176) + 8 * align256(n * N * 4));
+}
+
+// The lane = path kernels (pydl.cu): cost volume and per-direction volumes as [y][label column][x][16-byte frame], shift
+// descriptors per pixel and direction, one sweep launch for all directions, winner-take-all with lane = pixel.
+int pyd_pipeline_lane(fsgm_ctx* c, int n, const uint32_t* cen1, const uint32_t* cen2, const uint8_t* d_I1, int W, int H,
+                      const double* d_preMv, int mvW, int mvH, const PydCfg& g, const int* dirs, int nd,
+                      uint32_t* d_bestD, uint32_t* d_minC, double* d_mvSub)
+{
+    const size_t N = (size_t)W * H;
+    const int PITCH = 16 * g.Sx;
+    uint8_t* C; uint8_t* L[8] = {}; uint32_t* desc[8] = {};
+    FSGM_TRY(arena_get(c, n * N * PITCH, &C));
+    for (int k = 0; k < nd; ++k) { FSGM_TRY(arena_get(c, n * N * PITCH, &L[k])); FSGM_TRY(arena_get(c, n * N, &desc[k])); }
+    FSGM_TRY(launch_pyd_cost(c, n, cen1, cen2, W, H, d_preMv, mvW, mvH, g.agg, g.rx, g.ry, C, PITCH, 1));
+    FSGM_TRY(launch_pydl_desc(c, n, d_preMv, mvW, mvH, W, H, g.Sx, g.Sy, dirs, nd, desc, c->pyd_cluster == -2));
+    FSGM_TRY(launch_pydl_sweeps(c, n, C, d_I1, d_preMv, mvW, mvH, W, H, g.Sx, g.Sy, g.P1, g.P2, g.adaptive, dirs, nd, desc, L));
+    return launch_pydl_wta(c, n, L, nd, W, H, g.Sx, g.Sy, g.subpixel, d_bestD, d_minC, d_mvSub);
 }
 
 // The row-synchronous cluster path (pydv.cu): padded-grid cost volume, the two horizontal directions through the scanline kernel
@@ -89,7 +107,13 @@ int pyd_pipeline(fsgm_ctx* c, int n, const uint8_t* d_I1, const uint8_t* d_I2, i
     FSGM_TRY(arena_get(c, n * N, &cen2));
     FSGM_TRY(launch_census(c, n, d_I1, W, H, cen1));
     FSGM_TRY(launch_census(c, n, d_I2, W, H, cen2));
-    if (c->pyd_cluster >= 0 && (g.agg == 1 || g.agg == 2) && pydv_applicable(g.Sx, g.Sy, g.P1, g.P2, g.diag, g.passes, g.adaptive)) {
+    if ((c->pyd_cluster == 0 || c->pyd_cluster == -2) && (g.agg == 1 || g.agg == 2)) {
+        int dirs[8], weights[8];
+        const int nd = pyd_dirs(g, dirs, weights);
+        if (pydl_applicable(g.Sx, g.Sy, g.P1, g.P2, nd, weights))
+            return pyd_pipeline_lane(c, n, cen1, cen2, d_I1, W, H, d_preMv, mvW, mvH, g, dirs, nd, d_bestD, d_minC, d_mvSub);
+    }
+    if (c->pyd_cluster > 0 && (g.agg == 1 || g.agg == 2) && pydv_applicable(g.Sx, g.Sy, g.P1, g.P2, g.diag, g.passes, g.adaptive)) {
         const int cs = pydv_pick_cluster(c, n, W, g.Sx, c->pyd_cluster);
         if (cs) return pyd_pipeline_cluster(c, n, cs, cen1, cen2, d_I1, W, H, d_preMv, mvW, mvH, g, d_bestD, d_minC, d_mvSub);
     }

@@ -166,7 +166,7 @@ int launch_vs_finalize(fsgm_ctx* c, int n, const uint16_t* rec, const uint32_t* 
 
 // ---- pyramidal 2-D-window variant (pyd.cu) ----------------------------------------------------------
 int launch_pyd_cost(fsgm_ctx* c, int n, const uint32_t* cen1, const uint32_t* cen2, int W, int H,
-                    const double* preMv, int mvW, int mvH, int agg, int rx, int ry, uint8_t* C, int pitch = 0);
+                    const double* preMv, int mvW, int mvH, int agg, int rx, int ry, uint8_t* C, int pitch = 0, int soa = 0);
 int launch_pyd_sweeps(fsgm_ctx* c, int n, const uint8_t* C, const uint8_t* I1, const double* preMv, int mvW, int mvH,
                       int W, int H, int Sx, int Sy, int P1, int P2, int adaptive, const int* dirs, int n_dirs, uint8_t* const* Lvols,
                       int pitch = 0);
@@ -182,6 +182,15 @@ int launch_pydv(fsgm_ctx* c, int n, int cs, bool final_, const uint8_t* C, const
                 int P1, int P2);
 int launch_pydv_finalize(fsgm_ctx* c, int n, const uint4* rec, int W, int H, int Sx, int Sy, int subpixel,
                          uint32_t* bestD, uint32_t* minC, double* mvSub);
+
+// ---- lane = path aggregation of the pyramidal variant (pydl.cu): volumes as [y][label column][x][16-byte frame] --------------
+bool pydl_applicable(int Sx, int Sy, int P1, int P2, int n_dirs, const int* weights);
+int launch_pydl_desc(fsgm_ctx* c, int n, const double* preMv, int mvW, int mvH, int W, int H, int Sx, int Sy, const int* dirs, int n_dirs,
+                     uint32_t* const* out, int force_generic);
+int launch_pydl_sweeps(fsgm_ctx* c, int n, const uint8_t* C, const uint8_t* I1, const double* preMv, int mvW, int mvH, int W, int H,
+                       int Sx, int Sy, int P1, int P2, int adaptive, const int* dirs, int n_dirs, uint32_t* const* desc, uint8_t* const* Lvols);
+int launch_pydl_wta(fsgm_ctx* c, int n, uint8_t* const* Lvols, int n_dirs, int W, int H, int Sx, int Sy, int subpixel,
+                    uint32_t* bestD, uint32_t* minC, double* mvSub);
 
 // ---- dense epipolar prologue / epilogue (geometry.cu): F, H, epipole -> Pd0, direction, offset, Rflow; labels -> flow ------
 int launch_geo_prologue(fsgm_ctx* c, int n, const double* F, const double* Hm, const double* epi, const int* direction, int W, int H,

@@ -390,11 +390,11 @@ constexpr int PYC_WARPS = 4;
 template <int AGG>
 __global__ void __launch_bounds__(PYC_WARPS * 32)
 pyd_cost_px_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restrict__ cen2, int W, int H,
-                   const double* __restrict__ preMv, int mvW, int mvH, int rx, int ry, int pitch, uint8_t* __restrict__ C)
+                   const double* __restrict__ preMv, int mvW, int mvH, int rx, int ry, int pitch, int soa, uint8_t* __restrict__ C)
 {
     // pitch == 0: compact label rows (D bytes per pixel, the reference's layout).  pitch == 16*Sx: the PADDED GRID of the
     // row-synchronous aggregation kernels (pydv.cu): column ox at byte 16*ox, two leading pad bytes, Sy labels, trailing pads,
-    // every pad byte 255.
+    // every pad byte 255.  soa: the same 16-byte frames as [y][label column][x] (pydl.cu: lane = path aggregation).
     constexpr int T = 2 * AGG + 1, WPX = T * T;
     extern __shared__ __align__(16) unsigned char pyc_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -498,7 +498,12 @@ pyd_cost_px_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restrict
     // the warp's pixels are consecutive and so are their label rows: one contiguous run of nlive * D bytes
     uint8_t* out = C + (pair * N + (size_t)y * W + x0) * PT;
     const int nbytes = nlive * PT;
-    if (pitch) {                                          // 16-byte aligned on both sides
+    if (soa) {                                            // one 512-byte run per label column
+        uint8_t* o2 = C + (size_t)pair * N * PT + (((size_t)y * Sx) * W + x0 + lane) * 16;
+        if (lane < nlive)
+            for (int ox = 0; ox < Sx; ++ox)
+                *reinterpret_cast<uint4*>(o2 + (size_t)ox * W * 16) = *reinterpret_cast<const uint4*>(tile + lane * PT + ox * 16);
+    } else if (pitch) {                                   // 16-byte aligned on both sides
         for (int i = lane; i < nbytes / 16; i += 32) reinterpret_cast<uint4*>(out)[i] = reinterpret_cast<const uint4*>(tile)[i];
     } else {
         for (int i = lane; i < nbytes; i += 32) out[i] = tile[i];
@@ -514,7 +519,7 @@ static size_t pyd_cost_px_smem(int agg, int rx, int ry, int pitch)
 }
 
 int launch_pyd_cost(fsgm_ctx* c, int n, const uint32_t* cen1, const uint32_t* cen2, int W, int H,
-                    const double* preMv, int mvW, int mvH, int agg, int rx, int ry, uint8_t* C, int pitch)
+                    const double* preMv, int mvW, int mvH, int agg, int rx, int ry, uint8_t* C, int pitch, int soa)
 {
     StageScope ss(c, ST_PYD_COST);
     if (2 * (rx + agg) + 1 > PYD_MAXS + 32 || 2 * (ry + agg) + 1 > PYD_MAXS + 32)
@@ -528,10 +533,10 @@ int launch_pyd_cost(fsgm_ctx* c, int n, const uint32_t* cen1, const uint32_t* ce
         dim3 grid((unsigned)((jobs + PYC_WARPS - 1) / PYC_WARPS), n);
         if (agg == 2) {
             FSGM_CUDA(c, cudaFuncSetAttribute(pyd_cost_px_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            pyd_cost_px_kernel<2><<<grid, PYC_WARPS * 32, smem, c->stream>>>(cen1, cen2, W, H, preMv, mvW, mvH, rx, ry, pitch, C);
+            pyd_cost_px_kernel<2><<<grid, PYC_WARPS * 32, smem, c->stream>>>(cen1, cen2, W, H, preMv, mvW, mvH, rx, ry, pitch, soa, C);
         } else {
             FSGM_CUDA(c, cudaFuncSetAttribute(pyd_cost_px_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            pyd_cost_px_kernel<1><<<grid, PYC_WARPS * 32, smem, c->stream>>>(cen1, cen2, W, H, preMv, mvW, mvH, rx, ry, pitch, C);
+            pyd_cost_px_kernel<1><<<grid, PYC_WARPS * 32, smem, c->stream>>>(cen1, cen2, W, H, preMv, mvW, mvH, rx, ry, pitch, soa, C);
         }
         FSGM_LAUNCHED(c);
         return FSGM_OK;

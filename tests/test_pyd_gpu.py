@@ -164,7 +164,10 @@ def test_pyd_cluster_path_vs_oracle(ctx, oracle, W, H, rx, ry, agg, sub, P1, P2,
         ctx.profile(True); ctx.profile_reset()
         bestD, minC, mvSub = ctx.calc_pyd_cost_sgm(fp["I1"], fp["I2"], mv, rx, ry, agg, sub, P1, P2, 1, 2, 0)
         st = ctx.profile_read(); ctx.profile(False)
-        assert st["pyd_sweep"][1] == 4, st                  # shift flags, horizontal pair, down pass, up pass: the cluster path ran
+        if cs > 0:
+            assert st["pyd_sweep"][1] == 4, st              # shift flags, horizontal pair, down pass, up pass: the cluster path ran
+        else:
+            assert st["pyd_sweep"][1] == 2, st              # shift descriptors + one launch for all directions: lane = path kernels
         assert "pyd_wta" in st and st["pyd_wta"][1] == 1
         ctx.tune(5, -1)
         b2, m2, s2 = ctx.calc_pyd_cost_sgm(fp["I1"], fp["I2"], mv, rx, ry, agg, sub, P1, P2, 1, 2, 0)
@@ -175,6 +178,58 @@ def test_pyd_cluster_path_vs_oracle(ctx, oracle, W, H, rx, ry, agg, sub, P1, P2,
     assert np.array_equal(bestD, want["bestD"])
     assert np.array_equal(mvSub, want["mvSub"], equal_nan=True)
     assert np.array_equal(minC, m2) and np.array_equal(bestD, b2) and np.array_equal(mvSub, s2, equal_nan=True)
+
+
+# (W, H, rx, ry, agg, sub, P1, P2, diag, passes, adaptive, prior kind): the lane = path kernels of pydl.cu (one thread per scanline
+# and direction, volumes as [y][label column][x][16-byte frame]) on every window width they are instantiated for, with
+# truncation-toward-zero duplicates in both axes (negative integer shifts), shifts beyond the window, NaN / inf / huge priors,
+# exact .5 ties, adaptive P2, no diagonals, a single pass, images narrower than a warp and wider than two
+LANE_CASES = [
+    (60, 40, 5, 5, 2, 1, 6, 32, 1, 2, 0, "zero"), (70, 37, 5, 5, 2, 1, 6, 32, 1, 2, 0, "blocks"), (61, 33, 5, 5, 2, 1, 6, 32, 1, 2, 0, "int"),
+    (75, 28, 4, 4, 2, 1, 6, 32, 1, 2, 0, "frac"), (90, 24, 5, 4, 1, 0, 6, 32, 1, 2, 1, "blocks"), (64, 20, 3, 5, 2, 1, 6, 32, 1, 2, 0, "far"),
+    (48, 27, 2, 1, 2, 1, 10, 60, 0, 2, 0, "frac"), (40, 30, 0, 5, 1, 1, 6, 32, 1, 1, 0, "int"), (40, 30, 5, 0, 2, 1, 0, 0, 1, 2, 1, "int"),
+    (21, 50, 1, 1, 2, 1, 6, 32, 1, 2, 0, "far"), (130, 21, 5, 5, 2, 1, 6, 32, 1, 2, 1, "int"), (47, 47, 4, 5, 2, 1, 100, 105, 1, 2, 0, "far"),
+    (5, 70, 5, 5, 2, 1, 6, 32, 1, 2, 0, "int"), (33, 3, 3, 3, 2, 1, 6, 32, 1, 2, 0, "frac"),
+]
+
+
+@pytest.mark.parametrize("forced", [0, -2])
+@pytest.mark.parametrize("W,H,rx,ry,agg,sub,P1,P2,diag,passes,adp,prior", LANE_CASES)
+def test_pyd_lane_path_vs_oracle(ctx, oracle, W, H, rx, ry, agg, sub, P1, P2, diag, passes, adp, prior, forced):
+    """forced = -2 sends every shifted step through the label-by-label form that the kernel keeps for prior differences whose
+    (int)(s + dd + 0.5) map is not `shift, plus one below zero` (fsgm_tune key 5)."""
+    fp = synth.flow_pair(W, H, seed=W + rx, umax=max(1, rx - 1), vmax=max(1, ry - 1))
+    mv = _prior(prior, np.random.default_rng(W * 3 + H), H, W)
+    want = _oracle_pyd(oracle, fp["I1"], fp["I2"], mv, rx, ry, agg, sub, P1, P2, diag, passes, adp)
+    try:
+        ctx.tune(5, forced)
+        ctx.profile(True); ctx.profile_reset()
+        bestD, minC, mvSub = ctx.calc_pyd_cost_sgm(fp["I1"], fp["I2"], mv, rx, ry, agg, sub, P1, P2, diag, passes, adp)
+        st = ctx.profile_read()
+    finally:
+        ctx.profile(False)
+        ctx.tune(5, 0)
+    assert st["pyd_sweep"][1] == 2, st
+    assert np.array_equal(minC, want["minC"])
+    assert np.array_equal(bestD, want["bestD"])
+    assert np.array_equal(mvSub, want["mvSub"], equal_nan=True)
+
+
+def test_pyd_lane_path_rounding_anomaly(ctx, oracle):
+    """Prior differences just below .5: (double)s + dd rounds up for some label rows only, so (int)(s + dd + 0.5) is not a
+    shift — the descriptor pre-pass must flag these steps (the result then comes from the label-by-label form)."""
+    W, H = 40, 24
+    fp = synth.flow_pair(W, H, seed=5, umax=2, vmax=2)
+    mv = np.zeros((2, H, W))
+    eps = 2.0 ** -53
+    mv[0, :, 1::2] = 0.5 - eps
+    mv[1, 1::2, :] = -(0.5 - eps)
+    mv[0, 5:9, 7:20] += 1.0
+    want = _oracle_pyd(oracle, fp["I1"], fp["I2"], mv, 5, 5, 2, 1, 6, 32, 1, 2, 0)
+    bestD, minC, mvSub = ctx.calc_pyd_cost_sgm(fp["I1"], fp["I2"], mv, 5, 5, 2, 1, 6, 32, 1, 2, 0)
+    assert np.array_equal(minC, want["minC"])
+    assert np.array_equal(bestD, want["bestD"])
+    assert np.array_equal(mvSub, want["mvSub"], equal_nan=True)
 
 
 def test_pyd_cluster_batch_pairs_are_independent(ctx, oracle):

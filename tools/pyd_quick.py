@@ -37,7 +37,7 @@ for r in (5, 4):
         e1.record(); torch.cuda.synchronize()
         st = ctx.profile_read(); ctx.profile(False)
         ms = e0.elapsed_time(e1) / 3
-        print(f"r={r} mode={'cluster' if mode == 0 else 'scanline'} n={n}: {ms:.2f} ms per batch -> {n / ms * 1e3:.0f} pairs/s; stages ms/batch:",
+        print(f"r={r} mode={'lane' if mode == 0 else 'scanline'} n={n}: {ms:.2f} ms per batch -> {n / ms * 1e3:.0f} pairs/s; stages ms/batch:",
               {k: round(v[0] / 3, 2) for k, v in st.items()}, flush=True)
-    print("  cluster == scanline:", bool(torch.equal(mv, mv2) and torch.equal(mC, mC2)), flush=True)
+    print("  lane == scanline:", bool(torch.equal(mv, mv2) and torch.equal(mC, mC2)), flush=True)
 ctx.tune(5, 0); ctx.close()
