@@ -52,7 +52,7 @@ size_t pyd_scratch_bytes(int n, int W, int H, int D)
     const size_t N = (size_t)W * H;
     // generic path: C + 8 L volumes of D bytes per pixel; cluster path: 4 padded volumes (<= 176 B per pixel) + records + flags
     return 2 * align256(n * N * 4) + std::max(std::max(9 * align256(n * N * D), 4 * align256(n * N * 176) + align256(n * N * 16) + align256(n * N)),
-                                              9 * align256(n * N * 176) + 8 * align256(n * N * 4));
+                                              9 * align256(n * N * 176) + 9 * align256(n * N * 4) + 256);
 }
 
 // The lane = path kernels (pydl.cu): cost volume and per-direction volumes as [y][label column][x][16-byte frame], shift
@@ -66,7 +66,14 @@ int pyd_pipeline_lane(fsgm_ctx* c, int n, const uint32_t* cen1, const uint32_t* 
     uint8_t* C; uint8_t* L[8] = {}; uint32_t* desc[8] = {};
     FSGM_TRY(arena_get(c, n * N * PITCH, &C));
     for (int k = 0; k < nd; ++k) { FSGM_TRY(arena_get(c, n * N * PITCH, &L[k])); FSGM_TRY(arena_get(c, n * N, &desc[k])); }
-    FSGM_TRY(launch_pyd_cost(c, n, cen1, cen2, W, H, d_preMv, mvW, mvH, g.agg, g.rx, g.ry, C, PITCH, 1));
+    if (c->pyd_direct_cost) {
+        FSGM_TRY(launch_pyd_cost(c, n, cen1, cen2, W, H, d_preMv, mvW, mvH, g.agg, g.rx, g.ry, C, PITCH, 1));
+    } else {
+        uint32_t *list, *count;
+        FSGM_TRY(arena_get(c, n * N, &list));
+        FSGM_TRY(arena_get(c, (size_t)n, &count));
+        FSGM_TRY(launch_pyd_cost_sep(c, n, cen1, cen2, W, H, d_preMv, mvW, mvH, g.agg, g.rx, g.ry, C, list, count));
+    }
     FSGM_TRY(launch_pydl_desc(c, n, d_preMv, mvW, mvH, W, H, g.Sx, g.Sy, dirs, nd, desc, c->pyd_cluster == -2));
     FSGM_TRY(launch_pydl_sweeps(c, n, C, d_I1, d_preMv, mvW, mvH, W, H, g.Sx, g.Sy, g.P1, g.P2, g.adaptive, dirs, nd, desc, L));
     return launch_pydl_wta(c, n, L, nd, W, H, g.Sx, g.Sy, g.subpixel, d_bestD, d_minC, d_mvSub);

@@ -40,6 +40,7 @@ struct fsgm_ctx {
     unsigned attr_mask = 0;                 // which kernels already had their max-dynamic-smem attribute set on this device
     int clusters_key[4] = {0, 0, 0, 0}, clusters_max = 0;   // resident clusters for the last queried (cluster size, W, D, ndir)
     int best_key[3] = {0, 0, 0}, best_cs = 0, best_clusters = 0;   // cached vsweep_best_cluster() decision for (W, D, ndir)
+    int pyd_direct_cost = 0;                // tuning knob (fsgm_tune key 6): 1 = the lane = path pipeline builds its cost volume with the direct kernel only
     int pyd_cluster = 0;                    // tuning knob (fsgm_tune key 5): cluster size of the pyd row-synchronous kernels, 0 auto, -1 off
     std::vector<std::pair<int, int>> pv_occ;   // cached cudaOccupancyMaxActiveClusters answers of pydv_kernel
     int ng_occupancy = 0;                   // tuning knob (fsgm_tune key 3): resident pairs per SM of the ng kernel, 0 = by batch size
@@ -166,7 +167,10 @@ int launch_vs_finalize(fsgm_ctx* c, int n, const uint16_t* rec, const uint32_t* 
 
 // ---- pyramidal 2-D-window variant (pyd.cu) ----------------------------------------------------------
 int launch_pyd_cost(fsgm_ctx* c, int n, const uint32_t* cen1, const uint32_t* cen2, int W, int H,
-                    const double* preMv, int mvW, int mvH, int agg, int rx, int ry, uint8_t* C, int pitch = 0, int soa = 0);
+                    const double* preMv, int mvW, int mvH, int agg, int rx, int ry, uint8_t* C, int pitch = 0, int soa = 0,
+                    const uint32_t* list = nullptr, const uint32_t* list_count = nullptr);
+int launch_pyd_cost_sep(fsgm_ctx* c, int n, const uint32_t* cen1, const uint32_t* cen2, int W, int H,
+                        const double* preMv, int mvW, int mvH, int agg, int rx, int ry, uint8_t* C, uint32_t* list, uint32_t* count);
 int launch_pyd_sweeps(fsgm_ctx* c, int n, const uint8_t* C, const uint8_t* I1, const double* preMv, int mvW, int mvH,
                       int W, int H, int Sx, int Sy, int P1, int P2, int adaptive, const int* dirs, int n_dirs, uint8_t* const* Lvols,
                       int pitch = 0);

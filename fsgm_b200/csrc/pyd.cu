@@ -390,8 +390,10 @@ constexpr int PYC_WARPS = 4;
 template <int AGG>
 __global__ void __launch_bounds__(PYC_WARPS * 32)
 pyd_cost_px_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restrict__ cen2, int W, int H,
-                   const double* __restrict__ preMv, int mvW, int mvH, int rx, int ry, int pitch, int soa, uint8_t* __restrict__ C)
+                   const double* __restrict__ preMv, int mvW, int mvH, int rx, int ry, int pitch, int soa, uint8_t* __restrict__ C,
+                   const uint32_t* __restrict__ list, const uint32_t* __restrict__ list_count)
 {
+    // list != nullptr (soa only): the warp's lanes take 32 entries of the pair's pixel list instead of 32 consecutive pixels
     // pitch == 0: compact label rows (D bytes per pixel, the reference's layout).  pitch == 16*Sx: the PADDED GRID of the
     // row-synchronous aggregation kernels (pydv.cu): column ox at byte 16*ox, two leading pad bytes, Sy labels, trailing pads,
     // every pad byte 255.  soa: the same 16-byte frames as [y][label column][x] (pydl.cu: lane = path aggregation).
@@ -411,10 +413,17 @@ pyd_cost_px_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restrict
     const int xblocks = (W + 31) / 32;
     const int job = blockIdx.x * PYC_WARPS + wib;
     if (job >= xblocks * H) return;                      // warps are independent (only __syncwarp below)
-    const int y = job / xblocks, x0 = (job - y * xblocks) * 32, x = min(x0 + lane, W - 1);      // lanes past the row end repeat its last pixel
-    const int nlive = min(32, W - x0);
     const size_t N = (size_t)W * H;
     const int pair = blockIdx.y;
+    int y = job / xblocks, x0 = (job - y * xblocks) * 32, x = min(x0 + lane, W - 1);      // lanes past the row end repeat its last pixel
+    int nlive = min(32, W - x0);
+    if (list) {
+        const int cnt = (int)list_count[pair];
+        if (job * 32 >= cnt) return;
+        nlive = min(32, cnt - job * 32);
+        const uint32_t pi = list[(size_t)pair * N + job * 32 + min(lane, nlive - 1)];
+        y = (int)(pi / (uint32_t)W); x = (int)(pi - (uint32_t)y * (uint32_t)W);
+    }
     const double* mvp = preMv + (size_t)pair * 2 * mvW * mvH;
     const double mvx = mvp[(size_t)mvW * y + x], mvy = mvp[(size_t)mvW * mvH + (size_t)mvW * y + x];
     const uint32_t* c1 = cen1 + pair * N;
@@ -499,7 +508,7 @@ pyd_cost_px_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restrict
     uint8_t* out = C + (pair * N + (size_t)y * W + x0) * PT;
     const int nbytes = nlive * PT;
     if (soa) {                                            // one 512-byte run per label column
-        uint8_t* o2 = C + (size_t)pair * N * PT + (((size_t)y * Sx) * W + x0 + lane) * 16;
+        uint8_t* o2 = C + (size_t)pair * N * PT + (((size_t)y * Sx) * W + x) * 16;
         if (lane < nlive)
             for (int ox = 0; ox < Sx; ++ox)
                 *reinterpret_cast<uint4*>(o2 + (size_t)ox * W * 16) = *reinterpret_cast<const uint4*>(tile + lane * PT + ox * 16);
@@ -508,6 +517,214 @@ pyd_cost_px_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restrict
     } else {
         for (int i = lane; i < nbytes; i += 32) out[i] = tile[i];
     }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// cost volume where the prior is locally constant: a separable box filter over SHARED raw costs.
+// The reference samples every pixel q of p's aggregation window with the prior of the CENTRE p (:388-389); when all pixels of
+// the window carry bitwise the same prior, that is the pixel's own prior and h(q, o) = popc(cen1[q] ^ cen2[q + o + mv(q)])
+// (or the constant 5) does not depend on p any more: cost(p, o) is a T x T box sum of one raw volume, T*T times fewer
+// Hamming distances.  This kernel computes that for EVERY pixel; pyd_uniform_kernel lists the pixels whose window is not
+// uniform and pyd_cost_px_kernel (list mode) recomputes exactly those.
+// A thread owns one image column of a 128-column strip (T - 1 of them halo) and marches down a segment of rows: per row the raw
+// costs of its pixel (three words per label column: rows 0..11 as bytes), a horizontal T-sum through shared memory (bytes:
+// <= 5 * 25), a vertical running sum in u16x2 registers with the row that leaves the window read back from a ring of T rows.
+// Output in the [y][label column][x][16-byte frame] layout of pydl.cu.
+// ------------------------------------------------------------------------------------------------
+constexpr int PCS_COLS = 128;            // image columns per block (T - 1 of them halo)
+constexpr int PCS_ROWS = 32;             // rows per segment (the T - 1 halo rows are recomputed per segment)
+
+// G threads share an image column: thread (column, g) owns label columns [g*OXG, (g+1)*OXG) — the per-column shared-memory
+// footprint (ring of T rows) caps the columns in flight per SM, the split multiplies the warps that work on them.
+template <int AGG, int SX, int G>
+__global__ void __launch_bounds__(PCS_COLS * G, 2)
+pyd_cost_sep_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restrict__ cen2, int W, int H,
+                    const double* __restrict__ preMv, int mvW, int mvH, int ry, uint8_t* __restrict__ C)
+{
+    constexpr int T = 2 * AGG + 1, WPX = T * T, NW = 3 * SX, RX = (SX - 1) / 2, OXG = (SX + G - 1) / G;
+    constexpr uint32_t MUL = WPX == 25 ? 1311u : 3641u;                 // floor(n / (2*WPX)) == (n * MUL) >> 16 for n <= 2*WPX*25 + WPX
+    extern __shared__ uint32_t pcs_smem[];
+    uint32_t* rawb = pcs_smem;                                           // [NW][128]
+    uint32_t* ring = pcs_smem + NW * PCS_COLS;                           // [T][NW][128]
+    const int tid = threadIdx.x % PCS_COLS, g = threadIdx.x / PCS_COLS;
+    const int ox0 = g * OXG;
+    const int Sy = 2 * ry + 1;
+    const int TW = PCS_COLS - 2 * AGG;
+    const int xq = blockIdx.x * TW - AGG + tid;
+    const int y0 = blockIdx.y * PCS_ROWS, y1 = min(y0 + PCS_ROWS, H);
+    const int pair = blockIdx.z;
+    const size_t N = (size_t)W * H;
+    const uint32_t* c1 = cen1 + pair * N;
+    const uint32_t* c2 = cen2 + pair * N;
+    const double* mvxp = preMv + (size_t)pair * 2 * mvW * mvH;
+    const double* mvyp = mvxp + (size_t)mvW * mvH;
+    uint8_t* Cb = C + (size_t)pair * N * (SX * 16);
+    const bool col_in = xq >= 0 && xq < W;
+    const bool interior = tid >= AGG && tid < PCS_COLS - AGG && col_in;
+
+    for (int i = threadIdx.x; i < T * NW * PCS_COLS; i += PCS_COLS * G) ring[i] = 0;
+    uint32_t vs[OXG][6];
+#pragma unroll
+    for (int o = 0; o < OXG; ++o)
+#pragma unroll
+        for (int i = 0; i < 6; ++i) vs[o][i] = 0;
+    uint32_t padw[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint32_t m = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) { const int row = 4 * j + b - 2; if (row < 0 || row >= Sy) m |= 0xFFu << (8 * b); }
+        padw[j] = m;
+    }
+    __syncthreads();
+
+    int slot = 0;
+    for (int yq = y0 - AGG; yq < y1 + AGG; ++yq) {
+        // ---- raw costs of pixel (xq, yq), this thread's label columns ----------------------------------------------------------
+        const bool inimg = col_in && yq >= 0 && yq < H;
+        int fx[OXG], fy[12];
+        uint32_t w1 = 0;
+        bool allok = true;
+        if (inimg) {
+            const double mvx = mvxp[(size_t)mvW * yq + xq], mvy = mvyp[(size_t)mvW * yq + xq];
+            w1 = __ldg(c1 + (size_t)W * yq + xq);
+#pragma unroll
+            for (int o = 0; o < OXG; ++o) {
+                const int v = x86_d2i(__dadd_rn(__dadd_rn((double)(ox0 + o - RX + xq), mvx), 0.5));
+                fx[o] = (v < 0 || v > W - 1) ? -1 : v;
+                if (ox0 + o < SX) allok &= fx[o] >= 0;
+            }
+#pragma unroll
+            for (int oy = 0; oy < 12; ++oy) {
+                const int v = x86_d2i(__dadd_rn(__dadd_rn((double)(oy - ry + yq), mvy), 0.5));
+                fy[oy] = (oy >= Sy || v < 0 || v > H - 1) ? -1 : v;
+                if (oy < Sy) allok &= fy[oy] >= 0;
+            }
+        }
+        const bool fast = __all_sync(0xffffffffu, allok);          // every thread of the block gets here: no divergence above
+        if (inimg) {
+            if (fast) {
+#pragma unroll
+                for (int o = 0; o < OXG; ++o) {
+                    if (ox0 + o < SX) {
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) {
+                            uint32_t w = 0;
+#pragma unroll
+                            for (int b = 0; b < 4; ++b) {
+                                const int oy = 4 * j + b;
+                                if (oy < Sy) w += (uint32_t)__popc(w1 ^ __ldg(c2 + (size_t)W * fy[oy] + fx[o])) << (8 * b);
+                            }
+                            rawb[((ox0 + o) * 3 + j) * PCS_COLS + tid] = w;
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int o = 0; o < OXG; ++o) {
+                    if (ox0 + o < SX) {
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) {
+                            uint32_t w = 0;
+#pragma unroll
+                            for (int b = 0; b < 4; ++b) {
+                                const int oy = 4 * j + b;
+                                const bool ok = fx[o] >= 0 && fy[oy] >= 0;
+                                const uint32_t h = ok ? (uint32_t)__popc(w1 ^ __ldg(c2 + (size_t)W * max(fy[oy], 0) + max(fx[o], 0))) : 5u;
+                                w += h << (8 * b);
+                            }
+                            rawb[((ox0 + o) * 3 + j) * PCS_COLS + tid] = w;
+                        }
+                    }
+                }
+            }
+        } else {
+            // a window pixel outside the image contributes the constant (:405-408)
+#pragma unroll
+            for (int o = 0; o < OXG; ++o)
+                if (ox0 + o < SX)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) rawb[((ox0 + o) * 3 + j) * PCS_COLS + tid] = 0x05050505u;
+        }
+        __syncthreads();
+        // ---- horizontal T-sum (bytes), vertical running sum (u16x2), ring of the last T rows ------------------------------------
+        if (interior) {
+#pragma unroll
+            for (int o = 0; o < OXG; ++o) {
+                if (ox0 + o < SX) {
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        const int w = (ox0 + o) * 3 + j;
+                        uint32_t hs = 0;
+#pragma unroll
+                        for (int ax = -AGG; ax <= AGG; ++ax) hs += rawb[w * PCS_COLS + tid + ax];
+                        uint32_t* rp = ring + (slot * NW + w) * PCS_COLS + tid;
+                        const uint32_t old = *rp;
+                        *rp = hs;
+                        vs[o][2 * j] += __byte_perm(hs, 0, 0x4140) - __byte_perm(old, 0, 0x4140);
+                        vs[o][2 * j + 1] += __byte_perm(hs, 0, 0x4342) - __byte_perm(old, 0, 0x4342);
+                    }
+                }
+            }
+            const int yp = yq - AGG;
+            if (yp >= y0) {
+                uint8_t* op = Cb + (((size_t)yp * SX) * W + xq) * 16;
+#pragma unroll
+                for (int o = 0; o < OXG; ++o) {
+                    if (ox0 + o < SX) {
+                        // (u8)(1.0*s/wp + 0.5) == (2s + wp) / (2wp): byte 2 of the product
+                        uint32_t pr[12];
+#pragma unroll
+                        for (int i = 0; i < 6; ++i) {
+                            pr[2 * i] = (vs[o][i] & 0xFFFFu) * (2u * MUL) + WPX * MUL;
+                            pr[2 * i + 1] = (vs[o][i] >> 16) * (2u * MUL) + WPX * MUL;
+                        }
+                        uint4 f;
+                        f.x = (__byte_perm(pr[0], pr[1], 0x6200) | 0x0000FFFFu) | padw[0];
+                        f.y = __byte_perm(__byte_perm(pr[2], pr[3], 0x0062), __byte_perm(pr[4], pr[5], 0x0062), 0x5410) | padw[1];
+                        f.z = __byte_perm(__byte_perm(pr[6], pr[7], 0x0062), __byte_perm(pr[8], pr[9], 0x0062), 0x5410) | padw[2];
+                        f.w = (__byte_perm(pr[10], 0, 0x4442) | 0xFFFFFF00u) | padw[3];
+                        *reinterpret_cast<uint4*>(op + (size_t)(ox0 + o) * W * 16) = f;
+                    }
+                }
+            }
+        }
+        slot = slot + 1 == T ? 0 : slot + 1;
+        __syncthreads();
+    }
+}
+
+// pixels whose aggregation window does not carry one prior (bit patterns compared): appended to the pair's list
+__global__ void pyd_uniform_kernel(const double* __restrict__ preMv, int mvW, int mvH, int W, int H, int agg,
+                                   uint32_t* __restrict__ list, uint32_t* __restrict__ count)
+{
+    const size_t N = (size_t)W * H;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int pair = blockIdx.y;
+    bool flag = false;
+    if (i < N) {
+        const int y = (int)(i / W), x = (int)(i - (size_t)y * W);
+        const long long* mx = reinterpret_cast<const long long*>(preMv) + (size_t)pair * 2 * mvW * mvH;
+        const long long* my = mx + (size_t)mvW * mvH;
+        const long long cx = mx[(size_t)mvW * y + x], cy = my[(size_t)mvW * y + x];
+        for (int ay = -agg; ay <= agg; ++ay) {
+            const int yy = y + ay;
+            if (yy < 0 || yy >= H) continue;
+            for (int ax = -agg; ax <= agg; ++ax) {
+                const int xx = x + ax;
+                if (xx < 0 || xx >= W) continue;
+                flag |= mx[(size_t)mvW * yy + xx] != cx || my[(size_t)mvW * yy + xx] != cy;
+            }
+        }
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, flag);
+    if (!mask) return;
+    const int lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(count + pair, (uint32_t)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (flag) list[(size_t)pair * N + base + __popc(mask & ((1u << lane) - 1u))] = (uint32_t)i;
 }
 
 static size_t pyd_cost_px_smem(int agg, int rx, int ry, int pitch)
@@ -519,7 +736,8 @@ static size_t pyd_cost_px_smem(int agg, int rx, int ry, int pitch)
 }
 
 int launch_pyd_cost(fsgm_ctx* c, int n, const uint32_t* cen1, const uint32_t* cen2, int W, int H,
-                    const double* preMv, int mvW, int mvH, int agg, int rx, int ry, uint8_t* C, int pitch, int soa)
+                    const double* preMv, int mvW, int mvH, int agg, int rx, int ry, uint8_t* C, int pitch, int soa,
+                    const uint32_t* list, const uint32_t* list_count)
 {
     StageScope ss(c, ST_PYD_COST);
     if (2 * (rx + agg) + 1 > PYD_MAXS + 32 || 2 * (ry + agg) + 1 > PYD_MAXS + 32)
@@ -533,10 +751,10 @@ int launch_pyd_cost(fsgm_ctx* c, int n, const uint32_t* cen1, const uint32_t* ce
         dim3 grid((unsigned)((jobs + PYC_WARPS - 1) / PYC_WARPS), n);
         if (agg == 2) {
             FSGM_CUDA(c, cudaFuncSetAttribute(pyd_cost_px_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            pyd_cost_px_kernel<2><<<grid, PYC_WARPS * 32, smem, c->stream>>>(cen1, cen2, W, H, preMv, mvW, mvH, rx, ry, pitch, soa, C);
+            pyd_cost_px_kernel<2><<<grid, PYC_WARPS * 32, smem, c->stream>>>(cen1, cen2, W, H, preMv, mvW, mvH, rx, ry, pitch, soa, C, list, list_count);
         } else {
             FSGM_CUDA(c, cudaFuncSetAttribute(pyd_cost_px_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            pyd_cost_px_kernel<1><<<grid, PYC_WARPS * 32, smem, c->stream>>>(cen1, cen2, W, H, preMv, mvW, mvH, rx, ry, pitch, soa, C);
+            pyd_cost_px_kernel<1><<<grid, PYC_WARPS * 32, smem, c->stream>>>(cen1, cen2, W, H, preMv, mvW, mvH, rx, ry, pitch, soa, C, list, list_count);
         }
         FSGM_LAUNCHED(c);
         return FSGM_OK;
@@ -545,6 +763,50 @@ int launch_pyd_cost(fsgm_ctx* c, int n, const uint32_t* cen1, const uint32_t* ce
     pyd_cost_kernel<<<grid, 256, 0, c->stream>>>(cen1, cen2, W, H, preMv, mvW, mvH, agg, rx, ry, C);
     FSGM_LAUNCHED(c);
     return FSGM_OK;
+}
+
+
+template <int AGG, int SX>
+static int pcs_launch(fsgm_ctx* c, int n, const uint32_t* cen1, const uint32_t* cen2, int W, int H, const double* preMv, int mvW, int mvH,
+                      int ry, uint8_t* C)
+{
+    constexpr int T = 2 * AGG + 1;
+    constexpr int G = SX >= 9 ? 3 : SX >= 5 ? 2 : 1;
+    const size_t smem = (size_t)(T + 1) * 3 * SX * PCS_COLS * 4;
+    auto kern = pyd_cost_sep_kernel<AGG, SX, G>;
+    FSGM_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int TW = PCS_COLS - 2 * AGG;
+    dim3 grid((W + TW - 1) / TW, (H + PCS_ROWS - 1) / PCS_ROWS, n);
+    kern<<<grid, PCS_COLS * G, smem, c->stream>>>(cen1, cen2, W, H, preMv, mvW, mvH, ry, C);
+    FSGM_LAUNCHED(c);
+    return FSGM_OK;
+}
+
+// cost volume in the [y][label column][x][16-byte frame] layout: separable box filter everywhere + exact recomputation of the
+// pixels whose aggregation window sees more than one prior.  list: n*N u32, count: n u32 (scratch).
+int launch_pyd_cost_sep(fsgm_ctx* c, int n, const uint32_t* cen1, const uint32_t* cen2, int W, int H,
+                        const double* preMv, int mvW, int mvH, int agg, int rx, int ry, uint8_t* C, uint32_t* list, uint32_t* count)
+{
+    const size_t N = (size_t)W * H;
+    {
+        StageScope ss(c, ST_PYD_COST);
+        FSGM_CUDA(c, cudaMemsetAsync(count, 0, (size_t)n * 4, c->stream));
+        pyd_uniform_kernel<<<dim3((unsigned)((N + 127) / 128), n), 128, 0, c->stream>>>(preMv, mvW, mvH, W, H, agg, list, count);
+        FSGM_LAUNCHED(c);
+        const int Sx = 2 * rx + 1;
+#define PCS_GO(A, S) FSGM_TRY((pcs_launch<A, S>(c, n, cen1, cen2, W, H, preMv, mvW, mvH, ry, C)))
+        if (agg == 2) {
+            switch (Sx) { case 1: PCS_GO(2, 1); break; case 3: PCS_GO(2, 3); break; case 5: PCS_GO(2, 5); break;
+                          case 7: PCS_GO(2, 7); break; case 9: PCS_GO(2, 9); break; case 11: PCS_GO(2, 11); break;
+                          default: return fail(c, FSGM_ERR_DOMAIN, "separable pyd cost: window width must be odd and <= 11"); }
+        } else if (agg == 1) {
+            switch (Sx) { case 1: PCS_GO(1, 1); break; case 3: PCS_GO(1, 3); break; case 5: PCS_GO(1, 5); break;
+                          case 7: PCS_GO(1, 7); break; case 9: PCS_GO(1, 9); break; case 11: PCS_GO(1, 11); break;
+                          default: return fail(c, FSGM_ERR_DOMAIN, "separable pyd cost: window width must be odd and <= 11"); }
+        } else return fail(c, FSGM_ERR_DOMAIN, "separable pyd cost: aggregation radius 1 or 2");
+#undef PCS_GO
+    }
+    return launch_pyd_cost(c, n, cen1, cen2, W, H, preMv, mvW, mvH, agg, rx, ry, C, 16 * (2 * rx + 1), 1, list, count);
 }
 
 int launch_pyd_sweeps(fsgm_ctx* c, int n, const uint8_t* C, const uint8_t* I1, const double* preMv, int mvW, int mvH,

@@ -44,6 +44,13 @@ __device__ __forceinline__ uint32_t pl_lds32(uint32_t a) { uint32_t v; asm volat
 __device__ __forceinline__ uint32_t pl_lds8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ void pl_sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void pl_sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+// volatile: the compiler keeps these where they are written (requests issued early, far from their first use)
+__device__ __forceinline__ uint4 pl_ldg128(const void* p)
+{
+    uint4 v; asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p)); return v;
+}
+__device__ __forceinline__ uint32_t pl_ldg32(const void* p) { uint32_t v; asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+__device__ __forceinline__ void pl_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ uint32_t pl_min3(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_u16x2(a, b, c); }
 
 __device__ __forceinline__ int pl_x86_d2i(double v)
@@ -142,7 +149,9 @@ pydl_sweep_kernel(const PlParams prm)
         // next position and its descriptor
         int nx = x + dx, ny = y + dy;
         if (dy != 0) nx = nx < 0 ? W - 1 : (nx >= W ? 0 : nx);
-        if (t + 1 < len) dnext = __ldg(desc + (uint32_t)ny * (uint32_t)W + (uint32_t)nx);
+        if (t + 1 < len) {
+            dnext = pl_ldg32(desc + (uint32_t)ny * (uint32_t)W + (uint32_t)nx);
+        }
         int P2 = prm.P2;
         if (prm.adaptive) {
             const int icur = Ib[pix];
@@ -210,7 +219,7 @@ pydl_sweep_kernel(const PlParams prm)
             const int c = cp + 2;                                       // output column of this iteration
             uint4 ccol = make_uint4(0, 0, 0, 0);
             if (c >= 0 && c < SX) ccol = cq[it % 3];
-            if (it >= 1 && SX - it >= 0) cq[it % 3] = __ldg(reinterpret_cast<const uint4*>(cpix + (size_t)(SX - it) * colstride));
+            if (it >= 1 && SX - it >= 0) cq[it % 3] = pl_ldg128(cpix + (size_t)(SX - it) * colstride);
             if (c >= 0 && c < SX) {
                 uint32_t bst[6];
 #pragma unroll
@@ -271,6 +280,15 @@ struct PlDescParams { uint32_t* out[8]; int dir[8]; int n_dirs; };
 // [-3, S+2] (three or more outside the window: no neighbour inside).  Returns true when a(s) = s + k + [s < t].
 __device__ __forceinline__ bool pl_analyse(double dd, int S, int* k_out, int* t_out)
 {
+    // integer-valued difference n (what the pyramid driver produces: priors are 2 x integer): the argument s + n + 0.5 truncates
+    // to s + n where it is positive and to s + n + 1 where it is negative
+    if (dd == rint(dd) && fabs(dd) <= 64.0) {
+        const int n = (int)dd;
+        int k = n, t = min(max(-n, 0), S);
+        if (t == S) { k = n + 1; t = 0; }
+        *k_out = min(max(k, -15), 15); *t_out = t;
+        return true;
+    }
     int a[11];
 #pragma unroll
     for (int s = 0; s < 11; ++s)
