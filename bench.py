@@ -474,9 +474,10 @@ def workload_C(env: Env):
     calc_pyd_cost_sgm.cpp:439 per level), reference window r=5 (121 labels) and BASELINE's +-4 (81 labels)"""
     torch, ctx, api = env.torch, env.ctx, env.api
     from fsgm_b200 import synth
-    n = 8
-    fps = [synth.flow_pair(W, H, seed=1 + i, umax=20, vmax=10) for i in range(n)]
-    I0 = torch.from_numpy(np.stack([f["I1"] for f in fps])).cuda(); I1 = torch.from_numpy(np.stack([f["I2"] for f in fps])).cuda()
+    n, distinct = 32, 8                                        # 32 pairs per step (8 distinct synthetic pairs, each four times)
+    fps = [synth.flow_pair(W, H, seed=1 + i, umax=20, vmax=10) for i in range(distinct)]
+    I0 = torch.from_numpy(np.stack([fps[i % distinct]["I1"] for i in range(n)])).cuda()
+    I1 = torch.from_numpy(np.stack([fps[i % distinct]["I2"] for i in range(n)])).cuda()
     mv = torch.empty((n, 2, H, W), dtype=torch.float64, device="cuda"); mC = torch.empty((n, H, W), dtype=torch.int32, device="cuda")
     ws, hs = api.pyramid_dims(W, H, 3)
     out = {}
@@ -643,6 +644,7 @@ def dirsplit_4k(env: Env):
     n4 = w4 * h4
     sent = (env.world - 1) / env.world * n4 * D * (1 if plan.exchange_u8 else 2)
     ex_ms = st.get("exchange", (0.0, 0))[0] / reps
+    per_rank = {k: [round(v, 3) for v in env.gather(st.get(k, (0.0, 0))[0] / reps)] for k in ("epi_cost", "sweep", "exchange", "wta")}
     # A/B: the same call with the peer-store form switched off (partial volumes exchanged by NCCL after the sweeps)
     ctx.tune(4, 1)
     split(); split()
@@ -661,7 +663,7 @@ def dirsplit_4k(env: Env):
             "bit_equal_to_single_gpu_call": same, "gde_per_s": n4 * D / (ms * 1e-3) / 1e9,
             "exchange": "none: the sweep kernel stores every L row into the peer-mapped memory of the slab's owner (NVLink) while it computes",
             "nvlink_bytes_sent_per_rank": int((env.world - 1) / env.world * n4 * D * plan.n_dirs),
-            "stage_ms_rank0": {k: v[0] / reps for k, v in st.items()},
+            "stage_ms_rank0": {k: v[0] / reps for k, v in st.items()}, "stage_ms_per_rank": per_rank,
             "nvlink_gbs_per_rank_during_sweeps": ((env.world - 1) / env.world * n4 * D * plan.n_dirs / (st["sweep"][0] / reps * 1e-3) / 1e9) if "sweep" in st else None,
             "nvlink_peak_gbs_per_direction": 900.0,
             "nccl_exchange_form": {"value": ms_nccl, "unit": "ms", "bit_equal_to_single_gpu_call": same_nccl,

@@ -47,11 +47,16 @@ struct SweepParams {
     int W, H, D;
     int P1, P2, adaptive_thr;
     // SCATTER (direction split over GPUs, dist.cu): a pixel's L row goes straight into the memory of the rank that owns the pixel's
-    // slab — peer[j] is rank j's receive buffer (peer-mapped over NVLink, or local for j == this rank), laid out
-    // [direction slot][slab_pixels][D]; direction k of this launch writes slot slot[k].
+    // STRIPE — stripes of a few image rows are dealt to the ranks round-robin, so that the down / up sweeps of all ranks, which
+    // move through the image rows together, spread their stores over every owner at any time instead of all hitting the one
+    // rank that owns the current part of the image (NVLink ingress of one GPU).  peer[j] is rank j's receive buffer (peer-mapped
+    // over NVLink, or local for j == this rank), laid out [direction slot][local stripe][chunk_pixels][D] with
+    // chunk_pixels = stripe_pixels + 1: the extra pixel holds a copy of the first pixel of the NEXT stripe (the reference's read of
+    // the next pixel's label 0, calc_cost_sgm.cpp:293-296).  Direction k of this launch writes slot slot[k].
     uint8_t* peer[16];
     int slot[8];
-    unsigned slab_pixels;
+    unsigned stripe_pixels, chunk_pixels, local_pixels;
+    int world;
 };
 
 template <int NREG> struct Words { uint32_t w[(NREG + 1) / 2]; };
@@ -180,8 +185,8 @@ sweep_fast_kernel(const SweepParams prm)
     uint32_t M = 0;
     int prev_pix = 0;
     bool restart = true;
-    // SCATTER: the slab [own_lo, own_hi) the cursor is in and the base its rows are written against; a scanline changes slab a
-    // handful of times (horizontal: at most once), so the division runs only then
+    // SCATTER: the stripe [own_lo, own_hi) the cursor is in and the base its rows are written against; the divisions run only
+    // when a scanline enters another stripe (horizontal: never)
     unsigned own_lo = 1, own_hi = 0;
     uint8_t* own_base = nullptr;
 
@@ -223,11 +228,18 @@ sweep_fast_kernel(const SweepParams prm)
             if (SCATTER) {
                 const unsigned up = (unsigned)pix;
                 if (up < own_lo || up >= own_hi) {
-                    const unsigned j = up / prm.slab_pixels;
-                    own_lo = j * prm.slab_pixels; own_hi = own_lo + prm.slab_pixels;
-                    own_base = prm.peer[j] + ((size_t)prm.slot[k] * prm.slab_pixels - own_lo) * (size_t)D;
+                    const unsigned j = up / prm.stripe_pixels;
+                    const unsigned owner = j % (unsigned)prm.world, ls = j / (unsigned)prm.world;
+                    own_lo = j * prm.stripe_pixels; own_hi = own_lo + prm.stripe_pixels;
+                    own_base = prm.peer[owner] + ((size_t)prm.slot[k] * prm.local_pixels + (size_t)ls * prm.chunk_pixels - own_lo) * (size_t)D;
                 }
                 store_row<NREG, MODE>(own_base + (size_t)up * (uint32_t)D, lane, D, Lr);
+                if (up == own_lo && up != 0) {                      // first pixel of a stripe: a copy behind the previous stripe
+                    const unsigned j = up / prm.stripe_pixels - 1;
+                    const unsigned owner = j % (unsigned)prm.world, ls = j / (unsigned)prm.world;
+                    uint8_t* ex = prm.peer[owner] + ((size_t)prm.slot[k] * prm.local_pixels + (size_t)ls * prm.chunk_pixels + prm.stripe_pixels) * (size_t)D;
+                    store_row<NREG, MODE>(ex, lane, D, Lr);
+                }
             } else
             store_row<NREG, MODE>(Lb + (size_t)(uint32_t)pix * (uint32_t)D, lane, D, Lr);
             prev_pix = pix;
@@ -550,7 +562,7 @@ int launch_sweeps(fsgm_ctx* c, int n, const uint8_t* C, const uint8_t* I1, int W
 // rank that owns the pixel's slab (see SweepParams).  No-wrap domain, no adaptive P2 (the caller falls back to local volumes +
 // an NCCL exchange otherwise).
 int launch_sweeps_scatter(fsgm_ctx* c, const uint8_t* C, int W, int H, int D, int P1, int P2, const int* dirs, const int* slots,
-                          int n_dirs, uint8_t* const* peer, int world, size_t slab_pixels)
+                          int n_dirs, uint8_t* const* peer, int world, size_t stripe_pixels, size_t local_pixels)
 {
     if (D < 1 || D > 512) return fail(c, FSGM_ERR_DOMAIN, "label count must be in 1..512");
     if (n_dirs < 1 || n_dirs > 8 || world < 1 || world > 16) return fail(c, FSGM_ERR_ARG, "n_dirs / world");
@@ -558,7 +570,7 @@ int launch_sweeps_scatter(fsgm_ctx* c, const uint8_t* C, int W, int H, int D, in
     StageScope ss(c, ST_SWEEP);
     SweepParams p{};
     p.C = C; p.n_dirs = n_dirs; p.W = W; p.H = H; p.D = D; p.P1 = P1; p.P2 = P2; p.adaptive_thr = 0;
-    p.slab_pixels = (unsigned)slab_pixels;
+    p.stripe_pixels = (unsigned)stripe_pixels; p.chunk_pixels = (unsigned)stripe_pixels + 1; p.local_pixels = (unsigned)local_pixels; p.world = world;
     for (int j = 0; j < world; ++j) p.peer[j] = peer[j];
     p.line_start[0] = 0;
     for (int k = 0; k < n_dirs; ++k) {

@@ -165,12 +165,28 @@ int p2p_ensure(fsgm_ctx* c, NcclApi* a, size_t bytes, bool* usable)
     return FSGM_OK;
 }
 
-// word[0] = total of the first voxel (label 0 of the first pixel) of the NEXT rank's slab, read through its peer mapping
-__global__ void first_voxel_peer_kernel(const uint8_t* next_rank_buf, int n_vols, size_t stride, uint32_t* out)
+// ---- striped ownership of the peer-store form: global stripe j (stripe_pixels pixels) lives on rank j % world as its local
+// stripe j / world, in chunks of stripe_pixels + 1 pixels ------------------------------------------------------------------------
+// offsetFromPosD0 of a rank's local pixels (zero for the extra / unused ones)
+__global__ void stripe_gather_f64_kernel(const double* __restrict__ src, size_t N, unsigned stripe_pixels, int rank, int world,
+                                         size_t local_pixels, double* __restrict__ dst)
 {
-    uint32_t a = 0;
-    for (int k = 0; k < n_vols; ++k) a += next_rank_buf[(size_t)k * stride];
-    *out = a;
+    const size_t lp = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (lp >= local_pixels) return;
+    const size_t chunk = (size_t)stripe_pixels + 1, ls = lp / chunk, off = lp - ls * chunk;
+    const size_t g = (ls * world + rank) * stripe_pixels + off;
+    dst[lp] = (off < stripe_pixels && g < N) ? src[g] : 0.0;
+}
+
+// all-gathered local outputs [world][local_pixels] -> the image
+__global__ void stripe_scatter_u32_kernel(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, size_t N, unsigned stripe_pixels,
+                                          int world, size_t local_pixels, uint32_t* __restrict__ oa, uint32_t* __restrict__ ob)
+{
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= N) return;
+    const size_t j = g / stripe_pixels, owner = j % world, ls = j / world;
+    const size_t src = owner * local_pixels + ls * ((size_t)stripe_pixels + 1) + (g - j * stripe_pixels);
+    oa[g] = a[src]; ob[g] = b[src];
 }
 
 }  // namespace
@@ -198,6 +214,17 @@ int fsgm_shard_range(int n, int rank, int world, int* first, int* count)
     return FSGM_OK;
 }
 
+// The enabled directions in the order they are dealt to the ranks (rank r takes positions r, r + world, ...).  Horizontal
+// scanlines are the longest serial chains and the fewest warps, diagonals the cheapest: swapping neighbours in the reversed
+// half (0 1 2 3 5 4 7 6) gives every rank one direction of each kind at world = 2 and a horizontal + a vertical one at
+// world = 4, so nobody waits for a rank that drew both horizontal sweeps.
+static int split_order(const fsgm_epi_opts& o, int* dirs)
+{
+    const int nd = enabled_dirs(o, dirs);
+    for (int k = nd / 2; k + 1 < nd; k += 2) std::swap(dirs[k], dirs[k + 1]);
+    return nd;
+}
+
 int fsgm_dirsplit_plan(int width, int height, int dMax, int paths, int P1, int P2, int rank, int world, fsgm_dirsplit_info* out)
 {
     if (!out || width < 1 || height < 1 || dMax < 1 || (paths != 4 && paths != 8) || world < 1 || rank < 0 || rank >= world) return FSGM_ERR_ARG;
@@ -208,7 +235,7 @@ int fsgm_dirsplit_plan(int width, int height, int dMax, int paths, int P1, int P
     out->padded_pixels = slab * world;
     fsgm_epi_opts o; fsgm_epi_opts_default(&o); o.paths = paths;
     int dirs[8];
-    const int nd = enabled_dirs(o, dirs);
+    const int nd = split_order(o, dirs);
     out->n_dirs = 0;
     for (int k = rank; k < nd; k += world) out->dirs[out->n_dirs++] = dirs[k];
     const int k_max = (nd + world - 1) / world;         // most directions any rank owns
@@ -301,7 +328,7 @@ int fsgm_calc_cost_sgm_dirsplit_dev(fsgm_ctx* c, const uint8_t* d_I1, const uint
     int my[8], nmy = 0;
     {
         int dirs[8];
-        const int nd = enabled_dirs(o, dirs);
+        const int nd = split_order(o, dirs);
         for (int k = rank; k < nd; k += world) my[nmy++] = dirs[k];
     }
     const bool adaptive = o.adaptive_p2 != 0;
@@ -309,6 +336,7 @@ int fsgm_calc_cost_sgm_dirsplit_dev(fsgm_ctx* c, const uint8_t* d_I1, const uint
     const size_t slab = plan.slab_pixels, npad = plan.padded_pixels, cnt = plan.n_pixels;
     const bool fused_cost = (D == 64 || D == 128 || D == 256);
     size_t need = 2 * align256(N * 4) + align256((size_t)D * 8) + (fused_cost ? 1 : 2) * align256(V) + 4 * align256(npad * 4) + 4096;
+    need += (size_t)(3 + 2 * world) * align256(((size_t)8 * W + 1) * (((size_t)(H + 7) / 8 + world - 1) / world) * 8);   // striped peer-store form
     if (u8x) need += 2 * align256(npad * D) + (size_t)std::max(0, nmy - 1) * align256(V);
     else need += (size_t)std::max(1, nmy) * align256(V) + align256(npad * D * 2) + align256(slab * D * 2) + 2 * align256(N * 4);
     FSGM_TRY(arena_reserve(c, need));
@@ -338,25 +366,48 @@ int fsgm_calc_cost_sgm_dirsplit_dev(fsgm_ctx* c, const uint8_t* d_I1, const uint
     int all_dirs[8];
     const int nd_all = enabled_dirs(o, all_dirs);
     bool scatter = !adaptive && !sweep_needs_wrap(P1, P2, 24) && D % 16 == 0;
-    if (scatter) FSGM_TRY(p2p_ensure(c, a, (size_t)nd_all * slab * D, &scatter));
+    // peer-store form: stripes of 8 image rows dealt round-robin to the ranks
+    constexpr int STRIPE_ROWS = 8;
+    const size_t sp = (size_t)STRIPE_ROWS * W, chunk = sp + 1;
+    const size_t nls = ((size_t)(H + STRIPE_ROWS - 1) / STRIPE_ROWS + world - 1) / world, LP = nls * chunk;
+    if (scatter) FSGM_TRY(p2p_ensure(c, a, (size_t)nd_all * LP * D, &scatter));
     if (scatter) {
-        // ---- peer-store form: the sweeps write every L row into its slab owner's buffer; no exchange step -------------------------
+        // ---- the sweeps write every L row into its stripe owner's buffer; no exchange step ------------------------------------------
+        double* localO; uint32_t *locB, *locM, *gatB, *gatM;
+        FSGM_TRY(arena_get(c, LP, &localO));
+        FSGM_TRY(arena_get(c, LP, &locB));
+        FSGM_TRY(arena_get(c, LP, &locM));
+        FSGM_TRY(arena_get(c, LP * world, &gatB));
+        FSGM_TRY(arena_get(c, LP * world, &gatM));
         int slots[8];
-        for (int i = 0; i < nmy; ++i) slots[i] = rank + i * world;           // position of my i-th direction in the enabled list
+        for (int i = 0; i < nmy; ++i) slots[i] = rank + i * world;           // position of my i-th direction in the dealt order
         uint8_t* peers[16];
         for (int j = 0; j < world; ++j) peers[j] = static_cast<uint8_t*>(c->p2p_peer[j]);
-        if (nmy) FSGM_TRY(launch_sweeps_scatter(c, C, W, H, D, P1, P2, my, slots, nmy, peers, world, slab));
+        {
+            // the pixel after the last one reads as zero (the reference reads past its buffer there): nobody writes that row
+            const size_t j = (N - 1) / sp;
+            if ((int)(j % world) == rank)
+                for (int k = 0; k < nd_all; ++k)
+                    FSGM_CUDA(c, cudaMemsetAsync(static_cast<uint8_t*>(c->p2p_local) + ((size_t)k * LP + (j / world) * chunk + (N - j * sp)) * D, 0, D, c->stream));
+        }
+        if (nmy) FSGM_TRY(launch_sweeps_scatter(c, C, W, H, D, P1, P2, my, slots, nmy, peers, world, sp, LP));
         {
             StageScope ss(c, ST_EXCHANGE);
             // every rank's stores have landed once every rank has passed this point (kernel completion makes them visible)
             FSGM_NCCL(c, a->AllGather(firsts, firsts + 1, 1, ncclUint32, comm, c->stream));
-            if (rank + 1 < world) {
-                first_voxel_peer_kernel<<<1, 1, 0, c->stream>>>(peers[rank + 1], nd_all, slab * D, firsts + 1 + rank + 1);
-                FSGM_LAUNCHED(c);
-            }
+            stripe_gather_f64_kernel<<<(unsigned)((LP + 255) / 256), 256, 0, c->stream>>>(d_O, N, (unsigned)sp, rank, world, LP, localO);
+            FSGM_LAUNCHED(c);
         }
-        if (cnt) FSGM_TRY(launch_slab_wta(c, static_cast<const uint8_t*>(c->p2p_local), nd_all, slab * D, next0, cnt, D, o.subpixel,
-                                          o.vz_to_disp, d_O + plan.first_pixel, vMax, slabB, slabM));
+        FSGM_TRY(launch_slab_wta(c, static_cast<const uint8_t*>(c->p2p_local), nd_all, LP * D, nullptr, LP, D, o.subpixel,
+                                 o.vz_to_disp, localO, vMax, locB, locM));
+        {
+            StageScope ss(c, ST_EXCHANGE);
+            FSGM_NCCL(c, a->AllGather(locB, gatB, LP, ncclUint32, comm, c->stream));
+            FSGM_NCCL(c, a->AllGather(locM, gatM, LP, ncclUint32, comm, c->stream));
+            stripe_scatter_u32_kernel<<<(unsigned)((N + 255) / 256), 256, 0, c->stream>>>(gatB, gatM, N, (unsigned)sp, world, LP, d_bestD, d_minC);
+            FSGM_LAUNCHED(c);
+        }
+        return FSGM_OK;
     } else if (u8x) {
         // ---- this rank's directions summed into one u8 volume, exchanged slab-wise, summed inside the WTA kernel -------------------
         uint8_t *part, *recv, *L[8];

@@ -135,7 +135,7 @@ int launch_sweeps(fsgm_ctx* c, int n, const uint8_t* C, const uint8_t* I1, int W
                   int P1, int P2, int adaptive_thr, int cmax, const int* dirs, int n_dirs, uint8_t* const* Lvols);
 bool sweep_needs_wrap(int P1, int P2, int cmax);
 int launch_sweeps_scatter(fsgm_ctx* c, const uint8_t* C, int W, int H, int D, int P1, int P2, const int* dirs, const int* slots,
-                          int n_dirs, uint8_t* const* peer, int world, size_t slab_pixels);
+                          int n_dirs, uint8_t* const* peer, int world, size_t stripe_pixels, size_t local_pixels);
 // sum of n_dirs L volumes -> WTA -> subpixel -> (optionally) vz->disparity; Sp16 (u16 [n][N][D]) may be null
 int launch_epi_wta(fsgm_ctx* c, int n, uint8_t* const* Lvols, int n_dirs, int W, int H, int D, int subpixel,
                    int vz_to_disp, const double* O, double vMax, uint16_t* Sp16, uint32_t* bestD, uint32_t* minC);
