@@ -689,6 +689,10 @@ def run_ours(args):
     ceil = min(h2d) * 1e9 / (W * H * 42) * env.world
     line["e2e"]["h2d_ceiling_pairs_per_s"] = ceil
     line["e2e"]["frac_of_h2d_ceiling"] = line["e2e"]["value"] / ceil
+    # the same with the 8 B/px download counted on the same host fabric (what the 8-GPU box shows: uploads and downloads add up)
+    ceil2 = env.world / (W * H * 42 / (min(h2d) * 1e9) + W * H * 8 / (min(d2h) * 1e9))
+    line["e2e"]["h2d_plus_d2h_ceiling_pairs_per_s"] = ceil2
+    line["e2e"]["frac_of_h2d_plus_d2h_ceiling"] = line["e2e"]["value"] / ceil2
     wl = {}
     if env.world == 1:
         for name, fn in (("A", workload_A), ("C", workload_C), ("D", workload_D)):
