@@ -50,7 +50,15 @@ __device__ __forceinline__ uint4 pl_ldg128(const void* p)
     uint4 v; asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p)); return v;
 }
 __device__ __forceinline__ uint32_t pl_ldg32(const void* p) { uint32_t v; asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
-__device__ __forceinline__ void pl_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ uint4 pl_lds128(uint32_t a)
+{
+    uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v;
+}
+// asynchronous global -> shared copies (LDGSTS): no register, no scoreboard; one wait per step
+__device__ __forceinline__ void pl_cp16(uint32_t dst, const void* src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory"); }
+__device__ __forceinline__ void pl_cp4(uint32_t dst, const void* src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory"); }
+__device__ __forceinline__ void pl_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void pl_cp_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ uint32_t pl_min3(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_u16x2(a, b, c); }
 
 __device__ __forceinline__ int pl_x86_d2i(double v)
@@ -92,12 +100,12 @@ __device__ __noinline__ uint32_t pl_generic_step(uint32_t src_s, uint32_t dst_s,
 }
 
 template <int SX>
-__global__ void __launch_bounds__(PL_WARPS * 32, 3)
+__global__ void __launch_bounds__(PL_WARPS * 32, 2)
 pydl_sweep_kernel(const PlParams prm)
 {
     constexpr int STW = (SX + 1) * 4;                       // words of one state buffer: SX label columns + one all-255 column
     constexpr int WW = 4 + STW + 8 + STW + 8;               // slack | buffer 0 | slack | buffer 1 | slack (shifted reads overrun a column)
-    extern __shared__ uint32_t pl_smem[];
+    extern __shared__ __align__(128) uint32_t pl_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     // blocks are numbered scanline-chunk-major, pair-minor: the long horizontal sweeps of EVERY pair are scheduled first
     const int pair = blockIdx.x % prm.n_pairs;
@@ -118,9 +126,12 @@ pydl_sweep_kernel(const PlParams prm)
     const uint8_t* __restrict__ Ib = prm.I1 + (size_t)pair * N;
     const size_t colstride = (size_t)W * 16;
 
-    const uint32_t st_s = (uint32_t)__cvta_generic_to_shared(pl_smem + (size_t)wib * (WW * 32) + lane);
+    // per warp: WW state words x 32 lanes | cost-column stage [2][SX][32 lanes][16 B] | descriptor stage [2][32 lanes]
+    constexpr int PW = WW * 32 + 2 * SX * 128 + 64;         // words per warp
+    const uint32_t warp_s = (uint32_t)__cvta_generic_to_shared(pl_smem + (size_t)wib * PW);
+    const uint32_t st_s = warp_s + lane * 4;
     for (int w = 0; w < WW; ++w) pl_sts32(st_s + w * 128, 0xFFFFFFFFu);         // lane-private words: no synchronisation needed
-    const uint32_t buf_s[2] = {st_s + 4 * 128, st_s + (4 + STW + 8) * 128};
+    const uint32_t cst_s = warp_s + WW * 128 + lane * 16, dst_stage_s = warp_s + WW * 128 + 2 * SX * 512 + lane * 4;
 
     // pad bytes of a frame (rows outside [0, Sy)) and the per-register row masks
     uint32_t padw[4];
@@ -138,20 +149,26 @@ pydl_sweep_kernel(const PlParams prm)
     else         { x = line; y = dy > 0 ? 0 : H - 1; }
     uint32_t M = 0;
     int cur = 0;
-    uint32_t dnext = 0;
     int iprev = 0;
     uint32_t ppix = 0;
+    // a step's cost columns and descriptor are copied into the stage asynchronously during the step before it
+    auto request = [&](int px_, int py_, int slot) {
+        const uint8_t* cn = Cb + ((size_t)((uint32_t)py_ * (uint32_t)SX) * W + px_) * 16;
+#pragma unroll
+        for (int cc = 0; cc < SX; ++cc) pl_cp16(cst_s + (uint32_t)((slot * SX + cc) * 512), cn + (size_t)cc * colstride);
+        pl_cp4(dst_stage_s + (uint32_t)(slot * 128), desc + (uint32_t)py_ * (uint32_t)W + (uint32_t)px_);
+        pl_cp_commit();
+    };
+    request(x, y, 0);
 
     for (int t = 0; t < len; ++t) {
         const uint32_t pix = (uint32_t)y * (uint32_t)W + (uint32_t)x;
         const bool start = (t == 0) || (dy != 0 && dx != 0 && x == (dx > 0 ? 0 : W - 1));
-        const uint32_t d = start ? 0u : dnext;
-        // next position and its descriptor
+        pl_cp_wait();
+        const uint32_t d = start ? 0u : pl_lds32(dst_stage_s + (uint32_t)((t & 1) * 128));
         int nx = x + dx, ny = y + dy;
         if (dy != 0) nx = nx < 0 ? W - 1 : (nx >= W ? 0 : nx);
-        if (t + 1 < len) {
-            dnext = pl_ldg32(desc + (uint32_t)ny * (uint32_t)W + (uint32_t)nx);
-        }
+        if (t + 1 < len) request(nx, ny, (t + 1) & 1);
         int P2 = prm.P2;
         if (prm.adaptive) {
             const int icur = Ib[pix];
@@ -182,23 +199,35 @@ pydl_sweep_kernel(const PlParams prm)
 #pragma unroll
         for (int i = 0; i < 5; ++i) dm[i] = (2 * i < ty ? 0xFFFFu : 0u) | (2 * i + 1 < ty ? 0xFFFF0000u : 0u);
 
-        const uint32_t src_s = buf_s[cur ^ 1] + (uint32_t)(q * 128), dst_s = buf_s[cur];
+        const uint32_t src0_s = st_s + (uint32_t)((4 + (cur ^ 1) * (STW + 8)) * 128), dst_s = st_s + (uint32_t)((4 + cur * (STW + 8)) * 128);
+        const uint32_t src_s = src0_s + (uint32_t)(q * 128);
+        const uint32_t ccol_s = cst_s + (uint32_t)((t & 1) * SX * 512);
         const uint8_t* cpix = Cb + ((size_t)((uint32_t)y * (uint32_t)SX) * W + x) * 16;
         uint8_t* lpix = Lb + ((size_t)((uint32_t)y * (uint32_t)SX) * W + x) * 16;
 
         uint32_t Y[5][6], EC[3][6], bprev[6];
-        uint4 cq[3];
         uint32_t mm = 0xFFFFFFFFu;
 #pragma unroll
         for (int i = 0; i < 6; ++i) bprev[i] = 0;
+        // the five words of a source column are requested two iterations before they are used (and so, in program order, before
+        // the stores of the columns finished in between: the hardware keeps shared-memory accesses of a thread in order)
+        uint32_t wq[3][5];
+        uint4 cnext = make_uint4(0, 0, 0, 0);
+        auto fetch = [&](int it_) {
+            const int cp_ = SX + 1 - it_;
+            const uint32_t ce = min((uint32_t)(cp_ + kx), (uint32_t)SX);
+            const uint32_t a = src_s + ce * 512u;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) wq[it_ % 3][j] = pl_lds32(a + 128 * j);
+        };
+        fetch(0); fetch(1);
 #pragma unroll
         for (int it = 0; it < SX + 4; ++it) {
             const int cp = SX + 1 - it;                                 // shifted-grid column whose y-window minima are built now
+            if (it + 2 < SX + 4) fetch(it + 2);
             // ---- source column cp + kx (anything outside the window: the all-255 column), shifted by ky rows --------------------
             {
-                const uint32_t ce = min((uint32_t)(cp + kx), (uint32_t)SX);
-                const uint32_t a = src_s + ce * 512u;
-                const uint32_t w0 = pl_lds32(a), w1 = pl_lds32(a + 128), w2 = pl_lds32(a + 256), w3 = pl_lds32(a + 384), w4 = pl_lds32(a + 512);
+                const uint32_t w0 = wq[it % 3][0], w1 = wq[it % 3][1], w2 = wq[it % 3][2], w3 = wq[it % 3][3], w4 = wq[it % 3][4];
                 const uint32_t b0 = __funnelshift_r(w0, w1, rr8) | mk[0], b1 = __funnelshift_r(w1, w2, rr8) | mk[1],
                                b2 = __funnelshift_r(w2, w3, rr8) | mk[2], b3 = __funnelshift_r(w3, w4, rr8) | mk[3];
                 uint32_t E[8], O[7];                                    // E[i]: rows (2i-2, 2i-1); O[i]: rows (2i-1, 2i)
@@ -215,12 +244,11 @@ pydl_sweep_kernel(const PlParams prm)
                     EC[(cp + 2) % 3][i] = E[i + 1];
                 }
             }
-            // ---- cost column, requested three iterations ahead of its use ---------------------------------------------------------
             const int c = cp + 2;                                       // output column of this iteration
-            uint4 ccol = make_uint4(0, 0, 0, 0);
-            if (c >= 0 && c < SX) ccol = cq[it % 3];
-            if (it >= 1 && SX - it >= 0) cq[it % 3] = pl_ldg128(cpix + (size_t)(SX - it) * colstride);
+            if (c == SX) cnext = pl_lds128(ccol_s + (uint32_t)((SX - 1) * 512));   // first cost column
             if (c >= 0 && c < SX) {
+                const uint4 ccol = cnext;
+                if (c >= 1) cnext = pl_lds128(ccol_s + (uint32_t)((c - 1) * 512));
                 uint32_t bst[6];
 #pragma unroll
                 for (int i = 0; i < 6; ++i) {
@@ -263,7 +291,7 @@ pydl_sweep_kernel(const PlParams prm)
                 const uint32_t py = ppix / (uint32_t)W, px = ppix - py * (uint32_t)W;
                 const double ddx = __dsub_rn(mvx[(size_t)y * prm.mvW + x], mvx[(size_t)py * prm.mvW + px]);
                 const double ddy = __dsub_rn(mvy[(size_t)y * prm.mvW + x], mvy[(size_t)py * prm.mvW + px]);
-                m = pl_generic_step(buf_s[cur ^ 1], dst_s, cpix, lpix, colstride, SX, Sy, ddx, ddy, M, prm.P1, P2, active);
+                m = pl_generic_step(src0_s, dst_s, cpix, lpix, colstride, SX, Sy, ddx, ddy, M, prm.P1, P2, active);
             }
         }
         M = start ? 0u : m;
@@ -435,7 +463,7 @@ int launch_pydl_desc(fsgm_ctx* c, int n, const double* preMv, int mvW, int mvH, 
 template <int SX>
 static int pl_launch_sweep(fsgm_ctx* c, const PlParams& p, dim3 grid)
 {
-    constexpr size_t smem = (size_t)PL_WARPS * (4 + 2 * ((SX + 1) * 4) + 16) * 128;
+    constexpr size_t smem = (size_t)PL_WARPS * ((4 + 2 * ((SX + 1) * 4) + 16) * 32 + 2 * SX * 128 + 64) * 4;
     auto kern = pydl_sweep_kernel<SX>;
     FSGM_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, PL_WARPS * 32, smem, c->stream>>>(p);
