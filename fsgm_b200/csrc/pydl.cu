@@ -25,7 +25,11 @@
 
 namespace fsgm {
 
-constexpr int PL_WARPS = 4;
+constexpr int PL_WARPS = 2;                 // warps are independent; the block size only sets the shared-memory granularity (8 warps per SM)
+#ifndef FSGM_PL_DUP_ALWAYS
+#define FSGM_PL_DUP_ALWAYS 0
+#endif
+constexpr bool PL_DUP_ALWAYS = FSGM_PL_DUP_ALWAYS != 0;   // 1: the truncation-duplicate selects run unconditionally (straight-line step)
 
 struct PlParams {
     const uint8_t* C;
@@ -100,11 +104,12 @@ __device__ __noinline__ uint32_t pl_generic_step(uint32_t src_s, uint32_t dst_s,
 }
 
 template <int SX>
-__global__ void __launch_bounds__(PL_WARPS * 32, 2)
+__global__ void __launch_bounds__(PL_WARPS * 32, 4)
 pydl_sweep_kernel(const PlParams prm)
 {
     constexpr int STW = (SX + 1) * 4;                       // words of one state buffer: SX label columns + one all-255 column
-    constexpr int WW = 4 + STW + 8 + STW + 8;               // slack | buffer 0 | slack | buffer 1 | slack (shifted reads overrun a column)
+    constexpr int WW = 4 + STW + STW + 8;                   // slack | buffer 0 | buffer 1 | slack: a shifted read overruns its column by up to 4 words
+                                                            // in front and 8 behind; between the buffers it lands in the other buffer (masked bytes)
     extern __shared__ __align__(128) uint32_t pl_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     // blocks are numbered scanline-chunk-major, pair-minor: the long horizontal sweeps of EVERY pair are scheduled first
@@ -126,12 +131,12 @@ pydl_sweep_kernel(const PlParams prm)
     const uint8_t* __restrict__ Ib = prm.I1 + (size_t)pair * N;
     const size_t colstride = (size_t)W * 16;
 
-    // per warp: WW state words x 32 lanes | cost-column stage [2][SX][32 lanes][16 B] | descriptor stage [2][32 lanes]
-    constexpr int PW = WW * 32 + 2 * SX * 128 + 64;         // words per warp
+    // per warp: WW state words x 32 lanes | cost-column stage [SX][32 lanes][16 B] | descriptor stage [2][32 lanes]
+    constexpr int PW = WW * 32 + SX * 128 + 64;             // words per warp
     const uint32_t warp_s = (uint32_t)__cvta_generic_to_shared(pl_smem + (size_t)wib * PW);
     const uint32_t st_s = warp_s + lane * 4;
     for (int w = 0; w < WW; ++w) pl_sts32(st_s + w * 128, 0xFFFFFFFFu);         // lane-private words: no synchronisation needed
-    const uint32_t cst_s = warp_s + WW * 128 + lane * 16, dst_stage_s = warp_s + WW * 128 + 2 * SX * 512 + lane * 4;
+    const uint32_t cst_s = warp_s + WW * 128 + lane * 16, dst_stage_s = warp_s + WW * 128 + SX * 512 + lane * 4;
 
     // pad bytes of a frame (rows outside [0, Sy)) and the per-register row masks
     uint32_t padw[4];
@@ -151,24 +156,26 @@ pydl_sweep_kernel(const PlParams prm)
     int cur = 0;
     int iprev = 0;
     uint32_t ppix = 0;
-    // a step's cost columns and descriptor are copied into the stage asynchronously during the step before it
-    auto request = [&](int px_, int py_, int slot) {
-        const uint8_t* cn = Cb + ((size_t)((uint32_t)py_ * (uint32_t)SX) * W + px_) * 16;
+    // A step's cost columns and descriptor are copied into the stage asynchronously (LDGSTS) during the step before it: the slot
+    // of cost column c is requested again right after the step has read it, one commit group per column, so that at every read
+    // exactly SX - 1 younger groups may still be in flight (cp.async.wait_group SX-1).  The descriptor rides with column SX-1.
+    {
+        const uint8_t* cn = Cb + ((size_t)((uint32_t)y * (uint32_t)SX) * W + x) * 16;
 #pragma unroll
-        for (int cc = 0; cc < SX; ++cc) pl_cp16(cst_s + (uint32_t)((slot * SX + cc) * 512), cn + (size_t)cc * colstride);
-        pl_cp4(dst_stage_s + (uint32_t)(slot * 128), desc + (uint32_t)py_ * (uint32_t)W + (uint32_t)px_);
-        pl_cp_commit();
-    };
-    request(x, y, 0);
+        for (int cc = SX - 1; cc >= 0; --cc) { pl_cp16(cst_s + (uint32_t)(cc * 512), cn + (size_t)cc * colstride); pl_cp_commit(); }
+    }
 
     for (int t = 0; t < len; ++t) {
         const uint32_t pix = (uint32_t)y * (uint32_t)W + (uint32_t)x;
         const bool start = (t == 0) || (dy != 0 && dx != 0 && x == (dx > 0 ? 0 : W - 1));
-        pl_cp_wait();
+        // the descriptor of this step arrived with the first cost column of the previous step's requests
+        asm volatile("cp.async.wait_group %0;" ::"n"(SX - 1) : "memory");
         const uint32_t d = start ? 0u : pl_lds32(dst_stage_s + (uint32_t)((t & 1) * 128));
         int nx = x + dx, ny = y + dy;
         if (dy != 0) nx = nx < 0 ? W - 1 : (nx >= W ? 0 : nx);
-        if (t + 1 < len) request(nx, ny, (t + 1) & 1);
+        const bool more = t + 1 < len;
+        const uint8_t* cnx = Cb + ((size_t)((uint32_t)(more ? ny : y) * (uint32_t)SX) * W + (more ? nx : x)) * 16;
+        const uint32_t* dnx = desc + (uint32_t)(more ? ny : y) * (uint32_t)W + (uint32_t)(more ? nx : x);
         int P2 = prm.P2;
         if (prm.adaptive) {
             const int icur = Ib[pix];
@@ -199,9 +206,9 @@ pydl_sweep_kernel(const PlParams prm)
 #pragma unroll
         for (int i = 0; i < 5; ++i) dm[i] = (2 * i < ty ? 0xFFFFu : 0u) | (2 * i + 1 < ty ? 0xFFFF0000u : 0u);
 
-        const uint32_t src0_s = st_s + (uint32_t)((4 + (cur ^ 1) * (STW + 8)) * 128), dst_s = st_s + (uint32_t)((4 + cur * (STW + 8)) * 128);
+        const uint32_t src0_s = st_s + (uint32_t)((4 + (cur ^ 1) * STW) * 128), dst_s = st_s + (uint32_t)((4 + cur * STW) * 128);
         const uint32_t src_s = src0_s + (uint32_t)(q * 128);
-        const uint32_t ccol_s = cst_s + (uint32_t)((t & 1) * SX * 512);
+        const uint32_t ccol_s = cst_s;
         const uint8_t* cpix = Cb + ((size_t)((uint32_t)y * (uint32_t)SX) * W + x) * 16;
         uint8_t* lpix = Lb + ((size_t)((uint32_t)y * (uint32_t)SX) * W + x) * 16;
 
@@ -212,7 +219,7 @@ pydl_sweep_kernel(const PlParams prm)
         // the five words of a source column are requested two iterations before they are used (and so, in program order, before
         // the stores of the columns finished in between: the hardware keeps shared-memory accesses of a thread in order)
         uint32_t wq[3][5];
-        uint4 cnext = make_uint4(0, 0, 0, 0);
+        uint4 cnext = make_uint4(0, 0, 0, 0), ccur = cnext;
         auto fetch = [&](int it_) {
             const int cp_ = SX + 1 - it_;
             const uint32_t ce = min((uint32_t)(cp_ + kx), (uint32_t)SX);
@@ -245,17 +252,25 @@ pydl_sweep_kernel(const PlParams prm)
                 }
             }
             const int c = cp + 2;                                       // output column of this iteration
-            if (c == SX) cnext = pl_lds128(ccol_s + (uint32_t)((SX - 1) * 512));   // first cost column
+            // cost column c - 1 is read one iteration ahead; its slot is then requested for the next step (the last step re-requests
+            // its own columns: harmless, and the group count stays uniform)
+            if (c >= 1 && c <= SX) {
+                if (c < SX) asm volatile("cp.async.wait_group %0;" ::"n"(SX - 1) : "memory");
+                ccur = cnext;
+                cnext = pl_lds128(ccol_s + (uint32_t)((c - 1) * 512));
+                pl_cp16(ccol_s + (uint32_t)((c - 1) * 512), cnx + (size_t)(c - 1) * colstride);
+                if (c == SX) pl_cp4(dst_stage_s + (uint32_t)(((t + 1) & 1) * 128), dnx);
+                pl_cp_commit();
+            } else if (c == 0) ccur = cnext;
             if (c >= 0 && c < SX) {
-                const uint4 ccol = cnext;
-                if (c >= 1) cnext = pl_lds128(ccol_s + (uint32_t)((c - 1) * 512));
+                const uint4 ccol = ccur;
                 uint32_t bst[6];
 #pragma unroll
                 for (int i = 0; i < 6; ++i) {
                     const uint32_t xm = pl_min3(pl_min3(Y[0][i], Y[1][i], Y[2][i]), Y[3][i], Y[4][i]);
                     bst[i] = pl_min3(far2, xm + P1P1, EC[(cp + 4) % 3][i]);
                 }
-                if (anydup) {
+                if (PL_DUP_ALWAYS || anydup) {
                     // rows below ty take the next row's value, columns below tx the next column's (truncation toward zero)
 #pragma unroll
                     for (int i = 0; i < 5; ++i) {
@@ -299,6 +314,7 @@ pydl_sweep_kernel(const PlParams prm)
         ppix = pix;
         x = nx; y = ny;
     }
+    pl_cp_wait();
 }
 
 // ---- shift descriptors ---------------------------------------------------------------------------------------------------------
@@ -463,7 +479,7 @@ int launch_pydl_desc(fsgm_ctx* c, int n, const double* preMv, int mvW, int mvH, 
 template <int SX>
 static int pl_launch_sweep(fsgm_ctx* c, const PlParams& p, dim3 grid)
 {
-    constexpr size_t smem = (size_t)PL_WARPS * ((4 + 2 * ((SX + 1) * 4) + 16) * 32 + 2 * SX * 128 + 64) * 4;
+    constexpr size_t smem = (size_t)PL_WARPS * ((4 + 2 * ((SX + 1) * 4) + 8) * 32 + SX * 128 + 64) * 4;
     auto kern = pydl_sweep_kernel<SX>;
     FSGM_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, PL_WARPS * 32, smem, c->stream>>>(p);
