@@ -101,6 +101,8 @@ __global__ void __launch_bounds__(NG_WARPS * 32)
 pydng_sweep_kernel(const NgSweepParams prm)
 {
     __shared__ int ex[NG_WARPS][2][NJ * 32], ey[NG_WARPS][2][NJ * 32], lc[NG_WARPS][2][NJ * 32];
+    __shared__ uchar4 gr4[NG_WARPS][9 * 6];          // S == 3: row-interval minima (rows 0, 1, 2) of the previous pixel's nine candidate grids
+    __shared__ int4 gm[NG_WARPS][9];                 //         smallest P1 term, its cell, second smallest
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int gw = blockIdx.x * NG_WARPS + wib;
     if (gw >= prm.line_start[prm.n_dirs]) return;
@@ -150,6 +152,71 @@ pydng_sweep_kernel(const NgSweepParams prm)
             uint32_t same[NJ], near_[NJ];
 #pragma unroll
             for (int j = 0; j < NJ; ++j) { same[j] = far_; near_[j] = far_; }
+            // S == 3: the previous pixel's candidates are nine 3 x 3 grids of consecutive flow vectors (when (int)(mv + off) has
+            // no duplicate at zero: checked).  For a candidate (mx, my) and a grid with corner (X0, Y0) the cell of EQUAL flow is
+            // (ex, ey) = (mx - X0, my - Y0) and the cells within +-2 are the x-interval [ex-2, ex+2] x the y-interval, clipped to
+            // the grid — the whole grid whenever the equal cell lies inside it.  So per grid: the smallest and second-smallest
+            // P1 term with the position of the smallest (equal cell inside: the minimum over the grid WITHOUT that cell), and
+            // the minima over the six x-intervals per grid row (equal cell outside: at most three of them).  9 grid queries per
+            // candidate instead of 81 cell tests.
+            bool grid_ok = false;
+            if (S == 3) {
+                bool reg = true;
+                if (lane < 9) {
+                    const int b = lane * 9;
+                    reg = exp_[b + 3] == exp_[b] + 1 && exp_[b + 6] == exp_[b] + 2 && eyp[b + 1] == eyp[b] + 1 && eyp[b + 2] == eyp[b] + 2;
+                }
+                grid_ok = __all_sync(0xffffffffu, reg);
+            }
+            if (grid_ok) {
+                // row-interval minima: entry (h, xi, oy), x-intervals [0,0] [0,1] [0,2] [1,1] [1,2] [2,2]
+                for (int e = lane; e < 9 * 6; e += 32) {
+                    const int h = e / 6, xi = e - h * 6;
+                    const int a = xi < 3 ? 0 : xi < 5 ? 1 : 2, bnd = xi == 0 ? 0 : (xi == 1 || xi == 3) ? 1 : 2;
+                    uint32_t v[3] = {255, 255, 255};
+                    for (int ox = a; ox <= bnd; ++ox)
+#pragma unroll
+                        for (int oy = 0; oy < 3; ++oy) v[oy] = min(v[oy], ((uint32_t)lcp[h * 9 + ox * 3 + oy] + (uint32_t)prm.P1) & 0xFFu);
+                    gr4[wib][e] = make_uchar4((unsigned char)v[0], (unsigned char)v[1], (unsigned char)v[2], 255);
+                }
+                if (lane < 9) {
+                    uint32_t k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
+                    for (int cidx = 0; cidx < 9; ++cidx) {
+                        const uint32_t key = ((((uint32_t)lcp[lane * 9 + cidx] + (uint32_t)prm.P1) & 0xFFu) << 8) | (uint32_t)cidx;
+                        if (key < k1) { k2 = k1; k1 = key; } else if (key < k2) k2 = key;
+                    }
+                    gm[wib][lane] = make_int4((int)(k1 >> 8), (int)(k1 & 0xFFu), (int)(k2 >> 8), 0);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    for (int h = 0; h < 9; ++h) {
+                        const int ex = mx[j] - exp_[h * 9], ey = my[j] - eyp[h * 9];
+                        const uint32_t ux = (uint32_t)(ex + 2), uy = (uint32_t)(ey + 2);
+                        // warp-uniform branches only: a form is evaluated when some lane needs it, and selected per lane
+                        const bool valid = ux <= 6u && uy <= 6u;             // something of this grid within +-2
+                        const bool inside = valid && ux - 2u <= 2u && uy - 2u <= 2u;   // the cell of equal flow lies in the grid
+                        if (!__any_sync(0xffffffffu, valid)) continue;
+                        if (__any_sync(0xffffffffu, inside)) {
+                            const int cell = inside ? ex * 3 + ey : 0;
+                            const int4 g = gm[wib][h];
+                            const uint32_t cs = (uint32_t)lcp[h * 9 + cell] & 0xFFu;
+                            const uint32_t nin = (uint32_t)(cell == g.y ? g.z : g.x);
+                            same[j] = inside ? cs : same[j];                 // later grids overwrite: the last match wins (:62-63)
+                            near_[j] = min(near_[j], inside ? nin : 255u);
+                        }
+                        if (__any_sync(0xffffffffu, valid && !inside)) {
+                            const int xi = ux == 0 ? 0 : ux == 1 ? 1 : ux <= 4 ? 2 : ux == 5 ? 4 : 5;
+                            const uint32_t rw = (valid && !inside) ? *reinterpret_cast<const uint32_t*>(&gr4[wib][h * 6 + xi]) : 0xFFFFFFFFu;
+                            // rows [uy-4, uy] of the three: drop row 0 when uy > 4, row 1 when uy > 5 or uy < 1, row 2 when uy < 2
+                            const uint32_t r0 = uy <= 4u ? (rw & 0xFFu) : 255u;
+                            const uint32_t r1 = (uy >= 1u && uy <= 5u) ? ((rw >> 8) & 0xFFu) : 255u;
+                            const uint32_t r2 = uy >= 2u ? ((rw >> 16) & 0xFFu) : 255u;
+                            near_[j] = min(near_[j], min(min(r0, r1), r2));
+                        }
+                    }
+                }
+            } else
             for (int d2 = 0; d2 < D; ++d2) {
                 const int ax = exp_[d2], ay = eyp[d2];
                 const uint32_t c2 = (uint32_t)lcp[d2];
