@@ -286,6 +286,10 @@ ng_pipe_kernel(const NgParams prm)
     __shared__ int cmx[2][NGD], cmy[2][NGD], ccost[2][NGD];   // candidates of pixel p (parity p&1) and p+1
     __shared__ int Lc[4][NGD];
     __shared__ int4 pent[4][NGD];                             // predecessor entries of the pixel being stepped
+    // per predecessor and 3x3 candidate grid (12 per predecessor): minima of the P1 term over the six x-intervals, rows 0..2
+    // (byte 3 = 255), and the smallest / its cell / the second smallest over the whole grid
+    __shared__ uint32_t gr4[4][12 * 6];
+    __shared__ int4 gm[4][12];
     __shared__ Top2 top1[2];
     __shared__ Top2 hint[2][3];                               // stale ring slots of L2,L3,L4 for pixel q (parity q&1)
     __shared__ int preMin[4];
@@ -382,6 +386,36 @@ ng_pipe_kernel(const NgParams prm)
             if (tid >= 352 && tid < 377) pf_c1 = load_c1(p2, tid - 352);
         }
         if (warp < 14) {
+            // A predecessor's 108 entries are twelve 3 x 3 grids of consecutive flow vectors (hint + offset, offy outer).  For a
+            // candidate (mx, my) and a grid with corner (X0, Y0) the cell of EQUAL flow is (ex, ey) = (mx - X0, my - Y0); the cells
+            // within +-2 (the P1 term, :73-74) are [ex-2, ex+2] x [ey-2, ey+2] clipped to the grid — the whole grid minus the equal
+            // cell when that cell lies inside, a rectangle that touches a grid edge otherwise.  So: per grid the smallest / second
+            // smallest P1 term with the cell of the smallest, and row-wise minima over the six x-intervals; 12 grid queries per
+            // candidate and direction instead of 108 entry tests.  Values are the reference's own per-entry terms
+            // ((cost + P1) & 255, cost & 255), so no parameter domain is excluded.
+            if (tid < 288) {
+                const int dir = tid / 72, rem = tid - dir * 72, g = rem / 6, xi = rem - g * 6;
+                const int a = xi < 3 ? 0 : xi < 5 ? 1 : 2, b = xi == 0 ? 0 : (xi == 1 || xi == 3) ? 1 : 2;
+                const int4* e = pent[dir] + g * 9;
+                uint32_t v0 = 255, v1 = 255, v2 = 255;
+                for (int cx = a; cx <= b; ++cx) {
+                    v0 = min(v0, ((uint32_t)e[cx].z + (uint32_t)prm.P1) & 0xFFu);
+                    v1 = min(v1, ((uint32_t)e[3 + cx].z + (uint32_t)prm.P1) & 0xFFu);
+                    v2 = min(v2, ((uint32_t)e[6 + cx].z + (uint32_t)prm.P1) & 0xFFu);
+                }
+                gr4[dir][g * 6 + xi] = v0 | (v1 << 8) | (v2 << 16) | 0xFF000000u;
+            } else if (tid < 336) {
+                const int t = tid - 288, dir = t / 12, g = t - dir * 12;
+                const int4* e = pent[dir] + g * 9;
+                uint32_t k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
+#pragma unroll
+                for (int c = 0; c < 9; ++c) {
+                    const uint32_t key = ((((uint32_t)e[c].z + (uint32_t)prm.P1) & 0xFFu) << 8) | (uint32_t)c;
+                    if (key < k1) { k2 = k1; k1 = key; } else if (key < k2) k2 = key;
+                }
+                gm[dir][g] = make_int4((int)(k1 >> 8), (int)(k1 & 0xFFu), (int)(k2 >> 8), 0);
+            }
+            asm volatile("bar.sync 1, 448;" ::: "memory");         // the fourteen warps of this phase only
             const int pixCur = I1[p];
             if (tid < 4 * NGD) {
                 const int dir = tid / NGD, d = tid - dir * NGD;    // 0 L1, 1 L2, 2 L3, 3 L4
@@ -397,13 +431,25 @@ ng_pipe_kernel(const NgParams prm)
                     uint32_t same = far_, near_ = far_;
                     const int mx = cmx[cp][d], my = cmy[cp][d];
 #pragma unroll 4
-                    for (int d2 = 0; d2 < NGD; ++d2) {
-                        const int4 e = q[d2];
-                        const uint32_t c2 = (uint32_t)e.z;
-                        const bool eq = (e.x == mx) & (e.y == my);
-                        const bool nr = ((uint32_t)(e.x - mx + 2) <= 4u) & ((uint32_t)(e.y - my + 2) <= 4u);
-                        same = eq ? (c2 & 0xFFu) : same;                                      // last match wins (:71-72)
-                        near_ = min(near_, (nr & !eq) ? ((c2 + (uint32_t)prm.P1) & 0xFFu) : 0xFFu);
+                    for (int g = 0; g < 12; ++g) {
+                        const int4 c0 = q[g * 9];
+                        const int ex = mx - c0.x, ey = my - c0.y;
+                        const uint32_t ux = (uint32_t)(ex + 2), uy = (uint32_t)(ey + 2);
+                        const bool valid = ux <= 6u && uy <= 6u;                               // some cell of the grid within +-2
+                        const bool inside = valid && ux - 2u <= 2u && uy - 2u <= 2u;           // the equal cell lies in the grid
+                        const int cell = inside ? ey * 3 + ex : 0;
+                        const uint32_t cs = (uint32_t)q[g * 9 + cell].z & 0xFFu;
+                        const int4 gv = gm[dir][g];
+                        const uint32_t nin = (uint32_t)(cell == gv.y ? gv.z : gv.x);
+                        const uint32_t xi = (0x5422210u >> (4u * min(ux, 6u))) & 7u;          // x-interval [ux-4, ux] clipped to [0, 2]
+                        const uint32_t rw = gr4[dir][g * 6 + xi];
+                        // rows [uy-4, uy] clipped to [0, 2]: the others are masked to 255
+                        const uint32_t km = (uy <= 4u ? 0u : 0xFFu) | ((uy >= 1u && uy <= 5u) ? 0u : 0xFF00u) | (uy >= 2u ? 0u : 0xFF0000u);
+                        const uint32_t v = rw | km;
+                        const uint32_t m2 = __vminu2(v & 0x00FF00FFu, (v >> 8) & 0x00FF00FFu);
+                        const uint32_t nout = min(m2 & 0xFFFFu, m2 >> 16);
+                        same = inside ? cs : same;                                             // later grids overwrite: last match wins (:71-72)
+                        near_ = min(near_, valid ? (inside ? nin : nout) : 0xFFu);
                     }
                     out = ccost[cp][d] + (int)min(min(far_, same), near_) - (int)pm;           // int, not truncated (:80)
                 }
