@@ -118,7 +118,7 @@ int fsgm_calc_pyd_cost_sgm_ng_dev(fsgm_ctx* c, int n, const uint8_t* d_I1, const
     if (n < 1 || W < 1 || H < 1 || mvW < 1 || mvH < 1) return fail(c, FSGM_ERR_ARG, "sizes must be positive");
     if (!d_I1 || !d_I2 || !d_preMv || !d_minC || !d_flow) return fail(c, FSGM_ERR_ARG, "null pointer");
     const int r = halfSearchWinSize, agg = aggSize / 2;          // calc_pyd_cost_sgm_ng.cpp:488-490
-    if (r < 0 || r > 3 || agg < 0 || agg > 4) return fail(c, FSGM_ERR_DOMAIN, "halfSearchWinSize must be 0..3 and aggSize 0..9");
+    if (r < 0 || r > 5 || agg < 0 || agg > 4) return fail(c, FSGM_ERR_DOMAIN, "halfSearchWinSize must be 0..5 and aggSize 0..9");
     FSGM_CUDA(c, cudaSetDevice(c->device));
     const size_t N = (size_t)W * H;
     const int S = 2 * r + 1, D = 9 * S * S;

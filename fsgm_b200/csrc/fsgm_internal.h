@@ -43,6 +43,7 @@ struct fsgm_ctx {
     int pyd_direct_cost = 0;                // tuning knob (fsgm_tune key 6): 1 = the lane = path pipeline builds its cost volume with the direct kernel only
     int pyd_cluster = 0;                    // tuning knob (fsgm_tune key 5): cluster size of the pyd row-synchronous kernels, 0 auto, -1 off
     std::vector<std::pair<int, int>> pv_occ;   // cached cudaOccupancyMaxActiveClusters answers of pydv_kernel
+    int pydng_generic = 0;                  // tuning knob (fsgm_tune key 7): 1 = calc_pyd_cost_sgm_ng searches cell by cell at every step (no grid tables)
     int ng_occupancy = 0;                   // tuning knob (fsgm_tune key 3): resident pairs per SM of the ng kernel, 0 = by batch size
     int force_cluster = 0;                  // tuning/test knob: 0 auto, -1 generic path only, 1/2/4/8 forced cluster size
     std::string err;

@@ -286,12 +286,15 @@ ng_pipe_kernel(const NgParams prm)
     __shared__ int cmx[2][NGD], cmy[2][NGD], ccost[2][NGD];   // candidates of pixel p (parity p&1) and p+1
     __shared__ int Lc[4][NGD];
     __shared__ int4 pent[4][NGD];                             // predecessor entries of the pixel being stepped
-    // per predecessor and 3x3 candidate grid (12 per predecessor): minima of the P1 term over the six x-intervals, rows 0..2
-    // (byte 3 = 255), and the smallest / its cell / the second smallest over the whole grid
-    __shared__ uint32_t gr4[4][12 * 6];
-    __shared__ int4 gm[4][12];
+    // per predecessor and 3x3 candidate grid (12 per predecessor): the answer of the compatibility search for every displacement
+    // of a candidate against the grid corner, T[dir][grid][uy * 8 + ux] with (ux, uy) = candidate - corner + 2 clamped to 7
+    // (row / column 7 = "no cell within +-2": 0xFF, written once); low half = smallest P1 term among the compatible cells, bits
+    // 16-23 = cost of the cell of equal flow, bit 24 = such a cell exists
+    __shared__ uint32_t T[4][12][64];
+    __shared__ int2 corner[4][12];                            // grid corner - 2
     __shared__ Top2 top1[2];
-    __shared__ Top2 hint[2][3];                               // stale ring slots of L2,L3,L4 for pixel q (parity q&1)
+    __shared__ Top2 hint[3][3];                               // stale ring slots of L2,L3,L4 for pixel q (slot q % 3): its hints, and the
+                                                              // content its own top-2 commit starts from
     __shared__ int preMin[4];
     __shared__ uint32_t c1win[2][25];
     __shared__ int rnd[2][8];
@@ -310,28 +313,37 @@ ng_pipe_kernel(const NgParams prm)
         }
         rf = f; rr = r;
     };
-    auto load_c1 = [&](size_t q, int k) {
-        const int x = (int)(q % W), y = (int)(q / W);
+    auto load_c1 = [&](int x, int y, int k) {
         return cen1[(size_t)clampi(y + k / 5 - 2, 0, H - 1) * W + clampi(x + k % 5 - 2, 0, W - 1)];
     };
     // candidates of pixel q by `nthr` cooperating threads (thread index t), one candidate at a time per thread
-    auto make_candidates = [&](size_t q, int t, int nthr) {
-        const int x = (int)(q % W), y = (int)(q / W), qp = (int)(q & 1);
+    auto make_candidates = [&](size_t q, int q3, int x, int y, int t, int nthr) {
+        const int qp = (int)(q & 1);
         const int cur1q = (int)((q + 1) & 1);
+        const bool pin = x >= 2 && x + 2 < W && y >= 2 && y + 2 < H;          // the pixel's own 5 x 5 window is not clamped
         for (int c = t; c < NGD; c += nthr) {
             const int l = c / 27, i = (c % 27) / 9, off = c % 9, oy = off / 3 - 1, ox = off % 3 - 1;
             int hx, hy;
             if (i < 2) {
-                const Top2& tt = (l == 0) ? top1[cur1q] : hint[qp][l - 1];
+                const Top2& tt = (l == 0) ? top1[cur1q] : hint[q3][l - 1];
                 hx = tt.mvx[i]; hy = tt.mvy[i];
             } else { hx = rnd[qp][2 * l] % 256 - 128; hy = rnd[qp][2 * l + 1] % 128 - 64; }
             uint32_t s = 0;
+            const int bx = (int)((uint32_t)(x - 2 + ox) + (uint32_t)hx), by = (int)((uint32_t)(y - 2 + oy) + (uint32_t)hy);
+            if (pin && bx >= 0 && bx < W - 4 && by >= 0 && by < H - 4) {          // nor is the displaced one: 25 loads at fixed offsets
+                const uint32_t* r = cen2 + (size_t)by * W + bx;
+#pragma unroll
+                for (int ky = 0; ky < 5; ++ky, r += W)
+#pragma unroll
+                    for (int kx = 0; kx < 5; ++kx) s += __popc(c1win[qp][ky * 5 + kx] ^ __ldg(r + kx));
+            } else {
 #pragma unroll 5
-            for (int k = 0; k < 25; ++k) {
-                const int y1 = clampi(y + k / 5 - 2, 0, H - 1), x1 = clampi(x + k % 5 - 2, 0, W - 1);
-                const int y2 = clampi((int)((uint32_t)(oy + y1) + (uint32_t)hy), 0, H - 1);
-                const int x2 = clampi((int)((uint32_t)(ox + x1) + (uint32_t)hx), 0, W - 1);
-                s += __popc(c1win[qp][k] ^ __ldg(cen2 + (size_t)W * y2 + x2));
+                for (int k = 0; k < 25; ++k) {
+                    const int y1 = clampi(y + k / 5 - 2, 0, H - 1), x1 = clampi(x + k % 5 - 2, 0, W - 1);
+                    const int y2 = clampi((int)((uint32_t)(oy + y1) + (uint32_t)hy), 0, H - 1);
+                    const int x2 = clampi((int)((uint32_t)(ox + x1) + (uint32_t)hx), 0, W - 1);
+                    s += __popc(c1win[qp][k] ^ __ldg(cen2 + (size_t)W * y2 + x2));
+                }
             }
             ccost[qp][c] = (int)((2 * s + 25) / 50);
             cmx[qp][c] = (int)((uint32_t)hx + (uint32_t)ox);
@@ -341,25 +353,27 @@ ng_pipe_kernel(const NgParams prm)
 
     // ---- prologue: everything pixel 0 and pixel 1 need ------------------------------------------------------
     if (tid < 2) { for (int i = 0; i < 2; ++i) { top1[tid].mvx[i] = 0; top1[tid].mvy[i] = 0; top1[tid].cost[i] = 0; } }
-    if (tid < 6) { Top2 z; for (int i = 0; i < 2; ++i) { z.mvx[i] = z.mvy[i] = z.cost[i] = 0; } hint[tid / 3][tid % 3] = z; }   // ring rows start zeroed
+    if (tid < 9) { Top2 z; for (int i = 0; i < 2; ++i) { z.mvx[i] = z.mvy[i] = z.cost[i] = 0; } hint[tid / 3][tid % 3] = z; }   // ring rows start zeroed
     if (tid < NGD) { pent[0][tid] = make_int4(0, 0, 0, 0); }
     if (tid < 31 && !prm.rand_stream) rstate[tid] = prm.rng_state[pair * 31 + tid];
     if (tid == 0) { rf = 3; rr = 0; }
-    if (tid >= 64 && tid < 89) c1win[0][tid - 64] = load_c1(0, tid - 64);
-    if (tid >= 96 && tid < 121 && N > 1) c1win[1][tid - 96] = load_c1(1, tid - 96);
+    if (tid >= 64 && tid < 89) c1win[0][tid - 64] = load_c1(0, 0, tid - 64);
+    if (tid >= 96 && tid < 121 && N > 1) c1win[1][tid - 96] = load_c1(1 % W, 1 / W, tid - 96);
+    for (int i = tid; i < 4 * 12 * 64; i += NG_THREADS) (&T[0][0][0])[i] = 0xFFu;
     __syncthreads();
     if (tid == 0) { gen_rnd(0); if (N > 1) gen_rnd(1); }
     __syncthreads();
-    make_candidates(0, tid, NG_THREADS);
+    make_candidates(0, 0, 0, 0, tid, NG_THREADS);
     __syncthreads();
 
+    int x = 0, y = 0, p3 = 0;                                 // p3 = p % 3
     for (size_t p = 0; p < N; ++p) {
-        const int x = (int)(p % W), y = (int)(p / W);
         const int curRow = (y + 1) & 1;
         const int cp = (int)(p & 1), cur1 = (int)((p + 1) & 1);
         const bool startX = (x == 0), startY = (y == 0), startR = (x == W - 1);
         const size_t p1 = p + 1, p2 = p + 2;
-        const int x1n = (int)(p1 % W), y1n = (int)(p1 / W);
+        const int x1n = x + 1 == W ? 0 : x + 1, y1n = x + 1 == W ? y + 1 : y;
+        const int x2n = x1n + 1 == W ? 0 : x1n + 1, y2n = x1n + 1 == W ? y1n + 1 : y1n;
 
         // ---- phase X ----------------------------------------------------------------------------------------------
         // register prefetch (consumed in phase Y): predecessor rows + previous minima of p+1, stale hints + census of p+2
@@ -381,39 +395,48 @@ ng_pipe_kernel(const NgParams prm)
             }
         }
         if (p2 < N) {
-            const int x2n = (int)(p2 % W), y2n = (int)(p2 / W);
             if (tid >= 324 && tid < 327) pf_hint = toprow[((size_t)(tid - 324) * 2 + ((y2n + 1) & 1)) * W + x2n];
-            if (tid >= 352 && tid < 377) pf_c1 = load_c1(p2, tid - 352);
+            if (tid >= 352 && tid < 377) pf_c1 = load_c1(x2n, y2n, tid - 352);
         }
         if (warp < 14) {
             // A predecessor's 108 entries are twelve 3 x 3 grids of consecutive flow vectors (hint + offset, offy outer).  For a
             // candidate (mx, my) and a grid with corner (X0, Y0) the cell of EQUAL flow is (ex, ey) = (mx - X0, my - Y0); the cells
             // within +-2 (the P1 term, :73-74) are [ex-2, ex+2] x [ey-2, ey+2] clipped to the grid — the whole grid minus the equal
-            // cell when that cell lies inside, a rectangle that touches a grid edge otherwise.  So: per grid the smallest / second
-            // smallest P1 term with the cell of the smallest, and row-wise minima over the six x-intervals; 12 grid queries per
-            // candidate and direction instead of 108 entry tests.  Values are the reference's own per-entry terms
-            // ((cost + P1) & 255, cost & 255), so no parameter domain is excluded.
-            if (tid < 288) {
-                const int dir = tid / 72, rem = tid - dir * 72, g = rem / 6, xi = rem - g * 6;
-                const int a = xi < 3 ? 0 : xi < 5 ? 1 : 2, b = xi == 0 ? 0 : (xi == 1 || xi == 3) ? 1 : 2;
+            // cell when that cell lies inside, a rectangle that touches a grid edge otherwise.  The answer depends only on
+            // (ux, uy) = (ex + 2, ey + 2) in 0..6 (anything else: no compatible cell), so it is tabulated per grid by 336 threads
+            // (one per direction, grid and uy) and the search is ONE table look-up per grid: 12 per candidate and direction
+            // instead of 108 entry tests.  Values are the reference's own per-entry terms ((cost + P1) & 255, cost & 255), so no
+            // parameter domain is excluded.
+            if (tid < 336) {
+                const int uy = tid / 48, r = tid - uy * 48, dir = r / 12, g = r - dir * 12;
                 const int4* e = pent[dir] + g * 9;
-                uint32_t v0 = 255, v1 = 255, v2 = 255;
-                for (int cx = a; cx <= b; ++cx) {
-                    v0 = min(v0, ((uint32_t)e[cx].z + (uint32_t)prm.P1) & 0xFFu);
-                    v1 = min(v1, ((uint32_t)e[3 + cx].z + (uint32_t)prm.P1) & 0xFFu);
-                    v2 = min(v2, ((uint32_t)e[6 + cx].z + (uint32_t)prm.P1) & 0xFFu);
-                }
-                gr4[dir][g * 6 + xi] = v0 | (v1 << 8) | (v2 << 16) | 0xFF000000u;
-            } else if (tid < 336) {
-                const int t = tid - 288, dir = t / 12, g = t - dir * 12;
-                const int4* e = pent[dir] + g * 9;
-                uint32_t k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
+                uint32_t z[9], a[9];
 #pragma unroll
-                for (int c = 0; c < 9; ++c) {
-                    const uint32_t key = ((((uint32_t)e[c].z + (uint32_t)prm.P1) & 0xFFu) << 8) | (uint32_t)c;
-                    if (key < k1) { k2 = k1; k1 = key; } else if (key < k2) k2 = key;
+                for (int c = 0; c < 9; ++c) { z[c] = (uint32_t)e[c].z; a[c] = (z[c] + (uint32_t)prm.P1) & 0xFFu; }
+                if (uy == 0) corner[dir][g] = make_int2(e[0].x - 2, e[0].y - 2);
+                uint32_t* t = &T[dir][g][uy * 8];
+                // rows [uy-4, uy] clipped to [0, 2]
+                const bool r0 = uy <= 4, r1 = uy >= 1 && uy <= 5, r2 = uy >= 2;
+                uint32_t c0 = 255u, c1 = 255u, c2 = 255u;                          // column minima over those rows
+                if (r0) { c0 = a[0]; c1 = a[1]; c2 = a[2]; }
+                if (r1) { c0 = min(c0, a[3]); c1 = min(c1, a[4]); c2 = min(c2, a[5]); }
+                if (r2) { c0 = min(c0, a[6]); c1 = min(c1, a[7]); c2 = min(c2, a[8]); }
+                const uint32_t m01 = min(c0, c1), m12 = min(c1, c2);
+                t[0] = c0; t[1] = m01; t[5] = m12; t[6] = c2;                       // columns [ux-4, ux] clipped to [0, 2]
+                if (uy < 2 || uy > 4) { const uint32_t m = min(m01, c2); t[2] = m; t[3] = m; t[4] = m; }
+                else {
+                    // the equal cell lies in row uy - 2: the whole grid minus that cell, and the cell's own cost
+                    const int rr = uy - 2;
+                    const uint32_t f0 = min(min(a[0], a[1]), a[2]), f1 = min(min(a[3], a[4]), a[5]), f2 = min(min(a[6], a[7]), a[8]);
+                    const uint32_t o = rr == 0 ? min(f1, f2) : rr == 1 ? min(f0, f2) : min(f0, f1);
+                    const uint32_t b0 = rr == 0 ? a[0] : rr == 1 ? a[3] : a[6], b1 = rr == 0 ? a[1] : rr == 1 ? a[4] : a[7],
+                                   b2 = rr == 0 ? a[2] : rr == 1 ? a[5] : a[8];
+                    const uint32_t s0 = rr == 0 ? z[0] : rr == 1 ? z[3] : z[6], s1 = rr == 0 ? z[1] : rr == 1 ? z[4] : z[7],
+                                   s2 = rr == 0 ? z[2] : rr == 1 ? z[5] : z[8];
+                    t[2] = min(o, min(b1, b2)) | ((s0 & 0xFFu) << 16) | 0x01000000u;
+                    t[3] = min(o, min(b0, b2)) | ((s1 & 0xFFu) << 16) | 0x01000000u;
+                    t[4] = min(o, min(b0, b1)) | ((s2 & 0xFFu) << 16) | 0x01000000u;
                 }
-                gm[dir][g] = make_int4((int)(k1 >> 8), (int)(k1 & 0xFFu), (int)(k2 >> 8), 0);
             }
             asm volatile("bar.sync 1, 448;" ::: "memory");         // the fourteen warps of this phase only
             const int pixCur = I1[p];
@@ -423,40 +446,29 @@ ng_pipe_kernel(const NgParams prm)
                 int out;
                 if (start) out = ccost[cp][d];
                 else {
-                    const int4* q = pent[dir];
                     const int pixPre = dir == 0 ? I1[p - 1] : I1[p - W + (dir - 2)];
                     const int P2 = abs(pixCur - pixPre) > 50 ? prm.P2 / 8 : prm.P2;          // :101-105
                     const uint32_t pm = (uint32_t)preMin[dir];
                     const uint32_t far_ = (pm + (uint32_t)P2) & 0xFFu;
-                    uint32_t same = far_, near_ = far_;
+                    uint32_t acc = far_, se = 0;                                               // low half of acc: the running P1 minimum
                     const int mx = cmx[cp][d], my = cmy[cp][d];
-#pragma unroll 4
+                    const uint32_t* Td = &T[dir][0][0];
+                    const int2* cr = corner[dir];
+#pragma unroll
                     for (int g = 0; g < 12; ++g) {
-                        const int4 c0 = q[g * 9];
-                        const int ex = mx - c0.x, ey = my - c0.y;
-                        const uint32_t ux = (uint32_t)(ex + 2), uy = (uint32_t)(ey + 2);
-                        const bool valid = ux <= 6u && uy <= 6u;                               // some cell of the grid within +-2
-                        const bool inside = valid && ux - 2u <= 2u && uy - 2u <= 2u;           // the equal cell lies in the grid
-                        const int cell = inside ? ey * 3 + ex : 0;
-                        const uint32_t cs = (uint32_t)q[g * 9 + cell].z & 0xFFu;
-                        const int4 gv = gm[dir][g];
-                        const uint32_t nin = (uint32_t)(cell == gv.y ? gv.z : gv.x);
-                        const uint32_t xi = (0x5422210u >> (4u * min(ux, 6u))) & 7u;          // x-interval [ux-4, ux] clipped to [0, 2]
-                        const uint32_t rw = gr4[dir][g * 6 + xi];
-                        // rows [uy-4, uy] clipped to [0, 2]: the others are masked to 255
-                        const uint32_t km = (uy <= 4u ? 0u : 0xFFu) | ((uy >= 1u && uy <= 5u) ? 0u : 0xFF00u) | (uy >= 2u ? 0u : 0xFF0000u);
-                        const uint32_t v = rw | km;
-                        const uint32_t m2 = __vminu2(v & 0x00FF00FFu, (v >> 8) & 0x00FF00FFu);
-                        const uint32_t nout = min(m2 & 0xFFFFu, m2 >> 16);
-                        same = inside ? cs : same;                                             // later grids overwrite: last match wins (:71-72)
-                        near_ = min(near_, valid ? (inside ? nin : nout) : 0xFFu);
+                        const int2 c0 = cr[g];
+                        const uint32_t ux = min((uint32_t)(mx - c0.x), 7u), uy = min((uint32_t)(my - c0.y), 7u);
+                        const uint32_t e = Td[g * 64 + uy * 8 + ux];
+                        acc = __vminu2(acc, e);
+                        se = e >= 0x01000000u ? e : se;                                        // later grids overwrite: last match wins (:71-72)
                     }
+                    const uint32_t near_ = acc & 0xFFFFu, same = se ? (se >> 16) & 0xFFu : far_;
                     out = ccost[cp][d] + (int)min(min(far_, same), near_) - (int)pm;           // int, not truncated (:80)
                 }
                 Lc[dir][d] = out;
             }
         } else if (p1 < N) {
-            make_candidates(p1, tid - 14 * 32, NG_THREADS - 14 * 32);
+            make_candidates(p1, p3 == 2 ? 0 : p3 + 1, x1n, y1n, tid - 14 * 32, NG_THREADS - 14 * 32);
         }
         __syncthreads();
 
@@ -465,7 +477,8 @@ ng_pipe_kernel(const NgParams prm)
             const int dir = warp;
             const bool start = dir == 0 ? startX : dir == 1 ? (startX || startY) : dir == 2 ? startY : (startY || startR);
             Top2* slot = (dir == 0) ? &top1[cur1] : &toprow[((size_t)(dir - 1) * 2 + curRow) * W + x];
-            const Top2 old = *slot;                                   // stale content is part of the reference's behaviour
+            // stale content is part of the reference's behaviour; the row slots were fetched two pixels ago (hint[])
+            const Top2 old = (dir == 0) ? top1[cur1] : hint[p3][dir - 1];
             Top2 nw = old;
             if (start) nw.cost[0] = 0;
             else {
@@ -531,11 +544,12 @@ ng_pipe_kernel(const NgParams prm)
         if (pf_ok) pent[1 + tid / NGD][tid % NGD] = make_int4(pf_mv.x, pf_mv.y, pf_c, 0);
         if (tid >= 400 && tid < 403) preMin[1 + tid - 400] = pf_min;
         if (p2 < N) {
-            if (tid >= 324 && tid < 327) hint[p2 & 1][tid - 324] = pf_hint;
+            if (tid >= 324 && tid < 327) hint[p3 == 0 ? 2 : p3 - 1][tid - 324] = pf_hint;
             if (tid >= 352 && tid < 377) c1win[p2 & 1][tid - 352] = pf_c1;
             if (tid == 384) gen_rnd(p2);
         }
         __syncthreads();
+        x = x1n; y = y1n; p3 = p3 == 2 ? 0 : p3 + 1;
     }
 }
 

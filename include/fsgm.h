@@ -50,7 +50,8 @@ FSGM_API const char* fsgm_last_error(const fsgm_ctx* ctx);
  * key 4 = 1: the direction split never uses the peer-store form (NCCL exchange of the partial volumes instead).
  * key 5 = aggregation path of the pyramidal variant: 0 auto (one thread per path where it applies), -1 one-warp-per-scanline kernels only,
  *         -2 = auto with every shifted step forced through the label-by-label form (test knob), 1..16 = row-synchronous clusters of that size.
- * key 6 = 1: the pyramidal variant builds its cost volume with the direct kernel only (no separable box filter + fix-up list). */
+ * key 6 = 1: the pyramidal variant builds its cost volume with the direct kernel only (no separable box filter + fix-up list).
+ * key 7 = 1: calc_pyd_cost_sgm_ng runs the cell-by-cell compatibility search at every step (no per-grid tables). */
 FSGM_API int         fsgm_tune(fsgm_ctx* ctx, int key, int value);
 /* occupancy probe: resident clusters of `cluster_size` CTAs x `threads` threads with `smem_bytes` dynamic shared memory */
 FSGM_API int         fsgm_debug_max_clusters(int cluster_size, size_t smem_bytes, int threads);
@@ -337,7 +338,7 @@ FSGM_API int fsgm_calc_cost_sgm_ng_dev(fsgm_ctx* ctx, int n_pairs, const uint8_t
 /* ---- gateway 4: calc_pyd_cost_sgm_ng (calc_pyd_cost_sgm_ng.cpp:448-523) -------------------------
  * [minC, flow] = calc_pyd_cost_sgm_ng(I1, I2, preMv, halfSearchWinSize, aggSize, subPixelRefine, P1, P2)
  * preMv f64[2][mvHeight][mvWidth] (hints are clamped to its size, :392-393); candidates = 9*(2r+1)^2 with
- * r = halfSearchWinSize (0..3 supported); aggregation radius = aggSize/2 (:490). */
+ * r = halfSearchWinSize (0..5 supported: up to 9 x 11 x 11 = 1089 candidates); aggregation radius = aggSize/2 (:490). */
 FSGM_API int fsgm_calc_pyd_cost_sgm_ng(fsgm_ctx* ctx, const uint8_t* I1, const uint8_t* I2, int width, int height,
                           const double* preMv, int mvWidth, int mvHeight, int halfSearchWinSize, int aggSize,
                           int subPixelRefine, int P1, int P2, uint32_t* minC, double* flow);

@@ -94,7 +94,9 @@ def test_pydng_vs_golden(ctx, name):
 
 @pytest.mark.parametrize("W,H,r,aggSize,sub,P1,P2,prior", [
     (36, 26, 1, 5, 1, 6, 32, "frac"), (30, 22, 2, 5, 0, 6, 32, "int"), (24, 18, 0, 3, 1, 6, 32, "frac"),
-    (22, 16, 1, 5, 1, 100, 250, "frac"), (20, 14, 1, 1, 1, 6, 32, "wild"), (26, 15, 3, 5, 0, 6, 32, "int")])
+    (22, 16, 1, 5, 1, 100, 250, "frac"), (20, 14, 1, 1, 1, 6, 32, "wild"), (26, 15, 3, 5, 0, 6, 32, "int"),
+    (28, 17, 2, 5, 1, 100, 250, "int"), (25, 14, 3, 5, 1, 6, 32, "frac"), (18, 12, 4, 5, 0, 6, 32, "int"), (16, 11, 5, 3, 1, 6, 32, "frac"),
+    (31, 20, 1, 5, 0, 250, 100, "big")])
 def test_pydng_vs_oracle(ctx, oracle, W, H, r, aggSize, sub, P1, P2, prior):
     fp = synth.flow_pair(W, H, seed=W + r, umax=2, vmax=2)
     rng = np.random.default_rng(W)
@@ -103,11 +105,18 @@ def test_pydng_vs_oracle(ctx, oracle, W, H, r, aggSize, sub, P1, P2, prior):
         mv = np.round(mv)
     if prior == "wild":
         mv[0, 1, 2], mv[1, 3, 4], mv[0, 5, 6] = np.nan, 1e300, -3e9
+    if prior == "big":                                      # |mv| > 1 almost everywhere: regular candidate grids, fractional priors
+        mv = mv + np.where(mv >= 0, 1.5, -1.5)
     f = oracle.ref_pydng if oracle.have_ref("pydng") else oracle.port_pydng
     want = f(fp["I1"], fp["I2"], mv, r, aggSize, sub, P1, P2)
-    minC, flow = ctx.calc_pyd_cost_sgm_ng(fp["I1"], fp["I2"], mv, r, aggSize, sub, P1, P2)
-    assert np.array_equal(minC, want["minC"])
-    assert np.array_equal(flow, want["flow"], equal_nan=True)
+    for generic in (0, 1):                                  # per-grid tables where the grids are regular / cell-by-cell search everywhere
+        ctx.tune(7, generic)
+        try:
+            minC, flow = ctx.calc_pyd_cost_sgm_ng(fp["I1"], fp["I2"], mv, r, aggSize, sub, P1, P2)
+        finally:
+            ctx.tune(7, 0)
+        assert np.array_equal(minC, want["minC"]), f"generic={generic}"
+        assert np.array_equal(flow, want["flow"], equal_nan=True), f"generic={generic}"
 
 
 @pytest.mark.timeout(600)
