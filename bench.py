@@ -541,8 +541,9 @@ def workload_D(env: Env):
                  "unit": "pairs/s", "pairs_per_step": n, "ms_per_step": ms, "latency_ms_single_pair": lat,
                  "roofline": {"bound": "integer issue", "achieved": value * W * H * ops_px / 1e12, "peak": int_peak / 1e12, "unit": "Tops/s",
                               "frac": value * W * H * ops_px / int_peak, "ops_per_pixel": ops_px, "traffic": None,
-                              "basis": "4*108^2 candidate-compatibility tests + 108*25 Hamming taps per pixel against 64 integer lane-ops "
-                                       "per clock and SM (alu pipe)"}}
+                              "basis": "REFERENCE-EQUIVALENT operations: 4*108^2 candidate-compatibility tests + 108*25 Hamming taps per pixel "
+                                       "(the reference's formulation) against 64 integer lane-ops per clock and SM (alu pipe); the kernel "
+                                       "itself answers the compatibility search from per-grid tables (12 look-ups per candidate and direction)"}}
     del I1, I2, mC, fl
     # ---- pyd_ng: r = 1 (81 candidates) and r = 2 (225) ----------------------------------------------------------------------------
     for r, n in ((1, 8), (2, 4)):
@@ -557,7 +558,9 @@ def workload_D(env: Env):
                               "unit": "pairs/s", "pairs_per_step": n, "ms_per_step": ms,
                               "roofline": {"bound": "integer issue", "achieved": value * W * H * ops_px / 1e12, "peak": int_peak / 1e12,
                                            "unit": "Tops/s", "frac": value * W * H * ops_px / int_peak, "ops_per_pixel": ops_px, "traffic": None,
-                                           "basis": "the reference's O(D^2) formulation: 4*D^2 compatibility tests + 25*D Hamming taps per pixel"}}
+                                           "basis": "REFERENCE-EQUIVALENT operations (the reference's O(D^2) formulation: 4*D^2 compatibility tests + 25*D "
+                                                    "Hamming taps per pixel); the kernel answers the search from per-grid tables (9 look-ups per "
+                                                    "candidate and step), so frac is a speed in reference work units, not pipe utilisation"}}
         del I1, I2, mv, mC, fl
     if not env.args.no_cpu:
         from oracle import pyoracle as po
