@@ -19,6 +19,7 @@ namespace fsgm {
 
 constexpr int NGD = 108;              // DIRECTION_NUM * (N + M) * MV_PER_HINT (:194)
 constexpr int NG_THREADS = 512;
+constexpr int NG_TP = 65;               // words per grid table of the pipelined kernel (64 + 1 pad)
 
 struct Top2 { int mvx[2], mvy[2], cost[2]; };       // the two extra slots L[D], L[D+1] of the reference (:196)
 
@@ -261,10 +262,12 @@ ng_kernel(const NgParams prm)
 
 // ------------------------------------------------------------------------------------------------------------
 // Pipelined variant (W >= 4).  Same arithmetic, two block barriers per pixel instead of five:
-//   phase X: warps 0-13 run the 4 x 108 compatibility searches of pixel p; warps 14-15 build the candidates of pixel
-//            p+1 (they only need ring slots written before pixel p: the L1 slot of p-1 and rows y-1 / y-2), and the
-//            global rows pixel p+1 / p+2 will need are fetched into registers;
-//   phase Y: top-2 per direction, Sp + WTA and the ring commits of pixel p, plus the prefetched rows go to shared memory.
+//   phase X: warps 0-13 run the 4 x 108 compatibility searches of pixel p (through per-grid tables, below); warp 14 builds the
+//            18 candidates of pixel p+1 that hang on the L1 ring slot written by pixel p-1; the global rows pixel p+1 needs and
+//            the row slots / census window of pixel p+3 are fetched into registers;
+//   phase Y: top-2 per direction, Sp + WTA and the ring commits of pixel p; warps 12-14 build the 90 candidates of pixel p+2
+//            whose hints are a row old (row ring slots, random hints); the prefetched rows go to shared memory.
+// Candidates live in three buffers (pixel q: q % 3), the stale row slots in four (q % 4).
 // ------------------------------------------------------------------------------------------------------------
 // OCC = CTAs (pairs) resident per SM.  The walk is a chain of dependent phases separated by block barriers, so one CTA leaves most
 // issue slots empty; a second and third pair on the same SM fill them.  OCC = 2 fits without spills (64 registers per thread),
@@ -283,26 +286,27 @@ ng_pipe_kernel(const NgParams prm)
     int16_t* Lrow = prm.Lrow + (size_t)pair * 3 * 2 * W * NGD;
     Top2* toprow = prm.toprow + (size_t)pair * 3 * 2 * W;
 
-    __shared__ int cmx[2][NGD], cmy[2][NGD], ccost[2][NGD];   // candidates of pixel p (parity p&1) and p+1
+    __shared__ int cmx[3][NGD], cmy[3][NGD], ccost[3][NGD];   // candidates of pixel q: buffer q % 3
     __shared__ int Lc[4][NGD];
-    __shared__ int4 pent[4][NGD];                             // predecessor entries of the pixel being stepped
+    __shared__ int2 pxy[4][NGD];                              // predecessor entries of the pixel being stepped: flow vectors
+    __shared__ int pz[4][NGD];                                //                                                 path costs
     // per predecessor and 3x3 candidate grid (12 per predecessor): the answer of the compatibility search for every displacement
     // of a candidate against the grid corner, T[dir][grid][uy * 8 + ux] with (ux, uy) = candidate - corner + 2 clamped to 7
     // (row / column 7 = "no cell within +-2": 0xFF, written once); low half = smallest P1 term among the compatible cells, bits
     // 16-23 = cost of the cell of equal flow, bit 24 = such a cell exists
-    __shared__ uint32_t T[4][12][64];
+    __shared__ uint32_t T[4][12][NG_TP];                      // pitch 65 words: the builders of neighbouring grids hit different banks
     __shared__ int2 corner[4][12];                            // grid corner - 2
     __shared__ Top2 top1[2];
-    __shared__ Top2 hint[3][3];                               // stale ring slots of L2,L3,L4 for pixel q (slot q % 3): its hints, and the
+    __shared__ Top2 hint[4][3];                               // stale ring slots of L2,L3,L4 for pixel q (slot q % 4): its hints, and the
                                                               // content its own top-2 commit starts from
     __shared__ int preMin[4];
-    __shared__ uint32_t c1win[2][25];
-    __shared__ int rnd[2][8];
+    __shared__ uint32_t c1win[3][25];                         // 5 x 5 census window of pixel q: q % 3
+    __shared__ int rnd[3][8];
     __shared__ uint32_t rstate[31];
     __shared__ int rf, rr;
 
-    auto gen_rnd = [&](size_t q) {                            // thread 0 only: the 8 rand() values of pixel q
-        int* out = rnd[q & 1];
+    auto gen_rnd = [&](size_t q, int q3) {                    // one thread: the 8 rand() values of pixel q
+        int* out = rnd[q3];
         if (prm.rand_stream) { for (int i = 0; i < 8; ++i) out[i] = prm.rand_stream[(pair * N + q) * 8 + i]; return; }
         int f = rf, r = rr;
         for (int i = 0; i < 8; ++i) {
@@ -316,67 +320,73 @@ ng_pipe_kernel(const NgParams prm)
     auto load_c1 = [&](int x, int y, int k) {
         return cen1[(size_t)clampi(y + k / 5 - 2, 0, H - 1) * W + clampi(x + k % 5 - 2, 0, W - 1)];
     };
-    // candidates of pixel q by `nthr` cooperating threads (thread index t), one candidate at a time per thread
-    auto make_candidates = [&](size_t q, int q3, int x, int y, int t, int nthr) {
-        const int qp = (int)(q & 1);
+    // candidate c of pixel q = (x, y): hint, 25 Hamming taps, entry (mv, cost) into buffer q3 = q % 3; q4 = q % 4
+    auto make_candidate = [&](int c, size_t q, int q3, int q4, int x, int y) {
         const int cur1q = (int)((q + 1) & 1);
         const bool pin = x >= 2 && x + 2 < W && y >= 2 && y + 2 < H;          // the pixel's own 5 x 5 window is not clamped
-        for (int c = t; c < NGD; c += nthr) {
-            const int l = c / 27, i = (c % 27) / 9, off = c % 9, oy = off / 3 - 1, ox = off % 3 - 1;
-            int hx, hy;
-            if (i < 2) {
-                const Top2& tt = (l == 0) ? top1[cur1q] : hint[q3][l - 1];
-                hx = tt.mvx[i]; hy = tt.mvy[i];
-            } else { hx = rnd[qp][2 * l] % 256 - 128; hy = rnd[qp][2 * l + 1] % 128 - 64; }
-            uint32_t s = 0;
-            const int bx = (int)((uint32_t)(x - 2 + ox) + (uint32_t)hx), by = (int)((uint32_t)(y - 2 + oy) + (uint32_t)hy);
-            if (pin && bx >= 0 && bx < W - 4 && by >= 0 && by < H - 4) {          // nor is the displaced one: 25 loads at fixed offsets
-                const uint32_t* r = cen2 + (size_t)by * W + bx;
+        const int l = c / 27, i = (c % 27) / 9, off = c % 9, oy = off / 3 - 1, ox = off % 3 - 1;
+        int hx, hy;
+        if (i < 2) {
+            const Top2& tt = (l == 0) ? top1[cur1q] : hint[q4][l - 1];
+            hx = tt.mvx[i]; hy = tt.mvy[i];
+        } else { hx = rnd[q3][2 * l] % 256 - 128; hy = rnd[q3][2 * l + 1] % 128 - 64; }
+        uint32_t s = 0;
+        const int bx = (int)((uint32_t)(x - 2 + ox) + (uint32_t)hx), by = (int)((uint32_t)(y - 2 + oy) + (uint32_t)hy);
+        if (pin && bx >= 0 && bx < W - 4 && by >= 0 && by < H - 4) {          // nor is the displaced one: 25 loads at fixed offsets
+            const uint32_t* r = cen2 + (size_t)by * W + bx;
 #pragma unroll
-                for (int ky = 0; ky < 5; ++ky, r += W)
+            for (int ky = 0; ky < 5; ++ky, r += W)
 #pragma unroll
-                    for (int kx = 0; kx < 5; ++kx) s += __popc(c1win[qp][ky * 5 + kx] ^ __ldg(r + kx));
-            } else {
-#pragma unroll 5
-                for (int k = 0; k < 25; ++k) {
-                    const int y1 = clampi(y + k / 5 - 2, 0, H - 1), x1 = clampi(x + k % 5 - 2, 0, W - 1);
-                    const int y2 = clampi((int)((uint32_t)(oy + y1) + (uint32_t)hy), 0, H - 1);
-                    const int x2 = clampi((int)((uint32_t)(ox + x1) + (uint32_t)hx), 0, W - 1);
-                    s += __popc(c1win[qp][k] ^ __ldg(cen2 + (size_t)W * y2 + x2));
-                }
+                for (int kx = 0; kx < 5; ++kx) s += __popc(c1win[q3][ky * 5 + kx] ^ __ldg(r + kx));
+        } else {                                                              // clamped twice (:161-166): five columns, five rows
+            int xo[5];
+#pragma unroll
+            for (int kx = 0; kx < 5; ++kx) xo[kx] = clampi((int)((uint32_t)(ox + clampi(x + kx - 2, 0, W - 1)) + (uint32_t)hx), 0, W - 1);
+#pragma unroll
+            for (int ky = 0; ky < 5; ++ky) {
+                const int y2 = clampi((int)((uint32_t)(oy + clampi(y + ky - 2, 0, H - 1)) + (uint32_t)hy), 0, H - 1);
+                const uint32_t* r = cen2 + (size_t)W * y2;
+#pragma unroll
+                for (int kx = 0; kx < 5; ++kx) s += __popc(c1win[q3][ky * 5 + kx] ^ __ldg(r + xo[kx]));
             }
-            ccost[qp][c] = (int)((2 * s + 25) / 50);
-            cmx[qp][c] = (int)((uint32_t)hx + (uint32_t)ox);
-            cmy[qp][c] = (int)((uint32_t)hy + (uint32_t)oy);
         }
+        ccost[q3][c] = (int)((2 * s + 25) / 50);
+        cmx[q3][c] = (int)((uint32_t)hx + (uint32_t)ox);
+        cmy[q3][c] = (int)((uint32_t)hy + (uint32_t)oy);
     };
+    constexpr int NFRESH = 18;                                 // candidates 0..17: the two L1 hints (l = 0, i < 2) x 9 offsets
 
-    // ---- prologue: everything pixel 0 and pixel 1 need ------------------------------------------------------
+    // ---- prologue: everything pixels 0, 1 and 2 need ---------------------------------------------------------
     if (tid < 2) { for (int i = 0; i < 2; ++i) { top1[tid].mvx[i] = 0; top1[tid].mvy[i] = 0; top1[tid].cost[i] = 0; } }
-    if (tid < 9) { Top2 z; for (int i = 0; i < 2; ++i) { z.mvx[i] = z.mvy[i] = z.cost[i] = 0; } hint[tid / 3][tid % 3] = z; }   // ring rows start zeroed
-    if (tid < NGD) { pent[0][tid] = make_int4(0, 0, 0, 0); }
+    if (tid < 12) { Top2 z; for (int i = 0; i < 2; ++i) { z.mvx[i] = z.mvy[i] = z.cost[i] = 0; } hint[tid / 3][tid % 3] = z; }   // ring rows start zeroed
+    if (tid < NGD) { pxy[0][tid] = make_int2(0, 0); pz[0][tid] = 0; }
     if (tid < 31 && !prm.rand_stream) rstate[tid] = prm.rng_state[pair * 31 + tid];
     if (tid == 0) { rf = 3; rr = 0; }
-    if (tid >= 64 && tid < 89) c1win[0][tid - 64] = load_c1(0, 0, tid - 64);
-    if (tid >= 96 && tid < 121 && N > 1) c1win[1][tid - 96] = load_c1(1 % W, 1 / W, tid - 96);
-    for (int i = tid; i < 4 * 12 * 64; i += NG_THREADS) (&T[0][0][0])[i] = 0xFFu;
+    if (tid >= 64 && tid < 64 + 75) {
+        const int q = (tid - 64) / 25, k = (tid - 64) % 25;
+        if ((size_t)q < N) c1win[q][k] = load_c1(q % W, q / W, k);
+    }
+    for (int i = tid; i < 4 * 12 * NG_TP; i += NG_THREADS) (&T[0][0][0])[i] = 0xFFu;
     __syncthreads();
-    if (tid == 0) { gen_rnd(0); if (N > 1) gen_rnd(1); }
+    if (tid == 0) { for (int q = 0; q < 3 && (size_t)q < N; ++q) gen_rnd(q, q); }
     __syncthreads();
-    make_candidates(0, 0, 0, 0, tid, NG_THREADS);
+    if (tid < NGD) make_candidate(tid, 0, 0, 0, 0, 0);
+    else if (tid >= 128 && tid < 128 + NGD - NFRESH && N > 1) make_candidate(tid - 128 + NFRESH, 1, 1, 1, 1 % W, 1 / W);
     __syncthreads();
 
-    int x = 0, y = 0, p3 = 0;                                 // p3 = p % 3
+    int x = 0, y = 0, p3 = 0, p4 = 0;                         // p3 = p % 3, p4 = p % 4
     for (size_t p = 0; p < N; ++p) {
         const int curRow = (y + 1) & 1;
-        const int cp = (int)(p & 1), cur1 = (int)((p + 1) & 1);
+        const int cur1 = (int)((p + 1) & 1);
         const bool startX = (x == 0), startY = (y == 0), startR = (x == W - 1);
-        const size_t p1 = p + 1, p2 = p + 2;
+        const size_t p1 = p + 1, p2 = p + 2, p3n = p + 3;
         const int x1n = x + 1 == W ? 0 : x + 1, y1n = x + 1 == W ? y + 1 : y;
         const int x2n = x1n + 1 == W ? 0 : x1n + 1, y2n = x1n + 1 == W ? y1n + 1 : y1n;
+        const int x3n = x2n + 1 == W ? 0 : x2n + 1, y3n = x2n + 1 == W ? y2n + 1 : y2n;
+        const int cp = p3;                                    // candidate buffer of this pixel
 
         // ---- phase X ----------------------------------------------------------------------------------------------
-        // register prefetch (consumed in phase Y): predecessor rows + previous minima of p+1, stale hints + census of p+2
+        // register prefetch (consumed in phase Y): predecessor rows + previous minima of p+1, stale row slots + census of p+3
         int2 pf_mv = make_int2(0, 0); int pf_c = 0; bool pf_ok = false;
         Top2 pf_hint; uint32_t pf_c1 = 0; int pf_min = 0;
         if (p1 < N && y1n > 0) {
@@ -389,14 +399,14 @@ ng_pipe_kernel(const NgParams prm)
                     pf_c = (int)Lrow[((size_t)q * 2 * W + cell) * NGD + d];
                     pf_ok = true;
                 }
-            } else if (tid >= 400 && tid < 403) {
-                const int q = tid - 400, xs = x1n + q - 1;
+            } else if (tid >= 330 && tid < 333) {
+                const int q = tid - 330, xs = x1n + q - 1;
                 if (xs >= 0 && xs < W) pf_min = toprow[((size_t)q * 2 + preRow1) * W + xs].cost[0] & 0xFF;
             }
         }
-        if (p2 < N) {
-            if (tid >= 324 && tid < 327) pf_hint = toprow[((size_t)(tid - 324) * 2 + ((y2n + 1) & 1)) * W + x2n];
-            if (tid >= 352 && tid < 377) pf_c1 = load_c1(x2n, y2n, tid - 352);
+        if (p3n < N) {
+            if (tid >= 324 && tid < 327) pf_hint = toprow[((size_t)(tid - 324) * 2 + ((y3n + 1) & 1)) * W + x3n];
+            if (tid >= 352 && tid < 377) pf_c1 = load_c1(x3n, y3n, tid - 352);
         }
         if (warp < 14) {
             // A predecessor's 108 entries are twelve 3 x 3 grids of consecutive flow vectors (hint + offset, offy outer).  For a
@@ -409,11 +419,11 @@ ng_pipe_kernel(const NgParams prm)
             // parameter domain is excluded.
             if (tid < 336) {
                 const int uy = tid / 48, r = tid - uy * 48, dir = r / 12, g = r - dir * 12;
-                const int4* e = pent[dir] + g * 9;
+                const int* e = pz[dir] + g * 9;
                 uint32_t z[9], a[9];
 #pragma unroll
-                for (int c = 0; c < 9; ++c) { z[c] = (uint32_t)e[c].z; a[c] = (z[c] + (uint32_t)prm.P1) & 0xFFu; }
-                if (uy == 0) corner[dir][g] = make_int2(e[0].x - 2, e[0].y - 2);
+                for (int c = 0; c < 9; ++c) { z[c] = (uint32_t)e[c]; a[c] = (z[c] + (uint32_t)prm.P1) & 0xFFu; }
+                if (uy == 0) { const int2 c0 = pxy[dir][g * 9]; corner[dir][g] = make_int2(c0.x - 2, c0.y - 2); }
                 uint32_t* t = &T[dir][g][uy * 8];
                 // rows [uy-4, uy] clipped to [0, 2]
                 const bool r0 = uy <= 4, r1 = uy >= 1 && uy <= 5, r2 = uy >= 2;
@@ -426,13 +436,13 @@ ng_pipe_kernel(const NgParams prm)
                 if (uy < 2 || uy > 4) { const uint32_t m = min(m01, c2); t[2] = m; t[3] = m; t[4] = m; }
                 else {
                     // the equal cell lies in row uy - 2: the whole grid minus that cell, and the cell's own cost
-                    const int rr = uy - 2;
+                    const int rr_ = uy - 2;
                     const uint32_t f0 = min(min(a[0], a[1]), a[2]), f1 = min(min(a[3], a[4]), a[5]), f2 = min(min(a[6], a[7]), a[8]);
-                    const uint32_t o = rr == 0 ? min(f1, f2) : rr == 1 ? min(f0, f2) : min(f0, f1);
-                    const uint32_t b0 = rr == 0 ? a[0] : rr == 1 ? a[3] : a[6], b1 = rr == 0 ? a[1] : rr == 1 ? a[4] : a[7],
-                                   b2 = rr == 0 ? a[2] : rr == 1 ? a[5] : a[8];
-                    const uint32_t s0 = rr == 0 ? z[0] : rr == 1 ? z[3] : z[6], s1 = rr == 0 ? z[1] : rr == 1 ? z[4] : z[7],
-                                   s2 = rr == 0 ? z[2] : rr == 1 ? z[5] : z[8];
+                    const uint32_t o = rr_ == 0 ? min(f1, f2) : rr_ == 1 ? min(f0, f2) : min(f0, f1);
+                    const uint32_t b0 = rr_ == 0 ? a[0] : rr_ == 1 ? a[3] : a[6], b1 = rr_ == 0 ? a[1] : rr_ == 1 ? a[4] : a[7],
+                                   b2 = rr_ == 0 ? a[2] : rr_ == 1 ? a[5] : a[8];
+                    const uint32_t s0 = rr_ == 0 ? z[0] : rr_ == 1 ? z[3] : z[6], s1 = rr_ == 0 ? z[1] : rr_ == 1 ? z[4] : z[7],
+                                   s2 = rr_ == 0 ? z[2] : rr_ == 1 ? z[5] : z[8];
                     t[2] = min(o, min(b1, b2)) | ((s0 & 0xFFu) << 16) | 0x01000000u;
                     t[3] = min(o, min(b0, b2)) | ((s1 & 0xFFu) << 16) | 0x01000000u;
                     t[4] = min(o, min(b0, b1)) | ((s2 & 0xFFu) << 16) | 0x01000000u;
@@ -458,7 +468,7 @@ ng_pipe_kernel(const NgParams prm)
                     for (int g = 0; g < 12; ++g) {
                         const int2 c0 = cr[g];
                         const uint32_t ux = min((uint32_t)(mx - c0.x), 7u), uy = min((uint32_t)(my - c0.y), 7u);
-                        const uint32_t e = Td[g * 64 + uy * 8 + ux];
+                        const uint32_t e = Td[g * NG_TP + uy * 8 + ux];
                         acc = __vminu2(acc, e);
                         se = e >= 0x01000000u ? e : se;                                        // later grids overwrite: last match wins (:71-72)
                     }
@@ -467,8 +477,9 @@ ng_pipe_kernel(const NgParams prm)
                 }
                 Lc[dir][d] = out;
             }
-        } else if (p1 < N) {
-            make_candidates(p1, p3 == 2 ? 0 : p3 + 1, x1n, y1n, tid - 14 * 32, NG_THREADS - 14 * 32);
+        } else if (warp == 14 && lane < NFRESH && p1 < N) {
+            // the L1 ring slot pixel p+1 takes its hints from was written by pixel p-1 (:276-277): only these wait for it
+            make_candidate(lane, p1, p3 == 2 ? 0 : p3 + 1, (p4 + 1) & 3, x1n, y1n);
         }
         __syncthreads();
 
@@ -477,8 +488,8 @@ ng_pipe_kernel(const NgParams prm)
             const int dir = warp;
             const bool start = dir == 0 ? startX : dir == 1 ? (startX || startY) : dir == 2 ? startY : (startY || startR);
             Top2* slot = (dir == 0) ? &top1[cur1] : &toprow[((size_t)(dir - 1) * 2 + curRow) * W + x];
-            // stale content is part of the reference's behaviour; the row slots were fetched two pixels ago (hint[])
-            const Top2 old = (dir == 0) ? top1[cur1] : hint[p3][dir - 1];
+            // stale content is part of the reference's behaviour; the row slots were fetched three pixels ago (hint[])
+            const Top2 old = (dir == 0) ? top1[cur1] : hint[p4][dir - 1];
             Top2 nw = old;
             if (start) nw.cost[0] = 0;
             else {
@@ -526,12 +537,12 @@ ng_pipe_kernel(const NgParams prm)
                 prm.flow[(size_t)pair * 2 * N + p] = (double)cmx[cp][d];
                 prm.flow[(size_t)pair * 2 * N + N + p] = (double)cmy[cp][d];
             }
-        } else if (warp == 5 || warp == 6 || warp == 7 || warp == 8) {
+        } else if (warp >= 5 && warp <= 8) {
             // ring commits of pixel p: candidate mvs + L2,L3,L4 costs to the row rings, L1 entries for the next pixel
             const size_t cell = (size_t)curRow * W + x;
             for (int i = tid - 160; i < NGD; i += 128) {
                 *reinterpret_cast<int2*>(mvrow + (cell * NGD + i) * 2) = make_int2(cmx[cp][i], cmy[cp][i]);
-                pent[0][i] = make_int4(cmx[cp][i], cmy[cp][i], Lc[0][i], 0);
+                pxy[0][i] = make_int2(cmx[cp][i], cmy[cp][i]); pz[0][i] = Lc[0][i];
 #pragma unroll
                 for (int q = 0; q < 3; ++q) Lrow[((size_t)q * 2 * W + cell) * NGD + i] = (int16_t)Lc[q + 1][i];
                 if (prm.Cent) {
@@ -539,17 +550,20 @@ ng_pipe_kernel(const NgParams prm)
                     e[0] = cmx[cp][i]; e[1] = cmy[cp][i]; e[2] = ccost[cp][i];
                 }
             }
+            if (tid == 287 && p3n < N) gen_rnd(p3n, p3);                                   // (p + 3) % 3
+        } else if (warp >= 12 && tid < 384 + NGD - NFRESH && p2 < N) {
+            // the 90 candidates of pixel p+2 whose hints are a row old (fetched during pixel p-1) or random
+            make_candidate(tid - 384 + NFRESH, p2, p3 == 0 ? 2 : p3 - 1, (p4 + 2) & 3, x2n, y2n);
         }
-        // prefetched rows -> shared memory (pent[1..3] were last read in phase X of this pixel)
-        if (pf_ok) pent[1 + tid / NGD][tid % NGD] = make_int4(pf_mv.x, pf_mv.y, pf_c, 0);
-        if (tid >= 400 && tid < 403) preMin[1 + tid - 400] = pf_min;
-        if (p2 < N) {
-            if (tid >= 324 && tid < 327) hint[p3 == 0 ? 2 : p3 - 1][tid - 324] = pf_hint;
-            if (tid >= 352 && tid < 377) c1win[p2 & 1][tid - 352] = pf_c1;
-            if (tid == 384) gen_rnd(p2);
+        // prefetched rows -> shared memory (pxy / pz[1..3] were last read in phase X of this pixel)
+        if (pf_ok) { pxy[1 + tid / NGD][tid % NGD] = pf_mv; pz[1 + tid / NGD][tid % NGD] = pf_c; }
+        if (tid >= 330 && tid < 333) preMin[1 + tid - 330] = pf_min;
+        if (p3n < N) {
+            if (tid >= 324 && tid < 327) hint[(p4 + 3) & 3][tid - 324] = pf_hint;
+            if (tid >= 352 && tid < 377) c1win[p3][tid - 352] = pf_c1;                    // (p + 3) % 3
         }
         __syncthreads();
-        x = x1n; y = y1n; p3 = p3 == 2 ? 0 : p3 + 1;
+        x = x1n; y = y1n; p3 = p3 == 2 ? 0 : p3 + 1; p4 = (p4 + 1) & 3;
     }
 }
 
