@@ -528,7 +528,7 @@ def workload_D(env: Env):
     fp = synth.flow_pair(W, H, seed=2, umax=20, vmax=10)
     out = {}
     # ---- ng: one pair per CTA (raster-serial chain inside a pair), so a step is a batch of >= one pair per SM ----------------------
-    n = env.args.ng_pairs or 3 * sm                      # three pairs resident per SM (fsgm_tune key 3 picks it from the batch size)
+    n = env.args.ng_pairs or 2 * sm                      # two pairs resident per SM (fsgm_tune key 3 picks it from the batch size)
     I1 = torch.from_numpy(np.stack([fp["I1"]] * n)).cuda(); I2 = torch.from_numpy(np.stack([fp["I2"]] * n)).cuda()
     mC = torch.empty((n, H, W), dtype=torch.int32, device="cuda"); fl = torch.empty((n, 2, H, W), dtype=torch.float64, device="cuda")
     seeds = list(range(1, n + 1))

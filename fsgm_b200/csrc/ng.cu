@@ -270,8 +270,8 @@ ng_kernel(const NgParams prm)
 // Candidates live in three buffers (pixel q: q % 3), the stale row slots in four (q % 4).
 // ------------------------------------------------------------------------------------------------------------
 // OCC = CTAs (pairs) resident per SM.  The walk is a chain of dependent phases separated by block barriers, so one CTA leaves most
-// issue slots empty; a second and third pair on the same SM fill them.  OCC = 2 fits without spills (64 registers per thread),
-// OCC = 3 caps the kernel at 40 registers (a few spilled words in the candidate builder).
+// issue slots empty; a second pair on the same SM fills them.  OCC = 2 fits in 64 registers per thread; OCC = 3 caps the kernel
+// at 40 registers and spills (slower than 2, kept for A/B through fsgm_tune key 3).
 template <int OCC>
 __global__ void __launch_bounds__(NG_THREADS, OCC)
 ng_pipe_kernel(const NgParams prm)
@@ -598,7 +598,8 @@ int launch_ng(fsgm_ctx* c, int n, const uint8_t* I1, const uint32_t* cen1, const
     p.rng_state = d_state;
     if (W >= 4) {                                    // pipelined phases need p+1 / p+2 to lie outside the cells pixel p commits
         // resident pairs per SM: as many as the batch can use (a single pair runs fastest with all the registers)
-        const int occ = c->ng_occupancy > 0 ? c->ng_occupancy : (n > 2 * c->sm_count ? 3 : n > c->sm_count ? 2 : 1);
+        // measured on 1242 x 48 strips: 108 / 152 / 146 pairs/s at 1 / 2 / 3 pairs per SM (the third costs spills at 40 registers)
+        const int occ = c->ng_occupancy > 0 ? c->ng_occupancy : (n > c->sm_count ? 2 : 1);
         if (occ >= 3) ng_pipe_kernel<3><<<n, NG_THREADS, 0, c->stream>>>(p);
         else if (occ == 2) ng_pipe_kernel<2><<<n, NG_THREADS, 0, c->stream>>>(p);
         else ng_pipe_kernel<1><<<n, NG_THREADS, 0, c->stream>>>(p);

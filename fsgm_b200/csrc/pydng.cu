@@ -151,9 +151,12 @@ struct NgSweepParams {
 // there is one; row / column S + 4 = 0xFF (written once).  The table is built separably (window minima along y with and
 // without the centre, then along x), and the search is ONE look-up per candidate and grid: 9 instead of 9 S^2 entry tests.
 template <int S> struct PydngSmem {
-    static constexpr int SS = S * S, D = 9 * SS, NJ = (D + 31) / 32, NE = NJ * 32, TW = S + 5, TV = S + 4;
+    static constexpr int SS = S * S, D = 9 * SS, NJ = (D + 31) / 32, NE = NJ * 32, TV = S + 4;
+    static constexpr int TW = S + 6;                                // table pitch: TV entries + the invalid one, odd (S is odd): the
+                                                                    // builders of neighbouring columns / grids hit different banks
     static constexpr int TVP = (TV + 1) / 2;                        // u16 pairs per window-minimum row
-    static constexpr int ints_per_warp = 6 * NE + 9 * TW * TW + 9 * S * 2 * TVP;
+    static constexpr int VP = 2 * TVP + 1;                          // words per (grid, column) row pair, odd
+    static constexpr int ints_per_warp = 6 * NE + 9 * TW * TW + 9 * S * VP;
     static constexpr size_t bytes = (size_t)NG_WARPS * ints_per_warp * 4;
 };
 
@@ -162,7 +165,7 @@ __global__ void __launch_bounds__(NG_WARPS * 32)
 pydng_sweep_kernel(const NgSweepParams prm)
 {
     using SM = PydngSmem<S>;
-    constexpr int SS = SM::SS, D = SM::D, NJ = SM::NJ, NE = SM::NE, TW = SM::TW, TV = SM::TV, TVP = SM::TVP;
+    constexpr int SS = SM::SS, D = SM::D, NJ = SM::NJ, NE = SM::NE, TW = SM::TW, TV = SM::TV, TVP = SM::TVP, VP = SM::VP;
     extern __shared__ __align__(16) int pydng_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     int* base = pydng_smem + wib * SM::ints_per_warp;
@@ -255,8 +258,8 @@ pydng_sweep_kernel(const NgSweepParams prm)
                     }
 #pragma unroll
                     for (int w = 0; w < TVP; ++w) {
-                        V[i * 2 * TVP + w] = v[2 * w] | (v[2 * w + 1] << 16);
-                        V[i * 2 * TVP + TVP + w] = vx[2 * w] | (vx[2 * w + 1] << 16);
+                        V[i * VP + w] = v[2 * w] | (v[2 * w + 1] << 16);
+                        V[i * VP + TVP + w] = vx[2 * w] | (vx[2 * w + 1] << 16);
                     }
                 }
                 __syncwarp();
@@ -271,7 +274,7 @@ pydng_sweep_kernel(const NgSweepParams prm)
                     for (int q = 0; q < 5; ++q) {
                         const int ox = ux - 4 + q;
                         if (ox >= 0 && ox < S) {
-                            const uint32_t* row = V + (h * S + ox) * 2 * TVP + (q == 2 ? TVP : 0);
+                            const uint32_t* row = V + (h * S + ox) * VP + (q == 2 ? TVP : 0);
 #pragma unroll
                             for (int w = 0; w < TVP; ++w) m[w] = __vminu2(m[w], row[w]);
                         }
