@@ -741,7 +741,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--skip", default="", help="comma-separated side workloads to skip: A,C,D,strong_256,dirsplit_4k")
-    ap.add_argument("--ng-pairs", type=int, default=0, help="pairs per step of the ng workload (default: three per SM)")
+    ap.add_argument("--ng-pairs", type=int, default=0, help="pairs per step of the ng workload (default: two per SM)")
     ap.add_argument("--no-overlap", action="store_true", help="A/B knob (fsgm_tune key 2): disable the two-stream wave pipeline")
     ap.add_argument("--tune-cluster", type=int, default=0,
                     help="A/B knob (fsgm_tune key 1): 0 auto, -1 generic sweeps only, 1/2/4/8 cluster size")

@@ -52,7 +52,7 @@ size_t pyd_scratch_bytes(int n, int W, int H, int D)
     const size_t N = (size_t)W * H;
     // generic path: C + 8 L volumes of D bytes per pixel; cluster path: 4 padded volumes (<= 176 B per pixel) + records + flags
     return 2 * align256(n * N * 4) + std::max(std::max(9 * align256(n * N * D), 4 * align256(n * N * 176) + align256(n * N * 16) + align256(n * N)),
-                                              9 * align256(n * N * 176) + 9 * align256(n * N * 4) + 256);
+                                              9 * align256(n * N * 176) + 9 * align256(n * N * 4) + align256((size_t)n * 8) + 256);
 }
 
 // The lane = path kernels (pydl.cu): cost volume and per-direction volumes as [y][label column][x][16-byte frame], shift
@@ -71,7 +71,7 @@ int pyd_pipeline_lane(fsgm_ctx* c, int n, const uint32_t* cen1, const uint32_t* 
     } else {
         uint32_t *list, *count;
         FSGM_TRY(arena_get(c, n * N, &list));
-        FSGM_TRY(arena_get(c, (size_t)n, &count));
+        FSGM_TRY(arena_get(c, (size_t)2 * n, &count));
         FSGM_TRY(launch_pyd_cost_sep(c, n, cen1, cen2, W, H, d_preMv, mvW, mvH, g.agg, g.rx, g.ry, C, list, count));
     }
     FSGM_TRY(launch_pydl_desc(c, n, d_preMv, mvW, mvH, W, H, g.Sx, g.Sy, dirs, nd, desc, c->pyd_cluster == -2));

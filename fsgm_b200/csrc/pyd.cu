@@ -412,17 +412,26 @@ pyd_cost_px_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restrict
 
     const int xblocks = (W + 31) / 32;
     const int job = blockIdx.x * PYC_WARPS + wib;
-    if (job >= xblocks * H) return;                      // warps are independent (only __syncwarp below)
+    if (job >= xblocks * H + (list ? 1 : 0)) return;     // warps are independent (only __syncwarp below); the two-ended list rounds up twice
     const size_t N = (size_t)W * H;
     const int pair = blockIdx.y;
     int y = job / xblocks, x0 = (job - y * xblocks) * 32, x = min(x0 + lane, W - 1);      // lanes past the row end repeat its last pixel
     int nlive = min(32, W - x0);
     if (list) {
-        const int cnt = (int)list_count[pair];
-        if (job * 32 >= cnt) return;
-        nlive = min(32, cnt - job * 32);
-        const uint32_t pi = list[(size_t)pair * N + job * 32 + min(lane, nlive - 1)];
-        y = (int)(pi / (uint32_t)W); x = (int)(pi - (uint32_t)y * (uint32_t)W);
+        // two-ended list (pyd_uniform_kernel): cf entries from the front, cb entries from the back; a warp never mixes them
+        const int cf = (int)list_count[2 * pair], cb = (int)list_count[2 * pair + 1];
+        const int jf = (cf + 31) / 32;
+        if (job < jf) {
+            nlive = min(32, cf - job * 32);
+            const uint32_t pi = list[(size_t)pair * N + job * 32 + min(lane, nlive - 1)];
+            y = (int)(pi / (uint32_t)W); x = (int)(pi - (uint32_t)y * (uint32_t)W);
+        } else {
+            const int jb = job - jf;
+            if (jb * 32 >= cb) return;
+            nlive = min(32, cb - jb * 32);
+            const uint32_t pi = list[(size_t)pair * N + (N - 1) - (size_t)(jb * 32 + min(lane, nlive - 1))];
+            y = (int)(pi / (uint32_t)W); x = (int)(pi - (uint32_t)y * (uint32_t)W);
+        }
     }
     const double* mvp = preMv + (size_t)pair * 2 * mvW * mvH;
     const double mvx = mvp[(size_t)mvW * y + x], mvy = mvp[(size_t)mvW * mvH + (size_t)mvW * y + x];
@@ -695,14 +704,18 @@ pyd_cost_sep_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restric
     }
 }
 
-// pixels whose aggregation window does not carry one prior (bit patterns compared): appended to the pair's list
-__global__ void pyd_uniform_kernel(const double* __restrict__ preMv, int mvW, int mvH, int W, int H, int agg,
+// pixels whose aggregation window does not carry one prior (bit patterns compared): appended to the pair's list.  The list is
+// filled from both ends: pixels for which every tap of pyd_cost_px_kernel is certainly inside both images (window and the
+// displaced window with a margin for the rounding of the prior) from the front, count[2 * pair]; the others from the back,
+// count[2 * pair + 1] — so that the 32 lanes of a warp of the list kernel take its check-free path together, which 32 pixels
+// appended in arrival order almost never do (one lane near the image border is enough).
+__global__ void pyd_uniform_kernel(const double* __restrict__ preMv, int mvW, int mvH, int W, int H, int agg, int rx, int ry,
                                    uint32_t* __restrict__ list, uint32_t* __restrict__ count)
 {
     const size_t N = (size_t)W * H;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int pair = blockIdx.y;
-    bool flag = false;
+    bool flag = false, inner = false;
     if (i < N) {
         const int y = (int)(i / W), x = (int)(i - (size_t)y * W);
         const long long* mx = reinterpret_cast<const long long*>(preMv) + (size_t)pair * 2 * mvW * mvH;
@@ -717,14 +730,30 @@ __global__ void pyd_uniform_kernel(const double* __restrict__ preMv, int mvW, in
                 flag |= mx[(size_t)mvW * yy + xx] != cx || my[(size_t)mvW * yy + xx] != cy;
             }
         }
+        // conservative: the sample coordinates are (int)(s + mv + 0.5), s within rx + agg (ry + agg) of the pixel
+        const double fx = __longlong_as_double(cx), fy = __longlong_as_double(cy);
+        const double mxr = (double)(rx + agg + 2), myr = (double)(ry + agg + 2);
+        inner = x >= agg && x + agg < W && y >= agg && y + agg < H &&
+                (double)x + fx - mxr >= 0.0 && (double)x + fx + mxr <= (double)(W - 1) &&
+                (double)y + fy - myr >= 0.0 && (double)y + fy + myr <= (double)(H - 1);     // false for NaN
     }
-    const unsigned mask = __ballot_sync(0xffffffffu, flag);
-    if (!mask) return;
-    const int lane = threadIdx.x & 31;
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(count + pair, (uint32_t)__popc(mask));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (flag) list[(size_t)pair * N + base + __popc(mask & ((1u << lane) - 1u))] = (uint32_t)i;
+    // one append per block and class: the block's flagged pixels (128 consecutive pixels of a row) stay together in the list, so a
+    // warp of the list kernel gathers from one or two row segments instead of wherever concurrently running warps appended
+    __shared__ uint32_t wc[2][4], wb[2];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const unsigned mi = __ballot_sync(0xffffffffu, flag && inner), mo = __ballot_sync(0xffffffffu, flag && !inner);
+    if (lane == 0) { wc[0][wib] = (uint32_t)__popc(mi); wc[1][wib] = (uint32_t)__popc(mo); }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        const uint32_t t = wc[threadIdx.x][0] + wc[threadIdx.x][1] + wc[threadIdx.x][2] + wc[threadIdx.x][3];
+        wb[threadIdx.x] = t ? atomicAdd(count + 2 * pair + threadIdx.x, t) : 0u;
+    }
+    __syncthreads();
+    uint32_t bi = wb[0], bo = wb[1];
+    for (int w = 0; w < wib; ++w) { bi += wc[0][w]; bo += wc[1][w]; }
+    const unsigned below = (1u << lane) - 1u;
+    if (flag && inner) list[(size_t)pair * N + bi + __popc(mi & below)] = (uint32_t)i;
+    if (flag && !inner) list[(size_t)pair * N + (N - 1) - (bo + __popc(mo & below))] = (uint32_t)i;
 }
 
 static size_t pyd_cost_px_smem(int agg, int rx, int ry, int pitch)
@@ -747,7 +776,7 @@ int launch_pyd_cost(fsgm_ctx* c, int n, const uint32_t* cen1, const uint32_t* ce
     const size_t smem = (agg == 1 || agg == 2) ? pyd_cost_px_smem(agg, rx, ry, pitch) : 0;
     if (pitch && !(smem && smem <= 100 * 1024)) return fail(c, FSGM_ERR_DOMAIN, "padded cost volume needs the lane = pixel cost kernel");
     if (smem && smem <= 100 * 1024) {
-        const int jobs = ((W + 31) / 32) * H;
+        const int jobs = ((W + 31) / 32) * H + (list ? 1 : 0);
         dim3 grid((unsigned)((jobs + PYC_WARPS - 1) / PYC_WARPS), n);
         if (agg == 2) {
             FSGM_CUDA(c, cudaFuncSetAttribute(pyd_cost_px_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -783,15 +812,15 @@ static int pcs_launch(fsgm_ctx* c, int n, const uint32_t* cen1, const uint32_t* 
 }
 
 // cost volume in the [y][label column][x][16-byte frame] layout: separable box filter everywhere + exact recomputation of the
-// pixels whose aggregation window sees more than one prior.  list: n*N u32, count: n u32 (scratch).
+// pixels whose aggregation window sees more than one prior.  list: n*N u32, count: 2*n u32 (scratch).
 int launch_pyd_cost_sep(fsgm_ctx* c, int n, const uint32_t* cen1, const uint32_t* cen2, int W, int H,
                         const double* preMv, int mvW, int mvH, int agg, int rx, int ry, uint8_t* C, uint32_t* list, uint32_t* count)
 {
     const size_t N = (size_t)W * H;
     {
         StageScope ss(c, ST_PYD_COST);
-        FSGM_CUDA(c, cudaMemsetAsync(count, 0, (size_t)n * 4, c->stream));
-        pyd_uniform_kernel<<<dim3((unsigned)((N + 127) / 128), n), 128, 0, c->stream>>>(preMv, mvW, mvH, W, H, agg, list, count);
+        FSGM_CUDA(c, cudaMemsetAsync(count, 0, (size_t)n * 8, c->stream));
+        pyd_uniform_kernel<<<dim3((unsigned)((N + 127) / 128), n), 128, 0, c->stream>>>(preMv, mvW, mvH, W, H, agg, rx, ry, list, count);
         FSGM_LAUNCHED(c);
         const int Sx = 2 * rx + 1;
 #define PCS_GO(A, S) FSGM_TRY((pcs_launch<A, S>(c, n, cen1, cen2, W, H, preMv, mvW, mvH, ry, C)))
