@@ -375,11 +375,14 @@ ng_pipe_kernel(const NgParams prm)
     __syncthreads();
 
     int x = 0, y = 0, p3 = 0, p4 = 0;                         // p3 = p % 3, p4 = p % 4
-    for (size_t p = 0; p < N; ++p) {
+    const uint32_t Nn = (uint32_t)N;                          // N < 2^31 (checked at launch): 32-bit pixel counters
+    const int pfq = tid / NGD, pfd = tid - pfq * NGD;         // prefetch role of threads 0..323: (row ring q, entry d)
+    const uint32_t pf_L_base = (uint32_t)pfq * 2u * (uint32_t)W * NGD + (uint32_t)pfd;
+    for (uint32_t p = 0; p < Nn; ++p) {
         const int curRow = (y + 1) & 1;
         const int cur1 = (int)((p + 1) & 1);
         const bool startX = (x == 0), startY = (y == 0), startR = (x == W - 1);
-        const size_t p1 = p + 1, p2 = p + 2, p3n = p + 3;
+        const uint32_t p1 = p + 1, p2 = p + 2, p3n = p + 3;
         const int x1n = x + 1 == W ? 0 : x + 1, y1n = x + 1 == W ? y + 1 : y;
         const int x2n = x1n + 1 == W ? 0 : x1n + 1, y2n = x1n + 1 == W ? y1n + 1 : y1n;
         const int x3n = x2n + 1 == W ? 0 : x2n + 1, y3n = x2n + 1 == W ? y2n + 1 : y2n;
@@ -389,14 +392,14 @@ ng_pipe_kernel(const NgParams prm)
         // register prefetch (consumed in phase Y): predecessor rows + previous minima of p+1, stale row slots + census of p+3
         int2 pf_mv = make_int2(0, 0); int pf_c = 0; bool pf_ok = false;
         Top2 pf_hint; uint32_t pf_c1 = 0; int pf_min = 0;
-        if (p1 < N && y1n > 0) {
+        if (p1 < Nn && y1n > 0) {
             const int preRow1 = y1n & 1;
             if (tid < 3 * NGD) {
-                const int q = tid / NGD, d = tid - q * NGD, xs = x1n + q - 1;
-                if (xs >= 0 && xs < W) {
-                    const size_t cell = (size_t)preRow1 * W + xs;
-                    pf_mv = *reinterpret_cast<const int2*>(mvrow + (cell * NGD + d) * 2);
-                    pf_c = (int)Lrow[((size_t)q * 2 * W + cell) * NGD + d];
+                const int xs = x1n + pfq - 1;
+                if ((unsigned)xs < (unsigned)W) {
+                    const uint32_t cell = (uint32_t)(preRow1 * W + xs);
+                    pf_mv = *reinterpret_cast<const int2*>(mvrow + (cell * NGD + (uint32_t)pfd) * 2u);
+                    pf_c = (int)Lrow[cell * NGD + pf_L_base];
                     pf_ok = true;
                 }
             } else if (tid >= 330 && tid < 333) {
@@ -404,7 +407,7 @@ ng_pipe_kernel(const NgParams prm)
                 if (xs >= 0 && xs < W) pf_min = toprow[((size_t)q * 2 + preRow1) * W + xs].cost[0] & 0xFF;
             }
         }
-        if (p3n < N) {
+        if (p3n < Nn) {
             if (tid >= 324 && tid < 327) pf_hint = toprow[((size_t)(tid - 324) * 2 + ((y3n + 1) & 1)) * W + x3n];
             if (tid >= 352 && tid < 377) pf_c1 = load_c1(x3n, y3n, tid - 352);
         }
@@ -477,7 +480,7 @@ ng_pipe_kernel(const NgParams prm)
                 }
                 Lc[dir][d] = out;
             }
-        } else if (warp == 14 && lane < NFRESH && p1 < N) {
+        } else if (warp == 14 && lane < NFRESH && p1 < Nn) {
             // the L1 ring slot pixel p+1 takes its hints from was written by pixel p-1 (:276-277): only these wait for it
             make_candidate(lane, p1, p3 == 2 ? 0 : p3 + 1, (p4 + 1) & 3, x1n, y1n);
         }
@@ -550,15 +553,15 @@ ng_pipe_kernel(const NgParams prm)
                     e[0] = cmx[cp][i]; e[1] = cmy[cp][i]; e[2] = ccost[cp][i];
                 }
             }
-            if (tid == 287 && p3n < N) gen_rnd(p3n, p3);                                   // (p + 3) % 3
-        } else if (warp >= 12 && tid < 384 + NGD - NFRESH && p2 < N) {
+            if (tid == 287 && p3n < Nn) gen_rnd(p3n, p3);                                   // (p + 3) % 3
+        } else if (warp >= 12 && tid < 384 + NGD - NFRESH && p2 < Nn) {
             // the 90 candidates of pixel p+2 whose hints are a row old (fetched during pixel p-1) or random
             make_candidate(tid - 384 + NFRESH, p2, p3 == 0 ? 2 : p3 - 1, (p4 + 2) & 3, x2n, y2n);
         }
         // prefetched rows -> shared memory (pxy / pz[1..3] were last read in phase X of this pixel)
-        if (pf_ok) { pxy[1 + tid / NGD][tid % NGD] = pf_mv; pz[1 + tid / NGD][tid % NGD] = pf_c; }
+        if (pf_ok) { pxy[1 + pfq][pfd] = pf_mv; pz[1 + pfq][pfd] = pf_c; }
         if (tid >= 330 && tid < 333) preMin[1 + tid - 330] = pf_min;
-        if (p3n < N) {
+        if (p3n < Nn) {
             if (tid >= 324 && tid < 327) hint[(p4 + 3) & 3][tid - 324] = pf_hint;
             if (tid >= 352 && tid < 377) c1win[p3][tid - 352] = pf_c1;                    // (p + 3) % 3
         }
@@ -596,7 +599,7 @@ int launch_ng(fsgm_ctx* c, int n, const uint8_t* I1, const uint32_t* cen1, const
         FSGM_CUDA(c, cudaStreamSynchronize(c->stream));       // host_rng_states is a caller temporary
     }
     p.rng_state = d_state;
-    if (W >= 4) {                                    // pipelined phases need p+1 / p+2 to lie outside the cells pixel p commits
+    if (W >= 4 && (size_t)W * H < ((size_t)1 << 31)) {  // pipelined phases need p+1 .. p+3 to lie outside the cells pixel p commits; 32-bit pixel counters
         // resident pairs per SM: as many as the batch can use (a single pair runs fastest with all the registers)
         // measured on 1242 x 48 strips: 108 / 152 / 146 pairs/s at 1 / 2 / 3 pairs per SM (the third costs spills at 40 registers)
         const int occ = c->ng_occupancy > 0 ? c->ng_occupancy : (n > c->sm_count ? 2 : 1);
