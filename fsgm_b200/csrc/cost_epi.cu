@@ -11,6 +11,7 @@
 //
 // Layout: label-contiguous u8 [pair][y][x][d]; a warp writes 128 B (uchar4 per lane) per store.
 #include "fsgm_internal.h"
+#include <type_traits>
 
 namespace fsgm {
 
@@ -209,6 +210,34 @@ __device__ __forceinline__ uint32_t ref_round_clamp_w(double w, uint32_t hi)
     return min((f + 1u) >> 1, hi);
 }
 
+// The fast loop keeps the clamped value DOUBLED, k = min(floor(w) + 1, 2*hi + 1) (round(v) = k >> 1), so that add and clamp are
+// one instruction (VIADDMNMX.U32: the add wraps, 0xFFFFFFFF + 1 -> 0 as above) and the shift is all that is left.
+#ifndef FSGM_FC_VARIANT
+#define FSGM_FC_VARIANT 2            // A/B (tools/build_variant.sh, 60 pairs per step): 0 = round-1 loop 1912 pairs/s, 1 = VIADDMNMX form 1981, 2 = magic-number form 2013
+#endif
+#ifndef FSGM_FC_ASYNC
+#define FSGM_FC_ASYNC 1
+#endif
+__device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ uint32_t h2fma(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+__device__ __forceinline__ uint32_t ref_round_clamp_k(double w, uint32_t k2)
+{
+#if FSGM_FC_VARIANT == 2
+    // floor(w) + 1 as the low mantissa word of w + (1.5 * 2^52 + 1) rounded down (two's complement for negative w; exact for
+    // |w| < 2^31 - 2, which the staging step checks per pixel), clamped to [0, k2] by one VIMNMX.RELU: the conversion moves from
+    // the quarter-rate XU pipe to the fp64 pipe.
+    const int L = __double2loint(__dadd_rd(w, 6755399441055745.0));
+    return (uint32_t)__vimin_s32_relu(L, (int)k2);
+#else
+    return __viaddmin_u32(__double2uint_rd(w), 1u, k2);
+#endif
+}
+
 // (u8)(1.0*s/25 + 0.5) == (2s + 25)/50 == (s*2622 + 32775) >> 16 for s <= 600; the quotient (<= 24) is byte 2 of the product
 __device__ __forceinline__ uint32_t box_norm4_fast(uint32_t lo, uint32_t hi)   // lo: labels 0,2 as u16x2; hi: labels 1,3
 {
@@ -248,10 +277,26 @@ epi_cost_fused_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restr
     const double* DrX = dirn + (size_t)pair * 2 * N; const double* DrY = DrX + N;
     const double* Op = O + pair * N;
     uint32_t* Cout = reinterpret_cast<uint32_t*>(C + pair * N * (size_t)(4 * D4)) + q;
-    const int lane = tid & 31, warp = tid >> 5;
+    const int lane = tid & 31, warp = __shfl_sync(0xFFFFFFFFu, tid >> 5, 0);      // warp-uniform for the compiler: label-table addresses live in uniform registers
+#if FSGM_FC_VARIANT == 2
+    // upper bound of |vz| over the table (high word + 1; inf / NaN give a non-finite bound and every pixel takes the checked path)
+    uint32_t* vzhi_s = gcen + 2 * NPIX;
+    if (tid == 0) *vzhi_s = 0;
+    __syncthreads();
+    uint32_t vzhi = 0;
+    for (int i = tid; i < 4 * D4; i += FC_THREADS) { const double v = vz[i]; vzs[i] = v; vzhi = max(vzhi, (uint32_t)__double2hiint(fabs(v))); }
+    vzhi = __reduce_max_sync(0xFFFFFFFFu, vzhi);
+    if ((tid & 31) == 0) atomicMax(vzhi_s, vzhi);
+    __syncthreads();
+    const double vzmax = __hiloint2double((int)(*vzhi_s + 1u), 0);
+#else
     for (int i = tid; i < 4 * D4; i += FC_THREADS) vzs[i] = vz[i];
+#endif
     const int yend = min(y0 + FC_TY, H);
     const uint32_t wmax = (uint32_t)(W - 1), hmax = (uint32_t)(H - 1);
+    const uint32_t wk2 = 2u * wmax + 1u, hk2 = 2u * hmax + 1u, Wu = (uint32_t)W;
+    const uint32_t* c2w = cen2 + pair * N;
+    (void)wk2; (void)hk2; (void)Wu; (void)c2w;
 
     for (int i = tid; i < 5 * FC_TX * D4; i += FC_THREADS) hring[i] = 0;      // rows before the window count as zero
     uint32_t vlo[XP], vhi[XP];                                               // running vertical 5-sums (u16x2) per column
@@ -263,6 +308,7 @@ epi_cost_fused_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restr
     // barriers instead of three.  `slow` = some pixel of the strip row can produce NaN (checked path, CTA-uniform branch).
     // (One barrier per row — raw row double-buffered, geometry staged two rows ahead, vz read with __ldg — was measured slower,
     // 10.15 -> 10.59 ms per 60 pairs: at four CTAs per SM the extra 7 KB per CTA leave the gathers half the L1.)
+#if !FSGM_FC_ASYNC
     auto load_geo = [&](int r, double (&a)[5], uint32_t& cen) {
         const int yc = min(max(r, 0), H - 1), xc = min(max(x0 - 2 + tid, 0), W - 1);
         const size_t p = (size_t)yc * W + xc;
@@ -275,24 +321,74 @@ epi_cost_fused_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restr
         g[0] = __dmul_rn(__dsub_rn(a[0], 1.0), 2.0); g[1] = __dmul_rn(__dsub_rn(a[1], 1.0), 2.0);
         g[2] = a[2]; g[3] = a[3]; g[4] = __dmul_rn(a[4], 2.0);
         gcen[buf * NPIX + tid] = cen;
+#if FSGM_FC_VARIANT == 2
+        // every |w| of this pixel stays below 2^30 (NaN anywhere fails the comparison): the magic-number conversion is exact
+        const double reach = __dmul_rn(fabs(g[4]), vzmax);
+        const bool fin = __dadd_rn(fabs(g[0]), __dmul_rn(reach, fabs(a[2]))) < 1073741824.0 &&
+                         __dadd_rn(fabs(g[1]), __dmul_rn(reach, fabs(a[3]))) < 1073741824.0;
+#else
         const bool fin = isfinite(a[0]) && isfinite(a[1]) && isfinite(a[2]) && isfinite(a[3]) && fabs(a[4]) <= 1e300;
+#endif
         return fin ? 0 : 1;
     };
+#endif
+#if FSGM_FC_ASYNC
+    // Geometry rows travel global -> shared by cp.async, one 8-byte (census: 4-byte) element per thread, a row ahead: no staging
+    // registers live across the raw-cost phase (at 64 registers per thread the eleven of them cost rematerialised addresses all
+    // over the row loop).  Each warp turns the raw planes of its lane's pixel into the doubled constants itself and votes on the
+    // checked path, so the row's second barrier carries no reduction.
+    constexpr int GEO_T = 6 * NPIX;                                           // threads that copy: plane = tid / NPIX, pixel = tid % NPIX
+    static_assert(GEO_T <= FC_THREADS, "one geometry element per thread");
+    const int gpl = tid / NPIX, gpx = tid - gpl * NPIX;
+    const int gxc = min(max(x0 - 2 + gpx, 0), W - 1);
+    const char* gsrc = gpl == 0 ? (const char*)PdX : gpl == 1 ? (const char*)PdY : gpl == 2 ? (const char*)DrX : gpl == 3 ? (const char*)DrY
+                     : gpl == 4 ? (const char*)Op : (const char*)(cen1 + pair * N);
+    const uint32_t gdst0 = gpl < 5 ? (uint32_t)__cvta_generic_to_shared(geo + gpx * 5 + gpl) : (uint32_t)__cvta_generic_to_shared(gcen + gpx);
+    auto fetch_geo = [&](int r, int buf) {
+        if (tid < GEO_T) {
+            const int yc = min(max(r, 0), H - 1);
+            const uint32_t p = (uint32_t)yc * Wu + (uint32_t)gxc;
+            if (gpl < 5) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(gdst0 + buf * (NPIX * 5 * 8)), "l"(gsrc + (size_t)p * 8) : "memory");
+            else         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(gdst0 + buf * (NPIX * 4)), "l"(gsrc + (size_t)p * 4) : "memory");
+        }
+    };
+    fetch_geo(y0 - 2, 0);
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+#else
     double ga[5] = {0, 0, 0, 0, 0};
     uint32_t gc = 0;
     int slow_mine = 0;
     if (tid < NPIX) { load_geo(y0 - 2, ga, gc); slow_mine = store_geo(0, ga, gc); }
     int slow = __syncthreads_or(slow_mine);
+#endif
 
     for (int r = y0 - 2; r < yend + 2; ++r) {
         const int buf = (r - (y0 - 2)) & 1;
         const bool more = r + 1 < yend + 2;
-        if (tid < NPIX && more) load_geo(r + 1, ga, gc);
         const double* geo_r = geo + buf * NPIX * 5;
         const uint32_t* gcen_r = gcen + buf * NPIX;
+#if FSGM_FC_ASYNC
+        if (more) fetch_geo(r + 1, buf ^ 1);
+        const int gl = min(lane, NPIX - 1);
+        const double a0 = geo_r[gl * 5], a1 = geo_r[gl * 5 + 1], ux = geo_r[gl * 5 + 2], uy = geo_r[gl * 5 + 3], a4 = geo_r[gl * 5 + 4];
+        // doubled constants: w = 2*(b + (off*vz)*u) = 2b + ((2 off)*vz)*u exactly
+        const double bx = __dmul_rn(__dsub_rn(a0, 1.0), 2.0), by = __dmul_rn(__dsub_rn(a1, 1.0), 2.0), off = __dmul_rn(a4, 2.0);
+#if FSGM_FC_VARIANT == 2
+        const double reach = __dmul_rn(fabs(off), vzmax);
+        const bool fin = __dadd_rn(fabs(bx), __dmul_rn(reach, fabs(ux))) < 1073741824.0 && __dadd_rn(fabs(by), __dmul_rn(reach, fabs(uy))) < 1073741824.0;
+#else
+        const bool fin = isfinite(a0) && isfinite(a1) && isfinite(ux) && isfinite(uy) && fabs(a4) <= 1e300;
+#endif
+        const int slow = __any_sync(0xFFFFFFFFu, !fin);
+#else
+        if (tid < NPIX && more) load_geo(r + 1, ga, gc);
+#endif
         // (1) raw cost of NPIX pixels x D labels: this lane's pixel, this warp's label quads
         if (lane < NPIX) {
+#if !FSGM_FC_ASYNC
             const double bx = geo_r[lane * 5], by = geo_r[lane * 5 + 1], ux = geo_r[lane * 5 + 2], uy = geo_r[lane * 5 + 3], off = geo_r[lane * 5 + 4];
+#endif
             const uint32_t c1 = gcen_r[lane];
             uint32_t* rr_out = raw_row + lane * D4S;
             if (!slow) {
@@ -300,13 +396,24 @@ epi_cost_fused_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restr
                 for (int k = 0; k < QPW; ++k) {
                     const int qq = warp * QPW + k;
                     uint32_t packed = 0;
+                    uint32_t hq[4];
+                    (void)hq;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const double t = __dmul_rn(off, vzs[4 * qq + j]);
+#if FSGM_FC_VARIANT == 0
                         const uint32_t x2 = ref_round_clamp_w(__dadd_rn(bx, __dmul_rn(t, ux)), wmax);
                         const uint32_t y2 = ref_round_clamp_w(__dadd_rn(by, __dmul_rn(t, uy)), hmax);
                         packed |= (uint32_t)__popc(c1 ^ __ldg(reinterpret_cast<const uint32_t*>(c2b + (y2 * W4 + x2 * 4u)))) << (8 * j);
+#else
+                        const uint32_t xk = ref_round_clamp_k(__dadd_rn(bx, __dmul_rn(t, ux)), wk2);
+                        const uint32_t yk = ref_round_clamp_k(__dadd_rn(by, __dmul_rn(t, uy)), hk2);
+                        hq[j] = (uint32_t)__popc(c1 ^ __ldg(c2w + ((yk >> 1) * Wu + (xk >> 1))));    // 32-bit word index: IMAD + IMAD.WIDE
+#endif
                     }
+#if FSGM_FC_VARIANT != 0
+                    packed = mad_u32(mad_u32(hq[3], 256u, hq[2]), 65536u, mad_u32(hq[1], 256u, hq[0]));         // three IMADs (FMA pipe)
+#endif
                     rr_out[qq] = packed;
                 }
             } else {
@@ -335,6 +442,7 @@ epi_cost_fused_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restr
         const int yo = r - 2;
         const bool emit = yo >= y0;
         uint32_t* crow = Cout + ((size_t)yo * W + x0 + i0 * XP) * D4;
+#if FSGM_FC_VARIANT == 0
 #pragma unroll
         for (int k = 0; k < XP; ++k) {
             if (k) h = h - rr[(k - 1) * D4S] + rr[(k + 4) * D4S];
@@ -344,8 +452,33 @@ epi_cost_fused_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restr
             vhi[k] += ((h >> 8) & 0x00FF00FFu) - ((old >> 8) & 0x00FF00FFu);
             if (emit && x0 + i0 * XP + k < W) crow[k * D4] = box_norm4_fast(vlo[k], vhi[k]);
         }
+#else
+        // The running sums stay u16 pairs (one PRMT per half of h and of the leaving row, one IADD3 per pair).  Normalisation is ONE
+        // fma per pair: the integer s < 1024 in a 16-bit half IS the fp16 subnormal s * 2^-24, and
+        // fp16(2^20 / 25) * (s * 2^-24) + 64 rounds (to a multiple of 2^-4, the spacing at 64) to 64 + round(s / 25) / 16, pattern
+        // 0x5400 | q — checked for every s <= 1023: the relative error of the constant times s stays below the 1/50 that separates
+        // s / 25 from a rounding boundary.  FMA pipe instead of mask / shift / multiply chains on the ALU pipe.
+        auto box_cols = [&](auto checked) {
+#pragma unroll
+            for (int k = 0; k < XP; ++k) {
+                if (k) h = h - rr[(k - 1) * D4S] + rr[(k + 4) * D4S];
+                const uint32_t old = hr[k * D4];
+                hr[k * D4] = h;
+                vlo[k] = vlo[k] + __byte_perm(h, 0u, 0x4240) - __byte_perm(old, 0u, 0x4240);
+                vhi[k] = vhi[k] + __byte_perm(h, 0u, 0x4341) - __byte_perm(old, 0u, 0x4341);
+                const uint32_t out = __byte_perm(h2fma(vlo[k], 0x791F791Fu, 0x54005400u), h2fma(vhi[k], 0x791F791Fu, 0x54005400u), 0x6240);
+                if (emit && (!decltype(checked)::value || x0 + i0 * XP + k < W)) crow[k * D4] = out;
+            }
+        };
+        if (x0 + FC_TX <= W) box_cols(std::false_type{}); else box_cols(std::true_type{});      // CTA-uniform: only the last strip tests columns
+#endif
+#if FSGM_FC_ASYNC
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncthreads();                              // next row's geometry has landed; everyone is done with raw_row
+#else
         slow_mine = (tid < NPIX && more) ? store_geo(buf ^ 1, ga, gc) : 0;
         slow = __syncthreads_or(slow_mine);           // also: everyone is done with raw_row
+#endif
     }
 }
 
