@@ -444,6 +444,7 @@ int fsgm_tune(fsgm_ctx* c, int key, int value)
     if (key == 5) { c->pyd_cluster = value; return FSGM_OK; }
     if (key == 6) { c->pyd_direct_cost = value != 0; return FSGM_OK; }
     if (key == 7) { c->pydng_generic = value != 0; return FSGM_OK; }
+    if (key == 8) { c->fc_rows = value < 0 ? 0 : value > 4096 ? 4096 : value; return FSGM_OK; }
     if (key == 3) { c->ng_occupancy = value < 0 ? 0 : value > 3 ? 3 : value; return FSGM_OK; }
     return fail(c, FSGM_ERR_ARG, "unknown tuning key");
 }

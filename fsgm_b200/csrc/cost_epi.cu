@@ -488,6 +488,17 @@ static size_t fused_cost_smem(int D4)
     return (size_t)4 * D4 * 8 + 2 * npix * 5 * 8 + npix * (D4 + 1) * 4 + 5 * tx * D4 * 4 + 2 * npix * 4 + 64;
 }
 
+// Rows per CTA: tall strips waste less on the 4 warm-up rows, but a small batch needs enough CTAs to fill the GPU.  (A list-schedule
+// estimate that trims the partly filled last round of CTAs — 2025 CTAs on 592 resident slots are 3.4 rounds — picked 54 rows at
+// KITTI size; measured in the two-stream wave pipeline, where other kernels fill that tail: 128 rows 2014 pairs/s, 96: 2013, 75: 2010,
+// 63: 2005, 54: 2001, 47: 1996.  fsgm_tune key 8 overrides.)
+static int fused_cost_rows(fsgm_ctx* c, int W, int H, int n, int tx)
+{
+    int ty = 128;
+    while (ty > 32 && (size_t)((W + tx - 1) / tx) * ((H + ty - 1) / ty) * n < (size_t)c->sm_count * 8) ty >>= 1;
+    return ty;
+}
+
 // returns FSGM_OK and sets *done = true if the fused kernel handles this label count
 int launch_epi_cost_fused(fsgm_ctx* c, int n, const double* d_vz, const uint32_t* cen1, const uint32_t* cen2, int W, int H, int D,
                           const double* Pd0, const double* dirn, const double* O, uint8_t* C, bool* done)
@@ -499,9 +510,8 @@ int launch_epi_cost_fused(fsgm_ctx* c, int n, const double* d_vz, const uint32_t
     const int D4 = D / 4;
     const size_t smem = fused_cost_smem(D4);
     // rows per CTA: tall strips waste less on the 4 warm-up rows, but a small batch needs enough CTAs to fill the GPU
-    int ty = 128;
     const int tx = fc_tx(D4);
-    while (ty > 32 && (size_t)((W + tx - 1) / tx) * ((H + ty - 1) / ty) * n < (size_t)c->sm_count * 8) ty >>= 1;
+    int ty = c->fc_rows > 0 ? c->fc_rows : fused_cost_rows(c, W, H, n, tx);
     dim3 grid((W + tx - 1) / tx, (H + ty - 1) / ty, n);
 #define FSGM_FC(D4V)                                                                                              \
     do {                                                                                                          \

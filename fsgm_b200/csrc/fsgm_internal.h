@@ -37,6 +37,7 @@ struct fsgm_ctx {
     cudaStream_t aux_stream = nullptr;      // second stream: front-end of wave i+1 under the cluster kernels of wave i
     cudaEvent_t ev_entry = nullptr, ev_front[2] = {nullptr, nullptr};
     int no_overlap = 0;                     // tuning knob (fsgm_tune key 2)
+    int fc_rows = 0;                        // tuning knob (fsgm_tune key 8): rows per CTA of the fused cost kernel, 0 = chosen from the grid size
     unsigned attr_mask = 0;                 // which kernels already had their max-dynamic-smem attribute set on this device
     int clusters_key[4] = {0, 0, 0, 0}, clusters_max = 0;   // resident clusters for the last queried (cluster size, W, D, ndir)
     int best_key[3] = {0, 0, 0}, best_cs = 0, best_clusters = 0;   // cached vsweep_best_cluster() decision for (W, D, ndir)
