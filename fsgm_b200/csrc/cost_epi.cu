@@ -218,6 +218,9 @@ __device__ __forceinline__ uint32_t ref_round_clamp_w(double w, uint32_t hi)
 #ifndef FSGM_FC_ASYNC
 #define FSGM_FC_ASYNC 1
 #endif
+#ifndef FSGM_FC_PIPE
+#define FSGM_FC_PIPE 1            // gathers consumed one quad later: 2015 -> 2062 pairs/s (lag 2: 2061, lag 3: 2050)
+#endif
 __device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c)
 {
     uint32_t r;
@@ -392,6 +395,35 @@ epi_cost_fused_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restr
             const uint32_t c1 = gcen_r[lane];
             uint32_t* rr_out = raw_row + lane * D4S;
             if (!slow) {
+#if FSGM_FC_PIPE
+                // software pipeline: the four gathers of a quad are consumed FSGM_FC_PIPE quads later, after the coordinates of the
+                // following quads have been computed (the compiler alone keeps one quad in flight and waits for it)
+                constexpr int LAG = FSGM_FC_PIPE < QPW ? FSGM_FC_PIPE : QPW;
+                uint32_t g[LAG][4];
+#pragma unroll
+                for (int k = 0; k < QPW + LAG; ++k) {
+                    const int qq = warp * QPW + k;
+                    uint32_t idx[4] = {0, 0, 0, 0};
+                    if (k < QPW) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const double t = __dmul_rn(off, vzs[4 * qq + j]);
+                            const uint32_t xk = ref_round_clamp_k(__dadd_rn(bx, __dmul_rn(t, ux)), wk2);
+                            const uint32_t yk = ref_round_clamp_k(__dadd_rn(by, __dmul_rn(t, uy)), hk2);
+                            idx[j] = (yk >> 1) * Wu + (xk >> 1);
+                        }
+                    }
+                    if (k >= LAG) {
+                        const uint32_t* gg = g[k % LAG];
+                        const uint32_t h0 = __popc(c1 ^ gg[0]), h1 = __popc(c1 ^ gg[1]), h2 = __popc(c1 ^ gg[2]), h3 = __popc(c1 ^ gg[3]);
+                        rr_out[qq - LAG] = mad_u32(mad_u32(h3, 256u, h2), 65536u, mad_u32(h1, 256u, h0));
+                    }
+                    if (k < QPW) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) g[k % LAG][j] = __ldg(c2w + idx[j]);
+                    }
+                }
+#else
 #pragma unroll
                 for (int k = 0; k < QPW; ++k) {
                     const int qq = warp * QPW + k;
@@ -416,6 +448,7 @@ epi_cost_fused_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restr
 #endif
                     rr_out[qq] = packed;
                 }
+#endif
             } else {
                 for (int k = 0; k < QPW; ++k) {
                     const int qq = warp * QPW + k;
