@@ -34,6 +34,11 @@ namespace fsgm {
 #ifndef FSGM_VS_PDF
 #define FSGM_VS_PDF 3
 #endif
+#ifndef FSGM_VS_DEFER
+#define FSGM_VS_DEFER 0              // A/B: 1 = final pass consumes a pixel's global rows / runs its WTA after the NEXT pixel's direction steps.
+                                     // Measured slower like every other way of moving the first use of the rows away from the row start:
+                                     // 2060 -> 2021 pairs/s with a ring of 3 or 4 pixels, 2045 with a ring of 2 (r2x).
+#endif
 #ifndef FSGM_VS_RELIEF
 #define FSGM_VS_RELIEF 1
 #endif
@@ -162,12 +167,66 @@ __device__ __forceinline__ void vs_fetch(const VsThread<NREG>& th, uint32_t pix,
     }
 }
 
+// winner-take-all over the accumulated sums of one pixel (lane = 2*NREG consecutive labels) + the record vs_finalize_kernel reads
+template <int NREG, bool FAST>
+__device__ __forceinline__ void vs_wta(const VsThread<NREG>& th, uint32_t (&acc)[NREG], uint32_t pix)
+{
+    const int lane = th.lane;
+    // winner-take-all: first minimum (strict <, calc_cost_sgm.cpp:267) via (sum << 16 | label)
+    uint32_t key = 0xFFFFFFFFu;
+    uint16_t* ws = th.ws;
+#pragma unroll
+    for (int i = 0; i < NREG; ++i) {
+        // (sum << 16 | position inside the lane) for the two labels of this register: one PRMT each, the position an
+        // immediate; the lane's first label (a multiple of 2*NREG) is OR-ed in once after the lane-level minimum
+        key = min(key, __byte_perm(acc[i], 2 * i, 0x1054));
+        key = min(key, __byte_perm(acc[i], 2 * i + 1, 0x3254));
+    }
+    key |= (uint32_t)(lane * 2 * NREG);
+    if (NREG == 4) reinterpret_cast<uint4*>(ws)[lane] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+    else if (NREG == 2) reinterpret_cast<uint2*>(ws)[lane] = make_uint2(acc[0], acc[1]);
+    else reinterpret_cast<uint32_t*>(ws)[lane] = acc[0];
+    key = __reduce_min_sync(0xffffffffu, key);
+    __syncwarp();
+    if (lane == 0) {
+        const uint32_t idx = key & 0xFFFFu;
+        th.minC[pix] = (key >> 16) - (FAST ? (H2_BIAS2 & 0xFFFFu) : 0u);
+        uint16_t* r = th.rec + (size_t)pix * 4;
+        // unconditional neighbour reads: for idx == 0 / idx == D-1 they land in the adjacent shared-memory words (inside the
+        // allocation) and vs_finalize_kernel never looks at those fields (label 0 and 1 are not refined, label D-1 takes the
+        // next pixel's Sp[0]) — two predicated branches less in a section the whole warp waits for
+        const uint16_t c_1 = ws[(int)idx - 1], c1 = ws[idx + 1];
+        *reinterpret_cast<uint2*>(r) = make_uint2(idx | ((uint32_t)c_1 << 16), (uint32_t)c1 | (acc[0] << 16));      // lane 0's acc[0] low half = Sp[0]
+    }
+    __syncwarp();
+}
+
+// Tail of a FAST final-pass pixel: both horizontal rows (their byte-wise sum cannot carry: 2*(cmax+P2) <= 255) and the first pass's
+// byte row are added as integers onto the biased pattern, then winner-take-all.  Separate from vs_pixel so that the row loop can
+// run it one pixel late (FSGM_VS_DEFER, an A/B build): the rows were requested PD pixels ahead, but behind the row barrier every
+// warp's ring is empty and the first pixel waits for DRAM (ncu r2s: 17.5 % of the pass's stall samples on the first use of the rows);
+// with the tail of pixel i behind the direction steps of pixel i+1 the first use comes two pixel-times after the request — and the
+// pass gets slower (see the macro).
+template <int NREG>
+__device__ __forceinline__ void vs_tail_fast(const VsThread<NREG>& th, uint32_t (&acc)[NREG], const VsGlobals<NREG>& g, uint32_t pix)
+{
+    constexpr int NW = (NREG + 1) / 2;
+    uint32_t ab[NW], t[NREG], u[NREG];
+#pragma unroll
+    for (int i = 0; i < NW; ++i) ab[i] = g.a[i] + g.b[i];
+    unpack_cost<NREG>(ab, t);
+    unpack_cost<NREG>(g.s8, u);
+#pragma unroll
+    for (int i = 0; i < NREG; ++i) acc[i] += t[i] + u[i];
+    vs_wta<NREG, true>(th, acc, pix);
+}
+
 // One pixel of one row: all NDIR directions, sum, output.  EDGE = the pixel may restart a path, take one from a
 // neighbour CTA's hand-over, or hand one over (first row, first / last column of the strip); interior pixels compile
 // to a straight line of LDS -> step -> STS per direction.
-template <int NREG, int NDIR, bool FINAL, bool EDGE, bool FAST>
+template <int NREG, int NDIR, bool FINAL, bool EDGE, bool FAST, bool DEFER = false>
 __device__ __forceinline__ void vs_pixel(const VsThread<NREG>& th, uint32_t crow_s, int xl, int yy, int par, int off, uint32_t pix,
-                                         const VsGlobals<NREG>& g, bool arrive)
+                                         const VsGlobals<NREG>& g, bool arrive, uint32_t* acc_out = nullptr)
 {
     constexpr int D = 64 * NREG, NW = (NREG + 1) / 2, NB = 2 * NREG;
     const int lane = th.lane, Wk = th.Wk;
@@ -290,15 +349,14 @@ __device__ __forceinline__ void vs_pixel(const VsThread<NREG>& th, uint32_t crow
             st_row<NREG>(reinterpret_cast<uint8_t*>(th.Sout_l) + vox, 0, sb);      // Sout_l carries a BYTE lane offset here
             return;
         }
-        // both horizontal rows (their byte-wise sum cannot carry: 2*(cmax+P2) <= 255) and the first pass's byte row are added
-        // as integers onto the biased pattern
-        uint32_t ab[NW], t[NREG], u[NREG];
+        if (DEFER) {
+            // the caller runs vs_tail_fast for this pixel after the next pixel's direction steps
 #pragma unroll
-        for (int i = 0; i < NW; ++i) ab[i] = g.a[i] + g.b[i];
-        unpack_cost<NREG>(ab, t);
-        unpack_cost<NREG>(g.s8, u);
-#pragma unroll
-        for (int i = 0; i < NREG; ++i) acc[i] += t[i] + u[i];
+            for (int i = 0; i < NREG; ++i) acc_out[i] = acc[i];
+            return;
+        }
+        vs_tail_fast<NREG>(th, acc, g, pix);
+        return;
     } else if (hasA && hasB && th.preadd) {
         // both horizontal rows present and their byte-wise sum cannot carry (2*(cmax+P2) <= 255): add first, unpack once
         uint32_t ab[NW], t[NREG];
@@ -330,33 +388,7 @@ __device__ __forceinline__ void vs_pixel(const VsThread<NREG>& th, uint32_t crow
 #pragma unroll
             for (int i = 0; i < NREG; ++i) sp[i] = acc[i];
         }
-        // winner-take-all: first minimum (strict <, calc_cost_sgm.cpp:267) via (sum << 16 | label)
-        uint32_t key = 0xFFFFFFFFu;
-        uint16_t* ws = th.ws;
-#pragma unroll
-        for (int i = 0; i < NREG; ++i) {
-            // (sum << 16 | position inside the lane) for the two labels of this register: one PRMT each, the position an
-            // immediate; the lane's first label (a multiple of 2*NREG) is OR-ed in once after the lane-level minimum
-            key = min(key, __byte_perm(acc[i], 2 * i, 0x1054));
-            key = min(key, __byte_perm(acc[i], 2 * i + 1, 0x3254));
-        }
-        key |= (uint32_t)(lane * 2 * NREG);
-        if (NREG == 4) reinterpret_cast<uint4*>(ws)[lane] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
-        else if (NREG == 2) reinterpret_cast<uint2*>(ws)[lane] = make_uint2(acc[0], acc[1]);
-        else reinterpret_cast<uint32_t*>(ws)[lane] = acc[0];
-        key = __reduce_min_sync(0xffffffffu, key);
-        __syncwarp();
-        if (lane == 0) {
-            const uint32_t idx = key & 0xFFFFu;
-            th.minC[pix] = (key >> 16) - (FAST ? (H2_BIAS2 & 0xFFFFu) : 0u);
-            uint16_t* r = th.rec + (size_t)pix * 4;
-            // unconditional neighbour reads: for idx == 0 / idx == D-1 they land in the adjacent shared-memory words (inside the
-            // allocation) and vs_finalize_kernel never looks at those fields (label 0 and 1 are not refined, label D-1 takes the
-            // next pixel's Sp[0]) — two predicated branches less in a section the whole warp waits for
-            const uint16_t c_1 = ws[(int)idx - 1], c1 = ws[idx + 1];
-            *reinterpret_cast<uint2*>(r) = make_uint2(idx | ((uint32_t)c_1 << 16), (uint32_t)c1 | (acc[0] << 16));      // lane 0's acc[0] low half = Sp[0]
-        }
-        __syncwarp();
+        vs_wta<NREG, FAST>(th, acc, pix);
     }
 }
 
@@ -492,15 +524,33 @@ vsweep_kernel(const VsParams prm)
         } else {
             // the only edge pixels of a later row are xl = 0 and xl = Wk-1: pixel i = 0 of warps 0 and HW, i.e. ring slot 0 of
             // their first round
+            constexpr bool DEFER = FAST && FINAL && FSGM_VS_DEFER;
+            uint32_t accp[NREG];                       // DEFER: sums of the previous pixel, whose tail runs after this pixel's steps
+            uint32_t pixp = 0;
             for (int i0 = wsub; i0 < lim; i0 += PD * HW) {
 #pragma unroll
                 for (int u = 0; u < PD; ++u) {
                     const int i = i0 + u * HW;
                     if (i < lim) {
                         const int xl = xl_of(i);
-                        if (u == 0 && i == 0) vs_pixel<NREG, NDIR, FINAL, true, FAST>(th, crow_l, xl, yy, par, off, rowpix + xl, gq[u], true);
-                        else vs_pixel<NREG, NDIR, FINAL, false, FAST>(th, crow_l, xl, yy, par, off, rowpix + xl, gq[u], false);
-                        if (i + PD * HW < lim) vs_fetch<NREG, FINAL, FAST>(th, rowpix + xl_of(i + PD * HW), gq[u]);
+                        if (DEFER) {
+                            uint32_t accn[NREG];
+                            if (u == 0 && i == 0) vs_pixel<NREG, NDIR, FINAL, true, FAST, true>(th, crow_l, xl, yy, par, off, rowpix + xl, gq[u], true, accn);
+                            else vs_pixel<NREG, NDIR, FINAL, false, FAST, true>(th, crow_l, xl, yy, par, off, rowpix + xl, gq[u], false, accn);
+                            const int up = (u + PD - 1) % PD;                  // ring slot of the previous pixel (a constant once unrolled)
+                            if (i != wsub) {
+                                vs_tail_fast<NREG>(th, accp, gq[up], pixp);
+                                if (i - HW + PD * HW < lim) vs_fetch<NREG, FINAL, FAST>(th, rowpix + xl_of(i - HW + PD * HW), gq[up]);
+                            }
+                            if (i + HW >= lim) vs_tail_fast<NREG>(th, accn, gq[u], rowpix + xl);     // the warp's last pixel of the row: nothing to hide behind
+#pragma unroll
+                            for (int r = 0; r < NREG; ++r) accp[r] = accn[r];
+                            pixp = rowpix + xl;
+                        } else {
+                            if (u == 0 && i == 0) vs_pixel<NREG, NDIR, FINAL, true, FAST>(th, crow_l, xl, yy, par, off, rowpix + xl, gq[u], true);
+                            else vs_pixel<NREG, NDIR, FINAL, false, FAST>(th, crow_l, xl, yy, par, off, rowpix + xl, gq[u], false);
+                            if (i + PD * HW < lim) vs_fetch<NREG, FINAL, FAST>(th, rowpix + xl_of(i + PD * HW), gq[u]);
+                        }
                     }
                 }
             }

@@ -196,6 +196,36 @@ def test_fused_cost_kernel_wild_geometry(ctx, oracle, W, H, D):
     assert np.array_equal(raw_g.cpu().numpy()[0], raw) and np.array_equal(Cv2.cpu().numpy()[0], want)
 
 
+@pytest.mark.parametrize("W,H,D", [(61, 40, 64), (90, 37, 256)])
+def test_fused_cost_kernel_large_finite_geometry(ctx, oracle, W, H, D):
+    """Finite but large ray coordinates on both sides of 2^30, the bound below which the fused kernel converts with the
+    magic-number add (low mantissa word of w + 1.5*2^52 + 1, rounded down) and above which the strip row takes the checked
+    conversion; negative, huge-positive and sign-changing rays included (calc_cost_sgm.cpp:366-375)."""
+    import torch
+    import ctypes as C
+    p = synth.epipolar_pair(W, H, D, seed=7 * D)
+    rng = np.random.default_rng(D + 1)
+    O = p["O"].copy(); Pd0 = p["Pd0"].copy(); dirn = p["dirn"].copy()
+    big = np.array([1e6, -1e6, 3e7, -3e7, 2.5e8, -2.5e8, 6e8, -6e8, 1.2e9, -1.2e9, 2.4e9, -2.4e9, 5e9, 4.9e8, 5.3e8, -5.3e8])
+    for r in range(2, H, 3):                                  # every third row: large offsets (the ray length scales with O)
+        xs = rng.choice(W, size=min(W, 12), replace=False)
+        O[r, xs] = rng.choice(big, size=xs.size)
+    for r in range(3, H, 5):                                  # large base positions, both signs, with fractional parts
+        xs = rng.choice(W, size=min(W, 8), replace=False)
+        Pd0[0, r, xs] = rng.choice(big, size=xs.size) + rng.uniform(-1, 1, xs.size)
+        Pd0[1, r, xs] = rng.choice(big, size=xs.size) * 0.5 + 0.5
+    dirn[0, 1, :] *= -1.0                                      # a row of rays that run the other way
+    cen1, cen2 = oracle.port_census(p["I1"]), oracle.port_census(p["I2"])
+    lib = oracle._port()
+    raw = np.empty((H, W, D), np.uint8); want = np.empty((H, W, D), np.uint8)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    lib.orc_epi_cost_raw(vp(cen1), vp(cen2), W, H, D, C.c_double(0.3), vp(Pd0), vp(dirn), vp(O), vp(raw))
+    lib.orc_box5(vp(raw), W, H, D, vp(want))
+    Cv = torch.empty((1, H, W, D), dtype=torch.uint8, device="cuda")
+    ctx.epi_cost_dev(_t(cen1.view(np.int32)[None]), _t(cen2.view(np.int32)[None]), D, 0.3, _t(Pd0[None]), _t(dirn[None]), _t(O[None]), None, Cv)
+    assert np.array_equal(Cv.cpu().numpy()[0], want)
+
+
 @pytest.mark.parametrize("W,H,D,paths,passes,cluster", [
     (150, 40, 64, 8, 2, 1), (150, 40, 64, 8, 2, 2), (150, 40, 64, 8, 2, 4), (151, 37, 64, 8, 2, 8),
     (97, 33, 128, 8, 2, 4), (64, 50, 256, 8, 2, 8), (90, 30, 256, 4, 2, 4), (90, 30, 128, 8, 1, 2), (33, 70, 64, 4, 1, 8),
