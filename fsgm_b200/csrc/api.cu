@@ -244,7 +244,7 @@ static int epi_pipeline_dev(fsgm_ctx* c, int n, const uint8_t* I1, const uint8_t
     FSGM_TRY(launch_census(c, n, I2, W, H, cen2));
     FSGM_TRY(launch_vz_table(c, D, vMax, vz));
     bool fused = false;
-    FSGM_TRY(launch_epi_cost_fused(c, n, vz, cen1, cen2, W, H, D, Pd0, dirn, O, C, &fused));
+    FSGM_TRY(launch_epi_cost_fused(c, n, vMax, cen1, cen2, W, H, D, Pd0, dirn, O, C, &fused));
     if (!fused) {
         FSGM_TRY(arena_get(c, n * V, &raw));
         FSGM_TRY(launch_epi_cost(c, n, vz, cen1, cen2, W, H, D, vMax, Pd0, dirn, O, raw, C));
@@ -297,7 +297,7 @@ static int epi_pipeline_waves(fsgm_ctx* c, int n, int cs, const uint8_t* I1, con
         FSGM_TRY(launch_census(c, m, I1 + p0 * N, W, H, cen1 + p0 * N));
         FSGM_TRY(launch_census(c, m, I2 + p0 * N, W, H, cen2 + p0 * N));
         bool fused = false;
-        FSGM_TRY(launch_epi_cost_fused(c, m, vz, cen1 + p0 * N, cen2 + p0 * N, W, H, D, Pd0 + p0 * 2 * N, dirn + p0 * 2 * N,
+        FSGM_TRY(launch_epi_cost_fused(c, m, vMax, cen1 + p0 * N, cen2 + p0 * N, W, H, D, Pd0 + p0 * 2 * N, dirn + p0 * 2 * N,
                                        O + p0 * N, C + p0 * V, &fused));
         if (!fused) return fail(c, FSGM_ERR_DOMAIN, "wave pipeline needs the fused cost kernel");
         uint8_t* Lh[2] = {Lh0 + p0 * V, Lh1 + p0 * V};
@@ -335,7 +335,7 @@ static int epi_pipeline_waves(fsgm_ctx* c, int n, int cs, const uint8_t* I1, con
         FSGM_TRY(launch_census(c, ng, I1 + po, W, H, cen1 + po));
         FSGM_TRY(launch_census(c, ng, I2 + po, W, H, cen2 + po));
         bool fused = false;
-        FSGM_TRY(launch_epi_cost_fused(c, ng, vz, cen1 + po, cen2 + po, W, H, D, Pd0 + 2 * po, dirn + 2 * po, O + po, C + po * D, &fused));
+        FSGM_TRY(launch_epi_cost_fused(c, ng, vMax, cen1 + po, cen2 + po, W, H, D, Pd0 + 2 * po, dirn + 2 * po, O + po, C + po * D, &fused));
         fsgm_epi_opts og = o;
         const int saved = c->force_cluster;
         c->force_cluster = -1;                                // generic path for these pairs
@@ -510,7 +510,7 @@ int fsgm_epi_cost_dev(fsgm_ctx* c, int n, const uint32_t* d_cen1, const uint32_t
     FSGM_TRY(launch_vz_table(c, D, vMax, vz));
     if (!d_raw) {                                   // nobody wants the pre-box volume: fused kernel when it applies
         bool fused = false;
-        FSGM_TRY(launch_epi_cost_fused(c, n, vz, d_cen1, d_cen2, W, H, D, d_Pd0, d_dir, d_O, d_C, &fused));
+        FSGM_TRY(launch_epi_cost_fused(c, n, vMax, d_cen1, d_cen2, W, H, D, d_Pd0, d_dir, d_O, d_C, &fused));
         if (fused) return FSGM_OK;
     }
     return launch_epi_cost(c, n, vz, d_cen1, d_cen2, W, H, D, vMax, d_Pd0, d_dir, d_O, raw, d_C);

@@ -190,37 +190,45 @@ int launch_epi_cost(fsgm_ctx* c, int n, const double* d_vz, const uint32_t* cen1
 // out-of-range conversion (cvttsd2si -> INT_MIN -> clamped to 0).  Working on w = 2v (exact: the per-pixel constants
 // are doubled once, and scaling by two commutes with every IEEE rounding in bx + (off*vz)*ux):
 //   v >= 0:  round(v) = floor(v + 0.5) = (floor(w) + 1) >> 1     (integer identity, no double rounding)
-//   v <  0:  round(v) <= 0, clamps to 0                            (cvt.rmi.u32 saturates negatives to 0 -> 0)
-//   NaN   :  INT_MIN on x86, clamps to 0                           (cvt of NaN gives 0 -> 0)
-//   round(v) >= 2^31, i.e. w >= 2^32 - 1: INT_MIN on x86, clamps to 0   (cvt.rmi.u32 saturates to 0xFFFFFFFF, +1 wraps to 0)
-// so one unsigned conversion, an add, a shift and an unsigned min reproduce all of it — except NaN, for which the
-// hardware conversion does not return 0.  NaN can only appear when an input is non-finite or |offset| is so large
-// that offset*vz overflows (inf*0); such pixels are flagged while staging and take a checked path.
-// Raw-cost phase mapping: LANE = PIXEL of the strip row (strip + halo = 32 pixels at D = 256), warp = a set of label quads.
-// Neighbouring pixels look at neighbouring census words for the same label, so one gather instruction touches 4-5 sectors; with
-// the former mapping (lane = label quad of ONE pixel) a warp's 32 addresses were strung along the epipolar line, 17 sectors
-// and 5.6 L1 wavefronts per request, and the L1 data pipe (67 % busy, ncu r1q) limited the kernel as much as instruction issue.
-// The pixel's geometry stays in registers for the whole row; the labels' vz values are warp-uniform shared-memory reads.
-constexpr int FC_THREADS = 256;                          // rows per CTA are chosen at launch (32..128)
-__host__ __device__ constexpr int fc_tx(int D4) { return D4 == 64 ? 28 : D4 == 32 ? 24 : 16; }      // strip width: TX + 4 <= 32 lanes, TX % (256 / D4) == 0
+//   v <  0:  round(v) <= 0, clamps to 0
+//   NaN, or round(v) >= 2^31: INT_MIN on x86, clamps to 0
+// Fast path: k = clamp(floor(w) + 1, 0, 2*hi + 1) and round-clamp(v) = k >> 1, with floor(w) + 1 taken as the low mantissa word
+// of w + (1.5 * 2^52 + 1) rounded DOWN (two's complement for negative w, exact for |w| < 2^31 - 2) and the clamp as one
+// VIMNMX.RELU: the conversion runs on the fp64 pipe instead of the quarter-rate XU pipe, which POPC alone keeps busy (ncu r1s:
+// two F2I + POPC per voxel = 8 of every ~36 issue cycles each).  A strip row with a pixel whose rays can leave |w| < 2^30 — or
+// hold a NaN (non-finite input, inf*0) — takes the checked conversion (unsigned floor conversion, NaN test) as a whole; the
+// bound |2b| + |2 off| * max|vz| * |u| is evaluated per pixel and row by the warps themselves.
+//
+// Mapping.  Raw-cost phase: LANE = PIXEL of the strip row (strip + halo = 32 pixels at D = 256), WARP = QPW consecutive label
+// quads.  Neighbouring pixels look at neighbouring census words for the same label, so one gather touches 4-5 sectors (with lane =
+// label quad of ONE pixel a warp's addresses were strung along the epipolar line: 17 sectors, 5.6 L1 wavefronts per request, ncu
+// r1q).  The four gathers of a quad are consumed one quad later (software pipeline: the compiler alone kept one quad in flight and
+// waited for it, 2015 -> 2062 pairs/s).  Box phase: the SAME warp filters its own QPW quads — lane = (quad, group of XP columns) —
+// so the raw row is warp-private ([quad][pixel] words, pitch PQ chosen so that both phases are bank-conflict free) and the
+// row needs ONE block barrier, at its end, where the next row's geometry (cp.async, a row ahead, no staging registers) must have
+// landed; with a CTA-wide raw row a second barrier sat between the phases and held 12 % of the stall samples (ncu r2s).
+// Box filter: horizontal 5-sums slide over the lane's XP columns (bytes <= 120), the vertical 5-sum is a running u16x2 pair
+// (one PRMT per half of the entering and of the leaving row, one IADD3), and the /25 rounding is ONE fp16 fma per pair: the
+// integer s < 1024 in a 16-bit half IS the fp16 subnormal s * 2^-24, and fp16(2^20 / 25) * (s * 2^-24) + 64 rounds (to a multiple
+// of 2^-4, the spacing at 64) to 64 + round(s / 25) / 16, pattern 0x5400 | q — checked for every s <= 1023: the relative error of
+// the constant times s stays below the 1/50 that separates s / 25 from a rounding boundary.
+// History of the row loop (instructions per row and thread / pairs per s at 60 pairs per step): round 1 1091 / 1912; index
+// clamp on the doubled value, word-index gathers, IMAD packing, fp16 normalisation, cp.async geometry 765 / 1981; magic-number
+// conversion 2013; pipelined gathers 2062.
+constexpr int FC_THREADS = 256, FC_WARPS = FC_THREADS / 32;          // rows per CTA are chosen at launch (32..128)
+__host__ __device__ constexpr int fc_tx(int D4) { return D4 == 64 ? 28 : D4 == 32 ? 24 : 16; }      // strip width: TX + 4 <= 32 lanes
+__host__ __device__ constexpr int fc_pq(int D4) { return D4 == 64 ? 36 : D4 == 32 ? 40 : 48; }      // raw-tile pitch per quad (words)
 
-__device__ __forceinline__ uint32_t ref_round_clamp_w(double w, uint32_t hi)
+__device__ __forceinline__ uint32_t ref_round_clamp_w(double w, uint32_t hi)          // checked path: all of the table above but NaN
 {
     const uint32_t f = __double2uint_rd(w);
     return min((f + 1u) >> 1, hi);
 }
-
-// The fast loop keeps the clamped value DOUBLED, k = min(floor(w) + 1, 2*hi + 1) (round(v) = k >> 1), so that add and clamp are
-// one instruction (VIADDMNMX.U32: the add wraps, 0xFFFFFFFF + 1 -> 0 as above) and the shift is all that is left.
-#ifndef FSGM_FC_VARIANT
-#define FSGM_FC_VARIANT 2            // A/B (tools/build_variant.sh, 60 pairs per step): 0 = round-1 loop 1912 pairs/s, 1 = VIADDMNMX form 1981, 2 = magic-number form 2013
-#endif
-#ifndef FSGM_FC_ASYNC
-#define FSGM_FC_ASYNC 1
-#endif
-#ifndef FSGM_FC_PIPE
-#define FSGM_FC_PIPE 1            // gathers consumed one quad later: 2015 -> 2062 pairs/s (lag 2: 2061, lag 3: 2050)
-#endif
+__device__ __forceinline__ uint32_t ref_round_clamp_k(double w, uint32_t k2)          // fast path, doubled index
+{
+    const int L = __double2loint(__dadd_rd(w, 6755399441055745.0));
+    return (uint32_t)__vimin_s32_relu(L, (int)k2);
+}
 __device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c)
 {
     uint32_t r;
@@ -228,118 +236,63 @@ __device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c)
     return r;
 }
 __device__ __forceinline__ uint32_t h2fma(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
-__device__ __forceinline__ uint32_t ref_round_clamp_k(double w, uint32_t k2)
-{
-#if FSGM_FC_VARIANT == 2
-    // floor(w) + 1 as the low mantissa word of w + (1.5 * 2^52 + 1) rounded down (two's complement for negative w; exact for
-    // |w| < 2^31 - 2, which the staging step checks per pixel), clamped to [0, k2] by one VIMNMX.RELU: the conversion moves from
-    // the quarter-rate XU pipe to the fp64 pipe.
-    const int L = __double2loint(__dadd_rd(w, 6755399441055745.0));
-    return (uint32_t)__vimin_s32_relu(L, (int)k2);
-#else
-    return __viaddmin_u32(__double2uint_rd(w), 1u, k2);
-#endif
-}
 
-// (u8)(1.0*s/25 + 0.5) == (2s + 25)/50 == (s*2622 + 32775) >> 16 for s <= 600; the quotient (<= 24) is byte 2 of the product
-__device__ __forceinline__ uint32_t box_norm4_fast(uint32_t lo, uint32_t hi)   // lo: labels 0,2 as u16x2; hi: labels 1,3
-{
-    const uint32_t p0 = (lo & 0xFFFFu) * 2622u + 32775u, p2 = (lo >> 16) * 2622u + 32775u;
-    const uint32_t p1 = (hi & 0xFFFFu) * 2622u + 32775u, p3 = (hi >> 16) * 2622u + 32775u;
-    return __byte_perm(__byte_perm(p0, p1, 0x0062), __byte_perm(p2, p3, 0x0062), 0x5410);
-}
-
-// measured (60 pairs, cost stage, former lane = label-quad mapping): 4 CTAs/SM + full unroll 11.17 ms, 4 + unroll 3 11.75, 3 CTAs/SM 11.29,
-// no unroll at 108 registers 13.9
+// measured (60 pairs per step): 4 CTAs/SM 2014 pairs/s, 3 CTAs/SM (84 registers) 1987, 2 CTAs/SM 1888
 #ifndef FSGM_FC_MINB
 #define FSGM_FC_MINB 4
 #endif
+// vz(d) travels as a kernel parameter (constant bank, warp-uniform LDC reads): the table is evaluated on the host with the
+// reference's expression (the reference IS host code: same IEEE operations) and 2 KB of shared memory stay free — four CTAs per SM
+// then fit the 196 KB carve-out and the gathers keep 60 KB of L1 (one more KB per CTA and the carve-out jumps to 228 KB).
+template <int D4> struct alignas(16) FcVzTable { double v[4 * D4]; };
 template <int D4>      // D = 4*D4 labels, D4 in {16, 32, 64}
 __global__ void __launch_bounds__(FC_THREADS, FSGM_FC_MINB)
 epi_cost_fused_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restrict__ cen2,
                       const double* __restrict__ Pd0, const double* __restrict__ dirn, const double* __restrict__ O,
-                      const double* __restrict__ vz, int W, int H, int FC_TY, uint8_t* __restrict__ C)
+                      const __grid_constant__ FcVzTable<D4> vzt, int W, int H, int FC_TY, uint8_t* __restrict__ C)
 {
-    constexpr int FC_TX = fc_tx(D4), NPIX = FC_TX + 4, IPT = FC_THREADS / D4, XP = FC_TX / IPT;   // XP consecutive output columns per thread
-    constexpr int D4S = D4 + 1;                      // raw-row pitch in words: lanes write different pixels of one quad (bank = pixel + quad)
-    constexpr int QPW = D4 / (FC_THREADS / 32);      // label quads per warp in the raw-cost phase
-    static_assert(NPIX <= 32 && FC_TX % IPT == 0 && QPW >= 1, "strip geometry");
+    constexpr int FC_TX = fc_tx(D4), NPIX = FC_TX + 4, PQ = fc_pq(D4);
+    constexpr int QPW = D4 / FC_WARPS;               // label quads per warp (both phases)
+    constexpr int NCG = 32 / QPW, XP = FC_TX / NCG;  // box phase: lane = (quad, column group), XP consecutive output columns per lane
+    static_assert(NPIX <= 32 && NPIX <= PQ && QPW >= 1 && NCG * QPW == 32 && XP * NCG == FC_TX, "strip geometry");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* vzs = reinterpret_cast<double*>(smem_raw);                                      // [4*D4]
-    double* geo = vzs + 4 * D4;                                                             // [2][NPIX][5]
-    uint32_t* raw_row = reinterpret_cast<uint32_t*>(geo + 2 * NPIX * 5);                    // [NPIX][D4S]
-    uint32_t* hring = raw_row + NPIX * D4S;                                                 // [5][FC_TX][D4]
-    uint32_t* gcen = hring + 5 * FC_TX * D4;                                                // [2][NPIX]
+    double* geo = reinterpret_cast<double*>(smem_raw);                                      // [2][NPIX][5] raw planes of a strip row
+    uint32_t* rawt = reinterpret_cast<uint32_t*>(geo + 2 * NPIX * 5);                       // [warp][QPW][PQ]
+    uint32_t* hring = rawt + FC_WARPS * QPW * PQ;                                           // [warp][5][FC_TX][QPW]
+    uint32_t* gcen = hring + 5 * FC_TX * D4;                                                // [2][NPIX], then one word for max|vz|
 
     const size_t N = (size_t)W * H;
     const int pair = blockIdx.z, x0 = blockIdx.x * FC_TX, y0 = blockIdx.y * FC_TY;
-    const int tid = threadIdx.x, q = tid % D4, i0 = tid / D4;
-    const char* c2b = reinterpret_cast<const char*>(cen2 + pair * N);          // gathers use a 32-bit BYTE offset from this base
-    const uint32_t W4 = (uint32_t)W * 4u;
+    const int tid = threadIdx.x;
     const double* PdX = Pd0 + (size_t)pair * 2 * N; const double* PdY = PdX + N;
     const double* DrX = dirn + (size_t)pair * 2 * N; const double* DrY = DrX + N;
     const double* Op = O + pair * N;
-    uint32_t* Cout = reinterpret_cast<uint32_t*>(C + pair * N * (size_t)(4 * D4)) + q;
     const int lane = tid & 31, warp = __shfl_sync(0xFFFFFFFFu, tid >> 5, 0);      // warp-uniform for the compiler: label-table addresses live in uniform registers
-#if FSGM_FC_VARIANT == 2
-    // upper bound of |vz| over the table (high word + 1; inf / NaN give a non-finite bound and every pixel takes the checked path)
+    const int kq = lane % QPW, cg = lane / QPW;                                   // box phase: this lane's quad (of the warp's) and column group
+    uint32_t* Cout = reinterpret_cast<uint32_t*>(C + pair * N * (size_t)(4 * D4)) + warp * QPW + kq;
+    uint32_t* rawt_w = rawt + warp * (QPW * PQ);
+    uint32_t* hring_w = hring + warp * (5 * FC_TX * QPW);
+
+    // upper bound of |vz| over the table (high word + 1; inf / NaN give a non-finite bound and every row takes the checked path)
     uint32_t* vzhi_s = gcen + 2 * NPIX;
     if (tid == 0) *vzhi_s = 0;
+    for (int i = tid; i < 5 * FC_TX * D4; i += FC_THREADS) hring[i] = 0;      // rows before the window count as zero
     __syncthreads();
     uint32_t vzhi = 0;
-    for (int i = tid; i < 4 * D4; i += FC_THREADS) { const double v = vz[i]; vzs[i] = v; vzhi = max(vzhi, (uint32_t)__double2hiint(fabs(v))); }
+    for (int i = tid; i < 4 * D4; i += FC_THREADS) vzhi = max(vzhi, (uint32_t)__double2hiint(fabs(vzt.v[i])));
     vzhi = __reduce_max_sync(0xFFFFFFFFu, vzhi);
-    if ((tid & 31) == 0) atomicMax(vzhi_s, vzhi);
-    __syncthreads();
-    const double vzmax = __hiloint2double((int)(*vzhi_s + 1u), 0);
-#else
-    for (int i = tid; i < 4 * D4; i += FC_THREADS) vzs[i] = vz[i];
-#endif
+    if (lane == 0) atomicMax(vzhi_s, vzhi);
+
     const int yend = min(y0 + FC_TY, H);
     const uint32_t wmax = (uint32_t)(W - 1), hmax = (uint32_t)(H - 1);
     const uint32_t wk2 = 2u * wmax + 1u, hk2 = 2u * hmax + 1u, Wu = (uint32_t)W;
     const uint32_t* c2w = cen2 + pair * N;
-    (void)wk2; (void)hk2; (void)Wu; (void)c2w;
-
-    for (int i = tid; i < 5 * FC_TX * D4; i += FC_THREADS) hring[i] = 0;      // rows before the window count as zero
+    asm volatile("" : "+l"(c2w));                    // one opaque 64-bit base: a gather's address is IMAD.WIDE.U32(index, 4, base), not a rebuilt sum
     uint32_t vlo[XP], vhi[XP];                                               // running vertical 5-sums (u16x2) per column
 #pragma unroll
     for (int k = 0; k < XP; ++k) { vlo[k] = 0; vhi[k] = 0; }
 
-    // Geometry of a row is staged in a double buffer: the global loads for row r+1 are issued before the raw-cost phase of row r
-    // and written to shared memory after its box phase, so their latency hides under the arithmetic and a row needs two
-    // barriers instead of three.  `slow` = some pixel of the strip row can produce NaN (checked path, CTA-uniform branch).
-    // (One barrier per row — raw row double-buffered, geometry staged two rows ahead, vz read with __ldg — was measured slower,
-    // 10.15 -> 10.59 ms per 60 pairs: at four CTAs per SM the extra 7 KB per CTA leave the gathers half the L1.)
-#if !FSGM_FC_ASYNC
-    auto load_geo = [&](int r, double (&a)[5], uint32_t& cen) {
-        const int yc = min(max(r, 0), H - 1), xc = min(max(x0 - 2 + tid, 0), W - 1);
-        const size_t p = (size_t)yc * W + xc;
-        a[0] = PdX[p]; a[1] = PdY[p]; a[2] = DrX[p]; a[3] = DrY[p]; a[4] = Op[p];
-        cen = cen1[pair * N + p];
-    };
-    auto store_geo = [&](int buf, const double (&a)[5], uint32_t cen) -> int {
-        double* g = geo + (buf * NPIX + tid) * 5;
-        // doubled constants: w = 2*(b + (off*vz)*u) = 2b + ((2 off)*vz)*u exactly
-        g[0] = __dmul_rn(__dsub_rn(a[0], 1.0), 2.0); g[1] = __dmul_rn(__dsub_rn(a[1], 1.0), 2.0);
-        g[2] = a[2]; g[3] = a[3]; g[4] = __dmul_rn(a[4], 2.0);
-        gcen[buf * NPIX + tid] = cen;
-#if FSGM_FC_VARIANT == 2
-        // every |w| of this pixel stays below 2^30 (NaN anywhere fails the comparison): the magic-number conversion is exact
-        const double reach = __dmul_rn(fabs(g[4]), vzmax);
-        const bool fin = __dadd_rn(fabs(g[0]), __dmul_rn(reach, fabs(a[2]))) < 1073741824.0 &&
-                         __dadd_rn(fabs(g[1]), __dmul_rn(reach, fabs(a[3]))) < 1073741824.0;
-#else
-        const bool fin = isfinite(a[0]) && isfinite(a[1]) && isfinite(a[2]) && isfinite(a[3]) && fabs(a[4]) <= 1e300;
-#endif
-        return fin ? 0 : 1;
-    };
-#endif
-#if FSGM_FC_ASYNC
-    // Geometry rows travel global -> shared by cp.async, one 8-byte (census: 4-byte) element per thread, a row ahead: no staging
-    // registers live across the raw-cost phase (at 64 registers per thread the eleven of them cost rematerialised addresses all
-    // over the row loop).  Each warp turns the raw planes of its lane's pixel into the doubled constants itself and votes on the
-    // checked path, so the row's second barrier carries no reduction.
+    // geometry rows: global -> shared by cp.async, one 8-byte (census: 4-byte) element per thread, a row ahead
     constexpr int GEO_T = 6 * NPIX;                                           // threads that copy: plane = tid / NPIX, pixel = tid % NPIX
     static_assert(GEO_T <= FC_THREADS, "one geometry element per thread");
     const int gpl = tid / NPIX, gpx = tid - gpl * NPIX;
@@ -358,167 +311,96 @@ epi_cost_fused_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restr
     fetch_geo(y0 - 2, 0);
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
-#else
-    double ga[5] = {0, 0, 0, 0, 0};
-    uint32_t gc = 0;
-    int slow_mine = 0;
-    if (tid < NPIX) { load_geo(y0 - 2, ga, gc); slow_mine = store_geo(0, ga, gc); }
-    int slow = __syncthreads_or(slow_mine);
-#endif
+    const double vzmax = __hiloint2double((int)(*vzhi_s + 1u), 0);
 
     for (int r = y0 - 2; r < yend + 2; ++r) {
         const int buf = (r - (y0 - 2)) & 1;
-        const bool more = r + 1 < yend + 2;
         const double* geo_r = geo + buf * NPIX * 5;
-        const uint32_t* gcen_r = gcen + buf * NPIX;
-#if FSGM_FC_ASYNC
-        if (more) fetch_geo(r + 1, buf ^ 1);
+        if (r + 1 < yend + 2) fetch_geo(r + 1, buf ^ 1);
+        // this lane's pixel: doubled constants, w = 2*(b + (off*vz)*u) = 2b + ((2 off)*vz)*u exactly
         const int gl = min(lane, NPIX - 1);
         const double a0 = geo_r[gl * 5], a1 = geo_r[gl * 5 + 1], ux = geo_r[gl * 5 + 2], uy = geo_r[gl * 5 + 3], a4 = geo_r[gl * 5 + 4];
-        // doubled constants: w = 2*(b + (off*vz)*u) = 2b + ((2 off)*vz)*u exactly
         const double bx = __dmul_rn(__dsub_rn(a0, 1.0), 2.0), by = __dmul_rn(__dsub_rn(a1, 1.0), 2.0), off = __dmul_rn(a4, 2.0);
-#if FSGM_FC_VARIANT == 2
+        const uint32_t c1 = gcen[buf * NPIX + gl];
+        // every |w| of the pixel stays below 2^30 (a NaN anywhere fails the comparison): the magic-number conversion is exact
         const double reach = __dmul_rn(fabs(off), vzmax);
         const bool fin = __dadd_rn(fabs(bx), __dmul_rn(reach, fabs(ux))) < 1073741824.0 && __dadd_rn(fabs(by), __dmul_rn(reach, fabs(uy))) < 1073741824.0;
-#else
-        const bool fin = isfinite(a0) && isfinite(a1) && isfinite(ux) && isfinite(uy) && fabs(a4) <= 1e300;
-#endif
         const int slow = __any_sync(0xFFFFFFFFu, !fin);
-#else
-        if (tid < NPIX && more) load_geo(r + 1, ga, gc);
-#endif
-        // (1) raw cost of NPIX pixels x D labels: this lane's pixel, this warp's label quads
+        // (1) raw cost of NPIX pixels x the warp's QPW label quads
         if (lane < NPIX) {
-#if !FSGM_FC_ASYNC
-            const double bx = geo_r[lane * 5], by = geo_r[lane * 5 + 1], ux = geo_r[lane * 5 + 2], uy = geo_r[lane * 5 + 3], off = geo_r[lane * 5 + 4];
-#endif
-            const uint32_t c1 = gcen_r[lane];
-            uint32_t* rr_out = raw_row + lane * D4S;
+            uint32_t* rr_out = rawt_w + lane;
             if (!slow) {
-#if FSGM_FC_PIPE
-                // software pipeline: the four gathers of a quad are consumed FSGM_FC_PIPE quads later, after the coordinates of the
-                // following quads have been computed (the compiler alone keeps one quad in flight and waits for it)
-                constexpr int LAG = FSGM_FC_PIPE < QPW ? FSGM_FC_PIPE : QPW;
-                uint32_t g[LAG][4];
+                uint32_t g[4];
 #pragma unroll
-                for (int k = 0; k < QPW + LAG; ++k) {
+                for (int k = 0; k < QPW + 1; ++k) {
                     const int qq = warp * QPW + k;
                     uint32_t idx[4] = {0, 0, 0, 0};
                     if (k < QPW) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const double t = __dmul_rn(off, vzs[4 * qq + j]);
+                            const double t = __dmul_rn(off, vzt.v[4 * qq + j]);
                             const uint32_t xk = ref_round_clamp_k(__dadd_rn(bx, __dmul_rn(t, ux)), wk2);
                             const uint32_t yk = ref_round_clamp_k(__dadd_rn(by, __dmul_rn(t, uy)), hk2);
-                            idx[j] = (yk >> 1) * Wu + (xk >> 1);
+                            idx[j] = (yk >> 1) * Wu + (xk >> 1);                   // 32-bit word index: IMAD + IMAD.WIDE
                         }
                     }
-                    if (k >= LAG) {
-                        const uint32_t* gg = g[k % LAG];
-                        const uint32_t h0 = __popc(c1 ^ gg[0]), h1 = __popc(c1 ^ gg[1]), h2 = __popc(c1 ^ gg[2]), h3 = __popc(c1 ^ gg[3]);
-                        rr_out[qq - LAG] = mad_u32(mad_u32(h3, 256u, h2), 65536u, mad_u32(h1, 256u, h0));
+                    if (k >= 1) {
+                        const uint32_t h0 = __popc(c1 ^ g[0]), h1 = __popc(c1 ^ g[1]), h2 = __popc(c1 ^ g[2]), h3 = __popc(c1 ^ g[3]);
+                        rr_out[(k - 1) * PQ] = mad_u32(mad_u32(h3, 256u, h2), 65536u, mad_u32(h1, 256u, h0));      // three IMADs (FMA pipe)
                     }
                     if (k < QPW) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) g[k % LAG][j] = __ldg(c2w + idx[j]);
+                        for (int j = 0; j < 4; ++j) g[j] = __ldg(c2w + idx[j]);
                     }
                 }
-#else
-#pragma unroll
-                for (int k = 0; k < QPW; ++k) {
-                    const int qq = warp * QPW + k;
-                    uint32_t packed = 0;
-                    uint32_t hq[4];
-                    (void)hq;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const double t = __dmul_rn(off, vzs[4 * qq + j]);
-#if FSGM_FC_VARIANT == 0
-                        const uint32_t x2 = ref_round_clamp_w(__dadd_rn(bx, __dmul_rn(t, ux)), wmax);
-                        const uint32_t y2 = ref_round_clamp_w(__dadd_rn(by, __dmul_rn(t, uy)), hmax);
-                        packed |= (uint32_t)__popc(c1 ^ __ldg(reinterpret_cast<const uint32_t*>(c2b + (y2 * W4 + x2 * 4u)))) << (8 * j);
-#else
-                        const uint32_t xk = ref_round_clamp_k(__dadd_rn(bx, __dmul_rn(t, ux)), wk2);
-                        const uint32_t yk = ref_round_clamp_k(__dadd_rn(by, __dmul_rn(t, uy)), hk2);
-                        hq[j] = (uint32_t)__popc(c1 ^ __ldg(c2w + ((yk >> 1) * Wu + (xk >> 1))));    // 32-bit word index: IMAD + IMAD.WIDE
-#endif
-                    }
-#if FSGM_FC_VARIANT != 0
-                    packed = mad_u32(mad_u32(hq[3], 256u, hq[2]), 65536u, mad_u32(hq[1], 256u, hq[0]));         // three IMADs (FMA pipe)
-#endif
-                    rr_out[qq] = packed;
-                }
-#endif
             } else {
                 for (int k = 0; k < QPW; ++k) {
                     const int qq = warp * QPW + k;
                     uint32_t packed = 0;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const double t = __dmul_rn(off, vzs[4 * qq + j]);
+                        const double t = __dmul_rn(off, vzt.v[4 * qq + j]);
                         const double wx = __dadd_rn(bx, __dmul_rn(t, ux)), wy = __dadd_rn(by, __dmul_rn(t, uy));
                         const uint32_t x2 = (wx != wx) ? 0u : ref_round_clamp_w(wx, wmax);
                         const uint32_t y2 = (wy != wy) ? 0u : ref_round_clamp_w(wy, hmax);
-                        packed |= (uint32_t)__popc(c1 ^ __ldg(reinterpret_cast<const uint32_t*>(c2b + (y2 * W4 + x2 * 4u)))) << (8 * j);
+                        packed |= (uint32_t)__popc(c1 ^ __ldg(c2w + (y2 * Wu + x2))) << (8 * j);
                     }
-                    rr_out[qq] = packed;
+                    rr_out[k * PQ] = packed;
                 }
             }
         }
-        __syncthreads();
-        // (2) horizontal 5-sums by a sliding window over this thread's XP consecutive columns; vertical 5-sums as
+        __syncwarp();
+        // (2) horizontal 5-sums by a sliding window over this lane's XP consecutive columns; vertical 5-sums as
         //     running sums (add the new row, drop the row that leaves the window: it sits in the ring slot being rewritten)
         const int slot = (r + 10) % 5;
-        const uint32_t* rr = raw_row + (i0 * XP) * D4S + q;
-        uint32_t* hr = hring + (slot * FC_TX + i0 * XP) * D4 + q;
-        uint32_t h = rr[0] + rr[D4S] + rr[2 * D4S] + rr[3 * D4S] + rr[4 * D4S];           // bytes <= 120: no carries
+        const uint32_t* rr = rawt_w + kq * PQ + cg * XP;
+        uint32_t* hr = hring_w + (slot * FC_TX + cg * XP) * QPW + kq;
+        uint32_t h = rr[0] + rr[1] + rr[2] + rr[3] + rr[4];                                  // bytes <= 120: no carries
         const int yo = r - 2;
         const bool emit = yo >= y0;
-        uint32_t* crow = Cout + ((size_t)yo * W + x0 + i0 * XP) * D4;
-#if FSGM_FC_VARIANT == 0
-#pragma unroll
-        for (int k = 0; k < XP; ++k) {
-            if (k) h = h - rr[(k - 1) * D4S] + rr[(k + 4) * D4S];
-            const uint32_t old = hr[k * D4];
-            hr[k * D4] = h;
-            vlo[k] += (h & 0x00FF00FFu) - (old & 0x00FF00FFu);
-            vhi[k] += ((h >> 8) & 0x00FF00FFu) - ((old >> 8) & 0x00FF00FFu);
-            if (emit && x0 + i0 * XP + k < W) crow[k * D4] = box_norm4_fast(vlo[k], vhi[k]);
-        }
-#else
-        // The running sums stay u16 pairs (one PRMT per half of h and of the leaving row, one IADD3 per pair).  Normalisation is ONE
-        // fma per pair: the integer s < 1024 in a 16-bit half IS the fp16 subnormal s * 2^-24, and
-        // fp16(2^20 / 25) * (s * 2^-24) + 64 rounds (to a multiple of 2^-4, the spacing at 64) to 64 + round(s / 25) / 16, pattern
-        // 0x5400 | q — checked for every s <= 1023: the relative error of the constant times s stays below the 1/50 that separates
-        // s / 25 from a rounding boundary.  FMA pipe instead of mask / shift / multiply chains on the ALU pipe.
+        uint32_t* crow = Cout + ((size_t)yo * W + x0 + cg * XP) * D4;
         auto box_cols = [&](auto checked) {
 #pragma unroll
             for (int k = 0; k < XP; ++k) {
-                if (k) h = h - rr[(k - 1) * D4S] + rr[(k + 4) * D4S];
-                const uint32_t old = hr[k * D4];
-                hr[k * D4] = h;
+                if (k) h = h - rr[k - 1] + rr[k + 4];
+                const uint32_t old = hr[k * QPW];
+                hr[k * QPW] = h;
                 vlo[k] = vlo[k] + __byte_perm(h, 0u, 0x4240) - __byte_perm(old, 0u, 0x4240);
                 vhi[k] = vhi[k] + __byte_perm(h, 0u, 0x4341) - __byte_perm(old, 0u, 0x4341);
                 const uint32_t out = __byte_perm(h2fma(vlo[k], 0x791F791Fu, 0x54005400u), h2fma(vhi[k], 0x791F791Fu, 0x54005400u), 0x6240);
-                if (emit && (!decltype(checked)::value || x0 + i0 * XP + k < W)) crow[k * D4] = out;
+                if (emit && (!decltype(checked)::value || x0 + cg * XP + k < W)) crow[k * D4] = out;
             }
         };
         if (x0 + FC_TX <= W) box_cols(std::false_type{}); else box_cols(std::true_type{});      // CTA-uniform: only the last strip tests columns
-#endif
-#if FSGM_FC_ASYNC
         asm volatile("cp.async.wait_all;" ::: "memory");
-        __syncthreads();                              // next row's geometry has landed; everyone is done with raw_row
-#else
-        slow_mine = (tid < NPIX && more) ? store_geo(buf ^ 1, ga, gc) : 0;
-        slow = __syncthreads_or(slow_mine);           // also: everyone is done with raw_row
-#endif
+        __syncthreads();                              // next row's geometry has landed (and this warp is done with its raw tile)
     }
 }
 
 static size_t fused_cost_smem(int D4)
 {
-    const size_t tx = fc_tx(D4), npix = tx + 4;
-    return (size_t)4 * D4 * 8 + 2 * npix * 5 * 8 + npix * (D4 + 1) * 4 + 5 * tx * D4 * 4 + 2 * npix * 4 + 64;
+    const size_t tx = fc_tx(D4), npix = tx + 4, qpw = D4 / FC_WARPS;
+    return 2 * npix * 5 * 8 + (size_t)FC_WARPS * qpw * fc_pq(D4) * 4 + 5 * tx * D4 * 4 + 2 * npix * 4 + 64;
 }
 
 // Rows per CTA: tall strips waste less on the 4 warm-up rows, but a small batch needs enough CTAs to fill the GPU.  (A list-schedule
@@ -533,7 +415,7 @@ static int fused_cost_rows(fsgm_ctx* c, int W, int H, int n, int tx)
 }
 
 // returns FSGM_OK and sets *done = true if the fused kernel handles this label count
-int launch_epi_cost_fused(fsgm_ctx* c, int n, const double* d_vz, const uint32_t* cen1, const uint32_t* cen2, int W, int H, int D,
+int launch_epi_cost_fused(fsgm_ctx* c, int n, double vMax, const uint32_t* cen1, const uint32_t* cen2, int W, int H, int D,
                           const double* Pd0, const double* dirn, const double* O, uint8_t* C, bool* done)
 {
     *done = false;
@@ -553,7 +435,12 @@ int launch_epi_cost_fused(fsgm_ctx* c, int n, const double* d_vz, const uint32_t
             FSGM_CUDA(c, cudaFuncSetAttribute(epi_cost_fused_kernel<D4V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
             c->attr_mask |= bit;                                                                                  \
         }                                                                                                         \
-        epi_cost_fused_kernel<D4V><<<grid, FC_THREADS, smem, c->stream>>>(cen1, cen2, Pd0, dirn, O, d_vz, W, H, ty, C); \
+        FcVzTable<D4V> vzt;                                                                                       \
+        for (int d = 0; d < D; ++d) {        /* calc_cost_sgm.cpp:339,360-361, the reference's evaluation order */   \
+            const double r = 1.0 * d / (D + 1) * vMax;                                                                \
+            vzt.v[d] = r / (1 - r);                                                                                   \
+        }                                                                                                             \
+        epi_cost_fused_kernel<D4V><<<grid, FC_THREADS, smem, c->stream>>>(cen1, cen2, Pd0, dirn, O, vzt, W, H, ty, C); \
     } while (0)
     if (D4 == 16) FSGM_FC(16); else if (D4 == 32) FSGM_FC(32); else FSGM_FC(64);
 #undef FSGM_FC

@@ -351,7 +351,7 @@ int fsgm_calc_cost_sgm_dirsplit_dev(fsgm_ctx* c, const uint8_t* d_I1, const uint
     FSGM_TRY(launch_census(c, 1, d_I2, W, H, cen2));
     FSGM_TRY(launch_vz_table(c, D, vMax, vz));
     bool fused = false;
-    FSGM_TRY(launch_epi_cost_fused(c, 1, vz, cen1, cen2, W, H, D, d_Pd0, d_dir, d_O, C, &fused));
+    FSGM_TRY(launch_epi_cost_fused(c, 1, vMax, cen1, cen2, W, H, D, d_Pd0, d_dir, d_O, C, &fused));
     if (!fused) {
         FSGM_TRY(arena_get(c, V, &raw));
         FSGM_TRY(launch_epi_cost(c, 1, vz, cen1, cen2, W, H, D, vMax, d_Pd0, d_dir, d_O, raw, C));

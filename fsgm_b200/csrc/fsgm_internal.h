@@ -125,7 +125,7 @@ void dist_release(fsgm_ctx* c);                                 // dist.cu: drop
 
 // ---- kernel launchers (definitions in the .cu files) -------------------------------------------
 int launch_census(fsgm_ctx* c, int n_images, const uint8_t* img, int W, int H, uint32_t* cen);
-int launch_epi_cost_fused(fsgm_ctx* c, int n, const double* d_vz, const uint32_t* cen1, const uint32_t* cen2, int W, int H, int D,
+int launch_epi_cost_fused(fsgm_ctx* c, int n, double vMax, const uint32_t* cen1, const uint32_t* cen2, int W, int H, int D,
                           const double* Pd0, const double* dirn, const double* O, uint8_t* C, bool* done);
 int launch_vz_table(fsgm_ctx* c, int D, double vMax, double* d_vz);
 int launch_epi_cost(fsgm_ctx* c, int n, const double* d_vz, const uint32_t* cen1, const uint32_t* cen2, int W, int H, int D, double vMax,
