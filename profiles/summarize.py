@@ -31,5 +31,31 @@ def main(path):
                 print(f"   {k:95s} {r[hdr.index(k)]} {units[hdr.index(k)]}")
 
 
+def traffic(path, pairs_per_launch, source):
+    """profiles/traffic.json for bench.py's roofline.traffic: DRAM bytes (read + written) per pair and launch of the dominant kernel
+    (vsweep_kernel, mean over its launches in the capture = the two passes of a wave)."""
+    import json
+    import os
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    tot, n = 0.0, 0
+    for r in rows[2:]:
+        if "vsweep_kernel" not in r[hdr.index("Kernel Name")]:
+            continue
+        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[hdr.index(k)]]
+            tot += float(r[hdr.index(k)]) * scale
+        n += 1
+    rec = {"kernel": "vsweep_kernel", "launches_in_capture": n, "pairs_per_launch": pairs_per_launch,
+           "dram_bytes_per_pair_per_launch": tot / n / pairs_per_launch, "source": source}
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "traffic.json"), "w") as f:
+        json.dump(rec, f, indent=1)
+    print(rec)
+
+
 if __name__ == "__main__":
-    main(sys.argv[1])
+    if len(sys.argv) > 2 and sys.argv[2] == "--traffic":      # summarize.py X.ncu-rep --traffic PAIRS_PER_LAUNCH "source text"
+        traffic(sys.argv[1], float(sys.argv[3]), sys.argv[4])
+    else:
+        main(sys.argv[1])
