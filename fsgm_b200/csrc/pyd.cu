@@ -441,14 +441,20 @@ pyd_cost_px_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restrict
     if (pitch) {                                          // pad bytes of the grid
         for (int i = lane; i < 32 * PT / 4; i += 32) reinterpret_cast<uint32_t*>(tile)[i] = 0xFFFFFFFFu;
     }
-    // sample coordinates: x2 depends only on s = offx + ax (tabulated per lane), -1 = outside the image; same for y
+    // sample coordinates: x2 depends only on s = offx + ax (tabulated per lane); same for y.  The tables hold CLAMPED coordinates
+    // (y premultiplied by W: a gather's word index is one add) and validity travels as one bit per entry in two registers.
+    uint32_t xvalid = 0, yvalid = 0;
     for (int sI = 0; sI < SX2; ++sI) {
         const int v = x86_d2i(__dadd_rn(__dadd_rn((double)(sI - rx - AGG + x), mvx), 0.5));
-        fx[sI * 32 + lane] = (v < 0 || v > W - 1) ? -1 : v;
+        const bool ok = !(v < 0 || v > W - 1);
+        fx[sI * 32 + lane] = ok ? v : 0;
+        xvalid |= (ok ? 1u : 0u) << sI;
     }
     for (int sI = 0; sI < SY2; ++sI) {
         const int v = x86_d2i(__dadd_rn(__dadd_rn((double)(sI - ry - AGG + y), mvy), 0.5));
-        fy[sI * 32 + lane] = (v < 0 || v > H - 1) ? -1 : v;
+        const bool ok = !(v < 0 || v > H - 1);
+        fy[sI * 32 + lane] = ok ? v * W : 0;
+        yvalid |= (ok ? 1u : 0u) << sI;
     }
     // window taps of the current image; a tap outside the image contributes the constant
     uint32_t t1[T][T];
@@ -463,53 +469,61 @@ pyd_cost_px_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restrict
             tapok |= (in ? 1u : 0u) << (ay * T + ax);
         }
     __syncwarp();
-    bool rows_ok = tapok == (1u << WPX) - 1u;             // every window tap inside the image and every sample row valid
-    for (int sI = 0; sI < SY2; ++sI) rows_ok &= fy[sI * 32 + lane] >= 0;
+    const bool rows_ok = tapok == (1u << WPX) - 1u && yvalid == (1u << SY2) - 1u;   // every window tap inside the image and every sample row valid
+    asm volatile("" : "+l"(c2));                          // one opaque 64-bit base: a gather's address is IMAD.WIDE.U32(index, 4, base)
 
     for (int ox = 0; ox < Sx; ++ox) {
         // column validity (bit ax) and the T x SY2 reference words of this label column
-        int fxv[T];
-        uint32_t colok = 0;
+        uint32_t fxv[T];
 #pragma unroll
-        for (int ax = 0; ax < T; ++ax) { fxv[ax] = fx[(ox + ax) * 32 + lane]; colok |= (fxv[ax] >= 0 ? 1u : 0u) << ax; }
-        // sample rows live in a ring of T rows (every entry is private to its lane: no synchronisation): rows 0 .. T-2 now,
-        // row oy + T - 1 at the head of label oy
-        auto load_row = [&](int sy) {
-            const int yy = fy[sy * 32 + lane];
-            const uint32_t* row = c2 + (size_t)W * max(yy, 0);
-            uint32_t* dst = V + ((sy % T) * T) * 32 + lane;
+        for (int ax = 0; ax < T; ++ax) fxv[ax] = (uint32_t)fx[(ox + ax) * 32 + lane];
+        const uint32_t colok = (xvalid >> ox) & ((1u << T) - 1u);
+        // Sample rows live in a ring of T rows (every entry is private to its lane: no synchronisation).  The label loop is unrolled
+        // by T, so ring slots are compile-time constants (row sy sits in slot sy % T: every tap is LDS at base + immediate), and the
+        // row a label adds to the window is fetched one label ahead into registers and stored at the head of its label.
+        uint32_t nxt[T];
+        auto fetch_row = [&](int sy) {
+            const uint32_t rb = (uint32_t)fy[sy * 32 + lane];
 #pragma unroll
-            for (int ax = 0; ax < T; ++ax) dst[ax * 32] = __ldg(row + max(fxv[ax], 0));
+            for (int ax = 0; ax < T; ++ax) nxt[ax] = __ldg(c2 + (rb + fxv[ax]));
         };
-        for (int sy = 0; sy < T - 1; ++sy) load_row(sy);
+        auto commit_row = [&](int slot) {
+#pragma unroll
+            for (int ax = 0; ax < T; ++ax) V[(slot * T + ax) * 32 + lane] = nxt[ax];
+        };
+#pragma unroll
+        for (int sy = 0; sy < T - 1; ++sy) { fetch_row(sy); commit_row(sy); }
+        fetch_row(T - 1);
         // every tap of every label of the column is valid for every lane -> no checks (the interior of the image)
         const bool clean = __all_sync(0xffffffffu, rows_ok && colok == (1u << T) - 1u);
-        int r0 = 0;                                       // oy % T: ring slot of sample row oy
-        for (int oy = 0; oy < Sy; ++oy) {
-            load_row(oy + T - 1);
-            uint32_t sum = 0;
-            const uint32_t* Vr[T];
+        for (int oy0 = 0; oy0 < Sy; oy0 += T) {
 #pragma unroll
-            for (int ay = 0; ay < T; ++ay) { int q = r0 + ay; q -= q >= T ? T : 0; Vr[ay] = V + (q * T) * 32 + lane; }
-            if (clean) {
+            for (int u = 0; u < T; ++u) {
+                const int oy = oy0 + u;
+                if (oy < Sy) {
+                    commit_row((u + T - 1) % T);                  // sample row oy + T - 1
+                    if (oy + 1 < Sy) fetch_row(oy + T);
+                    uint32_t sum = 0;
+                    if (clean) {
 #pragma unroll
-                for (int ay = 0; ay < T; ++ay)
+                        for (int ay = 0; ay < T; ++ay)
 #pragma unroll
-                    for (int ax = 0; ax < T; ++ax) sum += __popc(t1[ay][ax] ^ Vr[ay][ax * 32]);
-            } else {
+                            for (int ax = 0; ax < T; ++ax) sum += __popc(t1[ay][ax] ^ V[(((u + ay) % T) * T + ax) * 32 + lane]);
+                    } else {
 #pragma unroll
-                for (int ay = 0; ay < T; ++ay) {
-                    const bool rowok = fy[(oy + ay) * 32 + lane] >= 0;
+                        for (int ay = 0; ay < T; ++ay) {
+                            const bool rowok = (yvalid >> (oy + ay)) & 1u;
 #pragma unroll
-                    for (int ax = 0; ax < T; ++ax) {
-                        const bool ok = rowok && ((colok >> ax) & 1u) && ((tapok >> (ay * T + ax)) & 1u);
-                        sum += ok ? (uint32_t)__popc(t1[ay][ax] ^ Vr[ay][ax * 32]) : 5u;
+                            for (int ax = 0; ax < T; ++ax) {
+                                const bool ok = rowok && ((colok >> ax) & 1u) && ((tapok >> (ay * T + ax)) & 1u);
+                                sum += ok ? (uint32_t)__popc(t1[ay][ax] ^ V[(((u + ay) % T) * T + ax) * 32 + lane]) : 5u;
+                            }
+                        }
                     }
+                    // (u8)(1.0*s/wp + 0.5) == (2s + wp) / (2wp) in integers (see pyd_cost_kernel)
+                    tile[lane * PT + (pitch ? ox * 16 + 2 + oy : ox * Sy + oy)] = (uint8_t)((2 * sum + WPX) / (2 * WPX));
                 }
             }
-            r0 = r0 + 1 == T ? 0 : r0 + 1;
-            // (u8)(1.0*s/wp + 0.5) == (2s + wp) / (2wp) in integers (see pyd_cost_kernel)
-            tile[lane * PT + (pitch ? ox * 16 + 2 + oy : ox * Sy + oy)] = (uint8_t)((2 * sum + WPX) / (2 * WPX));
         }
         __syncwarp();
     }
