@@ -381,12 +381,14 @@ pyd_sweep_kernel(const PydSweepParams prm)
 // cost volume, lane = pixel: a warp owns 32 consecutive pixels of a row.  For one label and one window tap the 32 lanes read
 // neighbouring census words (the prior is piecewise constant over a warp in practice), so a gather touches 4-5 sectors
 // instead of the ~20 of the one-warp-per-pixel kernel above, whose lanes spread over the search window.  Per label column ox
-// the T x (2ry+T) reference census words the column needs are gathered ONCE, row by row, into a shared-memory ring of T rows
-// ([row][tap][lane], lane-private, conflict free); the T*T taps of its Sy labels are then LDS + XOR + POPC + IADD each.  The constant-5 rule (sample or window pixel
+// the T x (2ry+T) reference census words the column needs are gathered ONCE, row by row, into a ring of T rows held in REGISTERS
+// (the label loop is unrolled by T, so every ring index is a compile-time constant); the T*T taps of a label are XORs against the
+// pixel's own T*T census words + POPC.  (A carry-save adder tree that needs 7 POPC instead of 25 was measured: not faster, 775 against 780 pairs/s — POPC is not this kernel's limit.)  The constant-5 rule (sample or window pixel
 // outside the image, calc_pyd_cost_sgm.cpp:405-421) is a per-lane validity word per row / column, all-ones in the interior,
 // so the inner loop stays branch-free.  Results go through a shared-memory tile and leave as one contiguous run of bytes.
 // ------------------------------------------------------------------------------------------------
 constexpr int PYC_WARPS = 4;
+
 template <int AGG>
 __global__ void __launch_bounds__(PYC_WARPS * 32)
 pyd_cost_px_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restrict__ cen2, int W, int H,
@@ -401,14 +403,13 @@ pyd_cost_px_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restrict
     extern __shared__ __align__(16) unsigned char pyc_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int Sx = 2 * rx + 1, Sy = 2 * ry + 1, D = Sx * Sy, SX2 = Sx + T - 1, SY2 = Sy + T - 1;
-    // per warp: fx[SX2][32], fy[SY2][32] (int), V[T][T][32] (u32: a ring of T sample rows), tile[32][D] (u8, padded to 16 bytes)
+    // per warp: fx[SX2][32], fy[SY2][32] (int), tile[32][D] (u8, padded to 16 bytes)
     const int PT = pitch ? pitch : D;                     // bytes per pixel in the output tile
-    const size_t per_warp = (size_t)(SX2 + SY2) * 32 * 4 + (size_t)T * T * 32 * 4 + (((size_t)32 * PT + 15) & ~(size_t)15);
+    const size_t per_warp = (size_t)(SX2 + SY2) * 32 * 4 + (((size_t)32 * PT + 15) & ~(size_t)15);
     unsigned char* base = pyc_smem + wib * per_warp;
     int* fx = reinterpret_cast<int*>(base);
     int* fy = fx + SX2 * 32;
-    uint32_t* V = reinterpret_cast<uint32_t*>(fy + SY2 * 32);
-    uint8_t* tile = reinterpret_cast<uint8_t*>(V + T * T * 32);
+    uint8_t* tile = reinterpret_cast<uint8_t*>(fy + SY2 * 32);
 
     const int xblocks = (W + 31) / 32;
     const int job = blockIdx.x * PYC_WARPS + wib;
@@ -468,6 +469,12 @@ pyd_cost_px_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restrict
             t1[ay][ax] = in ? __ldg(c1 + (size_t)W * y1 + x1) : 0u;
             tapok |= (in ? 1u : 0u) << (ay * T + ax);
         }
+    uint32_t tybits = 0, txbits = 0;                      // window rows / columns inside the image (tapok = their outer product)
+#pragma unroll
+    for (int a = 0; a < T; ++a) {
+        tybits |= (y + a - AGG >= 0 && y + a - AGG < H ? 1u : 0u) << a;
+        txbits |= (x + a - AGG >= 0 && x + a - AGG < W ? 1u : 0u) << a;
+    }
     __syncwarp();
     const bool rows_ok = tapok == (1u << WPX) - 1u && yvalid == (1u << SY2) - 1u;   // every window tap inside the image and every sample row valid
     asm volatile("" : "+l"(c2));                          // one opaque 64-bit base: a gather's address is IMAD.WIDE.U32(index, 4, base)
@@ -478,18 +485,22 @@ pyd_cost_px_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restrict
 #pragma unroll
         for (int ax = 0; ax < T; ++ax) fxv[ax] = (uint32_t)fx[(ox + ax) * 32 + lane];
         const uint32_t colok = (xvalid >> ox) & ((1u << T) - 1u);
-        // Sample rows live in a ring of T rows (every entry is private to its lane: no synchronisation).  The label loop is unrolled
-        // by T, so ring slots are compile-time constants (row sy sits in slot sy % T: every tap is LDS at base + immediate), and the
-        // row a label adds to the window is fetched one label ahead into registers and stored at the head of its label.
+        uint32_t cmw[T];                                  // checked path: all-ones where window column ax and sample column ox + ax are inside
+#pragma unroll
+        for (int ax = 0; ax < T; ++ax) cmw[ax] = ((colok & txbits) >> ax) & 1u ? 0xFFFFFFFFu : 0u;
+        const int ncol = __popc(colok & txbits);
+        // Sample rows live in a ring of T rows in registers.  The label loop is unrolled by T, so ring slots are compile-time
+        // constants (row sy sits in slot sy % T), and the row a label adds to the window is fetched one label ahead.
         uint32_t nxt[T];
         auto fetch_row = [&](int sy) {
             const uint32_t rb = (uint32_t)fy[sy * 32 + lane];
 #pragma unroll
             for (int ax = 0; ax < T; ++ax) nxt[ax] = __ldg(c2 + (rb + fxv[ax]));
         };
+        uint32_t vr[T][T];                                // the ring: T sample rows x T columns in registers (all indices static)
         auto commit_row = [&](int slot) {
 #pragma unroll
-            for (int ax = 0; ax < T; ++ax) V[(slot * T + ax) * 32 + lane] = nxt[ax];
+            for (int ax = 0; ax < T; ++ax) vr[slot][ax] = nxt[ax];
         };
 #pragma unroll
         for (int sy = 0; sy < T - 1; ++sy) { fetch_row(sy); commit_row(sy); }
@@ -508,17 +519,20 @@ pyd_cost_px_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restrict
 #pragma unroll
                         for (int ay = 0; ay < T; ++ay)
 #pragma unroll
-                            for (int ax = 0; ax < T; ++ax) sum += __popc(t1[ay][ax] ^ V[(((u + ay) % T) * T + ax) * 32 + lane]);
+                            for (int ax = 0; ax < T; ++ax) sum += __popc(t1[ay][ax] ^ vr[(u + ay) % T][ax]);
                     } else {
+                        // validity is separable — a tap counts iff its window row, its sample row, its window column and its sample
+                        // column are inside: invalid columns are masked out of the XOR (one LOP3), invalid rows drop their row sum, and
+                        // every invalid tap adds the constant once
+                        const uint32_t rowbits = (yvalid >> oy) & tybits;
 #pragma unroll
                         for (int ay = 0; ay < T; ++ay) {
-                            const bool rowok = (yvalid >> (oy + ay)) & 1u;
+                            uint32_t rs = 0;
 #pragma unroll
-                            for (int ax = 0; ax < T; ++ax) {
-                                const bool ok = rowok && ((colok >> ax) & 1u) && ((tapok >> (ay * T + ax)) & 1u);
-                                sum += ok ? (uint32_t)__popc(t1[ay][ax] ^ V[(((u + ay) % T) * T + ax) * 32 + lane]) : 5u;
-                            }
+                            for (int ax = 0; ax < T; ++ax) rs += __popc((t1[ay][ax] ^ vr[(u + ay) % T][ax]) & cmw[ax]);
+                            sum += ((rowbits >> ay) & 1u) ? rs : 0u;
                         }
+                        sum += 5u * (uint32_t)(WPX - __popc(rowbits) * ncol);
                     }
                     // (u8)(1.0*s/wp + 0.5) == (2s + wp) / (2wp) in integers (see pyd_cost_kernel)
                     tile[lane * PT + (pitch ? ox * 16 + 2 + oy : ox * Sy + oy)] = (uint8_t)((2 * sum + WPX) / (2 * WPX));
@@ -774,7 +788,7 @@ static size_t pyd_cost_px_smem(int agg, int rx, int ry, int pitch)
 {
     const int T = 2 * agg + 1, Sx = 2 * rx + 1, Sy = 2 * ry + 1, SX2 = Sx + T - 1, SY2 = Sy + T - 1;
     const size_t PT = pitch ? pitch : Sx * Sy;
-    const size_t per_warp = (size_t)(SX2 + SY2) * 32 * 4 + (size_t)T * T * 32 * 4 + (((size_t)32 * PT + 15) & ~(size_t)15);
+    const size_t per_warp = (size_t)(SX2 + SY2) * 32 * 4 + (((size_t)32 * PT + 15) & ~(size_t)15);
     return per_warp * PYC_WARPS;
 }
 
