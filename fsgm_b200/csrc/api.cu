@@ -277,8 +277,7 @@ static int epi_pipeline_waves(fsgm_ctx* c, int n, int cs, const uint8_t* I1, con
         FSGM_CUDA(c, cudaEventCreateWithFlags(&c->ev_front[0], cudaEventDisableTiming));
         FSGM_CUDA(c, cudaEventCreateWithFlags(&c->ev_front[1], cudaEventDisableTiming));
     }
-    uint32_t *cen1, *cen2; uint8_t *C, *Lh0, *Lh1; uint16_t *S1, *rec; double* vz;
-    FSGM_TRY(arena_get(c, (size_t)D, &vz));
+    uint32_t *cen1, *cen2; uint8_t *C, *Lh0, *Lh1; uint16_t *S1, *rec;
     FSGM_TRY(arena_get(c, n * N, &cen1));
     FSGM_TRY(arena_get(c, n * N, &cen2));
     FSGM_TRY(arena_get(c, n * V, &C));
@@ -287,8 +286,7 @@ static int epi_pipeline_waves(fsgm_ctx* c, int n, int cs, const uint8_t* I1, con
     FSGM_TRY(arena_get(c, nf * V, &S1));
     FSGM_TRY(arena_get(c, nf * N * 4, &rec));
     cudaStream_t A = c->stream, B = c->aux_stream;
-    FSGM_TRY(launch_vz_table(c, D, vMax, vz));
-    FSGM_CUDA(c, cudaEventRecord(c->ev_entry, A));            // everything queued so far (inputs, vz) precedes stream B
+    FSGM_CUDA(c, cudaEventRecord(c->ev_entry, A));            // everything queued so far (the caller's inputs) precedes stream B
     FSGM_CUDA(c, cudaStreamWaitEvent(B, c->ev_entry, 0));
     const int hd[2] = {0, 4};
     const bool fast = vsweep_fast_ok(ndir, P2);         // FAST operand configuration of the two cluster passes (vsweep.cu)

@@ -580,7 +580,7 @@ pyd_cost_sep_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restric
                     const double* __restrict__ preMv, int mvW, int mvH, int ry, uint8_t* __restrict__ C)
 {
     constexpr int T = 2 * AGG + 1, WPX = T * T, NW = 3 * SX, RX = (SX - 1) / 2, OXG = (SX + G - 1) / G;
-    constexpr uint32_t MUL = WPX == 25 ? 1311u : 3641u;                 // floor(n / (2*WPX)) == (n * MUL) >> 16 for n <= 2*WPX*25 + WPX
+    static_assert(WPX == 25 || WPX == 9, "normalisation constants");
     extern __shared__ uint32_t pcs_smem[];
     uint32_t* rawb = pcs_smem;                                           // [NW][128]
     uint32_t* ring = pcs_smem + NW * PCS_COLS;                           // [T][NW][128]
@@ -594,6 +594,7 @@ pyd_cost_sep_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restric
     const size_t N = (size_t)W * H;
     const uint32_t* c1 = cen1 + pair * N;
     const uint32_t* c2 = cen2 + pair * N;
+    asm volatile("" : "+l"(c2));                          // one opaque 64-bit base: a gather's address is IMAD.WIDE.U32(index, 4, base)
     const double* mvxp = preMv + (size_t)pair * 2 * mvW * mvH;
     const double* mvyp = mvxp + (size_t)mvW * mvH;
     uint8_t* Cb = C + (size_t)pair * N * (SX * 16);
@@ -635,7 +636,7 @@ pyd_cost_sep_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restric
 #pragma unroll
             for (int oy = 0; oy < 12; ++oy) {
                 const int v = x86_d2i(__dadd_rn(__dadd_rn((double)(oy - ry + yq), mvy), 0.5));
-                fy[oy] = (oy >= Sy || v < 0 || v > H - 1) ? -1 : v;
+                fy[oy] = (oy >= Sy || v < 0 || v > H - 1) ? -1 : v * W;           // premultiplied: a gather's word index is one add
                 if (oy < Sy) allok &= fy[oy] >= 0;
             }
         }
@@ -651,7 +652,7 @@ pyd_cost_sep_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restric
 #pragma unroll
                             for (int b = 0; b < 4; ++b) {
                                 const int oy = 4 * j + b;
-                                if (oy < Sy) w += (uint32_t)__popc(w1 ^ __ldg(c2 + (size_t)W * fy[oy] + fx[o])) << (8 * b);
+                                if (oy < Sy) w += (uint32_t)__popc(w1 ^ __ldg(c2 + (uint32_t)(fy[oy] + fx[o]))) << (8 * b);
                             }
                             rawb[((ox0 + o) * 3 + j) * PCS_COLS + tid] = w;
                         }
@@ -668,7 +669,7 @@ pyd_cost_sep_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restric
                             for (int b = 0; b < 4; ++b) {
                                 const int oy = 4 * j + b;
                                 const bool ok = fx[o] >= 0 && fy[oy] >= 0;
-                                const uint32_t h = ok ? (uint32_t)__popc(w1 ^ __ldg(c2 + (size_t)W * max(fy[oy], 0) + max(fx[o], 0))) : 5u;
+                                const uint32_t h = ok ? (uint32_t)__popc(w1 ^ __ldg(c2 + (uint32_t)(max(fy[oy], 0) + max(fx[o], 0)))) : 5u;
                                 w += h << (8 * b);
                             }
                             rawb[((ox0 + o) * 3 + j) * PCS_COLS + tid] = w;
@@ -710,18 +711,19 @@ pyd_cost_sep_kernel(const uint32_t* __restrict__ cen1, const uint32_t* __restric
 #pragma unroll
                 for (int o = 0; o < OXG; ++o) {
                     if (ox0 + o < SX) {
-                        // (u8)(1.0*s/wp + 0.5) == (2s + wp) / (2wp): byte 2 of the product
-                        uint32_t pr[12];
+                        // (u8)(1.0*s/wp + 0.5) by one fp16 fma per two labels: the u16 sum s < 1024 IS the fp16 subnormal s * 2^-24,
+                        // and fp16(2^(24-k) / wp) * (s * 2^-24) + 2^(10-k) rounds to pattern (B | q), q = round(s / wp) (k = 4, B =
+                        // 0x5400 for wp = 25; k = 5, B = 0x5000 for wp = 9; checked for every s <= 1023 — the derivation is in
+                        // cost_epi.cu)
+                        uint32_t nq[6];
 #pragma unroll
-                        for (int i = 0; i < 6; ++i) {
-                            pr[2 * i] = (vs[o][i] & 0xFFFFu) * (2u * MUL) + WPX * MUL;
-                            pr[2 * i + 1] = (vs[o][i] >> 16) * (2u * MUL) + WPX * MUL;
-                        }
+                        for (int i = 0; i < 6; ++i)
+                            asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(nq[i]) : "r"(vs[o][i]), "r"(WPX == 25 ? 0x791F791Fu : 0x7B1C7B1Cu), "r"(WPX == 25 ? 0x54005400u : 0x50005000u));
                         uint4 f;
-                        f.x = (__byte_perm(pr[0], pr[1], 0x6200) | 0x0000FFFFu) | padw[0];
-                        f.y = __byte_perm(__byte_perm(pr[2], pr[3], 0x0062), __byte_perm(pr[4], pr[5], 0x0062), 0x5410) | padw[1];
-                        f.z = __byte_perm(__byte_perm(pr[6], pr[7], 0x0062), __byte_perm(pr[8], pr[9], 0x0062), 0x5410) | padw[2];
-                        f.w = (__byte_perm(pr[10], 0, 0x4442) | 0xFFFFFF00u) | padw[3];
+                        f.x = __byte_perm(nq[0], 0xFFFFFFFFu, 0x2044) | padw[0];
+                        f.y = __byte_perm(nq[1], nq[2], 0x6420) | padw[1];
+                        f.z = __byte_perm(nq[3], nq[4], 0x6420) | padw[2];
+                        f.w = __byte_perm(nq[5], 0xFFFFFFFFu, 0x4440) | padw[3];
                         *reinterpret_cast<uint4*>(op + (size_t)(ox0 + o) * W * 16) = f;
                     }
                 }
