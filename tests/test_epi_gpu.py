@@ -226,6 +226,27 @@ def test_fused_cost_kernel_large_finite_geometry(ctx, oracle, W, H, D):
     assert np.array_equal(Cv.cpu().numpy()[0], want)
 
 
+@pytest.mark.parametrize("D,vMax", [(128, 1.5), (64, 1.5), (256, 0.999), (128, -0.4)])
+def test_fused_cost_kernel_odd_vmax(ctx, oracle, D, vMax):
+    """vMax outside (0, 1): the label table r / (1 - r) is not monotone, changes sign, and at D = 128, vMax = 1.5 holds an infinity
+    (r = 86 / 129 * 1.5 = 1).  The fused kernel takes the table as a host-evaluated kernel parameter and bounds every ray with
+    max |vz|: a non-finite bound sends every strip row down the checked conversion (calc_cost_sgm.cpp:360-375)."""
+    import torch
+    import ctypes as C
+    W, H = 70, 33
+    p = synth.epipolar_pair(W, H, D, seed=3 * D)
+    cen1, cen2 = oracle.port_census(p["I1"]), oracle.port_census(p["I2"])
+    lib = oracle._port()
+    raw = np.empty((H, W, D), np.uint8); want = np.empty((H, W, D), np.uint8)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    lib.orc_epi_cost_raw(vp(cen1), vp(cen2), W, H, D, C.c_double(vMax), vp(p["Pd0"]), vp(p["dirn"]), vp(p["O"]), vp(raw))
+    lib.orc_box5(vp(raw), W, H, D, vp(want))
+    Cv = torch.empty((1, H, W, D), dtype=torch.uint8, device="cuda")
+    ctx.epi_cost_dev(_t(cen1.view(np.int32)[None]), _t(cen2.view(np.int32)[None]), D, vMax, _t(p["Pd0"][None]), _t(p["dirn"][None]),
+                     _t(p["O"][None]), None, Cv)
+    assert np.array_equal(Cv.cpu().numpy()[0], want)
+
+
 @pytest.mark.parametrize("W,H,D,paths,passes,cluster", [
     (150, 40, 64, 8, 2, 1), (150, 40, 64, 8, 2, 2), (150, 40, 64, 8, 2, 4), (151, 37, 64, 8, 2, 8),
     (97, 33, 128, 8, 2, 4), (64, 50, 256, 8, 2, 8), (90, 30, 256, 4, 2, 4), (90, 30, 128, 8, 1, 2), (33, 70, 64, 4, 1, 8),
