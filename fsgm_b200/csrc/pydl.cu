@@ -26,6 +26,9 @@
 namespace fsgm {
 
 constexpr int PL_WARPS = 2;                 // warps are independent; the block size only sets the shared-memory granularity (8 warps per SM)
+// (Register caps for more resident warps were measured at 32 pairs, r = 5: 1-warp blocks at 164 / 160 registers — 11 warps per SM, the
+// shared-memory limit — 782 pairs/s, 2-warp blocks at 157 registers 786, against 807 uncapped at 188: each warp is a serial chain
+// and loses more from the tighter schedule than the SM gains from one more chain.)
 #ifndef FSGM_PL_DUP_ALWAYS
 #define FSGM_PL_DUP_ALWAYS 0
 #endif
