@@ -26,9 +26,10 @@
 namespace fsgm {
 
 constexpr int PL_WARPS = 2;                 // warps are independent; the block size only sets the shared-memory granularity (8 warps per SM)
-// (Register caps for more resident warps were measured at 32 pairs, r = 5: 1-warp blocks at 164 / 160 registers — 11 warps per SM, the
-// shared-memory limit — 782 pairs/s, 2-warp blocks at 157 registers 786, against 807 uncapped at 188: each warp is a serial chain
-// and loses more from the tighter schedule than the SM gains from one more chain.)
+// (ncu r2I, 32 pairs at level 0: 8 warps resident per SM — at 188 registers a sub-partition's 16 K registers hold two warps — and
+// the stall samples sit on shared memory: short scoreboard 18 %, MIO queue 15 %, i.e. on the ~140 LDS.32 / STS.32 / LDGSTS a step
+// issues, which the [word][lane] state layout keeps 32 bits wide.  More resident warps do not help: register caps of 157-164 with
+// the maximum shared-memory carve-out, 10-11 warps per SM, gave 783-796 pairs/s against 805-807 uncapped.)
 #ifndef FSGM_PL_DUP_ALWAYS
 #define FSGM_PL_DUP_ALWAYS 0
 #endif

@@ -1,5 +1,5 @@
 OUT=gpurun_out/r2H; mkdir -p $OUT
-for t in main pl1_11 pl1_12 pl2_6; do
+for t in main pl1_11 pl2_5 pl1_10; do
   L=$PWD/fsgm_b200/libfsgm_$t.so; [ $t = main ] && L=$PWD/fsgm_b200/libfsgm.so
   FSGM_LIB=$L timeout 600 python bench.py --skip A,D,strong_256 --no-cpu --steps 5 --warmup 3 > $OUT/bench_$t.json 2> $OUT/bench_$t.err; echo "$t rc=$?"
   python - <<PY
