@@ -29,7 +29,9 @@ constexpr int PL_WARPS = 2;                 // warps are independent; the block 
 // (ncu r2I, 32 pairs at level 0: 8 warps resident per SM — at 188 registers a sub-partition's 16 K registers hold two warps — and
 // the stall samples sit on shared memory: short scoreboard 18 %, MIO queue 15 %, i.e. on the ~140 LDS.32 / STS.32 / LDGSTS a step
 // issues, which the [word][lane] state layout keeps 32 bits wide.  More resident warps do not help: register caps of 157-164 with
-// the maximum shared-memory carve-out, 10-11 warps per SM, gave 783-796 pairs/s against 805-807 uncapped.)
+// the maximum shared-memory carve-out, 10-11 warps per SM, gave 783-796 pairs/s against 805-807 uncapped.  Neither does halving the
+// instruction count: a [word pair][lane][2] layout with 64-bit accesses (3 LDS.64 + a clamp-mode funnel shift for odd word offsets
+// instead of 5 LDS.32, 2 STS.64 instead of 4 STS.32; equally conflict free) passed every parity test and ran at 806 against 811.)
 #ifndef FSGM_PL_DUP_ALWAYS
 #define FSGM_PL_DUP_ALWAYS 0
 #endif
