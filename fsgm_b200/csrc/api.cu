@@ -316,19 +316,10 @@ static int epi_pipeline_waves(fsgm_ctx* c, int n, int cs, const uint8_t* I1, con
         return launch_vs_finalize(c, m, rec + p0 * N * 4, minC + p0 * N, O + p0 * N, W, H, D, o.subpixel, o.vz_to_disp, vMax, fast ? 1 : 0,
                                   bestD + p0 * N);
     };
-    const int waves = (nf + K - 1) / K;
-    FSGM_TRY(front(0, std::min(K, nf), A));
-    for (int i = 0; i < waves; ++i) {
-        const int p0 = i * K, m = std::min(K, nf - p0);
-        if (i + 1 < waves) {
-            const int q0 = (i + 1) * K, qm = std::min(K, nf - q0);
-            FSGM_TRY(front(q0, qm, B));
-            FSGM_CUDA(c, cudaEventRecord(c->ev_front[(i + 1) & 1], B));
-        }
-        if (i > 0) FSGM_CUDA(c, cudaStreamWaitEvent(A, c->ev_front[i & 1], 0));
-        FSGM_TRY(back(p0, m));
-    }
-    if (ng) {                                                 // partial wave: generic kernels on the main stream
+    // partial wave (fewer pairs than resident clusters are left): generic one-warp-per-scanline kernels.  It is queued on stream B under
+    // the cluster passes of the last full wave (a fixed batch of 32 pairs per GPU — config E on 8 GPUs — is two waves + 2 pairs).
+    auto tail = [&](cudaStream_t st) -> int {
+        StreamSwap sw(c, st);
         const size_t po = (size_t)nf * N;
         FSGM_TRY(launch_census(c, ng, I1 + po, W, H, cen1 + po));
         FSGM_TRY(launch_census(c, ng, I2 + po, W, H, cen2 + po));
@@ -339,7 +330,27 @@ static int epi_pipeline_waves(fsgm_ctx* c, int n, int cs, const uint8_t* I1, con
         c->force_cluster = -1;                                // generic path for these pairs
         int rc = aggregate_and_wta(c, ng, C + po * D, I1 + po, W, H, D, P1, P2, 24, og, O + po, vMax, nullptr, bestD + po, minC + po);
         c->force_cluster = saved;
-        FSGM_TRY(rc);
+        return rc;
+    };
+    const int waves = (nf + K - 1) / K;
+    if (waves > 0) FSGM_TRY(front(0, std::min(K, nf), A));
+    for (int i = 0; i < waves; ++i) {
+        const int p0 = i * K, m = std::min(K, nf - p0);
+        if (i + 1 < waves) {
+            const int q0 = (i + 1) * K, qm = std::min(K, nf - q0);
+            FSGM_TRY(front(q0, qm, B));
+            FSGM_CUDA(c, cudaEventRecord(c->ev_front[(i + 1) & 1], B));
+        }
+        if (i > 0) FSGM_CUDA(c, cudaStreamWaitEvent(A, c->ev_front[i & 1], 0));
+        if (i + 1 == waves && ng) FSGM_TRY(tail(B));          // stream B has nothing left to do for the last wave: the partial wave goes there
+        FSGM_TRY(back(p0, m));
+    }
+    if (ng) {
+        if (waves == 0) FSGM_TRY(tail(A));
+        else {
+            FSGM_CUDA(c, cudaEventRecord(c->ev_front[waves & 1], B));
+            FSGM_CUDA(c, cudaStreamWaitEvent(A, c->ev_front[waves & 1], 0));
+        }
     }
     return FSGM_OK;
 }
