@@ -1,4 +1,4 @@
-OUT=gpurun_out/r2E; mkdir -p $OUT
+OUT=gpurun_out/r2M; mkdir -p $OUT
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 8 --steps 10 --warmup 3 > $OUT/bench_8gpu.json 2> $OUT/bench_8gpu.err; echo "bench8 rc=$?"; head -c 400 $OUT/bench_8gpu.json; echo
 python - <<PY
 import json
