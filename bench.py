@@ -222,6 +222,8 @@ class Env:
         self.ctx.tune(2, int(args.no_overlap))
         if args.tune_cost_rows:
             self.ctx.tune(8, args.tune_cost_rows)
+        if args.tune_stage_waves:
+            self.ctx.tune(9, args.tune_stage_waves)
         self.opts = api.epi_opts(paths=PATHS)
         self.peak, self.peak_src, self.sm_mhz = peaks()
 
@@ -747,6 +749,7 @@ def main():
     ap.add_argument("--skip", default="", help="comma-separated side workloads to skip: A,C,D,strong_256,dirsplit_4k")
     ap.add_argument("--ng-pairs", type=int, default=0, help="pairs per step of the ng workload (default: two per SM)")
     ap.add_argument("--no-overlap", action="store_true", help="A/B knob (fsgm_tune key 2): disable the two-stream wave pipeline")
+    ap.add_argument("--tune-stage-waves", type=int, default=0, help="A/B knob (fsgm_tune key 9): cluster waves per staging chunk of the host gateways, 0 = default")
     ap.add_argument("--tune-cost-rows", type=int, default=0, help="A/B knob (fsgm_tune key 8): rows per CTA of the fused cost kernel, 0 auto")
     ap.add_argument("--tune-cluster", type=int, default=0,
                     help="A/B knob (fsgm_tune key 1): 0 auto, -1 generic sweeps only, 1/2/4/8 cluster size")

@@ -453,6 +453,7 @@ int fsgm_tune(fsgm_ctx* c, int key, int value)
     if (key == 5) { c->pyd_cluster = value; return FSGM_OK; }
     if (key == 6) { c->pyd_direct_cost = value != 0; return FSGM_OK; }
     if (key == 7) { c->pydng_generic = value != 0; return FSGM_OK; }
+    if (key == 9) { c->stage_waves = value < 1 ? 3 : value > 64 ? 64 : value; return FSGM_OK; }
     if (key == 8) { c->fc_rows = value < 0 ? 0 : value > 4096 ? 4096 : value; return FSGM_OK; }
     if (key == 3) { c->ng_occupancy = value < 0 ? 0 : value > 3 ? 3 : value; return FSGM_OK; }
     return fail(c, FSGM_ERR_ARG, "unknown tuning key");
@@ -710,7 +711,7 @@ int fsgm_calc_cost_sgm_batch_async(fsgm_ctx* c, int n, const uint8_t* I1, const 
         const int cs = fast_path_cluster(c, W, D, P1, P2, 24, o);
         if (cs) {                                    // two waves per chunk so that the wave pipeline has something to overlap
             fast_pairs(c, n, cs, D, W, o.paths == 8 ? 3 : 1);
-            chunk = std::min(n, std::max(chunk, (c->no_overlap ? 1 : 2) * c->clusters_max));
+            chunk = std::min(n, std::max(chunk, (c->no_overlap ? 1 : c->stage_waves) * c->clusters_max));
         }
     }
     FSGM_TRY(pipe_reserve(c, (size_t)chunk * (in_pair + out_pair)));
@@ -915,7 +916,7 @@ static int sgm_of_batch_async(fsgm_ctx* c, int n, const uint8_t* I0, const uint8
         const int cs = fast_path_cluster(c, W, D, P1, P2, 24, o);
         if (cs) {
             fast_pairs(c, n, cs, D, W, o.paths == 8 ? 3 : 1);
-            chunk = std::min(n, std::max(chunk, (c->no_overlap ? 1 : 2) * c->clusters_max));
+            chunk = std::min(n, std::max(chunk, (c->no_overlap ? 1 : c->stage_waves) * c->clusters_max));
         }
     }
     FSGM_TRY(pipe_reserve(c, (size_t)chunk * per_pair));

@@ -37,6 +37,7 @@ struct fsgm_ctx {
     cudaStream_t aux_stream = nullptr;      // second stream: front-end of wave i+1 under the cluster kernels of wave i
     cudaEvent_t ev_entry = nullptr, ev_front[2] = {nullptr, nullptr};
     int no_overlap = 0;                     // tuning knob (fsgm_tune key 2)
+    int stage_waves = 3;                    // tuning knob (fsgm_tune key 9): cluster waves per staging chunk of the host-pointer gateways
     int fc_rows = 0;                        // tuning knob (fsgm_tune key 8): rows per CTA of the fused cost kernel, 0 = chosen from the grid size
     unsigned attr_mask = 0;                 // which kernels already had their max-dynamic-smem attribute set on this device
     int clusters_key[4] = {0, 0, 0, 0}, clusters_max = 0;   // resident clusters for the last queried (cluster size, W, D, ndir)

@@ -52,7 +52,9 @@ FSGM_API const char* fsgm_last_error(const fsgm_ctx* ctx);
  *         -2 = auto with every shifted step forced through the label-by-label form (test knob), 1..16 = row-synchronous clusters of that size.
  * key 6 = 1: the pyramidal variant builds its cost volume with the direct kernel only (no separable box filter + fix-up list).
  * key 7 = 1: calc_pyd_cost_sgm_ng runs the cell-by-cell compatibility search at every step (no per-grid tables).
- * key 8 = rows per CTA of the fused epipolar cost kernel (0 = chosen from the grid size). */
+ * key 8 = rows per CTA of the fused epipolar cost kernel (0 = chosen from the grid size).
+ * key 9 = cluster waves per staging chunk of the host-pointer batch gateways (default 3; a chunk is uploaded while the previous
+ *         one computes, and the wave pipeline inside a chunk needs at least two waves to overlap anything). */
 FSGM_API int         fsgm_tune(fsgm_ctx* ctx, int key, int value);
 /* occupancy probe: resident clusters of `cluster_size` CTAs x `threads` threads with `smem_bytes` dynamic shared memory */
 FSGM_API int         fsgm_debug_max_clusters(int cluster_size, size_t smem_bytes, int threads);
